@@ -1,0 +1,198 @@
+/*
+  Reference harness -- TEST INFRASTRUCTURE (oracle), not product code.
+
+  Compiled together with the UNMODIFIED reference sources (taken where they lie under
+  /root/reference; see oracle/Makefile) and the ciglet shim into oracle/_ref/libllsm2_ref*.so.
+  It only drives the reference's public API (llsm.h) with flat "structure of arrays" buffers so
+  that the Python tests and bench.py can feed the very same numbers to the reference build and to
+  the CUDA library. Layout of the flat buffers = include/llsm_b200.h (one utterance per call).
+*/
+#define _POSIX_C_SOURCE 199309L
+#include <time.h>
+#include <ciglet/ciglet.h>
+#include "llsm.h"
+#include "llsmrt.h"
+#include "dsputils.h"
+#include "llsmutils.h"
+
+/* ---- chunk construction from flat arrays (layer 0) ---- */
+static llsm_chunk* chunk_from_soa(int nfrm, float fs, float thop, int maxnhar, int maxnhar_e,
+  int npsd, int nchannel, const float* chanfreq, float lip_radius,
+  const float* f0, const int* nhar, const float* ampl, const float* phse,
+  const float* psd, const float* psdres, const float* edc, const int* enhar,
+  const float* eampl, const float* ephse) {
+  llsm_aoptions* opt = llsm_create_aoptions();
+  opt -> thop = thop;
+  opt -> maxnhar = maxnhar;
+  opt -> maxnhar_e = maxnhar_e;
+  opt -> npsd = npsd;
+  opt -> nchannel = nchannel;
+  free(opt -> chanfreq);
+  opt -> chanfreq = calloc(nchannel > 1 ? nchannel - 1 : 1, sizeof(FP_TYPE));
+  for(int c = 0; c < nchannel - 1; c ++) opt -> chanfreq[c] = chanfreq[c];
+  opt -> lip_radius = lip_radius;
+  llsm_container* conf = llsm_aoptions_toconf(opt, fs / 2.0);
+  ((int*)llsm_container_get(conf, LLSM_CONF_NFRM))[0] = nfrm;
+  llsm_chunk* chunk = llsm_create_chunk(conf, 1);
+  llsm_delete_container(conf);
+  llsm_delete_aoptions(opt);
+
+  for(int i = 0; i < nfrm; i ++) {
+    llsm_container* frame = chunk -> frames[i];
+    ((FP_TYPE*)llsm_container_get(frame, LLSM_FRAME_F0))[0] = f0[i];
+    if(f0[i] > 0 && nhar != NULL) {
+      llsm_hmframe* hm = llsm_create_hmframe(nhar[i]);
+      memcpy(hm -> ampl, ampl + (size_t)i * maxnhar, nhar[i] * sizeof(FP_TYPE));
+      memcpy(hm -> phse, phse + (size_t)i * maxnhar, nhar[i] * sizeof(FP_TYPE));
+      llsm_container_attach(frame, LLSM_FRAME_HM, hm, llsm_delete_hmframe, llsm_copy_hmframe);
+    }
+    llsm_nmframe* nm = llsm_container_get(frame, LLSM_FRAME_NM);
+    if(psd != NULL) memcpy(nm -> psd, psd + (size_t)i * npsd, npsd * sizeof(FP_TYPE));
+    for(int c = 0; c < nchannel; c ++) {
+      if(edc != NULL) nm -> edc[c] = edc[(size_t)i * nchannel + c];
+      if(enhar != NULL) {
+        int ne = enhar[(size_t)i * nchannel + c];
+        llsm_hmframe* e = llsm_create_hmframe(ne);
+        size_t off = ((size_t)i * nchannel + c) * maxnhar_e;
+        memcpy(e -> ampl, eampl + off, ne * sizeof(FP_TYPE));
+        memcpy(e -> phse, ephse + off, ne * sizeof(FP_TYPE));
+        llsm_copy_hmframe_inplace(nm -> eenv[c], e);
+        llsm_delete_hmframe(e);
+      }
+    }
+    if(psdres != NULL) {
+      FP_TYPE* res = llsm_create_fparray(npsd);
+      memcpy(res, psdres + (size_t)i * npsd, npsd * sizeof(FP_TYPE));
+      llsm_container_attach(frame, LLSM_FRAME_PSDRES, res, llsm_delete_fparray,
+        llsm_copy_fparray);
+    }
+  }
+  return chunk;
+}
+
+int ref_output_length(int nfrm, float thop, float fs) {
+  return round((nfrm + 1) * thop * fs); /* same float expression as layer0.c:643 */
+}
+
+/* llsm_synthesize on one utterance; srand(seed) first so that the noise template is reproducible
+   (the template is drawn inside llsm_synthesize, layer0.c:544 -> dsputils.c:353-361).
+   Returns ny, or -1 if the reference returned NULL. */
+int ref_synthesize_soa(int nfrm, float fs, float thop, int maxnhar, int maxnhar_e, int npsd,
+  int nchannel, const float* chanfreq, float lip_radius, int use_iczt,
+  const float* f0, const int* nhar, const float* ampl, const float* phse,
+  const float* psd, const float* psdres, const float* edc, const int* enhar,
+  const float* eampl, const float* ephse, unsigned seed,
+  float* y, float* y_sin, float* y_noise) {
+  llsm_chunk* chunk = chunk_from_soa(nfrm, fs, thop, maxnhar, maxnhar_e, npsd, nchannel,
+    chanfreq, lip_radius, f0, nhar, ampl, phse, psd, psdres, edc, enhar, eampl, ephse);
+  llsm_soptions* sopt = llsm_create_soptions(fs);
+  sopt -> use_iczt = use_iczt;
+  srand(seed);
+  llsm_output* out = llsm_synthesize(sopt, chunk);
+  int ny = -1;
+  if(out != NULL) {
+    ny = out -> ny;
+    if(y != NULL) memcpy(y, out -> y, ny * sizeof(float));
+    if(y_sin != NULL) memcpy(y_sin, out -> y_sin, ny * sizeof(float));
+    if(y_noise != NULL) memcpy(y_noise, out -> y_noise, ny * sizeof(float));
+    llsm_delete_output(out);
+  }
+  llsm_delete_soptions(sopt);
+  llsm_delete_chunk(chunk);
+  return ny;
+}
+
+/* The white-noise draw of one llsm_synthesize call, channel by channel, exactly as
+   llsm_generate_white_noise consumes rand() (dsputils.c:353-361, :385-388): used by the tests to
+   hand the CUDA path the same template. dst: [nchannel][min(20000,ny)+128]. */
+int ref_draw_white_noise(int ny, int nchannel, unsigned seed, float* dst) {
+  int nt = min(20000, ny) + 128;
+  srand(seed);
+  for(int c = 0; c < nchannel; c ++) {
+    FP_TYPE* w = llsm_generate_white_noise(nt);
+    memcpy(dst + (size_t)c * nt, w, nt * sizeof(float));
+    free(w);
+  }
+  return nt;
+}
+
+/* llsm_analyze on one utterance, results unpacked to flat arrays. f0 is in/out (refinement,
+   layer0.c:487-488). hm_method: 0 = peak picking, 1 = CZT. Returns 0 on success. */
+int ref_analyze_soa(const float* x, int nx, float fs, float* f0, int nfrm, float thop,
+  int maxnhar, int maxnhar_e, int npsd, int nchannel, const float* chanfreq,
+  int f0_refine, int hm_method, float rel_winsize,
+  int* nhar, float* ampl, float* phse, float* psd, float* psdres, float* edc, int* enhar,
+  float* eampl, float* ephse, float* x_res) {
+  llsm_aoptions* opt = llsm_create_aoptions();
+  opt -> thop = thop;
+  opt -> maxnhar = maxnhar;
+  opt -> maxnhar_e = maxnhar_e;
+  opt -> npsd = npsd;
+  opt -> nchannel = nchannel;
+  free(opt -> chanfreq);
+  opt -> chanfreq = calloc(nchannel > 1 ? nchannel - 1 : 1, sizeof(FP_TYPE));
+  for(int c = 0; c < nchannel - 1; c ++) opt -> chanfreq[c] = chanfreq[c];
+  opt -> f0_refine = f0_refine;
+  opt -> hm_method = hm_method;
+  opt -> rel_winsize = rel_winsize;
+  FP_TYPE* xap = NULL;
+  FP_TYPE* xcopy = malloc(nx * sizeof(FP_TYPE));
+  memcpy(xcopy, x, nx * sizeof(FP_TYPE));
+  llsm_chunk* chunk = llsm_analyze(opt, xcopy, nx, fs, f0, nfrm, & xap);
+  free(xcopy);
+  llsm_delete_aoptions(opt);
+  if(chunk == NULL) return -1;
+  if(x_res != NULL) memcpy(x_res, xap, nx * sizeof(float));
+  free(xap);
+  for(int i = 0; i < nfrm; i ++) {
+    llsm_container* frame = chunk -> frames[i];
+    llsm_hmframe* hm = llsm_container_get(frame, LLSM_FRAME_HM);
+    llsm_nmframe* nm = llsm_container_get(frame, LLSM_FRAME_NM);
+    FP_TYPE* res = llsm_container_get(frame, LLSM_FRAME_PSDRES);
+    int nh = (f0[i] > 0 && hm != NULL) ? hm -> nhar : 0;
+    nhar[i] = nh;
+    for(int k = 0; k < maxnhar; k ++) {
+      ampl[(size_t)i * maxnhar + k] = k < nh ? hm -> ampl[k] : 0;
+      phse[(size_t)i * maxnhar + k] = k < nh ? hm -> phse[k] : 0;
+    }
+    memcpy(psd + (size_t)i * npsd, nm -> psd, npsd * sizeof(float));
+    if(psdres != NULL) {
+      if(res != NULL) memcpy(psdres + (size_t)i * npsd, res, npsd * sizeof(float));
+      else memset(psdres + (size_t)i * npsd, 0, npsd * sizeof(float));
+    }
+    for(int c = 0; c < nchannel; c ++) {
+      edc[(size_t)i * nchannel + c] = nm -> edc[c];
+      int ne = f0[i] > 0 ? nm -> eenv[c] -> nhar : 0;
+      enhar[(size_t)i * nchannel + c] = ne;
+      size_t off = ((size_t)i * nchannel + c) * maxnhar_e;
+      for(int k = 0; k < maxnhar_e; k ++) {
+        eampl[off + k] = k < ne ? nm -> eenv[c] -> ampl[k] : 0;
+        ephse[off + k] = k < ne ? nm -> eenv[c] -> phse[k] : 0;
+      }
+    }
+  }
+  llsm_delete_chunk(chunk);
+  return 0;
+}
+
+/* timing helper for bench.py --impl reference: nrep x llsm_synthesize on the same chunk */
+double ref_time_synthesize_soa(int nrep, int nfrm, float fs, float thop, int maxnhar,
+  int maxnhar_e, int npsd, int nchannel, const float* chanfreq, float lip_radius, int use_iczt,
+  const float* f0, const int* nhar, const float* ampl, const float* phse,
+  const float* psd, const float* psdres, const float* edc, const int* enhar,
+  const float* eampl, const float* ephse) {
+  struct timespec t0, t1;
+  llsm_chunk* chunk = chunk_from_soa(nfrm, fs, thop, maxnhar, maxnhar_e, npsd, nchannel,
+    chanfreq, lip_radius, f0, nhar, ampl, phse, psd, psdres, edc, enhar, eampl, ephse);
+  llsm_soptions* sopt = llsm_create_soptions(fs);
+  sopt -> use_iczt = use_iczt;
+  clock_gettime(CLOCK_MONOTONIC, & t0);
+  for(int r = 0; r < nrep; r ++) {
+    llsm_output* out = llsm_synthesize(sopt, chunk);
+    llsm_delete_output(out);
+  }
+  clock_gettime(CLOCK_MONOTONIC, & t1);
+  llsm_delete_soptions(sopt);
+  llsm_delete_chunk(chunk);
+  return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+}
