@@ -1,0 +1,163 @@
+/*
+  llsm_b200.h -- C ABI of the B200 hot path (batched, structure-of-arrays).
+
+  This is the FFI boundary of libllsm2_b200.so for the layer-0 analysis / synthesis loops of
+  libllsm2. Plain pointers and sizes only. The reference API is one utterance at a time over
+  pointer-chasing containers (llsm.h:310-313, :336-339); the entry points below take the same
+  quantities as flat arrays for a whole batch of utterances, and the drop-in llsm_synthesize /
+  llsm_analyze of include/llsm.h are thin packers around them (batch = 1).
+
+  Every entry point returns 0 on success and a negative code on failure;
+  llsm_b200_last_error() describes the last failure of the calling thread. There is no CPU
+  fallback: without a CUDA device every compute call fails with LLSM_B200_ENODEVICE.
+
+  Array layout (row-major, B = nutt utterances, F = nfrm frames per utterance):
+    f0      [B][F]                 Hz, 0 = unvoiced                (llsm.h:98  LLSM_FRAME_F0)
+    nhar    [B][F]                 harmonics in use                (llsm.h:134-138 llsm_hmframe.nhar)
+    ampl    [B][F][maxnhar]        linear amplitude                (llsm_hmframe.ampl)
+    phse    [B][F][maxnhar]        radians                         (llsm_hmframe.phse)
+    psd     [B][F][npsd]           dB                              (llsm.h:157-165 llsm_nmframe.psd)
+    psdres  [B][F][npsd]           dB residual, optional (NULL)    (llsm.h:101 LLSM_FRAME_PSDRES)
+    edc     [B][F][nchannel]       envelope mean                   (llsm_nmframe.edc)
+    enhar   [B][F][nchannel]       envelope harmonics in use       (llsm_nmframe.eenv[c]->nhar)
+    eampl   [B][F][nchannel][maxnhar_e]                            (llsm_nmframe.eenv[c]->ampl)
+    ephse   [B][F][nchannel][maxnhar_e]                            (llsm_nmframe.eenv[c]->phse)
+  Waveforms: [B][nsamp] with a common row stride.
+*/
+#ifndef LLSM_B200_H
+#define LLSM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LLSM_B200_MAXCHANNEL 8
+
+#define LLSM_B200_OK         0
+#define LLSM_B200_EINVAL    -1   /* inconsistent sizes / NULL required pointer */
+#define LLSM_B200_ENODEVICE -2   /* no CUDA device, or library built without its kernels */
+#define LLSM_B200_ECUDA     -3   /* a CUDA runtime call or kernel failed */
+#define LLSM_B200_ENOMEM    -4
+#define LLSM_B200_ERANGE    -5   /* size outside what the kernels support */
+
+typedef struct llsm_b200_ctx llsm_b200_ctx; /* device, stream, scratch, cached plans */
+
+/* Model configuration shared by a batch: the LLSM_CONF_* entries the path needs (llsm.h:115-128)
+   plus the output sampling rate of llsm_soptions (llsm.h:290-299). */
+typedef struct {
+  int   nutt;                               /* B */
+  int   nfrm;                               /* F (row stride of the frame arrays) */
+  int   maxnhar;                            /* LLSM_CONF_MAXNHAR / row stride of ampl, phse */
+  int   maxnhar_e;                          /* LLSM_CONF_MAXNHAR_E */
+  int   npsd;                               /* LLSM_CONF_NPSD */
+  int   nchannel;                           /* LLSM_CONF_NCHANNEL (<= LLSM_B200_MAXCHANNEL) */
+  float fs;                                 /* sampling rate, Hz (fnyq = fs / 2) */
+  float thop;                               /* LLSM_CONF_THOP, seconds */
+  float chanfreq[LLSM_B200_MAXCHANNEL];     /* LLSM_CONF_CHANFREQ, nchannel - 1 used */
+  float lip_radius;                         /* LLSM_CONF_LIPRADIUS */
+} llsm_b200_conf;
+
+typedef struct {
+  const int*   nfrm_utt;  /* [B] frames actually present per utterance, NULL = all nfrm */
+  const float* f0;
+  const int*   nhar;
+  const float* ampl;
+  const float* phse;
+  const float* psd;
+  const float* psdres;    /* may be NULL */
+  const float* edc;
+  const int*   enhar;
+  const float* eampl;
+  const float* ephse;
+} llsm_b200_frames;
+
+/* Writable twin of llsm_b200_frames, filled by analysis. */
+typedef struct {
+  float* f0;              /* in/out: refined when f0_refine is set (layer0.c:487-488) */
+  int*   nhar;
+  float* ampl;
+  float* phse;
+  float* psd;
+  float* psdres;
+  float* edc;
+  int*   enhar;
+  float* eampl;
+  float* ephse;
+} llsm_b200_frames_out;
+
+/* Synthesis options: llsm_soptions (llsm.h:290-299) + the noise source.
+   white == NULL : the white-noise templates are drawn on the device (Philox + Box-Muller) from
+                   `seed` -- statistically equivalent to, but not bit-equal with, the reference.
+   white != NULL : [B][nchannel][ntemplate] host-drawn N(0,1) templates, ntemplate =
+                   llsm_b200_template_length(); the drop-in llsm_synthesize fills this with the
+                   reference's randn() sequence so outputs match the reference build. */
+typedef struct {
+  int      use_iczt;
+  float    iczt_param_a;
+  float    iczt_param_b;
+  const float* white;
+  uint64_t seed;
+} llsm_b200_soptions;
+
+typedef struct {
+  float* y;               /* [B][stride] y_sin + y_noise            (llsm.h:246-252 llsm_output.y) */
+  float* y_sin;           /* [B][stride]                                            (.y_sin)        */
+  float* y_noise;         /* [B][stride]                                            (.y_noise)      */
+  int    stride;          /* >= llsm_b200_output_length() */
+} llsm_b200_output;
+
+/* Analysis options: llsm_aoptions (llsm.h:260-272); sizes come from llsm_b200_conf. */
+typedef struct {
+  int   f0_refine;
+  int   hm_method;        /* 0 = LLSM_AOPTION_HMPP, 1 = LLSM_AOPTION_HMCZT */
+  float rel_winsize;
+} llsm_b200_aoptions;
+
+/* ---- context ---- */
+llsm_b200_ctx* llsm_b200_create(int device);            /* NULL on failure */
+void           llsm_b200_destroy(llsm_b200_ctx* ctx);
+const char*    llsm_b200_last_error(void);
+int            llsm_b200_set_stream(llsm_b200_ctx* ctx, void* cuda_stream); /* cudaStream_t */
+int            llsm_b200_synchronize(llsm_b200_ctx* ctx);
+/* number of kernels this library has launched on ctx since creation (bench.py gpu_launches) */
+long long      llsm_b200_launch_count(const llsm_b200_ctx* ctx);
+
+/* ---- size helpers (host only, exact replicas of the reference's float expressions) ---- */
+int llsm_b200_output_length(int nfrm, float thop, float fs);    /* layer0.c:643 */
+int llsm_b200_template_length(int ny);                          /* dsputils.c:386-388 */
+
+/* ---- layer-0 synthesis: replaces the frame loops of llsm_synthesize (layer0.c:636-664:
+        llsm_synthesize_harmonics_l0 :117-146, llsm_synthesize_noise_excitation :535-555,
+        llsm_synthesize_noise_envelope :289-316, llsm_filter_noise :557-634) ---- */
+/* all pointers are DEVICE pointers on ctx's device */
+int llsm_b200_synthesize_l0(llsm_b200_ctx* ctx, const llsm_b200_conf* conf,
+  const llsm_b200_frames* frames, const llsm_b200_soptions* opt, const llsm_b200_output* out);
+/* all pointers are HOST pointers; copies in, runs, copies out, synchronises */
+int llsm_b200_synthesize_l0_host(llsm_b200_ctx* ctx, const llsm_b200_conf* conf,
+  const llsm_b200_frames* frames, const llsm_b200_soptions* opt, const llsm_b200_output* out);
+
+/* Only the harmonic component (y_sin): the harmonic-bank kernel alone, device pointers.
+   Used for the residual resynthesis of analysis (layer0.c:498, options == NULL there) and by the
+   benchmark's roofline leg. nsamp = row length of y_sin (layer0.c:118 `ny`). */
+int llsm_b200_synthesize_harmonics(llsm_b200_ctx* ctx, const llsm_b200_conf* conf,
+  const llsm_b200_frames* frames, const llsm_b200_soptions* opt_or_null,
+  float* y_sin, int nsamp, int stride);
+
+/* ---- layer-0 analysis: replaces the frame loops of llsm_analyze (layer0.c:478-511:
+        llsm_refine_f0 dsputils.c:72-94, llsm_harmonic_analysis :175-228, residual layer0.c:498-501,
+        llsm_analyze_noise_psd :318-415, llsm_analyze_noise_envelope :417-469) ----
+   x: [B][xstride] waveforms of nx samples; x_res (optional, may be NULL) receives x - x_sin. */
+int llsm_b200_analyze_l0(llsm_b200_ctx* ctx, const llsm_b200_conf* conf,
+  const llsm_b200_aoptions* opt, const float* x, int nx, int xstride,
+  const llsm_b200_frames_out* frames, float* x_res);
+int llsm_b200_analyze_l0_host(llsm_b200_ctx* ctx, const llsm_b200_conf* conf,
+  const llsm_b200_aoptions* opt, const float* x, int nx, int xstride,
+  const llsm_b200_frames_out* frames, float* x_res);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,7 @@
+"""libllsm2_b200: B200-native (sm_100a CUDA) implementation of libllsm2's layer-0 analysis /
+synthesis hot path behind the reference's C API. See DESIGN.md and include/llsm_b200.h.
+
+Python side = thin host mirror over the C ABI (ctypes); torch is used only for device memory,
+streams and torch.distributed."""
+from .api import Context, synthesize_l0, synthesize_l0_host, synthesize_harmonics, output_length  # noqa: F401
+from ._lib import LlsmB200Error  # noqa: F401

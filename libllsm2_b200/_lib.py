@@ -1,0 +1,51 @@
+"""Loader of the CUDA shared library. There is deliberately no fallback: if libllsm2_b200.so is
+missing or no CUDA device is present the package raises."""
+import ctypes as C
+import os
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libllsm2_b200.so")
+_lib = None
+
+
+class LlsmB200Error(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_SO):
+        raise LlsmB200Error(
+            "libllsm2_b200.so is not built (run libllsm2_b200/build.sh or __graft_entry__.build()); "
+            "this package has no CPU path")
+    L = C.CDLL(_SO)
+    L.llsm_b200_create.restype = C.c_void_p
+    L.llsm_b200_create.argtypes = [C.c_int]
+    L.llsm_b200_destroy.argtypes = [C.c_void_p]
+    L.llsm_b200_last_error.restype = C.c_char_p
+    L.llsm_b200_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    L.llsm_b200_synchronize.argtypes = [C.c_void_p]
+    L.llsm_b200_launch_count.restype = C.c_longlong
+    L.llsm_b200_launch_count.argtypes = [C.c_void_p]
+    L.llsm_b200_output_length.argtypes = [C.c_int, C.c_float, C.c_float]
+    L.llsm_b200_template_length.argtypes = [C.c_int]
+    P = C.c_void_p
+    L.llsm_b200_synthesize_l0.argtypes = [P, C.POINTER(abi.Conf), C.POINTER(abi.Frames),
+                                          C.POINTER(abi.SOptions), C.POINTER(abi.Output)]
+    L.llsm_b200_synthesize_l0_host.argtypes = L.llsm_b200_synthesize_l0.argtypes
+    L.llsm_b200_synthesize_harmonics.argtypes = [P, C.POINTER(abi.Conf), C.POINTER(abi.Frames),
+                                                 C.POINTER(abi.SOptions), P, C.c_int, C.c_int]
+    L.llsm_b200_analyze_l0.argtypes = [P, C.POINTER(abi.Conf), C.POINTER(abi.AOptions), P, C.c_int,
+                                       C.c_int, C.POINTER(abi.FramesOut), P]
+    L.llsm_b200_analyze_l0_host.argtypes = L.llsm_b200_analyze_l0.argtypes
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise LlsmB200Error("libllsm2_b200 error %d: %s" % (rc, lib().llsm_b200_last_error().decode()))

@@ -1,0 +1,127 @@
+"""Host-side mirror of the reference's synthesis / analysis interface over the C ABI.
+
+Names and argument meaning follow llsm.h: a *conf* (LLSM_CONF_* entries), per-frame members
+(F0, HM = ampl/phse/nhar, NM = psd/edc/eenv, PSDRES) -- here as flat [B][F][...] arrays -- and an
+output triple (y, y_sin, y_noise) as in llsm_output (llsm.h:246-252).
+"""
+import ctypes as C
+import numpy as np
+
+from . import abi
+from ._lib import lib, check, LlsmB200Error
+
+FRAME_KEYS = ("nfrm_utt", "f0", "nhar", "ampl", "phse", "psd", "psdres", "edc", "enhar", "eampl", "ephse")
+
+
+def output_length(nfrm, thop, fs):
+    """ny = round((nfrm + 1) * thop * fs) in the reference's float arithmetic (layer0.c:643)."""
+    return lib().llsm_b200_output_length(int(nfrm), C.c_float(thop), C.c_float(fs))
+
+
+class Context:
+    """Device context (stream, cached plans, scratch). One per process / GPU."""
+
+    def __init__(self, device=0, use_torch_stream=True):
+        L = lib()
+        self._h = L.llsm_b200_create(int(device))
+        if not self._h:
+            raise LlsmB200Error("llsm_b200_create failed: " + L.llsm_b200_last_error().decode())
+        self.device = int(device)
+        if use_torch_stream:
+            import torch
+            with torch.cuda.device(self.device):
+                self.set_stream(torch.cuda.current_stream().cuda_stream)
+
+    def set_stream(self, cuda_stream_ptr):
+        check(lib().llsm_b200_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def synchronize(self):
+        check(lib().llsm_b200_synchronize(self._h))
+
+    @property
+    def launches(self):
+        return int(lib().llsm_b200_launch_count(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().llsm_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if hasattr(a, "data_ptr"):          # torch tensor
+        assert a.is_contiguous()
+        return a.data_ptr()
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data
+
+
+def _frames(frames):
+    f = abi.Frames()
+    for k in FRAME_KEYS:
+        setattr(f, k, _ptr(frames.get(k)))
+    return f
+
+
+def _soptions(options, white, seed):
+    o = abi.default_soptions(_ptr(white), int(seed))
+    if options is not None:
+        o.use_iczt = int(options.get("use_iczt", 1))
+        o.iczt_param_a = float(options.get("iczt_param_a", 0.275))
+        o.iczt_param_b = float(options.get("iczt_param_b", 2.26))
+    return o
+
+
+def synthesize_l0(ctx, conf, frames, white=None, seed=0, options=None, out=None):
+    """llsm_synthesize (layer0.c:636-664) for a batch held in CUDA tensors.
+    frames: dict of torch CUDA tensors keyed as FRAME_KEYS. Returns dict(y, y_sin, y_noise)."""
+    import torch
+    ny = output_length(conf.nfrm, conf.thop, conf.fs)
+    dev = frames["f0"].device
+    if out is None:
+        out = {k: torch.empty((conf.nutt, ny), dtype=torch.float32, device=dev)
+               for k in ("y", "y_sin", "y_noise")}
+    o = abi.Output()
+    o.y, o.y_sin, o.y_noise, o.stride = _ptr(out["y"]), _ptr(out["y_sin"]), _ptr(out["y_noise"]), out["y"].shape[1]
+    f = _frames(frames)
+    so = _soptions(options, white, seed)
+    check(lib().llsm_b200_synthesize_l0(ctx._h, C.byref(conf), C.byref(f), C.byref(so), C.byref(o)))
+    return out
+
+
+def synthesize_l0_host(ctx, conf, frames, white=None, seed=0, options=None, out=None):
+    """Same through host (numpy or pinned torch CPU) buffers: H2D, kernels, D2H, synchronise."""
+    ny = output_length(conf.nfrm, conf.thop, conf.fs)
+    if out is None:
+        out = {k: np.empty((conf.nutt, ny), np.float32) for k in ("y", "y_sin", "y_noise")}
+    o = abi.Output()
+    o.y, o.y_sin, o.y_noise = _ptr(out.get("y")), _ptr(out.get("y_sin")), _ptr(out.get("y_noise"))
+    first = next(v for v in out.values() if v is not None)
+    o.stride = first.shape[1]
+    f = _frames(frames)
+    so = _soptions(options, white, seed)
+    check(lib().llsm_b200_synthesize_l0_host(ctx._h, C.byref(conf), C.byref(f), C.byref(so), C.byref(o)))
+    return out
+
+
+def synthesize_harmonics(ctx, conf, frames, nsamp, options=None, with_options=True, out=None):
+    """Harmonic component only (llsm_synthesize_harmonics_l0, layer0.c:117-146), CUDA tensors.
+    with_options=False reproduces the options == NULL call of the analysis residual."""
+    import torch
+    dev = frames["f0"].device
+    if out is None:
+        out = torch.empty((conf.nutt, nsamp), dtype=torch.float32, device=dev)
+    f = _frames(frames)
+    so = _soptions(options, None, 0)
+    check(lib().llsm_b200_synthesize_harmonics(ctx._h, C.byref(conf), C.byref(f),
+                                               C.byref(so) if with_options else None,
+                                               _ptr(out), int(nsamp), out.shape[1]))
+    return out

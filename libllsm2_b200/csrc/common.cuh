@@ -1,0 +1,125 @@
+// Shared device helpers for the libllsm2 B200 kernels (sm_100a).
+//
+// The same sources compile in two modes:
+//   * nvcc, -gencode arch=compute_100a,code=sm_100a : the product;
+//   * g++ -DLLSM_EMU (tests/emu/) : CPU thread emulation used only by the CPU-side unit tests.
+#pragma once
+
+#ifdef LLSM_EMU
+#include "cuda_emu.h"
+typedef void* cudaStream_t;
+#define LLSM_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  emu::launch((grid), (block), (smem), [&]() { kernel(__VA_ARGS__); })
+#else
+#include <cuda_runtime.h>
+#include <stdint.h>
+#define LLSM_DYN_SMEM(name) extern __shared__ __align__(16) char name[]
+#define LLSM_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+
+#define LLSM_PI 3.14159265358979323846
+#define LLSM_WARP 32
+
+// ---- packed FP32x2 arithmetic (Blackwell FFMA2 / FMUL2: two FP32 lanes per issue slot) ----
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+#else
+  return make_float2(__fmaf_rn(a.x, b.x, c.x), __fmaf_rn(a.y, b.y, c.y));
+#endif
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+  float2 d;
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "mul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+#else
+  return make_float2(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y));
+#endif
+}
+
+// e^{i 2 pi u}: u (turns) is reduced in double, the sine/cosine are evaluated in float.
+// Phases on this path reach ~1e3 rad (harmonic number x sample offset), where a float argument
+// would lose 1e-4 rad; reducing the product in double first keeps the seed error at ~1e-7 rad.
+__device__ __forceinline__ float2 unit_phasor_turns(double u) {
+  u -= rint(u);                 // [-0.5, 0.5]
+  float s, c;
+  sincospif(2.0f * (float)u, &s, &c);
+  return make_float2(c, s);
+}
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+// ---- block-wide Stockham FFT in shared memory -----------------------------------------------
+// n = 2^lg complex points in `a` (second buffer `b`, same size); all threads of the block take
+// part; radix-4 passes plus one radix-2 pass when lg is odd. `tw` is the full-circle table
+// tw[m] = exp(-2 pi i m / ntw) (ntw >= n, power of two, built on the host in double).
+// Returns the buffer holding the result. Forward: X[k] = sum x[m] e^{-2 pi i k m / n};
+// inverse (INV): conjugate twiddles, unscaled. Every pass ends with __syncthreads().
+template <bool INV>
+__device__ __forceinline__ float2 fft_tw(const float2* __restrict__ tw, int idx) {
+  float2 w = tw[idx];
+  if(INV) w.y = -w.y;
+  return w;
+}
+
+template <bool INV>
+__device__ float2* block_fft(float2* a, float2* b, int lg, const float2* __restrict__ tw, int ntw) {
+  const int n = 1 << lg;
+  const int tid = threadIdx.x, nth = blockDim.x;
+  int p = 1; // butterflies already combined
+  int rem = lg;
+  while(rem >= 2) {
+    const int t = n >> 2;
+    const int tws = ntw / (4 * p); // index step: angle -2 pi k / (4p)
+    for(int i = tid; i < t; i += nth) {
+      int k = i & (p - 1);
+      float2 u0 = a[i];
+      float2 u1 = cmul(a[i + t], fft_tw<INV>(tw, k * tws));
+      float2 u2 = cmul(a[i + 2 * t], fft_tw<INV>(tw, 2 * k * tws));
+      float2 u3 = cmul(a[i + 3 * t], fft_tw<INV>(tw, 3 * k * tws));
+      float2 v0 = make_float2(u0.x + u2.x, u0.y + u2.y);
+      float2 v1 = make_float2(u0.x - u2.x, u0.y - u2.y);
+      float2 v2 = make_float2(u1.x + u3.x, u1.y + u3.y);
+      float2 v3 = make_float2(u1.x - u3.x, u1.y - u3.y);
+      // forward: multiply v3 by -i; inverse: by +i
+      float2 v3r = INV ? make_float2(-v3.y, v3.x) : make_float2(v3.y, -v3.x);
+      int j = ((i - k) << 2) + k;
+      b[j]         = make_float2(v0.x + v2.x, v0.y + v2.y);
+      b[j + p]     = make_float2(v1.x + v3r.x, v1.y + v3r.y);
+      b[j + 2 * p] = make_float2(v0.x - v2.x, v0.y - v2.y);
+      b[j + 3 * p] = make_float2(v1.x - v3r.x, v1.y - v3r.y);
+    }
+    __syncthreads();
+    float2* sw = a; a = b; b = sw;
+    p <<= 2; rem -= 2;
+  }
+  if(rem == 1) {
+    const int t = n >> 1;
+    const int tws = ntw / (2 * p);
+    for(int i = tid; i < t; i += nth) {
+      int k = i & (p - 1);
+      float2 u0 = a[i];
+      float2 u1 = cmul(a[i + t], fft_tw<INV>(tw, k * tws));
+      int j = ((i - k) << 1) + k;
+      b[j]     = make_float2(u0.x + u1.x, u0.y + u1.y);
+      b[j + p] = make_float2(u0.x - u1.x, u0.y - u1.y);
+    }
+    __syncthreads();
+    float2* sw = a; a = b; b = sw;
+  }
+  return a;
+}

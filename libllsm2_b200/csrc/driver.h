@@ -1,0 +1,176 @@
+// Launch orchestration shared by the CUDA library (api.cu) and the CPU thread emulation used by the
+// unit tests (tests/emu/emu_api.cpp). "Device" memory is cudaMalloc'd in the product and plain
+// malloc'd under LLSM_EMU.
+#pragma once
+#include "../../include/llsm_b200.h"
+#include "plan.h"
+#include "kernels_synth.cuh"
+#include <vector>
+#include <string>
+#include <map>
+#include <cstring>
+
+#ifdef LLSM_EMU
+static inline int dev_alloc(void** p, size_t n) { *p = calloc(n ? n : 1, 1); return *p ? 0 : -1; }
+static inline void dev_free(void* p) { free(p); }
+static inline int dev_upload(void* d, const void* h, size_t n, cudaStream_t) { memcpy(d, h, n); return 0; }
+static inline int dev_download(void* h, const void* d, size_t n, cudaStream_t) { memcpy(h, d, n); return 0; }
+static inline int dev_sync(cudaStream_t) { return 0; }
+static inline const char* dev_last_error() { return nullptr; }
+#else
+static inline int dev_alloc(void** p, size_t n) { return cudaMalloc(p, n ? n : 1) == cudaSuccess ? 0 : -1; }
+static inline void dev_free(void* p) { if(p) cudaFree(p); }
+static inline int dev_upload(void* d, const void* h, size_t n, cudaStream_t s) {
+  return cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s) == cudaSuccess ? 0 : -1;
+}
+static inline int dev_download(void* h, const void* d, size_t n, cudaStream_t s) {
+  return cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s) == cudaSuccess ? 0 : -1;
+}
+static inline int dev_sync(cudaStream_t s) { return cudaStreamSynchronize(s) == cudaSuccess ? 0 : -1; }
+static inline const char* dev_last_error() {
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? nullptr : cudaGetErrorString(e);
+}
+#endif
+
+// growable device scratch buffer
+struct DevBuf {
+  void* p = nullptr; size_t cap = 0;
+  int reserve(size_t n) {
+    if(n <= cap) return 0;
+    dev_free(p); p = nullptr; cap = 0;
+    if(dev_alloc(&p, n) != 0) return -1;
+    cap = n; return 0;
+  }
+  void release() { dev_free(p); p = nullptr; cap = 0; }
+  template <class T> T* as() { return (T*)p; }
+};
+
+// device-resident copy of a SynthPlan
+struct SynthPlanDev {
+  SynthPlan h;
+  int *hm_base = nullptr, *env_off = nullptr, *psd_lo = nullptr;
+  float *hm_frac = nullptr, *win_hm = nullptr, *env_r = nullptr, *win_env = nullptr,
+        *win_ns = nullptr, *psd_r = nullptr;
+  float2* tw_ns = nullptr;
+  std::vector<void*> owned;
+  template <class T> int up(T** dst, const std::vector<T>& src, cudaStream_t st) {
+    void* d = nullptr;
+    if(dev_alloc(&d, src.size() * sizeof(T)) != 0) return -1;
+    owned.push_back(d);
+    if(! src.empty() && dev_upload(d, src.data(), src.size() * sizeof(T), st) != 0) return -1;
+    *dst = (T*)d;
+    return 0;
+  }
+  int build(int nfrm, float fs, float thop, int npsd, int nchannel, const float* chanfreq,
+    cudaStream_t st) {
+    build_synth_plan(h, nfrm, fs, thop, npsd, nchannel, chanfreq);
+    std::vector<float> tw;
+    build_twiddle(tw, h.nfft_ns);
+    int rc = 0;
+    rc |= up(&hm_base, h.hm_base, st); rc |= up(&hm_frac, h.hm_frac, st);
+    rc |= up(&win_hm, h.win_hm, st);   rc |= up(&env_r, h.env_r, st);
+    rc |= up(&env_off, h.env_off, st); rc |= up(&win_env, h.win_env, st);
+    rc |= up(&win_ns, h.win_ns, st);   rc |= up(&psd_lo, h.psd_lo, st);
+    rc |= up(&psd_r, h.psd_r, st);
+    float* twd = nullptr; rc |= up(&twd, tw, st); tw_ns = (float2*)twd;
+    if(dev_sync(st) != 0) rc = -1;   // the host vectors must outlive the async copies
+    return rc;
+  }
+  void release() { for(void* p : owned) dev_free(p); owned.clear(); }
+};
+
+struct SynthScratch {
+  DevBuf colored, y_exc, ny_utt;
+};
+
+struct LaunchCounter { long long n = 0; };
+
+// Harmonic component only. frames/y_sin are device pointers. has_options = 0 reproduces the
+// options == NULL call of the analysis residual (layer0.c:498).
+static inline int run_harmonics(const SynthPlanDev& pd, const llsm_b200_conf& conf,
+  const llsm_b200_frames& fr, const llsm_b200_soptions* opt, const int* ny_utt_dev,
+  float* y_sin, int ny_valid, int nsamp, int stride, cudaStream_t st, LaunchCounter* lc) {
+  BankParams P;
+  memset(&P, 0, sizeof(P));
+  P.nfrm = conf.nfrm; P.maxnhar = conf.maxnhar;
+  P.nfrm_utt = fr.nfrm_utt; P.ny_utt = ny_utt_dev;
+  P.f0 = fr.f0; P.nhar = fr.nhar; P.ampl = fr.ampl; P.phse = fr.phse;
+  P.hm_base = pd.hm_base; P.hm_frac = pd.hm_frac; P.win = pd.win_hm;
+  P.n_hm = pd.h.n_hm; P.ny = ny_valid; P.nsamp = nsamp; P.stride = stride;
+  P.fs = conf.fs;
+  P.has_options = opt != nullptr;
+  if(opt) { P.use_iczt = opt->use_iczt; P.iczt_a = opt->iczt_param_a; P.iczt_b = opt->iczt_param_b; }
+  P.npass = 2;
+  P.y_sin = y_sin;
+  if(launch_hm_bank(P, conf.nutt, conf.nfrm, st) != 0) return LLSM_B200_ERANGE;
+  if(lc) lc->n += 1;
+  return 0;
+}
+
+// Full layer-0 synthesis on device pointers (llsm_synthesize, layer0.c:636-664).
+static inline int run_synth_l0(const SynthPlanDev& pd, SynthScratch& sc, const llsm_b200_conf& conf,
+  const llsm_b200_frames& fr, const llsm_b200_soptions& opt, const llsm_b200_output& out,
+  const int* ny_utt_dev, cudaStream_t st, LaunchCounter* lc) {
+  const SynthPlan& h = pd.h;
+  const int B = conf.nutt, nch = conf.nchannel;
+  if(nch < 1 || nch > LLSM_B200_MAXCHANNEL) return LLSM_B200_EINVAL;
+  if(out.stride < h.ny) return LLSM_B200_EINVAL;
+  if(sc.colored.reserve((size_t)B * nch * h.nt * 4) != 0) return LLSM_B200_ENOMEM;
+  if(sc.y_exc.reserve((size_t)B * out.stride * 4) != 0) return LLSM_B200_ENOMEM;
+
+  // 1. harmonic component
+  int rc = run_harmonics(pd, conf, fr, &opt, ny_utt_dev, out.y_sin, h.ny, out.stride, out.stride,
+    st, lc);
+  if(rc != 0) return rc;
+
+  // 2. band-limited noise templates
+  TemplateParams T;
+  memset(&T, 0, sizeof(T));
+  T.nutt = B; T.nchannel = nch; T.nt = h.nt;
+  T.white = opt.white; T.seed = opt.seed;
+  T.colored = sc.colored.as<float>();
+  unsigned mask = 0;
+  for(int c = 0; c < nch; c ++) {
+    T.chan[c].nstage = h.chan[c].nstage;
+    memcpy(T.chan[c].b, h.chan[c].b, sizeof(T.chan[c].b));
+    memcpy(T.chan[c].a, h.chan[c].a, sizeof(T.chan[c].a));
+    if(h.chan[c].nstage > 0) mask |= 1u << c;
+  }
+  launch_noise_template(T, st);
+  if(lc) lc->n += 1;
+
+  // 3. excitation
+  ExcParams E;
+  memset(&E, 0, sizeof(E));
+  E.nfrm = conf.nfrm; E.nchannel = nch; E.maxnhar_e = conf.maxnhar_e;
+  E.nfrm_utt = fr.nfrm_utt; E.ny_utt = ny_utt_dev;
+  E.f0 = fr.f0; E.edc = fr.edc; E.enhar = fr.enhar; E.eampl = fr.eampl; E.ephse = fr.ephse;
+  E.env_r = pd.env_r; E.env_off = pd.env_off; E.win_env = pd.win_env; E.n_env = h.n_env;
+  E.ny = h.ny; E.nsamp = out.stride; E.stride = out.stride; E.fs = conf.fs;
+  E.has_options = 1; E.use_iczt = opt.use_iczt; E.iczt_a = opt.iczt_param_a; E.iczt_b = opt.iczt_param_b;
+  E.colored = sc.colored.as<float>(); E.nt = h.nt; E.ntemplate = h.ntemplate;
+  E.chan_mask = mask;
+  E.y_exc = sc.y_exc.as<float>();
+  if(launch_noise_excitation(E, B, st) != 0) return LLSM_B200_ERANGE;
+  if(lc) lc->n += 1;
+
+  // 4. shaping + mix
+  ShapeParams S;
+  memset(&S, 0, sizeof(S));
+  S.nfrm = conf.nfrm; S.npsd = conf.npsd;
+  S.nfrm_utt = fr.nfrm_utt; S.ny_utt = ny_utt_dev;
+  S.psd = fr.psd; S.psdres = fr.psdres;
+  S.center = pd.hm_base; S.win = pd.win_ns;
+  S.n_ns = h.n_ns; S.nfft = h.nfft_ns; S.lg_nfft = h.lg_nfft_ns; S.nspec = h.nspec_ns;
+  S.wsqr = h.wsqr; S.fs = conf.fs;
+  S.psd_lo = pd.psd_lo; S.psd_r = pd.psd_r; S.tw = pd.tw_ns;
+  S.y_exc = sc.y_exc.as<float>(); S.stride_exc = out.stride;
+  S.y_sin = out.y_sin; S.y_noise = out.y_noise; S.y = out.y;
+  S.ny = h.ny; S.nsamp = out.stride; S.stride = out.stride;
+  S.seg = 8192;
+  if(h.nfft_ns > 8192) return LLSM_B200_ERANGE;
+  if(launch_noise_shape(S, B, st) != 0) return LLSM_B200_ERANGE;
+  if(lc) lc->n += 1;
+  return 0;
+}

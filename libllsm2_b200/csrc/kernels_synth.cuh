@@ -1,0 +1,635 @@
+// Layer-0 synthesis kernels for B200 (sm_100a).
+//
+//   hm_bank_ola_kernel   llsm_synthesize_harmonics_l0 (layer0.c:117-146) + the per-frame harmonic
+//                        generator behind it (llsmutils.c:45-58, dsputils.c:328-351), Hann window
+//                        and overlap-add fused; every output sample is written exactly once.
+//   noise_template_kernel  llsm_generate_bandlimited_noise's chebyfilt (dsputils.c:385-394,51-70)
+//   noise_excitation_kernel llsm_synthesize_noise_envelope (layer0.c:289-316) for all channels +
+//                        the modulation/mix loop of llsm_synthesize_noise_excitation (:547-550)
+//                        + stretch_stationary_noise (dsputils.c:363-383) as an index map
+//   noise_shape_kernel   llsm_filter_noise (layer0.c:557-634) + the final y = y_sin + y_noise
+//                        (layer0.c:657-659)
+#pragma once
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------
+// Harmonic bank + Hann + OLA
+// ------------------------------------------------------------------------------------------
+struct BankParams {
+  int nfrm;                 // frame-array row length
+  int maxnhar;              // ampl/phse row length
+  const int* nfrm_utt;      // [B] or NULL
+  const int* ny_utt;        // [B] or NULL: per-utterance valid output length
+  const float* f0;          // [B][nfrm]
+  const int* nhar;          // [B][nfrm]
+  const float* ampl;        // [B][nfrm][maxnhar]
+  const float* phse;
+  const int* hm_base;       // [nfrm]  round(i * thop * fs)
+  const float* hm_frac;     // [nfrm]  rawidx - baseidx
+  const float* win;         // [n_hm]
+  int n_hm;                 // window length (even)
+  int ny;                   // valid output length when ny_utt == NULL
+  int nsamp;                // samples to write per row (>= ny; the tail is zero-filled)
+  int stride;               // output row stride
+  float fs;
+  int has_options;          // 0: options == NULL (always sinusoid bank, llsmutils.c:48-49)
+  int use_iczt; float iczt_a, iczt_b;
+  int npass;                // frame slots per CTA = warps * npass
+  float* y_sin;             // [B][stride]
+};
+
+#define BANK_KC 64          // harmonics staged per chunk
+
+template <int NP>
+__global__ void __launch_bounds__(512) hm_bank_ola_kernel(BankParams P) {
+  LLSM_DYN_SMEM(smem);
+  const int NW = blockDim.x >> 5;
+  const int nslot = NW * P.npass;
+  const int F = nslot - 2;                 // tiles owned by this CTA
+  const int N = P.n_hm, H = N >> 1;
+  const int npad = (N + 3) & ~3;
+  float* fb = (float*)smem;                                   // [nslot][npad]
+  float4* coef_all = (float4*)(fb + (size_t)nslot * npad);    // [NW][BANK_KC]
+  int* sb = (int*)(coef_all + NW * BANK_KC);                  // [nslot] frame position
+  int* sv = sb + nslot;                                       // [nslot] slot holds a frame
+
+  const int b = blockIdx.y, seg = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nf = P.nfrm_utt ? P.nfrm_utt[b] : P.nfrm;
+  const int ny_b = P.ny_utt ? P.ny_utt[b] : P.ny;
+  const int t0 = seg * F;
+  // owned output range [start, end)
+  const int start = t0 == 0 ? 0 : (t0 < nf ? P.hm_base[t0] : P.nsamp);
+  const int end = (t0 + F < nf) ? P.hm_base[t0 + F] : P.nsamp;
+  if(start >= end) return;                 // uniform per CTA
+
+  float4* coef = coef_all + warp * BANK_KC;
+  const size_t row = (size_t)b * P.nfrm;
+
+  for(int q = 0; q < P.npass; q ++) {
+    const int s = q * NW + warp;
+    const int f = t0 - 1 + s;
+    const bool inrange = f >= 0 && f < nf;
+    float f0 = 0; int nh = 0;
+    if(inrange) { f0 = P.f0[row + f]; nh = P.nhar[row + f]; }
+    if(nh > 2048) nh = 2048;               // layer0.c:119,130
+    const bool voiced = inrange && f0 > 0 && nh > 0;  // layer0.c:125 (f0 == 0 skips the frame)
+    if(lane == 0) {
+      sb[s] = inrange ? P.hm_base[f] : (f < 0 ? -(1 << 28) : (1 << 28));
+      sv[s] = voiced ? 1 : 0;
+    }
+    if(! voiced) continue;                 // warp-uniform
+
+    // ---- per-frame scalars, in the reference's precision (layer0.c:127-134, llsmutils.c:45-58,
+    //      dsputils.c:338-348)
+    const float f0n = f0 / P.fs;                                   // f0[i] / fs
+    const float omega0 = (float)(2.0 * LLSM_PI * (double)f0n);     // FP_TYPE omega0 = 2 pi f0
+    bool iczt = false;
+    if(P.has_options && P.use_iczt)
+      iczt = log((double)N) * (double)P.iczt_a < log((double)nh) - (double)P.iczt_b;
+    if(iczt && nh > N - 1) nh = N - 1;     // the ICZT branch transforms bins 0..nx-1 only
+    const double nu = iczt ? (double)omega0 / (2.0 * LLSM_PI) : (double)f0n;   // turns / sample
+    const float frac = P.hm_frac[f];
+    const float corr = (float)((double)(frac * 2.0f) * LLSM_PI / (double)P.fs * (double)f0);
+
+    // ---- rotation seeds z = e^{i 2 pi nu n} for this lane's sample offsets n
+    float2 zr[NP], zi[NP], nzi[NP], wr[NP], wi[NP], C[NP], S[NP];
+#pragma unroll
+    for(int m = 0; m < NP; m ++) {
+      int nA = lane + 64 * m, nB = nA + 32;
+      float2 a = unit_phasor_turns(nu * (double)nA);
+      float2 bq = unit_phasor_turns(nu * (double)nB);
+      zr[m] = make_float2(a.x, bq.x);  zi[m] = make_float2(a.y, bq.y);
+      nzi[m] = make_float2(-a.y, -bq.y);
+      wr[m] = make_float2(1.f, 1.f);   wi[m] = make_float2(0.f, 0.f);
+      C[m] = make_float2(0.f, 0.f);    S[m] = make_float2(0.f, 0.f);
+    }
+
+    const float* ampl = P.ampl + (row + f) * (size_t)P.maxnhar;
+    const float* phse = P.phse + (row + f) * (size_t)P.maxnhar;
+    for(int kc = 0; kc < nh; kc += BANK_KC) {
+      __syncwarp();
+      // stage a_k cos(phi'_k), a_k sin(phi'_k) with phi'_k = phse[k] - corr (k+1)  (layer0.c:132)
+      for(int kk = lane; kk < BANK_KC; kk += 32) {
+        int k = kc + kk;
+        float ca = 0.f, sa = 0.f;
+        if(k < nh) {
+          float a = ampl[k];
+          float ph = (float)((double)phse[k] - (double)corr * ((double)k + 1.0));
+          float s, c; sincosf(ph, &s, &c);
+          ca = a * c; sa = a * s;
+        }
+        coef[kk] = make_float4(ca, ca, sa, sa);
+      }
+      __syncwarp();
+      const int kn = min(BANK_KC, nh - kc);
+      for(int kk = 0; kk < kn; kk ++) {
+        const float4 cf = coef[kk];
+        const float2 aa = make_float2(cf.x, cf.y), bb = make_float2(cf.z, cf.w);
+#pragma unroll
+        for(int m = 0; m < NP; m ++) {
+          float2 t1 = fmul2(wr[m], zr[m]);
+          float2 t2 = fmul2(wi[m], zr[m]);
+          float2 nwr = ffma2(wi[m], nzi[m], t1);   // wr zr - wi zi
+          float2 nwi = ffma2(wr[m], zi[m], t2);    // wi zr + wr zi
+          wr[m] = nwr; wi[m] = nwi;
+          C[m] = ffma2(aa, nwr, C[m]);             // sum a cos(phi) cos(k w n)
+          S[m] = ffma2(bb, nwi, S[m]);             // sum a sin(phi) sin(k w n)
+        }
+      }
+    }
+
+    // ---- window and park the frame in shared memory: sample j = H +- n
+    float* dst = fb + (size_t)s * npad;
+#pragma unroll
+    for(int m = 0; m < NP; m ++) {
+#pragma unroll
+      for(int h = 0; h < 2; h ++) {
+        int n = lane + 64 * m + 32 * h;
+        float c = h ? C[m].y : C[m].x, sn = h ? S[m].y : S[m].x;
+        if(n <= H - 1) dst[H + n] = (c - sn) * P.win[H + n];
+        if(n >= 1 && n <= H) dst[H - n] = (c + sn) * P.win[H - n];
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- overlap-add: gather the (<= 3) frames covering each owned sample, ascending frame order
+  //      as in the reference's sequential y[idx] += yi[j] (layer0.c:135-140)
+  float* yrow = P.y_sin + (size_t)b * P.stride;
+  for(int idx = start + (int)threadIdx.x; idx < end; idx += blockDim.x) {
+    float acc = 0.f;
+    if(idx < ny_b) {
+      // first slot whose window end (sb + H) is beyond idx
+      int lo = 0, hi = nslot;
+      while(lo < hi) { int mid = (lo + hi) >> 1; if(sb[mid] + H > idx) hi = mid; else lo = mid + 1; }
+      for(int s = lo; s < nslot; s ++) {
+        int j = idx - sb[s] + H;
+        if(j < 0) break;
+        if(sv[s] && j < N) acc += fb[(size_t)s * npad + j];
+      }
+    }
+    yrow[idx] = acc;
+  }
+}
+
+static inline size_t bank_smem_bytes(int nwarps, int npass, int n_hm) {
+  int nslot = nwarps * npass;
+  size_t npad = (n_hm + 3) & ~3;
+  return (size_t)nslot * npad * 4 + (size_t)nwarps * BANK_KC * 16 + (size_t)nslot * 8 + 16;
+}
+
+// returns 0 on success, -1 when the window is too long for the specialisations below
+static inline int launch_hm_bank(const BankParams& P, int nutt, int nfrm_max, cudaStream_t st) {
+  const int NW = 16;
+  const int nslot = NW * P.npass;
+  const int F = nslot - 2;
+  // tiles: one per frame; the CTA owning tile 0 also owns [0, hm_base[0]); the last one the tail
+  int nseg = (std::max(nfrm_max, 1) + F - 1) / F;
+  dim3 grid(nseg, nutt), block(NW * 32);
+  size_t smem = bank_smem_bytes(NW, P.npass, P.n_hm);
+  int slots = (P.n_hm / 2 + 1 + 63) / 64;  // packed pair-slots per lane
+#ifndef LLSM_EMU
+#define BANK_ATTR(NPV) cudaFuncSetAttribute(hm_bank_ola_kernel<NPV>, \
+    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+#else
+#define BANK_ATTR(NPV) (void)0
+#endif
+  switch(slots) {
+    case 1: BANK_ATTR(1); LLSM_LAUNCH(hm_bank_ola_kernel<1>, grid, block, smem, st, P); break;
+    case 2: BANK_ATTR(2); LLSM_LAUNCH(hm_bank_ola_kernel<2>, grid, block, smem, st, P); break;
+    case 3: BANK_ATTR(3); LLSM_LAUNCH(hm_bank_ola_kernel<3>, grid, block, smem, st, P); break;
+    case 4: BANK_ATTR(4); LLSM_LAUNCH(hm_bank_ola_kernel<4>, grid, block, smem, st, P); break;
+    case 5: case 6: BANK_ATTR(6); LLSM_LAUNCH(hm_bank_ola_kernel<6>, grid, block, smem, st, P); break;
+    case 7: case 8: BANK_ATTR(8); LLSM_LAUNCH(hm_bank_ola_kernel<8>, grid, block, smem, st, P); break;
+    default: return -1;
+  }
+#undef BANK_ATTR
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Noise template: white -> band-limited ("coloured") template per (utterance, channel)
+// ------------------------------------------------------------------------------------------
+struct ChanFiltDev { int nstage; double b[2][5]; double a[2][5]; };
+
+struct TemplateParams {
+  int nutt, nchannel, nt;
+  const float* white;       // [B][nchannel][nt] N(0,1), or NULL -> Philox draw from seed
+  unsigned long long seed;
+  float* colored;           // [B][nchannel][nt]
+  ChanFiltDev chan[8];
+};
+
+// Philox4x32-10 counter-based generator (Salmon et al. 2011), used only when no host template is
+// supplied (throughput mode; the reference draws from libc rand(), dsputils.c:353-361).
+__device__ __forceinline__ void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3,
+  unsigned k0, unsigned k1, unsigned* out) {
+  const unsigned M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+  for(int r = 0; r < 10; r ++) {
+    unsigned hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+    unsigned hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+    unsigned n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += W0; k1 += W1;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ float device_white(unsigned long long seed, unsigned stream, unsigned n) {
+  // sample n of stream: Box-Muller on two 32-bit uniforms of block n/2
+  unsigned r[4];
+  philox4x32_10(n >> 1, stream, 0x6c6c736du, 0u, (unsigned)seed, (unsigned)(seed >> 32), r);
+  float u1 = ((float)r[0] + 1.0f) * (1.0f / 4294967808.0f);   // (0, 1)
+  float u2 = (float)r[1] * (1.0f / 4294967296.0f);
+  float rad = sqrtf(-2.0f * logf(u1));
+  float s, c; sincospif(2.0f * u2, &s, &c);
+  return (n & 1) ? rad * s : rad * c;
+}
+
+// zero-phase IIR (filtfilt with zero initial state, as the oracle's ciglet shim): forward pass,
+// then backward pass in place; state in double, direct form II transposed, order 4.
+__global__ void __launch_bounds__(32) noise_template_kernel(TemplateParams P) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if(t >= P.nutt * P.nchannel) return;
+  int c = t % P.nchannel;
+  const ChanFiltDev& cf = P.chan[c];
+  float* y = P.colored + (size_t)t * P.nt;
+  const float* x = P.white ? P.white + (size_t)t * P.nt : nullptr;
+  if(cf.nstage == 0) { for(int n = 0; n < P.nt; n ++) y[n] = 0.f; return; }
+  for(int st = 0; st < cf.nstage; st ++) {
+    const double b0 = cf.b[st][0] / cf.a[st][0], b1 = cf.b[st][1] / cf.a[st][0],
+                 b2 = cf.b[st][2] / cf.a[st][0], b3 = cf.b[st][3] / cf.a[st][0],
+                 b4 = cf.b[st][4] / cf.a[st][0];
+    const double a1 = cf.a[st][1] / cf.a[st][0], a2 = cf.a[st][2] / cf.a[st][0],
+                 a3 = cf.a[st][3] / cf.a[st][0], a4 = cf.a[st][4] / cf.a[st][0];
+    double z0 = 0, z1 = 0, z2 = 0, z3 = 0;
+    for(int n = 0; n < P.nt; n ++) {                 // forward
+      double xn;
+      if(st == 0) xn = x ? (double)x[n] : (double)device_white(P.seed, (unsigned)t, (unsigned)n);
+      else xn = (double)y[n];
+      double yn = b0 * xn + z0;
+      z0 = b1 * xn + z1 - a1 * yn;
+      z1 = b2 * xn + z2 - a2 * yn;
+      z2 = b3 * xn + z3 - a3 * yn;
+      z3 = b4 * xn - a4 * yn;
+      y[n] = (float)yn;
+    }
+    z0 = z1 = z2 = z3 = 0;
+    for(int n = P.nt - 1; n >= 0; n --) {            // backward, in place
+      double xn = (double)y[n];
+      double yn = b0 * xn + z0;
+      z0 = b1 * xn + z1 - a1 * yn;
+      z1 = b2 * xn + z2 - a2 * yn;
+      z2 = b3 * xn + z3 - a3 * yn;
+      z3 = b4 * xn - a4 * yn;
+      y[n] = (float)yn;
+    }
+  }
+}
+
+static inline void launch_noise_template(const TemplateParams& P, cudaStream_t st) {
+  int total = P.nutt * P.nchannel;
+  dim3 grid((total + 31) / 32), block(32);
+  LLSM_LAUNCH(noise_template_kernel, grid, block, 0, st, P);
+}
+
+// ------------------------------------------------------------------------------------------
+// Noise excitation: per-channel envelope (harmonic bank of <= maxnhar_e terms + DC, Hann, OLA),
+// modulation of the stretched band-limited templates, channel mix.
+// ------------------------------------------------------------------------------------------
+struct ExcParams {
+  int nfrm, nchannel, maxnhar_e;
+  const int* nfrm_utt; const int* ny_utt;
+  const float* f0; const float* edc; const int* enhar; const float* eampl; const float* ephse;
+  const float* env_r;       // [nfrm] (float)((i - 1) * thop * fs)
+  const int* env_off;       // [nfrm] round(env_r)
+  const float* win_env;     // [n_env]
+  int n_env;
+  int ny, nsamp, stride;
+  float fs;
+  int has_options, use_iczt; float iczt_a, iczt_b;
+  const float* colored;     // [B][nchannel][nt]
+  int nt, ntemplate;
+  unsigned chan_mask;       // bit c set when channel c exists (fmin < fs / 2)
+  float* y_exc;             // [B][stride]
+};
+
+#define EXC_THREADS 256
+#define EXC_FCHUNK 8
+
+// stretch_stationary_noise (dsputils.c:363-383) as a closed-form index map: value of the
+// stretched template at output position p.
+__device__ __forceinline__ float stretched_noise(const float* __restrict__ x, int nx, int ny, int p) {
+  const int overlap = 128;
+  const int period = nx - overlap;
+  float base; int ii = -1;
+  if(p < nx) {
+    base = x[p];
+    if(ny > nx && p >= nx - overlap) ii = p - (nx - overlap);
+  } else {
+    int s = (p - nx) / period;          // 0-based copy segment after the first template
+    int head = nx + s * period;
+    int i = p - head;
+    base = x[i + overlap];
+    if(i >= period - overlap && head + period <= ny) ii = i - (period - overlap);
+  }
+  if(ii >= 0) {
+    float r = (float)ii / (float)overlap;
+    float y = (float)((double)base * (1.0 - (double)r));
+    y = y + x[ii] * r;
+    float d = 2.0f * r; d = d * (r - 1.0f); d = d + 1.0f;
+    base = (float)((double)y / sqrt((double)d));
+  }
+  return base;
+}
+
+template <int MAXCH>
+__global__ void __launch_bounds__(EXC_THREADS) noise_excitation_kernel(ExcParams P) {
+  LLSM_DYN_SMEM(smem);
+  const int b = blockIdx.y;
+  const int p0 = blockIdx.x * EXC_THREADS;
+  const int p = p0 + (int)threadIdx.x;
+  const int nf = P.nfrm_utt ? P.nfrm_utt[b] : P.nfrm;
+  const int ny_b = P.ny_utt ? P.ny_utt[b] : P.ny;
+  const int nch = P.nchannel, mne = P.maxnhar_e;
+  const int fstride = 4 + nch * (2 + 2 * mne);     // floats per staged frame
+  float* fr = (float*)smem;                        // [EXC_FCHUNK][fstride]
+  const size_t row = (size_t)b * P.nfrm;
+
+  // frames that can reach [p0, p0 + EXC_THREADS): env_off + n_env + 1 > p0 and env_off - 1 <= pend
+  const int pend = p0 + EXC_THREADS - 1;
+  int lo = 0, hi = nf;
+  while(lo < hi) { int mid = (lo + hi) >> 1; if(P.env_off[mid] + P.n_env + 1 > p0) hi = mid; else lo = mid + 1; }
+  const int ia = lo;
+  lo = ia; hi = nf;
+  while(lo < hi) { int mid = (lo + hi) >> 1; if(P.env_off[mid] - 1 > pend) hi = mid; else lo = mid + 1; }
+  const int ib = lo;                               // frames [ia, ib)
+
+  float env[MAXCH];
+#pragma unroll
+  for(int c = 0; c < MAXCH; c ++) env[c] = 0.f;
+  const int half = P.n_env / 2;
+
+  for(int i0 = ia; i0 < ib; i0 += EXC_FCHUNK) {
+    const int nfc = min(EXC_FCHUNK, ib - i0);
+    __syncthreads();
+    // ---- stage frame parameters
+    for(int e = threadIdx.x; e < nfc * fstride; e += blockDim.x) {
+      int fi = e / fstride, q = e - fi * fstride;
+      int i = i0 + fi;
+      float f0 = P.f0[row + i];
+      float v;
+      if(q == 0) v = f0 > 0 ? f0 / P.fs : 0.f;               // f0[i] / fs (0 when unvoiced)
+      else if(q == 1) v = P.env_r[i];
+      else if(q == 2) v = __int_as_float(P.env_off[i]);
+      else if(q == 3) v = 0.f;
+      else {
+        int qq = q - 4, c = qq / (2 + 2 * mne), w = qq - c * (2 + 2 * mne);
+        size_t ec = (row + i) * nch + c;
+        int nh = f0 > 0 ? P.enhar[ec] : 0;                   // layer0.c:298 unvoiced -> 0 harmonics
+        if(nh > mne) nh = mne;
+        if(w == 0) v = P.edc[ec];
+        else if(w == 1) v = __int_as_float(nh);
+        else {
+          int k = (w - 2) >> 1;
+          if(k < nh) {
+            float a = P.eampl[ec * mne + k], ph = P.ephse[ec * mne + k];
+            float s, co; sincosf(ph, &s, &co);
+            v = ((w - 2) & 1) ? a * s : a * co;
+          } else v = 0.f;
+        }
+      }
+      fr[e] = v;
+    }
+    __syncthreads();
+    if(p < P.nsamp && p < ny_b) {
+      for(int fi = 0; fi < nfc; fi ++) {
+        const float* F = fr + fi * fstride;
+        const float f0n = F[0], r = F[1];
+        const int off = __float_as_int(F[2]);
+        for(int dj = -1; dj <= 1; dj ++) {
+          int j = p - off + dj;
+          if(j < 0 || j >= P.n_env) continue;
+          float tpos = __fadd_rn(r, (float)j);               // (i - 1) * thop * fs + j in float
+          int idx = (int)roundf(tpos);                       // layer0.c:307
+          if(idx != p) continue;
+          const float wj = P.win_env[j];
+          float2 z = unit_phasor_turns((double)f0n * (double)(j - half));
+          float2 w = make_float2(1.f, 0.f);
+          float hs[MAXCH];
+#pragma unroll
+          for(int c = 0; c < MAXCH; c ++) hs[c] = 0.f;
+          for(int k = 0; k < mne; k ++) {
+            w = cmul(w, z);
+#pragma unroll
+            for(int c = 0; c < MAXCH; c ++) if(c < nch) {
+              const float* Fc = F + 4 + c * (2 + 2 * mne);
+              hs[c] += Fc[2 + 2 * k] * w.x - Fc[3 + 2 * k] * w.y;
+            }
+          }
+#pragma unroll
+          for(int c = 0; c < MAXCH; c ++) if(c < nch) {
+            const float* Fc = F + 4 + c * (2 + 2 * mne);
+            float v = hs[c] + Fc[0];
+            if(! (v > 1e-8f)) v = 1e-8f;                     // layer0.c:304
+            env[c] += v * wj;                                // layer0.c:306,309
+          }
+        }
+      }
+    }
+  }
+
+  if(p < P.nsamp) {
+    float y = 0.f;
+    if(p < ny_b) {
+#pragma unroll
+      for(int c = 0; c < MAXCH; c ++) if(c < nch && ((P.chan_mask >> c) & 1u)) {
+        const float* tp = P.colored + ((size_t)b * nch + c) * P.nt;
+        float x = stretched_noise(tp, P.ntemplate, ny_b, p);
+        x = (float)((double)x * sqrt((double)env[c]));       // layer0.c:548
+        y += x;                                              // layer0.c:549
+      }
+    }
+    P.y_exc[(size_t)b * P.stride + p] = y;
+  }
+}
+
+static inline size_t exc_smem_bytes(int nchannel, int maxnhar_e) {
+  return (size_t)EXC_FCHUNK * (4 + nchannel * (2 + 2 * maxnhar_e)) * 4 + 16;
+}
+
+static inline int launch_noise_excitation(const ExcParams& P, int nutt, cudaStream_t st) {
+  dim3 grid((P.nsamp + EXC_THREADS - 1) / EXC_THREADS, nutt), block(EXC_THREADS);
+  size_t smem = exc_smem_bytes(P.nchannel, P.maxnhar_e);
+  if(smem > 200 * 1024) return -1;
+#ifndef LLSM_EMU
+  if(smem > 48 * 1024) {
+    cudaFuncSetAttribute(noise_excitation_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(noise_excitation_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  }
+#endif
+  if(P.nchannel <= 4) LLSM_LAUNCH(noise_excitation_kernel<4>, grid, block, smem, st, P);
+  else                LLSM_LAUNCH(noise_excitation_kernel<8>, grid, block, smem, st, P);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Noise shaping: per frame STFT -> PSD -> gain from the model PSD -> ISTFT -> OLA, + final mix.
+// One CTA owns a run of output samples of one utterance and walks, in ascending order, every
+// frame whose nfft-long output touches the run, accumulating in shared memory: no atomics, each
+// output sample is written once, and the summation order equals the reference's frame loop.
+// ------------------------------------------------------------------------------------------
+struct ShapeParams {
+  int nfrm, npsd;
+  const int* nfrm_utt; const int* ny_utt;
+  const float* psd; const float* psdres;    // [B][nfrm][npsd]; psdres may be NULL
+  const int* center;        // [nfrm] round(i * thop * fs)
+  const float* win;         // [n_ns]
+  int n_ns, nfft, lg_nfft, nspec;
+  float wsqr, fs;
+  const int* psd_lo; const float* psd_r;    // [nspec - 1] interpolation plan
+  const float2* tw;         // [nfft] exp(-2 pi i m / nfft)
+  const float* y_exc;       // [B][stride_exc]
+  int stride_exc;
+  const float* y_sin;       // [B][stride] (may be NULL: y = y_noise)
+  float* y_noise; float* y; // [B][stride]; y may be NULL
+  int ny, nsamp, stride;
+  int seg;                  // output samples owned by a CTA
+};
+
+#define SHAPE_THREADS 256
+
+__global__ void __launch_bounds__(SHAPE_THREADS) noise_shape_kernel(ShapeParams P) {
+  LLSM_DYN_SMEM(smem);
+  const int nfft = P.nfft, nspec = P.nspec, npsd = P.npsd;
+  float2* bufa = (float2*)smem;                    // [nfft]
+  float2* bufb = bufa + nfft;                      // [nfft]
+  float* acc = (float*)(bufb + nfft);              // [seg]
+  float* spsd = acc + P.seg;                       // [npsd]
+  float* pbuf = spsd + npsd;                       // [nspec]
+  float* wmax = pbuf + nspec;                      // [32]
+
+  const int b = blockIdx.y;
+  const int oa = blockIdx.x * P.seg;
+  const int ob = min(oa + P.seg, P.nsamp);
+  const int nf = P.nfrm_utt ? P.nfrm_utt[b] : P.nfrm;
+  const int ny_b = P.ny_utt ? P.ny_utt[b] : P.ny;
+  const int tid = threadIdx.x, nth = blockDim.x;
+  const int half = nfft >> 1, hw = P.n_ns / 2;
+  const size_t row = (size_t)b * P.nfrm;
+  const float* exc = P.y_exc + (size_t)b * P.stride_exc;
+
+  for(int i = tid; i < P.seg; i += nth) acc[i] = 0.f;
+
+  // frames with [center - half, center + half) intersecting [oa, ob)
+  int lo = 0, hi = nf;
+  while(lo < hi) { int mid = (lo + hi) >> 1; if(P.center[mid] + half > oa) hi = mid; else lo = mid + 1; }
+  const int ia = lo;
+  lo = ia; hi = nf;
+  while(lo < hi) { int mid = (lo + hi) >> 1; if(P.center[mid] - half >= ob) hi = mid; else lo = mid + 1; }
+  const int ib = lo;
+  const double resbias = 0.375 / 2.3025851 * 10.0;   // LOG2IN(LOGRESBIAS), constants.h:5,12
+
+  for(int i = ia; i < ib; i ++) {
+    __syncthreads();
+    // ---- model PSD (+ residual) and its peak (layer0.c:584-585,598-601)
+    const float* psd = P.psd + (row + i) * (size_t)npsd;
+    const float* res = P.psdres ? P.psdres + (row + i) * (size_t)npsd : nullptr;
+    float mx = -3.0e38f;
+    for(int j = tid; j < npsd; j += nth) {
+      float v = psd[j];
+      mx = fmaxf(mx, v);
+      if(res) v = (float)((double)v + ((double)res[j] - resbias));
+      spsd[j] = v;
+    }
+    for(int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if((tid & 31) == 0) wmax[tid >> 5] = mx;
+    // ---- windowed frame, centred in the FFT buffer (layer0.c:588-592)
+    const int center = P.center[i];
+    for(int j = tid; j < nfft; j += nth) {
+      int jj = j - half + hw;          // index into the nwin-long frame
+      float v = 0.f;
+      if(jj >= 0 && jj < P.n_ns) {
+        int idx = center + jj - hw;
+        if(idx >= 0 && idx < ny_b) v = exc[idx] * P.win[jj];
+      }
+      bufa[j] = make_float2(v, 0.f);
+    }
+    __syncthreads();
+    float peak = wmax[0];
+    for(int w = 1; w < (nth >> 5); w ++) peak = fmaxf(peak, wmax[w]);
+    if(peak < -100.f) continue;        // uniform: -100 dB floor, layer0.c:585
+
+    float2* X = block_fft<false>(bufa, bufb, P.lg_nfft, P.tw, nfft);
+    float2* Y = (X == bufa) ? bufb : bufa;
+
+    // ---- PSD (dsputils.c:237-244)
+    for(int k = tid; k < nspec; k += nth) {
+      float2 v = X[k];
+      float pw = v.x * v.x + v.y * v.y;
+      pbuf[k] = pw / P.wsqr;
+    }
+    __syncthreads();
+    // ---- gain: target PSD / smoothed measured PSD (layer0.c:597-612)
+    for(int k = tid; k < nspec - 1; k += nth) {
+      int l = max(0, k - 3), u = min(nspec - 1, k + 3);
+      float sm = 0.f;
+      for(int q = l; q <= u; q ++) sm += pbuf[q];
+      float envk = sm / (float)(u - l + 1);                  // moving_avg(psd, nspec, 3)
+      int pl = P.psd_lo[k]; float pr = P.psd_r[k];
+      float hdb = spsd[pl];
+      if(pr != 0.f) hdb = hdb + (spsd[pl + 1] - hdb) * pr;    // interp1 on the dB envelope
+      float denom = envk * 44100.f / P.fs + 1e-8f;
+      float H = expf(hdb * (2.3025851f / 20.0f)) / sqrtf(denom);
+      float2 v = X[k];
+      v.x *= H; v.y *= H;
+      X[k] = v;
+      if(k > 0) X[nfft - k] = make_float2(v.x, -v.y);         // complete_symm / complete_asymm
+      if(k == nspec - 2) X[nspec - 1] = make_float2(v.x, v.y); // Nyquist bin copies bin nspec-2
+    }
+    __syncthreads();
+    float2* T = block_fft<true>(X, Y, P.lg_nfft, P.tw, nfft);
+    // ---- scale, fades (layer0.c:616-619), accumulate (layer0.c:620-624)
+    const float inv = 1.0f / (float)nfft;
+    for(int j = tid; j < nfft; j += nth) {
+      float v = T[j].x * inv;
+      if(j < 16) v *= (float)j / 16.f;
+      if(j >= nfft - 16) v = (float)((double)v * (1.0 - (double)((float)(nfft - 1 - j) / 16.f)));
+      int idx = center + j - half;
+      if(idx >= oa && idx < ob && idx < ny_b) acc[idx - oa] += v;
+    }
+  }
+  __syncthreads();
+  for(int i = oa + tid; i < ob; i += nth) {
+    float v = i < ny_b ? acc[i - oa] : 0.f;
+    size_t o = (size_t)b * P.stride + i;
+    P.y_noise[o] = v;
+    if(P.y) P.y[o] = (P.y_sin ? P.y_sin[o] : 0.f) + v;       // layer0.c:658-659
+  }
+}
+
+static inline size_t shape_smem_bytes(int nfft, int seg, int npsd, int nspec) {
+  return (size_t)nfft * 16 + (size_t)(seg + npsd + nspec + 32) * 4 + 16;
+}
+
+static inline int launch_noise_shape(const ShapeParams& P, int nutt, cudaStream_t st) {
+  dim3 grid((P.nsamp + P.seg - 1) / P.seg, nutt), block(SHAPE_THREADS);
+  size_t smem = shape_smem_bytes(P.nfft, P.seg, P.npsd, P.nspec);
+  if(smem > 220 * 1024) return -1;
+#ifndef LLSM_EMU
+  cudaFuncSetAttribute(noise_shape_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#endif
+  LLSM_LAUNCH(noise_shape_kernel, grid, block, smem, st, P);
+  return 0;
+}
+
+// per-utterance output length round((nfrm_b + 1) * thop * fs) with the reference's float
+// products (layer0.c:643), for ragged batches
+__global__ void ny_utt_kernel(const int* nfrm_utt, int nutt, float thop, float fs, int* ny_utt) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if(b >= nutt) return;
+  float v = __fmul_rn((float)(nfrm_utt[b] + 1), thop);
+  v = __fmul_rn(v, fs);
+  ny_utt[b] = (int)round((double)v);
+}

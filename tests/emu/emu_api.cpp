@@ -1,0 +1,51 @@
+// C entry points of the CPU thread emulation of the kernels -- TEST INFRASTRUCTURE ONLY.
+// Same launch orchestration (driver.h) and kernel sources as the CUDA library, compiled by g++
+// with -DLLSM_EMU; "device" pointers are host pointers here. Loaded only by tests/.
+#include "cuda_emu.h"
+#include "../../libllsm2_b200/csrc/driver.h"
+
+extern "C" {
+
+int emu_synthesize_l0(const llsm_b200_conf* conf, const llsm_b200_frames* fr,
+  const llsm_b200_soptions* opt, const llsm_b200_output* out) {
+  SynthPlanDev pd;
+  if(pd.build(conf->nfrm, conf->fs, conf->thop, conf->npsd, conf->nchannel, conf->chanfreq, nullptr) != 0)
+    return -100;
+  SynthScratch sc;
+  DevBuf nyb;
+  const int* ny_utt = nullptr;
+  if(fr->nfrm_utt) {
+    nyb.reserve(conf->nutt * sizeof(int));
+    LLSM_LAUNCH(ny_utt_kernel, dim3((conf->nutt + 63) / 64), dim3(64), 0, nullptr,
+      fr->nfrm_utt, conf->nutt, conf->thop, conf->fs, nyb.as<int>());
+    ny_utt = nyb.as<int>();
+  }
+  int rc = run_synth_l0(pd, sc, *conf, *fr, *opt, *out, ny_utt, nullptr, nullptr);
+  sc.colored.release(); sc.y_exc.release(); nyb.release();
+  pd.release();
+  return rc;
+}
+
+int emu_synthesize_harmonics(const llsm_b200_conf* conf, const llsm_b200_frames* fr,
+  const llsm_b200_soptions* opt_or_null, float* y_sin, int nsamp, int stride) {
+  SynthPlanDev pd;
+  if(pd.build(conf->nfrm, conf->fs, conf->thop, conf->npsd, conf->nchannel, conf->chanfreq, nullptr) != 0)
+    return -100;
+  int rc = run_harmonics(pd, *conf, *fr, opt_or_null, nullptr, y_sin, nsamp, nsamp, stride, nullptr, nullptr);
+  pd.release();
+  return rc;
+}
+
+// plan introspection for the host-logic tests
+int emu_plan_query(int nfrm, float fs, float thop, int npsd, int* out_ints, int* hm_base, int* env_off) {
+  SynthPlan p;
+  float cf[8] = {2000, 4000, 8000, 0, 0, 0, 0, 0};
+  build_synth_plan(p, nfrm, fs, thop, npsd, 4, cf);
+  out_ints[0] = p.ny; out_ints[1] = p.n_hm; out_ints[2] = p.n_env; out_ints[3] = p.n_ns;
+  out_ints[4] = p.nfft_ns; out_ints[5] = p.ntemplate; out_ints[6] = p.nt;
+  if(hm_base) memcpy(hm_base, p.hm_base.data(), nfrm * sizeof(int));
+  if(env_off) memcpy(env_off, p.env_off.data(), nfrm * sizeof(int));
+  return 0;
+}
+
+}

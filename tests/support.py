@@ -1,0 +1,108 @@
+"""Shared helpers for the test-suite: oracle loaders, CPU thread-emulation loader, synthetic data.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load
+anything under oracle/ (it is the checker, never the product path).
+"""
+import os, subprocess, ctypes as C
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+from libllsm2_b200 import abi  # noqa: E402
+
+fp = C.POINTER(C.c_float)
+ip = C.POINTER(C.c_int)
+
+
+def _p(a, t=None):
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.c_void_p)
+
+
+# ------------------------------------------------------------------ oracle (reference build)
+_ref = {}
+
+
+def load_ref(fast=False):
+    """oracle/_ref/libllsm2_ref[_fast].so: the unmodified reference sources + ciglet shim."""
+    key = "fast" if fast else "parity"
+    if key in _ref:
+        return _ref[key]
+    name = "libllsm2_ref_fast.so" if fast else "libllsm2_ref.so"
+    path = os.path.join(ROOT, "oracle", "_ref", name)
+    if not os.path.exists(path) and os.path.isdir("/root/reference"):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "ref"],
+                              stdout=subprocess.DEVNULL)
+    lib = C.CDLL(path)
+    lib.ref_time_synthesize_soa.restype = C.c_double
+    _ref[key] = lib
+    return lib
+
+
+def ref_synthesize(frames, conf, seed=1, use_iczt=1, fast=False):
+    """Run the reference llsm_synthesize utterance by utterance. Returns y, y_sin, y_noise [B][ny]."""
+    lib = load_ref(fast)
+    B, F = conf.nutt, conf.nfrm
+    ny = lib.ref_output_length(F, C.c_float(conf.thop), C.c_float(conf.fs))
+    y = np.zeros((B, ny), np.float32); ys = np.zeros_like(y); yn = np.zeros_like(y)
+    cf = np.array(list(conf.chanfreq), np.float32)
+    for b in range(B):
+        nf = int(frames["nfrm_utt"][b]) if frames.get("nfrm_utt") is not None else F
+        nyb = lib.ref_output_length(nf, C.c_float(conf.thop), C.c_float(conf.fs))
+        args = [np.ascontiguousarray(frames[k][b]) for k in
+                ("f0", "nhar", "ampl", "phse", "psd", "psdres", "edc", "enhar", "eampl", "ephse")]
+        yb = np.zeros(nyb, np.float32); ysb = np.zeros(nyb, np.float32); ynb = np.zeros(nyb, np.float32)
+        r = lib.ref_synthesize_soa(nf, C.c_float(conf.fs), C.c_float(conf.thop), conf.maxnhar,
+                                   conf.maxnhar_e, conf.npsd, conf.nchannel, _p(cf),
+                                   C.c_float(conf.lip_radius), use_iczt,
+                                   *[_p(a) for a in args], C.c_uint(seed + b),
+                                   _p(yb), _p(ysb), _p(ynb))
+        assert r == nyb, r
+        y[b, :nyb] = yb; ys[b, :nyb] = ysb; yn[b, :nyb] = ynb
+    return y, ys, yn
+
+
+def ref_white_noise(conf, seed=1, nfrm_utt=None):
+    """The N(0,1) templates the reference draws inside llsm_synthesize for each utterance."""
+    lib = load_ref()
+    B = conf.nutt
+    ny = lib.ref_output_length(conf.nfrm, C.c_float(conf.thop), C.c_float(conf.fs))
+    nt = min(20000, ny) + 128
+    out = np.zeros((B, conf.nchannel, nt), np.float32)
+    for b in range(B):
+        nyb = ny
+        if nfrm_utt is not None:
+            nyb = lib.ref_output_length(int(nfrm_utt[b]), C.c_float(conf.thop), C.c_float(conf.fs))
+        ntb = min(20000, nyb) + 128
+        tmp = np.zeros((conf.nchannel, ntb), np.float32)
+        lib.ref_draw_white_noise(nyb, conf.nchannel, C.c_uint(seed + b), _p(tmp))
+        out[b, :, :ntb] = tmp
+    return out
+
+
+# ------------------------------------------------------------------ CPU thread emulation of the kernels
+_emu = None
+
+
+def load_emu():
+    global _emu
+    if _emu is None:
+        so = os.path.join(ROOT, "tests", "emu", "libllsm2_emu.so")
+        subprocess.check_call([os.path.join(ROOT, "tests", "emu", "build.sh")])
+        _emu = C.CDLL(so)
+    return _emu
+
+
+def frames_struct(frames):
+    f = abi.Frames()
+    for k in ("nfrm_utt", "f0", "nhar", "ampl", "phse", "psd", "psdres", "edc", "enhar", "eampl", "ephse"):
+        a = frames.get(k)
+        setattr(f, k, a.ctypes.data if a is not None else None)
+    return f
+
+
+from libllsm2_b200.synthetic import synth_frames  # noqa: E402,F401
+
+
+def rms(a):
+    return float(np.sqrt(np.mean(np.asarray(a, np.float64) ** 2)))

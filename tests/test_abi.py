@@ -1,0 +1,43 @@
+"""The C-ABI library loads and exports every symbol include/llsm_b200.h declares; without a GPU the
+compute entry points fail loudly (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "llsm_b200.h")).read()
+    return sorted(set(re.findall(r"\b(llsm_b200_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from libllsm2_b200._lib import lib
+    L = lib()
+    names = _declared()
+    assert len(names) >= 12
+    for n in names:
+        assert hasattr(L, n), n
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import libllsm2_b200 as L
+    with pytest.raises(L.LlsmB200Error):
+        L.Context(0, use_torch_stream=False)
+
+
+def test_product_never_imports_oracle():
+    """The package must not reference oracle/ or the emulator."""
+    pkg = os.path.join(ROOT, "libllsm2_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".inc", ".sh")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle/" not in txt and "libllsm2_ref" not in txt, f
+                if f.endswith(".py"):
+                    assert "emu" not in txt.replace("enumerate", ""), f
