@@ -103,10 +103,15 @@ def _ref_lib(fast=True):
     return lib
 
 
+_G = {}   # fork-inherited workload of the reference arm (nothing is pickled per step)
+
+
 def _ref_time_utts(job):
     """Worker: time llsm_synthesize (reference sources, -Ofast) on a list of utterances; returns
     (seconds inside llsm_synthesize, frames)."""
     fr, conf_t, idxs = job
+    if fr is None:
+        fr = _G["frames"]
     lib = _ref_lib(True)
     (nfrm, fs, thop, maxnhar, maxnhar_e, npsd, nch, cf, lip) = conf_t
     cfa = np.array(cf, np.float32)
@@ -142,9 +147,10 @@ def run_reference(args):
         return
     full, conf, distinct = workload(args, distinct=16)
     ncore = os.cpu_count() or 1
-    per_core = 2
+    per_core = 8
+    _G["frames"] = distinct
     pool = mp.get_context("fork").Pool(ncore)
-    jobs = [(distinct, _conf_tuple(conf), [(c * per_core + i) % 16 for i in range(per_core)]) for c in range(ncore)]
+    jobs = [(None, _conf_tuple(conf), [(c * per_core + i) % 16 for i in range(per_core)]) for c in range(ncore)]
     step_frames = conf.nfrm * per_core * ncore
     for _ in range(args.warmup):
         pool.map(_ref_time_utts, jobs)
@@ -154,7 +160,7 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     pool.close()
     v = step_frames * args.steps / dt
-    sample = ("each step = %d utterances x %d frames (2 per host core) of the bench workload through "
+    sample = ("each step = %d utterances x %d frames (8 per host core) of the bench workload through "
               "llsm_synthesize of the unmodified reference sources + ciglet shim (gcc -Ofast), one process "
               "per core" % (per_core * ncore, conf.nfrm))
     print(json.dumps({
