@@ -125,3 +125,65 @@ def synthesize_harmonics(ctx, conf, frames, nsamp, options=None, with_options=Tr
                                                C.byref(so) if with_options else None,
                                                _ptr(out), int(nsamp), out.shape[1]))
     return out
+
+
+OUT_KEYS = ("f0", "nhar", "ampl", "phse", "psd", "psdres", "edc", "enhar", "eampl", "ephse")
+
+
+def _aoptions(options):
+    """llsm_create_aoptions defaults that matter on this path (reference layer0.c:27-43)."""
+    a = abi.AOptions()
+    options = options or {}
+    a.f0_refine = int(options.get("f0_refine", 1))
+    a.hm_method = int(options.get("hm_method", 1))      # LLSM_AOPTION_HMCZT
+    a.rel_winsize = float(options.get("rel_winsize", 4.0))
+    return a
+
+
+def analysis_shapes(conf):
+    B, F, n = conf.nutt, conf.nfrm, conf.nchannel
+    return {"f0": ((B, F), "f"), "nhar": ((B, F), "i"), "ampl": ((B, F, conf.maxnhar), "f"),
+            "phse": ((B, F, conf.maxnhar), "f"), "psd": ((B, F, conf.npsd), "f"),
+            "psdres": ((B, F, conf.npsd), "f"), "edc": ((B, F, n), "f"), "enhar": ((B, F, n), "i"),
+            "eampl": ((B, F, n, conf.maxnhar_e), "f"), "ephse": ((B, F, n, conf.maxnhar_e), "f")}
+
+
+def analyze_l0(ctx, conf, x, f0, options=None, want_residual=False):
+    """llsm_analyze (layer0.c:478-511) for a batch of waveforms held in CUDA tensors.
+    x: [B][nx] float32 CUDA tensor, f0: [B][F] (copied; the refined track is returned, as the
+    reference overwrites the caller's f0). Returns dict of frame tensors (+ x_res)."""
+    import torch
+    dev = x.device
+    out = {}
+    for k, (shape, kind) in analysis_shapes(conf).items():
+        out[k] = torch.zeros(shape, dtype=torch.float32 if kind == "f" else torch.int32, device=dev)
+    out["f0"].copy_(f0)
+    fo = abi.FramesOut()
+    for k in OUT_KEYS:
+        setattr(fo, k, _ptr(out[k]))
+    xr = torch.empty_like(x) if want_residual else None
+    a = _aoptions(options)
+    check(lib().llsm_b200_analyze_l0(ctx._h, C.byref(conf), C.byref(a), _ptr(x), x.shape[1], x.stride(0),
+                                     C.byref(fo), _ptr(xr)))
+    if want_residual:
+        out["x_res"] = xr
+    return out
+
+
+def analyze_l0_host(ctx, conf, x, f0, options=None, want_residual=False):
+    """Same through host numpy buffers."""
+    out = {}
+    for k, (shape, kind) in analysis_shapes(conf).items():
+        out[k] = np.zeros(shape, np.float32 if kind == "f" else np.int32)
+    out["f0"][...] = f0
+    fo = abi.FramesOut()
+    for k in OUT_KEYS:
+        setattr(fo, k, _ptr(out[k]))
+    x = np.ascontiguousarray(x, np.float32)
+    xr = np.empty_like(x) if want_residual else None
+    a = _aoptions(options)
+    check(lib().llsm_b200_analyze_l0_host(ctx._h, C.byref(conf), C.byref(a), _ptr(x), x.shape[1], x.shape[1],
+                                          C.byref(fo), _ptr(xr)))
+    if want_residual:
+        out["x_res"] = xr
+    return out

@@ -53,6 +53,8 @@ struct SynthPlanDev {
   float *hm_frac = nullptr, *win_hm = nullptr, *env_r = nullptr, *win_env = nullptr,
         *win_ns = nullptr, *psd_r = nullptr;
   float2* tw_ns = nullptr;
+  double *iir_coef = nullptr, *iir_mpow = nullptr;   // template filters, chunk length iir_L
+  int iir_L = 0;
   std::vector<void*> owned;
   template <class T> int up(T** dst, const std::vector<T>& src, cudaStream_t st) {
     void* d = nullptr;
@@ -74,6 +76,13 @@ struct SynthPlanDev {
     rc |= up(&win_ns, h.win_ns, st);   rc |= up(&psd_lo, h.psd_lo, st);
     rc |= up(&psd_r, h.psd_r, st);
     float* twd = nullptr; rc |= up(&twd, tw, st); tw_ns = (float2*)twd;
+    iir_L = (h.nt + IIR_NT - 1) / IIR_NT;
+    std::vector<double> coef((size_t)LLSM_B200_MAXCHANNEL * 2 * 9, 0.0), mpow((size_t)LLSM_B200_MAXCHANNEL * 2 * IIR_NLOG * 16, 0.0);
+    for(int c = 0; c < nchannel; c ++)
+      for(int s2 = 0; s2 < h.chan[c].nstage; s2 ++)
+        build_iir_section(h.chan[c].b[s2], h.chan[c].a[s2], iir_L, IIR_NLOG,
+          &coef[((size_t)c * 2 + s2) * 9], &mpow[((size_t)c * 2 + s2) * IIR_NLOG * 16]);
+    rc |= up(&iir_coef, coef, st); rc |= up(&iir_mpow, mpow, st);
     if(dev_sync(st) != 0) rc = -1;   // the host vectors must outlive the async copies
     return rc;
   }
@@ -124,21 +133,23 @@ static inline int run_synth_l0(const SynthPlanDev& pd, SynthScratch& sc, const l
     st, lc);
   if(rc != 0) return rc;
 
-  // 2. band-limited noise templates
-  TemplateParams T;
-  memset(&T, 0, sizeof(T));
-  T.nutt = B; T.nchannel = nch; T.nt = h.nt;
-  T.white = opt.white; T.seed = opt.seed;
-  T.colored = sc.colored.as<float>();
+  // 2. band-limited noise templates (dsputils.c:385-394): white fill, chunk-parallel filtfilt
   unsigned mask = 0;
-  for(int c = 0; c < nch; c ++) {
-    T.chan[c].nstage = h.chan[c].nstage;
-    memcpy(T.chan[c].b, h.chan[c].b, sizeof(T.chan[c].b));
-    memcpy(T.chan[c].a, h.chan[c].a, sizeof(T.chan[c].a));
-    if(h.chan[c].nstage > 0) mask |= 1u << c;
+  {
+    WhiteParams W; memset(&W, 0, sizeof(W));
+    W.nseq = B * nch; W.nt = h.nt; W.white = opt.white; W.seed = opt.seed; W.out = sc.colored.as<float>();
+    LLSM_LAUNCH(white_fill_kernel, dim3((h.nt / 4 + 256) / 256, B * nch), dim3(256), 0, st, W);
+    if(lc) lc->n += 1;
+    IirParams I; memset(&I, 0, sizeof(I));
+    I.nchannel = nch; I.n = h.nt; I.L = pd.iir_L; I.y = sc.colored.as<float>(); I.ystride = h.nt;
+    I.coef = pd.iir_coef; I.mpow = pd.iir_mpow;
+    for(int c = 0; c < nch; c ++) {
+      I.nstage[c] = h.chan[c].nstage;
+      if(h.chan[c].nstage > 0) mask |= 1u << c;
+    }
+    LLSM_LAUNCH(iir_filtfilt_kernel, dim3(B * nch), dim3(IIR_NT), 0, st, I);
+    if(lc) lc->n += 1;
   }
-  launch_noise_template(T, st);
-  if(lc) lc->n += 1;
 
   // 3. excitation
   ExcParams E;

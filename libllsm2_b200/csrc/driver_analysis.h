@@ -1,10 +1,231 @@
 // Launch orchestration of the layer-0 analysis path (llsm_analyze, layer0.c:478-511).
 #pragma once
 #include "driver.h"
+#include "kernels_analysis.cuh"
+#include <cmath>
 
 struct AnaKey {
-  int nfrm, nx; float fs, thop;
+  int nfrm, npsd, nchannel; float fs, thop; float cf[LLSM_B200_MAXCHANNEL];
   bool operator<(const AnaKey& o) const { return memcmp(this, &o, sizeof(AnaKey)) < 0; }
 };
-struct AnaPlanDev { void release() {} };
-struct AnaScratch { void release() {} };
+
+// host plan of the analysis path: sizes and tables fixed by the configuration
+struct AnaPlan {
+  int nwin = 0, nfft = 0, lg_nfft = 0, nspec = 0, nfft_s = 0, lg_nfft_s = 0;
+  float win_power = 0, std_norm = 0;
+  std::vector<float> win_psd;
+  std::vector<int> ip_k; std::vector<float> ip_r;
+  struct ChanFilt { int nstage; double b[2][5]; double a[2][5]; };
+  ChanFilt chan[LLSM_B200_MAXCHANNEL];
+  unsigned use_x_mask = 0;
+};
+
+static inline int ilog2_ceil(int n) { int l = 0; while((1 << l) < n) l ++; return l; }
+
+static inline void build_ana_plan(AnaPlan& p, float fs, float thop, int npsd, int nchannel,
+  const float* chanfreq) {
+  // layer0.c:320-325
+  float t = thop * 4; t = t * fs;
+  p.nwin = (int)round((double)t);
+  p.nfft = (int)pow(2.0, ceil(log2((double)p.nwin)));
+  p.lg_nfft = ilog2_ceil(p.nfft);
+  p.nspec = p.nfft / 2 + 1;
+  p.nfft_s = (int)pow(2.0, ceil(log2(0.03 * (double)fs)));
+  p.lg_nfft_s = ilog2_ceil(p.nfft_s);
+  // blackman(nwin) and its float-accumulated power (dsputils.c:248-258)
+  make_blackman(p.win_psd, p.nwin);
+  float wp = 0;
+  for(int i = 0; i < p.nwin; i ++) { float sq = p.win_psd[i] * p.win_psd[i]; wp = wp + sq; }
+  p.win_power = wp;
+  // standard normaliser of llsm_compute_spectrogram (dsputils.c:100-105): sum of hanning(1024)
+  std::vector<float> h; make_hanning(h, 1024);
+  double ws = 0; for(int i = 0; i < 1024; i ++) ws += h[i];
+  float sn = (float)ws; sn = sn * 0.5f;
+  p.std_norm = sn;
+  // interp1u(0, fs / 2, v, nspec, linspace(0, fs / 2, npsd), npsd) (layer0.c:388-396), exclusive end
+  float x1 = (float)((double)fs / 2.0);
+  double step = ((double)x1 - 0.0) / p.nspec;
+  p.ip_k.resize(npsd); p.ip_r.resize(npsd);
+  for(int j = 0; j < npsd; j ++) {
+    float xq = npsd > 1 ? (float)(0.0 + ((double)x1 - 0.0) * j / (npsd - 1)) : 0.0f;
+    double pos = ((double)xq - 0.0) / step;
+    if(! (pos > 0)) { p.ip_k[j] = 0; p.ip_r[j] = 0; continue; }
+    if(pos >= p.nspec - 1) { p.ip_k[j] = p.nspec - 1; p.ip_r[j] = 0; continue; }
+    int k = (int)pos;
+    p.ip_k[j] = k; p.ip_r[j] = (float)(pos - k);
+  }
+  // channel filters (layer0.c:434-440)
+  p.use_x_mask = 0;
+  for(int c = 0; c < LLSM_B200_MAXCHANNEL; c ++) p.chan[c].nstage = 0;
+  for(int c = 0; c < nchannel; c ++) {
+    float fmin = c == 0 ? 0.0f : chanfreq[c - 1];
+    float fmax = c == nchannel - 1 ? (float)((double)fs / 2.0) : chanfreq[c];
+    if((double)fmin > 6000.0) p.use_x_mask |= 1u << c;
+    p.chan[c].nstage = select_chebyfilt(fmin / fs, fmax / fs, p.chan[c].b, p.chan[c].a);
+  }
+}
+
+struct AnaPlanDev {
+  AnaPlan h;
+  float *win_psd = nullptr, *ip_r = nullptr; int* ip_k = nullptr;
+  float2 *tw_s = nullptr, *tw_p = nullptr;
+  // chunk-parallel IIR tables of the sub-band filters, valid for sequences of iir_nx samples
+  DevBuf iir_coef, iir_mpow; int iir_nx = -1, iir_L = 0; int nchannel = 0;
+  std::vector<double> h_coef, h_mpow;
+  std::vector<void*> owned;
+  template <class T> int up(T** dst, const std::vector<T>& src, cudaStream_t st) {
+    void* d = nullptr;
+    if(dev_alloc(&d, src.size() * sizeof(T)) != 0) return -1;
+    owned.push_back(d);
+    if(! src.empty() && dev_upload(d, src.data(), src.size() * sizeof(T), st) != 0) return -1;
+    *dst = (T*)d; return 0;
+  }
+  int build(float fs, float thop, int npsd, int nchannel, const float* chanfreq, cudaStream_t st) {
+    build_ana_plan(h, fs, thop, npsd, nchannel, chanfreq);
+    this->nchannel = nchannel;
+    std::vector<float> tws, twp;
+    build_twiddle(tws, h.nfft_s); build_twiddle(twp, h.nfft);
+    int rc = 0;
+    rc |= up(&win_psd, h.win_psd, st); rc |= up(&ip_k, h.ip_k, st); rc |= up(&ip_r, h.ip_r, st);
+    float* a = nullptr; rc |= up(&a, tws, st); tw_s = (float2*)a;
+    float* b = nullptr; rc |= up(&b, twp, st); tw_p = (float2*)b;
+    if(dev_sync(st) != 0) rc = -1;
+    return rc;
+  }
+  int ensure_iir(int nx, cudaStream_t st) {
+    if(nx == iir_nx) return 0;
+    if(dev_sync(st) != 0) return -1;           // previous tables may still be in use / in flight
+    iir_L = (nx + IIR_NT - 1) / IIR_NT;
+    h_coef.assign((size_t)LLSM_B200_MAXCHANNEL * 2 * 9, 0.0);
+    h_mpow.assign((size_t)LLSM_B200_MAXCHANNEL * 2 * IIR_NLOG * 16, 0.0);
+    for(int c = 0; c < nchannel; c ++)
+      for(int s2 = 0; s2 < h.chan[c].nstage; s2 ++)
+        build_iir_section(h.chan[c].b[s2], h.chan[c].a[s2], iir_L, IIR_NLOG,
+          &h_coef[((size_t)c * 2 + s2) * 9], &h_mpow[((size_t)c * 2 + s2) * IIR_NLOG * 16]);
+    if(iir_coef.reserve(h_coef.size() * 8) || iir_mpow.reserve(h_mpow.size() * 8)) return -1;
+    if(dev_upload(iir_coef.p, h_coef.data(), h_coef.size() * 8, st) ||
+       dev_upload(iir_mpow.p, h_mpow.data(), h_mpow.size() * 8, st)) return -1;
+    if(dev_sync(st) != 0) return -1;
+    iir_nx = nx;
+    return 0;
+  }
+  void release() { for(void* p : owned) dev_free(p); owned.clear(); iir_coef.release(); iir_mpow.release(); iir_nx = -1; }
+};
+
+struct AnaScratch {
+  DevBuf x_sin, x_res, ce, env, lpsd, res, filt;
+  void release() { x_sin.release(); x_res.release(); ce.release(); env.release(); lpsd.release(); res.release(); filt.release(); }
+};
+
+// x: [B][xstride] device; fr: device output arrays; x_res_out optional [B][xstride]
+static inline int run_analyze_l0(const SynthPlanDev& sp, AnaPlanDev& ap, AnaScratch& sc,
+  const llsm_b200_conf& conf, const llsm_b200_aoptions& opt, const float* x, int nx, int xstride,
+  const llsm_b200_frames_out& fr, const int* nfrm_utt, float* x_res_out, cudaStream_t st,
+  LaunchCounter* lc) {
+  const int B = conf.nutt, F = conf.nfrm, nch = conf.nchannel;
+  const AnaPlan& h = ap.h;
+  if(opt.hm_method != 1) return LLSM_B200_ERANGE;        // HMPP: see DESIGN.md
+  if(h.nfft > 8192 || h.nfft_s > 8192) return LLSM_B200_ERANGE;
+  const size_t BF = (size_t)B * F;
+  if(sc.x_sin.reserve((size_t)B * nx * 4) || sc.x_res.reserve((size_t)B * nx * 4) ||
+     sc.ce.reserve((size_t)B * nch * nx * 4) || sc.env.reserve(BF * h.nspec * 4) ||
+     sc.lpsd.reserve(BF * h.nspec * 4) || sc.res.reserve(BF * h.nspec * 4) ||
+     sc.filt.reserve(BF * h.nspec * 4)) return LLSM_B200_ENOMEM;
+  if(ap.ensure_iir(nx, st) != 0) return LLSM_B200_ENOMEM;
+  float* x_res = x_res_out ? x_res_out : sc.x_res.as<float>();
+  const int rstride = x_res_out ? xstride : nx;
+
+  // 1. F0 refinement (dsputils.c:72-94)
+  if(opt.f0_refine) {
+    RefineParams R; memset(&R, 0, sizeof(R));
+    R.nfrm = F; R.nfrm_utt = nfrm_utt; R.x = x; R.nx = nx; R.xstride = xstride;
+    R.center = sp.hm_base; R.fs = conf.fs; R.f0 = fr.f0;
+    LLSM_LAUNCH(refine_f0_kernel, dim3(F, B), dim3(96), 0, st, R);
+    if(lc) lc->n ++;
+  }
+
+  // 2. harmonic analysis of x (dsputils.c:175-228)
+  const int max_half = (int)ceil((double)conf.fs / 20.0 * (double)opt.rel_winsize / 4.0 * 2.0) + 4;
+  {
+    HarmDftParams H; memset(&H, 0, sizeof(H));
+    H.nfrm = F; H.nfrm_utt = nfrm_utt; H.sig = x; H.nsig = 1; H.nx = nx; H.xstride = xstride;
+    H.f0 = fr.f0; H.center = sp.hm_base; H.fs = conf.fs; H.rel_winsize = opt.rel_winsize;
+    H.maxnhar = conf.maxnhar; H.nhar_out = fr.nhar; H.ampl = fr.ampl; H.phse = fr.phse;
+    H.max_half = max_half;
+    if(launch_harmonic_dft(H, B, st) != 0) return LLSM_B200_ERANGE;
+    if(lc) lc->n ++;
+  }
+
+  // 3. residual: x - resynthesised sinusoids (layer0.c:498-501; options == NULL, ny = nx)
+  {
+    llsm_b200_frames fin; memset(&fin, 0, sizeof(fin));
+    fin.nfrm_utt = nfrm_utt; fin.f0 = fr.f0; fin.nhar = fr.nhar; fin.ampl = fr.ampl; fin.phse = fr.phse;
+    int rc = run_harmonics(sp, conf, fin, nullptr, nullptr, sc.x_sin.as<float>(), nx, nx, nx, st, lc);
+    if(rc != 0) return rc;
+    LLSM_LAUNCH(residual_kernel, dim3((nx + 255) / 256, B), dim3(256), 0, st,
+      x, (const float*)sc.x_sin.as<float>(), x_res, nx, xstride, nx, rstride);
+    if(lc) lc->n ++;
+  }
+
+  // 4. noise PSD (layer0.c:318-415)
+  {
+    NoiseSpecParams N; memset(&N, 0, sizeof(N));
+    N.nfrm = F; N.nfrm_utt = nfrm_utt; N.x = x; N.xstride = xstride; N.x_res = x_res; N.rstride = rstride;
+    N.nx = nx; N.f0 = fr.f0; N.center = sp.hm_base; N.fs = conf.fs;
+    N.nwin = h.nwin; N.nfft = h.nfft; N.lg_nfft = h.lg_nfft; N.nspec = h.nspec;
+    N.nfft_s = h.nfft_s; N.lg_nfft_s = h.lg_nfft_s;
+    N.win_psd = ap.win_psd; N.win_power = h.win_power; N.std_norm = h.std_norm;
+    N.tw_s = ap.tw_s; N.tw_p = ap.tw_p;
+    N.env = sc.env.as<float>(); N.lpsd = sc.lpsd.as<float>();
+    size_t smem = (size_t)std::max(h.nfft, h.nfft_s) * 16 + 16;
+#ifndef LLSM_EMU
+    cudaFuncSetAttribute(noise_spec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#endif
+    LLSM_LAUNCH(noise_spec_kernel, dim3(F, B), dim3(NS_THREADS), smem, st, N);
+    if(lc) lc->n ++;
+
+    KalmanParams K; memset(&K, 0, sizeof(K));
+    K.nfrm = F; K.nspec = h.nspec; K.nfrm_utt = nfrm_utt;
+    K.env = sc.env.as<float>(); K.lpsd = sc.lpsd.as<float>(); K.res = sc.res.as<float>();
+    K.filt = sc.filt.as<float>();
+    LLSM_LAUNCH(noise_kalman_kernel, dim3((h.nspec + 127) / 128, B), dim3(128), 0, st, K);
+    if(lc) lc->n ++;
+
+    PsdOutParams O; memset(&O, 0, sizeof(O));
+    O.nfrm = F; O.nspec = h.nspec; O.npsd = conf.npsd; O.nfrm_utt = nfrm_utt;
+    O.lpsd = sc.lpsd.as<float>(); O.res = sc.res.as<float>(); O.ip_k = ap.ip_k; O.ip_r = ap.ip_r;
+    O.fs = conf.fs; O.psd = fr.psd; O.psdres = fr.psdres;
+    LLSM_LAUNCH(noise_psd_out_kernel, dim3(F, B), dim3(128), 0, st, O);
+    if(lc) lc->n ++;
+  }
+
+  // 5. noise envelope per channel (layer0.c:417-469)
+  {
+    IirParams I; memset(&I, 0, sizeof(I));
+    I.nchannel = nch; I.n = nx; I.L = ap.iir_L; I.y = sc.ce.as<float>(); I.ystride = nx;
+    I.src_a = x_res; I.sa_stride = rstride; I.src_b = x; I.sb_stride = xstride;
+    I.src_b_mask = h.use_x_mask; I.src_per_utt = 1;
+    I.coef = ap.iir_coef.as<double>(); I.mpow = ap.iir_mpow.as<double>();
+    for(int c = 0; c < nch; c ++) I.nstage[c] = h.chan[c].nstage;
+    I.square = 1;
+    LLSM_LAUNCH(iir_filtfilt_kernel, dim3(B * nch), dim3(IIR_NT), 0, st, I);
+    if(lc) lc->n ++;
+
+    HarmDftParams H; memset(&H, 0, sizeof(H));
+    H.nfrm = F; H.nfrm_utt = nfrm_utt; H.sig = sc.ce.as<float>(); H.nsig = nch; H.nx = nx; H.xstride = nx;
+    H.f0 = fr.f0; H.center = sp.hm_base; H.fs = conf.fs; H.rel_winsize = opt.rel_winsize;
+    H.maxnhar = conf.maxnhar_e; H.nhar_out = fr.enhar; H.ampl = fr.eampl; H.phse = fr.ephse;
+    H.max_half = max_half;
+    if(conf.maxnhar_e > 0) {
+      if(launch_harmonic_dft(H, B, st) != 0) return LLSM_B200_ERANGE;
+      if(lc) lc->n ++;
+    }
+
+    DcParams D; memset(&D, 0, sizeof(D));
+    D.nfrm = F; D.nchannel = nch; D.nfrm_utt = nfrm_utt; D.ce = sc.ce.as<float>(); D.cstride = nx; D.nx = nx;
+    D.f0 = fr.f0; D.center = sp.hm_base; D.fs = conf.fs; D.thop = conf.thop; D.edc = fr.edc;
+    LLSM_LAUNCH(frame_dc_kernel, dim3(F, B * nch), dim3(128), 0, st, D);
+    if(lc) lc->n ++;
+  }
+  return 0;
+}

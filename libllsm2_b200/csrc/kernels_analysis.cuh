@@ -1,0 +1,491 @@
+// Layer-0 analysis kernels for B200 (sm_100a).
+//
+//   refine_f0_kernel        llsm_refine_f0 (dsputils.c:72-94) + the IF detector it drives
+//   harmonic_dft_kernel     llsm_harmonic_analysis, HMCZT method (dsputils.c:175-228,145-169):
+//                           Blackman window, DFT at the harmonics of f0, centre rotation,
+//                           amplitude 2/sum(w), phase. Also used on the squared sub-band signals
+//                           (layer0.c:443) with maxnhar_e harmonics.
+//   residual_kernel         x_res = x - x_sin (layer0.c:500-501)
+//   (iir_filtfilt_kernel in kernels_iir.cuh: llsm_subband_energy, dsputils.c:230-235,51-70)
+//   frame_dc_kernel         llsm_compute_dc (dsputils.c:117-124) with the window rule of
+//                           layer0.c:430
+//   noise_spec_kernel       per-frame spectra of llsm_analyze_noise_psd (layer0.c:325-360):
+//                           Hann STFT -> cepstral envelope (spec2env) and Blackman PSD of x_res
+//   noise_kalman_kernel     per-bin moving variance, Kalman filter + RTS smoother along time
+//                           (layer0.c:361-385)
+//   noise_psd_out_kernel    interpolation to npsd bins, dB conversion (layer0.c:388-408)
+#pragma once
+#include "common.cuh"
+#include "kernels_synth.cuh"   // ChanFiltDev
+
+// reference index helpers, float/double steps as written in the C source ---------------------
+__device__ __forceinline__ int ana_winsize(float fs, float f0, float rel) {
+  float t = fs / f0;                 // dsputils.c:190  round(fs / f0[i] * rel_winsize / 2) * 2
+  t = __fmul_rn(t, rel);
+  t = t / 2.0f;
+  return (int)round((double)t) * 2;
+}
+__device__ __forceinline__ int ana_nhar(float fs, float f0, int maxnhar) {
+  float t = fs / f0;                 // dsputils.c:171-173  floor(fs / f0 / 2)
+  t = t / 2.0f;
+  int n = (int)floor((double)t);
+  return n < maxnhar ? n : maxnhar;
+}
+
+// ------------------------------------------------------------------------------------------
+// F0 refinement
+// ------------------------------------------------------------------------------------------
+struct RefineParams {
+  int nfrm; const int* nfrm_utt;
+  const float* x; int nx, xstride;
+  const int* center;        // [nfrm] round(i * thop * fs)
+  float fs;
+  float* f0;                // [B][nfrm] in/out
+};
+
+// One CTA (96 threads = 3 warps) per frame; warp j estimates the instantaneous frequency around
+// harmonic j+1 with the windowed complex-demodulation detector of the oracle's ciglet shim:
+// Hann window of nh = 2 round(2 / fres) + 1 taps (fres = f0 / fs), f = fc - Im(yd / y) / (2 pi).
+__global__ void __launch_bounds__(96) refine_f0_kernel(RefineParams P) {
+  __shared__ float s_f[3];
+  __shared__ int s_ok[3];
+  const int i = blockIdx.x, b = blockIdx.y;
+  const int nf = P.nfrm_utt ? P.nfrm_utt[b] : P.nfrm;
+  if(i >= nf) return;
+  const float f0 = P.f0[(size_t)b * P.nfrm + i];
+  if(f0 == 0) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = warp + 1;
+  const float fres = f0 / P.fs;
+  const float fc = fres * (float)j;                    // f0[i] / fs * j
+  int half = (int)round(2.0 / (double)fres);
+  if(half < 2) half = 2;
+  const int nh = 2 * half + 1;
+  const double L = 2.0 * half + 2.0;
+  const float* x = P.x + (size_t)b * P.xstride;
+  const int center = P.center[i];
+  double yr = 0, yi = 0, dr = 0, di = 0;
+  for(int t = lane; t < nh; t += 32) {
+    int idx = center + t - nh / 2;
+    if(idx < 0 || idx >= P.nx) continue;
+    double xv = (double)x[idx];
+    int m = t - nh / 2;
+    double sw, cw; sincospi(2.0 * (double)m / L, &sw, &cw);
+    double w = 0.5 + 0.5 * cw;
+    double wd = -0.5 * (2.0 * LLSM_PI / L) * sw;
+    double u = (double)fc * (double)m; u -= rint(u);
+    double sp, cp; sincospi(2.0 * u, &sp, &cp);
+    // taps are stored as FP_TYPE (float) in the detector
+    float hr = (float)(w * cp), hi = (float)(-w * sp), hdr = (float)(wd * cp), hdi = (float)(-wd * sp);
+    yr += xv * hr; yi += xv * hi; dr += xv * hdr; di += xv * hdi;
+  }
+  for(int o = 16; o > 0; o >>= 1) {
+    yr += __shfl_xor_sync(0xffffffffu, yr, o); yi += __shfl_xor_sync(0xffffffffu, yi, o);
+    dr += __shfl_xor_sync(0xffffffffu, dr, o); di += __shfl_xor_sync(0xffffffffu, di, o);
+  }
+  if(lane == 0) {
+    double den = yr * yr + yi * yi;
+    float est = fc;
+    if(! (den < 1e-30)) est = (float)((double)fc - ((di * yr - dr * yi) / den) / (2.0 * LLSM_PI));
+    float fj = est / (float)j;                          // dsputils.c:81
+    float diff = fj - fres;
+    s_f[warp] = fj;
+    s_ok[warp] = fabs((double)diff) < (double)f0 * 0.1 / (double)P.fs;   // dsputils.c:82
+  }
+  __syncthreads();
+  if(threadIdx.x == 0) {
+    float favg = 0; int n = 0;
+    for(int q = 0; q < 3; q ++) if(s_ok[q]) { favg += s_f[q]; n ++; }
+    if(n > 0) {
+      favg = favg / (float)n;
+      P.f0[(size_t)b * P.nfrm + i] = favg * P.fs;       // dsputils.c:89-92
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Harmonic estimator (HMCZT)
+// ------------------------------------------------------------------------------------------
+struct HarmDftParams {
+  int nfrm; const int* nfrm_utt;
+  const float* sig;         // [B][nsig][xstride]
+  int nsig, nx, xstride;
+  const float* f0;          // [B][nfrm]
+  const int* center;        // [nfrm]
+  float fs, rel_winsize;
+  int maxnhar;              // harmonics to estimate (row length of the outputs)
+  int out_stride;           // floats between consecutive frames in ampl/phse ([.., nsig, maxnhar])
+  int* nhar_out;            // [B][nfrm][nsig]
+  float* ampl; float* phse; // [B][nfrm][nsig][maxnhar]
+  int max_half;             // capacity of the staged half-frame (pairs)
+};
+
+#define HD_THREADS 128
+#define HD_RESEED 64
+
+__global__ void __launch_bounds__(HD_THREADS) harmonic_dft_kernel(HarmDftParams P) {
+  LLSM_DYN_SMEM(smem);
+  float2* sp = (float2*)smem;                         // [max_half + 1] (x+ + x-, x+ - x-)
+  double* red = (double*)(sp + P.max_half + 2);       // [HD_THREADS] reduction scratch
+  float* part = (float*)(red + HD_THREADS);           // [2 * HD_THREADS] slice partials
+
+  const int i = blockIdx.x;
+  const int b = blockIdx.y / P.nsig, c = blockIdx.y % P.nsig;
+  const int nf = P.nfrm_utt ? P.nfrm_utt[b] : P.nfrm;
+  const int tid = threadIdx.x;
+  const size_t fidx = ((size_t)b * P.nfrm + i) * P.nsig + c;
+  if(i >= nf) return;
+  const float f0 = P.f0[(size_t)b * P.nfrm + i];
+  if(! (f0 > 0)) {                                    // unvoiced: no harmonic model (layer0.c:106)
+    if(tid == 0) P.nhar_out[fidx] = 0;
+    for(int k = tid; k < P.maxnhar; k += blockDim.x) { P.ampl[fidx * P.maxnhar + k] = 0; P.phse[fidx * P.maxnhar + k] = 0; }
+    return;
+  }
+  const int ws = ana_winsize(P.fs, f0, P.rel_winsize);
+  const int nh = ana_nhar(P.fs, f0, P.maxnhar);
+  const int half = ws >> 1;                           // shift = nx / 2 (dsputils.c:151)
+  if(half > P.max_half) {                             // window longer than the staging buffer
+    if(tid == 0) P.nhar_out[fidx] = -1;
+    return;
+  }
+  const float* x = P.sig + ((size_t)b * P.nsig + c) * P.xstride;
+  const int center = P.center[i];
+
+  // ---- stage the Blackman-windowed frame as symmetric / antisymmetric halves; window sum
+  double wsum = 0;
+  for(int n = tid; n <= half; n += blockDim.x) {
+    float xp = 0, xm = 0;
+    if(n < half) {                                    // m = half + n
+      int m = half + n, idx = center + m - half;
+      double s1, c1, s2, c2;
+      sincospi(2.0 * (double)m / (double)ws, &s1, &c1); sincospi(4.0 * (double)m / (double)ws, &s2, &c2);
+      float w = (float)(0.42 - 0.5 * c1 + 0.08 * c2);
+      wsum += w;
+      if(idx >= 0 && idx < P.nx) xp = w * x[idx];
+    }
+    if(n >= 1) {                                      // m = half - n
+      int m = half - n, idx = center + m - half;
+      double s1, c1, s2, c2;
+      sincospi(2.0 * (double)m / (double)ws, &s1, &c1); sincospi(4.0 * (double)m / (double)ws, &s2, &c2);
+      float w = (float)(0.42 - 0.5 * c1 + 0.08 * c2);
+      wsum += w;
+      if(idx >= 0 && idx < P.nx) xm = w * x[idx];
+    }
+    sp[n] = make_float2(xp + xm, xp - xm);
+  }
+  red[tid] = wsum;
+  __syncthreads();
+  for(int o = blockDim.x >> 1; o > 0; o >>= 1) {
+    if(tid < o) red[tid] += red[tid + o];
+    __syncthreads();
+  }
+  const float winsum = (float)red[0];                 // FP_TYPE winsum = sumfp(w, nx)
+
+  // ---- frequencies as the reference rounds them (dsputils.c:156-158)
+  const float omega0 = (float)(2.0 * LLSM_PI * (double)f0 / (double)P.fs);   // czt step (FP_TYPE arg)
+  const double nu = (double)omega0 / (2.0 * LLSM_PI);                        // turns per sample
+
+  // work split: nhc harmonics across threads, nsl sample slices across the remaining factor
+  int nhc = 1; while(nhc < nh && nhc < (int)blockDim.x) nhc <<= 1;
+  const int nslp = blockDim.x / nhc;                  // parallel slices
+  const int kk = tid % nhc, sl0 = tid / nhc;
+  const int npair = half + 1;
+  const int nslice = (npair + HD_RESEED - 1) / HD_RESEED;
+
+  for(int k0 = 0; k0 < nh; k0 += nhc) {
+    const int k = k0 + kk;                            // harmonic index (0-based), frequency (k+1) f0
+    float re = 0.f, im = 0.f;
+    if(k < nh) {
+      const double th = (double)(k + 1) * nu;
+      const float2 z = unit_phasor_turns(th);
+      for(int sl = sl0; sl < nslice; sl += nslp) {
+        const int n0 = sl * HD_RESEED, n1 = min(n0 + HD_RESEED, npair);
+        float2 w = unit_phasor_turns(th * (double)n0);
+        for(int n = n0; n < n1; n ++) {
+          const float2 s = sp[n];
+          re = fmaf(s.x, w.x, re);                    // sum (x+ + x-) cos
+          im = fmaf(-s.y, w.y, im);                   // -sum (x+ - x-) sin
+          w = cmul(w, z);
+        }
+      }
+    }
+    if(nslp > 1) {                                    // deterministic cross-slice reduction
+      __syncthreads();
+      part[2 * tid] = re; part[2 * tid + 1] = im;
+      __syncthreads();
+      if(sl0 == 0) {
+        for(int q = 1; q < nslp; q ++) { re += part[2 * (q * nhc + kk)]; im += part[2 * (q * nhc + kk) + 1]; }
+      }
+    }
+    if(sl0 == 0 && k < nh) {
+      // residual of the reference's float-rounded centre shift (dsputils.c:158-162):
+      // ishift = (float)(shift * 2 pi f0 / fs * (k + 1)) versus (k + 1) * omega0 * shift
+      float ishift = (float)((double)half * 2.0 * LLSM_PI * (double)f0 / (double)P.fs * ((double)k + 1.0));
+      double eps = (double)ishift - (double)(k + 1) * (double)omega0 * (double)half;
+      float se = (float)sin(eps), ce = (float)cos(eps);
+      float dre = re * ce - im * se, dim = re * se + im * ce;
+      float a = (float)(sqrt((double)(dre * dre + dim * dim)) * 2.0 / (double)winsum);
+      P.ampl[fidx * P.maxnhar + k] = a;
+      P.phse[fidx * P.maxnhar + k] = atan2f(dim, dre);
+    }
+  }
+  for(int k = nh + tid; k < P.maxnhar; k += blockDim.x) { P.ampl[fidx * P.maxnhar + k] = 0; P.phse[fidx * P.maxnhar + k] = 0; }
+  if(tid == 0) P.nhar_out[fidx] = nh;
+}
+
+static inline size_t harm_dft_smem(int max_half) {
+  return (size_t)(max_half + 2) * 8 + HD_THREADS * 8 + 2 * HD_THREADS * 4 + 16;
+}
+
+static inline int launch_harmonic_dft(const HarmDftParams& P, int nutt, cudaStream_t st) {
+  dim3 grid(P.nfrm, nutt * P.nsig), block(HD_THREADS);
+  size_t smem = harm_dft_smem(P.max_half);
+  if(smem > 200 * 1024) return -1;
+#ifndef LLSM_EMU
+  cudaFuncSetAttribute(harmonic_dft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#endif
+  LLSM_LAUNCH(harmonic_dft_kernel, grid, block, smem, st, P);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// residual, sub-band energies, short-time mean
+// ------------------------------------------------------------------------------------------
+__global__ void residual_kernel(const float* x, const float* x_sin, float* x_res, int nx, int xstride,
+  int sstride, int rstride) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if(n < nx) x_res[(size_t)b * rstride + n] = x[(size_t)b * xstride + n] - x_sin[(size_t)b * sstride + n];
+}
+
+struct DcParams {
+  int nfrm, nchannel; const int* nfrm_utt;
+  const float* ce; int cstride, nx;
+  const float* f0; const int* center;
+  float fs, thop;
+  float* edc;               // [B][nfrm][nchannel]
+};
+
+// short-time mean over round((f0 == 0 ? thop * 2 : 2.0 / f0) * fs) samples (layer0.c:430,446)
+__global__ void __launch_bounds__(128) frame_dc_kernel(DcParams P) {
+  __shared__ double red[128];
+  const int i = blockIdx.x, b = blockIdx.y / P.nchannel, c = blockIdx.y % P.nchannel;
+  const int nf = P.nfrm_utt ? P.nfrm_utt[b] : P.nfrm;
+  if(i >= nf) return;
+  const float f0 = P.f0[(size_t)b * P.nfrm + i];
+  double wlen = f0 == 0 ? (double)(P.thop * 2.0f) : 2.0 / (double)f0;
+  const int nw = (int)round(wlen * (double)P.fs);
+  const float* x = P.ce + ((size_t)b * P.nchannel + c) * P.cstride;
+  const int center = P.center[i];
+  double acc = 0;
+  for(int j = threadIdx.x; j < nw; j += blockDim.x) {
+    int idx = center + j - nw / 2;
+    if(idx >= 0 && idx < P.nx) acc += (double)x[idx];
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for(int o = blockDim.x >> 1; o > 0; o >>= 1) {
+    if((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if(threadIdx.x == 0)
+    P.edc[((size_t)b * P.nfrm + i) * P.nchannel + c] = nw > 0 ? (float)(red[0] / nw) : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------
+// Noise PSD analysis
+// ------------------------------------------------------------------------------------------
+struct NoiseSpecParams {
+  int nfrm; const int* nfrm_utt;
+  const float* x; int xstride;        // original waveform (spectral envelope)
+  const float* x_res; int rstride;    // residual (noise PSD)
+  int nx;
+  const float* f0; const int* center;
+  float fs;
+  int nwin;                           // round(thop * 4 * fs)                layer0.c:320
+  int nfft, lg_nfft, nspec;           // PSD transform size                  layer0.c:321-322
+  int nfft_s, lg_nfft_s;              // envelope transform size             layer0.c:325
+  const float* win_psd;               // blackman(nwin)
+  float win_power;                    // float-accumulated sum of squares    dsputils.c:254-258
+  float std_norm;                     // 0.5 * sum(hanning(1024))            dsputils.c:100-105
+  const float2* tw_s; const float2* tw_p;
+  float* env;                         // [B][nfrm][nspec] log-power envelope (x 2)
+  float* lpsd;                        // [B][nfrm][nspec] log PSD of the residual
+};
+
+#define NS_THREADS 256
+
+__global__ void __launch_bounds__(NS_THREADS) noise_spec_kernel(NoiseSpecParams P) {
+  LLSM_DYN_SMEM(smem);
+  const int nfs = P.nfft_s;
+  const int nmax = nfs > P.nfft ? nfs : P.nfft;
+  float2* bufa = (float2*)smem;
+  float2* bufb = bufa + nmax;
+  const int i = blockIdx.x, b = blockIdx.y;
+  const int nf = P.nfrm_utt ? P.nfrm_utt[b] : P.nfrm;
+  if(i >= nf) return;
+  const int tid = threadIdx.x, nth = blockDim.x;
+  const float f0 = P.f0[(size_t)b * P.nfrm + i];
+  const int center = P.center[i];
+  const size_t orow = ((size_t)b * P.nfrm + i) * P.nspec;
+
+  // ---- (i) spectral envelope of x: Hann STFT (window 3 periods or nwin), cepstral smoothing
+  int ws = P.nwin;
+  if(f0 != 0) { float t = P.fs / f0; t = __fmul_rn(t, 3.0f); ws = (int)t; }       // layer0.c:331
+  const float* x = P.x + (size_t)b * P.xstride;
+  for(int kb = tid; kb < nfs; kb += nth) {
+    float acc = 0.f;
+    int j0 = (kb + ws / 2) % nfs;
+    for(int j = j0; j < ws; j += nfs) {           // time aliasing when the window exceeds nfft
+      int idx = center + j - ws / 2;
+      if(idx >= 0 && idx < P.nx) {
+        double s, c; sincospi(2.0 * (double)j / (double)ws, &s, &c);
+        float w = (float)(0.5 - 0.5 * c);
+        acc += x[idx] * w;
+      }
+    }
+    bufa[kb] = make_float2(acc, 0.f);
+  }
+  __syncthreads();
+  float2* X = block_fft<false>(bufa, bufb, P.lg_nfft_s, P.tw_s, nfs);
+  float2* Y = (X == bufa) ? bufb : bufa;
+  {
+    float normalizer = 1024.0f / P.std_norm; normalizer = normalizer / (float)ws;  // dsputils.c:111
+    for(int k = tid; k <= nfs / 2; k += nth) {
+      float2 v = X[k];
+      float mag = (float)sqrt((double)v.x * v.x + (double)v.y * v.y) * normalizer;
+      float lg = logf(mag > 1e-10f ? mag : 1e-10f);
+      Y[k] = make_float2(lg, 0.f);
+      if(k > 0 && k < nfs / 2) Y[nfs - k] = make_float2(lg, 0.f);
+    }
+  }
+  __syncthreads();
+  float2* Cq = block_fft<true>(Y, X, P.lg_nfft_s, P.tw_s, nfs);      // cepstrum * nfft
+  float2* D = (Cq == bufa) ? bufb : bufa;
+  {
+    const float f0s = (f0 == 0 ? 200.0f : f0) / P.fs;               // layer0.c:338
+    for(int q = tid; q <= nfs / 2; q += nth) {
+      double xq = (double)f0s * q;
+      double sinc = 1.0;
+      if(q > 0) { double s, c; sincospi(xq, &s, &c); sinc = s / (LLSM_PI * xq); }
+      double s2, c2; sincospi(2.0 * xq, &s2, &c2);
+      float cv = (float)((double)Cq[q].x / nfs * sinc * (1.18 - 0.18 * c2));
+      D[q] = make_float2(cv, 0.f);
+      if(q > 0 && q < nfs / 2) D[nfs - q] = make_float2(cv, 0.f);
+    }
+  }
+  __syncthreads();
+  float2* Ev = block_fft<false>(D, Cq, P.lg_nfft_s, P.tw_s, nfs);
+  for(int j = tid; j < P.nspec; j += nth) {
+    int idx = j * nfs / P.nfft;                                       // layer0.c:341-342
+    P.env[orow + j] = Ev[idx].x * 2.0f;
+  }
+  __syncthreads();
+
+  // ---- (ii) PSD of the residual frame (Blackman, zero-padded at the end; dsputils.c:246-265)
+  const float* xr = P.x_res + (size_t)b * P.rstride;
+  for(int j = tid; j < P.nfft; j += nth) {
+    float v = 0.f;
+    if(j < P.nwin) {
+      int idx = center + j - P.nwin / 2;
+      if(idx >= 0 && idx < P.nx) v = P.win_psd[j] * xr[idx];
+    }
+    bufa[j] = make_float2(v, 0.f);
+  }
+  __syncthreads();
+  float2* Z = block_fft<false>(bufa, bufb, P.lg_nfft, P.tw_p, P.nfft);
+  for(int j = tid; j < P.nspec; j += nth) {
+    float2 v = Z[j];
+    float pw = __fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)) / P.win_power;
+    P.lpsd[orow + j] = (float)log((double)(pw > 1e-10f ? pw : 1e-10f));   // layer0.c:358
+  }
+}
+
+struct KalmanParams {
+  int nfrm, nspec; const int* nfrm_utt;
+  float* env;      // in: envelope; reused as posterior variance storage
+  float* lpsd;     // in: raw log PSD; out: smoothed + Euler gamma
+  float* res;      // out: residual (scratch for Q on the way)
+  float* filt;     // scratch: filtered means
+};
+
+// One thread per (utterance, bin): process variance from a 3-frame moving variance of the
+// envelope, observation variance pi^2/6, random-walk Kalman filter + RTS smoother along time
+// (layer0.c:361-385; filter conventions of the oracle's ciglet shim: x0 = z0, P0 = R0).
+__global__ void __launch_bounds__(128) noise_kalman_kernel(KalmanParams P) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if(j >= P.nspec) return;
+  const int n = P.nfrm_utt ? P.nfrm_utt[b] : P.nfrm;
+  if(n <= 0) return;
+  const size_t base = (size_t)b * P.nfrm * P.nspec + j;
+  const size_t st = P.nspec;
+  const double R = (double)(float)(LLSM_PI * LLSM_PI / 6.0);      // LOGCHI2VAR stored as FP_TYPE
+  float e_prev = P.env[base], e_cur = e_prev, e_next = n > 1 ? P.env[base + st] : e_prev;
+  double xk = 0, Pk = 0;
+  for(int i = 0; i < n; i ++) {
+    // Q[i] = max(1e-8, m2 / 3 - m1 * m1 / 9) over frames clamp(i-1..i+1), float arithmetic
+    float m1 = 0.f, m2 = 0.f;
+    m1 = __fadd_rn(m1, e_prev); m2 = __fadd_rn(m2, __fmul_rn(e_prev, e_prev));
+    m1 = __fadd_rn(m1, e_cur);  m2 = __fadd_rn(m2, __fmul_rn(e_cur, e_cur));
+    m1 = __fadd_rn(m1, e_next); m2 = __fadd_rn(m2, __fmul_rn(e_next, e_next));
+    float qv = __fadd_rn(m2 / 3.0f, -(__fmul_rn(m1, m1) / 9.0f));
+    float Q = qv > 1e-8f ? qv : 1e-8f;
+    const double z = (double)P.lpsd[base + i * st];
+    if(i == 0) { xk = z; Pk = R; }
+    else {
+      double Pp = Pk + (double)Q;
+      double K = Pp / (Pp + R);
+      xk += K * (z - xk);
+      Pk = (1.0 - K) * Pp;
+    }
+    P.filt[base + i * st] = (float)xk;
+    P.env[base + i * st] = (float)Pk;          // posterior variance (FP_TYPE array P)
+    P.res[base + i * st] = Q;
+    e_prev = e_cur; e_cur = e_next;
+    e_next = (i + 2 < n) ? P.env[base + (size_t)(i + 2) * st] : e_next;
+  }
+  // RTS smoother, residual, bias removal
+  double sn = (double)P.filt[base + (size_t)(n - 1) * st];
+  float qnext = 0.f;
+  for(int t = n - 1; t >= 0; t --) {
+    float yt = P.filt[base + t * st];
+    float qt = P.res[base + t * st];
+    if(t < n - 1) {
+      double Pt = (double)P.env[base + t * st];
+      double Pp = Pt + (double)qnext;
+      double Cg = Pt / Pp;
+      sn = (double)yt + Cg * (sn - (double)yt);
+    }
+    float s = (float)sn;                        // stored as FP_TYPE; the recursion stays in double
+    float raw = P.lpsd[base + t * st];
+    P.res[base + t * st] = raw - s;             // layer0.c:381
+    P.lpsd[base + t * st] = (float)((double)s + 0.57721566);   // layer0.c:382 EULERGAMMA
+    qnext = qt;
+  }
+}
+
+struct PsdOutParams {
+  int nfrm, nspec, npsd; const int* nfrm_utt;
+  const float* lpsd; const float* res;
+  const int* ip_k; const float* ip_r;  // [npsd] interp1u plan (exclusive-end grid)
+  float fs;
+  float* psd; float* psdres;           // [B][nfrm][npsd]
+};
+
+__global__ void __launch_bounds__(128) noise_psd_out_kernel(PsdOutParams P) {
+  const int i = blockIdx.x, b = blockIdx.y;
+  const int nf = P.nfrm_utt ? P.nfrm_utt[b] : P.nfrm;
+  if(i >= nf) return;
+  const size_t irow = ((size_t)b * P.nfrm + i) * P.nspec, orow = ((size_t)b * P.nfrm + i) * P.npsd;
+  for(int j = threadIdx.x; j < P.npsd; j += blockDim.x) {
+    int k = P.ip_k[j]; float r = P.ip_r[j];
+    float a = P.lpsd[irow + k], rr = P.res[irow + k];
+    if(r != 0.f) {
+      a = (float)((double)a + ((double)P.lpsd[irow + k + 1] - (double)a) * (double)r);
+      rr = (float)((double)rr + ((double)P.res[irow + k + 1] - (double)rr) * (double)r);
+    }
+    float ex = (float)exp((double)a);                                           // layer0.c:402
+    float lin = ex * 44100.0f / P.fs;
+    P.psd[orow + j] = (float)(10.0 * log10((double)lin + 1e-12));               // layer0.c:403
+    P.psdres[orow + j] = (float)((double)rr / 2.3025851 * 10.0);                // LOG2IN
+  }
+}

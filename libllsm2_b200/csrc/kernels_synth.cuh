@@ -11,6 +11,7 @@
 //                        (layer0.c:657-659)
 #pragma once
 #include "common.cuh"
+#include "kernels_iir.cuh"
 
 // ------------------------------------------------------------------------------------------
 // Harmonic bank + Hann + OLA
@@ -212,87 +213,6 @@ static inline int launch_hm_bank(const BankParams& P, int nutt, int nfrm_max, cu
 // Noise template: white -> band-limited ("coloured") template per (utterance, channel)
 // ------------------------------------------------------------------------------------------
 struct ChanFiltDev { int nstage; double b[2][5]; double a[2][5]; };
-
-struct TemplateParams {
-  int nutt, nchannel, nt;
-  const float* white;       // [B][nchannel][nt] N(0,1), or NULL -> Philox draw from seed
-  unsigned long long seed;
-  float* colored;           // [B][nchannel][nt]
-  ChanFiltDev chan[8];
-};
-
-// Philox4x32-10 counter-based generator (Salmon et al. 2011), used only when no host template is
-// supplied (throughput mode; the reference draws from libc rand(), dsputils.c:353-361).
-__device__ __forceinline__ void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3,
-  unsigned k0, unsigned k1, unsigned* out) {
-  const unsigned M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-  for(int r = 0; r < 10; r ++) {
-    unsigned hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
-    unsigned hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
-    unsigned n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
-    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-    k0 += W0; k1 += W1;
-  }
-  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
-}
-
-__device__ __forceinline__ float device_white(unsigned long long seed, unsigned stream, unsigned n) {
-  // sample n of stream: Box-Muller on two 32-bit uniforms of block n/2
-  unsigned r[4];
-  philox4x32_10(n >> 1, stream, 0x6c6c736du, 0u, (unsigned)seed, (unsigned)(seed >> 32), r);
-  float u1 = ((float)r[0] + 1.0f) * (1.0f / 4294967808.0f);   // (0, 1)
-  float u2 = (float)r[1] * (1.0f / 4294967296.0f);
-  float rad = sqrtf(-2.0f * logf(u1));
-  float s, c; sincospif(2.0f * u2, &s, &c);
-  return (n & 1) ? rad * s : rad * c;
-}
-
-// zero-phase IIR (filtfilt with zero initial state, as the oracle's ciglet shim): forward pass,
-// then backward pass in place; state in double, direct form II transposed, order 4.
-__global__ void __launch_bounds__(32) noise_template_kernel(TemplateParams P) {
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if(t >= P.nutt * P.nchannel) return;
-  int c = t % P.nchannel;
-  const ChanFiltDev& cf = P.chan[c];
-  float* y = P.colored + (size_t)t * P.nt;
-  const float* x = P.white ? P.white + (size_t)t * P.nt : nullptr;
-  if(cf.nstage == 0) { for(int n = 0; n < P.nt; n ++) y[n] = 0.f; return; }
-  for(int st = 0; st < cf.nstage; st ++) {
-    const double b0 = cf.b[st][0] / cf.a[st][0], b1 = cf.b[st][1] / cf.a[st][0],
-                 b2 = cf.b[st][2] / cf.a[st][0], b3 = cf.b[st][3] / cf.a[st][0],
-                 b4 = cf.b[st][4] / cf.a[st][0];
-    const double a1 = cf.a[st][1] / cf.a[st][0], a2 = cf.a[st][2] / cf.a[st][0],
-                 a3 = cf.a[st][3] / cf.a[st][0], a4 = cf.a[st][4] / cf.a[st][0];
-    double z0 = 0, z1 = 0, z2 = 0, z3 = 0;
-    for(int n = 0; n < P.nt; n ++) {                 // forward
-      double xn;
-      if(st == 0) xn = x ? (double)x[n] : (double)device_white(P.seed, (unsigned)t, (unsigned)n);
-      else xn = (double)y[n];
-      double yn = b0 * xn + z0;
-      z0 = b1 * xn + z1 - a1 * yn;
-      z1 = b2 * xn + z2 - a2 * yn;
-      z2 = b3 * xn + z3 - a3 * yn;
-      z3 = b4 * xn - a4 * yn;
-      y[n] = (float)yn;
-    }
-    z0 = z1 = z2 = z3 = 0;
-    for(int n = P.nt - 1; n >= 0; n --) {            // backward, in place
-      double xn = (double)y[n];
-      double yn = b0 * xn + z0;
-      z0 = b1 * xn + z1 - a1 * yn;
-      z1 = b2 * xn + z2 - a2 * yn;
-      z2 = b3 * xn + z3 - a3 * yn;
-      z3 = b4 * xn - a4 * yn;
-      y[n] = (float)yn;
-    }
-  }
-}
-
-static inline void launch_noise_template(const TemplateParams& P, cudaStream_t st) {
-  int total = P.nutt * P.nchannel;
-  dim3 grid((total + 31) / 32), block(32);
-  LLSM_LAUNCH(noise_template_kernel, grid, block, 0, st, P);
-}
 
 // ------------------------------------------------------------------------------------------
 // Noise excitation: per-channel envelope (harmonic bank of <= maxnhar_e terms + DC, Hann, OLA),

@@ -151,3 +151,35 @@ void build_synth_plan(SynthPlan& p, int nfrm, float fs, float thop, int npsd, in
     cf.nstage = select_chebyfilt(fmin / fs, fmax / fs, cf.b, cf.a);
   }
 }
+
+static void mat4_mul(const long double* x, const long double* y, long double* out) {
+  long double t[16];
+  for(int i = 0; i < 4; i ++) for(int j = 0; j < 4; j ++) {
+    long double s = 0;
+    for(int k = 0; k < 4; k ++) s += x[i * 4 + k] * y[k * 4 + j];
+    t[i * 4 + j] = s;
+  }
+  for(int i = 0; i < 16; i ++) out[i] = t[i];
+}
+
+void build_iir_section(const double b[5], const double a[5], int L, int nlog, double* coef, double* mpow) {
+  for(int i = 0; i < 5; i ++) coef[i] = b[i] / a[0];
+  for(int i = 1; i < 5; i ++) coef[4 + i] = a[i] / a[0];
+  // zero-input transition of DF2T: y = z0; z0' = z1 - a1 y; z1' = z2 - a2 y; z2' = z3 - a3 y; z3' = -a4 y
+  long double A[16] = {0};
+  A[0] = -coef[5]; A[1] = 1;
+  A[4] = -coef[6]; A[6] = 1;
+  A[8] = -coef[7]; A[11] = 1;
+  A[12] = -coef[8];
+  // M = A^L by binary exponentiation
+  long double M[16], P[16];
+  for(int i = 0; i < 16; i ++) { M[i] = (i % 5 == 0) ? 1 : 0; P[i] = A[i]; }
+  for(int e = L; e > 0; e >>= 1) {
+    if(e & 1) mat4_mul(M, P, M);
+    mat4_mul(P, P, P);
+  }
+  for(int q = 0; q < nlog; q ++) {
+    for(int i = 0; i < 16; i ++) mpow[q * 16 + i] = (double)M[i];
+    mat4_mul(M, M, M);
+  }
+}

@@ -52,3 +52,8 @@ void make_blackman(std::vector<float>& w, int n);
 // Chebyshev sub-band filter selection (dsputils.c:28-70): fills up to two {b,a} sections for the
 // band [c1, c2] (cycles per sample); returns the number of sections.
 int select_chebyfilt(float c1, float c2, double b[2][5], double a[2][5]);
+
+// Tables of the chunk-parallel IIR kernel (kernels_iir.cuh) for one filter section {b, a}:
+// coef[9] = {b0..b4, a1..a4} / a0 ; mpow[nlog][16] = (A^L)^(2^q), A = zero-input state transition
+// of the direct-form-II-transposed realisation.
+void build_iir_section(const double b[5], const double a[5], int L, int nlog, double* coef, double* mpow);

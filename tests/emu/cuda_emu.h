@@ -111,3 +111,4 @@ static inline int __float2int_rn(float f) { return (int)std::nearbyint(f); }
 using std::min; using std::max;
 static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 static inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
+#define __shared__ static   /* blocks run one at a time in the emulator */

@@ -49,3 +49,14 @@ int emu_plan_query(int nfrm, float fs, float thop, int npsd, int* out_ints, int*
 }
 
 }
+
+#include "../../libllsm2_b200/csrc/driver_analysis.h"
+extern "C" int emu_analyze_l0(const llsm_b200_conf* conf, const llsm_b200_aoptions* opt, const float* x,
+  int nx, int xstride, const llsm_b200_frames_out* fr, float* x_res) {
+  SynthPlanDev sp; AnaPlanDev ap; AnaScratch sc;
+  if(sp.build(conf->nfrm, conf->fs, conf->thop, conf->npsd, conf->nchannel, conf->chanfreq, nullptr) != 0) return -100;
+  if(ap.build(conf->fs, conf->thop, conf->npsd, conf->nchannel, conf->chanfreq, nullptr) != 0) return -101;
+  int rc = run_analyze_l0(sp, ap, sc, *conf, *opt, x, nx, xstride, *fr, nullptr, x_res, nullptr, nullptr);
+  sc.release(); ap.release(); sp.release();
+  return rc;
+}

@@ -106,3 +106,54 @@ from libllsm2_b200.synthetic import synth_frames  # noqa: E402,F401
 
 def rms(a):
     return float(np.sqrt(np.mean(np.asarray(a, np.float64) ** 2)))
+
+
+def ref_analyze(x, f0, conf, f0_refine=1, hm_method=1, rel_winsize=4.0, fast=False):
+    """Reference llsm_analyze utterance by utterance on x [B][nx], f0 [B][F] (copied; refined f0
+    returned). Returns dict of flat arrays like the synthesis inputs + x_res."""
+    lib = load_ref(fast)
+    B, F = conf.nutt, conf.nfrm
+    nx = x.shape[1]
+    cf = np.array(list(conf.chanfreq), np.float32)
+    o = dict(f0=np.array(f0, np.float32, copy=True),
+             nhar=np.zeros((B, F), np.int32), ampl=np.zeros((B, F, conf.maxnhar), np.float32),
+             phse=np.zeros((B, F, conf.maxnhar), np.float32), psd=np.zeros((B, F, conf.npsd), np.float32),
+             psdres=np.zeros((B, F, conf.npsd), np.float32), edc=np.zeros((B, F, conf.nchannel), np.float32),
+             enhar=np.zeros((B, F, conf.nchannel), np.int32),
+             eampl=np.zeros((B, F, conf.nchannel, conf.maxnhar_e), np.float32),
+             ephse=np.zeros((B, F, conf.nchannel, conf.maxnhar_e), np.float32),
+             x_res=np.zeros((B, nx), np.float32))
+    for b in range(B):
+        xb = np.ascontiguousarray(x[b])
+        rc = lib.ref_analyze_soa(_p(xb), nx, C.c_float(conf.fs), _p(o["f0"][b]), F, C.c_float(conf.thop),
+                                 conf.maxnhar, conf.maxnhar_e, conf.npsd, conf.nchannel, _p(cf),
+                                 f0_refine, hm_method, C.c_float(rel_winsize),
+                                 _p(o["nhar"][b]), _p(o["ampl"][b]), _p(o["phse"][b]), _p(o["psd"][b]),
+                                 _p(o["psdres"][b]), _p(o["edc"][b]), _p(o["enhar"][b]), _p(o["eampl"][b]),
+                                 _p(o["ephse"][b]), _p(o["x_res"][b]))
+        assert rc == 0
+    return o
+
+
+def alloc_analysis_out(conf, nx, f0):
+    B, F = conf.nutt, conf.nfrm
+    return dict(f0=np.array(f0, np.float32, copy=True),
+                nhar=np.zeros((B, F), np.int32), ampl=np.zeros((B, F, conf.maxnhar), np.float32),
+                phse=np.zeros((B, F, conf.maxnhar), np.float32), psd=np.zeros((B, F, conf.npsd), np.float32),
+                psdres=np.zeros((B, F, conf.npsd), np.float32), edc=np.zeros((B, F, conf.nchannel), np.float32),
+                enhar=np.zeros((B, F, conf.nchannel), np.int32),
+                eampl=np.zeros((B, F, conf.nchannel, conf.maxnhar_e), np.float32),
+                ephse=np.zeros((B, F, conf.nchannel, conf.maxnhar_e), np.float32),
+                x_res=np.zeros((B, nx), np.float32))
+
+
+def frames_out_struct(o):
+    f = abi.FramesOut()
+    for k in ("f0", "nhar", "ampl", "phse", "psd", "psdres", "edc", "enhar", "eampl", "ephse"):
+        setattr(f, k, o[k].ctypes.data)
+    return f
+
+
+def phase_err(a, b):
+    d = np.asarray(a, np.float64) - np.asarray(b, np.float64)
+    return (d + np.pi) % (2 * np.pi) - np.pi

@@ -1,0 +1,41 @@
+"""Analysis kernels on the CPU thread emulator against the oracle's llsm_analyze (HMCZT, the
+reference's default method). Input = an oracle-synthesised waveform, so the analysis sees
+speech-like material."""
+import ctypes as C
+import numpy as np
+import support as S
+from libllsm2_b200 import abi
+
+
+def check_analysis(o, ref, conf):
+    """Parity bars for the analysis outputs (FP_TYPE=float):
+       f0 / nhar / enhar identical; amplitudes 1e-6 absolute; amplitude-weighted phase 1e-6;
+       residual waveform RMS < 1e-6; PSD within 0.05 dB (Kalman smoothing of float log-spectra);
+       envelope means 1e-4 relative."""
+    assert np.array_equal(o["nhar"], ref["nhar"])
+    assert np.array_equal(o["enhar"], ref["enhar"])
+    assert np.abs(o["f0"] - ref["f0"]).max() < 1e-3
+    assert np.abs(o["ampl"] - ref["ampl"]).max() < 1e-6
+    assert np.abs(S.phase_err(o["phse"], ref["phse"]) * ref["ampl"]).max() < 1e-6
+    assert S.rms(o["x_res"] - ref["x_res"]) < 1e-6
+    assert np.abs(o["psd"] - ref["psd"]).max() < 0.05
+    assert np.abs(o["psdres"] - ref["psdres"]).max() < 0.1
+    assert S.rms(o["psd"] - ref["psd"]) < 5e-3
+    assert (np.abs(o["edc"] - ref["edc"]) / np.abs(ref["edc"])).max() < 1e-4
+    assert np.abs(o["eampl"] - ref["eampl"]).max() < 1e-6 * max(1.0, float(ref["eampl"].max()))
+    assert np.abs(S.phase_err(o["ephse"], ref["ephse"]) * ref["eampl"]).max() < 1e-5 * float(ref["eampl"].max())
+
+
+def test_analysis_c2_shape_small():
+    fr, conf = S.synth_frames(1, 24, seed=3, nhar=100, maxnhar=100)
+    y, ys, yn = S.ref_synthesize(fr, conf, seed=7)
+    nx = y.shape[1]
+    ref = S.ref_analyze(y, fr["f0"], conf)
+    emu = S.load_emu()
+    o = S.alloc_analysis_out(conf, nx, fr["f0"])
+    ao = abi.AOptions(); ao.f0_refine = 1; ao.hm_method = 1; ao.rel_winsize = 4.0
+    fo = S.frames_out_struct(o)
+    rc = emu.emu_analyze_l0(C.byref(conf), C.byref(ao), y.ctypes.data_as(C.c_void_p), nx, nx,
+                            C.byref(fo), o["x_res"].ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    check_analysis(o, ref, conf)

@@ -1,0 +1,76 @@
+"""GPU parity of the analysis path (llsm_b200_analyze_l0) against the oracle's llsm_analyze, and the
+analysis -> synthesis round trip."""
+import numpy as np
+import pytest
+import support as S
+from test_emu_analysis import check_analysis
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import torch
+    import libllsm2_b200 as L
+    assert torch.cuda.is_available()
+    c = L.Context(0)
+    yield c
+    c.close()
+
+
+def _analyze_gpu(ctx, conf, x, f0):
+    import torch
+    import libllsm2_b200 as L
+    out = L.analyze_l0(ctx, conf, torch.from_numpy(x).cuda(), torch.from_numpy(f0).cuda(), want_residual=True)
+    torch.cuda.synchronize()
+    return {k: v.cpu().numpy() for k, v in out.items()}
+
+
+def _case(ctx, B, F, **kw):
+    fr, conf = S.synth_frames(B, F, **kw)
+    y, ys, yn = S.ref_synthesize(fr, conf, seed=7)
+    ref = S.ref_analyze(y, fr["f0"], conf)
+    o = _analyze_gpu(ctx, conf, np.ascontiguousarray(y), fr["f0"])
+    check_analysis(o, ref, conf)
+    return fr, conf, y, ref, o
+
+
+def test_analysis_c2_shape(ctx):
+    _case(ctx, 2, 200, seed=3, nhar=100, maxnhar=100)
+
+
+def test_analysis_c1_shape(ctx):
+    _case(ctx, 1, 150, seed=4, thop=128 / 44100.0, nhar=200, maxnhar=400, nhar_e=5, npsd=128, f0_lo=70, f0_hi=200)
+
+
+def test_analysis_all_unvoiced(ctx):
+    fr, conf = S.synth_frames(1, 60, seed=5)
+    fr["f0"][:] = 0; fr["nhar"][:] = 0; fr["enhar"][:] = 0
+    y, ys, yn = S.ref_synthesize(fr, conf, seed=7)
+    ref = S.ref_analyze(y, fr["f0"], conf)
+    o = _analyze_gpu(ctx, conf, np.ascontiguousarray(y), fr["f0"])
+    assert np.all(o["nhar"] == 0) and np.all(o["ampl"] == 0)
+    assert np.abs(o["psd"] - ref["psd"]).max() < 0.05
+
+
+def test_host_entry_matches_device(ctx):
+    import libllsm2_b200 as L
+    fr, conf = S.synth_frames(2, 60, seed=6, nhar=80, maxnhar=80)
+    y, _, _ = S.ref_synthesize(fr, conf, seed=7)
+    a = _analyze_gpu(ctx, conf, np.ascontiguousarray(y), fr["f0"])
+    b = L.analyze_l0_host(ctx, conf, y, fr["f0"], want_residual=True)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+
+
+def test_analysis_synthesis_roundtrip(ctx):
+    """analyse on the GPU, resynthesise on the GPU: the harmonic part must reproduce the oracle's own
+    analysis->synthesis round trip (size-independent property: x ~ x_sin + x_res)."""
+    import torch
+    import libllsm2_b200 as L
+    fr, conf, y, ref, o = _case(ctx, 2, 120, seed=9, nhar=100, maxnhar=100)
+    nx = y.shape[1]
+    d = {k: torch.from_numpy(np.ascontiguousarray(o[k])).cuda() for k in ("f0", "nhar", "ampl", "phse")}
+    d["nfrm_utt"] = None
+    xs = L.synthesize_harmonics(ctx, conf, d, nx, with_options=False).cpu().numpy()
+    assert S.rms((y - xs) - o["x_res"]) < 1e-6
