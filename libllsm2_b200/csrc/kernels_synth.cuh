@@ -41,8 +41,8 @@ struct BankParams {
 
 #define BANK_KC 64          // harmonics staged per chunk
 
-template <int NP>
-__global__ void __launch_bounds__(512) hm_bank_ola_kernel(BankParams P) {
+template <int NP, int NTHR, int MINB>
+__global__ void __launch_bounds__(NTHR, MINB) hm_bank_ola_kernel(BankParams P) {
   LLSM_DYN_SMEM(smem);
   const int NW = blockDim.x >> 5;
   const int nslot = NW * P.npass;
@@ -181,32 +181,51 @@ static inline size_t bank_smem_bytes(int nwarps, int npass, int n_hm) {
 }
 
 // returns 0 on success, -1 when the window is too long for the specialisations below
-static inline int launch_hm_bank(const BankParams& P, int nutt, int nfrm_max, cudaStream_t st) {
-  const int NW = 16;
-  const int nslot = NW * P.npass;
-  const int F = nslot - 2;
-  // tiles: one per frame; the CTA owning tile 0 also owns [0, hm_base[0]); the last one the tail
-  int nseg = (std::max(nfrm_max, 1) + F - 1) / F;
-  dim3 grid(nseg, nutt), block(NW * 32);
-  size_t smem = bank_smem_bytes(NW, P.npass, P.n_hm);
-  int slots = (P.n_hm / 2 + 1 + 63) / 64;  // packed pair-slots per lane
+template <int NP, int NTHR, int MINB>
+static inline void launch_hm_bank_t(const BankParams& P, dim3 grid, size_t smem, cudaStream_t st) {
+  auto kfn = hm_bank_ola_kernel<NP, NTHR, MINB>;
 #ifndef LLSM_EMU
-#define BANK_ATTR(NPV) cudaFuncSetAttribute(hm_bank_ola_kernel<NPV>, \
-    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-#else
-#define BANK_ATTR(NPV) (void)0
+  cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 #endif
+  LLSM_LAUNCH(kfn, grid, dim3(NTHR), smem, st, P);
+}
+
+template <int NTHR, int MINB>
+static inline int launch_hm_bank_v(BankParams P, int nutt, int nfrm_max, int npass, cudaStream_t st) {
+  const int NW = NTHR / 32;
+  P.npass = npass;
+  const int F = NW * npass - 2;
+  int nseg = (std::max(nfrm_max, 1) + F - 1) / F;
+  dim3 grid(nseg, nutt);
+  size_t smem = bank_smem_bytes(NW, npass, P.n_hm);
+  if(smem > 220 * 1024) return -1;
+  int slots = (P.n_hm / 2 + 1 + 63) / 64;  // packed pair-slots per lane
   switch(slots) {
-    case 1: BANK_ATTR(1); LLSM_LAUNCH(hm_bank_ola_kernel<1>, grid, block, smem, st, P); break;
-    case 2: BANK_ATTR(2); LLSM_LAUNCH(hm_bank_ola_kernel<2>, grid, block, smem, st, P); break;
-    case 3: BANK_ATTR(3); LLSM_LAUNCH(hm_bank_ola_kernel<3>, grid, block, smem, st, P); break;
-    case 4: BANK_ATTR(4); LLSM_LAUNCH(hm_bank_ola_kernel<4>, grid, block, smem, st, P); break;
-    case 5: case 6: BANK_ATTR(6); LLSM_LAUNCH(hm_bank_ola_kernel<6>, grid, block, smem, st, P); break;
-    case 7: case 8: BANK_ATTR(8); LLSM_LAUNCH(hm_bank_ola_kernel<8>, grid, block, smem, st, P); break;
+    case 1: launch_hm_bank_t<1, NTHR, MINB>(P, grid, smem, st); break;
+    case 2: launch_hm_bank_t<2, NTHR, MINB>(P, grid, smem, st); break;
+    case 3: launch_hm_bank_t<3, NTHR, MINB>(P, grid, smem, st); break;
+    case 4: launch_hm_bank_t<4, NTHR, MINB>(P, grid, smem, st); break;
+    case 5: case 6: launch_hm_bank_t<6, NTHR, 1>(P, grid, smem, st); break;
+    case 7: case 8: launch_hm_bank_t<8, NTHR, 1>(P, grid, smem, st); break;
     default: return -1;
   }
-#undef BANK_ATTR
   return 0;
+}
+
+static inline int bank_variant() {
+  static int v = -1;
+  if(v < 0) { const char* e = getenv("LLSM_BANK_VARIANT"); v = e ? atoi(e) : 1; }
+  return v;
+}
+
+static inline int launch_hm_bank(const BankParams& P, int nutt, int nfrm_max, cudaStream_t st) {
+  switch(bank_variant()) {
+    case 0: return launch_hm_bank_v<512, 1>(P, nutt, nfrm_max, 2, st);   // 16 warps, 30 tiles
+    case 2: return launch_hm_bank_v<256, 3>(P, nutt, nfrm_max, 2, st);   // 8 warps, 14 tiles, <= 85 regs
+    case 3: return launch_hm_bank_v<256, 3>(P, nutt, nfrm_max, 4, st);   // 8 warps, 30 tiles, <= 85 regs
+    case 4: return launch_hm_bank_v<128, 6>(P, nutt, nfrm_max, 4, st);   // 4 warps, 14 tiles
+    default: return launch_hm_bank_v<256, 2>(P, nutt, nfrm_max, 4, st);  // 8 warps, 30 tiles
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -344,14 +363,13 @@ __global__ void __launch_bounds__(EXC_THREADS) noise_excitation_kernel(ExcParams
             w = cmul(w, z);
 #pragma unroll
             for(int c = 0; c < MAXCH; c ++) if(c < nch) {
-              const float* Fc = F + 4 + c * (2 + 2 * mne);
-              hs[c] += Fc[2 + 2 * k] * w.x - Fc[3 + 2 * k] * w.y;
+              const float2 ab = ((const float2*)(F + 4 + c * (2 + 2 * mne) + 2))[k];
+              hs[c] = fmaf(ab.x, w.x, fmaf(-ab.y, w.y, hs[c]));
             }
           }
 #pragma unroll
           for(int c = 0; c < MAXCH; c ++) if(c < nch) {
-            const float* Fc = F + 4 + c * (2 + 2 * mne);
-            float v = hs[c] + Fc[0];
+            float v = hs[c] + F[4 + c * (2 + 2 * mne)];
             if(! (v > 1e-8f)) v = 1e-8f;                     // layer0.c:304
             env[c] += v * wj;                                // layer0.c:306,309
           }
@@ -367,7 +385,7 @@ __global__ void __launch_bounds__(EXC_THREADS) noise_excitation_kernel(ExcParams
       for(int c = 0; c < MAXCH; c ++) if(c < nch && ((P.chan_mask >> c) & 1u)) {
         const float* tp = P.colored + ((size_t)b * nch + c) * P.nt;
         float x = stretched_noise(tp, P.ntemplate, ny_b, p);
-        x = (float)((double)x * sqrt((double)env[c]));       // layer0.c:548
+        x = x * sqrtf(env[c]);                               // layer0.c:548
         y += x;                                              // layer0.c:549
       }
     }
@@ -420,15 +438,19 @@ struct ShapeParams {
 
 #define SHAPE_THREADS 256
 
+// Two consecutive frames share one complex FFT: frame A rides in the real part, frame B in the
+// imaginary part; their spectra are separated with the Hermitian symmetry, filtered with their own
+// gains, re-packed (both filtered spectra are Hermitian, so the inverse transform returns A's
+// output in the real part and B's in the imaginary part).
 __global__ void __launch_bounds__(SHAPE_THREADS) noise_shape_kernel(ShapeParams P) {
   LLSM_DYN_SMEM(smem);
   const int nfft = P.nfft, nspec = P.nspec, npsd = P.npsd;
   float2* bufa = (float2*)smem;                    // [nfft]
   float2* bufb = bufa + nfft;                      // [nfft]
   float* acc = (float*)(bufb + nfft);              // [seg]
-  float* spsd = acc + P.seg;                       // [npsd]
-  float* pbuf = spsd + npsd;                       // [nspec]
-  float* wmax = pbuf + nspec;                      // [32]
+  float* spsd = acc + P.seg;                       // [2][npsd]
+  float* pbuf = spsd + 2 * npsd;                   // [2][nspec]
+  float* wmax = pbuf + 2 * nspec;                  // [2][32]
 
   const int b = blockIdx.y;
   const int oa = blockIdx.x * P.seg;
@@ -450,74 +472,97 @@ __global__ void __launch_bounds__(SHAPE_THREADS) noise_shape_kernel(ShapeParams 
   while(lo < hi) { int mid = (lo + hi) >> 1; if(P.center[mid] - half >= ob) hi = mid; else lo = mid + 1; }
   const int ib = lo;
   const double resbias = 0.375 / 2.3025851 * 10.0;   // LOG2IN(LOGRESBIAS), constants.h:5,12
+  const float inv = 1.0f / (float)nfft;
 
-  for(int i = ia; i < ib; i ++) {
+  for(int i = ia; i < ib; i += 2) {
+    const bool hasB = i + 1 < ib;
     __syncthreads();
-    // ---- model PSD (+ residual) and its peak (layer0.c:584-585,598-601)
-    const float* psd = P.psd + (row + i) * (size_t)npsd;
-    const float* res = P.psdres ? P.psdres + (row + i) * (size_t)npsd : nullptr;
-    float mx = -3.0e38f;
-    for(int j = tid; j < npsd; j += nth) {
-      float v = psd[j];
-      mx = fmaxf(mx, v);
-      if(res) v = (float)((double)v + ((double)res[j] - resbias));
-      spsd[j] = v;
-    }
-    for(int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if((tid & 31) == 0) wmax[tid >> 5] = mx;
-    // ---- windowed frame, centred in the FFT buffer (layer0.c:588-592)
-    const int center = P.center[i];
-    for(int j = tid; j < nfft; j += nth) {
-      int jj = j - half + hw;          // index into the nwin-long frame
-      float v = 0.f;
-      if(jj >= 0 && jj < P.n_ns) {
-        int idx = center + jj - hw;
-        if(idx >= 0 && idx < ny_b) v = exc[idx] * P.win[jj];
+    // ---- model PSD (+ residual) and its peak for both frames (layer0.c:584-585,598-601)
+    for(int h = 0; h < 2; h ++) {
+      float mx = -3.0e38f;
+      if(h == 0 || hasB) {
+        const float* psd = P.psd + (row + i + h) * (size_t)npsd;
+        const float* res = P.psdres ? P.psdres + (row + i + h) * (size_t)npsd : nullptr;
+        for(int j = tid; j < npsd; j += nth) {
+          float v = psd[j];
+          mx = fmaxf(mx, v);
+          if(res) v = (float)((double)v + ((double)res[j] - resbias));
+          spsd[h * npsd + j] = v;
+        }
       }
-      bufa[j] = make_float2(v, 0.f);
+      for(int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      if((tid & 31) == 0) wmax[h * 32 + (tid >> 5)] = mx;
+    }
+    // ---- windowed frames, centred in the FFT buffer (layer0.c:588-592): A real, B imaginary
+    const int cA = P.center[i], cB = hasB ? P.center[i + 1] : 0;
+    for(int j = tid; j < nfft; j += nth) {
+      int jj = j - half + hw;
+      float va = 0.f, vb = 0.f;
+      if(jj >= 0 && jj < P.n_ns) {
+        float w = P.win[jj];
+        int ia2 = cA + jj - hw;
+        if(ia2 >= 0 && ia2 < ny_b) va = exc[ia2] * w;
+        if(hasB) { int ib2 = cB + jj - hw; if(ib2 >= 0 && ib2 < ny_b) vb = exc[ib2] * w; }
+      }
+      bufa[j] = make_float2(va, vb);
     }
     __syncthreads();
-    float peak = wmax[0];
-    for(int w = 1; w < (nth >> 5); w ++) peak = fmaxf(peak, wmax[w]);
-    if(peak < -100.f) continue;        // uniform: -100 dB floor, layer0.c:585
+    float pkA = wmax[0], pkB = wmax[32];
+    for(int w = 1; w < (nth >> 5); w ++) { pkA = fmaxf(pkA, wmax[w]); pkB = fmaxf(pkB, wmax[32 + w]); }
+    const bool doA = ! (pkA < -100.f);              // -100 dB floor, layer0.c:585
+    const bool doB = hasB && ! (pkB < -100.f);
+    if(! doA && ! doB) continue;                    // uniform
 
     float2* X = block_fft<false>(bufa, bufb, P.lg_nfft, P.tw, nfft);
     float2* Y = (X == bufa) ? bufb : bufa;
 
-    // ---- PSD (dsputils.c:237-244)
-    for(int k = tid; k < nspec; k += nth) {
-      float2 v = X[k];
-      float pw = v.x * v.x + v.y * v.y;
-      pbuf[k] = pw / P.wsqr;
+    // ---- separate the two spectra; PSDs (dsputils.c:237-244). A_k stays in X[k], B_k in X[nfft-k].
+    for(int k = tid; k <= half; k += nth) {
+      float2 zk = X[k];
+      float2 A, B;
+      if(k == 0 || k == half) { A = make_float2(zk.x, 0.f); B = make_float2(zk.y, 0.f); X[k] = make_float2(zk.x, zk.y); }
+      else {
+        float2 zn = X[nfft - k];
+        A = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+        B = make_float2(0.5f * (zk.y + zn.y), 0.5f * (zn.x - zk.x));
+        X[k] = A; X[nfft - k] = B;
+      }
+      pbuf[k] = (A.x * A.x + A.y * A.y) / P.wsqr;
+      pbuf[nspec + k] = (B.x * B.x + B.y * B.y) / P.wsqr;
     }
     __syncthreads();
-    // ---- gain: target PSD / smoothed measured PSD (layer0.c:597-612)
+    // ---- gains: target PSD / smoothed measured PSD (layer0.c:597-612); re-pack W = A' + i B'
     for(int k = tid; k < nspec - 1; k += nth) {
       int l = max(0, k - 3), u = min(nspec - 1, k + 3);
-      float sm = 0.f;
-      for(int q = l; q <= u; q ++) sm += pbuf[q];
-      float envk = sm / (float)(u - l + 1);                  // moving_avg(psd, nspec, 3)
+      float smA = 0.f, smB = 0.f;
+      for(int q = l; q <= u; q ++) { smA += pbuf[q]; smB += pbuf[nspec + q]; }
+      const float cnt = (float)(u - l + 1);
       int pl = P.psd_lo[k]; float pr = P.psd_r[k];
-      float hdb = spsd[pl];
-      if(pr != 0.f) hdb = hdb + (spsd[pl + 1] - hdb) * pr;    // interp1 on the dB envelope
-      float denom = envk * 44100.f / P.fs + 1e-8f;
-      float H = expf(hdb * (2.3025851f / 20.0f)) / sqrtf(denom);
-      float2 v = X[k];
-      v.x *= H; v.y *= H;
-      X[k] = v;
-      if(k > 0) X[nfft - k] = make_float2(v.x, -v.y);         // complete_symm / complete_asymm
-      if(k == nspec - 2) X[nspec - 1] = make_float2(v.x, v.y); // Nyquist bin copies bin nspec-2
+      float hA = spsd[pl], hB = spsd[npsd + pl];
+      if(pr != 0.f) { hA = hA + (spsd[pl + 1] - hA) * pr; hB = hB + (spsd[npsd + pl + 1] - hB) * pr; }
+      float HA = doA ? expf(hA * (2.3025851f / 20.0f)) / sqrtf(smA / cnt * 44100.f / P.fs + 1e-8f) : 0.f;
+      float HB = doB ? expf(hB * (2.3025851f / 20.0f)) / sqrtf(smB / cnt * 44100.f / P.fs + 1e-8f) : 0.f;
+      float2 A, B;
+      if(k == 0) { float2 z0 = X[0]; A = make_float2(z0.x * HA, 0.f); B = make_float2(z0.y * HB, 0.f); }
+      else { float2 a0 = X[k], b0 = X[nfft - k]; A = make_float2(a0.x * HA, a0.y * HA); B = make_float2(b0.x * HB, b0.y * HB); }
+      Y[k] = make_float2(A.x - B.y, A.y + B.x);
+      if(k > 0) Y[nfft - k] = make_float2(A.x + B.y, B.x - A.y);   // conj(A') + i conj(B')
+      if(k == nspec - 2) Y[half] = make_float2(A.x, B.x);            // Nyquist bin copies bin nspec-2
     }
     __syncthreads();
-    float2* T = block_fft<true>(X, Y, P.lg_nfft, P.tw, nfft);
-    // ---- scale, fades (layer0.c:616-619), accumulate (layer0.c:620-624)
-    const float inv = 1.0f / (float)nfft;
-    for(int j = tid; j < nfft; j += nth) {
-      float v = T[j].x * inv;
-      if(j < 16) v *= (float)j / 16.f;
-      if(j >= nfft - 16) v = (float)((double)v * (1.0 - (double)((float)(nfft - 1 - j) / 16.f)));
-      int idx = center + j - half;
-      if(idx >= oa && idx < ob && idx < ny_b) acc[idx - oa] += v;
+    float2* T = block_fft<true>(Y, X, P.lg_nfft, P.tw, nfft);
+    // ---- scale, fades (layer0.c:616-619), accumulate in frame order (layer0.c:620-624)
+    for(int h = 0; h < 2; h ++) {
+      if(h == 1) __syncthreads();
+      if(h == 0 ? ! doA : ! doB) continue;
+      const int center = h == 0 ? cA : cB;
+      for(int j = tid; j < nfft; j += nth) {
+        float v = (h == 0 ? T[j].x : T[j].y) * inv;
+        if(j < 16) v *= (float)j / 16.f;
+        if(j >= nfft - 16) v = (float)((double)v * (1.0 - (double)((float)(nfft - 1 - j) / 16.f)));
+        int idx = center + j - half;
+        if(idx >= oa && idx < ob && idx < ny_b) acc[idx - oa] += v;
+      }
     }
   }
   __syncthreads();
@@ -530,7 +575,7 @@ __global__ void __launch_bounds__(SHAPE_THREADS) noise_shape_kernel(ShapeParams 
 }
 
 static inline size_t shape_smem_bytes(int nfft, int seg, int npsd, int nspec) {
-  return (size_t)nfft * 16 + (size_t)(seg + npsd + nspec + 32) * 4 + 16;
+  return (size_t)nfft * 16 + (size_t)(seg + 2 * npsd + 2 * nspec + 64) * 4 + 16;
 }
 
 static inline int launch_noise_shape(const ShapeParams& P, int nutt, cudaStream_t st) {
