@@ -1,0 +1,646 @@
+/*
+  Host side of the drop-in API (include/llsm.h): the container / frame / chunk data model in plain
+  C, and llsm_analyze / llsm_synthesize as packers around the batched CUDA entry points of
+  include/llsm_b200.h. Behavioural contract = the reference's container.c, frame.c and the
+  option / chunk helpers of layer0.c (cited per function); written against that contract, not
+  copied from it.
+*/
+#include "../../include/llsm.h"
+#include "../../include/llsm_b200.h"
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+#include <math.h>
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+static __thread char g_compat_err[256] = "";
+static void set_err(const char* msg) { snprintf(g_compat_err, sizeof(g_compat_err), "%s", msg); }
+const char* llsm_last_error(void) {
+  return g_compat_err[0] ? g_compat_err : llsm_b200_last_error();
+}
+
+/* ------------------------------------------------------------------ boxed values ---------------- */
+/* fparray: an int length lives in the 4 bytes before the returned pointer (container.c:36-40). */
+FP_TYPE* llsm_create_fp(FP_TYPE x) { FP_TYPE* p = malloc(sizeof(FP_TYPE)); *p = x; return p; }
+int* llsm_create_int(int x) { int* p = malloc(sizeof(int)); *p = x; return p; }
+FP_TYPE* llsm_create_fparray(int size) {
+  int* raw = calloc(1, sizeof(int) + sizeof(FP_TYPE) * (size_t)(size > 0 ? size : 0));
+  raw[0] = size;
+  return (FP_TYPE*)(raw + 1);
+}
+FP_TYPE* llsm_copy_fp(FP_TYPE* src) { return llsm_create_fp(src[0]); }
+int* llsm_copy_int(int* src) { return llsm_create_int(src[0]); }
+int llsm_fparray_length(FP_TYPE* src) { return ((int*)src)[-1]; }
+FP_TYPE* llsm_copy_fparray(FP_TYPE* src) {
+  int n = llsm_fparray_length(src);
+  FP_TYPE* dst = llsm_create_fparray(n);
+  if(n > 0) memcpy(dst, src, sizeof(FP_TYPE) * (size_t)n);
+  return dst;
+}
+void llsm_delete_fp(FP_TYPE* dst) { free(dst); }
+void llsm_delete_int(int* dst) { free(dst); }
+void llsm_delete_fparray(FP_TYPE* dst) { if(dst != NULL) free((int*)dst - 1); }
+
+/* ------------------------------------------------------------------ container ------------------- */
+llsm_container* llsm_create_container(int nmember) {
+  llsm_container* c = malloc(sizeof(llsm_container));
+  size_t n = (size_t)(nmember > 0 ? nmember : 0);
+  c -> nmember = (int)n;
+  c -> members = calloc(n ? n : 1, sizeof(void*));
+  c -> destructors = calloc(n ? n : 1, sizeof(llsm_fdestructor));
+  c -> copyctors = calloc(n ? n : 1, sizeof(llsm_fcopy));
+  return c;
+}
+
+static void container_grow(llsm_container* c, int n) {
+  if(n <= c -> nmember) return;
+  c -> members = realloc(c -> members, sizeof(void*) * (size_t)n);
+  c -> destructors = realloc(c -> destructors, sizeof(llsm_fdestructor) * (size_t)n);
+  c -> copyctors = realloc(c -> copyctors, sizeof(llsm_fcopy) * (size_t)n);
+  for(int i = c -> nmember; i < n; i ++) {
+    c -> members[i] = NULL; c -> destructors[i] = NULL; c -> copyctors[i] = NULL;
+  }
+  c -> nmember = n;
+}
+
+void* llsm_container_get(llsm_container* src, int index) {
+  if(src == NULL || index < 0 || index >= src -> nmember) return NULL;
+  return src -> members[index];
+}
+
+/* removing calls the member's destructor when one was attached (container.c:148-156) */
+void llsm_container_remove(llsm_container* dst, int index) {
+  if(index < 0 || index >= dst -> nmember || dst -> members[index] == NULL) return;
+  if(dst -> destructors[index] != NULL) dst -> destructors[index](dst -> members[index]);
+  dst -> members[index] = NULL;
+  dst -> destructors[index] = NULL;
+  dst -> copyctors[index] = NULL;
+}
+
+/* attach replaces (and destroys) the previous member; attaching NULL is the "remove" idiom
+   (container.c:126-146, test/test-llsmrt.c:93) */
+void llsm_container_attach_(llsm_container* dst, int index, void* ptr,
+  llsm_fdestructor dtor, llsm_fcopy copyctor) {
+  container_grow(dst, index + 1);
+  llsm_container_remove(dst, index);
+  dst -> members[index] = ptr;
+  dst -> destructors[index] = dtor;
+  dst -> copyctors[index] = copyctor;
+}
+
+/* deep copy where a copy constructor exists, aliasing otherwise -- and an aliased member is NOT
+   owned by the copy (container.c:82-93; aliasing is pinned by test/test-structs.c:34-35) */
+llsm_container* llsm_copy_container(llsm_container* src) {
+  llsm_container* c = llsm_create_container(src -> nmember);
+  for(int i = 0; i < src -> nmember; i ++) {
+    c -> copyctors[i] = src -> copyctors[i];
+    if(src -> copyctors[i] != NULL) {
+      c -> members[i] = src -> copyctors[i](src -> members[i]);
+      c -> destructors[i] = src -> destructors[i];
+    } else
+      c -> members[i] = src -> members[i];
+  }
+  return c;
+}
+
+/* in-place variant: empties dst first; unlike llsm_copy_container, shallow-copied members keep
+   the source's destructor (container.c:95-107) */
+void llsm_copy_container_inplace(llsm_container* dst, llsm_container* src) {
+  for(int i = 0; i < dst -> nmember; i ++) llsm_container_remove(dst, i);
+  for(int i = 0; i < src -> nmember; i ++) {
+    if(src -> members[i] == NULL) continue;
+    void* m = src -> copyctors[i] != NULL ? src -> copyctors[i](src -> members[i]) : src -> members[i];
+    llsm_container_attach_(dst, i, m, src -> destructors[i], src -> copyctors[i]);
+  }
+}
+
+void llsm_delete_container(llsm_container* dst) {
+  if(dst == NULL) return;
+  for(int i = 0; i < dst -> nmember; i ++)
+    if(dst -> destructors[i] != NULL) dst -> destructors[i](dst -> members[i]);
+  free(dst -> members); free(dst -> destructors); free(dst -> copyctors);
+  free(dst);
+}
+
+/* ------------------------------------------------------------------ hm / nm frames -------------- */
+static FP_TYPE wrap_phase(double p) {           /* (-pi, pi] */
+  double q = p - 2.0 * M_PI * floor((p + M_PI) / (2.0 * M_PI));
+  if(q <= -M_PI) q += 2.0 * M_PI;
+  return (FP_TYPE)q;
+}
+
+llsm_hmframe* llsm_create_hmframe(int nhar) {
+  llsm_hmframe* h = malloc(sizeof(llsm_hmframe));
+  size_t n = (size_t)(nhar > 0 ? nhar : 0);
+  h -> nhar = nhar;
+  h -> ampl = calloc(n ? n : 1, sizeof(FP_TYPE));
+  h -> phse = calloc(n ? n : 1, sizeof(FP_TYPE));
+  return h;
+}
+
+void llsm_copy_hmframe_inplace(llsm_hmframe* dst, llsm_hmframe* src) {
+  size_t bytes = sizeof(FP_TYPE) * (size_t)(src -> nhar > 0 ? src -> nhar : 0);
+  if(dst -> nhar < src -> nhar) {
+    dst -> ampl = realloc(dst -> ampl, bytes);
+    dst -> phse = realloc(dst -> phse, bytes);
+  }
+  if(bytes) { memcpy(dst -> ampl, src -> ampl, bytes); memcpy(dst -> phse, src -> phse, bytes); }
+  dst -> nhar = src -> nhar;
+}
+
+llsm_hmframe* llsm_copy_hmframe(llsm_hmframe* src) {
+  llsm_hmframe* h = llsm_create_hmframe(src -> nhar);
+  llsm_copy_hmframe_inplace(h, src);
+  return h;
+}
+
+void llsm_delete_hmframe(llsm_hmframe* dst) {
+  if(dst == NULL) return;
+  free(dst -> ampl); free(dst -> phse); free(dst);
+}
+
+/* phase of harmonic k (1-based) advances by k * theta, wrapped (frame.c:57-60) */
+void llsm_hmframe_phaseshift(llsm_hmframe* dst, FP_TYPE theta) {
+  for(int k = 0; k < dst -> nhar; k ++)
+    dst -> phse[k] = wrap_phase((FP_TYPE)(dst -> phse[k] + theta * (k + 1.0)));
+}
+
+/* noise-equivalent power of each harmonic, a^2 / 2, optionally in dB (frame.c:62-69) */
+FP_TYPE* llsm_hmframe_harpsd(llsm_hmframe* src, int db_scale) {
+  FP_TYPE* psd = calloc(src -> nhar > 0 ? src -> nhar : 1, sizeof(FP_TYPE));
+  for(int k = 0; k < src -> nhar; k ++) {
+    psd[k] = src -> ampl[k] * src -> ampl[k] * 0.5;
+    if(db_scale) psd[k] = 10.0 * log10(psd[k]);
+  }
+  return psd;
+}
+
+/* defaults: psd -120 dB, edc 1e-5 (frame.c:71-90) */
+llsm_nmframe* llsm_create_nmframe(int nchannel, int nhar_e, int npsd) {
+  llsm_nmframe* n = malloc(sizeof(llsm_nmframe));
+  n -> nchannel = nchannel; n -> npsd = npsd;
+  n -> eenv = calloc(nchannel > 0 ? nchannel : 1, sizeof(llsm_hmframe*));
+  n -> edc = calloc(nchannel > 0 ? nchannel : 1, sizeof(FP_TYPE));
+  n -> psd = calloc(npsd > 0 ? npsd : 1, sizeof(FP_TYPE));
+  for(int j = 0; j < npsd; j ++) n -> psd[j] = -120.0;
+  for(int c = 0; c < nchannel; c ++) { n -> eenv[c] = llsm_create_hmframe(nhar_e); n -> edc[c] = 1e-5; }
+  return n;
+}
+
+void llsm_copy_nmframe_inplace(llsm_nmframe* dst, llsm_nmframe* src) {
+  if(dst -> npsd < src -> npsd) dst -> psd = realloc(dst -> psd, sizeof(FP_TYPE) * (size_t)src -> npsd);
+  memcpy(dst -> psd, src -> psd, sizeof(FP_TYPE) * (size_t)src -> npsd);
+  dst -> npsd = src -> npsd;
+  if(dst -> nchannel < src -> nchannel) {
+    dst -> edc = realloc(dst -> edc, sizeof(FP_TYPE) * (size_t)src -> nchannel);
+    dst -> eenv = realloc(dst -> eenv, sizeof(llsm_hmframe*) * (size_t)src -> nchannel);
+    for(int c = dst -> nchannel; c < src -> nchannel; c ++) dst -> eenv[c] = llsm_create_hmframe(0);
+  } else
+    for(int c = src -> nchannel; c < dst -> nchannel; c ++) llsm_delete_hmframe(dst -> eenv[c]);
+  for(int c = 0; c < src -> nchannel; c ++) {
+    dst -> edc[c] = src -> edc[c];
+    llsm_copy_hmframe_inplace(dst -> eenv[c], src -> eenv[c]);
+  }
+  dst -> nchannel = src -> nchannel;
+}
+
+llsm_nmframe* llsm_copy_nmframe(llsm_nmframe* src) {
+  llsm_nmframe* n = llsm_create_nmframe(src -> nchannel, 0, src -> npsd);
+  llsm_copy_nmframe_inplace(n, src);
+  return n;
+}
+
+void llsm_delete_nmframe(llsm_nmframe* dst) {
+  if(dst == NULL) return;
+  for(int c = 0; c < dst -> nchannel; c ++) llsm_delete_hmframe(dst -> eenv[c]);
+  free(dst -> eenv); free(dst -> edc); free(dst -> psd); free(dst);
+}
+
+/* ------------------------------------------------------------------ effects --------------------- */
+llsm_pbpeffect* llsm_create_pbpeffect(llsm_fgfm modifier, void* info) {
+  llsm_pbpeffect* e = malloc(sizeof(llsm_pbpeffect));
+  e -> modifier = modifier; e -> info = info;
+  return e;
+}
+llsm_pbpeffect* llsm_copy_pbpeffect(llsm_pbpeffect* src) {
+  return llsm_create_pbpeffect(src -> modifier, src -> info);
+}
+void llsm_delete_pbpeffect(llsm_pbpeffect* dst) { free(dst); }
+
+/* ------------------------------------------------------------------ frames ---------------------- */
+static void* copy_one_fp(void* p) { return llsm_create_fp(((FP_TYPE*)p)[0]); }
+
+/* a frame = container {F0 = 0, HM(nhar), NM(nchannel, nhar_e, npsd)} (frame.c:137-150) */
+llsm_container* llsm_create_frame(int nhar, int nchannel, int nhar_e, int npsd) {
+  llsm_container* f = llsm_create_container(3);
+  llsm_container_attach(f, LLSM_FRAME_F0, llsm_create_fp(0), free, copy_one_fp);
+  llsm_container_attach(f, LLSM_FRAME_HM, llsm_create_hmframe(nhar), llsm_delete_hmframe, llsm_copy_hmframe);
+  llsm_container_attach(f, LLSM_FRAME_NM, llsm_create_nmframe(nchannel, nhar_e, npsd),
+    llsm_delete_nmframe, llsm_copy_nmframe);
+  return f;
+}
+
+/* HM, every noise-envelope model and the source phases rotate together (frame.c:152-166) */
+void llsm_frame_phaseshift(llsm_container* dst, FP_TYPE theta) {
+  llsm_hmframe* hm = llsm_container_get(dst, LLSM_FRAME_HM);
+  llsm_nmframe* nm = llsm_container_get(dst, LLSM_FRAME_NM);
+  FP_TYPE* vs = llsm_container_get(dst, LLSM_FRAME_VSPHSE);
+  if(hm != NULL) llsm_hmframe_phaseshift(hm, theta);
+  if(nm != NULL) for(int c = 0; c < nm -> nchannel; c ++) llsm_hmframe_phaseshift(nm -> eenv[c], theta);
+  if(vs != NULL) {
+    int n = llsm_fparray_length(vs);
+    for(int k = 0; k < n; k ++) vs[k] = wrap_phase((FP_TYPE)(vs[k] + theta * (k + 1.0)));
+  }
+}
+
+/* relative phase shift: subtract the first harmonic's phase (frame.c:168-178) */
+void llsm_frame_phasesync_rps(llsm_container* dst, int layer1_based) {
+  llsm_hmframe* hm = llsm_container_get(dst, LLSM_FRAME_HM);
+  FP_TYPE* vs = llsm_container_get(dst, LLSM_FRAME_VSPHSE);
+  FP_TYPE ref = 0;
+  if(layer1_based && vs != NULL && llsm_fparray_length(vs) > 0) ref = vs[0];
+  else if(hm != NULL && hm -> nhar > 0) ref = hm -> phse[0];
+  llsm_frame_phaseshift(dst, -ref);
+}
+
+int llsm_frame_checklayer0(llsm_container* src) {      /* frame.c:211-218 */
+  FP_TYPE* f0 = llsm_container_get(src, LLSM_FRAME_F0);
+  if(f0 == NULL || llsm_container_get(src, LLSM_FRAME_NM) == NULL) return 0;
+  if(f0[0] != 0 && llsm_container_get(src, LLSM_FRAME_HM) == NULL) return 0;
+  return 1;
+}
+
+int llsm_frame_checklayer1(llsm_container* src) {      /* frame.c:220-229 */
+  FP_TYPE* f0 = llsm_container_get(src, LLSM_FRAME_F0);
+  if(f0 == NULL || llsm_container_get(src, LLSM_FRAME_RD) == NULL ||
+     llsm_container_get(src, LLSM_FRAME_NM) == NULL) return 0;
+  if(f0[0] > 0 && (llsm_container_get(src, LLSM_FRAME_VTMAGN) == NULL ||
+     llsm_container_get(src, LLSM_FRAME_VSPHSE) == NULL)) return 0;
+  return 1;
+}
+
+int llsm_conf_checklayer0(llsm_container* src) {       /* layer0.c:513-523 */
+  const int need[] = {LLSM_CONF_NFRM, LLSM_CONF_THOP, LLSM_CONF_NPSD, LLSM_CONF_FNYQ,
+    LLSM_CONF_NCHANNEL, LLSM_CONF_CHANFREQ};
+  for(size_t i = 0; i < sizeof(need) / sizeof(need[0]); i ++)
+    if(llsm_container_get(src, need[i]) == NULL) return 0;
+  return 1;
+}
+
+int llsm_conf_checklayer1(llsm_container* src) {
+  return llsm_conf_checklayer0(src) && llsm_container_get(src, LLSM_CONF_NSPEC) != NULL &&
+    llsm_container_get(src, LLSM_CONF_LIPRADIUS) != NULL;
+}
+
+/* needs the deprecated NOSWARP entry that llsm_aoptions_toconf never creates (frame.c:186-188):
+   always NULL for configurations made by this API, as in the reference */
+FP_TYPE* llsm_frame_compute_snr(llsm_container* src, llsm_container* conf, int as_aperiodicity) {
+  (void)src; (void)conf; (void)as_aperiodicity;
+  return NULL;
+}
+
+/* layer-1 conversions are outside the accelerated path of this round */
+void llsm_frame_tolayer0(llsm_container* dst, llsm_container* conf) { (void)dst; (void)conf; set_err("layer 1 not built"); }
+void llsm_chunk_tolayer1(llsm_chunk* dst, int nfft) { (void)dst; (void)nfft; set_err("layer 1 not built"); }
+void llsm_chunk_tolayer0(llsm_chunk* dst) { (void)dst; set_err("layer 1 not built"); }
+
+/* ------------------------------------------------------------------ options --------------------- */
+llsm_aoptions* llsm_create_aoptions(void) {            /* defaults of layer0.c:27-43 */
+  llsm_aoptions* o = malloc(sizeof(llsm_aoptions));
+  o -> thop = 0.005; o -> maxnhar = 100; o -> maxnhar_e = 4; o -> npsd = 256; o -> nchannel = 4;
+  o -> chanfreq = calloc(3, sizeof(FP_TYPE));
+  o -> chanfreq[0] = 2000.0; o -> chanfreq[1] = 4000.0; o -> chanfreq[2] = 8000.0;
+  o -> lip_radius = 1.5; o -> f0_refine = 1; o -> hm_method = LLSM_AOPTION_HMCZT; o -> rel_winsize = 4.0;
+  return o;
+}
+
+void llsm_delete_aoptions(llsm_aoptions* dst) {
+  if(dst == NULL) return;
+  free(dst -> chanfreq); free(dst);
+}
+
+llsm_container* llsm_aoptions_toconf(llsm_aoptions* src, FP_TYPE fnyq) {   /* layer0.c:51-76 */
+  llsm_container* c = llsm_create_container(10);
+  llsm_container_attach(c, LLSM_CONF_NFRM, llsm_create_int(0), llsm_delete_int, llsm_copy_int);
+  llsm_container_attach(c, LLSM_CONF_THOP, llsm_create_fp(src -> thop), llsm_delete_fp, llsm_copy_fp);
+  llsm_container_attach(c, LLSM_CONF_MAXNHAR, llsm_create_int(src -> maxnhar), llsm_delete_int, llsm_copy_int);
+  llsm_container_attach(c, LLSM_CONF_MAXNHAR_E, llsm_create_int(src -> maxnhar_e), llsm_delete_int, llsm_copy_int);
+  llsm_container_attach(c, LLSM_CONF_NPSD, llsm_create_int(src -> npsd), llsm_delete_int, llsm_copy_int);
+  llsm_container_attach(c, LLSM_CONF_FNYQ, llsm_create_fp(fnyq), llsm_delete_fp, llsm_copy_fp);
+  llsm_container_attach(c, LLSM_CONF_NCHANNEL, llsm_create_int(src -> nchannel), llsm_delete_int, llsm_copy_int);
+  llsm_container_attach(c, LLSM_CONF_LIPRADIUS, llsm_create_fp(src -> lip_radius), llsm_delete_fp, llsm_copy_fp);
+  FP_TYPE* cf = llsm_create_fparray(src -> nchannel - 1);
+  for(int i = 0; i < src -> nchannel - 1; i ++) cf[i] = src -> chanfreq[i];
+  llsm_container_attach(c, LLSM_CONF_CHANFREQ, cf, llsm_delete_fparray, llsm_copy_fparray);
+  return c;
+}
+
+llsm_soptions* llsm_create_soptions(FP_TYPE fs) {      /* layer0.c:78-87 */
+  llsm_soptions* o = malloc(sizeof(llsm_soptions));
+  o -> fs = fs; o -> use_iczt = 1; o -> use_l1 = 0; o -> iczt_param_a = 0.275; o -> iczt_param_b = 2.26;
+  return o;
+}
+void llsm_delete_soptions(llsm_soptions* dst) { free(dst); }
+
+void llsm_delete_output(llsm_output* dst) {
+  if(dst == NULL) return;
+  free(dst -> y); free(dst -> y_sin); free(dst -> y_noise); free(dst);
+}
+
+/* ------------------------------------------------------------------ chunks ---------------------- */
+llsm_chunk* llsm_create_chunk(llsm_container* conf, int init_frames) {      /* container.c:158-174 */
+  int* nfrm = llsm_container_get(conf, LLSM_CONF_NFRM);
+  int* nchannel = llsm_container_get(conf, LLSM_CONF_NCHANNEL);
+  int* npsd = llsm_container_get(conf, LLSM_CONF_NPSD);
+  if(nchannel == NULL || npsd == NULL) return NULL;
+  llsm_chunk* ck = malloc(sizeof(llsm_chunk));
+  ck -> conf = llsm_copy_container(conf);
+  ck -> frames = NULL;
+  if(nfrm != NULL) {
+    ck -> frames = calloc(*nfrm > 0 ? *nfrm : 1, sizeof(llsm_container*));
+    if(init_frames)
+      for(int i = 0; i < *nfrm; i ++) ck -> frames[i] = llsm_create_frame(0, *nchannel, 0, *npsd);
+  }
+  return ck;
+}
+
+llsm_chunk* llsm_copy_chunk(llsm_chunk* src) {
+  llsm_chunk* ck = llsm_create_chunk(src -> conf, 0);
+  int* nfrm = llsm_container_get(src -> conf, LLSM_CONF_NFRM);
+  if(ck != NULL && nfrm != NULL)
+    for(int i = 0; i < *nfrm; i ++) ck -> frames[i] = llsm_copy_container(src -> frames[i]);
+  return ck;
+}
+
+void llsm_delete_chunk(llsm_chunk* dst) {
+  if(dst == NULL) return;
+  int* nfrm = llsm_container_get(dst -> conf, LLSM_CONF_NFRM);
+  if(nfrm != NULL && dst -> frames != NULL)
+    for(int i = 0; i < *nfrm; i ++) llsm_delete_container(dst -> frames[i]);
+  llsm_delete_container(dst -> conf);
+  free(dst -> frames);
+  free(dst);
+}
+
+FP_TYPE* llsm_chunk_getf0(llsm_chunk* src, int* dst_nfrm) {                 /* layer0.c:674-685 */
+  int* nfrm = llsm_container_get(src -> conf, LLSM_CONF_NFRM);
+  if(nfrm == NULL) return NULL;
+  FP_TYPE* f0 = calloc(*nfrm > 0 ? *nfrm : 1, sizeof(FP_TYPE));
+  *dst_nfrm = *nfrm;
+  for(int i = 0; i < *nfrm; i ++) {
+    FP_TYPE* v = llsm_container_get(src -> frames[i], LLSM_FRAME_F0);
+    if(v != NULL) f0[i] = v[0];
+  }
+  return f0;
+}
+
+void llsm_chunk_phasesync_rps(llsm_chunk* dst, int layer1_based) {          /* layer0.c:687-692 */
+  int* nfrm = llsm_container_get(dst -> conf, LLSM_CONF_NFRM);
+  if(nfrm == NULL) return;
+  for(int i = 0; i < *nfrm; i ++) llsm_frame_phasesync_rps(dst -> frames[i], layer1_based);
+}
+
+/* add (sign = +1) or remove (-1) the running integral of F0, 2 pi thop cumsum(f0) (layer0.c:694-706;
+   the cumulative sum is accumulated in double and stored as FP_TYPE like the oracle's cumsum) */
+void llsm_chunk_phasepropagate(llsm_chunk* dst, int sign) {
+  int nfrm = 0;
+  FP_TYPE* f0 = llsm_chunk_getf0(dst, & nfrm);
+  FP_TYPE* thop = llsm_container_get(dst -> conf, LLSM_CONF_THOP);
+  if(thop == NULL || f0 == NULL) { free(f0); return; }
+  double acc = 0;
+  for(int i = 0; i < nfrm; i ++) {
+    acc += f0[i];
+    FP_TYPE d = (FP_TYPE)acc;
+    d = (FP_TYPE)(d * (*thop * sign * 2.0 * M_PI));
+    llsm_frame_phaseshift(dst -> frames[i], d);
+  }
+  free(f0);
+}
+
+/* ------------------------------------------------------------------ device context -------------- */
+static llsm_b200_ctx* g_ctx = NULL;
+static llsm_b200_ctx* shared_ctx(void) {
+  if(g_ctx == NULL) {
+    const char* e = getenv("LLSM_B200_DEVICE");
+    g_ctx = llsm_b200_create(e != NULL ? atoi(e) : 0);
+  }
+  return g_ctx;
+}
+
+/* N(0, var) from libc rand(): one Box-Muller cosine branch, two rand() draws per value -- the draw
+   sequence of the reference's llsm_generate_white_noise (dsputils.c:353-361) under the oracle's
+   randn(); keeps y_noise reproducible against the CPU reference for a given srand() state. */
+static FP_TYPE host_randn(void) {
+  double u1 = ((double)rand() + 1.0) / ((double)RAND_MAX + 2.0);
+  double u2 = ((double)rand() + 1.0) / ((double)RAND_MAX + 2.0);
+  return (FP_TYPE)(0.0 + sqrt(1.0) * (sqrt(-2.0 * log(u1)) * cos(2.0 * M_PI * u2)));
+}
+
+static int same_conf(llsm_container* a, llsm_container* b) {
+  const int ints[] = {LLSM_CONF_NFRM, LLSM_CONF_NPSD, LLSM_CONF_NCHANNEL};
+  for(int i = 0; i < 3; i ++)
+    if(*(int*)llsm_container_get(a, ints[i]) != *(int*)llsm_container_get(b, ints[i])) return 0;
+  if(*(FP_TYPE*)llsm_container_get(a, LLSM_CONF_THOP) != *(FP_TYPE*)llsm_container_get(b, LLSM_CONF_THOP)) return 0;
+  FP_TYPE* ca = llsm_container_get(a, LLSM_CONF_CHANFREQ); FP_TYPE* cb = llsm_container_get(b, LLSM_CONF_CHANFREQ);
+  int nch = *(int*)llsm_container_get(a, LLSM_CONF_NCHANNEL);
+  for(int c = 0; c < nch - 1; c ++) if(ca[c] != cb[c]) return 0;
+  return 1;
+}
+
+static int chunk_ok(llsm_chunk* src) {                 /* layer0.c:525-533 */
+  if(src == NULL || ! llsm_conf_checklayer0(src -> conf)) return 0;
+  int nfrm = *(int*)llsm_container_get(src -> conf, LLSM_CONF_NFRM);
+  for(int i = 0; i < nfrm; i ++)
+    if(! llsm_frame_checklayer0(src -> frames[i]) && ! llsm_frame_checklayer1(src -> frames[i])) return 0;
+  return 1;
+}
+
+/* ------------------------------------------------------------------ synthesis ------------------- */
+int llsm_synthesize_batch(llsm_soptions* options, llsm_chunk** src, int n, llsm_output** dst) {
+  g_compat_err[0] = 0;
+  for(int b = 0; b < n; b ++) dst[b] = NULL;
+  if(options == NULL || n < 1) { set_err("bad arguments"); return -1; }
+  for(int b = 0; b < n; b ++) {
+    if(! chunk_ok(src[b])) { set_err("chunk fails the layer-0 integrity check"); return -1; }
+    if(b > 0 && ! same_conf(src[0] -> conf, src[b] -> conf)) {
+      set_err("llsm_synthesize_batch: chunks must share one configuration"); return -1;
+    }
+  }
+  if(options -> use_l1) { set_err("use_l1 (pulse-by-pulse) synthesis is not built into this library yet"); return -1; }
+  llsm_b200_ctx* ctx = shared_ctx();
+  if(ctx == NULL) return -1;
+
+  llsm_container* conf = src[0] -> conf;
+  llsm_b200_conf c; memset(& c, 0, sizeof(c));
+  c.nutt = n;
+  c.nfrm = *(int*)llsm_container_get(conf, LLSM_CONF_NFRM);
+  c.npsd = *(int*)llsm_container_get(conf, LLSM_CONF_NPSD);
+  c.nchannel = *(int*)llsm_container_get(conf, LLSM_CONF_NCHANNEL);
+  c.thop = *(FP_TYPE*)llsm_container_get(conf, LLSM_CONF_THOP);
+  c.fs = options -> fs;
+  FP_TYPE* lip = llsm_container_get(conf, LLSM_CONF_LIPRADIUS);
+  c.lip_radius = lip != NULL ? *lip : 1.5f;
+  FP_TYPE* cf = llsm_container_get(conf, LLSM_CONF_CHANFREQ);
+  if(c.nchannel < 1 || c.nchannel > LLSM_B200_MAXCHANNEL || c.nfrm < 1) { set_err("unsupported configuration"); return -1; }
+  for(int i = 0; i < c.nchannel - 1; i ++) c.chanfreq[i] = cf[i];
+
+  /* row lengths = the largest harmonic counts present */
+  int maxnhar = 1, maxnhar_e = 1, has_res = 0;
+  for(int b = 0; b < n; b ++) for(int i = 0; i < c.nfrm; i ++) {
+    llsm_container* f = src[b] -> frames[i];
+    llsm_hmframe* hm = llsm_container_get(f, LLSM_FRAME_HM);
+    llsm_nmframe* nm = llsm_container_get(f, LLSM_FRAME_NM);
+    if(hm != NULL && hm -> nhar > maxnhar) maxnhar = hm -> nhar;
+    if(nm -> nchannel != c.nchannel || nm -> npsd != c.npsd) { set_err("frame / conf size mismatch"); return -1; }
+    for(int ch = 0; ch < c.nchannel; ch ++) if(nm -> eenv[ch] -> nhar > maxnhar_e) maxnhar_e = nm -> eenv[ch] -> nhar;
+    if(llsm_container_get(f, LLSM_FRAME_PSDRES) != NULL) has_res = 1;
+  }
+  if(maxnhar > 2048) maxnhar = 2048;                    /* layer0.c:119 */
+  c.maxnhar = maxnhar; c.maxnhar_e = maxnhar_e;
+
+  const size_t BF = (size_t)n * c.nfrm;
+  float* f0 = calloc(BF, 4); int* nhar = calloc(BF, 4);
+  float* ampl = calloc(BF * maxnhar, 4); float* phse = calloc(BF * maxnhar, 4);
+  float* psd = calloc(BF * c.npsd, 4); float* psdres = has_res ? calloc(BF * c.npsd, 4) : NULL;
+  float* edc = calloc(BF * c.nchannel, 4); int* enhar = calloc(BF * c.nchannel, 4);
+  float* eampl = calloc(BF * c.nchannel * maxnhar_e, 4); float* ephse = calloc(BF * c.nchannel * maxnhar_e, 4);
+  const double resbias = 0.375 / 2.3025851 * 10.0;
+  for(int b = 0; b < n; b ++) for(int i = 0; i < c.nfrm; i ++) {
+    size_t r = (size_t)b * c.nfrm + i;
+    llsm_container* f = src[b] -> frames[i];
+    FP_TYPE* pf0 = llsm_container_get(f, LLSM_FRAME_F0);
+    llsm_hmframe* hm = llsm_container_get(f, LLSM_FRAME_HM);
+    llsm_nmframe* nm = llsm_container_get(f, LLSM_FRAME_NM);
+    FP_TYPE* res = llsm_container_get(f, LLSM_FRAME_PSDRES);
+    f0[r] = pf0[0];
+    if(pf0[0] != 0 && hm != NULL) {
+      int k = hm -> nhar < maxnhar ? hm -> nhar : maxnhar;
+      nhar[r] = k;
+      memcpy(ampl + r * maxnhar, hm -> ampl, 4 * (size_t)k);
+      memcpy(phse + r * maxnhar, hm -> phse, 4 * (size_t)k);
+    }
+    memcpy(psd + r * c.npsd, nm -> psd, 4 * (size_t)c.npsd);
+    if(has_res) {
+      /* a frame without PSDRES adds nothing (layer0.c:599-601): encode as the bias itself */
+      for(int j = 0; j < c.npsd; j ++) psdres[r * c.npsd + j] = res != NULL ? res[j] : (float)resbias;
+    }
+    for(int ch = 0; ch < c.nchannel; ch ++) {
+      size_t e = r * c.nchannel + ch;
+      edc[e] = nm -> edc[ch];
+      int k = nm -> eenv[ch] -> nhar;
+      enhar[e] = k;
+      memcpy(eampl + e * maxnhar_e, nm -> eenv[ch] -> ampl, 4 * (size_t)k);
+      memcpy(ephse + e * maxnhar_e, nm -> eenv[ch] -> phse, 4 * (size_t)k);
+    }
+  }
+
+  const int ny = llsm_b200_output_length(c.nfrm, c.thop, c.fs);
+  const int nt = llsm_b200_template_length(ny);
+  float* white = malloc(sizeof(float) * (size_t)n * c.nchannel * nt);
+  for(int b = 0; b < n; b ++) for(int ch = 0; ch < c.nchannel; ch ++) {
+    /* llsm_synthesize_noise_excitation stops drawing at the first channel above Nyquist (layer0.c:543) */
+    FP_TYPE fmin = ch == 0 ? 0 : cf[ch - 1];
+    float* w = white + ((size_t)b * c.nchannel + ch) * nt;
+    if(fmin >= c.fs / 2.0) { memset(w, 0, sizeof(float) * nt); continue; }
+    int ntemplate = ny < 20000 ? ny : 20000;
+    int ndraw = (ntemplate + 128) < 20000 ? (ntemplate + 128) : 20000;   /* dsputils.c:355-359 */
+    for(int j = 0; j < ndraw; j ++) w[j] = host_randn();
+    for(int j = ndraw; j < nt; j ++) w[j] = w[(j - ndraw) % ndraw];
+  }
+
+  float* y = malloc(sizeof(float) * (size_t)n * ny);
+  float* ys = malloc(sizeof(float) * (size_t)n * ny);
+  float* yn = malloc(sizeof(float) * (size_t)n * ny);
+  llsm_b200_frames fr = {NULL, f0, nhar, ampl, phse, psd, psdres, edc, enhar, eampl, ephse};
+  llsm_b200_soptions so; memset(& so, 0, sizeof(so));
+  so.use_iczt = options -> use_iczt; so.iczt_param_a = options -> iczt_param_a; so.iczt_param_b = options -> iczt_param_b;
+  so.white = white; so.seed = 0;
+  llsm_b200_output out = {y, ys, yn, ny};
+  int rc = llsm_b200_synthesize_l0_host(ctx, & c, & fr, & so, & out);
+  if(rc == 0) {
+    for(int b = 0; b < n; b ++) {
+      llsm_output* o = malloc(sizeof(llsm_output));
+      o -> ny = ny; o -> fs = options -> fs;
+      o -> y = malloc(sizeof(FP_TYPE) * (size_t)ny); o -> y_sin = malloc(sizeof(FP_TYPE) * (size_t)ny);
+      o -> y_noise = malloc(sizeof(FP_TYPE) * (size_t)ny);
+      memcpy(o -> y, y + (size_t)b * ny, 4 * (size_t)ny);
+      memcpy(o -> y_sin, ys + (size_t)b * ny, 4 * (size_t)ny);
+      memcpy(o -> y_noise, yn + (size_t)b * ny, 4 * (size_t)ny);
+      dst[b] = o;
+    }
+  }
+  free(f0); free(nhar); free(ampl); free(phse); free(psd); free(psdres); free(edc); free(enhar);
+  free(eampl); free(ephse); free(white); free(y); free(ys); free(yn);
+  return rc;
+}
+
+llsm_output* llsm_synthesize(llsm_soptions* options, llsm_chunk* src) {     /* layer0.c:636-664 */
+  llsm_output* out = NULL;
+  if(llsm_synthesize_batch(options, & src, 1, & out) != 0) return NULL;
+  return out;
+}
+
+/* ------------------------------------------------------------------ analysis -------------------- */
+llsm_chunk* llsm_analyze(llsm_aoptions* options, FP_TYPE* x, int nx, FP_TYPE fs, FP_TYPE* f0,
+  int nfrm, FP_TYPE** x_ap) {                                               /* layer0.c:478-511 */
+  g_compat_err[0] = 0;
+  if(options == NULL || x == NULL || f0 == NULL || nx < 1 || nfrm < 1) { set_err("bad arguments"); return NULL; }
+  llsm_b200_ctx* ctx = shared_ctx();
+  if(ctx == NULL) return NULL;
+  llsm_b200_conf c; memset(& c, 0, sizeof(c));
+  c.nutt = 1; c.nfrm = nfrm; c.maxnhar = options -> maxnhar > 0 ? options -> maxnhar : 1;
+  c.maxnhar_e = options -> maxnhar_e; c.npsd = options -> npsd; c.nchannel = options -> nchannel;
+  c.fs = fs; c.thop = options -> thop; c.lip_radius = options -> lip_radius;
+  if(c.nchannel < 1 || c.nchannel > LLSM_B200_MAXCHANNEL) { set_err("unsupported nchannel"); return NULL; }
+  for(int i = 0; i < c.nchannel - 1; i ++) c.chanfreq[i] = options -> chanfreq[i];
+  llsm_b200_aoptions ao = {options -> f0_refine, options -> hm_method, options -> rel_winsize};
+
+  const size_t F = (size_t)nfrm;
+  int mne = c.maxnhar_e > 0 ? c.maxnhar_e : 1;
+  int* nhar = calloc(F, 4); float* ampl = calloc(F * c.maxnhar, 4); float* phse = calloc(F * c.maxnhar, 4);
+  float* psd = calloc(F * c.npsd, 4); float* psdres = calloc(F * c.npsd, 4);
+  float* edc = calloc(F * c.nchannel, 4); int* enhar = calloc(F * c.nchannel, 4);
+  float* eampl = calloc(F * c.nchannel * mne, 4); float* ephse = calloc(F * c.nchannel * mne, 4);
+  float* xres = malloc(sizeof(float) * (size_t)nx);
+  llsm_b200_frames_out fo = {f0, nhar, ampl, phse, psd, psdres, edc, enhar, eampl, ephse};
+  int rc = llsm_b200_analyze_l0_host(ctx, & c, & ao, x, nx, nx, & fo, xres);   /* f0 refined in place */
+  llsm_chunk* ret = NULL;
+  if(rc == 0) {
+    llsm_container* conf = llsm_aoptions_toconf(options, fs / 2.0);
+    ((int*)llsm_container_get(conf, LLSM_CONF_NFRM))[0] = nfrm;
+    ret = llsm_create_chunk(conf, 1);
+    llsm_delete_container(conf);
+    for(int i = 0; i < nfrm; i ++) {
+      llsm_container* f = ret -> frames[i];
+      ((FP_TYPE*)llsm_container_get(f, LLSM_FRAME_F0))[0] = f0[i];
+      llsm_nmframe* nm = llsm_container_get(f, LLSM_FRAME_NM);
+      if(f0[i] != 0) {
+        llsm_hmframe* hm = llsm_create_hmframe(nhar[i]);
+        memcpy(hm -> ampl, ampl + (size_t)i * c.maxnhar, 4 * (size_t)nhar[i]);
+        memcpy(hm -> phse, phse + (size_t)i * c.maxnhar, 4 * (size_t)nhar[i]);
+        llsm_container_attach(f, LLSM_FRAME_HM, hm, llsm_delete_hmframe, llsm_copy_hmframe);
+      }
+      memcpy(nm -> psd, psd + (size_t)i * c.npsd, 4 * (size_t)c.npsd);
+      FP_TYPE* res = llsm_create_fparray(c.npsd);
+      memcpy(res, psdres + (size_t)i * c.npsd, 4 * (size_t)c.npsd);
+      llsm_container_attach(f, LLSM_FRAME_PSDRES, res, llsm_delete_fparray, llsm_copy_fparray);
+      for(int ch = 0; ch < c.nchannel; ch ++) {
+        size_t e = (size_t)i * c.nchannel + ch;
+        nm -> edc[ch] = edc[e];
+        if(f0[i] == 0) continue;                        /* layer0.c:452 */
+        llsm_hmframe* eh = llsm_create_hmframe(enhar[e]);
+        memcpy(eh -> ampl, eampl + e * mne, 4 * (size_t)enhar[e]);
+        memcpy(eh -> phse, ephse + e * mne, 4 * (size_t)enhar[e]);
+        llsm_copy_hmframe_inplace(nm -> eenv[ch], eh);
+        llsm_delete_hmframe(eh);
+      }
+    }
+    if(x_ap != NULL) { *x_ap = xres; xres = NULL; }
+  }
+  free(nhar); free(ampl); free(phse); free(psd); free(psdres); free(edc); free(enhar); free(eampl);
+  free(ephse); free(xres);
+  return ret;
+}

@@ -214,7 +214,7 @@ static inline int launch_hm_bank_v(BankParams P, int nutt, int nfrm_max, int npa
 
 static inline int bank_variant() {
   static int v = -1;
-  if(v < 0) { const char* e = getenv("LLSM_BANK_VARIANT"); v = e ? atoi(e) : 1; }
+  if(v < 0) { const char* e = getenv("LLSM_BANK_VARIANT"); v = e ? atoi(e) : 3; }
   return v;
 }
 
