@@ -49,7 +49,7 @@ struct DevBuf {
 // device-resident copy of a SynthPlan
 struct SynthPlanDev {
   SynthPlan h;
-  int *hm_base = nullptr, *env_off = nullptr, *psd_lo = nullptr;
+  int *hm_base = nullptr, *env_off = nullptr, *psd_lo = nullptr, *env_contig = nullptr;
   float *hm_frac = nullptr, *win_hm = nullptr, *env_r = nullptr, *win_env = nullptr,
         *win_ns = nullptr, *psd_r = nullptr;
   float2* tw_ns = nullptr;
@@ -73,10 +73,11 @@ struct SynthPlanDev {
     rc |= up(&hm_base, h.hm_base, st); rc |= up(&hm_frac, h.hm_frac, st);
     rc |= up(&win_hm, h.win_hm, st);   rc |= up(&env_r, h.env_r, st);
     rc |= up(&env_off, h.env_off, st); rc |= up(&win_env, h.win_env, st);
+    rc |= up(&env_contig, h.env_contig, st);
     rc |= up(&win_ns, h.win_ns, st);   rc |= up(&psd_lo, h.psd_lo, st);
     rc |= up(&psd_r, h.psd_r, st);
     float* twd = nullptr; rc |= up(&twd, tw, st); tw_ns = (float2*)twd;
-    iir_L = (h.nt + IIR_NT - 1) / IIR_NT;
+    iir_L = ((h.nt + IIR_NT - 1) / IIR_NT + 3) & ~3;
     std::vector<double> coef((size_t)LLSM_B200_MAXCHANNEL * 2 * 9, 0.0), mpow((size_t)LLSM_B200_MAXCHANNEL * 2 * IIR_NLOG * 16, 0.0);
     for(int c = 0; c < nchannel; c ++)
       for(int s2 = 0; s2 < h.chan[c].nstage; s2 ++)
@@ -110,7 +111,6 @@ static inline int run_harmonics(const SynthPlanDev& pd, const llsm_b200_conf& co
   P.fs = conf.fs;
   P.has_options = opt != nullptr;
   if(opt) { P.use_iczt = opt->use_iczt; P.iczt_a = opt->iczt_param_a; P.iczt_b = opt->iczt_param_b; }
-  P.npass = 2;
   P.y_sin = y_sin;
   if(launch_hm_bank(P, conf.nutt, conf.nfrm, st) != 0) return LLSM_B200_ERANGE;
   if(lc) lc->n += 1;
@@ -125,7 +125,8 @@ static inline int run_synth_l0(const SynthPlanDev& pd, SynthScratch& sc, const l
   const int B = conf.nutt, nch = conf.nchannel;
   if(nch < 1 || nch > LLSM_B200_MAXCHANNEL) return LLSM_B200_EINVAL;
   if(out.stride < h.ny) return LLSM_B200_EINVAL;
-  if(sc.colored.reserve((size_t)B * nch * h.nt * 4) != 0) return LLSM_B200_ENOMEM;
+  const int tstride = (h.nt + 3) & ~3;
+  if(sc.colored.reserve((size_t)B * nch * tstride * 4) != 0) return LLSM_B200_ENOMEM;
   if(sc.y_exc.reserve((size_t)B * out.stride * 4) != 0) return LLSM_B200_ENOMEM;
 
   // 1. harmonic component
@@ -137,11 +138,11 @@ static inline int run_synth_l0(const SynthPlanDev& pd, SynthScratch& sc, const l
   unsigned mask = 0;
   {
     WhiteParams W; memset(&W, 0, sizeof(W));
-    W.nseq = B * nch; W.nt = h.nt; W.white = opt.white; W.seed = opt.seed; W.out = sc.colored.as<float>();
+    W.nseq = B * nch; W.nt = h.nt; W.ostride = tstride; W.white = opt.white; W.seed = opt.seed; W.out = sc.colored.as<float>();
     LLSM_LAUNCH(white_fill_kernel, dim3((h.nt / 4 + 256) / 256, B * nch), dim3(256), 0, st, W);
     if(lc) lc->n += 1;
     IirParams I; memset(&I, 0, sizeof(I));
-    I.nchannel = nch; I.n = h.nt; I.L = pd.iir_L; I.y = sc.colored.as<float>(); I.ystride = h.nt;
+    I.nchannel = nch; I.n = h.nt; I.L = pd.iir_L; I.y = sc.colored.as<float>(); I.ystride = tstride; I.vec_ok = 1;
     I.coef = pd.iir_coef; I.mpow = pd.iir_mpow;
     for(int c = 0; c < nch; c ++) {
       I.nstage[c] = h.chan[c].nstage;
@@ -157,10 +158,10 @@ static inline int run_synth_l0(const SynthPlanDev& pd, SynthScratch& sc, const l
   E.nfrm = conf.nfrm; E.nchannel = nch; E.maxnhar_e = conf.maxnhar_e;
   E.nfrm_utt = fr.nfrm_utt; E.ny_utt = ny_utt_dev;
   E.f0 = fr.f0; E.edc = fr.edc; E.enhar = fr.enhar; E.eampl = fr.eampl; E.ephse = fr.ephse;
-  E.env_r = pd.env_r; E.env_off = pd.env_off; E.win_env = pd.win_env; E.n_env = h.n_env;
+  E.env_r = pd.env_r; E.env_off = pd.env_off; E.env_contig = pd.env_contig; E.win_env = pd.win_env; E.n_env = h.n_env;
   E.ny = h.ny; E.nsamp = out.stride; E.stride = out.stride; E.fs = conf.fs;
   E.has_options = 1; E.use_iczt = opt.use_iczt; E.iczt_a = opt.iczt_param_a; E.iczt_b = opt.iczt_param_b;
-  E.colored = sc.colored.as<float>(); E.nt = h.nt; E.ntemplate = h.ntemplate;
+  E.colored = sc.colored.as<float>(); E.nt = h.nt; E.ntemplate = h.ntemplate; E.tstride = tstride;
   E.chan_mask = mask;
   E.y_exc = sc.y_exc.as<float>();
   if(launch_noise_excitation(E, B, st) != 0) return LLSM_B200_ERANGE;

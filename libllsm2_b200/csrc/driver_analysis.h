@@ -95,7 +95,7 @@ struct AnaPlanDev {
   int ensure_iir(int nx, cudaStream_t st) {
     if(nx == iir_nx) return 0;
     if(dev_sync(st) != 0) return -1;           // previous tables may still be in use / in flight
-    iir_L = (nx + IIR_NT - 1) / IIR_NT;
+    iir_L = ((nx + IIR_NT - 1) / IIR_NT + 3) & ~3;
     h_coef.assign((size_t)LLSM_B200_MAXCHANNEL * 2 * 9, 0.0);
     h_mpow.assign((size_t)LLSM_B200_MAXCHANNEL * 2 * IIR_NLOG * 16, 0.0);
     for(int c = 0; c < nchannel; c ++)
@@ -127,8 +127,9 @@ static inline int run_analyze_l0(const SynthPlanDev& sp, AnaPlanDev& ap, AnaScra
   if(opt.hm_method != 1) return LLSM_B200_ERANGE;        // HMPP: see DESIGN.md
   if(h.nfft > 8192 || h.nfft_s > 8192) return LLSM_B200_ERANGE;
   const size_t BF = (size_t)B * F;
+  const int cst = (nx + 3) & ~3;     // row stride of the sub-band signals (16-byte aligned rows)
   if(sc.x_sin.reserve((size_t)B * nx * 4) || sc.x_res.reserve((size_t)B * nx * 4) ||
-     sc.ce.reserve((size_t)B * nch * nx * 4) || sc.env.reserve(BF * h.nspec * 4) ||
+     sc.ce.reserve((size_t)B * nch * cst * 4) || sc.env.reserve(BF * h.nspec * 4) ||
      sc.lpsd.reserve(BF * h.nspec * 4) || sc.res.reserve(BF * h.nspec * 4) ||
      sc.filt.reserve(BF * h.nspec * 4)) return LLSM_B200_ENOMEM;
   if(ap.ensure_iir(nx, st) != 0) return LLSM_B200_ENOMEM;
@@ -202,7 +203,7 @@ static inline int run_analyze_l0(const SynthPlanDev& sp, AnaPlanDev& ap, AnaScra
   // 5. noise envelope per channel (layer0.c:417-469)
   {
     IirParams I; memset(&I, 0, sizeof(I));
-    I.nchannel = nch; I.n = nx; I.L = ap.iir_L; I.y = sc.ce.as<float>(); I.ystride = nx;
+    I.nchannel = nch; I.n = nx; I.L = ap.iir_L; I.y = sc.ce.as<float>(); I.ystride = cst; I.vec_ok = 1;
     I.src_a = x_res; I.sa_stride = rstride; I.src_b = x; I.sb_stride = xstride;
     I.src_b_mask = h.use_x_mask; I.src_per_utt = 1;
     I.coef = ap.iir_coef.as<double>(); I.mpow = ap.iir_mpow.as<double>();
@@ -212,7 +213,7 @@ static inline int run_analyze_l0(const SynthPlanDev& sp, AnaPlanDev& ap, AnaScra
     if(lc) lc->n ++;
 
     HarmDftParams H; memset(&H, 0, sizeof(H));
-    H.nfrm = F; H.nfrm_utt = nfrm_utt; H.sig = sc.ce.as<float>(); H.nsig = nch; H.nx = nx; H.xstride = nx;
+    H.nfrm = F; H.nfrm_utt = nfrm_utt; H.sig = sc.ce.as<float>(); H.nsig = nch; H.nx = nx; H.xstride = cst;
     H.f0 = fr.f0; H.center = sp.hm_base; H.fs = conf.fs; H.rel_winsize = opt.rel_winsize;
     H.maxnhar = conf.maxnhar_e; H.nhar_out = fr.enhar; H.ampl = fr.eampl; H.phse = fr.ephse;
     H.max_half = max_half;
@@ -222,7 +223,7 @@ static inline int run_analyze_l0(const SynthPlanDev& sp, AnaPlanDev& ap, AnaScra
     }
 
     DcParams D; memset(&D, 0, sizeof(D));
-    D.nfrm = F; D.nchannel = nch; D.nfrm_utt = nfrm_utt; D.ce = sc.ce.as<float>(); D.cstride = nx; D.nx = nx;
+    D.nfrm = F; D.nchannel = nch; D.nfrm_utt = nfrm_utt; D.ce = sc.ce.as<float>(); D.cstride = cst; D.nx = nx;
     D.f0 = fr.f0; D.center = sp.hm_base; D.fs = conf.fs; D.thop = conf.thop; D.edc = fr.edc;
     LLSM_LAUNCH(frame_dc_kernel, dim3(F, B * nch), dim3(128), 0, st, D);
     if(lc) lc->n ++;

@@ -26,6 +26,7 @@ struct IirParams {
   const double* mpow;                 // [nchannel][2][IIR_NLOG][16]
   int nstage[8];
   int square;                         // square the result (dsputils.c:232-233)
+  int vec_ok;                         // y rows are 16-byte aligned (ystride % 4 == 0) and L % 4 == 0
 };
 
 struct IirCoef { double b0, b1, b2, b3, b4, a1, a2, a3, a4; };
@@ -70,12 +71,21 @@ __global__ void __launch_bounds__(IIR_NT) iir_filtfilt_kernel(IirParams P) {
     cf.a1 = cfs[5]; cf.a2 = cfs[6]; cf.a3 = cfs[7]; cf.a4 = cfs[8];
     for(int dir = 0; dir < 2; dir ++) {
       const float* in = (st == 0 && dir == 0 && src0) ? src0 : y;
-      // ---- A: zero-state pass over the chunk
+      // ---- A: zero-state pass over the chunk (4 samples per step; 16-byte accesses on y)
+      const bool vec = (in == y) && P.vec_ok;
       double z0 = 0, z1 = 0, z2 = 0, z3 = 0, yn;
-      for(int q = 0; q < L; q ++) {
-        int idx = dir == 0 ? lo + q : lo + L - 1 - q;
-        double xn = idx < n ? (double)in[idx] : 0.0;
-        iir_step(cf, xn, z0, z1, z2, z3, yn);
+      for(int q = 0; q < L; q += 4) {
+        const int i0 = dir == 0 ? lo + q : lo + L - 4 - q;     // lowest index of the group
+        float v[4];
+        if(vec && i0 + 3 < n) {
+          float4 t = *(const float4*)(in + i0);
+          v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+        } else {
+#pragma unroll
+          for(int e = 0; e < 4; e ++) v[e] = (i0 + e < n) ? in[i0 + e] : 0.f;
+        }
+#pragma unroll
+        for(int e = 0; e < 4; e ++) iir_step(cf, (double)v[dir == 0 ? e : 3 - e], z0, z1, z2, z3, yn);
       }
       const int ord = dir == 0 ? tid : IIR_NT - 1 - tid;   // position in processing order
       fs[ord][0] = z0; fs[ord][1] = z1; fs[ord][2] = z2; fs[ord][3] = z3;
@@ -99,14 +109,28 @@ __global__ void __launch_bounds__(IIR_NT) iir_filtfilt_kernel(IirParams P) {
       if(ord == 0) { z0 = z1 = z2 = z3 = 0; }
       else { z0 = fs[ord - 1][0]; z1 = fs[ord - 1][1]; z2 = fs[ord - 1][2]; z3 = fs[ord - 1][3]; }
       const bool last = P.square && st == nst - 1 && dir == 1;
-      for(int q = 0; q < L; q ++) {
-        int idx = dir == 0 ? lo + q : lo + L - 1 - q;
-        if(idx < n) {
-          iir_step(cf, (double)in[idx], z0, z1, z2, z3, yn);
-          float yf = (float)yn;
-          y[idx] = last ? yf * yf : yf;
+      for(int q = 0; q < L; q += 4) {
+        const int i0 = dir == 0 ? lo + q : lo + L - 4 - q;
+        float v[4], o[4];
+        const bool full = i0 + 3 < n;
+        if(vec && full) {
+          float4 t = *(const float4*)(in + i0);
+          v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
         } else {
-          iir_step(cf, 0.0, z0, z1, z2, z3, yn);
+#pragma unroll
+          for(int e = 0; e < 4; e ++) v[e] = (i0 + e < n) ? in[i0 + e] : 0.f;
+        }
+#pragma unroll
+        for(int e = 0; e < 4; e ++) {
+          const int k = dir == 0 ? e : 3 - e;
+          iir_step(cf, (double)v[k], z0, z1, z2, z3, yn);
+          float yf = (float)yn;
+          o[k] = last ? yf * yf : yf;
+        }
+        if(P.vec_ok && full) *(float4*)(y + i0) = make_float4(o[0], o[1], o[2], o[3]);
+        else {
+#pragma unroll
+          for(int e = 0; e < 4; e ++) if(i0 + e < n) y[i0 + e] = o[e];
         }
       }
       __syncthreads();
@@ -115,7 +139,7 @@ __global__ void __launch_bounds__(IIR_NT) iir_filtfilt_kernel(IirParams P) {
 }
 
 // white-noise fill for the templates: copy the host-drawn template or draw on the device
-struct WhiteParams { int nseq, nt; const float* white; unsigned long long seed; float* out; };
+struct WhiteParams { int nseq, nt, ostride; const float* white; unsigned long long seed; float* out; };
 
 #ifndef LLSM_PHILOX_DEFINED
 #define LLSM_PHILOX_DEFINED
@@ -141,7 +165,7 @@ __global__ void __launch_bounds__(256) white_fill_kernel(WhiteParams P) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;       // group of 4 samples
   const int n0 = q * 4;
   if(n0 >= P.nt) return;
-  float* o = P.out + (size_t)seq * P.nt;
+  float* o = P.out + (size_t)seq * P.ostride;
   if(P.white) {
     const float* w = P.white + (size_t)seq * P.nt;
     for(int i = 0; i < 4 && n0 + i < P.nt; i ++) o[n0 + i] = w[n0 + i];

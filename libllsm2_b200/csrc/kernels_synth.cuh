@@ -41,7 +41,9 @@ struct BankParams {
 
 #define BANK_KC 64          // harmonics staged per chunk
 
-template <int NP, int NTHR, int MINB>
+// NP packed float2 slots (two sample pairs each, FFMA2 / FMUL2) followed by NS scalar sample pairs
+// (plain FFMA) per lane: lane l owns sample offsets n = l + 32 q, q < 2 NP + NS.
+template <int NP, int NS, int NTHR, int MINB>
 __global__ void __launch_bounds__(NTHR, MINB) hm_bank_ola_kernel(BankParams P) {
   LLSM_DYN_SMEM(smem);
   const int NW = blockDim.x >> 5;
@@ -94,7 +96,15 @@ __global__ void __launch_bounds__(NTHR, MINB) hm_bank_ola_kernel(BankParams P) {
     const float corr = (float)((double)(frac * 2.0f) * LLSM_PI / (double)P.fs * (double)f0);
 
     // ---- rotation seeds z = e^{i 2 pi nu n} for this lane's sample offsets n
-    float2 zr[NP], zi[NP], nzi[NP], wr[NP], wi[NP], C[NP], S[NP];
+    float2 zr[NP > 0 ? NP : 1], zi[NP > 0 ? NP : 1], nzi[NP > 0 ? NP : 1], wr[NP > 0 ? NP : 1],
+           wi[NP > 0 ? NP : 1], C[NP > 0 ? NP : 1], S[NP > 0 ? NP : 1];
+    float szr[NS > 0 ? NS : 1], szi[NS > 0 ? NS : 1], swr[NS > 0 ? NS : 1], swi[NS > 0 ? NS : 1],
+          sC[NS > 0 ? NS : 1], sS[NS > 0 ? NS : 1];
+#pragma unroll
+    for(int m = 0; m < NS; m ++) {
+      float2 a = unit_phasor_turns(nu * (double)(lane + 32 * (2 * NP + m)));
+      szr[m] = a.x; szi[m] = a.y; swr[m] = 1.f; swi[m] = 0.f; sC[m] = 0.f; sS[m] = 0.f;
+    }
 #pragma unroll
     for(int m = 0; m < NP; m ++) {
       int nA = lane + 64 * m, nB = nA + 32;
@@ -137,6 +147,14 @@ __global__ void __launch_bounds__(NTHR, MINB) hm_bank_ola_kernel(BankParams P) {
           C[m] = ffma2(aa, nwr, C[m]);             // sum a cos(phi) cos(k w n)
           S[m] = ffma2(bb, nwi, S[m]);             // sum a sin(phi) sin(k w n)
         }
+#pragma unroll
+        for(int m = 0; m < NS; m ++) {
+          float nwr = fmaf(-swi[m], szi[m], swr[m] * szr[m]);
+          float nwi = fmaf(swr[m], szi[m], swi[m] * szr[m]);
+          swr[m] = nwr; swi[m] = nwi;
+          sC[m] = fmaf(cf.x, nwr, sC[m]);
+          sS[m] = fmaf(cf.z, nwi, sS[m]);
+        }
       }
     }
 
@@ -151,6 +169,12 @@ __global__ void __launch_bounds__(NTHR, MINB) hm_bank_ola_kernel(BankParams P) {
         if(n <= H - 1) dst[H + n] = (c - sn) * P.win[H + n];
         if(n >= 1 && n <= H) dst[H - n] = (c + sn) * P.win[H - n];
       }
+    }
+#pragma unroll
+    for(int m = 0; m < NS; m ++) {
+      int n = lane + 32 * (2 * NP + m);
+      if(n <= H - 1) dst[H + n] = (sC[m] - sS[m]) * P.win[H + n];
+      if(n >= 1 && n <= H) dst[H - n] = (sC[m] + sS[m]) * P.win[H - n];
     }
   }
   __syncthreads();
@@ -181,51 +205,48 @@ static inline size_t bank_smem_bytes(int nwarps, int npass, int n_hm) {
 }
 
 // returns 0 on success, -1 when the window is too long for the specialisations below
-template <int NP, int NTHR, int MINB>
+template <int NP, int NS, int NTHR, int MINB>
 static inline void launch_hm_bank_t(const BankParams& P, dim3 grid, size_t smem, cudaStream_t st) {
-  auto kfn = hm_bank_ola_kernel<NP, NTHR, MINB>;
+  auto kfn = hm_bank_ola_kernel<NP, NS, NTHR, MINB>;
 #ifndef LLSM_EMU
   cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 #endif
   LLSM_LAUNCH(kfn, grid, dim3(NTHR), smem, st, P);
 }
 
-template <int NTHR, int MINB>
-static inline int launch_hm_bank_v(BankParams P, int nutt, int nfrm_max, int npass, cudaStream_t st) {
-  const int NW = NTHR / 32;
-  P.npass = npass;
-  const int F = NW * npass - 2;
-  int nseg = (std::max(nfrm_max, 1) + F - 1) / F;
-  dim3 grid(nseg, nutt);
-  size_t smem = bank_smem_bytes(NW, npass, P.n_hm);
-  if(smem > 220 * 1024) return -1;
-  int slots = (P.n_hm / 2 + 1 + 63) / 64;  // packed pair-slots per lane
-  switch(slots) {
-    case 1: launch_hm_bank_t<1, NTHR, MINB>(P, grid, smem, st); break;
-    case 2: launch_hm_bank_t<2, NTHR, MINB>(P, grid, smem, st); break;
-    case 3: launch_hm_bank_t<3, NTHR, MINB>(P, grid, smem, st); break;
-    case 4: launch_hm_bank_t<4, NTHR, MINB>(P, grid, smem, st); break;
-    case 5: case 6: launch_hm_bank_t<6, NTHR, 1>(P, grid, smem, st); break;
-    case 7: case 8: launch_hm_bank_t<8, NTHR, 1>(P, grid, smem, st); break;
-    default: return -1;
-  }
-  return 0;
-}
-
 static inline int bank_variant() {
   static int v = -1;
-  if(v < 0) { const char* e = getenv("LLSM_BANK_VARIANT"); v = e ? atoi(e) : 3; }
+  if(v < 0) { const char* e = getenv("LLSM_BANK_VARIANT"); v = e ? atoi(e) : 0; }
   return v;
 }
 
-static inline int launch_hm_bank(const BankParams& P, int nutt, int nfrm_max, cudaStream_t st) {
-  switch(bank_variant()) {
-    case 0: return launch_hm_bank_v<512, 1>(P, nutt, nfrm_max, 2, st);   // 16 warps, 30 tiles
-    case 2: return launch_hm_bank_v<256, 3>(P, nutt, nfrm_max, 2, st);   // 8 warps, 14 tiles, <= 85 regs
-    case 3: return launch_hm_bank_v<256, 3>(P, nutt, nfrm_max, 4, st);   // 8 warps, 30 tiles, <= 85 regs
-    case 4: return launch_hm_bank_v<128, 6>(P, nutt, nfrm_max, 4, st);   // 4 warps, 14 tiles
-    default: return launch_hm_bank_v<256, 2>(P, nutt, nfrm_max, 4, st);  // 8 warps, 30 tiles
+// returns 0 on success, -1 when the window is too long for the specialisations below
+static inline int launch_hm_bank(BankParams P, int nutt, int nfrm_max, cudaStream_t st) {
+  const int NTHR = 256, NW = NTHR / 32;
+  P.npass = 4;                              // 32 frame slots, 30 tiles per CTA
+  const int F = NW * P.npass - 2;
+  int nseg = (std::max(nfrm_max, 1) + F - 1) / F;
+  dim3 grid(nseg, nutt);
+  size_t smem = bank_smem_bytes(NW, P.npass, P.n_hm);
+  if(smem > 220 * 1024) return -1;
+  int pairs = (P.n_hm / 2 + 1 + 31) / 32;   // sample pairs per lane
+  if(pairs <= 2)  { launch_hm_bank_t<1, 0, NTHR, 3>(P, grid, smem, st); return 0; }
+  if(pairs <= 4)  { launch_hm_bank_t<2, 0, NTHR, 3>(P, grid, smem, st); return 0; }
+  if(pairs <= 6)  { launch_hm_bank_t<3, 0, NTHR, 3>(P, grid, smem, st); return 0; }
+  if(pairs <= 8) {
+    switch(bank_variant()) {                // packed : scalar split of the 8 pairs (tuning knob)
+      case 1: launch_hm_bank_t<0, 8, NTHR, 3>(P, grid, smem, st); break;
+      case 2: launch_hm_bank_t<2, 4, NTHR, 3>(P, grid, smem, st); break;
+      case 3: launch_hm_bank_t<3, 2, NTHR, 3>(P, grid, smem, st); break;
+      case 4: launch_hm_bank_t<1, 6, NTHR, 3>(P, grid, smem, st); break;
+      case 5: launch_hm_bank_t<2, 4, NTHR, 2>(P, grid, smem, st); break;
+      default: launch_hm_bank_t<4, 0, NTHR, 3>(P, grid, smem, st); break;
+    }
+    return 0;
   }
+  if(pairs <= 12) { launch_hm_bank_t<6, 0, NTHR, 1>(P, grid, smem, st); return 0; }
+  if(pairs <= 16) { launch_hm_bank_t<8, 0, NTHR, 1>(P, grid, smem, st); return 0; }
+  return -1;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -243,13 +264,14 @@ struct ExcParams {
   const float* f0; const float* edc; const int* enhar; const float* eampl; const float* ephse;
   const float* env_r;       // [nfrm] (float)((i - 1) * thop * fs)
   const int* env_off;       // [nfrm] round(env_r)
+  const int* env_contig;    // [nfrm] indices of the frame are off + j exactly
   const float* win_env;     // [n_env]
   int n_env;
   int ny, nsamp, stride;
   float fs;
   int has_options, use_iczt; float iczt_a, iczt_b;
   const float* colored;     // [B][nchannel][nt]
-  int nt, ntemplate;
+  int nt, ntemplate, tstride;   // tstride: row stride of colored
   unsigned chan_mask;       // bit c set when channel c exists (fmin < fs / 2)
   float* y_exc;             // [B][stride]
 };
@@ -257,26 +279,31 @@ struct ExcParams {
 #define EXC_THREADS 256
 #define EXC_FCHUNK 8
 
-// stretch_stationary_noise (dsputils.c:363-383) as a closed-form index map: value of the
-// stretched template at output position p.
-__device__ __forceinline__ float stretched_noise(const float* __restrict__ x, int nx, int ny, int p) {
+// stretch_stationary_noise (dsputils.c:363-383) as a closed-form index map: output position p reads
+// template index `base`, cross-faded with template index `ii` (>= 0) at the 128-sample seams.
+struct StretchIdx { int base, ii; };
+__device__ __forceinline__ StretchIdx stretch_index(int nx, int ny, int p) {
   const int overlap = 128;
   const int period = nx - overlap;
-  float base; int ii = -1;
+  StretchIdx s; s.ii = -1;
   if(p < nx) {
-    base = x[p];
-    if(ny > nx && p >= nx - overlap) ii = p - (nx - overlap);
+    s.base = p;
+    if(ny > nx && p >= nx - overlap) s.ii = p - (nx - overlap);
   } else {
-    int s = (p - nx) / period;          // 0-based copy segment after the first template
-    int head = nx + s * period;
+    int q = (p - nx) / period;          // copy segment after the first template
+    int head = nx + q * period;
     int i = p - head;
-    base = x[i + overlap];
-    if(i >= period - overlap && head + period <= ny) ii = i - (period - overlap);
+    s.base = i + overlap;
+    if(i >= period - overlap && head + period <= ny) s.ii = i - (period - overlap);
   }
-  if(ii >= 0) {
-    float r = (float)ii / (float)overlap;
+  return s;
+}
+__device__ __forceinline__ float stretched_value(const float* __restrict__ x, StretchIdx s) {
+  float base = x[s.base];
+  if(s.ii >= 0) {
+    const float r = (float)s.ii / 128.0f;
     float y = (float)((double)base * (1.0 - (double)r));
-    y = y + x[ii] * r;
+    y = y + x[s.ii] * r;
     float d = 2.0f * r; d = d * (r - 1.0f); d = d + 1.0f;
     base = (float)((double)y / sqrt((double)d));
   }
@@ -322,7 +349,7 @@ __global__ void __launch_bounds__(EXC_THREADS) noise_excitation_kernel(ExcParams
       if(q == 0) v = f0 > 0 ? f0 / P.fs : 0.f;               // f0[i] / fs (0 when unvoiced)
       else if(q == 1) v = P.env_r[i];
       else if(q == 2) v = __int_as_float(P.env_off[i]);
-      else if(q == 3) v = 0.f;
+      else if(q == 3) v = __int_as_float(P.env_contig[i]);
       else {
         int qq = q - 4, c = qq / (2 + 2 * mne), w = qq - c * (2 + 2 * mne);
         size_t ec = (row + i) * nch + c;
@@ -347,12 +374,17 @@ __global__ void __launch_bounds__(EXC_THREADS) noise_excitation_kernel(ExcParams
         const float* F = fr + fi * fstride;
         const float f0n = F[0], r = F[1];
         const int off = __float_as_int(F[2]);
-        for(int dj = -1; dj <= 1; dj ++) {
+        const unsigned rel = (unsigned)(p - off + 1);
+        if(rel > (unsigned)(P.n_env + 1)) continue;            // frame cannot reach this sample
+        const int contig = __float_as_int(F[3]);
+        for(int dj = contig ? 0 : -1; dj <= (contig ? 0 : 1); dj ++) {
           int j = p - off + dj;
           if(j < 0 || j >= P.n_env) continue;
-          float tpos = __fadd_rn(r, (float)j);               // (i - 1) * thop * fs + j in float
-          int idx = (int)roundf(tpos);                       // layer0.c:307
-          if(idx != p) continue;
+          if(! contig) {
+            float tpos = __fadd_rn(r, (float)j);               // (i - 1) * thop * fs + j in float
+            int idx = (int)roundf(tpos);                       // layer0.c:307
+            if(idx != p) continue;
+          }
           const float wj = P.win_env[j];
           float2 z = unit_phasor_turns((double)f0n * (double)(j - half));
           float2 w = make_float2(1.f, 0.f);
@@ -381,10 +413,11 @@ __global__ void __launch_bounds__(EXC_THREADS) noise_excitation_kernel(ExcParams
   if(p < P.nsamp) {
     float y = 0.f;
     if(p < ny_b) {
+      const StretchIdx si = stretch_index(P.ntemplate, ny_b, p);
 #pragma unroll
       for(int c = 0; c < MAXCH; c ++) if(c < nch && ((P.chan_mask >> c) & 1u)) {
-        const float* tp = P.colored + ((size_t)b * nch + c) * P.nt;
-        float x = stretched_noise(tp, P.ntemplate, ny_b, p);
+        const float* tp = P.colored + ((size_t)b * nch + c) * P.tstride;
+        float x = stretched_value(tp, si);
         x = x * sqrtf(env[c]);                               // layer0.c:548
         y += x;                                              // layer0.c:549
       }
@@ -578,7 +611,7 @@ static inline size_t shape_smem_bytes(int nfft, int seg, int npsd, int nspec) {
   return (size_t)nfft * 16 + (size_t)(seg + 2 * npsd + 2 * nspec + 64) * 4 + 16;
 }
 
-static inline int launch_noise_shape(const ShapeParams& P, int nutt, cudaStream_t st) {
+static inline int launch_noise_shape_block(const ShapeParams& P, int nutt, cudaStream_t st) {
   dim3 grid((P.nsamp + P.seg - 1) / P.seg, nutt), block(SHAPE_THREADS);
   size_t smem = shape_smem_bytes(P.nfft, P.seg, P.npsd, P.nspec);
   if(smem > 220 * 1024) return -1;
@@ -597,4 +630,230 @@ __global__ void ny_utt_kernel(const int* nfrm_utt, int nutt, float thop, float f
   float v = __fmul_rn((float)(nfrm_utt[b] + 1), thop);
   v = __fmul_rn(v, fs);
   ny_utt[b] = (int)round((double)v);
+}
+
+// ------------------------------------------------------------------------------------------
+// Noise shaping, warp-per-frame-pair version for nfft = 1024: every warp filters two consecutive
+// frames with one register-resident complex FFT / IFFT (warp_fft.cuh); a round = 8 warps = 16
+// frames, after which the 16 frame outputs (parked in shared memory) are added to the CTA's output
+// run in ascending frame order by sample-owning threads. Two block barriers per 16 frames.
+// ------------------------------------------------------------------------------------------
+#include "warp_fft.cuh"
+
+#define SHW_WARPS 8
+#define SHW_THREADS (SHW_WARPS * 32)
+
+__global__ void __launch_bounds__(SHW_THREADS, 2) noise_shape_warp_kernel(ShapeParams P) {
+  LLSM_DYN_SMEM(smem);
+  const int NF = 1024, HALF = 512, NSPEC = 513;
+  float2* tw2 = (float2*)smem;                                   // [1024]
+  char* wbase = (char*)(tw2 + 1024);
+  float* acc = (float*)(wbase + SHW_WARPS * WFFT_SCRATCH_BYTES); // [seg]
+  int* fcen = (int*)(acc + P.seg);                               // [2 * SHW_WARPS] centre, -1 = none
+  float2* z0 = (float2*)(fcen + 2 * SHW_WARPS) + 32 * (threadIdx.x >> 5);   // [SHW_WARPS][32]
+
+  const int b = blockIdx.y;
+  const int oa = blockIdx.x * P.seg;
+  const int ob = min(oa + P.seg, P.nsamp);
+  const int nf = P.nfrm_utt ? P.nfrm_utt[b] : P.nfrm;
+  const int ny_b = P.ny_utt ? P.ny_utt[b] : P.ny;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int npsd = P.npsd, hw = P.n_ns / 2;
+  const size_t row = (size_t)b * P.nfrm;
+  const float* exc = P.y_exc + (size_t)b * P.stride_exc;
+  float2* scratch = (float2*)(wbase + warp * WFFT_SCRATCH_BYTES);
+  float* slot = (float*)scratch;                                 // [2][1024] outputs of the pair
+  float* pbuf = (float*)scratch;                                 // [2][NSPEC] PSDs (between FFTs)
+  float* spsd = pbuf + 2 * NSPEC + 2;                            // [2][npsd]  (npsd <= 512)
+
+  wfft_build_tw2(tw2, P.tw);
+  for(int i = tid; i < P.seg; i += blockDim.x) acc[i] = 0.f;
+
+  int lo = 0, hi = nf;
+  while(lo < hi) { int mid = (lo + hi) >> 1; if(P.center[mid] + HALF > oa) hi = mid; else lo = mid + 1; }
+  const int ia = lo;
+  lo = ia; hi = nf;
+  while(lo < hi) { int mid = (lo + hi) >> 1; if(P.center[mid] - HALF >= ob) hi = mid; else lo = mid + 1; }
+  const int ib = lo;
+  const double resbias = 0.375 / 2.3025851 * 10.0;
+  const float inv = 1.0f / 1024.0f;
+  __syncthreads();
+
+  for(int r0 = ia; r0 < ib; r0 += 2 * SHW_WARPS) {
+    const int i = r0 + 2 * warp;                 // this warp's pair (i, i + 1)
+    const bool hasA = i < ib, hasB = i + 1 < ib;
+    bool doA = false, doB = false;
+    const int cA = hasA ? P.center[i] : 0, cB = hasB ? P.center[i + 1] : 0;
+    if(hasA) {
+      // ---- peaks of the model PSDs (layer0.c:584-585)
+      float mxA = -3.0e38f, mxB = -3.0e38f;
+      const float* psdA = P.psd + (row + i) * (size_t)npsd;
+      const float* psdB = P.psd + (row + i + (hasB ? 1 : 0)) * (size_t)npsd;
+      for(int j = lane; j < npsd; j += 32) { mxA = fmaxf(mxA, psdA[j]); if(hasB) mxB = fmaxf(mxB, psdB[j]); }
+      for(int o = 16; o > 0; o >>= 1) {
+        mxA = fmaxf(mxA, __shfl_xor_sync(0xffffffffu, mxA, o));
+        mxB = fmaxf(mxB, __shfl_xor_sync(0xffffffffu, mxB, o));
+      }
+      doA = ! (mxA < -100.f);
+      doB = hasB && ! (mxB < -100.f);
+    }
+    if(doA || doB) {                             // warp-uniform
+      // ---- load the two windowed frames: element j = lane + 32 r  (layer0.c:588-592)
+      float2 x[32];
+#pragma unroll
+      for(int r = 0; r < 32; r ++) {
+        int j = lane + 32 * r;
+        int jj = j - HALF + hw;
+        float va = 0.f, vb = 0.f;
+        if(jj >= 0 && jj < P.n_ns) {
+          float w = P.win[jj];
+          int ia2 = cA + jj - hw, ib2 = cB + jj - hw;
+          if(doA && ia2 >= 0 && ia2 < ny_b) va = exc[ia2] * w;
+          if(doB && ib2 >= 0 && ib2 < ny_b) vb = exc[ib2] * w;
+        }
+        x[r] = make_float2(va, vb);
+      }
+      warp_fft1024<false>(x, scratch, tw2, lane);
+      // ---- spectra of the two frames from Z = FFT(a + i b): with the partner bin Zn = Z[N - m],
+      //      A = (Z + conj Zn) / 2, B = (Z - conj Zn) / (2i). Bin m = lane + 32 k1; its partner sits in
+      //      lane (32 - lane) % 32, register 31 - k1 (lane 0: its own register (32 - k1) % 32, read
+      //      back from a small shared copy).
+      const int plane = (32 - lane) & 31;
+      if(lane == 0) {
+#pragma unroll
+        for(int k1 = 0; k1 < 32; k1 ++) z0[k1] = x[k1];
+      }
+      __syncwarp();
+      // PSDs of bins 0..512 into shared memory (dsputils.c:237-244)
+#pragma unroll
+      for(int k1 = 0; k1 <= 16; k1 ++) {
+        float px = __shfl_sync(0xffffffffu, x[31 - k1].x, plane);
+        float py = __shfl_sync(0xffffffffu, x[31 - k1].y, plane);
+        float2 zn = lane == 0 ? z0[(32 - k1) & 31] : make_float2(px, py);
+        float2 zk = x[k1];
+        int m = lane + 32 * k1;
+        if(m <= HALF) {
+          float ax = 0.5f * (zk.x + zn.x), ay = 0.5f * (zk.y - zn.y);
+          float bx = 0.5f * (zk.y + zn.y), by = 0.5f * (zn.x - zk.x);
+          pbuf[m] = (ax * ax + ay * ay) / P.wsqr;
+          pbuf[NSPEC + m] = (bx * bx + by * by) / P.wsqr;
+        }
+      }
+      // model PSD (+ residual) (layer0.c:598-601)
+      for(int h = 0; h < 2; h ++) {
+        if(h == 1 && ! hasB) break;
+        const float* psd = P.psd + (row + i + h) * (size_t)npsd;
+        const float* res = P.psdres ? P.psdres + (row + i + h) * (size_t)npsd : nullptr;
+        for(int j = lane; j < npsd; j += 32) {
+          float v = psd[j];
+          if(res) v = (float)((double)v + ((double)res[j] - resbias));
+          spsd[h * npsd + j] = v;
+        }
+      }
+      __syncwarp();
+      // ---- gains (layer0.c:597-612) and re-packing W = A' + i B'; registers k1 and 31 - k1 are
+      //      rewritten together so that every partner is read before it is overwritten
+      float nyqA = 0.f, nyqB = 0.f;              // Re of the scaled bin 511 (lane 31, register 15)
+#pragma unroll
+      for(int k1 = 0; k1 < 16; k1 ++) {
+        float p1x = __shfl_sync(0xffffffffu, x[31 - k1].x, plane), p1y = __shfl_sync(0xffffffffu, x[31 - k1].y, plane);
+        float p2x = __shfl_sync(0xffffffffu, x[k1].x, plane), p2y = __shfl_sync(0xffffffffu, x[k1].y, plane);
+#pragma unroll
+        for(int half2 = 0; half2 < 2; half2 ++) {
+          const int reg = half2 == 0 ? k1 : 31 - k1;
+          float2 zn = half2 == 0 ? (lane == 0 ? z0[(32 - k1) & 31] : make_float2(p1x, p1y))
+                                 : (lane == 0 ? z0[(k1 + 1) & 31] : make_float2(p2x, p2y));
+          float2 zk = x[reg];
+          float2 Ak = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+          float2 Bk = make_float2(0.5f * (zk.y + zn.y), 0.5f * (zn.x - zk.x));
+          int m = lane + 32 * reg;
+          int kk = m <= HALF ? m : 1024 - m;
+          float HA = 0.f, HB = 0.f;
+          if(kk < NSPEC - 1) {
+            int l = max(0, kk - 3), u = min(NSPEC - 1, kk + 3);
+            float smA = 0.f, smB = 0.f;
+            for(int q = l; q <= u; q ++) { smA += pbuf[q]; smB += pbuf[NSPEC + q]; }
+            const float cnt = (float)(u - l + 1);
+            int pl = P.psd_lo[kk]; float pr = P.psd_r[kk];
+            float hA = spsd[pl], hB = hasB ? spsd[npsd + pl] : 0.f;
+            if(pr != 0.f) { hA = hA + (spsd[pl + 1] - hA) * pr; if(hasB) hB = hB + (spsd[npsd + pl + 1] - hB) * pr; }
+            if(doA) HA = expf(hA * (2.3025851f / 20.0f)) / sqrtf(smA / cnt * 44100.f / P.fs + 1e-8f);
+            if(doB) HB = expf(hB * (2.3025851f / 20.0f)) / sqrtf(smB / cnt * 44100.f / P.fs + 1e-8f);
+          }
+          float2 a = make_float2(Ak.x * HA, Ak.y * HA), bq = make_float2(Bk.x * HB, Bk.y * HB);
+          if(m == 0) { a.y = 0.f; bq.y = 0.f; }
+          if(reg == 15) { nyqA = a.x; nyqB = bq.x; }
+          x[reg] = make_float2(a.x - bq.y, a.y + bq.x);
+        }
+      }
+      // Nyquist bin (lane 0, k1 = 16) copies the scaled bin 511 held by lane 31, k1 = 15
+      nyqA = __shfl_sync(0xffffffffu, nyqA, 31); nyqB = __shfl_sync(0xffffffffu, nyqB, 31);
+      if(lane == 0) x[16] = make_float2(nyqA, nyqB);
+      __syncwarp();
+      warp_fft1024<true>(x, scratch, tw2, lane);
+      // ---- scale, fades (layer0.c:616-619); park both outputs in the warp's slot
+#pragma unroll
+      for(int r = 0; r < 32; r ++) {
+        int j = lane + 32 * r;
+        float va = x[r].x * inv, vb = x[r].y * inv;
+        if(j < 16) { float g = (float)j / 16.f; va *= g; vb *= g; }
+        if(j >= NF - 16) {
+          double g = 1.0 - (double)((float)(NF - 1 - j) / 16.f);
+          va = (float)((double)va * g); vb = (float)((double)vb * g);
+        }
+        slot[j] = va; slot[1024 + j] = vb;
+      }
+    }
+    if(lane == 0) { fcen[2 * warp] = doA ? cA : -(1 << 30); fcen[2 * warp + 1] = doB ? cB : -(1 << 30); }
+    __syncthreads();
+    // ---- add the round's frames to the output run, ascending frame order (layer0.c:620-624)
+    {
+      int first = -(1 << 30), last = -(1 << 30);
+      for(int f = 0; f < 2 * SHW_WARPS; f ++) if(fcen[f] > -(1 << 29)) { if(first < -(1 << 29)) first = fcen[f]; last = fcen[f]; }
+      if(first > -(1 << 29)) {
+        int s0 = max(oa, first - HALF), s1 = min(min(ob, ny_b), last + HALF);
+        for(int n = s0 + tid; n < s1; n += blockDim.x) {
+          float a = acc[n - oa];
+          for(int f = 0; f < 2 * SHW_WARPS; f ++) {
+            int c = fcen[f];
+            int j = n - c + HALF;
+            if(c > -(1 << 29) && j >= 0 && j < NF)
+              a += ((const float*)(wbase + (f >> 1) * WFFT_SCRATCH_BYTES))[(f & 1) * 1024 + j];
+          }
+          acc[n - oa] = a;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  for(int i = oa + tid; i < ob; i += blockDim.x) {
+    float v = i < ny_b ? acc[i - oa] : 0.f;
+    size_t o = (size_t)b * P.stride + i;
+    P.y_noise[o] = v;
+    if(P.y) P.y[o] = (P.y_sin ? P.y_sin[o] : 0.f) + v;
+  }
+}
+
+static inline size_t shape_warp_smem_bytes(int seg) {
+  return (size_t)1024 * 8 + (size_t)SHW_WARPS * WFFT_SCRATCH_BYTES + (size_t)seg * 4 + 2 * SHW_WARPS * 4 +
+         (size_t)SHW_WARPS * 32 * 8 + 16;
+}
+
+static inline int shape_variant() {
+  static int v = -1;
+  if(v < 0) { const char* e = getenv("LLSM_SHAPE_VARIANT"); v = e ? atoi(e) : 1; }
+  return v;
+}
+
+static inline int launch_noise_shape(const ShapeParams& P, int nutt, cudaStream_t st) {
+  if(shape_variant() == 1 && P.nfft == 1024 && P.npsd <= 512 && P.n_ns <= 1024) {
+    dim3 grid((P.nsamp + P.seg - 1) / P.seg, nutt), block(SHW_THREADS);
+    size_t smem = shape_warp_smem_bytes(P.seg);
+#ifndef LLSM_EMU
+    cudaFuncSetAttribute(noise_shape_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#endif
+    LLSM_LAUNCH(noise_shape_warp_kernel, grid, block, smem, st, P);
+    return 0;
+  }
+  return launch_noise_shape_block(P, nutt, st);
 }

@@ -92,6 +92,14 @@ void build_synth_plan(SynthPlan& p, int nfrm, float fs, float thop, int npsd, in
       p.env_r[i] = r;
       p.env_off[i] = (int)round((double)r);
     }
+    // layer0.c:307 evaluates round((i - 1) * thop * fs + j) in float for every j: where the float sum
+    // keeps the fraction of env_r[i] the indices are contiguous and the kernel takes a fast path
+    p.env_contig.assign(nfrm, 1);
+    for(int i = 0; i < nfrm; i ++)
+      for(int j = 0; j < p.n_env; j ++) {
+        float t = p.env_r[i] + (float)j;
+        if((int)round((double)t) != p.env_off[i] + j) { p.env_contig[i] = 0; break; }
+      }
     make_hanning(p.win_env, p.n_env);
   }
 

@@ -20,6 +20,7 @@ struct SynthPlan {
   int n_env = 0;                      // round(thop * 2.0 * fs) in double
   std::vector<float> env_r;           // (float)((i - 1) * thop * fs)    [nfrm]
   std::vector<int> env_off;           // round(env_r[i])                 [nfrm]
+  std::vector<int> env_contig;        // 1 when round(env_r[i] + j) == env_off[i] + j for every j
   std::vector<float> win_env;         // hanning(n_env)
   // noise shaping STFT (layer0.c:559-603)
   int n_ns = 0;                       // round(thop * fs * 2) in float

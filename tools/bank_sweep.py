@@ -23,7 +23,7 @@ for i in range(10): L.synthesize_harmonics(ctx, conf, d, ny, out=ys)
 e1.record(); torch.cuda.synchronize()
 print(json.dumps({"ms": e0.elapsed_time(e1) / 10, "checksum": float(ys.double().abs().sum())}))
 ''' % ROOT
-for v in sys.argv[1:] or ["0", "1", "2", "3", "4"]:
+for v in sys.argv[1:] or ["0", "1", "2", "3", "4", "5"]:
     env = dict(os.environ, LLSM_BANK_VARIANT=v)
     out = subprocess.run([sys.executable, "-c", CODE], env=env, capture_output=True, text=True)
     print("variant", v, out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-500:])
