@@ -157,6 +157,30 @@ int llsm_b200_analyze_l0_host(llsm_b200_ctx* ctx, const llsm_b200_conf* conf,
   const llsm_b200_aoptions* opt, const float* x, int nx, int xstride,
   const llsm_b200_frames_out* frames, float* x_res);
 
+
+/* ---- layer-1 members (llsm.h:105-108): RD, VTMAGN, VSPHSE per frame, flat ----
+     rd      [B][F]            Rd glottal parameter (every frame, smoothed track)
+     vtmagn  [B][F][nspec]     vocal-tract magnitude response, dB (voiced frames)
+     vsphse  [B][F][maxnhar]   vocal-source harmonic phases (voiced frames)
+     nvs     [B][F]            length of the VSPHSE vector (0 when unvoiced)            */
+typedef struct {
+  float* rd;
+  float* vtmagn;
+  float* vsphse;
+  int*   nvs;
+  int    nspec;          /* LLSM_CONF_NSPEC = nfft / 2 + 1 */
+} llsm_b200_layer1;
+
+/* llsm_chunk_tolayer1 (layer1.c:129-149) for a batch: Rd track (glottal fitting + smoothing),
+   vocal-tract envelope and source phases of every voiced frame. Device pointers. Reads
+   frames->{nfrm_utt, f0, nhar, ampl, phse}. nfft as in the reference call (power of two). */
+int llsm_b200_tolayer1(llsm_b200_ctx* ctx, const llsm_b200_conf* conf,
+  const llsm_b200_frames* frames, int nfft, const llsm_b200_layer1* out);
+/* llsm_chunk_tolayer0 / llsm_frame_tolayer0 (layer1.c:151-201): harmonic model from the layer-1
+   members. Writes nhar / ampl / phse ([B][F], [B][F][maxnhar]). Device pointers. */
+int llsm_b200_tolayer0(llsm_b200_ctx* ctx, const llsm_b200_conf* conf, const int* nfrm_utt,
+  const float* f0, const llsm_b200_layer1* in, int* nhar, float* ampl, float* phse);
+
 #ifdef __cplusplus
 }
 #endif

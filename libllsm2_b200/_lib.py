@@ -42,6 +42,8 @@ def lib():
     L.llsm_b200_analyze_l0.argtypes = [P, C.POINTER(abi.Conf), C.POINTER(abi.AOptions), P, C.c_int,
                                        C.c_int, C.POINTER(abi.FramesOut), P]
     L.llsm_b200_analyze_l0_host.argtypes = L.llsm_b200_analyze_l0.argtypes
+    L.llsm_b200_tolayer1.argtypes = [P, C.POINTER(abi.Conf), C.POINTER(abi.Frames), C.c_int, C.POINTER(abi.Layer1)]
+    L.llsm_b200_tolayer0.argtypes = [P, C.POINTER(abi.Conf), P, P, C.POINTER(abi.Layer1), P, P, P]
     _lib = L
     return L
 

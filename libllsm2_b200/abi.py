@@ -55,3 +55,8 @@ def default_soptions(white_ptr=None, seed=0):
     o.use_iczt, o.iczt_param_a, o.iczt_param_b = 1, 0.275, 2.26
     o.white, o.seed = white_ptr, seed
     return o
+
+
+class Layer1(C.Structure):
+    _fields_ = [("rd", C.c_void_p), ("vtmagn", C.c_void_p), ("vsphse", C.c_void_p), ("nvs", C.c_void_p),
+                ("nspec", C.c_int)]

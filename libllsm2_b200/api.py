@@ -187,3 +187,37 @@ def analyze_l0_host(ctx, conf, x, f0, options=None, want_residual=False):
     if want_residual:
         out["x_res"] = xr
     return out
+
+
+def tolayer1(ctx, conf, frames, nfft):
+    """llsm_chunk_tolayer1 (layer1.c:129-149) on CUDA tensors: returns dict(rd, vtmagn, vsphse, nvs)."""
+    import torch
+    dev = frames["f0"].device
+    B, F, nspec = conf.nutt, conf.nfrm, nfft // 2 + 1
+    out = {"rd": torch.zeros((B, F), dtype=torch.float32, device=dev),
+           "vtmagn": torch.zeros((B, F, nspec), dtype=torch.float32, device=dev),
+           "vsphse": torch.zeros((B, F, conf.maxnhar), dtype=torch.float32, device=dev),
+           "nvs": torch.zeros((B, F), dtype=torch.int32, device=dev)}
+    l1 = abi.Layer1()
+    l1.rd, l1.vtmagn, l1.vsphse, l1.nvs, l1.nspec = (_ptr(out["rd"]), _ptr(out["vtmagn"]), _ptr(out["vsphse"]),
+                                                     _ptr(out["nvs"]), nspec)
+    f = _frames(frames)
+    check(lib().llsm_b200_tolayer1(ctx._h, C.byref(conf), C.byref(f), int(nfft), C.byref(l1)))
+    return out
+
+
+def tolayer0(ctx, conf, f0, layer1, nfrm_utt=None):
+    """llsm_chunk_tolayer0 (layer1.c:151-201) on CUDA tensors: returns dict(nhar, ampl, phse)."""
+    import torch
+    dev = f0.device
+    B, F = conf.nutt, conf.nfrm
+    out = {"nhar": torch.zeros((B, F), dtype=torch.int32, device=dev),
+           "ampl": torch.zeros((B, F, conf.maxnhar), dtype=torch.float32, device=dev),
+           "phse": torch.zeros((B, F, conf.maxnhar), dtype=torch.float32, device=dev)}
+    l1 = abi.Layer1()
+    l1.rd, l1.vtmagn, l1.vsphse, l1.nvs = (_ptr(layer1["rd"]), _ptr(layer1["vtmagn"]), _ptr(layer1["vsphse"]),
+                                           _ptr(layer1["nvs"]))
+    l1.nspec = layer1["vtmagn"].shape[-1]
+    check(lib().llsm_b200_tolayer0(ctx._h, C.byref(conf), _ptr(nfrm_utt), _ptr(f0), C.byref(l1),
+                                   _ptr(out["nhar"]), _ptr(out["ampl"]), _ptr(out["phse"])))
+    return out

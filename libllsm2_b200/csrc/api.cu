@@ -3,6 +3,7 @@
 // device is present.
 #include "driver.h"
 #include "driver_analysis.h"
+#include "driver_layer1.h"
 #include <cstdio>
 #include <cstdarg>
 #include <mutex>
@@ -29,6 +30,7 @@ struct llsm_b200_ctx {
   std::map<AnaKey, std::unique_ptr<AnaPlanDev>> aplans;
   SynthScratch scratch;
   AnaScratch ascratch;
+  std::unique_ptr<L1PlanDev> l1plan;
   DevBuf ny_utt;
   DevBuf stage[24];          // device staging for the *_host entry points
   LaunchCounter lc;
@@ -103,6 +105,7 @@ void llsm_b200_destroy(llsm_b200_ctx* ctx) {
   for(auto& kv : ctx->aplans) kv.second->release();
   ctx->scratch.colored.release(); ctx->scratch.y_exc.release(); ctx->scratch.ny_utt.release();
   ctx->ascratch.release();
+  if(ctx->l1plan) ctx->l1plan->release();
   ctx->ny_utt.release();
   for(auto& s : ctx->stage) s.release();
   if(ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -234,5 +237,6 @@ int llsm_b200_synthesize_l0_host(llsm_b200_ctx* ctx, const llsm_b200_conf* conf,
 }
 
 #include "api_analysis.inc"
+#include "api_layer1.inc"
 
 } // extern "C"

@@ -1,7 +1,7 @@
 // Liljencrants-Fant glottal flow-derivative model: Rd parameterisation (Fant 1995) and the
 // closed-form spectrum of the two LF segments (Doval, d'Alessandro & Henrich 2006).
 // Host + device (used by the layer-1 kernels and by host plans). The conventions are those of the
-// oracle's ciglet shim (oracle/ciglet-shim/ciglet.c, lfmodel_from_rd / lfmodel_spectrum), which the
+// CPU checker's ciglet restatement (lfmodel_from_rd / lfmodel_spectrum there), which the
 // reference calls at layer1.c:100-101,172-173, llsmutils.c:75-76,114-115, layer0.c:186-188,
 // dsputils.c:526-527: te / tp / ta relative to T0, Rap clamped to >= 1e-3, zero-net-flow alpha by
 // bisection, everything in double, struct fields rounded to FP_TYPE (float).

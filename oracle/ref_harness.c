@@ -196,3 +196,66 @@ double ref_time_synthesize_soa(int nrep, int nfrm, float fs, float thop, int max
   llsm_delete_chunk(chunk);
   return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
 }
+
+/* ---- layer 1 (layer1.c) ---- */
+int ref_tolayer1_soa(int nfrm, float fs, float thop, int maxnhar, float lip_radius, int nfft,
+  const float* f0, const int* nhar, const float* ampl, const float* phse,
+  float* rd, float* vtmagn, float* vsphse, int* nvs) {
+  float cf[3] = {2000, 4000, 8000};
+  llsm_chunk* chunk = chunk_from_soa(nfrm, fs, thop, maxnhar, 4, 8, 4, cf, lip_radius,
+    f0, nhar, ampl, phse, NULL, NULL, NULL, NULL, NULL, NULL);
+  llsm_chunk_tolayer1(chunk, nfft);
+  int nspec = nfft / 2 + 1;
+  for(int i = 0; i < nfrm; i ++) {
+    FP_TYPE* r = llsm_container_get(chunk -> frames[i], LLSM_FRAME_RD);
+    FP_TYPE* vt = llsm_container_get(chunk -> frames[i], LLSM_FRAME_VTMAGN);
+    FP_TYPE* vs = llsm_container_get(chunk -> frames[i], LLSM_FRAME_VSPHSE);
+    rd[i] = r != NULL ? r[0] : -1;
+    memset(vtmagn + (size_t)i * nspec, 0, nspec * sizeof(float));
+    memset(vsphse + (size_t)i * maxnhar, 0, maxnhar * sizeof(float));
+    nvs[i] = 0;
+    if(vt != NULL) memcpy(vtmagn + (size_t)i * nspec, vt, nspec * sizeof(float));
+    if(vs != NULL) {
+      nvs[i] = llsm_fparray_length(vs);
+      memcpy(vsphse + (size_t)i * maxnhar, vs, nvs[i] * sizeof(float));
+    }
+  }
+  llsm_delete_chunk(chunk);
+  return 0;
+}
+
+int ref_tolayer0_soa(int nfrm, float fs, float thop, int maxnhar, float lip_radius, int nspec,
+  const float* f0, const float* rd, const float* vtmagn, const float* vsphse, const int* nvs,
+  int* nhar_out, float* ampl, float* phse) {
+  float cf[3] = {2000, 4000, 8000};
+  llsm_chunk* chunk = chunk_from_soa(nfrm, fs, thop, maxnhar, 4, 8, 4, cf, lip_radius,
+    f0, NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL);
+  llsm_container_attach(chunk -> conf, LLSM_CONF_NSPEC, llsm_create_int(nspec), llsm_delete_int, llsm_copy_int);
+  for(int i = 0; i < nfrm; i ++) {
+    llsm_container* fr = chunk -> frames[i];
+    llsm_container_attach(fr, LLSM_FRAME_HM, NULL, NULL, NULL);
+    llsm_container_attach(fr, LLSM_FRAME_RD, llsm_create_fp(rd[i]), llsm_delete_fp, llsm_copy_fp);
+    if(f0[i] > 0) {
+      FP_TYPE* vt = llsm_create_fparray(nspec);
+      memcpy(vt, vtmagn + (size_t)i * nspec, nspec * sizeof(float));
+      FP_TYPE* vs = llsm_create_fparray(nvs[i]);
+      memcpy(vs, vsphse + (size_t)i * maxnhar, nvs[i] * sizeof(float));
+      llsm_container_attach(fr, LLSM_FRAME_VTMAGN, vt, llsm_delete_fparray, llsm_copy_fparray);
+      llsm_container_attach(fr, LLSM_FRAME_VSPHSE, vs, llsm_delete_fparray, llsm_copy_fparray);
+    }
+  }
+  llsm_chunk_tolayer0(chunk);
+  for(int i = 0; i < nfrm; i ++) {
+    llsm_hmframe* hm = llsm_container_get(chunk -> frames[i], LLSM_FRAME_HM);
+    int n = hm != NULL ? hm -> nhar : 0;
+    nhar_out[i] = n;
+    memset(ampl + (size_t)i * maxnhar, 0, maxnhar * sizeof(float));
+    memset(phse + (size_t)i * maxnhar, 0, maxnhar * sizeof(float));
+    if(n > 0) {
+      memcpy(ampl + (size_t)i * maxnhar, hm -> ampl, n * sizeof(float));
+      memcpy(phse + (size_t)i * maxnhar, hm -> phse, n * sizeof(float));
+    }
+  }
+  llsm_delete_chunk(chunk);
+  return 0;
+}

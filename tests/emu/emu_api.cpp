@@ -60,3 +60,16 @@ extern "C" int emu_analyze_l0(const llsm_b200_conf* conf, const llsm_b200_aoptio
   sc.release(); ap.release(); sp.release();
   return rc;
 }
+
+#include "../../libllsm2_b200/csrc/driver_layer1.h"
+extern "C" int emu_tolayer1(const llsm_b200_conf* conf, const llsm_b200_frames* fr, int nfft, const llsm_b200_layer1* out) {
+  L1PlanDev lp; if(lp.build(nullptr) != 0) return -100;
+  int rc = run_tolayer1(lp, *conf, *fr, nfft, *out, nullptr, nullptr);
+  lp.release(); return rc;
+}
+extern "C" int emu_tolayer0(const llsm_b200_conf* conf, const float* f0, const llsm_b200_layer1* in, int* nhar,
+  float* ampl, float* phse) {
+  L1PlanDev lp; if(lp.build(nullptr) != 0) return -100;
+  int rc = run_tolayer0(lp, *conf, nullptr, f0, *in, nhar, ampl, phse, nullptr, nullptr);
+  lp.release(); return rc;
+}

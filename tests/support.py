@@ -157,3 +157,45 @@ def frames_out_struct(o):
 def phase_err(a, b):
     d = np.asarray(a, np.float64) - np.asarray(b, np.float64)
     return (d + np.pi) % (2 * np.pi) - np.pi
+
+
+def ref_tolayer1(fr, conf, nfft):
+    """Reference llsm_chunk_tolayer1 per utterance -> dict(rd, vtmagn, vsphse, nvs)."""
+    lib = load_ref()
+    B, F, nspec = conf.nutt, conf.nfrm, nfft // 2 + 1
+    o = dict(rd=np.zeros((B, F), np.float32), vtmagn=np.zeros((B, F, nspec), np.float32),
+             vsphse=np.zeros((B, F, conf.maxnhar), np.float32), nvs=np.zeros((B, F), np.int32))
+    for b in range(B):
+        lib.ref_tolayer1_soa(F, C.c_float(conf.fs), C.c_float(conf.thop), conf.maxnhar, C.c_float(conf.lip_radius),
+                             nfft, _p(np.ascontiguousarray(fr["f0"][b])), _p(np.ascontiguousarray(fr["nhar"][b])),
+                             _p(np.ascontiguousarray(fr["ampl"][b])), _p(np.ascontiguousarray(fr["phse"][b])),
+                             _p(o["rd"][b]), _p(o["vtmagn"][b]), _p(o["vsphse"][b]), _p(o["nvs"][b]))
+    return o
+
+
+def ref_tolayer0(f0, l1, conf):
+    lib = load_ref()
+    B, F = conf.nutt, conf.nfrm
+    nspec = l1["vtmagn"].shape[-1]
+    o = dict(nhar=np.zeros((B, F), np.int32), ampl=np.zeros((B, F, conf.maxnhar), np.float32),
+             phse=np.zeros((B, F, conf.maxnhar), np.float32))
+    for b in range(B):
+        lib.ref_tolayer0_soa(F, C.c_float(conf.fs), C.c_float(conf.thop), conf.maxnhar, C.c_float(conf.lip_radius),
+                             nspec, _p(np.ascontiguousarray(f0[b])), _p(np.ascontiguousarray(l1["rd"][b])),
+                             _p(np.ascontiguousarray(l1["vtmagn"][b])), _p(np.ascontiguousarray(l1["vsphse"][b])),
+                             _p(np.ascontiguousarray(l1["nvs"][b])), _p(o["nhar"][b]), _p(o["ampl"][b]), _p(o["phse"][b]))
+    return o
+
+
+def check_layer1(o, ref, voiced):
+    """Parity bars for layer-1 members: Rd 1e-5, VTMAGN 1e-2 dB, VSPHSE 1e-4 rad, lengths equal."""
+    assert np.array_equal(o["nvs"], ref["nvs"])
+    assert np.abs(o["rd"] - ref["rd"]).max() < 1e-5
+    assert np.abs(o["vtmagn"] - ref["vtmagn"])[voiced].max() < 1e-2
+    assert np.abs(phase_err(o["vsphse"], ref["vsphse"])).max() < 1e-4
+
+
+def check_layer0_from_l1(o, ref):
+    assert np.array_equal(o["nhar"], ref["nhar"])
+    assert (np.abs(o["ampl"] - ref["ampl"]) / (np.abs(ref["ampl"]) + 1e-9)).max() < 1e-4
+    assert np.abs(phase_err(o["phse"], ref["phse"])).max() < 1e-4
