@@ -181,6 +181,19 @@ int llsm_b200_tolayer1(llsm_b200_ctx* ctx, const llsm_b200_conf* conf,
 int llsm_b200_tolayer0(llsm_b200_ctx* ctx, const llsm_b200_conf* conf, const int* nfrm_utt,
   const float* f0, const llsm_b200_layer1* in, int* nhar, float* ampl, float* phse);
 
+
+/* ---- layer-1 synthesis: llsm_synthesize with use_l1 = 1 (layer0.c:148-287 deterministic part: pulse
+        tracker, llsm_make_filtered_pulse llsmutils.c:132-201, HM <-> PbP cross-fade; then the layer-0
+        noise path). Device pointers.
+   l1      layer-1 members (in); pbpsyn [B][F] (LLSM_FRAME_PBPSYN flags, NULL = none set)
+   frames  noise model (psd, psdres, edc, enhar, eampl, ephse) and f0 are required; when nhar / ampl /
+           phse are all non-NULL they are the stored harmonic models, otherwise the harmonic frames are
+           derived from layer 1 on the fly (layer0.c:264-265).
+   User llsm_pbpeffect callbacks are host functions and are not part of this entry point. */
+int llsm_b200_synthesize_l1(llsm_b200_ctx* ctx, const llsm_b200_conf* conf,
+  const llsm_b200_frames* frames, const llsm_b200_layer1* l1, const int* pbpsyn,
+  const llsm_b200_soptions* opt, const llsm_b200_output* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -43,6 +43,8 @@ def lib():
                                        C.c_int, C.POINTER(abi.FramesOut), P]
     L.llsm_b200_analyze_l0_host.argtypes = L.llsm_b200_analyze_l0.argtypes
     L.llsm_b200_tolayer1.argtypes = [P, C.POINTER(abi.Conf), C.POINTER(abi.Frames), C.c_int, C.POINTER(abi.Layer1)]
+    L.llsm_b200_synthesize_l1.argtypes = [P, C.POINTER(abi.Conf), C.POINTER(abi.Frames), C.POINTER(abi.Layer1), P,
+                                          C.POINTER(abi.SOptions), C.POINTER(abi.Output)]
     L.llsm_b200_tolayer0.argtypes = [P, C.POINTER(abi.Conf), P, P, C.POINTER(abi.Layer1), P, P, P]
     _lib = L
     return L

@@ -221,3 +221,23 @@ def tolayer0(ctx, conf, f0, layer1, nfrm_utt=None):
     check(lib().llsm_b200_tolayer0(ctx._h, C.byref(conf), _ptr(nfrm_utt), _ptr(f0), C.byref(l1),
                                    _ptr(out["nhar"]), _ptr(out["ampl"]), _ptr(out["phse"])))
     return out
+
+
+def synthesize_l1(ctx, conf, frames, layer1, pbpsyn=None, white=None, seed=0, options=None, out=None):
+    """llsm_synthesize with use_l1 (layer0.c:148-287) on CUDA tensors. frames: noise model (+ optional
+    stored HM); layer1: dict(rd, vtmagn, vsphse, nvs); pbpsyn: [B][F] int32 flags or None."""
+    import torch
+    ny = output_length(conf.nfrm, conf.thop, conf.fs)
+    dev = frames["f0"].device
+    if out is None:
+        out = {k: torch.empty((conf.nutt, ny), dtype=torch.float32, device=dev) for k in ("y", "y_sin", "y_noise")}
+    o = abi.Output()
+    o.y, o.y_sin, o.y_noise, o.stride = _ptr(out["y"]), _ptr(out["y_sin"]), _ptr(out["y_noise"]), out["y"].shape[1]
+    l1 = abi.Layer1()
+    l1.rd, l1.vtmagn, l1.vsphse, l1.nvs = (_ptr(layer1["rd"]), _ptr(layer1["vtmagn"]), _ptr(layer1["vsphse"]),
+                                           _ptr(layer1["nvs"]))
+    l1.nspec = layer1["vtmagn"].shape[-1]
+    f = _frames(frames)
+    so = _soptions(options, white, seed)
+    check(lib().llsm_b200_synthesize_l1(ctx._h, C.byref(conf), C.byref(f), C.byref(l1), _ptr(pbpsyn), C.byref(so), C.byref(o)))
+    return out

@@ -4,6 +4,7 @@
 #include "driver.h"
 #include "driver_analysis.h"
 #include "driver_layer1.h"
+#include "driver_pbp.h"
 #include <cstdio>
 #include <cstdarg>
 #include <mutex>
@@ -31,6 +32,7 @@ struct llsm_b200_ctx {
   SynthScratch scratch;
   AnaScratch ascratch;
   std::unique_ptr<L1PlanDev> l1plan;
+  PbpScratch pbp;
   DevBuf ny_utt;
   DevBuf stage[24];          // device staging for the *_host entry points
   LaunchCounter lc;
@@ -106,6 +108,7 @@ void llsm_b200_destroy(llsm_b200_ctx* ctx) {
   ctx->scratch.colored.release(); ctx->scratch.y_exc.release(); ctx->scratch.ny_utt.release();
   ctx->ascratch.release();
   if(ctx->l1plan) ctx->l1plan->release();
+  ctx->pbp.release();
   ctx->ny_utt.release();
   for(auto& s : ctx->stage) s.release();
   if(ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);

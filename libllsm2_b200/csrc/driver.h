@@ -49,7 +49,8 @@ struct DevBuf {
 // device-resident copy of a SynthPlan
 struct SynthPlanDev {
   SynthPlan h;
-  int *hm_base = nullptr, *env_off = nullptr, *psd_lo = nullptr, *env_contig = nullptr;
+  int *hm_base = nullptr, *env_off = nullptr, *psd_lo = nullptr, *env_contig = nullptr, *base_trunc = nullptr;
+  float* zero_frac = nullptr;
   float *hm_frac = nullptr, *win_hm = nullptr, *env_r = nullptr, *win_env = nullptr,
         *win_ns = nullptr, *psd_r = nullptr;
   float2* tw_ns = nullptr;
@@ -73,7 +74,8 @@ struct SynthPlanDev {
     rc |= up(&hm_base, h.hm_base, st); rc |= up(&hm_frac, h.hm_frac, st);
     rc |= up(&win_hm, h.win_hm, st);   rc |= up(&env_r, h.env_r, st);
     rc |= up(&env_off, h.env_off, st); rc |= up(&win_env, h.win_env, st);
-    rc |= up(&env_contig, h.env_contig, st);
+    rc |= up(&env_contig, h.env_contig, st); rc |= up(&base_trunc, h.base_trunc, st);
+    { std::vector<float> z(nfrm, 0.0f); rc |= up(&zero_frac, z, st); if(dev_sync(st) != 0) rc = -1; }
     rc |= up(&win_ns, h.win_ns, st);   rc |= up(&psd_lo, h.psd_lo, st);
     rc |= up(&psd_r, h.psd_r, st);
     float* twd = nullptr; rc |= up(&twd, tw, st); tw_ns = (float2*)twd;
@@ -117,6 +119,12 @@ static inline int run_harmonics(const SynthPlanDev& pd, const llsm_b200_conf& co
   return 0;
 }
 
+// Noise component + final mix (layer0.c:652-659): templates, excitation, shaping, y = y_sin + y_noise.
+// out.y_sin must already hold the harmonic component.
+static inline int run_noise_part(const SynthPlanDev& pd, SynthScratch& sc, const llsm_b200_conf& conf,
+  const llsm_b200_frames& fr, const llsm_b200_soptions& opt, const llsm_b200_output& out,
+  const int* ny_utt_dev, cudaStream_t st, LaunchCounter* lc);
+
 // Full layer-0 synthesis on device pointers (llsm_synthesize, layer0.c:636-664).
 static inline int run_synth_l0(const SynthPlanDev& pd, SynthScratch& sc, const llsm_b200_conf& conf,
   const llsm_b200_frames& fr, const llsm_b200_soptions& opt, const llsm_b200_output& out,
@@ -125,14 +133,22 @@ static inline int run_synth_l0(const SynthPlanDev& pd, SynthScratch& sc, const l
   const int B = conf.nutt, nch = conf.nchannel;
   if(nch < 1 || nch > LLSM_B200_MAXCHANNEL) return LLSM_B200_EINVAL;
   if(out.stride < h.ny) return LLSM_B200_EINVAL;
-  const int tstride = (h.nt + 3) & ~3;
-  if(sc.colored.reserve((size_t)B * nch * tstride * 4) != 0) return LLSM_B200_ENOMEM;
-  if(sc.y_exc.reserve((size_t)B * out.stride * 4) != 0) return LLSM_B200_ENOMEM;
 
   // 1. harmonic component
   int rc = run_harmonics(pd, conf, fr, &opt, ny_utt_dev, out.y_sin, h.ny, out.stride, out.stride,
     st, lc);
   if(rc != 0) return rc;
+  return run_noise_part(pd, sc, conf, fr, opt, out, ny_utt_dev, st, lc);
+}
+
+static inline int run_noise_part(const SynthPlanDev& pd, SynthScratch& sc, const llsm_b200_conf& conf,
+  const llsm_b200_frames& fr, const llsm_b200_soptions& opt, const llsm_b200_output& out,
+  const int* ny_utt_dev, cudaStream_t st, LaunchCounter* lc) {
+  const SynthPlan& h = pd.h;
+  const int B = conf.nutt, nch = conf.nchannel;
+  const int tstride = (h.nt + 3) & ~3;
+  if(sc.colored.reserve((size_t)B * nch * tstride * 4) != 0) return LLSM_B200_ENOMEM;
+  if(sc.y_exc.reserve((size_t)B * out.stride * 4) != 0) return LLSM_B200_ENOMEM;
 
   // 2. band-limited noise templates (dsputils.c:385-394): white fill, chunk-parallel filtfilt
   unsigned mask = 0;

@@ -35,6 +35,7 @@ struct BankParams {
   float fs;
   int has_options;          // 0: options == NULL (always sinusoid bank, llsmutils.c:48-49)
   int use_iczt; float iczt_a, iczt_b;
+  const int* frame_mask;    // [B][nfrm] optional: 0 = skip the frame (PbP path, layer0.c:261)
   int npass;                // frame slots per CTA = warps * npass
   float* y_sin;             // [B][stride]
 };
@@ -76,7 +77,8 @@ __global__ void __launch_bounds__(NTHR, MINB) hm_bank_ola_kernel(BankParams P) {
     float f0 = 0; int nh = 0;
     if(inrange) { f0 = P.f0[row + f]; nh = P.nhar[row + f]; }
     if(nh > 2048) nh = 2048;               // layer0.c:119,130
-    const bool voiced = inrange && f0 > 0 && nh > 0;  // layer0.c:125 (f0 == 0 skips the frame)
+    bool voiced = inrange && f0 > 0 && nh > 0;        // layer0.c:125 (f0 == 0 skips the frame)
+    if(voiced && P.frame_mask) voiced = P.frame_mask[row + f] != 0;
     if(lane == 0) {
       sb[s] = inrange ? P.hm_base[f] : (f < 0 ? -(1 << 28) : (1 << 28));
       sv[s] = voiced ? 1 : 0;
@@ -679,6 +681,8 @@ __global__ void __launch_bounds__(SHW_THREADS, 2) noise_shape_warp_kernel(ShapeP
   const float inv = 1.0f / 1024.0f;
   __syncthreads();
 
+  const float psc = 44100.f / P.fs;
+  const float inv_wsqr = 1.0f / P.wsqr;
   for(int r0 = ia; r0 < ib; r0 += 2 * SHW_WARPS) {
     const int i = r0 + 2 * warp;                 // this warp's pair (i, i + 1)
     const bool hasA = i < ib, hasB = i + 1 < ib;
@@ -698,110 +702,138 @@ __global__ void __launch_bounds__(SHW_THREADS, 2) noise_shape_warp_kernel(ShapeP
       doB = hasB && ! (mxB < -100.f);
     }
     if(doA || doB) {                             // warp-uniform
-      // ---- load the two windowed frames: element j = lane + 32 r  (layer0.c:588-592)
       float2 x[32];
-#pragma unroll
-      for(int r = 0; r < 32; r ++) {
-        int j = lane + 32 * r;
-        int jj = j - HALF + hw;
-        float va = 0.f, vb = 0.f;
-        if(jj >= 0 && jj < P.n_ns) {
-          float w = P.win[jj];
-          int ia2 = cA + jj - hw, ib2 = cB + jj - hw;
-          if(doA && ia2 >= 0 && ia2 < ny_b) va = exc[ia2] * w;
-          if(doB && ib2 >= 0 && ib2 < ny_b) vb = exc[ib2] * w;
-        }
-        x[r] = make_float2(va, vb);
-      }
-      warp_fft1024<false>(x, scratch, tw2, lane);
-      // ---- spectra of the two frames from Z = FFT(a + i b): with the partner bin Zn = Z[N - m],
-      //      A = (Z + conj Zn) / 2, B = (Z - conj Zn) / (2i). Bin m = lane + 32 k1; its partner sits in
-      //      lane (32 - lane) % 32, register 31 - k1 (lane 0: its own register (32 - k1) % 32, read
-      //      back from a small shared copy).
       const int plane = (32 - lane) & 31;
-      if(lane == 0) {
-#pragma unroll
-        for(int k1 = 0; k1 < 32; k1 ++) z0[k1] = x[k1];
-      }
-      __syncwarp();
-      // PSDs of bins 0..512 into shared memory (dsputils.c:237-244)
-#pragma unroll
-      for(int k1 = 0; k1 <= 16; k1 ++) {
-        float px = __shfl_sync(0xffffffffu, x[31 - k1].x, plane);
-        float py = __shfl_sync(0xffffffffu, x[31 - k1].y, plane);
-        float2 zn = lane == 0 ? z0[(32 - k1) & 31] : make_float2(px, py);
-        float2 zk = x[k1];
-        int m = lane + 32 * k1;
-        if(m <= HALF) {
-          float ax = 0.5f * (zk.x + zn.x), ay = 0.5f * (zk.y - zn.y);
-          float bx = 0.5f * (zk.y + zn.y), by = 0.5f * (zn.x - zk.x);
-          pbuf[m] = (ax * ax + ay * ay) / P.wsqr;
-          pbuf[NSPEC + m] = (bx * bx + by * by) / P.wsqr;
-        }
-      }
-      // model PSD (+ residual) (layer0.c:598-601)
-      for(int h = 0; h < 2; h ++) {
-        if(h == 1 && ! hasB) break;
-        const float* psd = P.psd + (row + i + h) * (size_t)npsd;
-        const float* res = P.psdres ? P.psdres + (row + i + h) * (size_t)npsd : nullptr;
-        for(int j = lane; j < npsd; j += 32) {
-          float v = psd[j];
-          if(res) v = (float)((double)v + ((double)res[j] - resbias));
-          spsd[h * npsd + j] = v;
-        }
-      }
-      __syncwarp();
-      // ---- gains (layer0.c:597-612) and re-packing W = A' + i B'; registers k1 and 31 - k1 are
-      //      rewritten together so that every partner is read before it is overwritten
-      float nyqA = 0.f, nyqB = 0.f;              // Re of the scaled bin 511 (lane 31, register 15)
-#pragma unroll
-      for(int k1 = 0; k1 < 16; k1 ++) {
-        float p1x = __shfl_sync(0xffffffffu, x[31 - k1].x, plane), p1y = __shfl_sync(0xffffffffu, x[31 - k1].y, plane);
-        float p2x = __shfl_sync(0xffffffffu, x[k1].x, plane), p2y = __shfl_sync(0xffffffffu, x[k1].y, plane);
-#pragma unroll
-        for(int half2 = 0; half2 < 2; half2 ++) {
-          const int reg = half2 == 0 ? k1 : 31 - k1;
-          float2 zn = half2 == 0 ? (lane == 0 ? z0[(32 - k1) & 31] : make_float2(p1x, p1y))
-                                 : (lane == 0 ? z0[(k1 + 1) & 31] : make_float2(p2x, p2y));
-          float2 zk = x[reg];
-          float2 Ak = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
-          float2 Bk = make_float2(0.5f * (zk.y + zn.y), 0.5f * (zn.x - zk.x));
-          int m = lane + 32 * reg;
-          int kk = m <= HALF ? m : 1024 - m;
-          float HA = 0.f, HB = 0.f;
-          if(kk < NSPEC - 1) {
-            int l = max(0, kk - 3), u = min(NSPEC - 1, kk + 3);
-            float smA = 0.f, smB = 0.f;
-            for(int q = l; q <= u; q ++) { smA += pbuf[q]; smB += pbuf[NSPEC + q]; }
-            const float cnt = (float)(u - l + 1);
-            int pl = P.psd_lo[kk]; float pr = P.psd_r[kk];
-            float hA = spsd[pl], hB = hasB ? spsd[npsd + pl] : 0.f;
-            if(pr != 0.f) { hA = hA + (spsd[pl + 1] - hA) * pr; if(hasB) hB = hB + (spsd[npsd + pl + 1] - hB) * pr; }
-            if(doA) HA = expf(hA * (2.3025851f / 20.0f)) / sqrtf(smA / cnt * 44100.f / P.fs + 1e-8f);
-            if(doB) HB = expf(hB * (2.3025851f / 20.0f)) / sqrtf(smB / cnt * 44100.f / P.fs + 1e-8f);
+#pragma unroll 1
+      for(int pass = 0; pass < 2; pass ++) {     // 0: analysis FFT, 1: synthesis IFFT (shared FFT code)
+        if(pass == 0) {
+          // ---- load the two windowed frames (layer0.c:588-592) through shared memory (rolled loop:
+          //      small code), then pick element j = lane + 32 r into register r
+#pragma unroll 1
+          for(int r = 0; r < 32; r ++) {
+            int j = lane + 32 * r;
+            int jj = j - HALF + hw;
+            float va = 0.f, vb = 0.f;
+            if(jj >= 0 && jj < P.n_ns) {
+              float w = P.win[jj];
+              int ia2 = cA + jj - hw, ib2 = cB + jj - hw;
+              if(doA && ia2 >= 0 && ia2 < ny_b) va = exc[ia2] * w;
+              if(doB && ib2 >= 0 && ib2 < ny_b) vb = exc[ib2] * w;
+            }
+            scratch[j] = make_float2(va, vb);
           }
-          float2 a = make_float2(Ak.x * HA, Ak.y * HA), bq = make_float2(Bk.x * HB, Bk.y * HB);
-          if(m == 0) { a.y = 0.f; bq.y = 0.f; }
-          if(reg == 15) { nyqA = a.x; nyqB = bq.x; }
-          x[reg] = make_float2(a.x - bq.y, a.y + bq.x);
-        }
-      }
-      // Nyquist bin (lane 0, k1 = 16) copies the scaled bin 511 held by lane 31, k1 = 15
-      nyqA = __shfl_sync(0xffffffffu, nyqA, 31); nyqB = __shfl_sync(0xffffffffu, nyqB, 31);
-      if(lane == 0) x[16] = make_float2(nyqA, nyqB);
-      __syncwarp();
-      warp_fft1024<true>(x, scratch, tw2, lane);
-      // ---- scale, fades (layer0.c:616-619); park both outputs in the warp's slot
+          __syncwarp();
 #pragma unroll
-      for(int r = 0; r < 32; r ++) {
-        int j = lane + 32 * r;
-        float va = x[r].x * inv, vb = x[r].y * inv;
-        if(j < 16) { float g = (float)j / 16.f; va *= g; vb *= g; }
-        if(j >= NF - 16) {
-          double g = 1.0 - (double)((float)(NF - 1 - j) / 16.f);
-          va = (float)((double)va * g); vb = (float)((double)vb * g);
+          for(int r = 0; r < 32; r ++) x[r] = scratch[lane + 32 * r];
+          __syncwarp();
         }
-        slot[j] = va; slot[1024 + j] = vb;
+        warp_fft1024(x, scratch, tw2, lane, pass);
+        if(pass == 0) {
+          // ---- spectra of the two frames from Z = FFT(a + i b): with the partner bin Zn = Z[N - m],
+          //      A = (Z + conj Zn) / 2, B = (Z - conj Zn) / (2i). Bin m = lane + 32 k1; its partner sits
+          //      in lane (32 - lane) % 32, register 31 - k1 (lane 0: its own register (32 - k1) % 32,
+          //      read back from a small shared copy).
+          if(lane == 0) {
+#pragma unroll
+            for(int k1 = 0; k1 < 32; k1 ++) z0[k1] = x[k1];
+          }
+          __syncwarp();
+          // PSDs of bins 0..512 into shared memory (dsputils.c:237-244)
+#pragma unroll
+          for(int k1 = 0; k1 <= 16; k1 ++) {
+            float px = __shfl_sync(0xffffffffu, x[31 - k1].x, plane);
+            float py = __shfl_sync(0xffffffffu, x[31 - k1].y, plane);
+            float2 zn = lane == 0 ? z0[(32 - k1) & 31] : make_float2(px, py);
+            float2 zk = x[k1];
+            int m = lane + 32 * k1;
+            if(m <= HALF) {
+              float ax = 0.5f * (zk.x + zn.x), ay = 0.5f * (zk.y - zn.y);
+              float bx = 0.5f * (zk.y + zn.y), by = 0.5f * (zn.x - zk.x);
+              pbuf[m] = (ax * ax + ay * ay) * inv_wsqr;
+              pbuf[NSPEC + m] = (bx * bx + by * by) * inv_wsqr;
+            }
+          }
+          // model PSD (+ residual) (layer0.c:598-601)
+          for(int h = 0; h < 2; h ++) {
+            if(h == 1 && ! hasB) break;
+            const float* psd = P.psd + (row + i + h) * (size_t)npsd;
+            const float* res = P.psdres ? P.psdres + (row + i + h) * (size_t)npsd : nullptr;
+            for(int j = lane; j < npsd; j += 32) {
+              float v = psd[j];
+              if(res) v = (float)((double)v + ((double)res[j] - resbias));
+              spsd[h * npsd + j] = v;
+            }
+          }
+          __syncwarp();
+          // ---- gains (layer0.c:597-605), in place over the PSDs: block t = bins 32 t .. 32 t + 31 is
+          //      overwritten one iteration late, after block t + 1 has read its 3-bin margin
+          {
+            float hAp = 0.f, hBp = 0.f;
+#pragma unroll 1
+            for(int t = 0; t <= 16; t ++) {
+              const int kk = lane + 32 * t;
+              float HA = 0.f, HB = 0.f;
+              if(t < 16) {
+                int l = max(0, kk - 3), u = min(NSPEC - 1, kk + 3);
+                float smA = 0.f, smB = 0.f;
+                for(int q = l; q <= u; q ++) { smA += pbuf[q]; smB += pbuf[NSPEC + q]; }
+                const float rc = psc / (float)(u - l + 1);
+                int pl = P.psd_lo[kk]; float pr = P.psd_r[kk];
+                float hA = spsd[pl], hB = hasB ? spsd[npsd + pl] : 0.f;
+                if(pr != 0.f) { hA = hA + (spsd[pl + 1] - hA) * pr; if(hasB) hB = hB + (spsd[npsd + pl + 1] - hB) * pr; }
+                if(doA) HA = expf(hA * (2.3025851f / 20.0f)) * rsqrtf(smA * rc + 1e-8f);
+                if(doB) HB = expf(hB * (2.3025851f / 20.0f)) * rsqrtf(smB * rc + 1e-8f);
+              }
+              __syncwarp();
+              if(t >= 1) { pbuf[kk - 32] = hAp; pbuf[NSPEC + kk - 32] = hBp; }
+              hAp = HA; hBp = HB;
+            }
+            __syncwarp();
+          }
+          // ---- re-packing W = HA A + i HB B; registers k1 and 31 - k1 are rewritten together so that
+          //      every partner is read before it is overwritten
+          float nyqA = 0.f, nyqB = 0.f;          // Re of the scaled bin 511 (lane 31, register 15)
+#pragma unroll
+          for(int k1 = 0; k1 < 16; k1 ++) {
+            float p1x = __shfl_sync(0xffffffffu, x[31 - k1].x, plane), p1y = __shfl_sync(0xffffffffu, x[31 - k1].y, plane);
+            float p2x = __shfl_sync(0xffffffffu, x[k1].x, plane), p2y = __shfl_sync(0xffffffffu, x[k1].y, plane);
+#pragma unroll
+            for(int half2 = 0; half2 < 2; half2 ++) {
+              const int reg = half2 == 0 ? k1 : 31 - k1;
+              float2 zn = half2 == 0 ? (lane == 0 ? z0[(32 - k1) & 31] : make_float2(p1x, p1y))
+                                     : (lane == 0 ? z0[(k1 + 1) & 31] : make_float2(p2x, p2y));
+              float2 zk = x[reg];
+              int m = lane + 32 * reg;
+              int kk = m <= HALF ? m : 1024 - m;
+              float HA = kk < NSPEC - 1 ? pbuf[kk] : 0.f, HB = kk < NSPEC - 1 ? pbuf[NSPEC + kk] : 0.f;
+              float2 a = make_float2(0.5f * (zk.x + zn.x) * HA, 0.5f * (zk.y - zn.y) * HA);
+              float2 bq = make_float2(0.5f * (zk.y + zn.y) * HB, 0.5f * (zn.x - zk.x) * HB);
+              if(m == 0) { a.y = 0.f; bq.y = 0.f; }
+              if(reg == 15) { nyqA = a.x; nyqB = bq.x; }
+              x[reg] = make_float2(a.x - bq.y, a.y + bq.x);
+            }
+          }
+          // Nyquist bin (lane 0, register 16) copies the scaled bin 511 held by lane 31, register 15
+          nyqA = __shfl_sync(0xffffffffu, nyqA, 31); nyqB = __shfl_sync(0xffffffffu, nyqB, 31);
+          if(lane == 0) x[16] = make_float2(nyqA, nyqB);
+          __syncwarp();
+        } else {
+          // ---- scale and park both outputs in the warp's slot; fades (layer0.c:616-619) touch only the
+          //      first and last 16 samples
+#pragma unroll
+          for(int r = 0; r < 32; r ++) {
+            int j = lane + 32 * r;
+            slot[j] = x[r].x * inv; slot[1024 + j] = x[r].y * inv;
+          }
+          __syncwarp();
+          if(lane < 16) {
+            float g = (float)lane / 16.f;
+            slot[lane] *= g; slot[1024 + lane] *= g;
+            int j = NF - 16 + lane;
+            double g2 = 1.0 - (double)((float)(NF - 1 - j) / 16.f);
+            slot[j] = (float)((double)slot[j] * g2); slot[1024 + j] = (float)((double)slot[1024 + j] * g2);
+          }
+        }
       }
     }
     if(lane == 0) { fcen[2 * warp] = doA ? cA : -(1 << 30); fcen[2 * warp + 1] = doB ? cB : -(1 << 30); }

@@ -71,10 +71,12 @@ void build_synth_plan(SynthPlan& p, int nfrm, float fs, float thop, int npsd, in
   {
     float hop = thop * fs;
     p.n_hm = (int)(round((double)hop) * 2);
-    p.hm_base.resize(nfrm); p.hm_frac.resize(nfrm);
+    p.hm_base.resize(nfrm); p.hm_frac.resize(nfrm); p.base_trunc.resize(nfrm);
+    p.hop_f = hop;
     for(int i = 0; i < nfrm; i ++) {
       float rawidx = (float)i * thop;
       rawidx = rawidx * fs;
+      p.base_trunc[i] = (int)rawidx;
       int baseidx = (int)round((double)rawidx);
       p.hm_base[i] = baseidx;
       p.hm_frac[i] = rawidx - (float)baseidx;

@@ -16,6 +16,8 @@ struct SynthPlan {
   std::vector<int> hm_base;           // round(i * thop * fs)            [nfrm]
   std::vector<float> hm_frac;         // rawidx - baseidx (float)        [nfrm]
   std::vector<float> win_hm;          // hanning(n_hm)
+  std::vector<int> base_trunc;        // (int)(i * thop * fs), the PbP path's positions (layer0.c:173)
+  float hop_f = 0;                    // thop * fs as a float product
   // noise envelope OLA (layer0.c:293-309)
   int n_env = 0;                      // round(thop * 2.0 * fs) in double
   std::vector<float> env_r;           // (float)((i - 1) * thop * fs)    [nfrm]

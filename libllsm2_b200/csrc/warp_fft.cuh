@@ -65,26 +65,34 @@ __device__ __forceinline__ void wfft_build_tw2(float2* tw2, const float2* __rest
 }
 
 // x[r] = element (lane + 32 r) on entry and on exit. `scratch` = WFFT_SCRATCH_BYTES of shared
-// memory private to the warp. INV: inverse transform, unscaled.
-template <bool INV>
-__device__ __forceinline__ void warp_fft1024(float2 (&x)[32], float2* scratch, const float2* tw2, int lane) {
-  fft32_regs<INV>(x);                        // x[brev(k2)] = A[k2]
+// memory private to the warp. Forward transform; an inverse (unscaled) transform is obtained by
+// conjugating the data before and after (`inv` != 0). The two 32-point passes share one copy of
+// the butterfly code (rolled 2-iteration loop) to keep the kernel inside the instruction cache.
+__device__ __forceinline__ void warp_fft1024(float2 (&x)[32], float2* scratch, const float2* tw2, int lane, int inv) {
+  if(inv) {
 #pragma unroll
-  for(int k2 = 0; k2 < 32; k2 ++) {
-    float2 a = x[wfft_brev5(k2)];
-    float2 w = tw2[k2 * 32 + lane];
-    if(INV) w.y = -w.y;
-    scratch[lane * WFFT_ROW + k2] = make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x);
+    for(int r = 0; r < 32; r ++) x[r].y = -x[r].y;
   }
-  __syncwarp();
+#pragma unroll 1
+  for(int stage = 0; stage < 2; stage ++) {
+    fft32_regs<false>(x);                    // x[brev(k)] = DFT32(x)[k]
+    if(stage == 0) {
 #pragma unroll
-  for(int n1 = 0; n1 < 32; n1 ++) x[n1] = scratch[n1 * WFFT_ROW + lane];
-  __syncwarp();
-  fft32_regs<INV>(x);                        // x[brev(k1)] = X[lane + 32 k1]
-  // natural order (a compile-time register permutation)
+      for(int k2 = 0; k2 < 32; k2 ++) {
+        float2 a = x[wfft_brev5(k2)];
+        float2 w = tw2[k2 * 32 + lane];
+        scratch[lane * WFFT_ROW + k2] = make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x);
+      }
+      __syncwarp();
+#pragma unroll
+      for(int n1 = 0; n1 < 32; n1 ++) x[n1] = scratch[n1 * WFFT_ROW + lane];
+      __syncwarp();
+    }
+  }
+  // natural order (a compile-time register permutation); undo the conjugation for the inverse
   float2 t[32];
 #pragma unroll
   for(int k1 = 0; k1 < 32; k1 ++) t[k1] = x[wfft_brev5(k1)];
 #pragma unroll
-  for(int k1 = 0; k1 < 32; k1 ++) x[k1] = t[k1];
+  for(int k1 = 0; k1 < 32; k1 ++) x[k1] = make_float2(t[k1].x, inv ? -t[k1].y : t[k1].y);
 }

@@ -259,3 +259,49 @@ int ref_tolayer0_soa(int nfrm, float fs, float thop, int maxnhar, float lip_radi
   llsm_delete_chunk(chunk);
   return 0;
 }
+
+/* layer-1 synthesis (test/test-layer1-anasynth.c:29-56 pattern): L0 frames -> llsm_chunk_tolayer1 ->
+   optional removal of the HM members -> PBPSYN flags -> llsm_synthesize with use_l1 = 1.
+   The layer-1 members are also returned so that the device path can be fed the same numbers. */
+int ref_synthesize_l1_soa(int nfrm, float fs, float thop, int maxnhar, int maxnhar_e, int npsd,
+  int nchannel, const float* chanfreq, float lip_radius, int nfft, int remove_hm, const int* pbpsyn,
+  const float* f0, const int* nhar, const float* ampl, const float* phse,
+  const float* psd, const float* psdres, const float* edc, const int* enhar,
+  const float* eampl, const float* ephse, unsigned seed,
+  float* rd, float* vtmagn, float* vsphse, int* nvs,
+  float* y, float* y_sin, float* y_noise) {
+  llsm_chunk* chunk = chunk_from_soa(nfrm, fs, thop, maxnhar, maxnhar_e, npsd, nchannel,
+    chanfreq, lip_radius, f0, nhar, ampl, phse, psd, psdres, edc, enhar, eampl, ephse);
+  llsm_chunk_tolayer1(chunk, nfft);
+  int nspec = nfft / 2 + 1;
+  for(int i = 0; i < nfrm; i ++) {
+    llsm_container* fr = chunk -> frames[i];
+    FP_TYPE* r = llsm_container_get(fr, LLSM_FRAME_RD);
+    FP_TYPE* vt = llsm_container_get(fr, LLSM_FRAME_VTMAGN);
+    FP_TYPE* vs = llsm_container_get(fr, LLSM_FRAME_VSPHSE);
+    rd[i] = r != NULL ? r[0] : 0;
+    memset(vtmagn + (size_t)i * nspec, 0, nspec * sizeof(float));
+    memset(vsphse + (size_t)i * maxnhar, 0, maxnhar * sizeof(float));
+    nvs[i] = 0;
+    if(vt != NULL) memcpy(vtmagn + (size_t)i * nspec, vt, nspec * sizeof(float));
+    if(vs != NULL) { nvs[i] = llsm_fparray_length(vs); memcpy(vsphse + (size_t)i * maxnhar, vs, nvs[i] * sizeof(float)); }
+    if(remove_hm) llsm_container_attach(fr, LLSM_FRAME_HM, NULL, NULL, NULL);
+    if(pbpsyn != NULL && pbpsyn[i])
+      llsm_container_attach(fr, LLSM_FRAME_PBPSYN, llsm_create_int(1), llsm_delete_int, llsm_copy_int);
+  }
+  llsm_soptions* sopt = llsm_create_soptions(fs);
+  sopt -> use_l1 = 1;
+  srand(seed);
+  llsm_output* out = llsm_synthesize(sopt, chunk);
+  int ny = -1;
+  if(out != NULL) {
+    ny = out -> ny;
+    memcpy(y, out -> y, ny * sizeof(float));
+    memcpy(y_sin, out -> y_sin, ny * sizeof(float));
+    memcpy(y_noise, out -> y_noise, ny * sizeof(float));
+    llsm_delete_output(out);
+  }
+  llsm_delete_soptions(sopt);
+  llsm_delete_chunk(chunk);
+  return ny;
+}

@@ -73,3 +73,14 @@ extern "C" int emu_tolayer0(const llsm_b200_conf* conf, const float* f0, const l
   int rc = run_tolayer0(lp, *conf, nullptr, f0, *in, nhar, ampl, phse, nullptr, nullptr);
   lp.release(); return rc;
 }
+
+#include "../../libllsm2_b200/csrc/driver_pbp.h"
+extern "C" int emu_synthesize_l1(const llsm_b200_conf* conf, const llsm_b200_frames* fr, const llsm_b200_layer1* l1,
+  const int* pbpsyn, const llsm_b200_soptions* opt, const llsm_b200_output* out) {
+  SynthPlanDev pd; L1PlanDev lp; SynthScratch sc; PbpScratch ps;
+  if(pd.build(conf->nfrm, conf->fs, conf->thop, conf->npsd, conf->nchannel, conf->chanfreq, nullptr) != 0) return -100;
+  if(lp.build(nullptr) != 0) return -101;
+  int rc = run_synth_l1(pd, lp, sc, ps, *conf, *fr, *l1, pbpsyn, *opt, *out, nullptr, nullptr, nullptr);
+  sc.colored.release(); sc.y_exc.release(); ps.release(); lp.release(); pd.release();
+  return rc;
+}
