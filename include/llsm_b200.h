@@ -194,6 +194,25 @@ int llsm_b200_synthesize_l1(llsm_b200_ctx* ctx, const llsm_b200_conf* conf,
   const llsm_b200_frames* frames, const llsm_b200_layer1* l1, const int* pbpsyn,
   const llsm_b200_soptions* opt, const llsm_b200_output* out);
 
+
+/* Per-pulse hook of llsm_pbpeffect (llsm.h:190-197, called at layer0.c:208-217): the library calls it
+   once per glottal pulse, in time order, on the host. It receives the glottal-flow parameters of the
+   pulse (llsm_gfm fields) and delta_t, may modify them, and returns non-zero when the frame carries an
+   effect (the reference then round-trips the model through llsm_gfm even if nothing changed). */
+typedef int (*llsm_b200_pulse_hook)(void* user, int utt, int frame, float* Fa, float* Rk, float* Rg,
+  float* T0, float* Ee, float* delta_t);
+/* Host-buffer form of llsm_b200_synthesize_l1. hook == NULL: everything runs on the device. With a
+   hook the (cheap, strictly sequential) pulse tracker runs on the host so that user callbacks are
+   honoured in order; pulse generation, harmonic frames, noise and mixing stay on the device. */
+int llsm_b200_synthesize_l1_host(llsm_b200_ctx* ctx, const llsm_b200_conf* conf,
+  const llsm_b200_frames* frames, const llsm_b200_layer1* l1, const int* pbpsyn,
+  const llsm_b200_soptions* opt, const llsm_b200_output* out, llsm_b200_pulse_hook hook, void* user);
+/* Host-buffer forms of the layer-1 conversions. */
+int llsm_b200_tolayer1_host(llsm_b200_ctx* ctx, const llsm_b200_conf* conf,
+  const llsm_b200_frames* frames, int nfft, const llsm_b200_layer1* out);
+int llsm_b200_tolayer0_host(llsm_b200_ctx* ctx, const llsm_b200_conf* conf, const int* nfrm_utt,
+  const float* f0, const llsm_b200_layer1* in, int* nhar, float* ampl, float* phse);
+
 #ifdef __cplusplus
 }
 #endif

@@ -302,10 +302,139 @@ FP_TYPE* llsm_frame_compute_snr(llsm_container* src, llsm_container* conf, int a
   return NULL;
 }
 
-/* layer-1 conversions are outside the accelerated path of this round */
-void llsm_frame_tolayer0(llsm_container* dst, llsm_container* conf) { (void)dst; (void)conf; set_err("layer 1 not built"); }
-void llsm_chunk_tolayer1(llsm_chunk* dst, int nfft) { (void)dst; (void)nfft; set_err("layer 1 not built"); }
-void llsm_chunk_tolayer0(llsm_chunk* dst) { (void)dst; set_err("layer 1 not built"); }
+/* ------------------------------------------------------------------ layer 1 --------------------- */
+static llsm_b200_ctx* shared_ctx(void);
+
+static int conf_to_b200(llsm_container* conf, llsm_b200_conf* c, float fs_or_zero) {
+  memset(c, 0, sizeof(*c));
+  int* nfrm = llsm_container_get(conf, LLSM_CONF_NFRM);
+  int* npsd = llsm_container_get(conf, LLSM_CONF_NPSD);
+  int* nch = llsm_container_get(conf, LLSM_CONF_NCHANNEL);
+  FP_TYPE* thop = llsm_container_get(conf, LLSM_CONF_THOP);
+  FP_TYPE* fnyq = llsm_container_get(conf, LLSM_CONF_FNYQ);
+  FP_TYPE* lip = llsm_container_get(conf, LLSM_CONF_LIPRADIUS);
+  FP_TYPE* cf = llsm_container_get(conf, LLSM_CONF_CHANFREQ);
+  int* mne = llsm_container_get(conf, LLSM_CONF_MAXNHAR_E);
+  if(nfrm == NULL || thop == NULL || fnyq == NULL) return 0;
+  c -> nutt = 1; c -> nfrm = *nfrm; c -> npsd = npsd != NULL ? *npsd : 2; c -> nchannel = nch != NULL ? *nch : 1;
+  c -> thop = *thop; c -> fs = fs_or_zero > 0 ? fs_or_zero : (float)(*fnyq * 2.0);
+  c -> lip_radius = lip != NULL ? *lip : 1.5f;
+  c -> maxnhar = 1; c -> maxnhar_e = mne != NULL ? *mne : 0;
+  if(c -> nchannel < 1 || c -> nchannel > LLSM_B200_MAXCHANNEL) return 0;
+  if(cf != NULL) for(int i = 0; i < c -> nchannel - 1; i ++) c -> chanfreq[i] = cf[i];
+  return 1;
+}
+
+/* L0 -> L1 for a whole chunk (layer1.c:129-149): attaches NSPEC to the conf, RD to every frame,
+   VTMAGN / VSPHSE to the voiced ones. Returns silently on failure, like the reference. */
+void llsm_chunk_tolayer1(llsm_chunk* dst, int nfft) {
+  g_compat_err[0] = 0;
+  llsm_b200_conf c;
+  if(dst == NULL || ! conf_to_b200(dst -> conf, & c, 0) ||
+     llsm_container_get(dst -> conf, LLSM_CONF_LIPRADIUS) == NULL) return;
+  for(int i = 0; i < c.nfrm; i ++) if(! llsm_frame_checklayer0(dst -> frames[i])) return;   /* layer1.c:34-36 */
+  llsm_b200_ctx* ctx = shared_ctx();
+  if(ctx == NULL) return;
+  int maxnhar = 1;
+  for(int i = 0; i < c.nfrm; i ++) {
+    llsm_hmframe* hm = llsm_container_get(dst -> frames[i], LLSM_FRAME_HM);
+    if(hm != NULL && hm -> nhar > maxnhar) maxnhar = hm -> nhar;
+  }
+  c.maxnhar = maxnhar;
+  const size_t F = (size_t)c.nfrm; const int nspec = nfft / 2 + 1;
+  float* f0 = calloc(F, 4); int* nhar = calloc(F, 4); float* ampl = calloc(F * maxnhar, 4); float* phse = calloc(F * maxnhar, 4);
+  float* rd = calloc(F, 4); float* vt = calloc(F * nspec, 4); float* vs = calloc(F * maxnhar, 4); int* nvs = calloc(F, 4);
+  for(int i = 0; i < c.nfrm; i ++) {
+    FP_TYPE* pf0 = llsm_container_get(dst -> frames[i], LLSM_FRAME_F0);
+    llsm_hmframe* hm = llsm_container_get(dst -> frames[i], LLSM_FRAME_HM);
+    f0[i] = pf0[0];
+    if(pf0[0] != 0 && hm != NULL) {
+      nhar[i] = hm -> nhar;
+      memcpy(ampl + (size_t)i * maxnhar, hm -> ampl, 4 * (size_t)hm -> nhar);
+      memcpy(phse + (size_t)i * maxnhar, hm -> phse, 4 * (size_t)hm -> nhar);
+    }
+  }
+  llsm_b200_frames fr; memset(& fr, 0, sizeof(fr));
+  fr.f0 = f0; fr.nhar = nhar; fr.ampl = ampl; fr.phse = phse;
+  llsm_b200_layer1 l1 = {rd, vt, vs, nvs, nspec};
+  if(llsm_b200_tolayer1_host(ctx, & c, & fr, nfft, & l1) == 0) {
+    llsm_container_attach(dst -> conf, LLSM_CONF_NSPEC, llsm_create_int(nspec), llsm_delete_int, llsm_copy_int);
+    for(int i = 0; i < c.nfrm; i ++) {
+      llsm_container* f = dst -> frames[i];
+      llsm_container_attach(f, LLSM_FRAME_RD, llsm_create_fp(rd[i]), llsm_delete_fp, llsm_copy_fp);
+      if(f0[i] == 0) continue;
+      FP_TYPE* a = llsm_create_fparray(nspec);
+      memcpy(a, vt + (size_t)i * nspec, 4 * (size_t)nspec);
+      FP_TYPE* p = llsm_create_fparray(nvs[i]);
+      memcpy(p, vs + (size_t)i * maxnhar, 4 * (size_t)nvs[i]);
+      llsm_container_attach(f, LLSM_FRAME_VTMAGN, a, llsm_delete_fparray, llsm_copy_fparray);
+      llsm_container_attach(f, LLSM_FRAME_VSPHSE, p, llsm_delete_fparray, llsm_copy_fparray);
+    }
+  }
+  free(f0); free(nhar); free(ampl); free(phse); free(rd); free(vt); free(vs); free(nvs);
+}
+
+/* L1 -> L0 for `n` frames sharing `conf` (layer1.c:151-195): attaches an HM member to every voiced
+   frame that passes the layer-1 check. */
+static void frames_tolayer0(llsm_container** frames, int n, llsm_container* conf) {
+  FP_TYPE* fnyq = llsm_container_get(conf, LLSM_CONF_FNYQ);
+  FP_TYPE* lip = llsm_container_get(conf, LLSM_CONF_LIPRADIUS);
+  int* nspec = llsm_container_get(conf, LLSM_CONF_NSPEC);
+  int* cap = llsm_container_get(conf, LLSM_CONF_MAXNHAR);
+  if(fnyq == NULL || lip == NULL || nspec == NULL || n < 1) return;    /* layer1.c:40-46 */
+  llsm_b200_ctx* ctx = shared_ctx();
+  if(ctx == NULL) return;
+  int maxlen = 1;
+  for(int i = 0; i < n; i ++) {
+    FP_TYPE* vs = llsm_container_get(frames[i], LLSM_FRAME_VSPHSE);
+    if(vs != NULL && llsm_fparray_length(vs) > maxlen) maxlen = llsm_fparray_length(vs);
+  }
+  int maxnhar = maxlen;
+  if(cap != NULL && *cap < maxnhar) maxnhar = *cap > 0 ? *cap : 1;     /* rows only need min(len, MAXNHAR) */
+  llsm_b200_conf c; memset(& c, 0, sizeof(c));
+  c.nutt = 1; c.nfrm = n; c.maxnhar = maxnhar; c.maxnhar_e = 0; c.npsd = 2; c.nchannel = 1;
+  c.fs = (float)(*fnyq * 2.0); c.thop = 0.005f; c.lip_radius = *lip;
+  const size_t F = (size_t)n;
+  float* f0 = calloc(F, 4); float* rd = calloc(F, 4); float* vt = calloc(F * *nspec, 4); float* vsb = calloc(F * maxnhar, 4);
+  int* nvs = calloc(F, 4); int* nhar = calloc(F, 4); float* ampl = calloc(F * maxnhar, 4); float* phse = calloc(F * maxnhar, 4);
+  for(int i = 0; i < n; i ++) {
+    if(! llsm_frame_checklayer1(frames[i])) continue;
+    FP_TYPE* pf0 = llsm_container_get(frames[i], LLSM_FRAME_F0);
+    FP_TYPE* prd = llsm_container_get(frames[i], LLSM_FRAME_RD);
+    FP_TYPE* pvt = llsm_container_get(frames[i], LLSM_FRAME_VTMAGN);
+    FP_TYPE* pvs = llsm_container_get(frames[i], LLSM_FRAME_VSPHSE);
+    if(pf0[0] == 0) continue;
+    f0[i] = pf0[0]; rd[i] = prd[0];
+    memcpy(vt + (size_t)i * *nspec, pvt, 4 * (size_t)*nspec);
+    int len = llsm_fparray_length(pvs);
+    nvs[i] = len;                                           /* the kernel applies min(len, MAXNHAR, fnyq / f0) */
+    memcpy(vsb + (size_t)i * maxnhar, pvs, 4 * (size_t)(len < maxnhar ? len : maxnhar));
+  }
+  llsm_b200_layer1 l1 = {rd, vt, vsb, nvs, *nspec};
+  if(llsm_b200_tolayer0_host(ctx, & c, NULL, f0, & l1, nhar, ampl, phse) == 0) {
+    for(int i = 0; i < n; i ++) {
+      if(f0[i] == 0) continue;
+      llsm_hmframe* hm = llsm_create_hmframe(nhar[i]);
+      memcpy(hm -> ampl, ampl + (size_t)i * maxnhar, 4 * (size_t)nhar[i]);
+      memcpy(hm -> phse, phse + (size_t)i * maxnhar, 4 * (size_t)nhar[i]);
+      llsm_container_attach(frames[i], LLSM_FRAME_HM, hm, llsm_delete_hmframe, llsm_copy_hmframe);
+    }
+  }
+  free(f0); free(rd); free(vt); free(vsb); free(nvs); free(nhar); free(ampl); free(phse);
+}
+
+void llsm_frame_tolayer0(llsm_container* dst, llsm_container* conf) {
+  g_compat_err[0] = 0;
+  if(dst == NULL || conf == NULL) return;
+  frames_tolayer0(& dst, 1, conf);
+}
+
+void llsm_chunk_tolayer0(llsm_chunk* dst) {
+  g_compat_err[0] = 0;
+  int* nfrm = llsm_container_get(dst -> conf, LLSM_CONF_NFRM);
+  if(nfrm == NULL) return;
+  frames_tolayer0(dst -> frames, *nfrm, dst -> conf);
+}
 
 /* ------------------------------------------------------------------ options --------------------- */
 llsm_aoptions* llsm_create_aoptions(void) {            /* defaults of layer0.c:27-43 */
@@ -458,6 +587,147 @@ static int chunk_ok(llsm_chunk* src) {                 /* layer0.c:525-533 */
   return 1;
 }
 
+static FP_TYPE host_randn(void);
+/* ------------------------------------------------------------------ layer-1 synthesis ----------- */
+/* adapter between the C ABI's per-pulse hook and llsm_pbpeffect (llsm.h:190-197) */
+typedef struct { llsm_chunk** chunks; } hook_env;
+static int pulse_hook(void* user, int utt, int frame, float* Fa, float* Rk, float* Rg, float* T0, float* Ee,
+  float* delta_t) {
+  hook_env* env = user;
+  llsm_container* fr = env -> chunks[utt] -> frames[frame];
+  llsm_pbpeffect* eff = llsm_container_get(fr, LLSM_FRAME_PBPEFF);
+  if(eff == NULL) return 0;
+  llsm_gfm g = {*Fa, *Rk, *Rg, *T0, *Ee};
+  eff -> modifier(& g, delta_t, eff -> info, fr);                   /* layer0.c:212 */
+  *Fa = g.Fa; *Rk = g.Rk; *Rg = g.Rg; *T0 = g.T0; *Ee = g.Ee;
+  return 1;
+}
+
+static int synthesize_l1_batch(llsm_b200_ctx* ctx, llsm_soptions* options, llsm_chunk** src, int n,
+  llsm_output** dst) {
+  llsm_container* conf = src[0] -> conf;
+  llsm_b200_conf c;
+  if(! conf_to_b200(conf, & c, options -> fs)) { set_err("unsupported configuration"); return -1; }
+  c.nutt = n;
+  FP_TYPE* cf = llsm_container_get(conf, LLSM_CONF_CHANFREQ);
+  /* frames that will need a harmonic model but carry none: derive it now (layer0.c:264-265) */
+  int any_eff = 0, nspec = 0;
+  for(int b = 0; b < n; b ++) {
+    int cnt = 0;
+    llsm_container** todo = calloc(c.nfrm > 0 ? c.nfrm : 1, sizeof(llsm_container*));
+    for(int i = 0; i < c.nfrm; i ++) {
+      llsm_container* f = src[b] -> frames[i];
+      FP_TYPE* pf0 = llsm_container_get(f, LLSM_FRAME_F0);
+      FP_TYPE* vt = llsm_container_get(f, LLSM_FRAME_VTMAGN);
+      if(llsm_container_get(f, LLSM_FRAME_PBPEFF) != NULL) any_eff = 1;
+      if(vt != NULL && llsm_fparray_length(vt) > nspec) nspec = llsm_fparray_length(vt);
+      if(pf0[0] != 0 && llsm_frame_checklayer1(f) && llsm_container_get(f, LLSM_FRAME_HM) == NULL) todo[cnt ++] = f;
+    }
+    if(cnt > 0) frames_tolayer0(todo, cnt, src[b] -> conf);
+    free(todo);
+  }
+  if(nspec < 2) { int* ns = llsm_container_get(conf, LLSM_CONF_NSPEC); nspec = ns != NULL ? *ns : 2; }
+  int maxnhar = 1, maxnhar_e = 1, has_res = 0;
+  for(int b = 0; b < n; b ++) for(int i = 0; i < c.nfrm; i ++) {
+    llsm_container* f = src[b] -> frames[i];
+    llsm_hmframe* hm = llsm_container_get(f, LLSM_FRAME_HM);
+    llsm_nmframe* nm = llsm_container_get(f, LLSM_FRAME_NM);
+    FP_TYPE* vs = llsm_container_get(f, LLSM_FRAME_VSPHSE);
+    if(hm != NULL && hm -> nhar > maxnhar) maxnhar = hm -> nhar;
+    if(vs != NULL && llsm_fparray_length(vs) > maxnhar) maxnhar = llsm_fparray_length(vs);
+    if(nm -> nchannel != c.nchannel || nm -> npsd != c.npsd) { set_err("frame / conf size mismatch"); return -1; }
+    for(int ch = 0; ch < c.nchannel; ch ++) if(nm -> eenv[ch] -> nhar > maxnhar_e) maxnhar_e = nm -> eenv[ch] -> nhar;
+    if(llsm_container_get(f, LLSM_FRAME_PSDRES) != NULL) has_res = 1;
+  }
+  if(maxnhar > 2048) maxnhar = 2048;
+  c.maxnhar = maxnhar; c.maxnhar_e = maxnhar_e;
+
+  const size_t BF = (size_t)n * c.nfrm;
+  float* f0 = calloc(BF, 4); int* nhar = calloc(BF, 4);
+  float* ampl = calloc(BF * maxnhar, 4); float* phse = calloc(BF * maxnhar, 4);
+  float* psd = calloc(BF * c.npsd, 4); float* psdres = has_res ? calloc(BF * c.npsd, 4) : NULL;
+  float* edc = calloc(BF * c.nchannel, 4); int* enhar = calloc(BF * c.nchannel, 4);
+  float* eampl = calloc(BF * c.nchannel * maxnhar_e, 4); float* ephse = calloc(BF * c.nchannel * maxnhar_e, 4);
+  float* rd = calloc(BF, 4); float* vtm = calloc(BF * nspec, 4); float* vsp = calloc(BF * maxnhar, 4);
+  int* nvs = calloc(BF, 4); int* pbp = calloc(BF, 4);
+  const double resbias = 0.375 / 2.3025851 * 10.0;
+  for(int b = 0; b < n; b ++) for(int i = 0; i < c.nfrm; i ++) {
+    size_t r = (size_t)b * c.nfrm + i;
+    llsm_container* f = src[b] -> frames[i];
+    FP_TYPE* pf0 = llsm_container_get(f, LLSM_FRAME_F0);
+    llsm_hmframe* hm = llsm_container_get(f, LLSM_FRAME_HM);
+    llsm_nmframe* nm = llsm_container_get(f, LLSM_FRAME_NM);
+    FP_TYPE* res = llsm_container_get(f, LLSM_FRAME_PSDRES);
+    FP_TYPE* prd = llsm_container_get(f, LLSM_FRAME_RD);
+    FP_TYPE* pvt = llsm_container_get(f, LLSM_FRAME_VTMAGN);
+    FP_TYPE* pvs = llsm_container_get(f, LLSM_FRAME_VSPHSE);
+    int* psyn = llsm_container_get(f, LLSM_FRAME_PBPSYN);
+    f0[r] = pf0[0];
+    if(pf0[0] != 0 && hm != NULL) {
+      int k = hm -> nhar < maxnhar ? hm -> nhar : maxnhar;
+      nhar[r] = k;
+      memcpy(ampl + r * maxnhar, hm -> ampl, 4 * (size_t)k);
+      memcpy(phse + r * maxnhar, hm -> phse, 4 * (size_t)k);
+    }
+    if(pf0[0] != 0 && prd != NULL && pvt != NULL && pvs != NULL && llsm_fparray_length(pvt) == nspec) {   /* layer0.c:180 */
+      int len = llsm_fparray_length(pvs);
+      rd[r] = prd[0];
+      memcpy(vtm + r * nspec, pvt, 4 * (size_t)nspec);
+      nvs[r] = len < maxnhar ? len : maxnhar;
+      memcpy(vsp + r * maxnhar, pvs, 4 * (size_t)nvs[r]);
+    }
+    pbp[r] = psyn != NULL && psyn[0] == 1;
+    memcpy(psd + r * c.npsd, nm -> psd, 4 * (size_t)c.npsd);
+    if(has_res) for(int j = 0; j < c.npsd; j ++) psdres[r * c.npsd + j] = res != NULL ? res[j] : (float)resbias;
+    for(int ch = 0; ch < c.nchannel; ch ++) {
+      size_t e = r * c.nchannel + ch;
+      edc[e] = nm -> edc[ch];
+      int k = nm -> eenv[ch] -> nhar;
+      enhar[e] = k;
+      memcpy(eampl + e * maxnhar_e, nm -> eenv[ch] -> ampl, 4 * (size_t)k);
+      memcpy(ephse + e * maxnhar_e, nm -> eenv[ch] -> phse, 4 * (size_t)k);
+    }
+  }
+  const int ny = llsm_b200_output_length(c.nfrm, c.thop, c.fs);
+  const int nt = llsm_b200_template_length(ny);
+  float* white = malloc(sizeof(float) * (size_t)n * c.nchannel * nt);
+  for(int b = 0; b < n; b ++) for(int ch = 0; ch < c.nchannel; ch ++) {
+    FP_TYPE fmin = ch == 0 ? 0 : cf[ch - 1];
+    float* w = white + ((size_t)b * c.nchannel + ch) * nt;
+    if(fmin >= c.fs / 2.0) { memset(w, 0, sizeof(float) * nt); continue; }
+    int ntemplate = ny < 20000 ? ny : 20000;
+    int ndraw = (ntemplate + 128) < 20000 ? (ntemplate + 128) : 20000;
+    for(int j = 0; j < ndraw; j ++) w[j] = host_randn();
+    for(int j = ndraw; j < nt; j ++) w[j] = w[(j - ndraw) % ndraw];
+  }
+  float* y = malloc(sizeof(float) * (size_t)n * ny);
+  float* ys = malloc(sizeof(float) * (size_t)n * ny);
+  float* yn = malloc(sizeof(float) * (size_t)n * ny);
+  llsm_b200_frames fr = {NULL, f0, nhar, ampl, phse, psd, psdres, edc, enhar, eampl, ephse};
+  llsm_b200_layer1 l1 = {rd, vtm, vsp, nvs, nspec};
+  llsm_b200_soptions so; memset(& so, 0, sizeof(so));
+  so.use_iczt = options -> use_iczt; so.iczt_param_a = options -> iczt_param_a; so.iczt_param_b = options -> iczt_param_b;
+  so.white = white;
+  llsm_b200_output out = {y, ys, yn, ny};
+  hook_env env = {src};
+  int rc = llsm_b200_synthesize_l1_host(ctx, & c, & fr, & l1, pbp, & so, & out, any_eff ? pulse_hook : NULL, & env);
+  if(rc == 0) {
+    for(int b = 0; b < n; b ++) {
+      llsm_output* o = malloc(sizeof(llsm_output));
+      o -> ny = ny; o -> fs = options -> fs;
+      o -> y = malloc(sizeof(FP_TYPE) * (size_t)ny); o -> y_sin = malloc(sizeof(FP_TYPE) * (size_t)ny);
+      o -> y_noise = malloc(sizeof(FP_TYPE) * (size_t)ny);
+      memcpy(o -> y, y + (size_t)b * ny, 4 * (size_t)ny);
+      memcpy(o -> y_sin, ys + (size_t)b * ny, 4 * (size_t)ny);
+      memcpy(o -> y_noise, yn + (size_t)b * ny, 4 * (size_t)ny);
+      dst[b] = o;
+    }
+  }
+  free(f0); free(nhar); free(ampl); free(phse); free(psd); free(psdres); free(edc); free(enhar); free(eampl);
+  free(ephse); free(rd); free(vtm); free(vsp); free(nvs); free(pbp); free(white); free(y); free(ys); free(yn);
+  return rc;
+}
+
 /* ------------------------------------------------------------------ synthesis ------------------- */
 int llsm_synthesize_batch(llsm_soptions* options, llsm_chunk** src, int n, llsm_output** dst) {
   g_compat_err[0] = 0;
@@ -469,9 +739,9 @@ int llsm_synthesize_batch(llsm_soptions* options, llsm_chunk** src, int n, llsm_
       set_err("llsm_synthesize_batch: chunks must share one configuration"); return -1;
     }
   }
-  if(options -> use_l1) { set_err("use_l1 (pulse-by-pulse) synthesis is not built into this library yet"); return -1; }
   llsm_b200_ctx* ctx = shared_ctx();
   if(ctx == NULL) return -1;
+  if(options -> use_l1) return synthesize_l1_batch(ctx, options, src, n, dst);
 
   llsm_container* conf = src[0] -> conf;
   llsm_b200_conf c; memset(& c, 0, sizeof(c));

@@ -27,7 +27,7 @@ static inline int dev_zero(void* p, size_t n, cudaStream_t s) { return cudaMemse
 static inline int run_synth_l1(const SynthPlanDev& pd, const L1PlanDev& lp, SynthScratch& sc, PbpScratch& ps,
   const llsm_b200_conf& conf, const llsm_b200_frames& fr, const llsm_b200_layer1& l1, const int* pbpsyn,
   const llsm_b200_soptions& opt, const llsm_b200_output& out, const int* ny_utt_dev, cudaStream_t st,
-  LaunchCounter* lc) {
+  LaunchCounter* lc, bool plan_ready = false) {
   const SynthPlan& h = pd.h;
   const int B = conf.nutt, F = conf.nfrm;
   const size_t BF = (size_t)B * F;
@@ -54,6 +54,7 @@ static inline int run_synth_l1(const SynthPlanDev& pd, const L1PlanDev& lp, Synt
   plan.len_period = ps.len_period.as<float>(); plan.pulse_size = ps.pulse_size.as<int>();
   plan.pulses = ps.pulses.as<PbpPulse>(); plan.need_hm = ps.need_hm.as<int>();
 
+  if(! plan_ready) {
   PbpPrepParams Q; memset(&Q, 0, sizeof(Q));
   Q.nfrm = F; Q.nfrm_utt = fr.nfrm_utt; Q.f0 = fr.f0; Q.rd = l1.rd; Q.nvs = l1.nvs; Q.source_p0 = ps.source_p0.as<float>();
   LLSM_LAUNCH(pbp_prep_kernel, dim3((F + 127) / 128, B), dim3(128), 0, st, Q);
@@ -69,6 +70,10 @@ static inline int run_synth_l1(const SynthPlanDev& pd, const L1PlanDev& lp, Synt
   T.nspec = l1.nspec; T.plan = plan; T.y_mix = out.y_sin;
   LLSM_LAUNCH(pbp_track_kernel, dim3((B + 31) / 32), dim3(32), 0, st, T);
   if(lc) lc->n ++;
+  } else {
+    // plan, need_hm and the switch ramp (in out.y_sin) were produced by the host tracker and uploaded
+    if(dev_zero(ps.y_pbp.p, obytes, st)) return LLSM_B200_ECUDA;
+  }
 
   // harmonic-model frames at truncated positions, no sub-sample phase correction (layer0.c:173,263-277)
   {

@@ -71,9 +71,12 @@ struct PbpTrackParams {
   float* y_mix;              // [B][stride], zero-initialised by the caller
 };
 
-__global__ void __launch_bounds__(32) pbp_track_kernel(PbpTrackParams P) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if(b >= P.nutt) return;
+// Tracker of one utterance. `mod(model, delta_t, frame)` is the per-pulse hook of llsm_pbpeffect
+// (layer0.c:208-217): identity on the device, the user's callback in the host build of the drop-in API.
+struct PbpNoEffect { LF_HD void operator()(LfModel&, float&, int) const {} };
+
+template <class Mod>
+LF_HD void pbp_track_utterance(const PbpTrackParams& P, int b, Mod& mod) {
   const int nf = P.nfrm_utt ? P.nfrm_utt[b] : P.nfrm;
   const int ny = P.ny_utt ? P.ny_utt[b] : P.ny;
   float pulse_previous = 0.f;
@@ -92,8 +95,18 @@ __global__ void __launch_bounds__(32) pbp_track_kernel(PbpTrackParams P) {
     const int pbp_on = P.pbpsyn ? (P.pbpsyn[r] == 1) : 0;
     float len_period = P.fs / f0;
     const float source_p0 = P.source_p0[r];
-    const float p0 = wrapf(P.vsphse[r * P.vs_stride]);
-    float p0_dist = wrapf(p0 - source_p0);              // phase_diff(source_p0, p0)
+    float p0; {
+      double pv = (double)P.vsphse[r * P.vs_stride];
+      double q = pv - 2.0 * LLSM_PI * floor((pv + LLSM_PI) / (2.0 * LLSM_PI));
+      if(q <= -LLSM_PI) q += 2.0 * LLSM_PI;
+      p0 = (float)q;
+    }
+    float p0_dist; {
+      double pv = (double)(p0 - source_p0);             // phase_diff(source_p0, p0) = wrap(p0 - source_p0)
+      double q = pv - 2.0 * LLSM_PI * floor((pv + LLSM_PI) / (2.0 * LLSM_PI));
+      if(q <= -LLSM_PI) q += 2.0 * LLSM_PI;
+      p0_dist = (float)q;
+    }
     if(p0_dist < 0) p0_dist = (float)((double)p0_dist + 2.0 * LLSM_PI);
     const float pulse_projected = (float)((double)baseidx + (double)(p0_dist / 2.0f) / LLSM_PI * (double)len_period);
     const int len_reset = (int)((len_period > P.hop ? len_period : P.hop) * 2.0f);
@@ -101,19 +114,25 @@ __global__ void __launch_bounds__(32) pbp_track_kernel(PbpTrackParams P) {
     const int num_periods = (int)round((double)((pulse_projected - pulse_previous) / len_period));
     len_period = (pulse_projected - pulse_previous) / (float)num_periods;      // unguarded, layer0.c:200
     if((pbp_on || pbp_periods > 0) && num_periods > 0) {
-      const int pulse_size = (int)pow(2.0, ceil(log2((double)fmaxf(len_period * 2.0f, (float)P.nspec))));
+      float lp2 = len_period * 2.0f;
+      float mxs = lp2 > (float)P.nspec ? lp2 : (float)P.nspec;
+      const int pulse_size = (int)pow(2.0, ceil(log2((double)mxs)));
       const float t_period = (float)(1.0 / (double)f0);
       const LfModel sm = lf_from_rd(P.rd[r], t_period, 1.0f);
       const int np = num_periods < PBP_MAXP ? num_periods : PBP_MAXP;
       PbpPulse* pl = P.plan.pulses + r * PBP_MAXP;
-      float off0 = 0.f; int pulse_base = 0;
-      for(int j = 0; j < np; j ++) {
-        float off = pulse_previous + (float)j * len_period;     // + delta_t * fs with delta_t = 0
-        if(j == 0) { pulse_base = (int)off; off0 = off; }
-        pl[j].T0 = sm.T0; pl[j].te = sm.te; pl[j].tp = sm.tp; pl[j].ta = sm.ta; pl[j].Ee = sm.Ee;
-        pl[j].offset = off - (float)pulse_base;
+      int pulse_base = 0;
+      for(int j = 0; j < num_periods; j ++) {
+        LfModel m = sm; float delta_t = 0.f;
+        mod(m, delta_t, i);                               // called once per pulse, in time order
+        if(j >= np) continue;
+        float off = pulse_previous + (float)j * len_period;
+        off = off + delta_t * P.fs;                       // layer0.c:216
+        pl[j].T0 = m.T0; pl[j].te = m.te; pl[j].tp = m.tp; pl[j].ta = m.ta; pl[j].Ee = m.Ee;
+        pl[j].offset = off;
       }
-      (void)off0;
+      pulse_base = (int)pl[0].offset;                     // layer0.c:218-219
+      for(int j = 0; j < np; j ++) pl[j].offset = pl[j].offset - (float)pulse_base;
       P.plan.npulse[r] = num_periods <= PBP_MAXP ? num_periods : -num_periods;   // < 0: overflow
       P.plan.pulse_base[r] = pulse_base;
       P.plan.pre_rotate[r] = (int)len_period;
@@ -145,6 +164,13 @@ __global__ void __launch_bounds__(32) pbp_track_kernel(PbpTrackParams P) {
     if(pbp_on && pbp_periods == thrd && ! require_hm) continue;
     P.plan.need_hm[r] = 1;
   }
+}
+
+__global__ void __launch_bounds__(32) pbp_track_kernel(PbpTrackParams P) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if(b >= P.nutt) return;
+  PbpNoEffect none;
+  pbp_track_utterance(P, b, none);
 }
 
 // ---- pulses ------------------------------------------------------------------------------------------

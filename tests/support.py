@@ -188,14 +188,16 @@ def ref_tolayer0(f0, l1, conf):
 
 
 def check_layer1(o, ref, voiced):
-    """Parity bars for layer-1 members: Rd 1e-5 (see below), VTMAGN 1e-2 dB, VSPHSE 1e-4 rad, lengths equal.
-    The reference's Rd smoother (dsputils.c:596-601) counts samples >= / <= the window mean; on the exactly
-    linear ramps that fill unvoiced gaps the middle sample equals the mean up to one float ulp, so the
-    count -- and Rd by ~5e-4 -- flips with last-bit differences of the fitted Rd at the gap ends. That
-    knife edge is inherent to the reference: allow it on at most 2 % of the frames, bounded by 2e-3."""
+    """Parity bars for layer-1 members: Rd 1e-5 on voiced frames, VTMAGN 1e-2 dB, VSPHSE 1e-4 rad, lengths
+    equal. Unvoiced frames: the reference's Rd smoother (dsputils.c:596-601) counts samples >= / <= the
+    window mean; inside an unvoiced gap the track is an exactly linear ramp, the middle sample equals the mean
+    up to one float ulp, and the count -- hence Rd, by ~0.12 ramp steps -- flips with last-bit differences of
+    the fitted Rd at the gap ends. That knife edge is inherent to the reference and only touches frames whose
+    Rd is never used (no voiced layer-1 members); they are bounded loosely."""
     assert np.array_equal(o["nvs"], ref["nvs"])
     d = np.abs(o["rd"] - ref["rd"])
-    assert d.max() < 2e-3 and (d > 1e-5).mean() < 0.02
+    assert d[voiced].max() < 1e-5 if voiced.any() else True, d[voiced].max()
+    assert d.max() < 5e-3, d.max()
     assert np.abs(o["vtmagn"] - ref["vtmagn"])[voiced].max() < 1e-2
     assert np.abs(phase_err(o["vsphse"], ref["vsphse"])).max() < 1e-4
 

@@ -57,3 +57,65 @@ def test_llsm_analyze_dropin(libs):
     assert np.abs(a["ampl"] - b["ampl"]).max() < 1e-6
     assert S.rms(a["x_res"] - b["x_res"]) < 1e-6
     assert np.abs(a["psd"] - b["psd"]).max() < 0.05
+
+
+def _l1_members(L, ck, conf, nspec):
+    F = conf.nfrm
+    rd = np.zeros(F, np.float32); vt = np.zeros((F, nspec), np.float32); vs = np.zeros((F, conf.maxnhar), np.float32)
+    nvs = np.zeros(F, np.int32)
+    for i in range(F):
+        fr = ck.contents.frames[i]
+        r = L.llsm_container_get(fr, 10); v = L.llsm_container_get(fr, 11); s = L.llsm_container_get(fr, 12)
+        if r:
+            rd[i] = C.cast(r, U.fp)[0]
+        if v:
+            vt[i] = np.ctypeslib.as_array(C.cast(v, U.fp), (nspec,))
+        if s:
+            n = L.llsm_fparray_length(C.cast(s, U.fp)); nvs[i] = n
+            vs[i, :n] = np.ctypeslib.as_array(C.cast(s, U.fp), (n,))
+    return dict(rd=rd[None], vtmagn=vt[None], vsphse=vs[None], nvs=nvs[None])
+
+
+GFM = C.CFUNCTYPE(None, C.POINTER(C.c_float * 5), C.POINTER(C.c_float), C.c_void_p, C.c_void_p)
+
+
+@pytest.mark.parametrize("effect", [False, True])
+def test_layer1_dropin_roundtrip(libs, effect):
+    """llsm_chunk_tolayer1 -> remove HM -> PBPSYN on/off -> llsm_synthesize(use_l1 = 1), with and without an
+    llsm_pbpeffect callback (a deterministic growl-like modifier: test/test-pbpeffects.c:70-85 pattern)."""
+    fr, conf = S.synth_frames(1, 90, seed=21, nhar=80, maxnhar=80)
+    outs, l1s = [], []
+    for L in libs:
+        state = {"n": 0}
+
+        def modifier(g, delta_t, info, frame):
+            state["n"] += 1
+            k = state["n"]
+            g.contents[4] = g.contents[4] * (1.0 + 0.3 * np.sin(0.7 * k))      # Ee
+            g.contents[0] = g.contents[0] * (1.0 - 0.2 * np.cos(0.3 * k))      # Fa
+            delta_t[0] = 2e-4 * np.sin(1.3 * k)
+        cb = GFM(modifier)
+        ck = U.build_chunk(L, fr, conf)
+        L.llsm_chunk_tolayer1(ck, 2048)
+        l1s.append(_l1_members(L, ck, conf, 1025))
+        L.llsm_create_pbpeffect.restype = C.c_void_p
+        for i in range(conf.nfrm):
+            f = ck.contents.frames[i]
+            L.llsm_container_attach_(f, U.HMI, None, None, None)                      # test-layer1-anasynth.c:34
+            if i % 40 > 20:
+                L.llsm_container_attach_(f, 9, C.cast(L.llsm_create_int(1), C.c_void_p), U.fn_ptr(L, "llsm_delete_int"),
+                                         U.fn_ptr(L, "llsm_copy_int"))
+            if effect and 25 <= i < 70:
+                e = L.llsm_create_pbpeffect(cb, None)
+                L.llsm_container_attach_(f, 8, C.c_void_p(e), U.fn_ptr(L, "llsm_delete_pbpeffect"),
+                                         U.fn_ptr(L, "llsm_copy_pbpeffect"))
+        so = L.llsm_create_soptions(C.c_float(conf.fs))
+        so.contents.use_l1 = 1
+        libc.srand(5)
+        o = L.llsm_synthesize(so, ck)
+        assert o, "llsm_synthesize(use_l1) returned NULL"
+        outs.append(U.output_arrays(o))
+        L.llsm_delete_output(o); L.llsm_delete_soptions(so); L.llsm_delete_chunk(ck)
+    S.check_layer1(l1s[0], l1s[1], (fr["f0"] > 0))
+    for a, b, name in zip(outs[0], outs[1], ("y", "y_sin", "y_noise")):
+        assert S.rms(a - b) < 1e-4, (name, S.rms(a - b))
