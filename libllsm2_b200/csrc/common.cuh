@@ -123,3 +123,10 @@ __device__ float2* block_fft(float2* a, float2* b, int lg, const float2* __restr
   }
   return a;
 }
+
+// 2^ceil(e) as an exact integer (device pow() is only accurate to an ulp, and the reference
+// truncates pow(2, ceil(log2(x))) to int: layer0.c:201, dsputils.c:485)
+__host__ __device__ __forceinline__ int pow2_ceil(double e) {
+  int k = (int)ceil(e);
+  return k <= 0 ? 1 : (k >= 30 ? (1 << 30) : (1 << k));
+}

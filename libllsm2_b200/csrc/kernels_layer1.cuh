@@ -34,7 +34,7 @@ __device__ __forceinline__ float lip_arg(float2 r) { return (float)atan2((double
 // ampl[nhar] (shared or global) -> out[nhar] (shared). bufa / bufb: 2 x nfft float2 of shared memory,
 // ha: (nhar + 1) floats of shared scratch. nfft = max(64, 2^(ceil(log2 nhar) + 2)).
 __device__ __forceinline__ int minphase_nfft(int nhar) {
-  int n = (int)pow(2.0, ceil(log2((double)nhar) + 2.0));
+  int n = pow2_ceil(log2((double)nhar) + 2.0);
   return n > 64 ? n : 64;
 }
 

@@ -116,7 +116,7 @@ LF_HD void pbp_track_utterance(const PbpTrackParams& P, int b, Mod& mod) {
     if((pbp_on || pbp_periods > 0) && num_periods > 0) {
       float lp2 = len_period * 2.0f;
       float mxs = lp2 > (float)P.nspec ? lp2 : (float)P.nspec;
-      const int pulse_size = (int)pow(2.0, ceil(log2((double)mxs)));
+      const int pulse_size = pow2_ceil(log2((double)mxs));
       const float t_period = (float)(1.0 / (double)f0);
       const LfModel sm = lf_from_rd(P.rd[r], t_period, 1.0f);
       const int np = num_periods < PBP_MAXP ? num_periods : PBP_MAXP;
