@@ -12,7 +12,7 @@ struct AnaKey {
 // host plan of the analysis path: sizes and tables fixed by the configuration
 struct AnaPlan {
   int nwin = 0, nfft = 0, lg_nfft = 0, nspec = 0, nfft_s = 0, lg_nfft_s = 0;
-  float win_power = 0, std_norm = 0;
+  float win_power = 0, std_norm = 0, std_norm_blackman = 0;
   std::vector<float> win_psd;
   std::vector<int> ip_k; std::vector<float> ip_r;
   struct ChanFilt { int nstage; double b[2][5]; double a[2][5]; };
@@ -42,6 +42,10 @@ static inline void build_ana_plan(AnaPlan& p, float fs, float thop, int npsd, in
   double ws = 0; for(int i = 0; i < 1024; i ++) ws += h[i];
   float sn = (float)ws; sn = sn * 0.5f;
   p.std_norm = sn;
+  std::vector<float> bw; make_blackman(bw, 1024);
+  double wb = 0; for(int i = 0; i < 1024; i ++) wb += bw[i];
+  float snb = (float)wb; snb = snb * 0.5f;
+  p.std_norm_blackman = snb;
   // interp1u(0, fs / 2, v, nspec, linspace(0, fs / 2, npsd), npsd) (layer0.c:388-396), exclusive end
   float x1 = (float)((double)fs / 2.0);
   double step = ((double)x1 - 0.0) / p.nspec;
@@ -68,7 +72,7 @@ static inline void build_ana_plan(AnaPlan& p, float fs, float thop, int npsd, in
 struct AnaPlanDev {
   AnaPlan h;
   float *win_psd = nullptr, *ip_r = nullptr; int* ip_k = nullptr;
-  float2 *tw_s = nullptr, *tw_p = nullptr;
+  float2 *tw_s = nullptr, *tw_p = nullptr, *tw_pp = nullptr;   // tw_pp: 8192-point table for HMPP
   // chunk-parallel IIR tables of the sub-band filters, valid for sequences of iir_nx samples
   DevBuf iir_coef, iir_mpow; int iir_nx = -1, iir_L = 0; int nchannel = 0;
   std::vector<double> h_coef, h_mpow;
@@ -89,6 +93,8 @@ struct AnaPlanDev {
     rc |= up(&win_psd, h.win_psd, st); rc |= up(&ip_k, h.ip_k, st); rc |= up(&ip_r, h.ip_r, st);
     float* a = nullptr; rc |= up(&a, tws, st); tw_s = (float2*)a;
     float* b = nullptr; rc |= up(&b, twp, st); tw_p = (float2*)b;
+    std::vector<float> twpp; build_twiddle(twpp, 8192);
+    float* c2 = nullptr; rc |= up(&c2, twpp, st); tw_pp = (float2*)c2;
     if(dev_sync(st) != 0) rc = -1;
     return rc;
   }
@@ -113,8 +119,8 @@ struct AnaPlanDev {
 };
 
 struct AnaScratch {
-  DevBuf x_sin, x_res, ce, env, lpsd, res, filt;
-  void release() { x_sin.release(); x_res.release(); ce.release(); env.release(); lpsd.release(); res.release(); filt.release(); }
+  DevBuf x_sin, x_res, ce, env, lpsd, res, filt, nfft_utt;
+  void release() { nfft_utt.release(); x_sin.release(); x_res.release(); ce.release(); env.release(); lpsd.release(); res.release(); filt.release(); }
 };
 
 // x: [B][xstride] device; fr: device output arrays; x_res_out optional [B][xstride]
@@ -124,7 +130,7 @@ static inline int run_analyze_l0(const SynthPlanDev& sp, AnaPlanDev& ap, AnaScra
   LaunchCounter* lc) {
   const int B = conf.nutt, F = conf.nfrm, nch = conf.nchannel;
   const AnaPlan& h = ap.h;
-  if(opt.hm_method != 1) return LLSM_B200_ERANGE;        // HMPP: see DESIGN.md
+  if(opt.hm_method != 0 && opt.hm_method != 1) return LLSM_B200_EINVAL;
   if(h.nfft > 8192 || h.nfft_s > 8192) return LLSM_B200_ERANGE;
   const size_t BF = (size_t)B * F;
   const int cst = (nx + 3) & ~3;     // row stride of the sub-band signals (16-byte aligned rows)
@@ -147,15 +153,37 @@ static inline int run_analyze_l0(const SynthPlanDev& sp, AnaPlanDev& ap, AnaScra
 
   // 2. harmonic analysis of x (dsputils.c:175-228)
   const int max_half = (int)ceil((double)conf.fs / 20.0 * (double)opt.rel_winsize / 4.0 * 2.0) + 4;
-  {
-    HarmDftParams H; memset(&H, 0, sizeof(H));
-    H.nfrm = F; H.nfrm_utt = nfrm_utt; H.sig = x; H.nsig = 1; H.nx = nx; H.xstride = xstride;
-    H.f0 = fr.f0; H.center = sp.hm_base; H.fs = conf.fs; H.rel_winsize = opt.rel_winsize;
-    H.maxnhar = conf.maxnhar; H.nhar_out = fr.nhar; H.ampl = fr.ampl; H.phse = fr.phse;
-    H.max_half = max_half;
-    if(launch_harmonic_dft(H, B, st) != 0) return LLSM_B200_ERANGE;
+  auto harmonic_pass = [&](const float* sig, int nsig, int sstride, int maxnhar, int* nhar_o, float* ampl_o, float* phse_o) -> int {
+    if(opt.hm_method == 1) {
+      HarmDftParams H; memset(&H, 0, sizeof(H));
+      H.nfrm = F; H.nfrm_utt = nfrm_utt; H.sig = sig; H.nsig = nsig; H.nx = nx; H.xstride = sstride;
+      H.f0 = fr.f0; H.center = sp.hm_base; H.fs = conf.fs; H.rel_winsize = opt.rel_winsize;
+      H.maxnhar = maxnhar; H.nhar_out = nhar_o; H.ampl = ampl_o; H.phse = phse_o; H.max_half = max_half;
+      if(launch_harmonic_dft(H, B, st) != 0) return LLSM_B200_ERANGE;
+    } else {
+      HarmPpParams H; memset(&H, 0, sizeof(H));
+      H.nfrm = F; H.nfrm_utt = nfrm_utt; H.sig = sig; H.nsig = nsig; H.nx = nx; H.xstride = sstride;
+      H.f0 = fr.f0; H.center = sp.hm_base; H.nfft_utt = sc.nfft_utt.as<int>(); H.fs = conf.fs;
+      H.rel_winsize = opt.rel_winsize; H.std_norm = h.std_norm_blackman; H.maxnhar = maxnhar;
+      H.nhar_out = nhar_o; H.ampl = ampl_o; H.phse = phse_o; H.tw = ap.tw_pp; H.ntw = 8192; H.max_nfft = 8192;
+      size_t smem = (size_t)H.max_nfft * 16 + 16;
+#ifndef LLSM_EMU
+      cudaFuncSetAttribute(harmonic_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#endif
+      LLSM_LAUNCH(harmonic_pp_kernel, dim3(F, B * nsig), dim3(HP_THREADS), smem, st, H);
+    }
+    if(lc) lc->n ++;
+    return 0;
+  };
+  if(opt.hm_method == 0) {                       // one FFT size per utterance (dsputils.c:318-326)
+    if(sc.nfft_utt.reserve((size_t)B * 4) != 0) return LLSM_B200_ENOMEM;
+    MinF0Params M; memset(&M, 0, sizeof(M));
+    M.nfrm = F; M.nfrm_utt = nfrm_utt; M.f0 = fr.f0; M.fs = conf.fs; M.rel_winsize = opt.rel_winsize;
+    M.nfft_utt = sc.nfft_utt.as<int>();
+    LLSM_LAUNCH(utt_fftsize_kernel, dim3(B), dim3(128), 0, st, M);
     if(lc) lc->n ++;
   }
+  { int rc = harmonic_pass(x, 1, xstride, conf.maxnhar, fr.nhar, fr.ampl, fr.phse); if(rc) return rc; }
 
   // 3. residual: x - resynthesised sinusoids (layer0.c:498-501; options == NULL, ny = nx)
   {
@@ -212,14 +240,9 @@ static inline int run_analyze_l0(const SynthPlanDev& sp, AnaPlanDev& ap, AnaScra
     LLSM_LAUNCH(iir_filtfilt_kernel, dim3(B * nch), dim3(IIR_NT), 0, st, I);
     if(lc) lc->n ++;
 
-    HarmDftParams H; memset(&H, 0, sizeof(H));
-    H.nfrm = F; H.nfrm_utt = nfrm_utt; H.sig = sc.ce.as<float>(); H.nsig = nch; H.nx = nx; H.xstride = cst;
-    H.f0 = fr.f0; H.center = sp.hm_base; H.fs = conf.fs; H.rel_winsize = opt.rel_winsize;
-    H.maxnhar = conf.maxnhar_e; H.nhar_out = fr.enhar; H.ampl = fr.eampl; H.phse = fr.ephse;
-    H.max_half = max_half;
     if(conf.maxnhar_e > 0) {
-      if(launch_harmonic_dft(H, B, st) != 0) return LLSM_B200_ERANGE;
-      if(lc) lc->n ++;
+      int rc = harmonic_pass(sc.ce.as<float>(), nch, cst, conf.maxnhar_e, fr.enhar, fr.eampl, fr.ephse);
+      if(rc) return rc;
     }
 
     DcParams D; memset(&D, 0, sizeof(D));

@@ -489,3 +489,112 @@ __global__ void __launch_bounds__(128) noise_psd_out_kernel(PsdOutParams P) {
     P.psdres[orow + j] = (float)((double)rr / 2.3025851 * 10.0);                // LOG2IN
   }
 }
+
+// ------------------------------------------------------------------------------------------
+// Harmonic estimator, peak-picking method (LLSM_AOPTION_HMPP): llsm_compute_spectrogram
+// (dsputils.c:96-115, Blackman, zero-phase, one FFT size per utterance from its lowest voiced F0:
+// llsm_get_fftsize dsputils.c:318-326), log magnitude (dsputils.c:203-204), then per harmonic the
+// arg-max within +-0.3 f0, parabolic refinement on the log spectrum and a linear interpolation of
+// the WRAPPED phase between the two neighbouring bins (llsm_harmonic_peakpicking dsputils.c:126-143).
+// ------------------------------------------------------------------------------------------
+struct MinF0Params { int nfrm; const int* nfrm_utt; const float* f0; float fs, rel_winsize; int* nfft_utt; };
+
+__global__ void __launch_bounds__(128) utt_fftsize_kernel(MinF0Params P) {
+  __shared__ float red[128];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int nf = P.nfrm_utt ? P.nfrm_utt[b] : P.nfrm;
+  float m = 1000.f;                                   // dsputils.c:319
+  for(int i = tid; i < nf; i += blockDim.x) { float f = P.f0[(size_t)b * P.nfrm + i]; if(f > 0 && f < m) m = f; }
+  red[tid] = m;
+  __syncthreads();
+  for(int o = blockDim.x >> 1; o > 0; o >>= 1) { if(tid < o) red[tid] = fminf(red[tid], red[tid + o]); __syncthreads(); }
+  if(tid == 0) {
+    int mw = ana_winsize(P.fs, red[0], P.rel_winsize);  // round(fs / minf0 * rel_winsize / 2) * 2
+    P.nfft_utt[b] = pow2_ceil(log2((double)mw));
+  }
+}
+
+struct HarmPpParams {
+  int nfrm; const int* nfrm_utt;
+  const float* sig; int nsig, nx, xstride;
+  const float* f0; const int* center; const int* nfft_utt;
+  float fs, rel_winsize, std_norm;                    // std_norm = 0.5 * sum(blackman(1024))
+  int maxnhar;
+  int* nhar_out; float* ampl; float* phse;
+  const float2* tw; int ntw; int max_nfft;
+};
+
+#define HP_THREADS 256
+
+__global__ void __launch_bounds__(HP_THREADS) harmonic_pp_kernel(HarmPpParams P) {
+  LLSM_DYN_SMEM(smem);
+  float2* bufa = (float2*)smem;
+  float2* bufb = bufa + P.max_nfft;
+  const int i = blockIdx.x;
+  const int b = blockIdx.y / P.nsig, c = blockIdx.y % P.nsig;
+  const int nf = P.nfrm_utt ? P.nfrm_utt[b] : P.nfrm;
+  const int tid = threadIdx.x, nth = blockDim.x;
+  const size_t fidx = ((size_t)b * P.nfrm + i) * P.nsig + c;
+  if(i >= nf) return;
+  const float f0 = P.f0[(size_t)b * P.nfrm + i];
+  if(! (f0 > 0)) {
+    if(tid == 0) P.nhar_out[fidx] = 0;
+    for(int k = tid; k < P.maxnhar; k += nth) { P.ampl[fidx * P.maxnhar + k] = 0; P.phse[fidx * P.maxnhar + k] = 0; }
+    return;
+  }
+  const int nfft = P.nfft_utt[b];
+  if(nfft > P.max_nfft) { if(tid == 0) P.nhar_out[fidx] = -1; return; }
+  int lg = 0; while((1 << lg) < nfft) lg ++;
+  const int ws = ana_winsize(P.fs, f0, P.rel_winsize);
+  const int nh = ana_nhar(P.fs, f0, P.maxnhar);
+  const float* x = P.sig + ((size_t)b * P.nsig + c) * P.xstride;
+  const int center = P.center[i];
+  // zero-phase Blackman frame (window centre at buffer index 0)
+  for(int k = tid; k < nfft; k += nth) bufa[k] = make_float2(0.f, 0.f);
+  __syncthreads();
+  for(int j = tid; j < ws; j += nth) {
+    int idx = center + j - ws / 2;
+    float v = 0.f;
+    if(idx >= 0 && idx < P.nx) {
+      double s1, c1, s2, c2;
+      sincospi(2.0 * (double)j / (double)ws, &s1, &c1); sincospi(4.0 * (double)j / (double)ws, &s2, &c2);
+      float w = (float)(0.42 - 0.5 * c1 + 0.08 * c2);
+      v = x[idx] * w;
+    }
+    int k = ((j - ws / 2) % nfft + nfft) % nfft;      // ws <= nfft here: no aliasing, plain placement
+    bufa[k] = make_float2(v, 0.f);
+  }
+  __syncthreads();
+  float2* X = block_fft<false>(bufa, bufb, lg, P.tw, P.ntw);
+  float2* Y = (X == bufa) ? bufb : bufa;
+  // log magnitude (x: log(|X| normaliser + 1e-8)) and phase (y) per bin
+  float normalizer = 1024.0f / P.std_norm; normalizer = normalizer / (float)ws;
+  for(int k = tid; k <= nfft / 2; k += nth) {
+    float2 v = X[k];
+    float mag = (float)sqrt((double)v.x * v.x + (double)v.y * v.y) * normalizer;
+    Y[k] = make_float2((float)log((double)mag + 1e-8), (float)atan2((double)v.y, (double)v.x));
+  }
+  __syncthreads();
+  for(int k = tid; k < nh; k += nth) {
+    const int hi = k + 1;
+    float lo_f = __fmul_rn(f0, (float)hi - 0.3f); lo_f = lo_f / P.fs; lo_f = __fmul_rn(lo_f, (float)nfft);
+    float up_f = __fmul_rn(f0, (float)hi + 0.3f); up_f = up_f / P.fs; up_f = __fmul_rn(up_f, (float)nfft);
+    int l = (int)round((double)lo_f), u = (int)round((double)up_f);
+    if(l < 1) l = 1;
+    if(u > nfft / 2 - 1) u = nfft / 2 - 1;
+    int pk = l;
+    for(int q = l + 1; q <= u; q ++) if(Y[q].x > Y[pk].x) pk = q;
+    double a = Y[pk - 1].x, bq = Y[pk].x, cq = Y[pk + 1].x;
+    double a1 = (a + cq) * 0.5 - bq, a2 = (cq - a) * 0.5;
+    double xo = a1 != 0 ? -a2 / (2.0 * a1) : 0;
+    if(! (fabs(xo) < 1.0)) xo = 0;
+    float pf = (float)(pk + xo);
+    float pa = (float)(a1 * xo * xo + a2 * xo + bq);
+    P.ampl[fidx * P.maxnhar + k] = (float)exp((double)pa);
+    int ib = (int)pf;
+    float pa0 = Y[ib].y, pa1 = Y[ib + 1].y;
+    P.phse[fidx * P.maxnhar + k] = (float)((double)pa0 + ((double)pa1 - (double)pa0) * fmod((double)pf, 1.0));
+  }
+  for(int k = nh + tid; k < P.maxnhar; k += nth) { P.ampl[fidx * P.maxnhar + k] = 0; P.phse[fidx * P.maxnhar + k] = 0; }
+  if(tid == 0) P.nhar_out[fidx] = nh;
+}

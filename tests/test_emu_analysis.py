@@ -26,14 +26,18 @@ def check_analysis(o, ref, conf):
     assert np.abs(S.phase_err(o["ephse"], ref["ephse"]) * ref["eampl"]).max() < 1e-5 * float(ref["eampl"].max())
 
 
-def test_analysis_c2_shape_small():
+import pytest
+
+
+@pytest.mark.parametrize("method", [1, 0])     # LLSM_AOPTION_HMCZT (reference default), LLSM_AOPTION_HMPP
+def test_analysis_c2_shape_small(method):
     fr, conf = S.synth_frames(1, 24, seed=3, nhar=100, maxnhar=100)
     y, ys, yn = S.ref_synthesize(fr, conf, seed=7)
     nx = y.shape[1]
-    ref = S.ref_analyze(y, fr["f0"], conf)
+    ref = S.ref_analyze(y, fr["f0"], conf, hm_method=method)
     emu = S.load_emu()
     o = S.alloc_analysis_out(conf, nx, fr["f0"])
-    ao = abi.AOptions(); ao.f0_refine = 1; ao.hm_method = 1; ao.rel_winsize = 4.0
+    ao = abi.AOptions(); ao.f0_refine = 1; ao.hm_method = method; ao.rel_winsize = 4.0
     fo = S.frames_out_struct(o)
     rc = emu.emu_analyze_l0(C.byref(conf), C.byref(ao), y.ctypes.data_as(C.c_void_p), nx, nx,
                             C.byref(fo), o["x_res"].ctypes.data_as(C.c_void_p))

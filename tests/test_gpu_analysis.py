@@ -18,25 +18,32 @@ def ctx():
     c.close()
 
 
-def _analyze_gpu(ctx, conf, x, f0):
+def _analyze_gpu(ctx, conf, x, f0, method=1):
     import torch
     import libllsm2_b200 as L
-    out = L.analyze_l0(ctx, conf, torch.from_numpy(x).cuda(), torch.from_numpy(f0).cuda(), want_residual=True)
+    out = L.analyze_l0(ctx, conf, torch.from_numpy(x).cuda(), torch.from_numpy(f0).cuda(), want_residual=True,
+                       options={"hm_method": method})
     torch.cuda.synchronize()
     return {k: v.cpu().numpy() for k, v in out.items()}
 
 
-def _case(ctx, B, F, **kw):
+def _case(ctx, B, F, method=1, **kw):
     fr, conf = S.synth_frames(B, F, **kw)
     y, ys, yn = S.ref_synthesize(fr, conf, seed=7)
-    ref = S.ref_analyze(y, fr["f0"], conf)
-    o = _analyze_gpu(ctx, conf, np.ascontiguousarray(y), fr["f0"])
+    ref = S.ref_analyze(y, fr["f0"], conf, hm_method=method)
+    o = _analyze_gpu(ctx, conf, np.ascontiguousarray(y), fr["f0"], method)
     check_analysis(o, ref, conf)
     return fr, conf, y, ref, o
 
 
 def test_analysis_c2_shape(ctx):
     _case(ctx, 2, 200, seed=3, nhar=100, maxnhar=100)
+
+
+def test_analysis_peak_picking_method(ctx):
+    """LLSM_AOPTION_HMPP, the method test/test-layer0-anasynth.c uses by default (:34-37)."""
+    _case(ctx, 2, 150, method=0, seed=13, nhar=100, maxnhar=100)
+    _case(ctx, 1, 120, method=0, seed=14, thop=128 / 44100.0, nhar=200, maxnhar=400, nhar_e=5, npsd=128, f0_lo=70, f0_hi=200)
 
 
 def test_analysis_c1_shape(ctx):
