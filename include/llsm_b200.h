@@ -213,6 +213,19 @@ int llsm_b200_tolayer1_host(llsm_b200_ctx* ctx, const llsm_b200_conf* conf,
 int llsm_b200_tolayer0_host(llsm_b200_ctx* ctx, const llsm_b200_conf* conf, const int* nfrm_utt,
   const float* f0, const llsm_b200_layer1* in, int* nhar, float* ampl, float* phse);
 
+
+/* ---- frame-range sharding of one batch across GPUs ----
+   Only frames [frame_lo, frame_hi) of every utterance contribute: the outputs are PARTIAL sums over the
+   full-length rows (zero where the shard does not reach). Summing the partial y_sin / y_noise of all
+   shards gives the unsharded result; since a frame reaches at most llsm_b200_halo_length() samples
+   beyond its centre, only boundary strips have to be exchanged (libllsm2_b200/parallel.py does it with
+   one NCCL all-gather). The frame arrays must hold valid data for [frame_lo - 3, frame_hi + 3). */
+int llsm_b200_synthesize_l0_shard(llsm_b200_ctx* ctx, const llsm_b200_conf* conf,
+  const llsm_b200_frames* frames, const llsm_b200_soptions* opt, const llsm_b200_output* out,
+  int frame_lo, int frame_hi);
+int llsm_b200_halo_length(const llsm_b200_conf* conf);              /* samples a frame reaches past its centre */
+int llsm_b200_frame_position(int i, float thop, float fs);          /* round(i * thop * fs), layer0.c:127-128 */
+
 #ifdef __cplusplus
 }
 #endif

@@ -37,6 +37,9 @@ def lib():
     L.llsm_b200_synthesize_l0.argtypes = [P, C.POINTER(abi.Conf), C.POINTER(abi.Frames),
                                           C.POINTER(abi.SOptions), C.POINTER(abi.Output)]
     L.llsm_b200_synthesize_l0_host.argtypes = L.llsm_b200_synthesize_l0.argtypes
+    L.llsm_b200_synthesize_l0_shard.argtypes = L.llsm_b200_synthesize_l0.argtypes + [C.c_int, C.c_int]
+    L.llsm_b200_halo_length.argtypes = [C.POINTER(abi.Conf)]
+    L.llsm_b200_frame_position.argtypes = [C.c_int, C.c_float, C.c_float]
     L.llsm_b200_synthesize_harmonics.argtypes = [P, C.POINTER(abi.Conf), C.POINTER(abi.Frames),
                                                  C.POINTER(abi.SOptions), P, C.c_int, C.c_int]
     L.llsm_b200_analyze_l0.argtypes = [P, C.POINTER(abi.Conf), C.POINTER(abi.AOptions), P, C.c_int,

@@ -241,3 +241,19 @@ def synthesize_l1(ctx, conf, frames, layer1, pbpsyn=None, white=None, seed=0, op
     so = _soptions(options, white, seed)
     check(lib().llsm_b200_synthesize_l1(ctx._h, C.byref(conf), C.byref(f), C.byref(l1), _ptr(pbpsyn), C.byref(so), C.byref(o)))
     return out
+
+
+def synthesize_l0_shard(ctx, conf, frames, frame_lo, frame_hi, white=None, seed=0, options=None, out=None):
+    """Partial synthesis of frames [frame_lo, frame_hi) (see include/llsm_b200.h, frame-range sharding)."""
+    import torch
+    ny = output_length(conf.nfrm, conf.thop, conf.fs)
+    dev = frames["f0"].device
+    if out is None:
+        out = {k: torch.empty((conf.nutt, ny), dtype=torch.float32, device=dev) for k in ("y", "y_sin", "y_noise")}
+    o = abi.Output()
+    o.y, o.y_sin, o.y_noise, o.stride = _ptr(out["y"]), _ptr(out["y_sin"]), _ptr(out["y_noise"]), out["y"].shape[1]
+    f = _frames(frames)
+    so = _soptions(options, white, seed)
+    check(lib().llsm_b200_synthesize_l0_shard(ctx._h, C.byref(conf), C.byref(f), C.byref(so), C.byref(o),
+                                              int(frame_lo), int(frame_hi)))
+    return out

@@ -163,6 +163,41 @@ int llsm_b200_synthesize_l0(llsm_b200_ctx* ctx, const llsm_b200_conf* conf,
   return cuda_ok("synthesize_l0");
 }
 
+int llsm_b200_synthesize_l0_shard(llsm_b200_ctx* ctx, const llsm_b200_conf* conf,
+  const llsm_b200_frames* fr, const llsm_b200_soptions* opt, const llsm_b200_output* out,
+  int frame_lo, int frame_hi) {
+  if(ctx == nullptr) return fail(LLSM_B200_ENODEVICE, "no context (no CUDA device?)");
+  int rc = check_conf(conf); if(rc) return rc;
+  if(! fr || ! opt || ! out) return fail(LLSM_B200_EINVAL, "NULL argument");
+  if(! fr->f0 || ! fr->nhar || ! fr->ampl || ! fr->phse || ! fr->psd || ! fr->edc || ! fr->enhar ||
+     ! fr->eampl || ! fr->ephse) return fail(LLSM_B200_EINVAL, "a required frame array is NULL");
+  if(! out->y_sin || ! out->y_noise) return fail(LLSM_B200_EINVAL, "y_sin and y_noise are required");
+  std::lock_guard<std::mutex> lk(ctx->mtx);
+  cudaSetDevice(ctx->device);
+  SynthPlanDev* pd = get_plan(ctx, conf);
+  if(pd == nullptr) return fail(LLSM_B200_ENOMEM, "could not build the synthesis plan");
+  if(out->stride < pd->h.ny) return fail(LLSM_B200_EINVAL, "stride %d < ny %d", out->stride, pd->h.ny);
+  const int* ny_utt = ragged_lengths(ctx, conf, fr->nfrm_utt);
+  if(fr->nfrm_utt && ! ny_utt) return fail(LLSM_B200_ENOMEM, "ny_utt");
+  if(frame_lo < 0 || frame_hi > conf->nfrm || frame_lo >= frame_hi) return fail(LLSM_B200_EINVAL, "bad frame range [%d, %d)", frame_lo, frame_hi);
+  rc = run_synth_l0(*pd, ctx->scratch, *conf, *fr, *opt, *out, ny_utt, ctx->stream, &ctx->lc, frame_lo, frame_hi);
+  if(rc != 0) return fail(rc, "synthesis launch failed (code %d): size outside supported range?", rc);
+  return cuda_ok("synthesize_l0");
+}
+
+int llsm_b200_halo_length(const llsm_b200_conf* conf) {
+  if(conf == nullptr) return -1;
+  SynthPlan p; build_synth_plan(p, 2, conf->fs, conf->thop, conf->npsd, conf->nchannel, conf->chanfreq);
+  int h = p.n_hm / 2 + 1;
+  if(p.nfft_ns / 2 + 1 > h) h = p.nfft_ns / 2 + 1;
+  return h;
+}
+
+int llsm_b200_frame_position(int i, float thop, float fs) {
+  float r = (float)i * thop; r = r * fs;
+  return (int)round((double)r);
+}
+
 int llsm_b200_synthesize_harmonics(llsm_b200_ctx* ctx, const llsm_b200_conf* conf,
   const llsm_b200_frames* fr, const llsm_b200_soptions* opt, float* y_sin, int nsamp, int stride) {
   if(ctx == nullptr) return fail(LLSM_B200_ENODEVICE, "no context (no CUDA device?)");

@@ -102,7 +102,8 @@ struct LaunchCounter { long long n = 0; };
 // options == NULL call of the analysis residual (layer0.c:498).
 static inline int run_harmonics(const SynthPlanDev& pd, const llsm_b200_conf& conf,
   const llsm_b200_frames& fr, const llsm_b200_soptions* opt, const int* ny_utt_dev,
-  float* y_sin, int ny_valid, int nsamp, int stride, cudaStream_t st, LaunchCounter* lc) {
+  float* y_sin, int ny_valid, int nsamp, int stride, cudaStream_t st, LaunchCounter* lc,
+  int frame_lo = 0, int frame_hi = 0) {
   BankParams P;
   memset(&P, 0, sizeof(P));
   P.nfrm = conf.nfrm; P.maxnhar = conf.maxnhar;
@@ -113,7 +114,7 @@ static inline int run_harmonics(const SynthPlanDev& pd, const llsm_b200_conf& co
   P.fs = conf.fs;
   P.has_options = opt != nullptr;
   if(opt) { P.use_iczt = opt->use_iczt; P.iczt_a = opt->iczt_param_a; P.iczt_b = opt->iczt_param_b; }
-  P.y_sin = y_sin;
+  P.y_sin = y_sin; P.frame_lo = frame_lo; P.frame_hi = frame_hi;
   if(launch_hm_bank(P, conf.nutt, conf.nfrm, st) != 0) return LLSM_B200_ERANGE;
   if(lc) lc->n += 1;
   return 0;
@@ -123,12 +124,12 @@ static inline int run_harmonics(const SynthPlanDev& pd, const llsm_b200_conf& co
 // out.y_sin must already hold the harmonic component.
 static inline int run_noise_part(const SynthPlanDev& pd, SynthScratch& sc, const llsm_b200_conf& conf,
   const llsm_b200_frames& fr, const llsm_b200_soptions& opt, const llsm_b200_output& out,
-  const int* ny_utt_dev, cudaStream_t st, LaunchCounter* lc);
+  const int* ny_utt_dev, cudaStream_t st, LaunchCounter* lc, int frame_lo = 0, int frame_hi = 0);
 
 // Full layer-0 synthesis on device pointers (llsm_synthesize, layer0.c:636-664).
 static inline int run_synth_l0(const SynthPlanDev& pd, SynthScratch& sc, const llsm_b200_conf& conf,
   const llsm_b200_frames& fr, const llsm_b200_soptions& opt, const llsm_b200_output& out,
-  const int* ny_utt_dev, cudaStream_t st, LaunchCounter* lc) {
+  const int* ny_utt_dev, cudaStream_t st, LaunchCounter* lc, int frame_lo = 0, int frame_hi = 0) {
   const SynthPlan& h = pd.h;
   const int B = conf.nutt, nch = conf.nchannel;
   if(nch < 1 || nch > LLSM_B200_MAXCHANNEL) return LLSM_B200_EINVAL;
@@ -136,14 +137,14 @@ static inline int run_synth_l0(const SynthPlanDev& pd, SynthScratch& sc, const l
 
   // 1. harmonic component
   int rc = run_harmonics(pd, conf, fr, &opt, ny_utt_dev, out.y_sin, h.ny, out.stride, out.stride,
-    st, lc);
+    st, lc, frame_lo, frame_hi);
   if(rc != 0) return rc;
-  return run_noise_part(pd, sc, conf, fr, opt, out, ny_utt_dev, st, lc);
+  return run_noise_part(pd, sc, conf, fr, opt, out, ny_utt_dev, st, lc, frame_lo, frame_hi);
 }
 
 static inline int run_noise_part(const SynthPlanDev& pd, SynthScratch& sc, const llsm_b200_conf& conf,
   const llsm_b200_frames& fr, const llsm_b200_soptions& opt, const llsm_b200_output& out,
-  const int* ny_utt_dev, cudaStream_t st, LaunchCounter* lc) {
+  const int* ny_utt_dev, cudaStream_t st, LaunchCounter* lc, int frame_lo, int frame_hi) {
   const SynthPlan& h = pd.h;
   const int B = conf.nutt, nch = conf.nchannel;
   const int tstride = (h.nt + 3) & ~3;
@@ -179,6 +180,11 @@ static inline int run_noise_part(const SynthPlanDev& pd, SynthScratch& sc, const
   E.has_options = 1; E.use_iczt = opt.use_iczt; E.iczt_a = opt.iczt_param_a; E.iczt_b = opt.iczt_param_b;
   E.colored = sc.colored.as<float>(); E.nt = h.nt; E.ntemplate = h.ntemplate; E.tstride = tstride;
   E.chan_mask = mask;
+  if(frame_hi > 0) {                 // excitation is only needed under the owned frames' windows
+    E.samp_lo = h.hm_base[frame_lo] - h.n_ns / 2 - 2;
+    E.samp_hi = h.hm_base[frame_hi - 1] + h.n_ns / 2 + 2;
+    if(E.samp_lo < 0) E.samp_lo = 0;
+  }
   E.y_exc = sc.y_exc.as<float>();
   if(launch_noise_excitation(E, B, st) != 0) return LLSM_B200_ERANGE;
   if(lc) lc->n += 1;
@@ -196,7 +202,7 @@ static inline int run_noise_part(const SynthPlanDev& pd, SynthScratch& sc, const
   S.y_exc = sc.y_exc.as<float>(); S.stride_exc = out.stride;
   S.y_sin = out.y_sin; S.y_noise = out.y_noise; S.y = out.y;
   S.ny = h.ny; S.nsamp = out.stride; S.stride = out.stride;
-  S.seg = 8192;
+  S.seg = 8192; S.frame_lo = frame_lo; S.frame_hi = frame_hi;
   if(h.nfft_ns > 8192) return LLSM_B200_ERANGE;
   if(launch_noise_shape(S, B, st) != 0) return LLSM_B200_ERANGE;
   if(lc) lc->n += 1;

@@ -36,6 +36,7 @@ struct BankParams {
   int has_options;          // 0: options == NULL (always sinusoid bank, llsmutils.c:48-49)
   int use_iczt; float iczt_a, iczt_b;
   const int* frame_mask;    // [B][nfrm] optional: 0 = skip the frame (PbP path, layer0.c:261)
+  int frame_lo, frame_hi;   // frames [lo, hi) contribute (frame-range sharding); hi <= 0 means all
   int npass;                // frame slots per CTA = warps * npass
   float* y_sin;             // [B][stride]
 };
@@ -79,6 +80,7 @@ __global__ void __launch_bounds__(NTHR, MINB) hm_bank_ola_kernel(BankParams P) {
     if(nh > 2048) nh = 2048;               // layer0.c:119,130
     bool voiced = inrange && f0 > 0 && nh > 0;        // layer0.c:125 (f0 == 0 skips the frame)
     if(voiced && P.frame_mask) voiced = P.frame_mask[row + f] != 0;
+    if(P.frame_hi > 0 && (f < P.frame_lo || f >= P.frame_hi)) voiced = false;
     if(lane == 0) {
       sb[s] = inrange ? P.hm_base[f] : (f < 0 ? -(1 << 28) : (1 << 28));
       sv[s] = voiced ? 1 : 0;
@@ -275,6 +277,7 @@ struct ExcParams {
   const float* colored;     // [B][nchannel][nt]
   int nt, ntemplate, tstride;   // tstride: row stride of colored
   unsigned chan_mask;       // bit c set when channel c exists (fmin < fs / 2)
+  int samp_lo, samp_hi;     // only samples [lo, hi) are needed (frame-range sharding); hi <= 0 means all
   float* y_exc;             // [B][stride]
 };
 
@@ -318,6 +321,10 @@ __global__ void __launch_bounds__(EXC_THREADS) noise_excitation_kernel(ExcParams
   const int b = blockIdx.y;
   const int p0 = blockIdx.x * EXC_THREADS;
   const int p = p0 + (int)threadIdx.x;
+  if(P.samp_hi > 0 && (p0 + EXC_THREADS <= P.samp_lo || p0 >= P.samp_hi)) {   // CTA outside the shard (uniform)
+    if(p < P.nsamp) P.y_exc[(size_t)blockIdx.y * P.stride + p] = 0.f;
+    return;
+  }
   const int nf = P.nfrm_utt ? P.nfrm_utt[b] : P.nfrm;
   const int ny_b = P.ny_utt ? P.ny_utt[b] : P.ny;
   const int nch = P.nchannel, mne = P.maxnhar_e;
@@ -469,6 +476,7 @@ struct ShapeParams {
   float* y_noise; float* y; // [B][stride]; y may be NULL
   int ny, nsamp, stride;
   int seg;                  // output samples owned by a CTA
+  int frame_lo, frame_hi;   // frames [lo, hi) are filtered (frame-range sharding); hi <= 0 means all
 };
 
 #define SHAPE_THREADS 256
@@ -505,11 +513,13 @@ __global__ void __launch_bounds__(SHAPE_THREADS) noise_shape_kernel(ShapeParams 
   const int ia = lo;
   lo = ia; hi = nf;
   while(lo < hi) { int mid = (lo + hi) >> 1; if(P.center[mid] - half >= ob) hi = mid; else lo = mid + 1; }
-  const int ib = lo;
+  int ib = lo;
+  int ia_ = ia;
+  if(P.frame_hi > 0) { if(ia_ < P.frame_lo) ia_ = P.frame_lo; if(ib > P.frame_hi) ib = P.frame_hi; }
   const double resbias = 0.375 / 2.3025851 * 10.0;   // LOG2IN(LOGRESBIAS), constants.h:5,12
   const float inv = 1.0f / (float)nfft;
 
-  for(int i = ia; i < ib; i += 2) {
+  for(int i = ia_; i < ib; i += 2) {
     const bool hasB = i + 1 < ib;
     __syncthreads();
     // ---- model PSD (+ residual) and its peak for both frames (layer0.c:584-585,598-601)
@@ -676,14 +686,16 @@ __global__ void __launch_bounds__(SHW_THREADS, 2) noise_shape_warp_kernel(ShapeP
   const int ia = lo;
   lo = ia; hi = nf;
   while(lo < hi) { int mid = (lo + hi) >> 1; if(P.center[mid] - HALF >= ob) hi = mid; else lo = mid + 1; }
-  const int ib = lo;
+  int ib = lo;
+  int ia_ = ia;
+  if(P.frame_hi > 0) { if(ia_ < P.frame_lo) ia_ = P.frame_lo; if(ib > P.frame_hi) ib = P.frame_hi; }
   const double resbias = 0.375 / 2.3025851 * 10.0;
   const float inv = 1.0f / 1024.0f;
   __syncthreads();
 
   const float psc = 44100.f / P.fs;
   const float inv_wsqr = 1.0f / P.wsqr;
-  for(int r0 = ia; r0 < ib; r0 += 2 * SHW_WARPS) {
+  for(int r0 = ia_; r0 < ib; r0 += 2 * SHW_WARPS) {
     const int i = r0 + 2 * warp;                 // this warp's pair (i, i + 1)
     const bool hasA = i < ib, hasB = i + 1 < ib;
     bool doA = false, doB = false;

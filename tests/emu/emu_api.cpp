@@ -84,3 +84,13 @@ extern "C" int emu_synthesize_l1(const llsm_b200_conf* conf, const llsm_b200_fra
   sc.colored.release(); sc.y_exc.release(); ps.release(); lp.release(); pd.release();
   return rc;
 }
+
+extern "C" int emu_synthesize_l0_shard(const llsm_b200_conf* conf, const llsm_b200_frames* fr,
+  const llsm_b200_soptions* opt, const llsm_b200_output* out, int frame_lo, int frame_hi) {
+  SynthPlanDev pd;
+  if(pd.build(conf->nfrm, conf->fs, conf->thop, conf->npsd, conf->nchannel, conf->chanfreq, nullptr) != 0) return -100;
+  SynthScratch sc;
+  int rc = run_synth_l0(pd, sc, *conf, *fr, *opt, *out, nullptr, nullptr, nullptr, frame_lo, frame_hi);
+  sc.colored.release(); sc.y_exc.release(); pd.release();
+  return rc;
+}
