@@ -226,6 +226,30 @@ int llsm_b200_synthesize_l0_shard(llsm_b200_ctx* ctx, const llsm_b200_conf* conf
 int llsm_b200_halo_length(const llsm_b200_conf* conf);              /* samples a frame reaches past its centre */
 int llsm_b200_frame_position(int i, float thop, float fs);          /* round(i * thop * fs), layer0.c:127-128 */
 
+/* ---- streaming synthesis: llsm_rtsynth_buffer_* (llsmrt.h:33-56, llsmrt.c:157-602) --------------------
+   One llsm_b200_rt advances conf->nutt independent streams that share fs and thop (hence one hop
+   schedule: llsm_update_cycle, llsmrt.c:110-129). Every stream owns its ring buffers, circular noise
+   templates and previous noise model in HBM; one kernel launch per fed frame serves all streams.
+   Replaces: llsm_create_rtsynth_buffer (:157), _feed (:505), _fetch/_fetch_decomposed (:523/:545, here the
+   samples of a feed are returned by the feed itself), _getlatency (:568), _clear (:578), delete (:225).
+   conf->nfrm is ignored. opt->white: N(0,1) templates [nutt][nchannel][llsm_b200_rt_template_length(fs)]
+   (device pointer, or host pointer with white_on_host = 1) or NULL for the device generator (opt->seed). */
+typedef struct llsm_b200_rt llsm_b200_rt;
+int llsm_b200_rt_template_length(float fs);                          /* min(20000, (int)fs) + 128 */
+int llsm_b200_rt_create(llsm_b200_ctx* ctx, const llsm_b200_conf* conf, const llsm_b200_soptions* opt,
+  int white_on_host, llsm_b200_rt** out);
+void llsm_b200_rt_destroy(llsm_b200_rt* rt);
+int llsm_b200_rt_latency(const llsm_b200_rt* rt);                    /* llsmrt.c:568-571 */
+int llsm_b200_rt_output_length(const llsm_b200_rt* rt, int nfeed);   /* samples the next nfeed feeds produce */
+int llsm_b200_rt_clear(llsm_b200_rt* rt);                            /* llsmrt.c:578-602 */
+/* Feed nfeed consecutive frames per stream (frames: [nutt][nfeed][..]) and receive the samples they
+   release, periodic and aperiodic parts apart (fetch_decomposed): out_p/out_ap [nutt][out_stride],
+   *nout samples per stream. Device pointers; the _host variant copies in and out and synchronises. */
+int llsm_b200_rt_feed(llsm_b200_rt* rt, const llsm_b200_frames* frames, int nfeed,
+  float* out_p, float* out_ap, int out_stride, int* nout);
+int llsm_b200_rt_feed_host(llsm_b200_rt* rt, const llsm_b200_frames* frames, int nfeed,
+  float* out_p, float* out_ap, int out_stride, int* nout);
+
 #ifdef __cplusplus
 }
 #endif

@@ -49,6 +49,14 @@ def lib():
     L.llsm_b200_synthesize_l1.argtypes = [P, C.POINTER(abi.Conf), C.POINTER(abi.Frames), C.POINTER(abi.Layer1), P,
                                           C.POINTER(abi.SOptions), C.POINTER(abi.Output)]
     L.llsm_b200_tolayer0.argtypes = [P, C.POINTER(abi.Conf), P, P, C.POINTER(abi.Layer1), P, P, P]
+    L.llsm_b200_rt_template_length.argtypes = [C.c_float]
+    L.llsm_b200_rt_create.argtypes = [P, C.POINTER(abi.Conf), C.POINTER(abi.SOptions), C.c_int, C.POINTER(C.c_void_p)]
+    L.llsm_b200_rt_destroy.argtypes = [P]
+    L.llsm_b200_rt_latency.argtypes = [P]
+    L.llsm_b200_rt_output_length.argtypes = [P, C.c_int]
+    L.llsm_b200_rt_clear.argtypes = [P]
+    L.llsm_b200_rt_feed.argtypes = [P, C.POINTER(abi.Frames), C.c_int, P, P, C.c_int, C.POINTER(C.c_int)]
+    L.llsm_b200_rt_feed_host.argtypes = L.llsm_b200_rt_feed.argtypes
     _lib = L
     return L
 

@@ -257,3 +257,60 @@ def synthesize_l0_shard(ctx, conf, frames, frame_lo, frame_hi, white=None, seed=
     check(lib().llsm_b200_synthesize_l0_shard(ctx._h, C.byref(conf), C.byref(f), C.byref(so), C.byref(o),
                                               int(frame_lo), int(frame_hi)))
     return out
+
+
+class RtSynth:
+    """llsm_rtsynth_buffer (llsmrt.h:33-56) for a batch of conf.nutt streams sharing fs / thop.
+
+    feed() takes the next nfeed frames of every stream ([nutt][nfeed][..] arrays) and returns the
+    samples they release, (periodic, aperiodic) as llsm_rtsynth_buffer_fetch_decomposed yields them.
+    CUDA tensors in -> CUDA tensors out; numpy / CPU tensors in -> numpy out (copies inside)."""
+
+    def __init__(self, ctx, conf, white=None, seed=0, options=None):
+        self.ctx, self.conf = ctx, conf
+        so = _soptions(options, white, seed)
+        on_host = 0 if (white is None or hasattr(white, "data_ptr") and white.is_cuda) else 1
+        h = C.c_void_p()
+        check(lib().llsm_b200_rt_create(ctx._h, C.byref(conf), C.byref(so), on_host, C.byref(h)))
+        self._h = h
+
+    @staticmethod
+    def template_length(fs):
+        return lib().llsm_b200_rt_template_length(C.c_float(fs))
+
+    @property
+    def latency(self):
+        return lib().llsm_b200_rt_latency(self._h)
+
+    def output_length(self, nfeed=1):
+        return lib().llsm_b200_rt_output_length(self._h, int(nfeed))
+
+    def clear(self):
+        check(lib().llsm_b200_rt_clear(self._h))
+
+    def feed(self, frames, nfeed=1):
+        n = self.output_length(nfeed)
+        f = _frames({k: v for k, v in frames.items() if k != "nfrm_utt"})
+        got = C.c_int(0)
+        f0 = frames["f0"]
+        if hasattr(f0, "is_cuda") and f0.is_cuda:
+            import torch
+            p = torch.empty((self.conf.nutt, n), dtype=torch.float32, device=f0.device)
+            ap = torch.empty_like(p)
+            check(lib().llsm_b200_rt_feed(self._h, C.byref(f), int(nfeed), _ptr(p), _ptr(ap), n, C.byref(got)))
+        else:
+            p = np.empty((self.conf.nutt, n), np.float32); ap = np.empty_like(p)
+            check(lib().llsm_b200_rt_feed_host(self._h, C.byref(f), int(nfeed), _ptr(p), _ptr(ap), n, C.byref(got)))
+        assert got.value == n
+        return p, ap
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().llsm_b200_rt_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -5,6 +5,7 @@
 #include "driver_analysis.h"
 #include "driver_layer1.h"
 #include "driver_pbp.h"
+#include "driver_rt.h"
 #include <cstdio>
 #include <cstdarg>
 #include <mutex>
@@ -276,5 +277,6 @@ int llsm_b200_synthesize_l0_host(llsm_b200_ctx* ctx, const llsm_b200_conf* conf,
 
 #include "api_analysis.inc"
 #include "api_layer1.inc"
+#include "api_rt.inc"
 
 } // extern "C"

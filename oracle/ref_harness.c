@@ -305,3 +305,45 @@ int ref_synthesize_l1_soa(int nfrm, float fs, float thop, int maxnhar, int maxnh
   llsm_delete_chunk(chunk);
   return ny;
 }
+
+#include "llsmrt.h"
+
+/* Streaming synthesis of one utterance through llsm_rtsynth_buffer_* (llsmrt.c): srand(seed), create,
+   then feed every frame and drain the output ring after each feed. use_l1 != 0 converts the chunk to
+   layer 1 first and sets use_l1 (pulse-by-pulse streaming). Returns the number of samples fetched;
+   *latency = llsm_rtsynth_buffer_getlatency. */
+int ref_rtsynth_soa(int nfrm, float fs, float thop, int maxnhar, int maxnhar_e, int npsd,
+  int nchannel, const float* chanfreq, float lip_radius, int use_iczt, int use_l1,
+  const float* f0, const int* nhar, const float* ampl, const float* phse,
+  const float* psd, const float* psdres, const float* edc, const int* enhar,
+  const float* eampl, const float* ephse, unsigned seed,
+  float* y_p, float* y_ap, int cap, int* latency, int clear_at) {
+  llsm_chunk* chunk = chunk_from_soa(nfrm, fs, thop, maxnhar, maxnhar_e, npsd, nchannel,
+    chanfreq, lip_radius, f0, nhar, ampl, phse, psd, psdres, edc, enhar, eampl, ephse);
+  llsm_soptions* sopt = llsm_create_soptions(fs);
+  sopt -> use_iczt = use_iczt;
+  if(use_l1) {
+    llsm_chunk_tolayer1(chunk, 2048);
+    llsm_chunk_phasepropagate(chunk, -1);
+    for(int i = 0; i < nfrm; i ++)
+      llsm_container_attach(chunk -> frames[i], LLSM_FRAME_HM, NULL, NULL, NULL);
+    sopt -> use_l1 = 1;
+  }
+  srand(seed);
+  llsm_rtsynth_buffer* rt = llsm_create_rtsynth_buffer(sopt, chunk -> conf, 4096);
+  *latency = llsm_rtsynth_buffer_getlatency(rt);
+  int n = 0;
+  for(int i = 0; i < nfrm; i ++) {
+    if(i == clear_at) llsm_rtsynth_buffer_clear(rt);
+    llsm_rtsynth_buffer_feed(rt, chunk -> frames[i]);
+    FP_TYPE p, ap;
+    while(llsm_rtsynth_buffer_fetch_decomposed(rt, & p, & ap)) {
+      if(n < cap) { y_p[n] = p; y_ap[n] = ap; }
+      n ++;
+    }
+  }
+  llsm_delete_rtsynth_buffer(rt);
+  llsm_delete_soptions(sopt);
+  llsm_delete_chunk(chunk);
+  return n < cap ? n : cap;
+}

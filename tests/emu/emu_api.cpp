@@ -94,3 +94,23 @@ extern "C" int emu_synthesize_l0_shard(const llsm_b200_conf* conf, const llsm_b2
   sc.colored.release(); sc.y_exc.release(); pd.release();
   return rc;
 }
+
+#include "../../libllsm2_b200/csrc/driver_rt.h"
+// whole-utterance streaming run on the emulator: feed nfrm frames, collect the streamed samples
+extern "C" int emu_rtsynth(const llsm_b200_conf* conf, const llsm_b200_frames* fr, const llsm_b200_soptions* opt,
+  float* out_p, float* out_ap, int out_cap, int* nout, int* latency, int clear_at) {
+  RtBatch R;
+  int rc = rt_create(R, *conf, *opt, 0, nullptr, nullptr);
+  if(rc != 0) return rc;
+  *latency = -R.sin_pos - R.curr_nhop;
+  int total = 0;
+  for(int i = 0; i < conf->nfrm; i ++) {
+    if(i == clear_at) rt_clear(R, nullptr, nullptr);
+    rc = rt_feed(R, *fr, conf->nfrm, i, out_p, out_ap, out_cap, total, nullptr, nullptr);
+    if(rc != 0) { R.release(); return rc; }
+    total += R.next_nhop;
+  }
+  *nout = total;
+  R.release();
+  return 0;
+}

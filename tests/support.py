@@ -229,3 +229,31 @@ def ref_synthesize_l1(fr, conf, pbpsyn, nfft=2048, seed=9, remove_hm=1):
                                       _p(y[b]), _p(ys[b]), _p(yn[b]))
         assert r == ny
     return (y, ys, yn), l1
+
+
+def ref_rtsynth(fr, conf, seed=1, use_iczt=1, use_l1=0, clear_at=-1):
+    """llsm_rtsynth_buffer_* run over every utterance. Returns (p [B][n], ap [B][n], latency)."""
+    lib = load_ref()
+    B, F = conf.nutt, conf.nfrm
+    cap = int(F * conf.thop * conf.fs) + 4096
+    P = np.zeros((B, cap), np.float32); A = np.zeros((B, cap), np.float32)
+    cf = np.array(list(conf.chanfreq), np.float32)
+    lat = C.c_int(0); n = 0
+    for b in range(B):
+        args = [np.ascontiguousarray(fr[k][b]) for k in
+                ("f0", "nhar", "ampl", "phse", "psd", "psdres", "edc", "enhar", "eampl", "ephse")]
+        n = lib.ref_rtsynth_soa(F, C.c_float(conf.fs), C.c_float(conf.thop), conf.maxnhar, conf.maxnhar_e,
+                                conf.npsd, conf.nchannel, _p(cf), C.c_float(conf.lip_radius), use_iczt,
+                                use_l1, *[_p(a) for a in args], C.c_uint(seed + b),
+                                _p(P[b]), _p(A[b]), cap, C.byref(lat), clear_at)
+    return P[:, :n], A[:, :n], lat.value
+
+
+def ref_rt_white(conf, seed=1):
+    """White templates drawn by llsm_create_rtsynth_buffer (ntemplate = fs samples, llsmrt.c:93-107)."""
+    lib = load_ref()
+    nt = min(20000, int(conf.fs)) + 128
+    out = np.zeros((conf.nutt, conf.nchannel, nt), np.float32)
+    for b in range(conf.nutt):
+        lib.ref_draw_white_noise(int(conf.fs), conf.nchannel, C.c_uint(seed + b), _p(out[b]))
+    return out
