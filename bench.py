@@ -140,13 +140,35 @@ def cpu_baseline_single(distinct, conf, nutt=8):
                       "unmodified reference sources + ciglet shim, gcc -Ofast, single thread" % (len(idxs), conf.nfrm)}
 
 
+def usable_cores():
+    """Host threads this process may really use: affinity mask capped by the cgroup CPU quota."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(float(txt[0]) / float(txt[1]))))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                    n = min(n, max(1, q // per))
+        except (OSError, ValueError, IndexError):
+            pass
+    return max(1, n)
+
+
 def run_reference(args):
     import multiprocessing as mp
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     full, conf, distinct = workload(args, distinct=16)
-    ncore = os.cpu_count() or 1
+    ncore = usable_cores()
     per_core = 8
     _G["frames"] = distinct
     pool = mp.get_context("fork").Pool(ncore)

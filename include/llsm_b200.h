@@ -235,6 +235,7 @@ int llsm_b200_frame_position(int i, float thop, float fs);          /* round(i *
    conf->nfrm is ignored. opt->white: N(0,1) templates [nutt][nchannel][llsm_b200_rt_template_length(fs)]
    (device pointer, or host pointer with white_on_host = 1) or NULL for the device generator (opt->seed). */
 typedef struct llsm_b200_rt llsm_b200_rt;
+int llsm_b200_rt_fft_size(float fs, float thop);                     /* llsmrt.c:181; feed keeps min(nhar, nfft) harmonics */
 int llsm_b200_rt_template_length(float fs);                          /* min(20000, (int)fs) + 128 */
 int llsm_b200_rt_create(llsm_b200_ctx* ctx, const llsm_b200_conf* conf, const llsm_b200_soptions* opt,
   int white_on_host, llsm_b200_rt** out);

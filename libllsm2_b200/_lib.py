@@ -50,6 +50,7 @@ def lib():
                                           C.POINTER(abi.SOptions), C.POINTER(abi.Output)]
     L.llsm_b200_tolayer0.argtypes = [P, C.POINTER(abi.Conf), P, P, C.POINTER(abi.Layer1), P, P, P]
     L.llsm_b200_rt_template_length.argtypes = [C.c_float]
+    L.llsm_b200_rt_fft_size.argtypes = [C.c_float, C.c_float]
     L.llsm_b200_rt_create.argtypes = [P, C.POINTER(abi.Conf), C.POINTER(abi.SOptions), C.c_int, C.POINTER(C.c_void_p)]
     L.llsm_b200_rt_destroy.argtypes = [P]
     L.llsm_b200_rt_latency.argtypes = [P]

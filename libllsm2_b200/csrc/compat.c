@@ -914,3 +914,5 @@ llsm_chunk* llsm_analyze(llsm_aoptions* options, FP_TYPE* x, int nx, FP_TYPE fs,
   free(ephse); free(xres);
   return ret;
 }
+
+#include "compat_rt.inc"

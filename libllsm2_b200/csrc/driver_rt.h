@@ -77,7 +77,7 @@ static inline int rt_create(RtBatch& R, const llsm_b200_conf& conf, const llsm_b
   R.ntemplate = (int)conf.fs;                              // ret -> ntemplate = options -> fs
   R.cap = (int)((double)conf.fs * 0.2);                    // ninternal
   float t = conf.thop * conf.fs;
-  R.nfft = pow2_ceil(log2((double)t * 2.2 + 32));          // llsmrt.c:181
+  R.nfft = pow2_ceil(log2((double)t * 2.2 + 32));          // llsmrt.c:181 (also llsm_b200_rt_fft_size)          // llsmrt.c:181
   R.lg_nfft = 0; while((1 << R.lg_nfft) < R.nfft) R.lg_nfft ++;
   R.nspec = R.nfft / 2 + 1;
   if(R.cap < 2 * R.nfft || R.nfft > 8192 || R.nch < 1 || R.nch > LLSM_B200_MAXCHANNEL) return LLSM_B200_ERANGE;

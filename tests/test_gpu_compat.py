@@ -119,3 +119,45 @@ def test_layer1_dropin_roundtrip(libs, effect):
     S.check_layer1(l1s[0], l1s[1], (fr["f0"] > 0))
     for a, b, name in zip(outs[0], outs[1], ("y", "y_sin", "y_noise")):
         assert S.rms(a - b) < 1e-4, (name, S.rms(a - b))
+
+
+def test_llsmrt_dropin(libs):
+    """test-llsmrt.c's loop (feed a frame, drain the ring) on both libraries, a clear in the middle, and the
+    non-blocking fetch / latency / numoutput contracts."""
+    fr, conf = S.synth_frames(1, 36, seed=21, nhar=60, maxnhar=60)
+    outs = []
+    for L in libs:
+        L.llsm_create_rtsynth_buffer.restype = C.c_void_p
+        L.llsm_create_rtsynth_buffer.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        for f in ("llsm_rtsynth_buffer_feed", "llsm_rtsynth_buffer_fetch_decomposed", "llsm_rtsynth_buffer_fetch",
+                  "llsm_rtsynth_buffer_clear", "llsm_delete_rtsynth_buffer", "llsm_rtsynth_buffer_getlatency",
+                  "llsm_rtsynth_buffer_numoutput"):
+            getattr(L, f).argtypes = [C.c_void_p] + [C.c_void_p] * (2 if f.endswith("decomposed") else 1 if f.endswith(("feed", "fetch")) else 0)
+        ck = U.build_chunk(L, fr, conf)
+        so = L.llsm_create_soptions(C.c_float(conf.fs))
+        libc.srand(31)
+        rt = L.llsm_create_rtsynth_buffer(so, ck.contents.conf, 4096)
+        assert rt, "llsm_create_rtsynth_buffer returned NULL"
+        lat = L.llsm_rtsynth_buffer_getlatency(rt)
+        p, ap = C.c_float(), C.c_float()
+        assert L.llsm_rtsynth_buffer_fetch_decomposed(rt, C.byref(p), C.byref(ap)) == 0      # empty: no wait
+        ys, counts = [], []
+        for i in range(conf.nfrm):
+            if i == 20:
+                L.llsm_rtsynth_buffer_clear(rt)
+                assert L.llsm_rtsynth_buffer_numoutput(rt) == 0
+            L.llsm_rtsynth_buffer_feed(rt, ck.contents.frames[i])
+            counts.append(L.llsm_rtsynth_buffer_numoutput(rt))
+            if i % 2 == 0:
+                while L.llsm_rtsynth_buffer_fetch_decomposed(rt, C.byref(p), C.byref(ap)):
+                    ys.append((p.value, ap.value))
+            else:
+                y = C.c_float()
+                while L.llsm_rtsynth_buffer_fetch(rt, C.byref(y)):
+                    ys.append((y.value, 0.0))
+        L.llsm_delete_rtsynth_buffer(rt); L.llsm_delete_soptions(so); L.llsm_delete_chunk(ck)
+        outs.append((lat, counts, np.array(ys, np.float32)))
+    assert outs[0][0] == outs[1][0] and outs[0][1] == outs[1][1]
+    a, b = outs[0][2], outs[1][2]
+    assert a.shape == b.shape and S.rms(b) > 1e-3
+    assert S.rms(a - b) < 1e-4, S.rms(a - b)

@@ -11,7 +11,7 @@ echo "smoke exit $?" >> gpurun_out/${TAG}_smoke.log
 timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
 echo "bench exit $?" >> gpurun_out/${TAG}_bench.err
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2> gpurun_out/${TAG}_bench_ref.err
-timeout 600 python tools/bank_sweep.py > gpurun_out/${TAG}_bank_sweep.txt 2>&1
+timeout 300 python tools/rt_bench.py > gpurun_out/${TAG}_rt_bench.txt 2>&1
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv \
   --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline \
   > gpurun_out/${TAG}_ncu_bench.log 2>&1
@@ -20,4 +20,4 @@ if [ "$2" = "full" ]; then
     -o gpurun_out/${TAG}_bank python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline \
     > gpurun_out/${TAG}_ncu_full.log 2>&1
 fi
-tail -5 gpurun_out/${TAG}_pytest_gpu.log; cat gpurun_out/${TAG}_bank_sweep.txt; tail -3 gpurun_out/${TAG}_smoke.log; cat gpurun_out/${TAG}_bench.json; tail -2 gpurun_out/${TAG}_bench.err
+tail -5 gpurun_out/${TAG}_pytest_gpu.log; cat gpurun_out/${TAG}_rt_bench.txt; tail -3 gpurun_out/${TAG}_smoke.log; cat gpurun_out/${TAG}_bench.json; tail -2 gpurun_out/${TAG}_bench.err
