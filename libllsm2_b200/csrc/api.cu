@@ -36,6 +36,10 @@ struct llsm_b200_ctx {
   PbpScratch pbp;
   DevBuf ny_utt;
   DevBuf stage[24];          // device staging for the *_host entry points
+  // copy / compute pipeline of synthesize_l0_host: two slots of input and output staging
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+  DevBuf pin[2][12], pout[2][3];
   LaunchCounter lc;
   std::mutex mtx;
 };
@@ -112,6 +116,15 @@ void llsm_b200_destroy(llsm_b200_ctx* ctx) {
   ctx->pbp.release();
   ctx->ny_utt.release();
   for(auto& s : ctx->stage) s.release();
+  for(int k = 0; k < 2; k ++) {
+    for(auto& b : ctx->pin[k]) b.release();
+    for(auto& b : ctx->pout[k]) b.release();
+    if(ctx->ev_in[k]) cudaEventDestroy(ctx->ev_in[k]);
+    if(ctx->ev_comp[k]) cudaEventDestroy(ctx->ev_comp[k]);
+    if(ctx->ev_out[k]) cudaEventDestroy(ctx->ev_out[k]);
+  }
+  if(ctx->s_in) cudaStreamDestroy(ctx->s_in);
+  if(ctx->s_out) cudaStreamDestroy(ctx->s_out);
   if(ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -144,6 +157,19 @@ static const int* ragged_lengths(llsm_b200_ctx* ctx, const llsm_b200_conf* conf,
   return ctx->ny_utt.as<int>();
 }
 
+// body shared by the device entry and the host pipeline; the caller holds ctx->mtx
+static int synth_l0_impl(llsm_b200_ctx* ctx, const llsm_b200_conf* conf, const llsm_b200_frames* fr,
+  const llsm_b200_soptions* opt, const llsm_b200_output* out, int utt_base) {
+  SynthPlanDev* pd = get_plan(ctx, conf);
+  if(pd == nullptr) return fail(LLSM_B200_ENOMEM, "could not build the synthesis plan");
+  if(out->stride < pd->h.ny) return fail(LLSM_B200_EINVAL, "stride %d < ny %d", out->stride, pd->h.ny);
+  const int* ny_utt = ragged_lengths(ctx, conf, fr->nfrm_utt);
+  if(fr->nfrm_utt && ! ny_utt) return fail(LLSM_B200_ENOMEM, "ny_utt");
+  int rc = run_synth_l0(*pd, ctx->scratch, *conf, *fr, *opt, *out, ny_utt, ctx->stream, &ctx->lc, 0, 0, utt_base);
+  if(rc != 0) return fail(rc, "synthesis launch failed (code %d): size outside supported range?", rc);
+  return cuda_ok("synthesize_l0");
+}
+
 int llsm_b200_synthesize_l0(llsm_b200_ctx* ctx, const llsm_b200_conf* conf,
   const llsm_b200_frames* fr, const llsm_b200_soptions* opt, const llsm_b200_output* out) {
   if(ctx == nullptr) return fail(LLSM_B200_ENODEVICE, "no context (no CUDA device?)");
@@ -154,14 +180,7 @@ int llsm_b200_synthesize_l0(llsm_b200_ctx* ctx, const llsm_b200_conf* conf,
   if(! out->y_sin || ! out->y_noise) return fail(LLSM_B200_EINVAL, "y_sin and y_noise are required");
   std::lock_guard<std::mutex> lk(ctx->mtx);
   cudaSetDevice(ctx->device);
-  SynthPlanDev* pd = get_plan(ctx, conf);
-  if(pd == nullptr) return fail(LLSM_B200_ENOMEM, "could not build the synthesis plan");
-  if(out->stride < pd->h.ny) return fail(LLSM_B200_EINVAL, "stride %d < ny %d", out->stride, pd->h.ny);
-  const int* ny_utt = ragged_lengths(ctx, conf, fr->nfrm_utt);
-  if(fr->nfrm_utt && ! ny_utt) return fail(LLSM_B200_ENOMEM, "ny_utt");
-  rc = run_synth_l0(*pd, ctx->scratch, *conf, *fr, *opt, *out, ny_utt, ctx->stream, &ctx->lc);
-  if(rc != 0) return fail(rc, "synthesis launch failed (code %d): size outside supported range?", rc);
-  return cuda_ok("synthesize_l0");
+  return synth_l0_impl(ctx, conf, fr, opt, out, 0);
 }
 
 int llsm_b200_synthesize_l0_shard(llsm_b200_ctx* ctx, const llsm_b200_conf* conf,
@@ -229,50 +248,94 @@ static int upload_all(llsm_b200_ctx* ctx, std::vector<Up>& ups) {
   return 0;
 }
 
+// Host buffers in, host buffers out. The batch is cut into slices of utterances that flow through a
+// three-stage pipeline -- H2D on a copy stream, the kernels on the context's stream, D2H on a second copy
+// stream -- with two staging slots, so that PCIe traffic in both directions overlaps the kernels (the
+// step is PCIe-bound: ~3 KB in and ~5 KB out per frame). Pinned host memory is needed for real overlap;
+// pageable memory works, serialised by the driver. Results do not depend on the slicing.
+static int pipeline_ready(llsm_b200_ctx* ctx) {
+  if(ctx->s_in) return 0;
+  if(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking) != cudaSuccess ||
+     cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking) != cudaSuccess) return cuda_ok("pipeline streams");
+  for(int k = 0; k < 2; k ++)
+    if(cudaEventCreateWithFlags(&ctx->ev_in[k], cudaEventDisableTiming) != cudaSuccess ||
+       cudaEventCreateWithFlags(&ctx->ev_comp[k], cudaEventDisableTiming) != cudaSuccess ||
+       cudaEventCreateWithFlags(&ctx->ev_out[k], cudaEventDisableTiming) != cudaSuccess) return cuda_ok("pipeline events");
+  return 0;
+}
+
 int llsm_b200_synthesize_l0_host(llsm_b200_ctx* ctx, const llsm_b200_conf* conf,
   const llsm_b200_frames* fr, const llsm_b200_soptions* opt, const llsm_b200_output* out) {
   if(ctx == nullptr) return fail(LLSM_B200_ENODEVICE, "no context (no CUDA device?)");
   int rc = check_conf(conf); if(rc) return rc;
   if(! fr || ! opt || ! out) return fail(LLSM_B200_EINVAL, "NULL argument");
+  if(! fr->f0 || ! fr->nhar || ! fr->ampl || ! fr->phse || ! fr->psd || ! fr->edc || ! fr->enhar ||
+     ! fr->eampl || ! fr->ephse) return fail(LLSM_B200_EINVAL, "a required frame array is NULL");
+  std::lock_guard<std::mutex> lk(ctx->mtx);
   cudaSetDevice(ctx->device);
-  const size_t BF = (size_t)conf->nutt * conf->nfrm;
+  rc = pipeline_ready(ctx); if(rc) return rc;
+  const int B = conf->nutt, F = conf->nfrm;
   const size_t nch = conf->nchannel;
-  const int ny = plan_output_length(conf->nfrm, conf->thop, conf->fs);
+  const int ny = plan_output_length(F, conf->thop, conf->fs);
   if(out->stride < ny) return fail(LLSM_B200_EINVAL, "stride %d < ny %d", out->stride, ny);
   const int nt = plan_template_length(ny);
-  DevBuf* s = ctx->stage;
-  std::vector<Up> ups = {
-    {&s[0], fr->nfrm_utt, (size_t)conf->nutt * 4}, {&s[1], fr->f0, BF * 4}, {&s[2], fr->nhar, BF * 4},
-    {&s[3], fr->ampl, BF * conf->maxnhar * 4}, {&s[4], fr->phse, BF * conf->maxnhar * 4},
-    {&s[5], fr->psd, BF * conf->npsd * 4}, {&s[6], fr->psdres, BF * conf->npsd * 4},
-    {&s[7], fr->edc, BF * nch * 4}, {&s[8], fr->enhar, BF * nch * 4},
-    {&s[9], fr->eampl, BF * nch * conf->maxnhar_e * 4}, {&s[10], fr->ephse, BF * nch * conf->maxnhar_e * 4},
-    {&s[11], opt->white, (size_t)conf->nutt * nch * nt * 4},
-  };
-  rc = upload_all(ctx, ups); if(rc) return rc;
-  const size_t obytes = (size_t)conf->nutt * out->stride * 4;
-  for(int i = 12; i < 15; i ++)
-    if(s[i].reserve(obytes) != 0) return fail(LLSM_B200_ENOMEM, "device output staging");
-  llsm_b200_frames d;
-  d.nfrm_utt = fr->nfrm_utt ? s[0].as<int>() : nullptr;
-  d.f0 = s[1].as<float>(); d.nhar = s[2].as<int>(); d.ampl = s[3].as<float>(); d.phse = s[4].as<float>();
-  d.psd = s[5].as<float>(); d.psdres = fr->psdres ? s[6].as<float>() : nullptr;
-  d.edc = s[7].as<float>(); d.enhar = s[8].as<int>(); d.eampl = s[9].as<float>(); d.ephse = s[10].as<float>();
-  llsm_b200_soptions o = *opt;
-  o.white = opt->white ? s[11].as<float>() : nullptr;
-  llsm_b200_output od;
-  od.y = s[12].as<float>(); od.y_sin = s[13].as<float>(); od.y_noise = s[14].as<float>();
-  od.stride = out->stride;
-  rc = llsm_b200_synthesize_l0(ctx, conf, &d, &o, &od);
-  if(rc) return rc;
-  if(out->y && cudaMemcpyAsync(out->y, od.y, obytes, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
-    return cuda_ok("D2H y");
-  if(out->y_sin && cudaMemcpyAsync(out->y_sin, od.y_sin, obytes, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
-    return cuda_ok("D2H y_sin");
-  if(out->y_noise && cudaMemcpyAsync(out->y_noise, od.y_noise, obytes, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
-    return cuda_ok("D2H y_noise");
-  if(cudaStreamSynchronize(ctx->stream) != cudaSuccess) return cuda_ok("synchronize");
-  return 0;
+  // slice size: at least ~8 MB of output per slice, at most 16 slices
+  int nslice = 1;
+  {
+    const char* e = getenv("LLSM_B200_HOST_SLICES");
+    size_t total = (size_t)B * out->stride * 4;
+    nslice = e ? atoi(e) : (int)(total / (8u << 20));
+    if(nslice > 16) nslice = 16;
+    if(nslice > B) nslice = B;
+    if(nslice < 1) nslice = 1;
+  }
+  const int Bs = (B + nslice - 1) / nslice;
+  // row sizes (bytes per utterance) of the eleven frame arrays and the template
+  const size_t row[12] = {4, (size_t)F * 4, (size_t)F * 4, (size_t)F * conf->maxnhar * 4, (size_t)F * conf->maxnhar * 4,
+    (size_t)F * conf->npsd * 4, (size_t)F * conf->npsd * 4, (size_t)F * nch * 4, (size_t)F * nch * 4,
+    (size_t)F * nch * conf->maxnhar_e * 4, (size_t)F * nch * conf->maxnhar_e * 4, nch * nt * 4};
+  const void* src[12] = {fr->nfrm_utt, fr->f0, fr->nhar, fr->ampl, fr->phse, fr->psd, fr->psdres, fr->edc, fr->enhar,
+    fr->eampl, fr->ephse, opt->white};
+  float* dsth[3] = {out->y, out->y_sin, out->y_noise};
+  const size_t orow = (size_t)out->stride * 4;
+  for(int k = 0; k < 2 && k < nslice; k ++) {
+    for(int a = 0; a < 12; a ++)
+      if(src[a] && ctx->pin[k][a].reserve(row[a] * Bs) != 0) return fail(LLSM_B200_ENOMEM, "device input staging");
+    for(int a = 0; a < 3; a ++)
+      if(ctx->pout[k][a].reserve(orow * Bs) != 0) return fail(LLSM_B200_ENOMEM, "device output staging");
+  }
+  for(int c = 0, b0 = 0; b0 < B; c ++, b0 += Bs) {
+    const int k = c & 1, bc = (B - b0 < Bs) ? B - b0 : Bs;
+    DevBuf* in = ctx->pin[k]; DevBuf* ob = ctx->pout[k];
+    if(c >= 2) cudaStreamWaitEvent(ctx->s_in, ctx->ev_comp[k], 0);          // slot inputs consumed
+    for(int a = 0; a < 12; a ++)
+      if(src[a] && cudaMemcpyAsync(in[a].p, (const char*)src[a] + row[a] * b0, row[a] * bc, cudaMemcpyHostToDevice,
+           ctx->s_in) != cudaSuccess) return cuda_ok("H2D copy");
+    cudaEventRecord(ctx->ev_in[k], ctx->s_in);
+    cudaStreamWaitEvent(ctx->stream, ctx->ev_in[k], 0);
+    if(c >= 2) cudaStreamWaitEvent(ctx->stream, ctx->ev_out[k], 0);         // slot outputs drained
+    llsm_b200_conf cs = *conf; cs.nutt = bc;
+    llsm_b200_frames d;
+    d.nfrm_utt = fr->nfrm_utt ? in[0].as<int>() : nullptr;
+    d.f0 = in[1].as<float>(); d.nhar = in[2].as<int>(); d.ampl = in[3].as<float>(); d.phse = in[4].as<float>();
+    d.psd = in[5].as<float>(); d.psdres = fr->psdres ? in[6].as<float>() : nullptr;
+    d.edc = in[7].as<float>(); d.enhar = in[8].as<int>(); d.eampl = in[9].as<float>(); d.ephse = in[10].as<float>();
+    llsm_b200_soptions o = *opt;
+    o.white = opt->white ? in[11].as<float>() : nullptr;
+    llsm_b200_output od;
+    od.y = ob[0].as<float>(); od.y_sin = ob[1].as<float>(); od.y_noise = ob[2].as<float>(); od.stride = out->stride;
+    rc = synth_l0_impl(ctx, &cs, &d, &o, &od, b0);
+    if(rc) { cudaDeviceSynchronize(); return rc; }
+    cudaEventRecord(ctx->ev_comp[k], ctx->stream);
+    cudaStreamWaitEvent(ctx->s_out, ctx->ev_comp[k], 0);
+    for(int a = 0; a < 3; a ++)
+      if(dsth[a] && cudaMemcpyAsync((char*)dsth[a] + orow * b0, ob[a].p, orow * bc, cudaMemcpyDeviceToHost,
+           ctx->s_out) != cudaSuccess) return cuda_ok("D2H copy");
+    cudaEventRecord(ctx->ev_out[k], ctx->s_out);
+  }
+  if(cudaStreamSynchronize(ctx->s_out) != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess ||
+     cudaStreamSynchronize(ctx->s_in) != cudaSuccess) return cuda_ok("synchronize");
+  return cuda_ok("synthesize_l0_host");
 }
 
 #include "api_analysis.inc"

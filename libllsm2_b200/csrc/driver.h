@@ -124,14 +124,14 @@ static inline int run_harmonics(const SynthPlanDev& pd, const llsm_b200_conf& co
 // out.y_sin must already hold the harmonic component.
 static inline int run_noise_part(const SynthPlanDev& pd, SynthScratch& sc, const llsm_b200_conf& conf,
   const llsm_b200_frames& fr, const llsm_b200_soptions& opt, const llsm_b200_output& out,
-  const int* ny_utt_dev, cudaStream_t st, LaunchCounter* lc, int frame_lo = 0, int frame_hi = 0);
+  const int* ny_utt_dev, cudaStream_t st, LaunchCounter* lc, int frame_lo = 0, int frame_hi = 0, int utt_base = 0);
 
 // Full layer-0 synthesis on device pointers (llsm_synthesize, layer0.c:636-664).
 static inline int run_synth_l0(const SynthPlanDev& pd, SynthScratch& sc, const llsm_b200_conf& conf,
   const llsm_b200_frames& fr, const llsm_b200_soptions& opt, const llsm_b200_output& out,
-  const int* ny_utt_dev, cudaStream_t st, LaunchCounter* lc, int frame_lo = 0, int frame_hi = 0) {
+  const int* ny_utt_dev, cudaStream_t st, LaunchCounter* lc, int frame_lo = 0, int frame_hi = 0, int utt_base = 0) {
   const SynthPlan& h = pd.h;
-  const int B = conf.nutt, nch = conf.nchannel;
+  const int nch = conf.nchannel;
   if(nch < 1 || nch > LLSM_B200_MAXCHANNEL) return LLSM_B200_EINVAL;
   if(out.stride < h.ny) return LLSM_B200_EINVAL;
 
@@ -139,12 +139,12 @@ static inline int run_synth_l0(const SynthPlanDev& pd, SynthScratch& sc, const l
   int rc = run_harmonics(pd, conf, fr, &opt, ny_utt_dev, out.y_sin, h.ny, out.stride, out.stride,
     st, lc, frame_lo, frame_hi);
   if(rc != 0) return rc;
-  return run_noise_part(pd, sc, conf, fr, opt, out, ny_utt_dev, st, lc, frame_lo, frame_hi);
+  return run_noise_part(pd, sc, conf, fr, opt, out, ny_utt_dev, st, lc, frame_lo, frame_hi, utt_base);
 }
 
 static inline int run_noise_part(const SynthPlanDev& pd, SynthScratch& sc, const llsm_b200_conf& conf,
   const llsm_b200_frames& fr, const llsm_b200_soptions& opt, const llsm_b200_output& out,
-  const int* ny_utt_dev, cudaStream_t st, LaunchCounter* lc, int frame_lo, int frame_hi) {
+  const int* ny_utt_dev, cudaStream_t st, LaunchCounter* lc, int frame_lo, int frame_hi, int utt_base) {
   const SynthPlan& h = pd.h;
   const int B = conf.nutt, nch = conf.nchannel;
   const int tstride = (h.nt + 3) & ~3;
@@ -156,6 +156,7 @@ static inline int run_noise_part(const SynthPlanDev& pd, SynthScratch& sc, const
   {
     WhiteParams W; memset(&W, 0, sizeof(W));
     W.nseq = B * nch; W.nt = h.nt; W.ostride = tstride; W.white = opt.white; W.seed = opt.seed; W.out = sc.colored.as<float>();
+    W.seq_base = utt_base * nch;
     LLSM_LAUNCH(white_fill_kernel, dim3((h.nt / 4 + 256) / 256, B * nch), dim3(256), 0, st, W);
     if(lc) lc->n += 1;
     IirParams I; memset(&I, 0, sizeof(I));

@@ -139,7 +139,8 @@ __global__ void __launch_bounds__(IIR_NT) iir_filtfilt_kernel(IirParams P) {
 }
 
 // white-noise fill for the templates: copy the host-drawn template or draw on the device
-struct WhiteParams { int nseq, nt, ostride; const float* white; unsigned long long seed; float* out; };
+struct WhiteParams { int nseq, nt, ostride; const float* white; unsigned long long seed; float* out;
+  int seq_base; /* generator sequence number of row 0 (batches processed in slices draw the same noise) */ };
 
 #ifndef LLSM_PHILOX_DEFINED
 #define LLSM_PHILOX_DEFINED
@@ -172,7 +173,7 @@ __global__ void __launch_bounds__(256) white_fill_kernel(WhiteParams P) {
     return;
   }
   unsigned r[4];
-  philox4x32_10((unsigned)q, (unsigned)seq, 0x6c6c736du, 0u, (unsigned)P.seed, (unsigned)(P.seed >> 32), r);
+  philox4x32_10((unsigned)q, (unsigned)(seq + P.seq_base), 0x6c6c736du, 0u, (unsigned)P.seed, (unsigned)(P.seed >> 32), r);
   float v[4];
   for(int h = 0; h < 2; h ++) {
     float u1 = ((float)r[2 * h] + 1.0f) * (1.0f / 4294967808.0f);

@@ -130,6 +130,25 @@ def test_host_entry_matches_device_entry(ctx):
         assert np.array_equal(a, host[k]), k
 
 
+@pytest.mark.parametrize("slices", ["1", "3", "7"])
+def test_host_pipeline_is_slicing_invariant(ctx, slices, monkeypatch):
+    """The host entry cuts the batch into slices (H2D / kernels / D2H overlapped); outputs must not depend on
+    the slicing, with host templates and with the device generator alike, ragged lengths included."""
+    import torch
+    import libllsm2_b200 as L
+    fr, conf = S.synth_frames(7, 30, seed=18)
+    fr["nfrm_utt"] = np.array([30, 12, 30, 1, 25, 30, 8], np.int32)
+    white = S.ref_white_noise(conf, seed=8, nfrm_utt=None)
+    monkeypatch.setenv("LLSM_B200_HOST_SLICES", slices)
+    for kw in (dict(white=white), dict(seed=99)):
+        dkw = {k: (torch.from_numpy(v).cuda() if k == "white" else v) for k, v in kw.items()}
+        dev = L.synthesize_l0(ctx, conf, _to_dev(fr), **dkw)
+        torch.cuda.synchronize()
+        host = L.synthesize_l0_host(ctx, conf, fr, **kw)
+        for k in ("y", "y_sin", "y_noise"):
+            assert np.array_equal(dev[k].cpu().numpy(), host[k]), (k, kw.keys())
+
+
 def test_batch_properties_full_size(ctx):
     """Size-independent properties at a larger batch: y = y_sin + y_noise exactly; replicated
     utterances give bit-identical rows; spot rows match the oracle."""
