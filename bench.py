@@ -38,6 +38,8 @@ def parse():
     ap.add_argument("--nhar", type=int, default=128)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-analysis", action="store_true")
+    ap.add_argument("--analysis-batch", type=int, default=256, help="utterances of the analysis leg")
     return ap.parse_args()
 
 
@@ -138,6 +140,22 @@ def cpu_baseline_single(distinct, conf, nutt=8):
     return {"value": frames / t, "unit": UNIT, "cores": 1, "kind": "reference",
             "sample": "%d utterances x %d frames of the bench workload, llsm_synthesize of the "
                       "unmodified reference sources + ciglet shim, gcc -Ofast, single thread" % (len(idxs), conf.nfrm)}
+
+
+def cpu_baseline_analysis(x, distinct, conf, nutt=2):
+    """llsm_analyze of the reference sources (gcc -Ofast), one thread, on nutt synthesised utterances."""
+    lib = _ref_lib(True)
+    lib.ref_time_analyze.restype = C.c_double
+    cf = np.array(list(conf.chanfreq), np.float32)
+    tot = 0.0
+    for b in range(min(nutt, x.shape[0])):
+        xb = np.ascontiguousarray(x[b], np.float32); f0 = np.ascontiguousarray(distinct["f0"][b], np.float32)
+        tot += lib.ref_time_analyze(1, xb.ctypes.data_as(C.c_void_p), int(xb.shape[0]), C.c_float(conf.fs),
+                                    f0.ctypes.data_as(C.c_void_p), conf.nfrm, C.c_float(conf.thop), conf.maxnhar,
+                                    conf.maxnhar_e, conf.npsd, conf.nchannel, cf.ctypes.data_as(C.c_void_p), 1)
+    n = min(nutt, x.shape[0])
+    return {"value": n * conf.nfrm / tot, "unit": UNIT, "cores": 1, "kind": "reference",
+            "sample": "%d utterances x %d frames, llsm_analyze (CZT) of the reference sources, gcc -Ofast, single thread" % (n, conf.nfrm)}
 
 
 def usable_cores():
@@ -290,6 +308,30 @@ def run_b200(args):
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": ne,
                "note": "llsm_b200_synthesize_l0_host: pinned host frames in, y/y_sin/y_noise out"}
 
+    # analysis leg (llsm_analyze, CZT harmonics) on the waveforms the synthesis leg just produced
+    ana = None
+    if not args.no_analysis:
+        nb = min(args.analysis_batch, conf.nutt)
+        from libllsm2_b200 import abi
+        ca = abi.make_conf(nb, conf.nfrm, conf.maxnhar, conf.maxnhar_e, conf.npsd, conf.nchannel, conf.fs, conf.thop,
+                           list(conf.chanfreq)[:conf.nchannel - 1], conf.lip_radius)
+        xa = out["y"][:nb].contiguous(); fa = d["f0"][:nb].contiguous()
+        for _ in range(2):
+            L.analyze_l0(ctx, ca, xa, fa)
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        la = ctx.launches
+        na = max(2, min(args.steps, 5))
+        a0.record()
+        for _ in range(na):
+            L.analyze_l0(ctx, ca, xa, fa)
+        a1.record(); torch.cuda.synchronize()
+        ana_ms = a0.elapsed_time(a1) / na
+        ana = {"value": nb * conf.nfrm * world / (ana_ms * 1e-3), "unit": UNIT, "batch_per_gpu": nb, "ms_per_call": ana_ms,
+               "gpu_launches": int((ctx.launches - la) // na),
+               "note": "llsm_b200_analyze_l0 (f0 refine, CZT harmonics, residual, noise PSD + Kalman/RTS, sub-band "
+                       "envelopes) on %d of the synthesised utterances, device-resident" % nb}
+
     t = torch.tensor([ms, bank_ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -317,7 +359,7 @@ def run_b200(args):
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": config_dict(args, conf), "clocks": clocks, "e2e": e2e,
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches), "analysis": ana,
         "roofline": {"bound": "hbm", "kernel": "hm_bank_ola_kernel", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
@@ -325,9 +367,14 @@ def run_b200(args):
                      "algorithmic_bytes_per_launch": BANK_BYTES_PER_FRAME * frames_per_step,
                      "whole_step_gbs": FULL_BYTES_PER_FRAME * frames_per_step / (ms / args.steps * 1e-3) / 1e9},
     }
+    if ana is not None:
+        syn = value
+        ana["analysis_plus_synthesis"] = 1.0 / (1.0 / ana["value"] + 1.0 / syn)
     if not args.no_cpu_baseline and world == 1:
         try:
             res["cpu_baseline"] = cpu_baseline_single(distinct, conf)
+            if ana is not None:
+                ana["cpu_baseline"] = cpu_baseline_analysis(out["y"][:2].cpu().numpy(), distinct, conf)
         except Exception as e:  # the oracle .so travels with the repo; report rather than die
             res["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference",
                                    "sample": "unavailable: %s" % e}

@@ -201,50 +201,42 @@ __device__ __forceinline__ float interp_linspace(const float* y, int n, float xm
   return (float)((double)y[lo] + ((double)y[hi] - (double)y[lo]) * rr);
 }
 
-__global__ void __launch_bounds__(PBP_THREADS) pbp_pulse_kernel(PbpPulseParams P) {
-  LLSM_DYN_SMEM(smem);
-  float2* bufa = (float2*)smem;                      // [max_size]
-  float2* bufb = bufa + P.max_size;                  // [max_size]
-  float* ha = (float*)(bufb + P.max_size);           // [maxnhar + 2]
-  float* vta = ha + P.maxnhar + 2;                   // [maxnhar]     harmonic VT amplitudes
-  float* vtp = vta + P.maxnhar;                      // [maxnhar]     harmonic VT min-phase
-  float* pre = vtp + P.maxnhar;                      // [maxnhar + 1] cos(phase delta)
-  float* pim = pre + P.maxnhar + 1;                  // [maxnhar + 1] sin(phase delta)
-  __shared__ LfSolved solved[PBP_MAXP];              // LF model of every pulse of the frame
-  const int i = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, nth = blockDim.x;
-  const int nf = P.nfrm_utt ? P.nfrm_utt[b] : P.nfrm;
-  if(i >= nf) return;
-  const size_t r = (size_t)b * P.nfrm + i;
-  const int npulse = P.plan.npulse[r];
-  if(npulse <= 0) return;
-  const int ny = P.ny_utt ? P.ny_utt[b] : P.ny;
-  const int S = P.plan.pulse_size[r];
-  if(S > P.max_size) return;
+// One frame's filtered pulse train (llsm_make_filtered_pulse, llsmutils.c:132-201) computed by the whole CTA:
+// returns the buffer whose .x holds the `S` finished samples (inverse FFT scaled, fades applied).
+// smem: bufa/bufb [S] float2, ha [maxnhar + 2], vta/vtp [maxnhar], pre/pim [maxnhar + 1]; solved [PBP_MAXP].
+struct PulseFrame {
+  float f0, rd; const float* vtmagn; int nspec; const float* vsphse; int nhar;
+  float fs, fnyq, lip_radius; const float2* tw; int ntw;
+};
+struct PulseSmem { float2* bufa; float2* bufb; float* ha; float* vta; float* vtp; float* pre; float* pim; LfSolved* solved; };
+
+__device__ float2* pbp_make_pulse(const PulseFrame& F, const PbpPulse* pulses, int npulse, int pre_rotate, int S,
+  const PulseSmem& M) {
+  const int tid = threadIdx.x, nth = blockDim.x;
+  float2* bufa = M.bufa; float2* bufb = M.bufb;
+  float* ha = M.ha; float* vta = M.vta; float* vtp = M.vtp; float* pre = M.pre; float* pim = M.pim;
   int lgS = 0; while((1 << lgS) < S) lgS ++;
   const int halfsize = S / 2 + 1;
-  const float f0 = P.f0[r];
-  const int nhar = P.nvs[r] < P.maxnhar ? P.nvs[r] : P.maxnhar;
-  const float* vtmagn = P.vtmagn + r * (size_t)P.nspec;
-  const float* vsphse = P.vsphse + r * (size_t)P.vs_stride;
-  const int pre_rotate = P.plan.pre_rotate[r];
+  const float f0 = F.f0;
+  const int nhar = F.nhar;
+  const float* vtmagn = F.vtmagn;
+  const float* vsphse = F.vsphse;
 
   // ---- vocal-tract amplitudes at the harmonics and their minimum phase (llsmutils.c:152-160)
-  const LfSolved lf0 = lf_solve(lf_from_rd(P.rd[r], (float)(1.0 / (double)f0), 1.0f));
+  const LfSolved lf0 = lf_solve(lf_from_rd(F.rd, (float)(1.0 / (double)f0), 1.0f));
   for(int k = tid; k < nhar; k += nth) {
     float fh = (float)(k + 1) * f0;                                  // freq_har[i] = i * f0[0]
-    float v = interp_linspace(vtmagn, P.nspec, P.fnyq, fh);
+    float v = interp_linspace(vtmagn, F.nspec, F.fnyq, fh);
     vta[k] = (float)exp((double)v * 2.3025851 / 20.0);
   }
   __syncthreads();
-  block_harmonic_minphase(vta, nhar, vtp, bufa, bufb, ha, P.tw, P.ntw);
+  block_harmonic_minphase(vta, nhar, vtp, bufa, bufb, ha, F.tw, F.ntw);
   // ---- harmonic phase deltas (llsmutils.c:75-96)
   for(int k = tid; k <= nhar; k += nth) {
-    float ph = 0.f;
     if(k >= 1) {
       double m, p; lf_spectrum(lf0, (double)((float)k * f0), &m, &p);
       ha[k] = (float)p;                                              // raw LF phase of harmonic k
     }
-    (void)ph;
   }
   __syncthreads();
   const float vsshift = (float)((double)vsphse[0] - ((double)ha[1] - 0.5 * LLSM_PI));
@@ -261,9 +253,9 @@ __global__ void __launch_bounds__(PBP_THREADS) pbp_pulse_kernel(PbpPulseParams P
   double m0, p0u; lf_spectrum(lf0, (double)f0, &m0, &p0u);
   const float lfmagnf0 = (float)m0;
   if(tid < npulse) {
-    const PbpPulse pu = P.plan.pulses[r * PBP_MAXP + tid];
+    const PbpPulse pu = pulses[tid];
     LfModel mm; mm.T0 = pu.T0; mm.te = pu.te; mm.tp = pu.tp; mm.ta = pu.ta; mm.Ee = pu.Ee;
-    solved[tid] = lf_solve(mm);
+    M.solved[tid] = lf_solve(mm);
   }
   __syncthreads();
 
@@ -272,7 +264,7 @@ __global__ void __launch_bounds__(PBP_THREADS) pbp_pulse_kernel(PbpPulseParams P
   for(int q = tid; q < halfsize; q += nth) {
     float re = 0.f, im = 0.f;
     if(q >= 1) {
-      float fq = (float)q * P.fs; fq = fq / (float)S;                // freq_axis[i] = i * fs / size
+      float fq = (float)q * F.fs; fq = fq / (float)S;                // freq_axis[i] = i * fs / size
       // interp1(freq_har, phse_{re,im}, nhar + 1, freq_axis): knots k * f0, clamped
       float dre, dim;
       if(! (fq > 0.f)) { dre = pre[0]; dim = pim[0]; }
@@ -286,11 +278,11 @@ __global__ void __launch_bounds__(PBP_THREADS) pbp_pulse_kernel(PbpPulseParams P
       }
       const float pdelta = (float)atan2((double)dim, (double)dre);
       for(int p = 0; p < npulse; p ++) {
-        const float poff = P.plan.pulses[r * PBP_MAXP + p].offset;
-        const LfSolved ls = solved[p];
+        const float poff = pulses[p].offset;
+        const LfSolved ls = M.solved[p];
         double mg, pg; lf_spectrum(ls, (double)fq, &mg, &pg);
         float lm = (float)mg, lph = (float)pg;
-        float sc = P.fnyq / fq; sc = sc / lfmagnf0;
+        float sc = F.fnyq / fq; sc = sc / lfmagnf0;
         lm = lm * sc;
         const float phase_shift = -poff - (float)pre_rotate;
         float t = phase_shift * (float)q; t = t * 2.0f;
@@ -301,33 +293,69 @@ __global__ void __launch_bounds__(PBP_THREADS) pbp_pulse_kernel(PbpPulseParams P
       }
     }
     // lip radiation: bin q is filtered at frequency (q + 1) * fs / size (dsputils.c:418-419)
-    float fbase = P.fs / (float)S;
+    float fbase = F.fs / (float)S;
     float omega = (float)((double)fbase * (1.0 + q) * 2.0 * LLSM_PI);
-    float2 ir = lip_response(P.lip_radius, omega);
+    float2 ir = lip_response(F.lip_radius, omega);
     float yr = __fadd_rn(__fmul_rn(re, ir.x), -__fmul_rn(im, ir.y));
     float yi = __fadd_rn(__fmul_rn(re, ir.y), __fmul_rn(im, ir.x));
     // vocal-tract magnitude
-    float fq0 = (float)q * P.fs; fq0 = fq0 / (float)S;
-    float g = (float)exp((double)interp_linspace(vtmagn, P.nspec, P.fnyq, fq0) * 2.3025851 / 20.0);
+    float fq0 = (float)q * F.fs; fq0 = fq0 / (float)S;
+    float g = (float)exp((double)interp_linspace(vtmagn, F.nspec, F.fnyq, fq0) * 2.3025851 / 20.0);
     yr *= g; yi *= g;
     bufa[q] = make_float2(yr, yi);
     if(q > 0 && q < S / 2) bufa[S - q] = make_float2(yr, -yi);
   }
   __syncthreads();
-  float2* T = block_fft<true>(bufa, bufb, lgS, P.tw, P.ntw);
-  // ---- fades (llsmutils.c:189-197) and overlap-add (layer0.c:222-225)
+  float2* T = block_fft<true>(bufa, bufb, lgS, F.tw, F.ntw);
+  // ---- scale and fades (llsmutils.c:186-197)
   const int fadein = pre_rotate < 256 ? pre_rotate : 256;
   const int fadeout = S < 256 ? S : 256;
-  const float lenp = P.plan.len_period[r];
-  const int pbase = P.plan.pulse_base[r];
-  float* y = P.y_pbp + (size_t)b * P.stride;
   const float invS = 1.0f / (float)S;
   for(int k = tid; k < S; k += nth) {
     float v = T[k].x * invS;
     if(k < fadein) v *= (float)k / (float)fadein;
     if(k >= S - fadeout) v *= (float)(S - k) / (float)fadeout;
+    T[k].x = v;
+  }
+  __syncthreads();
+  return T;
+}
+
+__global__ void __launch_bounds__(PBP_THREADS) pbp_pulse_kernel(PbpPulseParams P) {
+  LLSM_DYN_SMEM(smem);
+  __shared__ LfSolved solved[PBP_MAXP];              // LF model of every pulse of the frame
+  PulseSmem M;
+  M.bufa = (float2*)smem;                            // [max_size]
+  M.bufb = M.bufa + P.max_size;                      // [max_size]
+  M.ha = (float*)(M.bufb + P.max_size);              // [maxnhar + 2]
+  M.vta = M.ha + P.maxnhar + 2;                      // [maxnhar]     harmonic VT amplitudes
+  M.vtp = M.vta + P.maxnhar;                         // [maxnhar]     harmonic VT min-phase
+  M.pre = M.vtp + P.maxnhar;                         // [maxnhar + 1] cos(phase delta)
+  M.pim = M.pre + P.maxnhar + 1;                     // [maxnhar + 1] sin(phase delta)
+  M.solved = solved;
+  const int i = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, nth = blockDim.x;
+  const int nf = P.nfrm_utt ? P.nfrm_utt[b] : P.nfrm;
+  if(i >= nf) return;
+  const size_t r = (size_t)b * P.nfrm + i;
+  const int npulse = P.plan.npulse[r];
+  if(npulse <= 0) return;
+  const int ny = P.ny_utt ? P.ny_utt[b] : P.ny;
+  const int S = P.plan.pulse_size[r];
+  if(S > P.max_size) return;
+  PulseFrame F;
+  F.f0 = P.f0[r]; F.rd = P.rd[r]; F.vtmagn = P.vtmagn + r * (size_t)P.nspec; F.nspec = P.nspec;
+  F.vsphse = P.vsphse + r * (size_t)P.vs_stride;
+  F.nhar = P.nvs[r] < P.maxnhar ? P.nvs[r] : P.maxnhar;
+  F.fs = P.fs; F.fnyq = P.fnyq; F.lip_radius = P.lip_radius; F.tw = P.tw; F.ntw = P.ntw;
+  const int pre_rotate = P.plan.pre_rotate[r];
+  float2* T = pbp_make_pulse(F, P.plan.pulses + r * PBP_MAXP, npulse, pre_rotate, S, M);
+  // ---- overlap-add (layer0.c:222-225)
+  const float lenp = P.plan.len_period[r];
+  const int pbase = P.plan.pulse_base[r];
+  float* y = P.y_pbp + (size_t)b * P.stride;
+  for(int k = tid; k < S; k += nth) {
     int idx = (int)__fadd_rn((float)(pbase + k), -lenp);             // int idx = pulse_base + k - len_period
-    if(idx >= 0 && idx < ny) atomicAdd(y + idx, v);
+    if(idx >= 0 && idx < ny) atomicAdd(y + idx, T[k].x);
   }
 }
 

@@ -347,3 +347,32 @@ int ref_rtsynth_soa(int nfrm, float fs, float thop, int maxnhar, int maxnhar_e, 
   llsm_delete_chunk(chunk);
   return n < cap ? n : cap;
 }
+
+/* timing helper for bench.py: nrep x llsm_analyze on one utterance (x, f0 are copied per run because
+   llsm_analyze refines f0 in place). Returns seconds inside llsm_analyze. */
+double ref_time_analyze(int nrep, const float* x, int nx, float fs, const float* f0, int nfrm, float thop,
+  int maxnhar, int maxnhar_e, int npsd, int nchannel, const float* chanfreq, int hm_method) {
+  struct timespec t0, t1;
+  double tot = 0;
+  llsm_aoptions* opt = llsm_create_aoptions();
+  opt -> thop = thop; opt -> maxnhar = maxnhar; opt -> maxnhar_e = maxnhar_e; opt -> npsd = npsd;
+  opt -> nchannel = nchannel;
+  free(opt -> chanfreq);
+  opt -> chanfreq = calloc(nchannel > 1 ? nchannel - 1 : 1, sizeof(FP_TYPE));
+  for(int c = 0; c < nchannel - 1; c ++) opt -> chanfreq[c] = chanfreq[c];
+  opt -> hm_method = hm_method;
+  FP_TYPE* xc = malloc(nx * sizeof(FP_TYPE));
+  FP_TYPE* fc = malloc(nfrm * sizeof(FP_TYPE));
+  for(int r = 0; r < nrep; r ++) {
+    memcpy(xc, x, nx * sizeof(FP_TYPE));
+    memcpy(fc, f0, nfrm * sizeof(FP_TYPE));
+    clock_gettime(CLOCK_MONOTONIC, & t0);
+    llsm_chunk* chunk = llsm_analyze(opt, xc, nx, fs, fc, nfrm, NULL);
+    clock_gettime(CLOCK_MONOTONIC, & t1);
+    tot += (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+    if(chunk != NULL) llsm_delete_chunk(chunk);
+  }
+  free(xc); free(fc);
+  llsm_delete_aoptions(opt);
+  return tot;
+}
