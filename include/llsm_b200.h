@@ -251,6 +251,22 @@ int llsm_b200_rt_feed(llsm_b200_rt* rt, const llsm_b200_frames* frames, int nfee
 int llsm_b200_rt_feed_host(llsm_b200_rt* rt, const llsm_b200_frames* frames, int nfeed,
   float* out_p, float* out_ap, int out_stride, int* nout);
 
+/* Streams synthesised from layer-1 members (soptions.use_l1 = 1, llsmrt.c:305-419): per frame the pulse
+   tracker locked on the first source harmonic, HM <-> pulse-by-pulse onset (two periods early) and
+   termination (trapezoid catch-up), filtered glottal pulses overlap-added in a forward/backward pulse
+   buffer (llsm_dualbuffer, buffer.h:146-209). nspec = LLSM_CONF_NSPEC. host_tracker = 1 keeps the
+   (tiny, sequential) tracker on the host so that llsm_pbpeffect callbacks run there, once per pulse, in time
+   order (feed_l1_host only); 0 runs it inside the feed kernel.
+   frames->ampl == NULL: the harmonic model of each frame is derived from layer 1 (llsm_frame_tolayer0,
+   llsmrt.c:346-347,388-389). pbpsyn: [nutt][nfeed] LLSM_FRAME_PBPSYN flags or NULL. */
+int llsm_b200_rt_create_l1(llsm_b200_ctx* ctx, const llsm_b200_conf* conf, const llsm_b200_soptions* opt,
+  int white_on_host, int nspec, int host_tracker, llsm_b200_rt** out);
+int llsm_b200_rt_feed_l1(llsm_b200_rt* rt, const llsm_b200_frames* frames, const llsm_b200_layer1* layer1,
+  const int* pbpsyn, int nfeed, float* out_p, float* out_ap, int out_stride, int* nout);
+int llsm_b200_rt_feed_l1_host(llsm_b200_rt* rt, const llsm_b200_frames* frames, const llsm_b200_layer1* layer1,
+  const int* pbpsyn, int nfeed, llsm_b200_pulse_hook hook, void* user,
+  float* out_p, float* out_ap, int out_stride, int* nout);
+
 #ifdef __cplusplus
 }
 #endif

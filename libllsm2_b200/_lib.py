@@ -58,6 +58,12 @@ def lib():
     L.llsm_b200_rt_clear.argtypes = [P]
     L.llsm_b200_rt_feed.argtypes = [P, C.POINTER(abi.Frames), C.c_int, P, P, C.c_int, C.POINTER(C.c_int)]
     L.llsm_b200_rt_feed_host.argtypes = L.llsm_b200_rt_feed.argtypes
+    L.llsm_b200_rt_create_l1.argtypes = [P, C.POINTER(abi.Conf), C.POINTER(abi.SOptions), C.c_int, C.c_int, C.c_int,
+                                         C.POINTER(C.c_void_p)]
+    L.llsm_b200_rt_feed_l1.argtypes = [P, C.POINTER(abi.Frames), C.POINTER(abi.Layer1), P, C.c_int, P, P, C.c_int,
+                                       C.POINTER(C.c_int)]
+    L.llsm_b200_rt_feed_l1_host.argtypes = [P, C.POINTER(abi.Frames), C.POINTER(abi.Layer1), P, C.c_int, P, P, P, P,
+                                            C.c_int, C.POINTER(C.c_int)]
     _lib = L
     return L
 

@@ -266,12 +266,19 @@ class RtSynth:
     samples they release, (periodic, aperiodic) as llsm_rtsynth_buffer_fetch_decomposed yields them.
     CUDA tensors in -> CUDA tensors out; numpy / CPU tensors in -> numpy out (copies inside)."""
 
-    def __init__(self, ctx, conf, white=None, seed=0, options=None):
+    def __init__(self, ctx, conf, white=None, seed=0, options=None, nspec=None, host_tracker=False):
+        """nspec (LLSM_CONF_NSPEC) given: a layer-1 stream (soptions.use_l1), fed with layer1= / pbpsyn=;
+        host_tracker keeps the pulse tracker on the host so that a per-pulse hook can run (numpy feeds only)."""
         self.ctx, self.conf = ctx, conf
         so = _soptions(options, white, seed)
         on_host = 0 if (white is None or hasattr(white, "data_ptr") and white.is_cuda) else 1
         h = C.c_void_p()
-        check(lib().llsm_b200_rt_create(ctx._h, C.byref(conf), C.byref(so), on_host, C.byref(h)))
+        self.nspec = nspec
+        if nspec is None:
+            check(lib().llsm_b200_rt_create(ctx._h, C.byref(conf), C.byref(so), on_host, C.byref(h)))
+        else:
+            check(lib().llsm_b200_rt_create_l1(ctx._h, C.byref(conf), C.byref(so), on_host, int(nspec),
+                                               1 if host_tracker else 0, C.byref(h)))
         self._h = h
 
     @staticmethod
@@ -288,19 +295,33 @@ class RtSynth:
     def clear(self):
         check(lib().llsm_b200_rt_clear(self._h))
 
-    def feed(self, frames, nfeed=1):
+    def feed(self, frames, nfeed=1, layer1=None, pbpsyn=None, hook=None):
         n = self.output_length(nfeed)
         f = _frames({k: v for k, v in frames.items() if k != "nfrm_utt"})
         got = C.c_int(0)
         f0 = frames["f0"]
+        l1 = None
+        if self.nspec is not None:
+            l1 = abi.Layer1()
+            l1.rd, l1.vtmagn, l1.vsphse, l1.nvs = (_ptr(layer1["rd"]), _ptr(layer1["vtmagn"]), _ptr(layer1["vsphse"]),
+                                                   _ptr(layer1["nvs"]))
+            l1.nspec = layer1["vtmagn"].shape[-1]
         if hasattr(f0, "is_cuda") and f0.is_cuda:
             import torch
             p = torch.empty((self.conf.nutt, n), dtype=torch.float32, device=f0.device)
             ap = torch.empty_like(p)
-            check(lib().llsm_b200_rt_feed(self._h, C.byref(f), int(nfeed), _ptr(p), _ptr(ap), n, C.byref(got)))
+            if l1 is None:
+                check(lib().llsm_b200_rt_feed(self._h, C.byref(f), int(nfeed), _ptr(p), _ptr(ap), n, C.byref(got)))
+            else:
+                check(lib().llsm_b200_rt_feed_l1(self._h, C.byref(f), C.byref(l1), _ptr(pbpsyn), int(nfeed),
+                                                 _ptr(p), _ptr(ap), n, C.byref(got)))
         else:
             p = np.empty((self.conf.nutt, n), np.float32); ap = np.empty_like(p)
-            check(lib().llsm_b200_rt_feed_host(self._h, C.byref(f), int(nfeed), _ptr(p), _ptr(ap), n, C.byref(got)))
+            if l1 is None:
+                check(lib().llsm_b200_rt_feed_host(self._h, C.byref(f), int(nfeed), _ptr(p), _ptr(ap), n, C.byref(got)))
+            else:
+                check(lib().llsm_b200_rt_feed_l1_host(self._h, C.byref(f), C.byref(l1), _ptr(pbpsyn), int(nfeed),
+                                                      hook, None, _ptr(p), _ptr(ap), n, C.byref(got)))
         assert got.value == n
         return p, ap
 

@@ -16,6 +16,7 @@ static inline void dev_free(void* p) { free(p); }
 static inline int dev_upload(void* d, const void* h, size_t n, cudaStream_t) { memcpy(d, h, n); return 0; }
 static inline int dev_download(void* h, const void* d, size_t n, cudaStream_t) { memcpy(h, d, n); return 0; }
 static inline int dev_sync(cudaStream_t) { return 0; }
+static inline int dev_memset(void* d, int v, size_t n, cudaStream_t) { memset(d, v, n); return 0; }
 static inline const char* dev_last_error() { return nullptr; }
 #else
 static inline int dev_alloc(void** p, size_t n) { return cudaMalloc(p, n ? n : 1) == cudaSuccess ? 0 : -1; }
@@ -27,6 +28,7 @@ static inline int dev_download(void* h, const void* d, size_t n, cudaStream_t s)
   return cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s) == cudaSuccess ? 0 : -1;
 }
 static inline int dev_sync(cudaStream_t s) { return cudaStreamSynchronize(s) == cudaSuccess ? 0 : -1; }
+static inline int dev_memset(void* d, int v, size_t n, cudaStream_t s) { return cudaMemsetAsync(d, v, n, s) == cudaSuccess ? 0 : -1; }
 static inline const char* dev_last_error() {
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? nullptr : cudaGetErrorString(e);

@@ -1,6 +1,7 @@
 // Streaming synthesis driver (llsmrt.c): shared hop clock on the host, per-stream state on the device.
 #pragma once
 #include "driver.h"
+#include "driver_layer1.h"
 #include "kernels_rt.cuh"
 #include <cmath>
 #include <map>
@@ -11,11 +12,11 @@ struct RtBatch {
   // configuration
   int S = 0, nch = 0, npsd = 0, maxnhar = 0, maxnhar_e = 0;
   float fs = 0, thop = 0;
-  int use_iczt = 1, use_l1 = 0; float iczt_a = 0.275f, iczt_b = 2.26f;
+  int use_iczt = 1, use_l1 = 0; float iczt_a = 0.275f, iczt_b = 2.26f, lip_radius = 1.5f;
   int ntemplate = 0, cap = 0, nfft = 0, lg_nfft = 0, nspec = 0;
   unsigned chan_mask = 0;
   // clock (llsmrt.c:40-53)
-  float cycle = 0, pulse = 0;
+  float cycle = 0;
   int curr_nhop = 0, next_nhop = 0, exc_cycle = 0, sin_pos = 0;
   int cur = 0, mod_cur = 0, exc_cur = 0;   // ring positions: sin & noise, modulation, excitation
   int has_prev = 0;
@@ -23,6 +24,11 @@ struct RtBatch {
   DevBuf mod, sinb, noise, exc, tmpl, prev_psd, out_p, out_ap, colored, iir_coef, iir_mpow;
   int* psd_lo = nullptr; float* psd_r = nullptr; float2* tw = nullptr;
   std::map<int, RtWindow> wins;
+  // layer-1 (pulse-by-pulse) streaming
+  int nspec_l1 = 0, max_pulse = 4096, host_tracker = 0, prev_nhop = 0;
+  DevBuf pulse_f, pulse_b, pstate, plans, hm_nhar, hm_ampl, hm_phse;
+  std::vector<RtPbpState> hstate;          // tracker state when the effect callbacks keep it on the host
+  std::vector<RtPbpPlan> hplans;
   std::vector<void*> owned;
   DevBuf stage[12];
 
@@ -35,7 +41,8 @@ struct RtBatch {
     *dst = (T*)d; return 0;
   }
   void release() {
-    DevBuf* all[] = {&mod, &sinb, &noise, &exc, &tmpl, &prev_psd, &out_p, &out_ap, &colored, &iir_coef, &iir_mpow};
+    DevBuf* all[] = {&mod, &sinb, &noise, &exc, &tmpl, &prev_psd, &out_p, &out_ap, &colored, &iir_coef, &iir_mpow,
+      &pulse_f, &pulse_b, &pstate, &plans, &hm_nhar, &hm_ampl, &hm_phse};
     for(DevBuf* b : all) b->release();
     for(auto& s : stage) s.release();
     for(void* p : owned) dev_free(p);
@@ -61,7 +68,7 @@ struct RtBatch {
     float cf = cycle * fs;
     curr_nhop = (int)floor((double)cf);
     cycle = cycle - (float)prev_nhop / fs;
-    pulse = pulse - (float)prev_nhop;
+    this->prev_nhop = prev_nhop;             // the per-stream pulse / pbp_offset updates run in the feed kernel
     float nf = (cycle + thop) * fs;
     next_nhop = (int)floor((double)nf);
     if(prev_out) *prev_out = prev_nhop;
@@ -107,7 +114,7 @@ static inline int rt_create(RtBatch& R, const llsm_b200_conf& conf, const llsm_b
      R.tmpl.reserve((size_t)S * nch * R.ntemplate * 4) || R.prev_psd.reserve((size_t)S * R.npsd * 4))
     return LLSM_B200_ENOMEM;
   // ---- clock: curr_nhop = 1; update_cycle; cycle = 0; sin_pos (llsmrt.c:213-217)
-  R.cycle = 0; R.pulse = 0; R.exc_cycle = 0; R.has_prev = 0;
+  R.cycle = 0; R.exc_cycle = 0; R.has_prev = 0;
   R.curr_nhop = 1;
   R.update_cycle(nullptr);
   R.cycle = 0;
@@ -157,12 +164,27 @@ static inline int rt_create(RtBatch& R, const llsm_b200_conf& conf, const llsm_b
   R.exc_cur = (5 * chunk) % R.cap;
   R.exc_cycle = (5 * chunk) % R.ntemplate;
   if(lc) lc->n += 4;
+  if(use_l1) {
+    R.lip_radius = conf.lip_radius;
+    if(R.pulse_f.reserve(ring) || R.pulse_b.reserve(ring) || R.pstate.reserve((size_t)S * sizeof(RtPbpState)) ||
+       R.plans.reserve((size_t)S * sizeof(RtPbpPlan))) return LLSM_B200_ENOMEM;
+    if(dev_memset(R.pulse_f.p, 0, ring, st) || dev_memset(R.pulse_b.p, 0, ring, st)) return LLSM_B200_ECUDA;
+    RtPbpState s0; s0.pulse = -1.0f; s0.state = 0; s0.offset = 0;      // pulse after the ctor's update_cycle
+    R.hstate.assign(S, s0); R.hplans.resize(S);
+    if(dev_upload(R.pstate.p, R.hstate.data(), (size_t)S * sizeof(RtPbpState), st) || dev_sync(st)) return LLSM_B200_ECUDA;
+  }
   return 0;
 }
 
 // one feed step on device frame arrays (row length 1 per stream); outputs next_nhop samples per stream
+struct RtL1Feed {                         // layer-1 inputs of a feed step (all device pointers)
+  const llsm_b200_layer1* l1 = nullptr; const int* pbpsyn = nullptr; const L1PlanDev* lp = nullptr;
+  const RtPbpPlan* plans = nullptr;       // host-made plans of this step, [S]
+};
+
 static inline int rt_feed(RtBatch& R, const llsm_b200_frames& fr, int row_stride, int row_off,
-  float* out_p, float* out_ap, int out_stride, int out_off, cudaStream_t st, LaunchCounter* lc) {
+  float* out_p, float* out_ap, int out_stride, int out_off, cudaStream_t st, LaunchCounter* lc,
+  const RtL1Feed* L = nullptr) {
   int prev = 0;
   R.update_cycle(&prev);
   const int H = R.curr_nhop;
@@ -186,11 +208,32 @@ static inline int rt_feed(RtBatch& R, const llsm_b200_frames& fr, int row_stride
   P.use_iczt = R.use_iczt; P.iczt_a = R.iczt_a; P.iczt_b = R.iczt_b;
   P.out_p = out_p; P.out_ap = out_ap; P.out_stride = out_stride; P.out_off = out_off;
   size_t smem = (size_t)R.nfft * 16 + ((size_t)R.nspec + R.npsd + 2 * H + 2 + 32 + 2 * R.maxnhar + 2 * R.nch * R.maxnhar_e) * 4 + 16;
+  RtL1Params Q; memset(&Q, 0, sizeof(Q));
+  if(R.use_l1) {
+    if(L == nullptr || L->l1 == nullptr || L->lp == nullptr) return LLSM_B200_EINVAL;
+    Q.rd = L->l1->rd; Q.vtmagn = L->l1->vtmagn; Q.nspec = L->l1->nspec; Q.vsphse = L->l1->vsphse; Q.nvs = L->l1->nvs;
+    Q.vs_stride = R.maxnhar; Q.pbpsyn = L->pbpsyn;
+    Q.pulse_f = R.pulse_f.as<float>(); Q.pulse_b = R.pulse_b.as<float>();
+    Q.state = R.pstate.as<RtPbpState>(); Q.plans = L->plans; Q.prev_nhop = R.prev_nhop;
+    Q.fnyq = (float)((double)R.fs / 2.0); Q.lip_radius = R.lip_radius;
+    Q.max_size = R.max_pulse; Q.maxnhar_vs = R.maxnhar; Q.tw_p = L->lp->tw; Q.ntw_p = L->lp->ntw;
+    size_t ps = (size_t)R.max_pulse * 16 + ((size_t)R.maxnhar * 5 + 8) * 4 + 16;
+    if(ps > smem) smem = ps;
+  }
   if(smem > 200 * 1024) return LLSM_B200_ERANGE;
+  if(R.use_l1) {
+    auto kfn = rt_feed_kernel<true>;
 #ifndef LLSM_EMU
-  cudaFuncSetAttribute(rt_feed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 #endif
-  LLSM_LAUNCH(rt_feed_kernel, dim3(R.S), dim3(RT_THREADS), smem, st, P);
+    LLSM_LAUNCH(kfn, dim3(R.S), dim3(RT_THREADS), smem, st, P, Q);
+  } else {
+    auto kfn = rt_feed_kernel<false>;
+#ifndef LLSM_EMU
+    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#endif
+    LLSM_LAUNCH(kfn, dim3(R.S), dim3(RT_THREADS), smem, st, P, Q);
+  }
   if(lc) lc->n ++;
   R.cur = P.cur_new; R.mod_cur = P.mod_new; R.exc_cur = P.exc_new;
   R.exc_cycle = (R.exc_cycle + H) % R.ntemplate;
@@ -200,7 +243,7 @@ static inline int rt_feed(RtBatch& R, const llsm_b200_frames& fr, int row_stride
 
 // samples the next `nfeed` feeds will produce in total, without advancing the clock
 static inline int rt_peek_output(const RtBatch& R, int nfeed) {
-  RtBatch c; c.cycle = R.cycle; c.pulse = R.pulse; c.curr_nhop = R.curr_nhop; c.thop = R.thop; c.fs = R.fs;
+  RtBatch c; c.cycle = R.cycle; c.curr_nhop = R.curr_nhop; c.thop = R.thop; c.fs = R.fs;
   int total = 0;
   for(int i = 0; i < nfeed; i ++) { c.update_cycle(nullptr); total += c.next_nhop; }
   return total;
@@ -218,7 +261,63 @@ static inline int rt_clear(RtBatch& R, cudaStream_t st, LaunchCounter* lc) {
   R.mod_cur = (R.mod_cur + R.curr_nhop) % R.cap;
   R.cur = R.curr_nhop % R.cap;
   R.exc_cur = 0;
-  R.cycle = 0; R.pulse = 0; R.exc_cycle = 0;
+  R.cycle = 0; R.exc_cycle = 0;
   R.sin_pos = -R.curr_nhop * 2 - R.nfft / 2;
+  if(R.use_l1) {
+    const size_t ring = (size_t)R.S * R.cap * 4;
+    RtPbpState s0; s0.pulse = 0.f; s0.state = 0; s0.offset = 0;
+    R.hstate.assign(R.S, s0);
+    if(dev_memset(R.pulse_f.p, 0, ring, st) || dev_memset(R.pulse_b.p, 0, ring, st) ||
+       dev_upload(R.pstate.p, R.hstate.data(), (size_t)R.S * sizeof(RtPbpState), st) || dev_sync(st)) return LLSM_B200_ECUDA;
+  }
+  return 0;
+}
+
+// ---- block feed with layer-1 members ------------------------------------------------------------------
+// Host view of the few scalars the pulse tracker needs, for streams whose frames carry effect callbacks.
+struct RtHostTrack {
+  const float* f0 = nullptr; const int* nvs = nullptr; const float* rd = nullptr;
+  const float* vsphse = nullptr; int vs_stride = 0; const int* pbpsyn = nullptr;   // host arrays [S][nfeed]
+};
+
+// Feed nfeed frames per stream ([S][nfeed][..] device arrays). fr.ampl == NULL: the harmonic model of
+// every frame is derived from its layer-1 members first (llsm_frame_tolayer0, llsmrt.c:346-347,388-389).
+// ht != NULL: tracker on the host with `mod` called once per pulse in time order, plans uploaded per step.
+template <class Mod>
+static inline int rt_feed_block_l1(RtBatch& R, llsm_b200_frames fr, int nfeed, const llsm_b200_layer1& l1,
+  const int* pbpsyn, const L1PlanDev& lp, const RtHostTrack* ht, Mod* mods,
+  float* out_p, float* out_ap, int out_stride, int* nout, cudaStream_t st, LaunchCounter* lc) {
+  const int S = R.S;
+  if(fr.ampl == nullptr) {
+    const size_t rows = (size_t)S * nfeed;
+    if(R.hm_nhar.reserve(rows * 4) || R.hm_ampl.reserve(rows * R.maxnhar * 4) || R.hm_phse.reserve(rows * R.maxnhar * 4))
+      return LLSM_B200_ENOMEM;
+    llsm_b200_conf c; memset(&c, 0, sizeof(c));
+    c.nutt = S; c.nfrm = nfeed; c.maxnhar = R.maxnhar; c.fs = R.fs; c.thop = R.thop; c.lip_radius = R.lip_radius;
+    int rc = run_tolayer0(lp, c, nullptr, fr.f0, l1, R.hm_nhar.as<int>(), R.hm_ampl.as<float>(), R.hm_phse.as<float>(), st, lc);
+    if(rc) return rc;
+    fr.nhar = R.hm_nhar.as<int>(); fr.ampl = R.hm_ampl.as<float>(); fr.phse = R.hm_phse.as<float>();
+  }
+  RtL1Feed L; L.l1 = &l1; L.pbpsyn = pbpsyn; L.lp = &lp;
+  int off = 0;
+  for(int i = 0; i < nfeed; i ++) {
+    if(ht != nullptr) {
+      // peek this step's clock, run the trackers, ship the plans
+      RtBatch c; c.cycle = R.cycle; c.curr_nhop = R.curr_nhop; c.thop = R.thop; c.fs = R.fs;
+      int prev = 0; c.update_cycle(&prev);
+      for(int s = 0; s < S; s ++) {
+        const size_t r = (size_t)s * nfeed + i;
+        rt_pbp_track(R.hstate[s], R.hplans[s], prev, c.curr_nhop, R.sin_pos, R.fs, l1.nspec, ht->f0[r], ht->nvs[r] > 0,
+          ht->rd[r], ht->vsphse[r * ht->vs_stride], ht->pbpsyn ? (ht->pbpsyn[r] == 1) : 0, mods[s], i);
+      }
+      if(dev_sync(st) || dev_upload(R.plans.p, R.hplans.data(), (size_t)S * sizeof(RtPbpPlan), st)) return LLSM_B200_ECUDA;
+      L.plans = R.plans.as<RtPbpPlan>();
+    }
+    int rc = rt_feed(R, fr, nfeed, i, out_p, out_ap, out_stride, off, st, lc, &L);
+    if(rc) return rc;
+    off += R.next_nhop;
+  }
+  if(ht != nullptr && dev_sync(st)) return LLSM_B200_ECUDA;      // hplans is reused by the next call
+  if(nout) *nout = off;
   return 0;
 }

@@ -14,6 +14,116 @@
 #pragma once
 #include "common.cuh"
 #include "kernels_synth.cuh"
+#include "kernels_pbp.cuh"
+
+// ---- pulse-by-pulse streaming (use_l1): per-stream tracker state and the plan of one feed step --------
+struct RtPbpState { float pulse; int state; int offset; };      // llsmrt.c:44,52-53: pulse, pbp_state, pbp_offset
+struct RtPbpPlan {
+  int do_sin;                 // feed the harmonic-model frame to the sinusoid ring
+  int npulse, pulse_base, pre_rotate, pulse_size;
+  int read_main, main_offset; // windowed copy pulse buffer -> sinusoid ring (llsmrt.c:395-403)
+  int termination, term_offset;   // trapezoid catch-up copy (llsmrt.c:404-419)
+  int overflow;               // more pulses than the plan holds
+  PbpPulse pulses[PBP_MAXP];
+};
+
+#if defined(__CUDA_ARCH__)
+#define RT_FMUL(a, b) __fmul_rn((a), (b))
+#define RT_FADD(a, b) __fadd_rn((a), (b))
+#else
+#define RT_FMUL(a, b) ((a) * (b))
+#define RT_FADD(a, b) ((a) + (b))
+#endif
+
+// The L1 part of llsm_update_cycle (llsmrt.c:114-116) and of llsm_rtsynth_buffer_feed_deterministic
+// (llsmrt.c:305-392) that is sequential per stream: pulse tracker locked on the first source harmonic,
+// HM <-> PbP onset / termination, the pulse list. `mod` is the per-pulse llsm_pbpeffect hook (identity on
+// the device; the drop-in runs this on the host when a frame carries an effect).
+template <class Mod>
+LF_HD void rt_pbp_track(RtPbpState& st, RtPbpPlan& pl, int prev_nhop, int nhop, int sin_pos, float fs, int nspec,
+  float f0, int has_l1, float rd, float vsphse0, int pbp_on, Mod& mod, int frame) {
+  st.pulse = st.pulse - (float)prev_nhop;
+  if(st.state && st.offset > sin_pos + nhop) st.offset -= prev_nhop;
+  pl.do_sin = 0; pl.npulse = 0; pl.pulse_base = 0; pl.pre_rotate = 0; pl.pulse_size = 0;
+  pl.read_main = 0; pl.main_offset = 0; pl.termination = 0; pl.term_offset = 0; pl.overflow = 0;
+  if(! has_l1 || f0 == 0) return;                                  // llsmrt.c:312
+  float len_period = fs / f0;
+  const float t_period = (float)(1.0 / (double)f0);
+  const LfModel sm = lf_from_rd(rd, t_period, 1.0f);
+  float source_p0; {
+    LfSolved ss = lf_solve(sm);
+    double m, ph; lf_spectrum(ss, (double)f0, &m, &ph);
+    source_p0 = (float)ph;
+    source_p0 = (float)((double)source_p0 - 0.5 * LLSM_PI);
+  }
+  float p0; {
+    double pv = (double)vsphse0;
+    double q = pv - 2.0 * LLSM_PI * floor((pv + LLSM_PI) / (2.0 * LLSM_PI));
+    if(q <= -LLSM_PI) q += 2.0 * LLSM_PI;
+    p0 = (float)q;
+  }
+  float p0_dist; {
+    double pv = (double)(p0 - source_p0);
+    double q = pv - 2.0 * LLSM_PI * floor((pv + LLSM_PI) / (2.0 * LLSM_PI));
+    if(q <= -LLSM_PI) q += 2.0 * LLSM_PI;
+    p0_dist = (float)q;
+  }
+  if(p0_dist < 0) p0_dist = (float)((double)p0_dist + 2.0 * LLSM_PI);
+  const float pulse_projected = (float)((double)(p0_dist / 2.0f) / LLSM_PI * (double)len_period);
+  const int len_reset = (int)RT_FMUL((len_period > (float)nhop ? len_period : (float)nhop), 2.0f);
+  if(pulse_projected - st.pulse > (float)len_reset) st.pulse = pulse_projected - (float)len_reset;
+  int num_periods = (int)round((double)((pulse_projected - st.pulse) / len_period));
+  if(num_periods > 0) len_period = (pulse_projected - st.pulse) / (float)num_periods;
+  float mxs = RT_FMUL(len_period, 2.0f); if(! (mxs > (float)nspec)) mxs = (float)nspec;
+  const int pulse_size = pow2_ceil(log2((double)mxs));
+  int onset = 0, termination = 0;
+  if(pbp_on && ! st.state) {                                       // llsmrt.c:343-350
+    onset = 1; st.state = 1; st.offset = -nhop;
+    pl.do_sin = 1;
+  }
+  if(! pbp_on && st.state) {                                       // llsmrt.c:351-355
+    termination = 1; st.state = 0;
+    num_periods = (int)((double)num_periods + ceil((double)((float)(-st.offset) / len_period)));
+  }
+  if(st.state || termination) {                                    // llsmrt.c:358-386
+    const int period_begin = onset ? -2 : 0;
+    const int num_pulses = num_periods - period_begin;
+    const float nh2 = (float)(nhop * 2);
+    const int pre_rotate = (int)(len_period < nh2 ? len_period : nh2);
+    if(num_pulses > 0) {
+      const int np = num_pulses < PBP_MAXP ? num_pulses : PBP_MAXP;
+      for(int i = 0; i < num_pulses; i ++) {
+        LfModel m = sm; float delta_t = 0.f;
+        mod(m, delta_t, frame);
+        if(i >= np) continue;
+        float off = RT_FADD(st.pulse, RT_FMUL((float)(i + period_begin), len_period));
+        off = RT_FADD(off, RT_FMUL(delta_t, fs));
+        pl.pulses[i].T0 = m.T0; pl.pulses[i].te = m.te; pl.pulses[i].tp = m.tp; pl.pulses[i].ta = m.ta;
+        pl.pulses[i].Ee = m.Ee; pl.pulses[i].offset = off;
+      }
+      const int pulse_base = (int)pl.pulses[0].offset;
+      for(int i = 0; i < np; i ++) pl.pulses[i].offset = pl.pulses[i].offset - (float)pulse_base;
+      pl.npulse = np; pl.overflow = num_pulses > PBP_MAXP;
+      pl.pulse_base = pulse_base; pl.pre_rotate = pre_rotate; pl.pulse_size = pulse_size;
+    }
+  }
+  if(! st.state) pl.do_sin = 1;                                    // llsmrt.c:387-391
+  st.pulse = pulse_projected;
+  if(st.state && st.offset <= sin_pos + nhop) { pl.read_main = 1; pl.main_offset = st.offset; }
+  if(termination) { pl.termination = 1; pl.term_offset = st.offset; }
+}
+
+struct RtL1Params {
+  const float* rd; const float* vtmagn; int nspec; const float* vsphse; const int* nvs; int vs_stride;
+  const int* pbpsyn;                      // [S][nfeed] or NULL
+  float* pulse_f; float* pulse_b;         // llsm_dualbuffer (buffer.h:146-209): forward / backward halves [S][cap]
+  RtPbpState* state;                      // [S]   device tracker state
+  const RtPbpPlan* plans;                 // [S]   plans made on the host (effect callbacks), or NULL
+  int prev_nhop;
+  float fnyq, lip_radius;
+  int max_size, maxnhar_vs;               // pulse FFT size limit, harmonic rows of the pulse scratch
+  const float2* tw_p; int ntw_p;
+};
 
 struct RtFeedParams {
   int S, nchannel, maxnhar, maxnhar_e, npsd, cap, ntemplate;
@@ -40,7 +150,6 @@ struct RtFeedParams {
   const int* psd_lo; const float* psd_r;   // interp1 plan of llsm_spectrum_from_envelope on nspec - 1 bins
   const float2* tw;         // [nfft]
   int use_iczt; float iczt_a, iczt_b;
-  int skip_sin;             // 1: the L1 path owns the sinusoid ring this step (PbP engaged)
   float* out_p; float* out_ap; int out_stride, out_off;   // [S][out_stride], next_nhop samples at out_off
 };
 
@@ -48,7 +157,8 @@ struct RtFeedParams {
 
 __device__ __forceinline__ int rt_wrap(int i, int cap) { i %= cap; return i < 0 ? i + cap : i; }
 
-__global__ void __launch_bounds__(RT_THREADS) rt_feed_kernel(RtFeedParams P) {
+template <bool L1>
+__global__ void __launch_bounds__(RT_THREADS) rt_feed_kernel(RtFeedParams P, RtL1Params Q) {
   LLSM_DYN_SMEM(smem);
   const int nfft = P.nfft, nspec = P.nspec, npsd = P.npsd, cap = P.cap, H = P.H, nwin = 2 * P.H;
   float2* bufa = (float2*)smem;
@@ -73,6 +183,10 @@ __global__ void __launch_bounds__(RT_THREADS) rt_feed_kernel(RtFeedParams P) {
     sinr[rt_wrap(P.cur_old + i, cap)] = 0.f;
     noiser[rt_wrap(P.cur_old + i, cap)] = 0.f;
     for(int c = 0; c < nch; c ++) modr[(size_t)c * cap + rt_wrap(P.mod_old + i, cap)] = 0.f;
+    if(L1) {                                           // llsm_dualbuffer_forward (buffer.h:186-192)
+      const size_t at = (size_t)s * cap + rt_wrap(P.cur_old + i, cap);
+      Q.pulse_b[at] = Q.pulse_f[at]; Q.pulse_f[at] = 0.f;
+    }
   }
   __syncthreads();
 
@@ -117,10 +231,68 @@ __global__ void __launch_bounds__(RT_THREADS) rt_feed_kernel(RtFeedParams P) {
       modr[(size_t)c * cap + rt_wrap(P.mod_new - nwin + j, cap)] += v;
     }
   }
+  // ---- layer-1 path: tracker step, filtered pulses into the dual buffer (llsmrt.c:305-386)
+  __shared__ RtPbpPlan plan;
+  __shared__ LfSolved solved[PBP_MAXP];
+  bool do_sin = true;
+  if(L1) {
+    if(tid == 0) {
+      if(Q.plans) plan = Q.plans[s];
+      else {
+        RtPbpState st = Q.state[s];
+        PbpNoEffect none;
+        const int has = Q.nvs[fr] > 0;
+        rt_pbp_track(st, plan, Q.prev_nhop, H, P.sin_pos, P.fs, Q.nspec, f0, has, Q.rd[fr], Q.vsphse[fr * Q.vs_stride],
+          Q.pbpsyn ? (Q.pbpsyn[fr] == 1) : 0, none, 0);
+        Q.state[s] = st;
+      }
+    }
+    __syncthreads();
+    do_sin = plan.do_sin != 0;
+    if(plan.npulse > 0 && plan.pulse_size <= Q.max_size) {
+      PulseSmem M;
+      M.bufa = (float2*)smem; M.bufb = M.bufa + Q.max_size;
+      M.ha = (float*)(M.bufb + Q.max_size); M.vta = M.ha + Q.maxnhar_vs + 2; M.vtp = M.vta + Q.maxnhar_vs;
+      M.pre = M.vtp + Q.maxnhar_vs; M.pim = M.pre + Q.maxnhar_vs + 1; M.solved = solved;
+      PulseFrame F;
+      F.f0 = f0; F.rd = Q.rd[fr]; F.vtmagn = Q.vtmagn + fr * (size_t)Q.nspec; F.nspec = Q.nspec;
+      F.vsphse = Q.vsphse + fr * (size_t)Q.vs_stride;
+      F.nhar = Q.nvs[fr] < Q.maxnhar_vs ? Q.nvs[fr] : Q.maxnhar_vs;
+      F.fs = P.fs; F.fnyq = Q.fnyq; F.lip_radius = Q.lip_radius; F.tw = Q.tw_p; F.ntw = Q.ntw_p;
+      float2* T = pbp_make_pulse(F, plan.pulses, plan.npulse, plan.pre_rotate, plan.pulse_size, M);
+      // llsm_dualbuffer_addchunk(buffer_pulse, pulse_base - pre_rotate - nhop, pulse_size, y) (llsmrt.c:379-380)
+      const int off = plan.pulse_base - plan.pre_rotate - H;
+      for(int k = tid; k < plan.pulse_size; k += nth) {
+        const int o = off + k;
+        const size_t at = (size_t)s * cap + rt_wrap(P.cur_new + o, cap);
+        if(o < 0) Q.pulse_b[at] += T[k].x; else Q.pulse_f[at] += T[k].x;
+      }
+      __syncthreads();
+      // the pulse scratch overlaps the harmonic coefficient tables: rebuild them
+      for(int e = tid; e < nch * P.maxnhar_e; e += nth) {
+        size_t ec = fr * nch + e / P.maxnhar_e;
+        float a = P.eampl[ec * P.maxnhar_e + e % P.maxnhar_e], ph = P.ephse[ec * P.maxnhar_e + e % P.maxnhar_e];
+        float sp, cp; sincosf(ph, &sp, &cp);
+        ea[e] = a * cp; eb[e] = a * sp;
+      }
+      {
+        float t = P.cycle * 2.0f;
+        const float phase_shift = (float)((double)t * LLSM_PI * (double)f0);
+        int nhs = P.nhar[fr]; if(nhs > P.maxnhar) nhs = P.maxnhar;
+        for(int k = tid; k < nhs; k += nth) {
+          float a = P.ampl[fr * P.maxnhar + k];
+          float ph = (float)((double)P.phse[fr * P.maxnhar + k] - (double)phase_shift * ((double)k + 1.0));
+          float sp, cp; sincosf(ph, &sp, &cp);
+          ca[k] = a * cp; cb[k] = a * sp;
+        }
+      }
+      __syncthreads();
+    }
+  }
   // ---- sinusoids (llsmrt.c:273-291): addchunk(sin, -nwin, nwin)
   int nh = P.nhar[fr];
   if(nh > nfft) nh = nfft;
-  if(! P.skip_sin && f0 > 0 && nh > 0) {
+  if(do_sin && f0 > 0 && nh > 0) {
     bool iczt = false;
     if(P.use_iczt) iczt = log((double)nwin) * (double)P.iczt_a < log((double)nh) - (double)P.iczt_b;
     if(iczt && nh > nwin - 1) nh = nwin - 1;
@@ -140,6 +312,29 @@ __global__ void __launch_bounds__(RT_THREADS) rt_feed_kernel(RtFeedParams P) {
     }
   }
   __syncthreads();
+  if(L1) {
+    if(plan.read_main) {                               // llsmrt.c:395-403
+      for(int i = tid; i < nwin; i += nth) {
+        const int o = plan.main_offset + i;
+        const size_t at = (size_t)s * cap + rt_wrap(P.cur_new + o, cap);
+        float v = (o < 0 ? Q.pulse_b[at] : Q.pulse_f[at]) * P.win[i];
+        sinr[rt_wrap(P.cur_new + o, cap)] += v;
+      }
+      __syncthreads();
+    }
+    if(plan.termination) {                             // llsmrt.c:404-419
+      const int size = -H - plan.term_offset;
+      for(int i = tid; i < size; i += nth) {
+        const int o = plan.term_offset + i;
+        const size_t at = (size_t)s * cap + rt_wrap(P.cur_new + o, cap);
+        float v = o < 0 ? Q.pulse_b[at] : Q.pulse_f[at];
+        if(i < H) v *= P.win[i];
+        if(i >= size - H) v *= P.win[i - (size - H) + H];
+        sinr[rt_wrap(P.cur_new + o, cap)] += v;
+      }
+      __syncthreads();
+    }
+  }
 
   // ---- llsm_run_excitation_buffers(dst, H) (llsmrt.c:134-147): mod chunk at lag -H - H, templates,
   //      appendchunk(exc_mix, H)

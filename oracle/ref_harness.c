@@ -317,16 +317,18 @@ int ref_rtsynth_soa(int nfrm, float fs, float thop, int maxnhar, int maxnhar_e, 
   const float* f0, const int* nhar, const float* ampl, const float* phse,
   const float* psd, const float* psdres, const float* edc, const int* enhar,
   const float* eampl, const float* ephse, unsigned seed,
-  float* y_p, float* y_ap, int cap, int* latency, int clear_at) {
+  float* y_p, float* y_ap, int cap, int* latency, int clear_at, const int* pbpsyn, int remove_hm) {
   llsm_chunk* chunk = chunk_from_soa(nfrm, fs, thop, maxnhar, maxnhar_e, npsd, nchannel,
     chanfreq, lip_radius, f0, nhar, ampl, phse, psd, psdres, edc, enhar, eampl, ephse);
   llsm_soptions* sopt = llsm_create_soptions(fs);
   sopt -> use_iczt = use_iczt;
   if(use_l1) {
     llsm_chunk_tolayer1(chunk, 2048);
-    llsm_chunk_phasepropagate(chunk, -1);
-    for(int i = 0; i < nfrm; i ++)
-      llsm_container_attach(chunk -> frames[i], LLSM_FRAME_HM, NULL, NULL, NULL);
+    for(int i = 0; i < nfrm; i ++) {
+      if(remove_hm) llsm_container_attach(chunk -> frames[i], LLSM_FRAME_HM, NULL, NULL, NULL);
+      if(pbpsyn != NULL && pbpsyn[i])
+        llsm_container_attach(chunk -> frames[i], LLSM_FRAME_PBPSYN, llsm_create_int(1), llsm_delete_int, llsm_copy_int);
+    }
     sopt -> use_l1 = 1;
   }
   srand(seed);

@@ -114,3 +114,57 @@ extern "C" int emu_rtsynth(const llsm_b200_conf* conf, const llsm_b200_frames* f
   R.release();
   return 0;
 }
+
+// layer-1 streaming: frames + L1 members ([S][F][..] host arrays = "device" arrays of the emulator)
+extern "C" int emu_rtsynth_l1(const llsm_b200_conf* conf, const llsm_b200_frames* fr, const llsm_b200_layer1* l1,
+  const int* pbpsyn, const llsm_b200_soptions* opt, float* out_p, float* out_ap, int out_cap, int* nout, int* latency,
+  int host_tracker, int block) {
+  RtBatch R;
+  int rc = rt_create(R, *conf, *opt, 1, nullptr, nullptr);
+  if(rc != 0) return rc;
+  R.host_tracker = host_tracker;
+  *latency = -R.sin_pos - R.curr_nhop;
+  L1PlanDev lp;
+  if(lp.build(nullptr) != 0) return -1;
+  const int S = conf->nutt, F = conf->nfrm;
+  int total = 0;
+  std::vector<float> bp((size_t)S * 8192), bap((size_t)S * 8192);
+  for(int i0 = 0; i0 < F; i0 += block) {
+    const int k = F - i0 < block ? F - i0 : block;
+    // slice [S][k] rows out of the [S][F] arrays
+    auto cut = [&](const void* src, size_t rowbytes, std::vector<char>& dst) -> void* {
+      if(src == nullptr) return nullptr;
+      dst.resize((size_t)S * k * rowbytes);
+      for(int s = 0; s < S; s ++)
+        memcpy(dst.data() + (size_t)s * k * rowbytes, (const char*)src + ((size_t)s * F + i0) * rowbytes, (size_t)k * rowbytes);
+      return dst.data();
+    };
+    std::vector<char> b[16];
+    const size_t nch = conf->nchannel;
+    llsm_b200_frames f; memset(&f, 0, sizeof(f));
+    f.f0 = (const float*)cut(fr->f0, 4, b[0]); f.nhar = (const int*)cut(fr->nhar, 4, b[1]);
+    f.ampl = (const float*)cut(fr->ampl, 4 * conf->maxnhar, b[2]); f.phse = (const float*)cut(fr->phse, 4 * conf->maxnhar, b[3]);
+    f.psd = (const float*)cut(fr->psd, 4 * conf->npsd, b[4]); f.psdres = (const float*)cut(fr->psdres, 4 * conf->npsd, b[5]);
+    f.edc = (const float*)cut(fr->edc, 4 * nch, b[6]); f.enhar = (const int*)cut(fr->enhar, 4 * nch, b[7]);
+    f.eampl = (const float*)cut(fr->eampl, 4 * nch * conf->maxnhar_e, b[8]); f.ephse = (const float*)cut(fr->ephse, 4 * nch * conf->maxnhar_e, b[9]);
+    llsm_b200_layer1 l = *l1;
+    l.rd = (float*)cut(l1->rd, 4, b[10]); l.vtmagn = (float*)cut(l1->vtmagn, 4 * (size_t)l1->nspec, b[11]);
+    l.vsphse = (float*)cut(l1->vsphse, 4 * conf->maxnhar, b[12]); l.nvs = (int*)cut(l1->nvs, 4, b[13]);
+    const int* pb = (const int*)cut(pbpsyn, 4, b[14]);
+    RtHostTrack ht; ht.f0 = f.f0; ht.nvs = l.nvs; ht.rd = l.rd; ht.vsphse = l.vsphse; ht.vs_stride = conf->maxnhar; ht.pbpsyn = pb;
+    std::vector<PbpNoEffect> mods(S);
+    int n = 0;
+    rc = rt_feed_block_l1(R, f, k, l, pb, lp, host_tracker ? &ht : nullptr, mods.data(), bp.data(), bap.data(), 8192, &n,
+      nullptr, nullptr);
+    if(rc != 0) { R.release(); lp.release(); return rc; }
+    for(int s = 0; s < S; s ++)
+      for(int q = 0; q < n && total + q < out_cap; q ++) {
+        out_p[(size_t)s * out_cap + total + q] = bp[(size_t)s * 8192 + q];
+        out_ap[(size_t)s * out_cap + total + q] = bap[(size_t)s * 8192 + q];
+      }
+    total += n;
+  }
+  *nout = total;
+  R.release(); lp.release();
+  return 0;
+}

@@ -231,7 +231,7 @@ def ref_synthesize_l1(fr, conf, pbpsyn, nfft=2048, seed=9, remove_hm=1):
     return (y, ys, yn), l1
 
 
-def ref_rtsynth(fr, conf, seed=1, use_iczt=1, use_l1=0, clear_at=-1):
+def ref_rtsynth(fr, conf, seed=1, use_iczt=1, use_l1=0, clear_at=-1, pbpsyn=None, remove_hm=1):
     """llsm_rtsynth_buffer_* run over every utterance. Returns (p [B][n], ap [B][n], latency)."""
     lib = load_ref()
     B, F = conf.nutt, conf.nfrm
@@ -245,7 +245,8 @@ def ref_rtsynth(fr, conf, seed=1, use_iczt=1, use_l1=0, clear_at=-1):
         n = lib.ref_rtsynth_soa(F, C.c_float(conf.fs), C.c_float(conf.thop), conf.maxnhar, conf.maxnhar_e,
                                 conf.npsd, conf.nchannel, _p(cf), C.c_float(conf.lip_radius), use_iczt,
                                 use_l1, *[_p(a) for a in args], C.c_uint(seed + b),
-                                _p(P[b]), _p(A[b]), cap, C.byref(lat), clear_at)
+                                _p(P[b]), _p(A[b]), cap, C.byref(lat), clear_at,
+                                _p(np.ascontiguousarray(pbpsyn[b], np.int32)) if pbpsyn is not None else None, remove_hm)
     return P[:, :n], A[:, :n], lat.value
 
 

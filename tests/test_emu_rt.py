@@ -59,3 +59,48 @@ def test_rt_clear_midstream():
     """llsm_rtsynth_buffer_clear keeps the modulation rings and the previous noise model (llsmrt.c:578-602)."""
     ref, got = _run(1, 24, thop=100.5 / 44100.0, clear_at=11)
     _check(ref, got)
+
+
+def _run_l1(B, F, pbp, seed=6, remove_hm=1, host_tracker=0, block=5, **kw):
+    fr, conf = S.synth_frames(B, F, seed=3, nhar=100, maxnhar=100, **kw)
+    P, A, lat = S.ref_rtsynth(fr, conf, seed=seed, use_l1=1, pbpsyn=pbp, remove_hm=remove_hm)
+    _, l1 = S.ref_synthesize_l1(fr, conf, pbp, seed=9)
+    white = S.ref_rt_white(conf, seed=seed)
+    so = abi.default_soptions(white.ctypes.data, 0)
+    fr2 = dict(fr)
+    if remove_hm:
+        fr2["nhar"] = None; fr2["ampl"] = None; fr2["phse"] = None
+    f = S.frames_struct(fr2)
+    s = abi.Layer1(); s.rd = l1["rd"].ctypes.data; s.vtmagn = l1["vtmagn"].ctypes.data
+    s.vsphse = l1["vsphse"].ctypes.data; s.nvs = l1["nvs"].ctypes.data; s.nspec = l1["vtmagn"].shape[-1]
+    cap = P.shape[1] + 64
+    op = np.full((B, cap), np.nan, np.float32); oap = op.copy()
+    n = C.c_int(0); l = C.c_int(0)
+    emu = S.load_emu()
+    rc = emu.emu_rtsynth_l1(C.byref(conf), C.byref(f), C.byref(s), pbp.ctypes.data_as(C.c_void_p), C.byref(so),
+                            op.ctypes.data_as(C.c_void_p), oap.ctypes.data_as(C.c_void_p), cap, C.byref(n), C.byref(l),
+                            host_tracker, block)
+    assert rc == 0
+    assert n.value == P.shape[1] and l.value == lat
+    return (P, A), (op[:, :n.value], oap[:, :n.value])
+
+
+@pytest.mark.parametrize("mode,host_tracker", [("switching", 0), ("switching", 1), ("all", 0), ("none", 0)])
+def test_rt_layer1_pulse_by_pulse(mode, host_tracker):
+    """use_l1 streaming: onset two periods early, windowed hand-over from the pulse buffer, trapezoid
+    catch-up at termination (llsmrt.c:305-419); HM derived from layer 1 when absent."""
+    B, F = 2, 48
+    pbp = np.zeros((B, F), np.int32)
+    if mode == "switching":
+        pbp[0, 10:22] = 1; pbp[0, 30:41] = 1; pbp[1, 5:40] = 1
+    elif mode == "all":
+        pbp[:] = 1
+    ref, got = _run_l1(B, F, pbp, host_tracker=host_tracker)
+    _check(ref, got, tol=1e-5)
+
+
+def test_rt_layer1_with_harmonic_model_present():
+    B, F = 1, 30
+    pbp = np.zeros((B, F), np.int32); pbp[0, 12:20] = 1
+    ref, got = _run_l1(B, F, pbp, remove_hm=0, block=30)
+    _check(ref, got, tol=1e-5)

@@ -93,3 +93,50 @@ def test_rt_device_generator_statistics(ctx):
     n0 = 20 * 441
     ratio = S.rms(ap[:, n0:]) / S.rms(A[:, n0:])
     assert 0.8 < ratio < 1.25, ratio
+
+
+def _l1_case(ctx, B, F, pbp, device, host_tracker=False, block=6, remove_hm=True, seed=6):
+    import torch
+    import libllsm2_b200 as L
+    fr, conf = S.synth_frames(B, F, seed=3, nhar=100, maxnhar=100)
+    ref = S.ref_rtsynth(fr, conf, seed=seed, use_l1=1, pbpsyn=pbp, remove_hm=1 if remove_hm else 0)
+    _, l1 = S.ref_synthesize_l1(fr, conf, pbp, seed=9)
+    white = S.ref_rt_white(conf, seed=seed)
+    rt = L.RtSynth(ctx, conf, white=torch.from_numpy(white).cuda() if device else white, nspec=l1["vtmagn"].shape[-1],
+                   host_tracker=host_tracker)
+    lat = rt.latency
+    ps, aps = [], []
+    for i in range(0, F, block):
+        k = min(block, F - i)
+        part = _slice(fr, i, i + k)
+        if remove_hm:
+            part["nhar"] = part["ampl"] = part["phse"] = None
+        lp = {kk: np.ascontiguousarray(v[:, i:i + k]) for kk, v in l1.items()}
+        pp = np.ascontiguousarray(pbp[:, i:i + k])
+        if device:
+            part = {kk: (torch.from_numpy(v).cuda() if v is not None else None) for kk, v in part.items()}
+            lp = {kk: torch.from_numpy(v).cuda() for kk, v in lp.items()}
+            pp = torch.from_numpy(pp).cuda()
+        p, ap = rt.feed(part, k, layer1=lp, pbpsyn=pp)
+        if device:
+            torch.cuda.synchronize(); p, ap = p.cpu().numpy(), ap.cpu().numpy()
+        ps.append(p.copy()); aps.append(ap.copy())
+    rt.close()
+    return ref, (np.concatenate(ps, 1), np.concatenate(aps, 1), lat)
+
+
+@pytest.mark.parametrize("device,host_tracker", [(True, False), (False, False), (False, True)])
+def test_rt_layer1_pulse_by_pulse(ctx, device, host_tracker):
+    B, F = 3, 48
+    pbp = np.zeros((B, F), np.int32)
+    pbp[0, 10:22] = 1; pbp[0, 30:41] = 1; pbp[1, 5:40] = 1
+    ref, got = _l1_case(ctx, B, F, pbp, device, host_tracker)
+    e = _check(ref, got)
+    assert max(e) < 1e-5, e
+
+
+def test_rt_layer1_all_pbp_with_stored_hm(ctx):
+    B, F = 1, 30
+    pbp = np.ones((B, F), np.int32)
+    ref, got = _l1_case(ctx, B, F, pbp, True, remove_hm=False, block=30)
+    assert max(_check(ref, got)) < 1e-5
