@@ -161,3 +161,56 @@ def test_llsmrt_dropin(libs):
     a, b = outs[0][2], outs[1][2]
     assert a.shape == b.shape and S.rms(b) > 1e-3
     assert S.rms(a - b) < 1e-4, S.rms(a - b)
+
+
+@pytest.mark.parametrize("effect", [False, True])
+def test_llsmrt_layer1_dropin(libs, effect):
+    """test-llsmrt.c / test-pbpeffects.c pattern: tolayer1, HM removed, PBPSYN toggling, use_l1 streaming, with
+    and without an llsm_pbpeffect callback per frame."""
+    fr, conf = S.synth_frames(1, 90, seed=21, nhar=80, maxnhar=80)
+    outs = []
+    for L in libs:
+        state = {"n": 0}
+
+        def modifier(g, delta_t, info, frame):
+            state["n"] += 1
+            k = state["n"]
+            g.contents[4] = g.contents[4] * (1.0 + 0.3 * np.sin(0.7 * k))
+            g.contents[0] = g.contents[0] * (1.0 - 0.2 * np.cos(0.3 * k))
+            delta_t[0] = 2e-4 * np.sin(1.3 * k)
+        cb = GFM(modifier)
+        L.llsm_create_rtsynth_buffer.restype = C.c_void_p
+        L.llsm_create_rtsynth_buffer.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.llsm_rtsynth_buffer_feed.argtypes = [C.c_void_p, C.c_void_p]
+        L.llsm_rtsynth_buffer_fetch_decomposed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.llsm_delete_rtsynth_buffer.argtypes = [C.c_void_p]
+        L.llsm_create_pbpeffect.restype = C.c_void_p
+        ck = U.build_chunk(L, fr, conf)
+        L.llsm_chunk_tolayer1(ck, 2048)
+        for i in range(conf.nfrm):
+            f = ck.contents.frames[i]
+            L.llsm_container_attach_(f, U.HMI, None, None, None)
+            if i % 40 > 20:
+                L.llsm_container_attach_(f, 9, C.cast(L.llsm_create_int(1), C.c_void_p), U.fn_ptr(L, "llsm_delete_int"),
+                                         U.fn_ptr(L, "llsm_copy_int"))
+            if effect and 25 <= i < 70:
+                e = L.llsm_create_pbpeffect(cb, None)
+                L.llsm_container_attach_(f, 8, C.c_void_p(e), U.fn_ptr(L, "llsm_delete_pbpeffect"),
+                                         U.fn_ptr(L, "llsm_copy_pbpeffect"))
+        so = L.llsm_create_soptions(C.c_float(conf.fs))
+        so.contents.use_l1 = 1
+        libc.srand(15)
+        rt = L.llsm_create_rtsynth_buffer(so, ck.contents.conf, 4096)
+        assert rt, "llsm_create_rtsynth_buffer(use_l1) returned NULL"
+        p, ap = C.c_float(), C.c_float()
+        ys = []
+        for i in range(conf.nfrm):
+            L.llsm_rtsynth_buffer_feed(rt, ck.contents.frames[i])
+            while L.llsm_rtsynth_buffer_fetch_decomposed(rt, C.byref(p), C.byref(ap)):
+                ys.append((p.value, ap.value))
+        L.llsm_delete_rtsynth_buffer(rt); L.llsm_delete_soptions(so); L.llsm_delete_chunk(ck)
+        outs.append((np.array(ys, np.float32), state["n"]))
+    a, b = outs[0][0], outs[1][0]
+    assert outs[0][1] == outs[1][1], "the effect callback must run once per pulse on both sides"
+    assert a.shape == b.shape and S.rms(b[:, 0]) > 1e-3
+    assert S.rms(a - b) < 1e-4, S.rms(a - b)
