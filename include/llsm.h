@@ -7,12 +7,13 @@
   each block cites the reference declaration it has to stay compatible with.
 
   What runs where
-    * llsm_analyze / llsm_synthesize: packed to flat arrays and executed by the CUDA kernels behind
-      include/llsm_b200.h (batch of one). No CPU fallback: they return NULL when no CUDA device is
-      usable (llsm_b200_last_error() tells why).
+    * llsm_analyze / llsm_synthesize (HM and use_l1 pulse-by-pulse) / llsm_chunk_tolayer1 /
+      llsm_chunk_tolayer0 / llsm_frame_tolayer0: packed to flat arrays and executed by the CUDA kernels
+      behind include/llsm_b200.h (batch of one). No CPU fallback: they return NULL (or silently, for the
+      void functions, as the reference does on bad input) when no CUDA device is usable
+      (llsm_last_error() tells why). llsm_pbpeffect callbacks run on the host, once per pulse, in order.
     * containers, frames, chunks, option structs, phase utilities: plain host C (bookkeeping).
-    * use_l1 (pulse-by-pulse) synthesis, layer-1 conversion, llsm_frame_compute_snr and the coder
-      are outside the accelerated path of this round: see DESIGN.md "Out of scope".
+    * llsm_frame_compute_snr and the coder are outside the path: see DESIGN.md "Out of scope".
 
   FP_TYPE must be float (the device kernels compute in FP32 like the reference's default build).
 */
