@@ -119,8 +119,8 @@ struct AnaPlanDev {
 };
 
 struct AnaScratch {
-  DevBuf x_sin, x_res, ce, env, lpsd, res, filt, nfft_utt;
-  void release() { nfft_utt.release(); x_sin.release(); x_res.release(); ce.release(); env.release(); lpsd.release(); res.release(); filt.release(); }
+  DevBuf x_sin, x_res, ce, env, lpsd, res, filt, pvar, nfft_utt;
+  void release() { nfft_utt.release(); x_sin.release(); x_res.release(); ce.release(); env.release(); lpsd.release(); res.release(); filt.release(); pvar.release(); }
 };
 
 // x: [B][xstride] device; fr: device output arrays; x_res_out optional [B][xstride]
@@ -137,7 +137,7 @@ static inline int run_analyze_l0(const SynthPlanDev& sp, AnaPlanDev& ap, AnaScra
   if(sc.x_sin.reserve((size_t)B * nx * 4) || sc.x_res.reserve((size_t)B * nx * 4) ||
      sc.ce.reserve((size_t)B * nch * cst * 4) || sc.env.reserve(BF * h.nspec * 4) ||
      sc.lpsd.reserve(BF * h.nspec * 4) || sc.res.reserve(BF * h.nspec * 4) ||
-     sc.filt.reserve(BF * h.nspec * 4)) return LLSM_B200_ENOMEM;
+     sc.filt.reserve(BF * h.nspec * 4) || sc.pvar.reserve(BF * h.nspec * 4)) return LLSM_B200_ENOMEM;
   if(ap.ensure_iir(nx, st) != 0) return LLSM_B200_ENOMEM;
   float* x_res = x_res_out ? x_res_out : sc.x_res.as<float>();
   const int rstride = x_res_out ? xstride : nx;
@@ -210,13 +210,13 @@ static inline int run_analyze_l0(const SynthPlanDev& sp, AnaPlanDev& ap, AnaScra
 #ifndef LLSM_EMU
     cudaFuncSetAttribute(noise_spec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 #endif
-    LLSM_LAUNCH(noise_spec_kernel, dim3(F, B), dim3(NS_THREADS), smem, st, N);
+    LLSM_LAUNCH(noise_spec_kernel, dim3((F + 1) / 2, B), dim3(NS_THREADS), smem, st, N);
     if(lc) lc->n ++;
 
     KalmanParams K; memset(&K, 0, sizeof(K));
     K.nfrm = F; K.nspec = h.nspec; K.nfrm_utt = nfrm_utt;
     K.env = sc.env.as<float>(); K.lpsd = sc.lpsd.as<float>(); K.res = sc.res.as<float>();
-    K.filt = sc.filt.as<float>();
+    K.filt = sc.filt.as<float>(); K.pvar = sc.pvar.as<float>();
     LLSM_LAUNCH(noise_kalman_kernel, dim3((h.nspec + 127) / 128, B), dim3(128), 0, st, K);
     if(lc) lc->n ++;
 

@@ -65,19 +65,31 @@ __global__ void __launch_bounds__(96) refine_f0_kernel(RefineParams P) {
   const float* x = P.x + (size_t)b * P.xstride;
   const int center = P.center[i];
   double yr = 0, yi = 0, dr = 0, di = 0;
-  for(int t = lane; t < nh; t += 32) {
-    int idx = center + t - nh / 2;
-    if(idx < 0 || idx >= P.nx) continue;
-    double xv = (double)x[idx];
-    int m = t - nh / 2;
-    double sw, cw; sincospi(2.0 * (double)m / L, &sw, &cw);
-    double w = 0.5 + 0.5 * cw;
-    double wd = -0.5 * (2.0 * LLSM_PI / L) * sw;
-    double u = (double)fc * (double)m; u -= rint(u);
-    double sp, cp; sincospi(2.0 * u, &sp, &cp);
-    // taps are stored as FP_TYPE (float) in the detector
-    float hr = (float)(w * cp), hi = (float)(-w * sp), hdr = (float)(wd * cp), hdi = (float)(-wd * sp);
-    yr += xv * hr; yi += xv * hi; dr += xv * hdr; di += xv * hdi;
+  {
+    // window angle 2 pi m / L and demodulation angle 2 pi fc m advance by fixed rotations (double) from one
+    // seed per lane: m = lane - half, lane - half + 32, ...
+    const int m0 = lane - nh / 2;
+    double sw, cw, sws, cws, sp, cp, sps, cps;
+    sincospi(2.0 * (double)m0 / L, &sw, &cw);
+    sincospi(2.0 * 32.0 / L, &sws, &cws);
+    double u = (double)fc * (double)m0; u -= rint(u);
+    sincospi(2.0 * u, &sp, &cp);
+    double us = (double)fc * 32.0; us -= rint(us);
+    sincospi(2.0 * us, &sps, &cps);
+    const double wdk = -0.5 * (2.0 * LLSM_PI / L);
+    for(int t = lane; t < nh; t += 32) {
+      const int idx = center + t - nh / 2;
+      if(idx >= 0 && idx < P.nx) {
+        const double xv = (double)x[idx];
+        const double w = 0.5 + 0.5 * cw;
+        const double wd = wdk * sw;
+        // taps are stored as FP_TYPE (float) in the detector
+        float hr = (float)(w * cp), hi = (float)(-w * sp), hdr = (float)(wd * cp), hdi = (float)(-wd * sp);
+        yr += xv * hr; yi += xv * hi; dr += xv * hdr; di += xv * hdi;
+      }
+      double t1 = cw * cws - sw * sws; sw = sw * cws + cw * sws; cw = t1;
+      double t2 = cp * cps - sp * sps; sp = sp * cps + cp * sps; cp = t2;
+    }
   }
   for(int o = 16; o > 0; o >>= 1) {
     yr += __shfl_xor_sync(0xffffffffu, yr, o); yi += __shfl_xor_sync(0xffffffffu, yi, o);
@@ -151,27 +163,33 @@ __global__ void __launch_bounds__(HD_THREADS) harmonic_dft_kernel(HarmDftParams 
   const float* x = P.sig + ((size_t)b * P.nsig + c) * P.xstride;
   const int center = P.center[i];
 
-  // ---- stage the Blackman-windowed frame as symmetric / antisymmetric halves; window sum
+  // ---- stage the Blackman-windowed frame as symmetric / antisymmetric halves; window sum.
+  // ws is even, so the periodic Blackman window is symmetric about m = half:
+  //   w(half +- n) = 0.42 + 0.5 cos(2 pi n / ws) + 0.08 cos(4 pi n / ws).
+  // Each thread walks n = tid, tid + T, ... and advances cos / sin (2 pi n / ws) by a fixed rotation in
+  // double (one sincospi pair per thread instead of four per sample).
   double wsum = 0;
-  for(int n = tid; n <= half; n += blockDim.x) {
-    float xp = 0, xm = 0;
-    if(n < half) {                                    // m = half + n
-      int m = half + n, idx = center + m - half;
-      double s1, c1, s2, c2;
-      sincospi(2.0 * (double)m / (double)ws, &s1, &c1); sincospi(4.0 * (double)m / (double)ws, &s2, &c2);
-      float w = (float)(0.42 - 0.5 * c1 + 0.08 * c2);
-      wsum += w;
-      if(idx >= 0 && idx < P.nx) xp = w * x[idx];
+  {
+    double cs, sn, cstep, sstep;
+    sincospi(2.0 * (double)tid / (double)ws, &sn, &cs);
+    sincospi(2.0 * (double)blockDim.x / (double)ws, &sstep, &cstep);
+    for(int n = tid; n <= half; n += blockDim.x) {
+      const float w = (float)(0.42 + 0.5 * cs + 0.08 * (2.0 * cs * cs - 1.0));
+      float xp = 0, xm = 0;
+      if(n < half) {                                  // m = half + n
+        int idx = center + n;
+        wsum += w;
+        if(idx >= 0 && idx < P.nx) xp = w * x[idx];
+      }
+      if(n >= 1) {                                    // m = half - n
+        int idx = center - n;
+        wsum += w;
+        if(idx >= 0 && idx < P.nx) xm = w * x[idx];
+      }
+      sp[n] = make_float2(xp + xm, xp - xm);
+      const double c2 = cs * cstep - sn * sstep;
+      sn = sn * cstep + cs * sstep; cs = c2;
     }
-    if(n >= 1) {                                      // m = half - n
-      int m = half - n, idx = center + m - half;
-      double s1, c1, s2, c2;
-      sincospi(2.0 * (double)m / (double)ws, &s1, &c1); sincospi(4.0 * (double)m / (double)ws, &s2, &c2);
-      float w = (float)(0.42 - 0.5 * c1 + 0.08 * c2);
-      wsum += w;
-      if(idx >= 0 && idx < P.nx) xm = w * x[idx];
-    }
-    sp[n] = make_float2(xp + xm, xp - xm);
   }
   red[tid] = wsum;
   __syncthreads();
@@ -314,95 +332,139 @@ struct NoiseSpecParams {
 
 #define NS_THREADS 256
 
+// One CTA per PAIR of consecutive frames: every transform is a complex FFT carrying frame i in the real
+// part and frame i + 1 in the imaginary part. The windowed frames are separated by Hermitian symmetry;
+// the log spectra and the liftered cepstra are real and even, so their transforms are real and the two
+// frames stay separated in re / im without any post-processing.
 __global__ void __launch_bounds__(NS_THREADS) noise_spec_kernel(NoiseSpecParams P) {
   LLSM_DYN_SMEM(smem);
   const int nfs = P.nfft_s;
   const int nmax = nfs > P.nfft ? nfs : P.nfft;
   float2* bufa = (float2*)smem;
   float2* bufb = bufa + nmax;
-  const int i = blockIdx.x, b = blockIdx.y;
+  const int i0 = 2 * blockIdx.x, b = blockIdx.y;
   const int nf = P.nfrm_utt ? P.nfrm_utt[b] : P.nfrm;
-  if(i >= nf) return;
+  if(i0 >= nf) return;
+  const bool two = i0 + 1 < nf;
   const int tid = threadIdx.x, nth = blockDim.x;
-  const float f0 = P.f0[(size_t)b * P.nfrm + i];
-  const int center = P.center[i];
-  const size_t orow = ((size_t)b * P.nfrm + i) * P.nspec;
+  const float* x = P.x + (size_t)b * P.xstride;
+  float f0v[2]; int cen[2], wsv[2];
+#pragma unroll
+  for(int h = 0; h < 2; h ++) {
+    const int i = (h == 0 || two) ? i0 + h : i0;
+    f0v[h] = P.f0[(size_t)b * P.nfrm + i];
+    cen[h] = P.center[i];
+    int ws = P.nwin;
+    if(f0v[h] != 0) { float t = P.fs / f0v[h]; t = __fmul_rn(t, 3.0f); ws = (int)t; }   // layer0.c:331
+    wsv[h] = ws;
+  }
+  const size_t orow = ((size_t)b * P.nfrm + i0) * P.nspec;
 
   // ---- (i) spectral envelope of x: Hann STFT (window 3 periods or nwin), cepstral smoothing
-  int ws = P.nwin;
-  if(f0 != 0) { float t = P.fs / f0; t = __fmul_rn(t, 3.0f); ws = (int)t; }       // layer0.c:331
-  const float* x = P.x + (size_t)b * P.xstride;
   for(int kb = tid; kb < nfs; kb += nth) {
-    float acc = 0.f;
-    int j0 = (kb + ws / 2) % nfs;
-    for(int j = j0; j < ws; j += nfs) {           // time aliasing when the window exceeds nfft
-      int idx = center + j - ws / 2;
-      if(idx >= 0 && idx < P.nx) {
-        double s, c; sincospi(2.0 * (double)j / (double)ws, &s, &c);
-        float w = (float)(0.5 - 0.5 * c);
-        acc += x[idx] * w;
+    float acc[2] = {0.f, 0.f};
+#pragma unroll
+    for(int h = 0; h < 2; h ++) {
+      if(h == 1 && ! two) break;
+      const int ws = wsv[h];
+      const float rws = 2.0f / (float)ws;
+      int j0 = (kb + ws / 2) % nfs;
+      for(int j = j0; j < ws; j += nfs) {           // time aliasing when the window exceeds nfft
+        int idx = cen[h] + j - ws / 2;
+        if(idx >= 0 && idx < P.nx) {
+          float w = 0.5f - 0.5f * cospif((float)j * rws);
+          acc[h] += x[idx] * w;
+        }
       }
     }
-    bufa[kb] = make_float2(acc, 0.f);
+    bufa[kb] = make_float2(acc[0], acc[1]);
   }
   __syncthreads();
   float2* X = block_fft<false>(bufa, bufb, P.lg_nfft_s, P.tw_s, nfs);
   float2* Y = (X == bufa) ? bufb : bufa;
   {
-    float normalizer = 1024.0f / P.std_norm; normalizer = normalizer / (float)ws;  // dsputils.c:111
+    float nrm[2];
+#pragma unroll
+    for(int h = 0; h < 2; h ++) { float t = 1024.0f / P.std_norm; nrm[h] = t / (float)wsv[h]; }   // dsputils.c:111
     for(int k = tid; k <= nfs / 2; k += nth) {
-      float2 v = X[k];
-      float mag = (float)sqrt((double)v.x * v.x + (double)v.y * v.y) * normalizer;
-      float lg = logf(mag > 1e-10f ? mag : 1e-10f);
-      Y[k] = make_float2(lg, 0.f);
-      if(k > 0 && k < nfs / 2) Y[nfs - k] = make_float2(lg, 0.f);
+      const float2 zk = X[k], zn = X[(nfs - k) & (nfs - 1)];
+      // A = (Zk + conj Zn) / 2, B = (Zk - conj Zn) / (2 i)
+      const float ar = 0.5f * (zk.x + zn.x), ai = 0.5f * (zk.y - zn.y);
+      const float br = 0.5f * (zk.y + zn.y), bi = -0.5f * (zk.x - zn.x);
+      float ma = sqrtf(ar * ar + ai * ai) * nrm[0], mb = sqrtf(br * br + bi * bi) * nrm[1];
+      const float2 lg = make_float2(logf(ma > 1e-10f ? ma : 1e-10f), logf(mb > 1e-10f ? mb : 1e-10f));
+      Y[k] = lg;
+      if(k > 0 && k < nfs / 2) Y[nfs - k] = lg;
     }
   }
   __syncthreads();
-  float2* Cq = block_fft<true>(Y, X, P.lg_nfft_s, P.tw_s, nfs);      // cepstrum * nfft
+  float2* Cq = block_fft<true>(Y, X, P.lg_nfft_s, P.tw_s, nfs);      // cepstra * nfft (real, even)
   float2* D = (Cq == bufa) ? bufb : bufa;
   {
-    const float f0s = (f0 == 0 ? 200.0f : f0) / P.fs;               // layer0.c:338
+    float f0s[2];
+#pragma unroll
+    for(int h = 0; h < 2; h ++) f0s[h] = (f0v[h] == 0 ? 200.0f : f0v[h]) / P.fs;   // layer0.c:338
+    const float inv = 1.0f / (float)nfs;
     for(int q = tid; q <= nfs / 2; q += nth) {
-      double xq = (double)f0s * q;
-      double sinc = 1.0;
-      if(q > 0) { double s, c; sincospi(xq, &s, &c); sinc = s / (LLSM_PI * xq); }
-      double s2, c2; sincospi(2.0 * xq, &s2, &c2);
-      float cv = (float)((double)Cq[q].x / nfs * sinc * (1.18 - 0.18 * c2));
-      D[q] = make_float2(cv, 0.f);
-      if(q > 0 && q < nfs / 2) D[nfs - q] = make_float2(cv, 0.f);
+      const float2 c = Cq[q];
+      float cv[2] = {c.x, c.y};
+#pragma unroll
+      for(int h = 0; h < 2; h ++) {
+        double xq = (double)f0s[h] * q;
+        float sinc = 1.0f;
+        double xr_ = xq - 2.0 * rint(xq * 0.5);                       // reduce to [-1, 1]
+        float s1 = sinpif((float)xr_);
+        if(q > 0) sinc = s1 / (float)(LLSM_PI * xq);
+        double x2 = 2.0 * xq; x2 -= 2.0 * rint(x2 * 0.5);
+        float c2 = cospif((float)x2);
+        cv[h] = cv[h] * inv * sinc * (1.18f - 0.18f * c2);
+      }
+      const float2 d = make_float2(cv[0], cv[1]);
+      D[q] = d;
+      if(q > 0 && q < nfs / 2) D[nfs - q] = d;
     }
   }
   __syncthreads();
   float2* Ev = block_fft<false>(D, Cq, P.lg_nfft_s, P.tw_s, nfs);
   for(int j = tid; j < P.nspec; j += nth) {
     int idx = j * nfs / P.nfft;                                       // layer0.c:341-342
-    P.env[orow + j] = Ev[idx].x * 2.0f;
+    const float2 e = Ev[idx];
+    P.env[orow + j] = e.x * 2.0f;
+    if(two) P.env[orow + P.nspec + j] = e.y * 2.0f;
   }
   __syncthreads();
 
-  // ---- (ii) PSD of the residual frame (Blackman, zero-padded at the end; dsputils.c:246-265)
+  // ---- (ii) PSD of the residual frames (Blackman, zero-padded at the end; dsputils.c:246-265)
   const float* xr = P.x_res + (size_t)b * P.rstride;
   for(int j = tid; j < P.nfft; j += nth) {
-    float v = 0.f;
+    float v0 = 0.f, v1 = 0.f;
     if(j < P.nwin) {
-      int idx = center + j - P.nwin / 2;
-      if(idx >= 0 && idx < P.nx) v = P.win_psd[j] * xr[idx];
+      const float w = P.win_psd[j];
+      int idx = cen[0] + j - P.nwin / 2;
+      if(idx >= 0 && idx < P.nx) v0 = w * xr[idx];
+      idx = cen[1] + j - P.nwin / 2;
+      if(two && idx >= 0 && idx < P.nx) v1 = w * xr[idx];
     }
-    bufa[j] = make_float2(v, 0.f);
+    bufa[j] = make_float2(v0, v1);
   }
   __syncthreads();
   float2* Z = block_fft<false>(bufa, bufb, P.lg_nfft, P.tw_p, P.nfft);
   for(int j = tid; j < P.nspec; j += nth) {
-    float2 v = Z[j];
-    float pw = __fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)) / P.win_power;
-    P.lpsd[orow + j] = (float)log((double)(pw > 1e-10f ? pw : 1e-10f));   // layer0.c:358
+    const float2 zk = Z[j], zn = Z[(P.nfft - j) & (P.nfft - 1)];
+    const float ar = 0.5f * (zk.x + zn.x), ai = 0.5f * (zk.y - zn.y);
+    const float br = 0.5f * (zk.y + zn.y), bi = -0.5f * (zk.x - zn.x);
+    float pa = __fadd_rn(__fmul_rn(ar, ar), __fmul_rn(ai, ai)) / P.win_power;
+    float pb = __fadd_rn(__fmul_rn(br, br), __fmul_rn(bi, bi)) / P.win_power;
+    P.lpsd[orow + j] = logf(pa > 1e-10f ? pa : 1e-10f);                // layer0.c:358
+    if(two) P.lpsd[orow + P.nspec + j] = logf(pb > 1e-10f ? pb : 1e-10f);
   }
 }
 
+#define KCH 8
 struct KalmanParams {
   int nfrm, nspec; const int* nfrm_utt;
-  float* env;      // in: envelope; reused as posterior variance storage
+  const float* env; // in: envelope
+  float* pvar;     // scratch: posterior variances
   float* lpsd;     // in: raw log PSD; out: smoothed + Euler gamma
   float* res;      // out: residual (scratch for Q on the way)
   float* filt;     // scratch: filtered means
@@ -419,47 +481,74 @@ __global__ void __launch_bounds__(128) noise_kalman_kernel(KalmanParams P) {
   const size_t base = (size_t)b * P.nfrm * P.nspec + j;
   const size_t st = P.nspec;
   const double R = (double)(float)(LLSM_PI * LLSM_PI / 6.0);      // LOGCHI2VAR stored as FP_TYPE
-  float e_prev = P.env[base], e_cur = e_prev, e_next = n > 1 ? P.env[base + st] : e_prev;
+  float e_prev = P.env[base], e_cur = e_prev;
   double xk = 0, Pk = 0;
-  for(int i = 0; i < n; i ++) {
-    // Q[i] = max(1e-8, m2 / 3 - m1 * m1 / 9) over frames clamp(i-1..i+1), float arithmetic
-    float m1 = 0.f, m2 = 0.f;
-    m1 = __fadd_rn(m1, e_prev); m2 = __fadd_rn(m2, __fmul_rn(e_prev, e_prev));
-    m1 = __fadd_rn(m1, e_cur);  m2 = __fadd_rn(m2, __fmul_rn(e_cur, e_cur));
-    m1 = __fadd_rn(m1, e_next); m2 = __fadd_rn(m2, __fmul_rn(e_next, e_next));
-    float qv = __fadd_rn(m2 / 3.0f, -(__fmul_rn(m1, m1) / 9.0f));
-    float Q = qv > 1e-8f ? qv : 1e-8f;
-    const double z = (double)P.lpsd[base + i * st];
-    if(i == 0) { xk = z; Pk = R; }
-    else {
-      double Pp = Pk + (double)Q;
-      double K = Pp / (Pp + R);
-      xk += K * (z - xk);
-      Pk = (1.0 - K) * Pp;
+  // The time loop is latency-bound (one dependent chain per thread): loads of the next KCH frames are
+  // issued together before the chain advances.
+  for(int i0 = 0; i0 < n; i0 += KCH) {
+    float ev[KCH], zv[KCH];
+#pragma unroll
+    for(int u = 0; u < KCH; u ++) {
+      int ie = i0 + u + 1; if(ie > n - 1) ie = n - 1;
+      ev[u] = P.env[base + (size_t)ie * st];
+      int iz = i0 + u; if(iz > n - 1) iz = n - 1;
+      zv[u] = P.lpsd[base + (size_t)iz * st];
     }
-    P.filt[base + i * st] = (float)xk;
-    P.env[base + i * st] = (float)Pk;          // posterior variance (FP_TYPE array P)
-    P.res[base + i * st] = Q;
-    e_prev = e_cur; e_cur = e_next;
-    e_next = (i + 2 < n) ? P.env[base + (size_t)(i + 2) * st] : e_next;
+#pragma unroll
+    for(int u = 0; u < KCH; u ++) {
+      const int i = i0 + u;
+      if(i < n) {
+        const float e_next = ev[u];
+        // Q[i] = max(1e-8, m2 / 3 - m1 * m1 / 9) over frames clamp(i-1..i+1), float arithmetic
+        float m1 = 0.f, m2 = 0.f;
+        m1 = __fadd_rn(m1, e_prev); m2 = __fadd_rn(m2, __fmul_rn(e_prev, e_prev));
+        m1 = __fadd_rn(m1, e_cur);  m2 = __fadd_rn(m2, __fmul_rn(e_cur, e_cur));
+        m1 = __fadd_rn(m1, e_next); m2 = __fadd_rn(m2, __fmul_rn(e_next, e_next));
+        float qv = __fadd_rn(m2 / 3.0f, -(__fmul_rn(m1, m1) / 9.0f));
+        float Q = qv > 1e-8f ? qv : 1e-8f;
+        const double z = (double)zv[u];
+        if(i == 0) { xk = z; Pk = R; }
+        else {
+          double Pp = Pk + (double)Q;
+          double K = Pp / (Pp + R);
+          xk += K * (z - xk);
+          Pk = (1.0 - K) * Pp;
+        }
+        P.filt[base + i * st] = (float)xk;
+        P.pvar[base + i * st] = (float)Pk;       // posterior variance (FP_TYPE array P)
+        P.res[base + i * st] = Q;
+        e_prev = e_cur; e_cur = e_next;
+      }
+    }
   }
   // RTS smoother, residual, bias removal
   double sn = (double)P.filt[base + (size_t)(n - 1) * st];
   float qnext = 0.f;
-  for(int t = n - 1; t >= 0; t --) {
-    float yt = P.filt[base + t * st];
-    float qt = P.res[base + t * st];
-    if(t < n - 1) {
-      double Pt = (double)P.env[base + t * st];
-      double Pp = Pt + (double)qnext;
-      double Cg = Pt / Pp;
-      sn = (double)yt + Cg * (sn - (double)yt);
+  for(int t0 = n - 1; t0 >= 0; t0 -= KCH) {
+    float yv[KCH], qv_[KCH], pv[KCH], rv[KCH];
+#pragma unroll
+    for(int u = 0; u < KCH; u ++) {
+      int t = t0 - u; if(t < 0) t = 0;
+      yv[u] = P.filt[base + (size_t)t * st]; qv_[u] = P.res[base + (size_t)t * st];
+      pv[u] = P.pvar[base + (size_t)t * st]; rv[u] = P.lpsd[base + (size_t)t * st];
     }
-    float s = (float)sn;                        // stored as FP_TYPE; the recursion stays in double
-    float raw = P.lpsd[base + t * st];
-    P.res[base + t * st] = raw - s;             // layer0.c:381
-    P.lpsd[base + t * st] = (float)((double)s + 0.57721566);   // layer0.c:382 EULERGAMMA
-    qnext = qt;
+#pragma unroll
+    for(int u = 0; u < KCH; u ++) {
+      const int t = t0 - u;
+      if(t >= 0) {
+        const float yt = yv[u], qt = qv_[u];
+        if(t < n - 1) {
+          double Pt = (double)pv[u];
+          double Pp = Pt + (double)qnext;
+          double Cg = Pt / Pp;
+          sn = (double)yt + Cg * (sn - (double)yt);
+        }
+        float s = (float)sn;                        // stored as FP_TYPE; the recursion stays in double
+        P.res[base + t * st] = rv[u] - s;           // layer0.c:381
+        P.lpsd[base + t * st] = (float)((double)s + 0.57721566);   // layer0.c:382 EULERGAMMA
+        qnext = qt;
+      }
+    }
   }
 }
 

@@ -333,13 +333,19 @@ __global__ void __launch_bounds__(EXC_THREADS) noise_excitation_kernel(ExcParams
   const size_t row = (size_t)b * P.nfrm;
 
   // frames that can reach [p0, p0 + EXC_THREADS): env_off + n_env + 1 > p0 and env_off - 1 <= pend
-  const int pend = p0 + EXC_THREADS - 1;
-  int lo = 0, hi = nf;
-  while(lo < hi) { int mid = (lo + hi) >> 1; if(P.env_off[mid] + P.n_env + 1 > p0) hi = mid; else lo = mid + 1; }
-  const int ia = lo;
-  lo = ia; hi = nf;
-  while(lo < hi) { int mid = (lo + hi) >> 1; if(P.env_off[mid] - 1 > pend) hi = mid; else lo = mid + 1; }
-  const int ib = lo;                               // frames [ia, ib)
+  // (two binary searches, done once per CTA)
+  __shared__ int s_range[2];
+  if(threadIdx.x == 0) {
+    const int pend = p0 + EXC_THREADS - 1;
+    int lo = 0, hi = nf;
+    while(lo < hi) { int mid = (lo + hi) >> 1; if(P.env_off[mid] + P.n_env + 1 > p0) hi = mid; else lo = mid + 1; }
+    s_range[0] = lo;
+    hi = nf;
+    while(lo < hi) { int mid = (lo + hi) >> 1; if(P.env_off[mid] - 1 > pend) hi = mid; else lo = mid + 1; }
+    s_range[1] = lo;
+  }
+  __syncthreads();
+  const int ia = s_range[0], ib = s_range[1];      // frames [ia, ib)
 
   float env[MAXCH];
 #pragma unroll

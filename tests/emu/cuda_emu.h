@@ -93,6 +93,8 @@ static inline void sincospif(float x, float* s, float* c) {
 static inline void sincospi(double x, double* s, double* c) {
   double r = std::fmod(x, 2.0); *s = std::sin(M_PI * r); *c = std::cos(M_PI * r);
 }
+static inline float cospif(float x) { double r = std::fmod((double)x, 2.0); return (float)std::cos(M_PI * r); }
+static inline float sinpif(float x) { double r = std::fmod((double)x, 2.0); return (float)std::sin(M_PI * r); }
 static inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
 static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
