@@ -76,8 +76,15 @@ __device__ __forceinline__ float2 fft_tw(const float2* __restrict__ tw, int idx)
   return w;
 }
 
-template <bool INV>
+// Bank swizzle for the FFT buffers (SWZ): element j lives at j ^ (((j >> 4) & 3) * 5). The radix-4 passes
+// write with strides 4 p (p = 1, 4): without the swizzle 8 lanes of a warp hit the same bank pair; with it
+// every pass touches 16 distinct bank pairs per half-warp. It permutes the low 4 index bits inside each
+// 64-element block, so buffers keep their size. Callers index the buffers through fsw() as well.
+__device__ __forceinline__ int fsw(int j) { return j ^ (((j >> 4) & 3) * 5); }
+
+template <bool INV, bool SWZ = false>
 __device__ float2* block_fft(float2* a, float2* b, int lg, const float2* __restrict__ tw, int ntw) {
+#define FIX(j) (SWZ ? fsw(j) : (j))
   const int n = 1 << lg;
   const int tid = threadIdx.x, nth = blockDim.x;
   int p = 1; // butterflies already combined
@@ -87,10 +94,10 @@ __device__ float2* block_fft(float2* a, float2* b, int lg, const float2* __restr
     const int tws = ntw / (4 * p); // index step: angle -2 pi k / (4p)
     for(int i = tid; i < t; i += nth) {
       int k = i & (p - 1);
-      float2 u0 = a[i];
-      float2 u1 = cmul(a[i + t], fft_tw<INV>(tw, k * tws));
-      float2 u2 = cmul(a[i + 2 * t], fft_tw<INV>(tw, 2 * k * tws));
-      float2 u3 = cmul(a[i + 3 * t], fft_tw<INV>(tw, 3 * k * tws));
+      float2 u0 = a[FIX(i)];
+      float2 u1 = cmul(a[FIX(i + t)], fft_tw<INV>(tw, k * tws));
+      float2 u2 = cmul(a[FIX(i + 2 * t)], fft_tw<INV>(tw, 2 * k * tws));
+      float2 u3 = cmul(a[FIX(i + 3 * t)], fft_tw<INV>(tw, 3 * k * tws));
       float2 v0 = make_float2(u0.x + u2.x, u0.y + u2.y);
       float2 v1 = make_float2(u0.x - u2.x, u0.y - u2.y);
       float2 v2 = make_float2(u1.x + u3.x, u1.y + u3.y);
@@ -98,10 +105,10 @@ __device__ float2* block_fft(float2* a, float2* b, int lg, const float2* __restr
       // forward: multiply v3 by -i; inverse: by +i
       float2 v3r = INV ? make_float2(-v3.y, v3.x) : make_float2(v3.y, -v3.x);
       int j = ((i - k) << 2) + k;
-      b[j]         = make_float2(v0.x + v2.x, v0.y + v2.y);
-      b[j + p]     = make_float2(v1.x + v3r.x, v1.y + v3r.y);
-      b[j + 2 * p] = make_float2(v0.x - v2.x, v0.y - v2.y);
-      b[j + 3 * p] = make_float2(v1.x - v3r.x, v1.y - v3r.y);
+      b[FIX(j)]         = make_float2(v0.x + v2.x, v0.y + v2.y);
+      b[FIX(j + p)]     = make_float2(v1.x + v3r.x, v1.y + v3r.y);
+      b[FIX(j + 2 * p)] = make_float2(v0.x - v2.x, v0.y - v2.y);
+      b[FIX(j + 3 * p)] = make_float2(v1.x - v3r.x, v1.y - v3r.y);
     }
     __syncthreads();
     float2* sw = a; a = b; b = sw;
@@ -112,16 +119,17 @@ __device__ float2* block_fft(float2* a, float2* b, int lg, const float2* __restr
     const int tws = ntw / (2 * p);
     for(int i = tid; i < t; i += nth) {
       int k = i & (p - 1);
-      float2 u0 = a[i];
-      float2 u1 = cmul(a[i + t], fft_tw<INV>(tw, k * tws));
+      float2 u0 = a[FIX(i)];
+      float2 u1 = cmul(a[FIX(i + t)], fft_tw<INV>(tw, k * tws));
       int j = ((i - k) << 1) + k;
-      b[j]     = make_float2(u0.x + u1.x, u0.y + u1.y);
-      b[j + p] = make_float2(u0.x - u1.x, u0.y - u1.y);
+      b[FIX(j)]     = make_float2(u0.x + u1.x, u0.y + u1.y);
+      b[FIX(j + p)] = make_float2(u0.x - u1.x, u0.y - u1.y);
     }
     __syncthreads();
     float2* sw = a; a = b; b = sw;
   }
   return a;
+#undef FIX
 }
 
 // 2^ceil(e) as an exact integer (device pow() is only accurate to an ulp, and the reference

@@ -153,12 +153,14 @@ static inline int run_analyze_l0(const SynthPlanDev& sp, AnaPlanDev& ap, AnaScra
 
   // 2. harmonic analysis of x (dsputils.c:175-228)
   const int max_half = (int)ceil((double)conf.fs / 20.0 * (double)opt.rel_winsize / 4.0 * 2.0) + 4;
-  auto harmonic_pass = [&](const float* sig, int nsig, int sstride, int maxnhar, int* nhar_o, float* ampl_o, float* phse_o) -> int {
+  auto harmonic_pass = [&](const float* sig, int nsig, int sstride, int maxnhar, int* nhar_o, float* ampl_o, float* phse_o,
+                           float* edc_o) -> int {
     if(opt.hm_method == 1) {
       HarmDftParams H; memset(&H, 0, sizeof(H));
       H.nfrm = F; H.nfrm_utt = nfrm_utt; H.sig = sig; H.nsig = nsig; H.nx = nx; H.xstride = sstride;
       H.f0 = fr.f0; H.center = sp.hm_base; H.fs = conf.fs; H.rel_winsize = opt.rel_winsize;
       H.maxnhar = maxnhar; H.nhar_out = nhar_o; H.ampl = ampl_o; H.phse = phse_o; H.max_half = max_half;
+      H.edc = edc_o; H.thop = conf.thop;
       if(launch_harmonic_dft(H, B, st) != 0) return LLSM_B200_ERANGE;
     } else {
       HarmPpParams H; memset(&H, 0, sizeof(H));
@@ -183,7 +185,7 @@ static inline int run_analyze_l0(const SynthPlanDev& sp, AnaPlanDev& ap, AnaScra
     LLSM_LAUNCH(utt_fftsize_kernel, dim3(B), dim3(128), 0, st, M);
     if(lc) lc->n ++;
   }
-  { int rc = harmonic_pass(x, 1, xstride, conf.maxnhar, fr.nhar, fr.ampl, fr.phse); if(rc) return rc; }
+  { int rc = harmonic_pass(x, 1, xstride, conf.maxnhar, fr.nhar, fr.ampl, fr.phse, nullptr); if(rc) return rc; }
 
   // 3. residual: x - resynthesised sinusoids (layer0.c:498-501; options == NULL, ny = nx)
   {
@@ -240,10 +242,14 @@ static inline int run_analyze_l0(const SynthPlanDev& sp, AnaPlanDev& ap, AnaScra
     LLSM_LAUNCH(iir_filtfilt_kernel, dim3(B * nch), dim3(IIR_NT), 0, st, I);
     if(lc) lc->n ++;
 
+    // CZT pass: the short-time means ride along in the same kernel; peak picking keeps the separate kernel
+    const bool dc_fused = conf.maxnhar_e > 0 && opt.hm_method == 1;
     if(conf.maxnhar_e > 0) {
-      int rc = harmonic_pass(sc.ce.as<float>(), nch, cst, conf.maxnhar_e, fr.enhar, fr.eampl, fr.ephse);
+      int rc = harmonic_pass(sc.ce.as<float>(), nch, cst, conf.maxnhar_e, fr.enhar, fr.eampl, fr.ephse,
+        dc_fused ? fr.edc : nullptr);
       if(rc) return rc;
     }
+    if(dc_fused) return 0;
 
     DcParams D; memset(&D, 0, sizeof(D));
     D.nfrm = F; D.nchannel = nch; D.nfrm_utt = nfrm_utt; D.ce = sc.ce.as<float>(); D.cstride = cst; D.nx = nx;

@@ -130,85 +130,124 @@ struct HarmDftParams {
   int* nhar_out;            // [B][nfrm][nsig]
   float* ampl; float* phse; // [B][nfrm][nsig][maxnhar]
   int max_half;             // capacity of the staged half-frame (pairs)
+  float* edc; float thop;   // optional: short-time mean of every signal, [B][nfrm][nsig]
 };
 
 #define HD_THREADS 128
 #define HD_RESEED 64
 
+// G = threads that share one signal: HD_THREADS (one signal per CTA: the main pass) or 32 (one warp per
+// signal, HD_THREADS / 32 signals of the same frame per CTA: the sub-band envelope pass, where the window,
+// its sum and the frame geometry are shared by the channels). With P.edc != NULL the group also writes
+// the short-time mean of its signal (llsm_compute_dc, dsputils.c:117-124; window rule layer0.c:430,446).
+template <int G>
 __global__ void __launch_bounds__(HD_THREADS) harmonic_dft_kernel(HarmDftParams P) {
   LLSM_DYN_SMEM(smem);
-  float2* sp = (float2*)smem;                         // [max_half + 1] (x+ + x-, x+ - x-)
-  double* red = (double*)(sp + P.max_half + 2);       // [HD_THREADS] reduction scratch
+  constexpr int NG = HD_THREADS / G;                  // signals per CTA
+  float* wv = (float*)smem;                           // [max_half + 2] window, w(half +- n)
+  double* red = (double*)(wv + ((P.max_half + 2 + 1) & ~1));   // [HD_THREADS] reduction scratch
   float* part = (float*)(red + HD_THREADS);           // [2 * HD_THREADS] slice partials
+  float2* spall = (float2*)(part + 2 * HD_THREADS);   // [NG][max_half + 2] (x+ + x-, x+ - x-)
 
   const int i = blockIdx.x;
-  const int b = blockIdx.y / P.nsig, c = blockIdx.y % P.nsig;
-  const int nf = P.nfrm_utt ? P.nfrm_utt[b] : P.nfrm;
+  const int ngrp = (P.nsig + NG - 1) / NG;            // CTAs per (utterance, frame)
+  const int b = blockIdx.y / ngrp;
   const int tid = threadIdx.x;
-  const size_t fidx = ((size_t)b * P.nfrm + i) * P.nsig + c;
+  const int g = tid / G, gt = tid % G;                // group, thread in group
+  const int c = (blockIdx.y % ngrp) * NG + g;         // signal of this group
+  const bool live = c < P.nsig;
+  const int nf = P.nfrm_utt ? P.nfrm_utt[b] : P.nfrm;
+  const size_t fidx = ((size_t)b * P.nfrm + i) * P.nsig + (live ? c : 0);
   if(i >= nf) return;
   const float f0 = P.f0[(size_t)b * P.nfrm + i];
+  const int center = P.center[i];
+  const float* x = P.sig + ((size_t)b * P.nsig + (live ? c : 0)) * P.xstride;
+  auto gsync = [&]() { if(G == 32) __syncwarp(); else __syncthreads(); };
+
+  // ---- short-time mean (sub-band pass): round((f0 == 0 ? thop * 2 : 2 / f0) * fs) samples around the centre
+  if(P.edc != nullptr && live) {
+    double wlen = f0 == 0 ? (double)(P.thop * 2.0f) : 2.0 / (double)f0;
+    const int nw = (int)round(wlen * (double)P.fs);
+    double acc = 0;
+    for(int j = gt; j < nw; j += G) {
+      int idx = center + j - nw / 2;
+      if(idx >= 0 && idx < P.nx) acc += (double)x[idx];
+    }
+    if(G == 32) {
+      for(int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    } else {
+      red[tid] = acc;
+      __syncthreads();
+      for(int o = G >> 1; o > 0; o >>= 1) { if(tid < o) red[tid] += red[tid + o]; __syncthreads(); }
+      acc = red[0];
+      __syncthreads();
+    }
+    if(gt == 0) P.edc[fidx] = nw > 0 ? (float)(acc / nw) : 0.f;
+  }
+
   if(! (f0 > 0)) {                                    // unvoiced: no harmonic model (layer0.c:106)
-    if(tid == 0) P.nhar_out[fidx] = 0;
-    for(int k = tid; k < P.maxnhar; k += blockDim.x) { P.ampl[fidx * P.maxnhar + k] = 0; P.phse[fidx * P.maxnhar + k] = 0; }
+    if(live) {
+      if(gt == 0) P.nhar_out[fidx] = 0;
+      for(int k = gt; k < P.maxnhar; k += G) { P.ampl[fidx * P.maxnhar + k] = 0; P.phse[fidx * P.maxnhar + k] = 0; }
+    }
     return;
   }
   const int ws = ana_winsize(P.fs, f0, P.rel_winsize);
   const int nh = ana_nhar(P.fs, f0, P.maxnhar);
   const int half = ws >> 1;                           // shift = nx / 2 (dsputils.c:151)
   if(half > P.max_half) {                             // window longer than the staging buffer
-    if(tid == 0) P.nhar_out[fidx] = -1;
+    if(live && gt == 0) P.nhar_out[fidx] = -1;
     return;
   }
-  const float* x = P.sig + ((size_t)b * P.nsig + c) * P.xstride;
-  const int center = P.center[i];
 
-  // ---- stage the Blackman-windowed frame as symmetric / antisymmetric halves; window sum.
-  // ws is even, so the periodic Blackman window is symmetric about m = half:
+  // ---- Blackman window once per CTA. ws is even, so the periodic window is symmetric about m = half:
   //   w(half +- n) = 0.42 + 0.5 cos(2 pi n / ws) + 0.08 cos(4 pi n / ws).
-  // Each thread walks n = tid, tid + T, ... and advances cos / sin (2 pi n / ws) by a fixed rotation in
-  // double (one sincospi pair per thread instead of four per sample).
+  // Each thread walks n = tid, tid + T, ... advancing cos / sin (2 pi n / ws) by a fixed rotation in double.
   double wsum = 0;
   {
     double cs, sn, cstep, sstep;
     sincospi(2.0 * (double)tid / (double)ws, &sn, &cs);
-    sincospi(2.0 * (double)blockDim.x / (double)ws, &sstep, &cstep);
-    for(int n = tid; n <= half; n += blockDim.x) {
+    sincospi(2.0 * (double)HD_THREADS / (double)ws, &sstep, &cstep);
+    for(int n = tid; n <= half; n += HD_THREADS) {
       const float w = (float)(0.42 + 0.5 * cs + 0.08 * (2.0 * cs * cs - 1.0));
-      float xp = 0, xm = 0;
-      if(n < half) {                                  // m = half + n
-        int idx = center + n;
-        wsum += w;
-        if(idx >= 0 && idx < P.nx) xp = w * x[idx];
-      }
-      if(n >= 1) {                                    // m = half - n
-        int idx = center - n;
-        wsum += w;
-        if(idx >= 0 && idx < P.nx) xm = w * x[idx];
-      }
-      sp[n] = make_float2(xp + xm, xp - xm);
+      wv[n] = w;
+      if(n < half) wsum += w;                         // m = half + n
+      if(n >= 1) wsum += w;                           // m = half - n
       const double c2 = cs * cstep - sn * sstep;
       sn = sn * cstep + cs * sstep; cs = c2;
     }
   }
   red[tid] = wsum;
   __syncthreads();
-  for(int o = blockDim.x >> 1; o > 0; o >>= 1) {
+  for(int o = HD_THREADS >> 1; o > 0; o >>= 1) {
     if(tid < o) red[tid] += red[tid + o];
     __syncthreads();
   }
   const float winsum = (float)red[0];                 // FP_TYPE winsum = sumfp(w, nx)
+  if(! live) return;                                  // (no block barrier below for G == 32)
+
+  // ---- stage the windowed frame of this group's signal as symmetric / antisymmetric halves
+  float2* sp = spall + (size_t)g * (P.max_half + 2);
+  for(int n = gt; n <= half; n += G) {
+    const float w = wv[n];
+    float xp = 0, xm = 0;
+    if(n < half) { int idx = center + n; if(idx >= 0 && idx < P.nx) xp = w * x[idx]; }
+    if(n >= 1) { int idx = center - n; if(idx >= 0 && idx < P.nx) xm = w * x[idx]; }
+    sp[n] = make_float2(xp + xm, xp - xm);
+  }
+  gsync();
 
   // ---- frequencies as the reference rounds them (dsputils.c:156-158)
   const float omega0 = (float)(2.0 * LLSM_PI * (double)f0 / (double)P.fs);   // czt step (FP_TYPE arg)
   const double nu = (double)omega0 / (2.0 * LLSM_PI);                        // turns per sample
 
   // work split: nhc harmonics across threads, nsl sample slices across the remaining factor
-  int nhc = 1; while(nhc < nh && nhc < (int)blockDim.x) nhc <<= 1;
-  const int nslp = blockDim.x / nhc;                  // parallel slices
-  const int kk = tid % nhc, sl0 = tid / nhc;
+  int nhc = 1; while(nhc < nh && nhc < G) nhc <<= 1;
+  const int nslp = G / nhc;                           // parallel slices
+  const int kk = gt % nhc, sl0 = gt / nhc;
   const int npair = half + 1;
   const int nslice = (npair + HD_RESEED - 1) / HD_RESEED;
+  float* gpart = part + 2 * g * G;
 
   for(int k0 = 0; k0 < nh; k0 += nhc) {
     const int k = k0 + kk;                            // harmonic index (0-based), frequency (k+1) f0
@@ -220,19 +259,19 @@ __global__ void __launch_bounds__(HD_THREADS) harmonic_dft_kernel(HarmDftParams 
         const int n0 = sl * HD_RESEED, n1 = min(n0 + HD_RESEED, npair);
         float2 w = unit_phasor_turns(th * (double)n0);
         for(int n = n0; n < n1; n ++) {
-          const float2 s = sp[n];
-          re = fmaf(s.x, w.x, re);                    // sum (x+ + x-) cos
-          im = fmaf(-s.y, w.y, im);                   // -sum (x+ - x-) sin
+          const float2 sv = sp[n];
+          re = fmaf(sv.x, w.x, re);                   // sum (x+ + x-) cos
+          im = fmaf(-sv.y, w.y, im);                  // -sum (x+ - x-) sin
           w = cmul(w, z);
         }
       }
     }
     if(nslp > 1) {                                    // deterministic cross-slice reduction
-      __syncthreads();
-      part[2 * tid] = re; part[2 * tid + 1] = im;
-      __syncthreads();
+      gsync();
+      gpart[2 * gt] = re; gpart[2 * gt + 1] = im;
+      gsync();
       if(sl0 == 0) {
-        for(int q = 1; q < nslp; q ++) { re += part[2 * (q * nhc + kk)]; im += part[2 * (q * nhc + kk) + 1]; }
+        for(int q = 1; q < nslp; q ++) { re += gpart[2 * (q * nhc + kk)]; im += gpart[2 * (q * nhc + kk) + 1]; }
       }
     }
     if(sl0 == 0 && k < nh) {
@@ -247,22 +286,33 @@ __global__ void __launch_bounds__(HD_THREADS) harmonic_dft_kernel(HarmDftParams 
       P.phse[fidx * P.maxnhar + k] = atan2f(dim, dre);
     }
   }
-  for(int k = nh + tid; k < P.maxnhar; k += blockDim.x) { P.ampl[fidx * P.maxnhar + k] = 0; P.phse[fidx * P.maxnhar + k] = 0; }
-  if(tid == 0) P.nhar_out[fidx] = nh;
+  for(int k = nh + gt; k < P.maxnhar; k += G) { P.ampl[fidx * P.maxnhar + k] = 0; P.phse[fidx * P.maxnhar + k] = 0; }
+  if(gt == 0) P.nhar_out[fidx] = nh;
 }
 
-static inline size_t harm_dft_smem(int max_half) {
-  return (size_t)(max_half + 2) * 8 + HD_THREADS * 8 + 2 * HD_THREADS * 4 + 16;
+static inline size_t harm_dft_smem(int max_half, int ng) {
+  return (size_t)((max_half + 3) & ~1) * 4 + HD_THREADS * 8 + 2 * HD_THREADS * 4 + (size_t)ng * (max_half + 2) * 8 + 16;
 }
 
 static inline int launch_harmonic_dft(const HarmDftParams& P, int nutt, cudaStream_t st) {
-  dim3 grid(P.nfrm, nutt * P.nsig), block(HD_THREADS);
-  size_t smem = harm_dft_smem(P.max_half);
+  const bool warp_groups = P.nsig > 1 && P.maxnhar <= 32;
+  const int ng = warp_groups ? HD_THREADS / 32 : 1;
+  dim3 grid(P.nfrm, nutt * ((P.nsig + ng - 1) / ng)), block(HD_THREADS);
+  size_t smem = harm_dft_smem(P.max_half, ng);
   if(smem > 200 * 1024) return -1;
+  if(warp_groups) {
+    auto kfn = harmonic_dft_kernel<32>;
 #ifndef LLSM_EMU
-  cudaFuncSetAttribute(harmonic_dft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 #endif
-  LLSM_LAUNCH(harmonic_dft_kernel, grid, block, smem, st, P);
+    LLSM_LAUNCH(kfn, grid, block, smem, st, P);
+  } else {
+    auto kfn = harmonic_dft_kernel<HD_THREADS>;
+#ifndef LLSM_EMU
+    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#endif
+    LLSM_LAUNCH(kfn, grid, block, smem, st, P);
+  }
   return 0;
 }
 
@@ -377,28 +427,28 @@ __global__ void __launch_bounds__(NS_THREADS) noise_spec_kernel(NoiseSpecParams 
         }
       }
     }
-    bufa[kb] = make_float2(acc[0], acc[1]);
+    bufa[fsw(kb)] = make_float2(acc[0], acc[1]);
   }
   __syncthreads();
-  float2* X = block_fft<false>(bufa, bufb, P.lg_nfft_s, P.tw_s, nfs);
+  float2* X = block_fft<false, true>(bufa, bufb, P.lg_nfft_s, P.tw_s, nfs);
   float2* Y = (X == bufa) ? bufb : bufa;
   {
     float nrm[2];
 #pragma unroll
     for(int h = 0; h < 2; h ++) { float t = 1024.0f / P.std_norm; nrm[h] = t / (float)wsv[h]; }   // dsputils.c:111
     for(int k = tid; k <= nfs / 2; k += nth) {
-      const float2 zk = X[k], zn = X[(nfs - k) & (nfs - 1)];
+      const float2 zk = X[fsw(k)], zn = X[fsw((nfs - k) & (nfs - 1))];
       // A = (Zk + conj Zn) / 2, B = (Zk - conj Zn) / (2 i)
       const float ar = 0.5f * (zk.x + zn.x), ai = 0.5f * (zk.y - zn.y);
       const float br = 0.5f * (zk.y + zn.y), bi = -0.5f * (zk.x - zn.x);
       float ma = sqrtf(ar * ar + ai * ai) * nrm[0], mb = sqrtf(br * br + bi * bi) * nrm[1];
       const float2 lg = make_float2(logf(ma > 1e-10f ? ma : 1e-10f), logf(mb > 1e-10f ? mb : 1e-10f));
-      Y[k] = lg;
-      if(k > 0 && k < nfs / 2) Y[nfs - k] = lg;
+      Y[fsw(k)] = lg;
+      if(k > 0 && k < nfs / 2) Y[fsw(nfs - k)] = lg;
     }
   }
   __syncthreads();
-  float2* Cq = block_fft<true>(Y, X, P.lg_nfft_s, P.tw_s, nfs);      // cepstra * nfft (real, even)
+  float2* Cq = block_fft<true, true>(Y, X, P.lg_nfft_s, P.tw_s, nfs);      // cepstra * nfft (real, even)
   float2* D = (Cq == bufa) ? bufb : bufa;
   {
     float f0s[2];
@@ -406,7 +456,7 @@ __global__ void __launch_bounds__(NS_THREADS) noise_spec_kernel(NoiseSpecParams 
     for(int h = 0; h < 2; h ++) f0s[h] = (f0v[h] == 0 ? 200.0f : f0v[h]) / P.fs;   // layer0.c:338
     const float inv = 1.0f / (float)nfs;
     for(int q = tid; q <= nfs / 2; q += nth) {
-      const float2 c = Cq[q];
+      const float2 c = Cq[fsw(q)];
       float cv[2] = {c.x, c.y};
 #pragma unroll
       for(int h = 0; h < 2; h ++) {
@@ -420,15 +470,15 @@ __global__ void __launch_bounds__(NS_THREADS) noise_spec_kernel(NoiseSpecParams 
         cv[h] = cv[h] * inv * sinc * (1.18f - 0.18f * c2);
       }
       const float2 d = make_float2(cv[0], cv[1]);
-      D[q] = d;
-      if(q > 0 && q < nfs / 2) D[nfs - q] = d;
+      D[fsw(q)] = d;
+      if(q > 0 && q < nfs / 2) D[fsw(nfs - q)] = d;
     }
   }
   __syncthreads();
-  float2* Ev = block_fft<false>(D, Cq, P.lg_nfft_s, P.tw_s, nfs);
+  float2* Ev = block_fft<false, true>(D, Cq, P.lg_nfft_s, P.tw_s, nfs);
   for(int j = tid; j < P.nspec; j += nth) {
     int idx = j * nfs / P.nfft;                                       // layer0.c:341-342
-    const float2 e = Ev[idx];
+    const float2 e = Ev[fsw(idx)];
     P.env[orow + j] = e.x * 2.0f;
     if(two) P.env[orow + P.nspec + j] = e.y * 2.0f;
   }
@@ -445,12 +495,12 @@ __global__ void __launch_bounds__(NS_THREADS) noise_spec_kernel(NoiseSpecParams 
       idx = cen[1] + j - P.nwin / 2;
       if(two && idx >= 0 && idx < P.nx) v1 = w * xr[idx];
     }
-    bufa[j] = make_float2(v0, v1);
+    bufa[fsw(j)] = make_float2(v0, v1);
   }
   __syncthreads();
-  float2* Z = block_fft<false>(bufa, bufb, P.lg_nfft, P.tw_p, P.nfft);
+  float2* Z = block_fft<false, true>(bufa, bufb, P.lg_nfft, P.tw_p, P.nfft);
   for(int j = tid; j < P.nspec; j += nth) {
-    const float2 zk = Z[j], zn = Z[(P.nfft - j) & (P.nfft - 1)];
+    const float2 zk = Z[fsw(j)], zn = Z[fsw((P.nfft - j) & (P.nfft - 1))];
     const float ar = 0.5f * (zk.x + zn.x), ai = 0.5f * (zk.y - zn.y);
     const float br = 0.5f * (zk.y + zn.y), bi = -0.5f * (zk.x - zn.x);
     float pa = __fadd_rn(__fmul_rn(ar, ar), __fmul_rn(ai, ai)) / P.win_power;
