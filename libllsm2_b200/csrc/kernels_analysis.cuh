@@ -226,16 +226,21 @@ __global__ void __launch_bounds__(HD_THREADS) harmonic_dft_kernel(HarmDftParams 
   const float winsum = (float)red[0];                 // FP_TYPE winsum = sumfp(w, nx)
   if(! live) return;                                  // (no block barrier below for G == 32)
 
-  // ---- stage the windowed frame of this group's signal as symmetric / antisymmetric halves
-  float2* sp = spall + (size_t)g * (P.max_half + 2);
-  for(int n = gt; n <= half; n += G) {
+  // ---- the windowed frame as symmetric / antisymmetric halves: staged in shared memory when the CTA
+  //      serves one signal; read straight from global memory (L1/L2-resident, a handful of harmonics) by
+  //      the warp-per-signal variant, whose shared memory only holds the window
+  auto pair_at = [&](int n) -> float2 {
     const float w = wv[n];
     float xp = 0, xm = 0;
     if(n < half) { int idx = center + n; if(idx >= 0 && idx < P.nx) xp = w * x[idx]; }
     if(n >= 1) { int idx = center - n; if(idx >= 0 && idx < P.nx) xm = w * x[idx]; }
-    sp[n] = make_float2(xp + xm, xp - xm);
+    return make_float2(xp + xm, xp - xm);
+  };
+  float2* sp = spall;
+  if(G != 32) {
+    for(int n = gt; n <= half; n += G) sp[n] = pair_at(n);
+    gsync();
   }
-  gsync();
 
   // ---- frequencies as the reference rounds them (dsputils.c:156-158)
   const float omega0 = (float)(2.0 * LLSM_PI * (double)f0 / (double)P.fs);   // czt step (FP_TYPE arg)
@@ -259,7 +264,7 @@ __global__ void __launch_bounds__(HD_THREADS) harmonic_dft_kernel(HarmDftParams 
         const int n0 = sl * HD_RESEED, n1 = min(n0 + HD_RESEED, npair);
         float2 w = unit_phasor_turns(th * (double)n0);
         for(int n = n0; n < n1; n ++) {
-          const float2 sv = sp[n];
+          const float2 sv = G != 32 ? sp[n] : pair_at(n);
           re = fmaf(sv.x, w.x, re);                   // sum (x+ + x-) cos
           im = fmaf(-sv.y, w.y, im);                  // -sum (x+ - x-) sin
           w = cmul(w, z);
@@ -291,7 +296,7 @@ __global__ void __launch_bounds__(HD_THREADS) harmonic_dft_kernel(HarmDftParams 
 }
 
 static inline size_t harm_dft_smem(int max_half, int ng) {
-  return (size_t)((max_half + 3) & ~1) * 4 + HD_THREADS * 8 + 2 * HD_THREADS * 4 + (size_t)ng * (max_half + 2) * 8 + 16;
+  return (size_t)((max_half + 3) & ~1) * 4 + HD_THREADS * 8 + 2 * HD_THREADS * 4 + (ng > 1 ? 0 : (size_t)(max_half + 2) * 8) + 16;
 }
 
 static inline int launch_harmonic_dft(const HarmDftParams& P, int nutt, cudaStream_t st) {
