@@ -135,6 +135,7 @@ struct HarmDftParams {
 
 #define HD_THREADS 128
 #define HD_RESEED 64
+#define HD_KW 8           // harmonics per signal in the warp-per-signal variant
 
 // G = threads that share one signal: HD_THREADS (one signal per CTA: the main pass) or 32 (one warp per
 // signal, HD_THREADS / 32 signals of the same frame per CTA: the sub-band envelope pass, where the window,
@@ -246,49 +247,86 @@ __global__ void __launch_bounds__(HD_THREADS) harmonic_dft_kernel(HarmDftParams 
   const float omega0 = (float)(2.0 * LLSM_PI * (double)f0 / (double)P.fs);   // czt step (FP_TYPE arg)
   const double nu = (double)omega0 / (2.0 * LLSM_PI);                        // turns per sample
 
-  // work split: nhc harmonics across threads, nsl sample slices across the remaining factor
-  int nhc = 1; while(nhc < nh && nhc < G) nhc <<= 1;
-  const int nslp = G / nhc;                           // parallel slices
-  const int kk = gt % nhc, sl0 = gt / nhc;
   const int npair = half + 1;
-  const int nslice = (npair + HD_RESEED - 1) / HD_RESEED;
-  float* gpart = part + 2 * g * G;
+  auto finish = [&](int k, float re, float im) {
+    // residual of the reference's float-rounded centre shift (dsputils.c:158-162):
+    // ishift = (float)(shift * 2 pi f0 / fs * (k + 1)) versus (k + 1) * omega0 * shift
+    float ishift = (float)((double)half * 2.0 * LLSM_PI * (double)f0 / (double)P.fs * ((double)k + 1.0));
+    double eps = (double)ishift - (double)(k + 1) * (double)omega0 * (double)half;
+    float se = (float)sin(eps), ce = (float)cos(eps);
+    float dre = re * ce - im * se, dim = re * se + im * ce;
+    float a = (float)(sqrt((double)(dre * dre + dim * dim)) * 2.0 / (double)winsum);
+    P.ampl[fidx * P.maxnhar + k] = a;
+    P.phse[fidx * P.maxnhar + k] = atan2f(dim, dre);
+  };
 
-  for(int k0 = 0; k0 < nh; k0 += nhc) {
-    const int k = k0 + kk;                            // harmonic index (0-based), frequency (k+1) f0
-    float re = 0.f, im = 0.f;
-    if(k < nh) {
-      const double th = (double)(k + 1) * nu;
-      const float2 z = unit_phasor_turns(th);
-      for(int sl = sl0; sl < nslice; sl += nslp) {
-        const int n0 = sl * HD_RESEED, n1 = min(n0 + HD_RESEED, npair);
-        float2 w = unit_phasor_turns(th * (double)n0);
-        for(int n = n0; n < n1; n ++) {
-          const float2 sv = G != 32 ? sp[n] : pair_at(n);
-          re = fmaf(sv.x, w.x, re);                   // sum (x+ + x-) cos
-          im = fmaf(-sv.y, w.y, im);                  // -sum (x+ - x-) sin
-          w = cmul(w, z);
+  if(G == 32) {
+    // ---- a warp per signal, at most HD_KW harmonics: every lane walks its own samples (coalesced reads)
+    //      carrying one phasor per harmonic, advanced 32 samples at a time and re-seeded every 8 steps
+    float2 w[HD_KW], z32[HD_KW]; float re[HD_KW], im[HD_KW];
+#pragma unroll
+    for(int k = 0; k < HD_KW; k ++) {
+      re[k] = 0.f; im[k] = 0.f;
+      z32[k] = k < nh ? unit_phasor_turns((double)(k + 1) * nu * 32.0) : make_float2(1.f, 0.f);
+    }
+    int step = 0;
+    for(int n = gt; n < npair; n += 32, step ++) {
+      if((step & 7) == 0) {
+#pragma unroll
+        for(int k = 0; k < HD_KW; k ++) if(k < nh) w[k] = unit_phasor_turns((double)(k + 1) * nu * (double)n);
+      }
+      const float2 sv = pair_at(n);
+#pragma unroll
+      for(int k = 0; k < HD_KW; k ++) if(k < nh) {
+        re[k] = fmaf(sv.x, w[k].x, re[k]);
+        im[k] = fmaf(-sv.y, w[k].y, im[k]);
+        w[k] = cmul(w[k], z32[k]);
+      }
+    }
+    float myre = 0.f, myim = 0.f;
+#pragma unroll
+    for(int k = 0; k < HD_KW; k ++) {
+      float r = re[k], q = im[k];
+      for(int o = 16; o > 0; o >>= 1) { r += __shfl_xor_sync(0xffffffffu, r, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+      if(gt == k) { myre = r; myim = q; }
+    }
+    if(gt < nh) finish(gt, myre, myim);
+  } else {
+    // work split: nhc harmonics across threads, nsl sample slices across the remaining factor
+    int nhc = 1; while(nhc < nh && nhc < G) nhc <<= 1;
+    const int nslp = G / nhc;                           // parallel slices
+    const int kk = gt % nhc, sl0 = gt / nhc;
+    const int nslice = (npair + HD_RESEED - 1) / HD_RESEED;
+    float* gpart = part + 2 * g * G;
+
+    for(int k0 = 0; k0 < nh; k0 += nhc) {
+      const int k = k0 + kk;                            // harmonic index (0-based), frequency (k+1) f0
+      float re = 0.f, im = 0.f;
+      if(k < nh) {
+        const double th = (double)(k + 1) * nu;
+        const float2 z = unit_phasor_turns(th);
+        for(int sl = sl0; sl < nslice; sl += nslp) {
+          const int n0 = sl * HD_RESEED, n1 = min(n0 + HD_RESEED, npair);
+          float2 w = unit_phasor_turns(th * (double)n0);
+          for(int n = n0; n < n1; n ++) {
+            const float2 sv = G != 32 ? sp[n] : pair_at(n);
+            re = fmaf(sv.x, w.x, re);                   // sum (x+ + x-) cos
+            im = fmaf(-sv.y, w.y, im);                  // -sum (x+ - x-) sin
+            w = cmul(w, z);
+          }
         }
       }
-    }
-    if(nslp > 1) {                                    // deterministic cross-slice reduction
-      gsync();
-      gpart[2 * gt] = re; gpart[2 * gt + 1] = im;
-      gsync();
-      if(sl0 == 0) {
-        for(int q = 1; q < nslp; q ++) { re += gpart[2 * (q * nhc + kk)]; im += gpart[2 * (q * nhc + kk) + 1]; }
+      if(nslp > 1) {                                    // deterministic cross-slice reduction
+        gsync();
+        gpart[2 * gt] = re; gpart[2 * gt + 1] = im;
+        gsync();
+        if(sl0 == 0) {
+          for(int q = 1; q < nslp; q ++) { re += gpart[2 * (q * nhc + kk)]; im += gpart[2 * (q * nhc + kk) + 1]; }
+        }
       }
-    }
-    if(sl0 == 0 && k < nh) {
-      // residual of the reference's float-rounded centre shift (dsputils.c:158-162):
-      // ishift = (float)(shift * 2 pi f0 / fs * (k + 1)) versus (k + 1) * omega0 * shift
-      float ishift = (float)((double)half * 2.0 * LLSM_PI * (double)f0 / (double)P.fs * ((double)k + 1.0));
-      double eps = (double)ishift - (double)(k + 1) * (double)omega0 * (double)half;
-      float se = (float)sin(eps), ce = (float)cos(eps);
-      float dre = re * ce - im * se, dim = re * se + im * ce;
-      float a = (float)(sqrt((double)(dre * dre + dim * dim)) * 2.0 / (double)winsum);
-      P.ampl[fidx * P.maxnhar + k] = a;
-      P.phse[fidx * P.maxnhar + k] = atan2f(dim, dre);
+      if(sl0 == 0 && k < nh) {
+        finish(k, re, im);
+      }
     }
   }
   for(int k = nh + gt; k < P.maxnhar; k += G) { P.ampl[fidx * P.maxnhar + k] = 0; P.phse[fidx * P.maxnhar + k] = 0; }
@@ -300,7 +338,7 @@ static inline size_t harm_dft_smem(int max_half, int ng) {
 }
 
 static inline int launch_harmonic_dft(const HarmDftParams& P, int nutt, cudaStream_t st) {
-  const bool warp_groups = P.nsig > 1 && P.maxnhar <= 32;
+  const bool warp_groups = P.nsig > 1 && P.maxnhar <= HD_KW;
   const int ng = warp_groups ? HD_THREADS / 32 : 1;
   dim3 grid(P.nfrm, nutt * ((P.nsig + ng - 1) / ng)), block(HD_THREADS);
   size_t smem = harm_dft_smem(P.max_half, ng);
