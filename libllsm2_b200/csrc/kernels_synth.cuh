@@ -667,8 +667,9 @@ __global__ void __launch_bounds__(SHW_THREADS, 2) noise_shape_warp_kernel(ShapeP
   float2* tw2 = (float2*)smem;                                   // [1024]
   char* wbase = (char*)(tw2 + 1024);
   float* acc = (float*)(wbase + SHW_WARPS * WFFT_SCRATCH_BYTES); // [seg]
-  int* fcen = (int*)(acc + P.seg);                               // [2 * SHW_WARPS] centre, -1 = none
-  float2* z0 = (float2*)(fcen + 2 * SHW_WARPS) + 32 * (threadIdx.x >> 5);   // [SHW_WARPS][32]
+  int* fcen = (int*)(acc + P.seg);                               // [2 * SHW_WARPS] frame centres of the round
+  int* fval = fcen + 2 * SHW_WARPS;                              // [2 * SHW_WARPS] frame produced output
+  float2* z0 = (float2*)(fval + 2 * SHW_WARPS) + 32 * (threadIdx.x >> 5);   // [SHW_WARPS][32]
 
   const int b = blockIdx.y;
   const int oa = blockIdx.x * P.seg;
@@ -794,7 +795,13 @@ __global__ void __launch_bounds__(SHW_THREADS, 2) noise_shape_warp_kernel(ShapeP
               if(t < 16) {
                 int l = max(0, kk - 3), u = min(NSPEC - 1, kk + 3);
                 float smA = 0.f, smB = 0.f;
-                for(int q = l; q <= u; q ++) { smA += pbuf[q]; smB += pbuf[NSPEC + q]; }
+                if(kk >= 3 && kk + 3 <= NSPEC - 1) {         // interior bins: fixed 7-tap sum, same order
+                  const float* pa = pbuf + kk - 3; const float* pb = pbuf + NSPEC + kk - 3;
+#pragma unroll
+                  for(int q = 0; q < 7; q ++) { smA += pa[q]; smB += pb[q]; }
+                } else {
+                  for(int q = l; q <= u; q ++) { smA += pbuf[q]; smB += pbuf[NSPEC + q]; }
+                }
                 const float rc = psc / (float)(u - l + 1);
                 int pl = P.psd_lo[kk]; float pr = P.psd_r[kk];
                 float hA = spsd[pl], hB = hasB ? spsd[npsd + pl] : 0.f;
@@ -854,24 +861,33 @@ __global__ void __launch_bounds__(SHW_THREADS, 2) noise_shape_warp_kernel(ShapeP
         }
       }
     }
-    if(lane == 0) { fcen[2 * warp] = doA ? cA : -(1 << 30); fcen[2 * warp + 1] = doB ? cB : -(1 << 30); }
+    // slot table of the round: centre of every frame (ascending) and whether it produced output
+    if(lane == 0) {
+      fcen[2 * warp] = hasA ? cA : (1 << 30); fcen[2 * warp + 1] = hasB ? cB : (1 << 30);
+      fval[2 * warp] = doA; fval[2 * warp + 1] = doB;
+    }
     __syncthreads();
-    // ---- add the round's frames to the output run, ascending frame order (layer0.c:620-624)
+    // ---- add the round's frames to the output run, ascending frame order (layer0.c:620-624). Centres are
+    //      about one hop apart, so a sample is reached by at most NF / hop + 1 consecutive slots: start from
+    //      an arithmetic guess of the first one instead of testing all sixteen.
     {
-      int first = -(1 << 30), last = -(1 << 30);
-      for(int f = 0; f < 2 * SHW_WARPS; f ++) if(fcen[f] > -(1 << 29)) { if(first < -(1 << 29)) first = fcen[f]; last = fcen[f]; }
-      if(first > -(1 << 29)) {
-        int s0 = max(oa, first - HALF), s1 = min(min(ob, ny_b), last + HALF);
-        for(int n = s0 + tid; n < s1; n += blockDim.x) {
-          float a = acc[n - oa];
-          for(int f = 0; f < 2 * SHW_WARPS; f ++) {
-            int c = fcen[f];
-            int j = n - c + HALF;
-            if(c > -(1 << 29) && j >= 0 && j < NF)
-              a += ((const float*)(wbase + (f >> 1) * WFFT_SCRATCH_BYTES))[(f & 1) * 1024 + j];
-          }
-          acc[n - oa] = a;
+      const int nslot = min(2 * SHW_WARPS, ib - r0);
+      const int first = fcen[0], last = fcen[nslot - 1];
+      const float inv_hop = nslot > 1 ? (float)(nslot - 1) / (float)(last - first) : 0.f;
+      int s0 = max(oa, first - HALF), s1 = min(min(ob, ny_b), last + HALF);
+      for(int n = s0 + tid; n < s1; n += blockDim.x) {
+        float a = acc[n - oa];
+        // first slot whose frame can still reach n: centre > n - HALF
+        int f = (int)((float)(n - HALF - first) * inv_hop) - 2;
+        if(f < 0) f = 0;
+        while(f < nslot && fcen[f] + HALF <= n) f ++;
+        for(; f < nslot; f ++) {
+          const int c = fcen[f];
+          const int j = n - c + HALF;
+          if(j < 0) break;                         // this and all later frames start after n
+          if(fval[f]) a += ((const float*)(wbase + (f >> 1) * WFFT_SCRATCH_BYTES))[(f & 1) * 1024 + j];
         }
+        acc[n - oa] = a;
       }
     }
     __syncthreads();
@@ -885,7 +901,7 @@ __global__ void __launch_bounds__(SHW_THREADS, 2) noise_shape_warp_kernel(ShapeP
 }
 
 static inline size_t shape_warp_smem_bytes(int seg) {
-  return (size_t)1024 * 8 + (size_t)SHW_WARPS * WFFT_SCRATCH_BYTES + (size_t)seg * 4 + 2 * SHW_WARPS * 4 +
+  return (size_t)1024 * 8 + (size_t)SHW_WARPS * WFFT_SCRATCH_BYTES + (size_t)seg * 4 + 4 * SHW_WARPS * 4 +
          (size_t)SHW_WARPS * 32 * 8 + 16;
 }
 
