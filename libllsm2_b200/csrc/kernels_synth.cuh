@@ -282,6 +282,8 @@ struct ExcParams {
 };
 
 #define EXC_THREADS 256
+#define EXC_SPT 2                       // output samples per thread
+#define EXC_TILE (EXC_THREADS * EXC_SPT)
 #define EXC_FCHUNK 8
 
 // stretch_stationary_noise (dsputils.c:363-383) as a closed-form index map: output position p reads
@@ -319,10 +321,12 @@ template <int MAXCH>
 __global__ void __launch_bounds__(EXC_THREADS) noise_excitation_kernel(ExcParams P) {
   LLSM_DYN_SMEM(smem);
   const int b = blockIdx.y;
-  const int p0 = blockIdx.x * EXC_THREADS;
-  const int p = p0 + (int)threadIdx.x;
-  if(P.samp_hi > 0 && (p0 + EXC_THREADS <= P.samp_lo || p0 >= P.samp_hi)) {   // CTA outside the shard (uniform)
-    if(p < P.nsamp) P.y_exc[(size_t)blockIdx.y * P.stride + p] = 0.f;
+  const int p0 = blockIdx.x * EXC_TILE;
+  if(P.samp_hi > 0 && (p0 + EXC_TILE <= P.samp_lo || p0 >= P.samp_hi)) {   // CTA outside the shard (uniform)
+    for(int q = 0; q < EXC_SPT; q ++) {
+      const int p = p0 + q * EXC_THREADS + (int)threadIdx.x;
+      if(p < P.nsamp) P.y_exc[(size_t)blockIdx.y * P.stride + p] = 0.f;
+    }
     return;
   }
   const int nf = P.nfrm_utt ? P.nfrm_utt[b] : P.nfrm;
@@ -336,7 +340,7 @@ __global__ void __launch_bounds__(EXC_THREADS) noise_excitation_kernel(ExcParams
   // (two binary searches, done once per CTA)
   __shared__ int s_range[2];
   if(threadIdx.x == 0) {
-    const int pend = p0 + EXC_THREADS - 1;
+    const int pend = p0 + EXC_TILE - 1;
     int lo = 0, hi = nf;
     while(lo < hi) { int mid = (lo + hi) >> 1; if(P.env_off[mid] + P.n_env + 1 > p0) hi = mid; else lo = mid + 1; }
     s_range[0] = lo;
@@ -347,9 +351,11 @@ __global__ void __launch_bounds__(EXC_THREADS) noise_excitation_kernel(ExcParams
   __syncthreads();
   const int ia = s_range[0], ib = s_range[1];      // frames [ia, ib)
 
-  float env[MAXCH];
+  float env[EXC_SPT][MAXCH];
 #pragma unroll
-  for(int c = 0; c < MAXCH; c ++) env[c] = 0.f;
+  for(int q = 0; q < EXC_SPT; q ++)
+#pragma unroll
+    for(int c = 0; c < MAXCH; c ++) env[q][c] = 0.f;
   const int half = P.n_env / 2;
 
   for(int i0 = ia; i0 < ib; i0 += EXC_FCHUNK) {
@@ -384,6 +390,9 @@ __global__ void __launch_bounds__(EXC_THREADS) noise_excitation_kernel(ExcParams
       fr[e] = v;
     }
     __syncthreads();
+#pragma unroll
+    for(int q = 0; q < EXC_SPT; q ++) {
+    const int p = p0 + q * EXC_THREADS + (int)threadIdx.x;
     if(p < P.nsamp && p < ny_b) {
       for(int fi = 0; fi < nfc; fi ++) {
         const float* F = fr + fi * fstride;
@@ -418,13 +427,17 @@ __global__ void __launch_bounds__(EXC_THREADS) noise_excitation_kernel(ExcParams
           for(int c = 0; c < MAXCH; c ++) if(c < nch) {
             float v = hs[c] + F[4 + c * (2 + 2 * mne)];
             if(! (v > 1e-8f)) v = 1e-8f;                     // layer0.c:304
-            env[c] += v * wj;                                // layer0.c:306,309
+            env[q][c] += v * wj;                             // layer0.c:306,309
           }
         }
       }
     }
+    }
   }
 
+#pragma unroll
+  for(int q = 0; q < EXC_SPT; q ++) {
+  const int p = p0 + q * EXC_THREADS + (int)threadIdx.x;
   if(p < P.nsamp) {
     float y = 0.f;
     if(p < ny_b) {
@@ -433,11 +446,12 @@ __global__ void __launch_bounds__(EXC_THREADS) noise_excitation_kernel(ExcParams
       for(int c = 0; c < MAXCH; c ++) if(c < nch && ((P.chan_mask >> c) & 1u)) {
         const float* tp = P.colored + ((size_t)b * nch + c) * P.tstride;
         float x = stretched_value(tp, si);
-        x = x * sqrtf(env[c]);                               // layer0.c:548
+        x = x * sqrtf(env[q][c]);                            // layer0.c:548
         y += x;                                              // layer0.c:549
       }
     }
     P.y_exc[(size_t)b * P.stride + p] = y;
+  }
   }
 }
 
@@ -446,7 +460,7 @@ static inline size_t exc_smem_bytes(int nchannel, int maxnhar_e) {
 }
 
 static inline int launch_noise_excitation(const ExcParams& P, int nutt, cudaStream_t st) {
-  dim3 grid((P.nsamp + EXC_THREADS - 1) / EXC_THREADS, nutt), block(EXC_THREADS);
+  dim3 grid((P.nsamp + EXC_TILE - 1) / EXC_TILE, nutt), block(EXC_THREADS);
   size_t smem = exc_smem_bytes(P.nchannel, P.maxnhar_e);
   if(smem > 200 * 1024) return -1;
 #ifndef LLSM_EMU
@@ -712,7 +726,17 @@ __global__ void __launch_bounds__(SHW_THREADS, 2) noise_shape_warp_kernel(ShapeP
       float mxA = -3.0e38f, mxB = -3.0e38f;
       const float* psdA = P.psd + (row + i) * (size_t)npsd;
       const float* psdB = P.psd + (row + i + (hasB ? 1 : 0)) * (size_t)npsd;
-      for(int j = lane; j < npsd; j += 32) { mxA = fmaxf(mxA, psdA[j]); if(hasB) mxB = fmaxf(mxB, psdB[j]); }
+      for(int j0 = 0; j0 < npsd; j0 += 256) {
+        float pa[8], pb[8];
+#pragma unroll
+        for(int u = 0; u < 8; u ++) {
+          const int j = j0 + lane + 32 * u;
+          pa[u] = j < npsd ? psdA[j] : -3.0e38f;
+          pb[u] = (hasB && j < npsd) ? psdB[j] : -3.0e38f;
+        }
+#pragma unroll
+        for(int u = 0; u < 8; u ++) { mxA = fmaxf(mxA, pa[u]); mxB = fmaxf(mxB, pb[u]); }
+      }
       for(int o = 16; o > 0; o >>= 1) {
         mxA = fmaxf(mxA, __shfl_xor_sync(0xffffffffu, mxA, o));
         mxB = fmaxf(mxB, __shfl_xor_sync(0xffffffffu, mxB, o));
@@ -728,18 +752,21 @@ __global__ void __launch_bounds__(SHW_THREADS, 2) noise_shape_warp_kernel(ShapeP
         if(pass == 0) {
           // ---- load the two windowed frames (layer0.c:588-592) through shared memory (rolled loop:
           //      small code), then pick element j = lane + 32 r into register r
+          //      (eight iterations in flight: the loop is bound by the latency of the excitation reads)
 #pragma unroll 1
-          for(int r = 0; r < 32; r ++) {
-            int j = lane + 32 * r;
-            int jj = j - HALF + hw;
-            float va = 0.f, vb = 0.f;
-            if(jj >= 0 && jj < P.n_ns) {
-              float w = P.win[jj];
-              int ia2 = cA + jj - hw, ib2 = cB + jj - hw;
-              if(doA && ia2 >= 0 && ia2 < ny_b) va = exc[ia2] * w;
-              if(doB && ib2 >= 0 && ib2 < ny_b) vb = exc[ib2] * w;
+          for(int r0 = 0; r0 < 32; r0 += 8) {
+            float va[8], vb[8], wv[8];
+#pragma unroll
+            for(int u = 0; u < 8; u ++) {
+              const int jj = lane + 32 * (r0 + u) - HALF + hw;
+              const bool in = jj >= 0 && jj < P.n_ns;
+              const int ia2 = cA + jj - hw, ib2 = cB + jj - hw;
+              wv[u] = in ? P.win[jj] : 0.f;
+              va[u] = (in && doA && ia2 >= 0 && ia2 < ny_b) ? exc[ia2] : 0.f;
+              vb[u] = (in && doB && ib2 >= 0 && ib2 < ny_b) ? exc[ib2] : 0.f;
             }
-            scratch[j] = make_float2(va, vb);
+#pragma unroll
+            for(int u = 0; u < 8; u ++) scratch[lane + 32 * (r0 + u)] = make_float2(va[u] * wv[u], vb[u] * wv[u]);
           }
           __syncwarp();
 #pragma unroll
@@ -777,10 +804,21 @@ __global__ void __launch_bounds__(SHW_THREADS, 2) noise_shape_warp_kernel(ShapeP
             if(h == 1 && ! hasB) break;
             const float* psd = P.psd + (row + i + h) * (size_t)npsd;
             const float* res = P.psdres ? P.psdres + (row + i + h) * (size_t)npsd : nullptr;
-            for(int j = lane; j < npsd; j += 32) {
-              float v = psd[j];
-              if(res) v = (float)((double)v + ((double)res[j] - resbias));
-              spsd[h * npsd + j] = v;
+            for(int j0 = 0; j0 < npsd; j0 += 256) {          // eight reads per array in flight
+              float pv[8], rv[8];
+#pragma unroll
+              for(int u = 0; u < 8; u ++) {
+                const int j = j0 + lane + 32 * u;
+                pv[u] = j < npsd ? psd[j] : 0.f;
+                rv[u] = (res && j < npsd) ? res[j] : 0.f;
+              }
+#pragma unroll
+              for(int u = 0; u < 8; u ++) {
+                const int j = j0 + lane + 32 * u;
+                float v = pv[u];
+                if(res) v = (float)((double)v + ((double)rv[u] - resbias));
+                if(j < npsd) spsd[h * npsd + j] = v;
+              }
             }
           }
           __syncwarp();
@@ -877,15 +915,17 @@ __global__ void __launch_bounds__(SHW_THREADS, 2) noise_shape_warp_kernel(ShapeP
       int s0 = max(oa, first - HALF), s1 = min(min(ob, ny_b), last + HALF);
       for(int n = s0 + tid; n < s1; n += blockDim.x) {
         float a = acc[n - oa];
-        // first slot whose frame can still reach n: centre > n - HALF
-        int f = (int)((float)(n - HALF - first) * inv_hop) - 2;
-        if(f < 0) f = 0;
-        while(f < nslot && fcen[f] + HALF <= n) f ++;
-        for(; f < nslot; f ++) {
-          const int c = fcen[f];
-          const int j = n - c + HALF;
-          if(j < 0) break;                         // this and all later frames start after n
-          if(fval[f]) a += ((const float*)(wbase + (f >> 1) * WFFT_SCRATCH_BYTES))[(f & 1) * 1024 + j];
+        // first slot whose frame can still reach n (centre > n - HALF), from the hop arithmetic, one slot
+        // early; NF / hop + 1 <= 6 frames cover a sample, so a fixed window of 8 slots holds them all
+        int f0 = (int)((float)(n - HALF - first) * inv_hop) - 1;
+        if(f0 < 0) f0 = 0;
+#pragma unroll
+        for(int df = 0; df < 8; df ++) {
+          const int f = f0 + df;
+          if(f < nslot) {
+            const int j = n - fcen[f] + HALF;
+            if(j >= 0 && j < NF && fval[f]) a += ((const float*)(wbase + (f >> 1) * WFFT_SCRATCH_BYTES))[(f & 1) * 1024 + j];
+          }
         }
         acc[n - oa] = a;
       }
