@@ -39,7 +39,7 @@ struct llsm_b200_ctx {
   // copy / compute pipeline of synthesize_l0_host: two slots of input and output staging
   cudaStream_t s_in = nullptr, s_out = nullptr;
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
-  DevBuf pin[2][12], pout[2][3];
+  DevBuf pin[2][12], pout[2][12];
   LaunchCounter lc;
   std::mutex mtx;
 };

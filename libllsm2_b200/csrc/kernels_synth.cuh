@@ -282,7 +282,7 @@ struct ExcParams {
 };
 
 #define EXC_THREADS 256
-#define EXC_SPT 2                       // output samples per thread
+#define EXC_SPT 1                       // output samples per thread (2 measured slower: 4.9 ms vs 3.1 ms at C2)
 #define EXC_TILE (EXC_THREADS * EXC_SPT)
 #define EXC_FCHUNK 8
 

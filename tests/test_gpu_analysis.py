@@ -70,6 +70,18 @@ def test_host_entry_matches_device(ctx):
         assert np.array_equal(a[k], b[k]), k
 
 
+@pytest.mark.parametrize("slices", ["1", "3"])
+def test_host_pipeline_is_slicing_invariant(ctx, slices, monkeypatch):
+    import libllsm2_b200 as L
+    fr, conf = S.synth_frames(5, 40, seed=16, nhar=80, maxnhar=80)
+    y, _, _ = S.ref_synthesize(fr, conf, seed=7)
+    a = _analyze_gpu(ctx, conf, np.ascontiguousarray(y), fr["f0"])
+    monkeypatch.setenv("LLSM_B200_HOST_SLICES", slices)
+    b = L.analyze_l0_host(ctx, conf, y, fr["f0"], want_residual=True)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+
+
 def test_analysis_synthesis_roundtrip(ctx):
     """analyse on the GPU, resynthesise on the GPU: the harmonic part must reproduce the oracle's own
     analysis->synthesis round trip (size-independent property: x ~ x_sin + x_res)."""
