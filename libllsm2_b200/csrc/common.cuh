@@ -132,6 +132,38 @@ __device__ float2* block_fft(float2* a, float2* b, int lg, const float2* __restr
 #undef FIX
 }
 
+// ---- warp-level tensor-core MMA, TF32 operands, FP32 accumulate -------------------------------------
+// D (16 x 8) += A (16 x 8, row) * B (8 x 8, col). Fragment ownership (g = lane / 4, t = lane % 4):
+//   a0 = A[g][t], a1 = A[g + 8][t], a2 = A[g][t + 4], a3 = A[g + 8][t + 4]
+//   b0 = B[t][g], b1 = B[t + 4][g]
+//   d0 = D[g][2t], d1 = D[g][2t + 1], d2 = D[g + 8][2t], d3 = D[g + 8][2t + 1]
+// Operands are FP32 bit patterns whose low 13 mantissa bits the tensor core ignores.
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const float (&a)[4], const float (&b)[2]) {
+#ifdef LLSM_EMU
+  static float sa[64][16][8], sb[64][8][8];           // per warp of the (single) running CTA
+  const int lane = threadIdx.x & 31, w = (threadIdx.x >> 5) & 63, g = lane >> 2, t = lane & 3;
+  auto tf = [](float v) { unsigned u; memcpy(&u, &v, 4); u &= 0xffffe000u; float r; memcpy(&r, &u, 4); return r; };
+  __syncwarp();
+  sa[w][g][t] = tf(a[0]); sa[w][g + 8][t] = tf(a[1]); sa[w][g][t + 4] = tf(a[2]); sa[w][g + 8][t + 4] = tf(a[3]);
+  sb[w][t][g] = tf(b[0]); sb[w][t + 4][g] = tf(b[1]);
+  __syncwarp();
+  for(int k = 0; k < 8; k ++) {
+    d[0] += sa[w][g][k] * sb[w][k][2 * t];     d[1] += sa[w][g][k] * sb[w][k][2 * t + 1];
+    d[2] += sa[w][g + 8][k] * sb[w][k][2 * t]; d[3] += sa[w][g + 8][k] * sb[w][k][2 * t + 1];
+  }
+#else
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+    : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+    : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])), "r"(__float_as_uint(a[3])),
+      "r"(__float_as_uint(b[0])), "r"(__float_as_uint(b[1])));
+#endif
+}
+// x = hi + lo with hi exactly representable in TF32 (truncation) and lo the exact remainder
+__device__ __forceinline__ void tf32_split(float x, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+  lo = x - hi;
+}
+
 // 2^ceil(e) as an exact integer (device pow() is only accurate to an ulp, and the reference
 // truncates pow(2, ceil(log2(x))) to int: layer0.c:201, dsputils.c:485)
 __host__ __device__ __forceinline__ int pow2_ceil(double e) {

@@ -131,6 +131,8 @@ struct HarmDftParams {
   float* ampl; float* phse; // [B][nfrm][nsig][maxnhar]
   int max_half;             // capacity of the staged half-frame (pairs)
   float* edc; float thop;   // optional: short-time mean of every signal, [B][nfrm][nsig]
+  int only_above_half;      // > 0: the direct kernel only serves frames whose half window exceeds this
+  int mma_cap_half;         // capacity (half window) of the tensor-core kernel's staging
 };
 
 #define HD_THREADS 128
@@ -200,6 +202,7 @@ __global__ void __launch_bounds__(HD_THREADS) harmonic_dft_kernel(HarmDftParams 
     if(live && gt == 0) P.nhar_out[fidx] = -1;
     return;
   }
+  if(P.only_above_half > 0 && half <= P.only_above_half) return;   // served by harmonic_mma_kernel
 
   // ---- Blackman window once per CTA. ws is even, so the periodic window is symmetric about m = half:
   //   w(half +- n) = 0.42 + 0.5 cos(2 pi n / ws) + 0.08 cos(4 pi n / ws).
@@ -333,11 +336,178 @@ __global__ void __launch_bounds__(HD_THREADS) harmonic_dft_kernel(HarmDftParams 
   if(gt == 0) P.nhar_out[fidx] = nh;
 }
 
+// ------------------------------------------------------------------------------------------
+// Tensor-core variant of the main pass (one signal, up to maxnhar harmonics per frame).
+// With the pair index n = 16 p + q the sums over the window factor into a small GEMM per frame:
+//   Re X_k =  sum_q [ cos(k w q) Ecc(k, q) - sin(k w q) Ecs(k, q) ],
+//   Im X_k = -sum_q [ cos(k w q) Ocs(k, q) + sin(k w q) Occ(k, q) ],
+//   E{c,s}(k, q) = sum_p e[16 p + q] {cos, sin}(16 k w p)   (same with o),
+// i.e. D[2K x 32] = A[2K x P] * B[P x 32]: A holds the stride-16 phasors (generated in the fragment
+// registers by rotation), B the windowed signal halves e | o (staged once in shared memory). TF32 tensor
+// cores with FP32 accumulation, each product as hi*hi + lo*hi + hi*lo (3xTF32) -- the dropped lo*lo
+// terms are 2^-20 relative. One warp owns tiles of 8 harmonics (16 rows: 8 cosine + 8 sine); the
+// q-phasors and the 16-term q-sum are the FP32 epilogue.
+// ------------------------------------------------------------------------------------------
+#define HM_THREADS 128
+#define HM_ROW 20                                     // float2 row stride of a staged p-row (16 used): conflict-free LDS.64
+
+__global__ void __launch_bounds__(HM_THREADS) harmonic_mma_kernel(HarmDftParams P) {
+  LLSM_DYN_SMEM(smem);
+  const int cap = P.mma_cap_half;
+  const int prow = (((cap + 1 + 15) / 16) + 7) & ~7;   // staged p-rows (multiple of 8)
+  float* wv = (float*)smem;                           // [cap + 2]
+  double* red = (double*)(wv + ((cap + 2 + 1) & ~1)); // [HM_THREADS]
+  float2* sph = (float2*)(red + HM_THREADS);          // [prow][HM_ROW] (e_hi, o_hi)
+  float2* spl = sph + (size_t)prow * HM_ROW;          // [prow][HM_ROW] (e_lo, o_lo)
+
+  const int i = blockIdx.x, b = blockIdx.y;
+  const int nf = P.nfrm_utt ? P.nfrm_utt[b] : P.nfrm;
+  const int tid = threadIdx.x;
+  const size_t fidx = (size_t)b * P.nfrm + i;
+  if(i >= nf) return;
+  const float f0 = P.f0[fidx];
+  if(! (f0 > 0)) {                                    // unvoiced: no harmonic model (layer0.c:106)
+    if(tid == 0) P.nhar_out[fidx] = 0;
+    for(int k = tid; k < P.maxnhar; k += HM_THREADS) { P.ampl[fidx * P.maxnhar + k] = 0; P.phse[fidx * P.maxnhar + k] = 0; }
+    return;
+  }
+  const int ws = ana_winsize(P.fs, f0, P.rel_winsize);
+  const int nh = ana_nhar(P.fs, f0, P.maxnhar);
+  const int half = ws >> 1;
+  if(half > P.max_half) { if(tid == 0) P.nhar_out[fidx] = -1; return; }
+  if(half > cap) return;                              // left to the direct kernel
+  const float* x = P.sig + (size_t)b * P.xstride;
+  const int center = P.center[i];
+
+  // ---- window (see harmonic_dft_kernel) and its sum
+  double wsum = 0;
+  {
+    double cs, sn, cstep, sstep;
+    sincospi(2.0 * (double)tid / (double)ws, &sn, &cs);
+    sincospi(2.0 * (double)HM_THREADS / (double)ws, &sstep, &cstep);
+    for(int n = tid; n <= half; n += HM_THREADS) {
+      const float w = (float)(0.42 + 0.5 * cs + 0.08 * (2.0 * cs * cs - 1.0));
+      wv[n] = w;
+      if(n < half) wsum += w;
+      if(n >= 1) wsum += w;
+      const double c2 = cs * cstep - sn * sstep;
+      sn = sn * cstep + cs * sstep; cs = c2;
+    }
+  }
+  red[tid] = wsum;
+  __syncthreads();
+  for(int o = HM_THREADS >> 1; o > 0; o >>= 1) { if(tid < o) red[tid] += red[tid + o]; __syncthreads(); }
+  const float winsum = (float)red[0];
+
+  // ---- stage e | o (symmetric / antisymmetric halves), split for 3xTF32, rows of 16 pairs
+  const int npair = half + 1;
+  const int np8 = (((npair + 15) / 16) + 7) & ~7;     // p-rows in use (multiple of 8, <= prow)
+  for(int n = tid; n < np8 * 16; n += HM_THREADS) {
+    float e = 0.f, o = 0.f;
+    if(n < npair) {
+      const float w = wv[n];
+      float xp = 0, xm = 0;
+      if(n < half) { int idx = center + n; if(idx >= 0 && idx < P.nx) xp = w * x[idx]; }
+      if(n >= 1) { int idx = center - n; if(idx >= 0 && idx < P.nx) xm = w * x[idx]; }
+      e = xp + xm; o = xp - xm;
+    }
+    float eh, el, oh, ol;
+    tf32_split(e, eh, el); tf32_split(o, oh, ol);
+    const int at = (n >> 4) * HM_ROW + (n & 15);
+    sph[at] = make_float2(eh, oh); spl[at] = make_float2(el, ol);
+  }
+  __syncthreads();
+
+  const float omega0 = (float)(2.0 * LLSM_PI * (double)f0 / (double)P.fs);   // czt step (FP_TYPE arg)
+  const double nu = (double)omega0 / (2.0 * LLSM_PI);                        // turns per sample
+  const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int nsteps = np8 >> 3;
+
+  for(int mt = warp; mt * 8 < nh; mt += HM_THREADS / 32) {
+    const int kg = mt * 8 + g;                        // this lane's harmonic (rows g: cosine, g + 8: sine)
+    const double th = (double)(kg + 1) * nu;
+    const float2 z8 = unit_phasor_turns(th * 128.0);  // 8 p-rows ahead
+    float2 uA = unit_phasor_turns(th * 16.0 * (double)t), uB = unit_phasor_turns(th * 16.0 * (double)(t + 4));
+    float d[4][4];
+#pragma unroll
+    for(int j = 0; j < 4; j ++) { d[j][0] = 0.f; d[j][1] = 0.f; d[j][2] = 0.f; d[j][3] = 0.f; }
+    for(int s = 0; s < nsteps; s ++) {
+      if(s > 0 && (s & 7) == 0) {                     // re-seed every 64 p-rows
+        uA = unit_phasor_turns(th * 16.0 * (double)(8 * s + t));
+        uB = unit_phasor_turns(th * 16.0 * (double)(8 * s + t + 4));
+      }
+      const float a[4] = {uA.x, uA.y, uB.x, uB.y};
+      float ah[4], al[4];
+#pragma unroll
+      for(int e = 0; e < 4; e ++) tf32_split(a[e], ah[e], al[e]);
+      const int r0 = (8 * s + t) * HM_ROW + g, r1 = (8 * s + t + 4) * HM_ROW + g;
+#pragma unroll
+      for(int j = 0; j < 2; j ++) {
+        const float2 h0 = sph[r0 + 8 * j], h1 = sph[r1 + 8 * j], l0 = spl[r0 + 8 * j], l1 = spl[r1 + 8 * j];
+        const float beh[2] = {h0.x, h1.x}, boh[2] = {h0.y, h1.y}, bel[2] = {l0.x, l1.x}, bol[2] = {l0.y, l1.y};
+        mma_tf32_16x8x8(d[j], ah, beh); mma_tf32_16x8x8(d[j], al, beh); mma_tf32_16x8x8(d[j], ah, bel);
+        mma_tf32_16x8x8(d[j + 2], ah, boh); mma_tf32_16x8x8(d[j + 2], al, boh); mma_tf32_16x8x8(d[j + 2], ah, bol);
+      }
+      uA = cmul(uA, z8); uB = cmul(uB, z8);
+    }
+    // ---- epilogue: q-phasors and the sum over the 16 columns (4 per lane, then across the 4 lanes of a row)
+    float re = 0.f, im = 0.f;
+#pragma unroll
+    for(int j = 0; j < 2; j ++)
+#pragma unroll
+      for(int e = 0; e < 2; e ++) {
+        const float2 wq = unit_phasor_turns(th * (double)(8 * j + 2 * t + e));
+        re = fmaf(wq.x, d[j][e], fmaf(-wq.y, d[j][2 + e], re));
+        im = fmaf(-wq.x, d[j + 2][2 + e], fmaf(-wq.y, d[j + 2][e], im));
+      }
+    re += __shfl_xor_sync(0xffffffffu, re, 1); im += __shfl_xor_sync(0xffffffffu, im, 1);
+    re += __shfl_xor_sync(0xffffffffu, re, 2); im += __shfl_xor_sync(0xffffffffu, im, 2);
+    if(t == 0 && kg < nh) {
+      float ishift = (float)((double)half * 2.0 * LLSM_PI * (double)f0 / (double)P.fs * ((double)kg + 1.0));
+      double eps = (double)ishift - (double)(kg + 1) * (double)omega0 * (double)half;
+      float se = (float)sin(eps), ce = (float)cos(eps);
+      float dre = re * ce - im * se, dim = re * se + im * ce;
+      float am = (float)(sqrt((double)(dre * dre + dim * dim)) * 2.0 / (double)winsum);
+      P.ampl[fidx * P.maxnhar + kg] = am;
+      P.phse[fidx * P.maxnhar + kg] = atan2f(dim, dre);
+    }
+  }
+  for(int k = nh + tid; k < P.maxnhar; k += HM_THREADS) { P.ampl[fidx * P.maxnhar + k] = 0; P.phse[fidx * P.maxnhar + k] = 0; }
+  if(tid == 0) P.nhar_out[fidx] = nh;
+}
+
+static inline size_t harm_mma_smem(int cap) {
+  const int prow = (((cap + 1 + 15) / 16) + 7) & ~7;
+  return (size_t)((cap + 3) & ~1) * 4 + HM_THREADS * 8 + (size_t)prow * HM_ROW * 8 * 2 + 16;
+}
+
+static inline int dft_variant() {
+  static int v = -1;
+  if(v < 0) { const char* e = getenv("LLSM_DFT_VARIANT"); v = e ? atoi(e) : 1; }
+  return v;
+}
+
 static inline size_t harm_dft_smem(int max_half, int ng) {
   return (size_t)((max_half + 3) & ~1) * 4 + HD_THREADS * 8 + 2 * HD_THREADS * 4 + (ng > 1 ? 0 : (size_t)(max_half + 2) * 8) + 16;
 }
 
-static inline int launch_harmonic_dft(const HarmDftParams& P, int nutt, cudaStream_t st) {
+static inline int launch_harmonic_dft(const HarmDftParams& Pin, int nutt, cudaStream_t st) {
+  HarmDftParams P = Pin;
+  if(P.nsig == 1 && P.edc == nullptr && dft_variant() == 1 && P.maxnhar > HD_KW) {
+    // tensor-core kernel for windows up to 4 periods of 50 Hz; the direct kernel picks up longer ones
+    int cap = (int)ceil((double)P.fs / 50.0 * (double)P.rel_winsize / 4.0 * 2.0) + 4;
+    if(cap > P.max_half) cap = P.max_half;
+    P.mma_cap_half = cap;
+    size_t smem = harm_mma_smem(cap);
+    if(smem <= 200 * 1024) {
+#ifndef LLSM_EMU
+      cudaFuncSetAttribute(harmonic_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#endif
+      LLSM_LAUNCH(harmonic_mma_kernel, dim3(P.nfrm, nutt), dim3(HM_THREADS), smem, st, P);
+      if(cap >= P.max_half) return 0;
+      P.only_above_half = cap;
+    }
+  }
   const bool warp_groups = P.nsig > 1 && P.maxnhar <= HD_KW;
   const int ng = warp_groups ? HD_THREADS / 32 : 1;
   dim3 grid(P.nfrm, nutt * ((P.nsig + ng - 1) / ng)), block(HD_THREADS);
