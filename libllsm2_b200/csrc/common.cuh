@@ -132,6 +132,15 @@ __device__ float2* block_fft(float2* a, float2* b, int lg, const float2* __restr
 #undef FIX
 }
 
+// request a line into L2 ahead of its use (no register, no stall)
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+#ifndef LLSM_EMU
+  asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+#else
+  (void)p;
+#endif
+}
+
 // ---- warp-level tensor-core MMA, TF32 operands, FP32 accumulate -------------------------------------
 // D (16 x 8) += A (16 x 8, row) * B (8 x 8, col). Fragment ownership (g = lane / 4, t = lane % 4):
 //   a0 = A[g][t], a1 = A[g + 8][t], a2 = A[g][t + 4], a3 = A[g + 8][t + 4]

@@ -744,6 +744,25 @@ __global__ void __launch_bounds__(SHW_THREADS, 2) noise_shape_warp_kernel(ShapeP
       doA = ! (mxA < -100.f);
       doB = hasB && ! (mxB < -100.f);
     }
+    // ---- warm the caches: the model PSDs of this pair are needed only after the first FFT, the excitation
+    //      of the pair this warp takes next round right at its start (one 128-byte line per lane and array)
+    if(hasA) {
+      const int nline = (npsd * 4 + 127) >> 7;
+      for(int h = 0; h < (hasB ? 2 : 1); h ++) {
+        if(lane < nline) {
+          prefetch_l2(P.psd + (row + i + h) * (size_t)npsd + lane * 32);
+          if(P.psdres) prefetch_l2(P.psdres + (row + i + h) * (size_t)npsd + lane * 32);
+        }
+      }
+      const int inext = i + 2 * SHW_WARPS;
+      if(inext < ib) {
+        const int c0 = P.center[inext] - hw;
+        for(int q = lane * 32; q < P.n_ns + 256; q += 32 * 32) {
+          const int at = c0 + q;
+          if(at >= 0 && at < ny_b) prefetch_l2(exc + at);
+        }
+      }
+    }
     if(doA || doB) {                             // warp-uniform
       float2 x[32];
       const int plane = (32 - lane) & 31;
@@ -932,11 +951,24 @@ __global__ void __launch_bounds__(SHW_THREADS, 2) noise_shape_warp_kernel(ShapeP
     }
     __syncthreads();
   }
-  for(int i = oa + tid; i < ob; i += blockDim.x) {
-    float v = i < ny_b ? acc[i - oa] : 0.f;
-    size_t o = (size_t)b * P.stride + i;
-    P.y_noise[o] = v;
-    if(P.y) P.y[o] = (P.y_sin ? P.y_sin[o] : 0.f) + v;
+  // write-out (layer0.c:658-659); the harmonic part is read eight rows ahead: the loop is latency-bound
+  for(int i0 = oa + tid; i0 < ob; i0 += 8 * SHW_THREADS) {
+    float ys[8];
+#pragma unroll
+    for(int u = 0; u < 8; u ++) {
+      const int i = i0 + u * SHW_THREADS;
+      ys[u] = (P.y && P.y_sin && i < ob) ? P.y_sin[(size_t)b * P.stride + i] : 0.f;
+    }
+#pragma unroll
+    for(int u = 0; u < 8; u ++) {
+      const int i = i0 + u * SHW_THREADS;
+      if(i < ob) {
+        const float v = i < ny_b ? acc[i - oa] : 0.f;
+        const size_t o = (size_t)b * P.stride + i;
+        P.y_noise[o] = v;
+        if(P.y) P.y[o] = ys[u] + v;
+      }
+    }
   }
 }
 
