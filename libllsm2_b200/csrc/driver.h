@@ -113,7 +113,7 @@ static inline int run_harmonics(const SynthPlanDev& pd, const llsm_b200_conf& co
   P.f0 = fr.f0; P.nhar = fr.nhar; P.ampl = fr.ampl; P.phse = fr.phse;
   P.hm_base = pd.hm_base; P.hm_frac = pd.hm_frac; P.win = pd.win_hm;
   P.n_hm = pd.h.n_hm; P.ny = ny_valid; P.nsamp = nsamp; P.stride = stride;
-  P.fs = conf.fs;
+  P.fs = conf.fs; P.hop = pd.h.hop_f;
   P.has_options = opt != nullptr;
   if(opt) { P.use_iczt = opt->use_iczt; P.iczt_a = opt->iczt_param_a; P.iczt_b = opt->iczt_param_b; }
   P.y_sin = y_sin; P.frame_lo = frame_lo; P.frame_hi = frame_hi;
@@ -182,7 +182,7 @@ static inline int run_noise_part(const SynthPlanDev& pd, SynthScratch& sc, const
   E.ny = h.ny; E.nsamp = out.stride; E.stride = out.stride; E.fs = conf.fs;
   E.has_options = 1; E.use_iczt = opt.use_iczt; E.iczt_a = opt.iczt_param_a; E.iczt_b = opt.iczt_param_b;
   E.colored = sc.colored.as<float>(); E.nt = h.nt; E.ntemplate = h.ntemplate; E.tstride = tstride;
-  E.chan_mask = mask;
+  E.chan_mask = mask; E.hop = h.hop_f;
   if(frame_hi > 0) {                 // excitation is only needed under the owned frames' windows
     E.samp_lo = h.hm_base[frame_lo] - h.n_ns / 2 - 2;
     E.samp_hi = h.hm_base[frame_hi - 1] + h.n_ns / 2 + 2;

@@ -81,7 +81,7 @@ static inline int run_synth_l1(const SynthPlanDev& pd, const L1PlanDev& lp, Synt
     P.nfrm = F; P.maxnhar = conf.maxnhar; P.nfrm_utt = fr.nfrm_utt; P.ny_utt = ny_utt_dev;
     P.f0 = hmf.f0; P.nhar = hmf.nhar; P.ampl = hmf.ampl; P.phse = hmf.phse;
     P.hm_base = pd.base_trunc; P.hm_frac = pd.zero_frac; P.win = pd.win_hm; P.n_hm = h.n_hm;
-    P.ny = h.ny; P.nsamp = out.stride; P.stride = out.stride; P.fs = conf.fs;
+    P.ny = h.ny; P.nsamp = out.stride; P.stride = out.stride; P.fs = conf.fs; P.hop = h.hop_f;
     P.has_options = 1; P.use_iczt = opt.use_iczt; P.iczt_a = opt.iczt_param_a; P.iczt_b = opt.iczt_param_b;
     P.frame_mask = plan.need_hm; P.y_sin = ps.y_hm.as<float>();
     if(launch_hm_bank(P, B, F, st) != 0) return LLSM_B200_ERANGE;

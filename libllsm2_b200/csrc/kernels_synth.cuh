@@ -38,6 +38,7 @@ struct BankParams {
   const int* frame_mask;    // [B][nfrm] optional: 0 = skip the frame (PbP path, layer0.c:261)
   int frame_lo, frame_hi;   // frames [lo, hi) contribute (frame-range sharding); hi <= 0 means all
   int npass;                // frame slots per CTA = warps * npass
+  float hop;                // thop * fs (float product): hm_base[f] = round(f * hop)
   float* y_sin;             // [B][stride]
 };
 
@@ -186,12 +187,14 @@ __global__ void __launch_bounds__(NTHR, MINB) hm_bank_ola_kernel(BankParams P) {
   // ---- overlap-add: gather the (<= 3) frames covering each owned sample, ascending frame order
   //      as in the reference's sequential y[idx] += yi[j] (layer0.c:135-140)
   float* yrow = P.y_sin + (size_t)b * P.stride;
+  const float inv_hop = 1.0f / P.hop;
   for(int idx = start + (int)threadIdx.x; idx < end; idx += blockDim.x) {
     float acc = 0.f;
     if(idx < ny_b) {
-      // first slot whose window end (sb + H) is beyond idx
-      int lo = 0, hi = nslot;
-      while(lo < hi) { int mid = (lo + hi) >> 1; if(sb[mid] + H > idx) hi = mid; else lo = mid + 1; }
+      // first slot whose window end (sb + H) is beyond idx: frame positions are round(f * hop), so the
+      // hop arithmetic gives it up to one frame; start one slot early (early frames fail j < N below)
+      int lo = (int)((float)(idx - H) * inv_hop) - (t0 - 1) - 1;
+      if(lo < 0) lo = 0;
       for(int s = lo; s < nslot; s ++) {
         int j = idx - sb[s] + H;
         if(j < 0) break;
@@ -277,6 +280,7 @@ struct ExcParams {
   const float* colored;     // [B][nchannel][nt]
   int nt, ntemplate, tstride;   // tstride: row stride of colored
   unsigned chan_mask;       // bit c set when channel c exists (fmin < fs / 2)
+  float hop;                // thop * fs (float product), spacing of env_off
   int samp_lo, samp_hi;     // only samples [lo, hi) are needed (frame-range sharding); hi <= 0 means all
   float* y_exc;             // [B][stride]
 };
@@ -336,20 +340,19 @@ __global__ void __launch_bounds__(EXC_THREADS) noise_excitation_kernel(ExcParams
   float* fr = (float*)smem;                        // [EXC_FCHUNK][fstride]
   const size_t row = (size_t)b * P.nfrm;
 
-  // frames that can reach [p0, p0 + EXC_THREADS): env_off + n_env + 1 > p0 and env_off - 1 <= pend
-  // (two binary searches, done once per CTA)
-  __shared__ int s_range[2];
-  if(threadIdx.x == 0) {
+  // frames that can reach [p0, p0 + EXC_TILE): env_off + n_env + 1 > p0 and env_off - 1 <= pend, with
+  // env_off[i] = round((i - 1) * hop). Bounds from the hop arithmetic, one frame of margin on either side
+  // (a frame that does not reach a sample is rejected per sample below); no dependent table reads.
+  int ia, ib;
+  {
     const int pend = p0 + EXC_TILE - 1;
-    int lo = 0, hi = nf;
-    while(lo < hi) { int mid = (lo + hi) >> 1; if(P.env_off[mid] + P.n_env + 1 > p0) hi = mid; else lo = mid + 1; }
-    s_range[0] = lo;
-    hi = nf;
-    while(lo < hi) { int mid = (lo + hi) >> 1; if(P.env_off[mid] - 1 > pend) hi = mid; else lo = mid + 1; }
-    s_range[1] = lo;
+    const float inv_hop = 1.0f / P.hop;
+    ia = (int)floorf((float)(p0 - P.n_env - 1) * inv_hop);          // (first reaching frame) - 1
+    ib = (int)floorf((float)(pend + 1) * inv_hop) + 3;              // (last reaching frame) + 2
+    if(ia < 0) ia = 0;
+    if(ib > nf) ib = nf;
+    if(ia > ib) ia = ib;
   }
-  __syncthreads();
-  const int ia = s_range[0], ib = s_range[1];      // frames [ia, ib)
 
   float env[EXC_SPT][MAXCH];
 #pragma unroll
