@@ -341,17 +341,19 @@ __global__ void __launch_bounds__(EXC_THREADS) noise_excitation_kernel(ExcParams
   const size_t row = (size_t)b * P.nfrm;
 
   // frames that can reach [p0, p0 + EXC_TILE): env_off + n_env + 1 > p0 and env_off - 1 <= pend, with
-  // env_off[i] = round((i - 1) * hop). Bounds from the hop arithmetic, one frame of margin on either side
-  // (a frame that does not reach a sample is rejected per sample below); no dependent table reads.
+  // env_off[i] = round((i - 1) * hop): bounds from the hop arithmetic (one frame of slack), then made exact
+  // with a couple of table reads (every extra frame costs a test per output sample)
   int ia, ib;
   {
     const int pend = p0 + EXC_TILE - 1;
     const float inv_hop = 1.0f / P.hop;
-    ia = (int)floorf((float)(p0 - P.n_env - 1) * inv_hop);          // (first reaching frame) - 1
-    ib = (int)floorf((float)(pend + 1) * inv_hop) + 3;              // (last reaching frame) + 2
+    ia = (int)floorf((float)(p0 - P.n_env - 1) * inv_hop);
+    ib = (int)floorf((float)(pend + 1) * inv_hop) + 3;
     if(ia < 0) ia = 0;
     if(ib > nf) ib = nf;
     if(ia > ib) ia = ib;
+    while(ia < ib && P.env_off[ia] + P.n_env + 1 <= p0) ia ++;
+    while(ib > ia && P.env_off[ib - 1] - 1 > pend) ib --;
   }
 
   float env[EXC_SPT][MAXCH];

@@ -1,8 +1,8 @@
 #!/bin/bash
-# ncu --set full capture of the analysis kernels (one launch each). Usage: tools/gpu_profile_ana.sh tag
-TAG=$1
+# ncu --set full capture of analysis kernels (one launch each). Usage: tools/gpu_profile_ana.sh tag kernel [kernel...]
+TAG=$1; shift
 mkdir -p gpurun_out
-for K in noise_spec harmonic_dft noise_kalman refine_f0 iir_filtfilt; do
+for K in "$@"; do
   SKIP=0
   if [ "$K" = "iir_filtfilt" ]; then SKIP=1; fi   # first iir launch belongs to the synthesis that makes the input
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$K -s $SKIP -c 1 \
