@@ -221,6 +221,15 @@ static inline void launch_hm_bank_t(const BankParams& P, dim3 grid, size_t smem,
   LLSM_LAUNCH(kfn, grid, dim3(NTHR), smem, st, P);
 }
 
+#include "kernels_bank_tc.cuh"
+
+// LLSM_BANK_TC=0 forces the CUDA-core bank (hm_bank_ola_kernel); default: tensor-core bank where it applies
+static inline int bank_tc_enabled() {
+  static int v = -1;
+  if(v < 0) { const char* e = getenv("LLSM_BANK_TC"); v = e ? atoi(e) : 1; }
+  return v;
+}
+
 static inline int bank_variant() {
   static int v = -1;
   if(v < 0) { const char* e = getenv("LLSM_BANK_VARIANT"); v = e ? atoi(e) : 0; }
@@ -229,6 +238,10 @@ static inline int bank_variant() {
 
 // returns 0 on success, -1 when the window is too long for the specialisations below
 static inline int launch_hm_bank(BankParams P, int nutt, int nfrm_max, cudaStream_t st) {
+#ifndef LLSM_EMU
+  // many harmonics: operand generation + tcgen05 GEMM (kernels_bank_tc.cuh); few: direct summation below
+  if(bank_tc_enabled() && P.maxnhar >= 24 && launch_hm_bank_tc(P, nutt, nfrm_max, st) == 0) return 0;
+#endif
   const int NTHR = 256, NW = NTHR / 32;
   P.npass = 4;                              // 32 frame slots, 30 tiles per CTA
   const int F = NW * P.npass - 2;
