@@ -16,20 +16,31 @@
 // (what the hardware reads) and lo = x - hi, and three products hi hi + lo hi + hi lo are accumulated in
 // FP32 -- 2^-21 relative per term, as good as the FP32 recurrences of the CUDA-core kernel.
 //
-// A is written from registers straight into tensor memory (tcgen05.st), B goes through 16 KB of shared
-// memory (K-major core matrices, no swizzle), the accumulators live in tensor memory. Four warps issue
-// the MMAs concurrently (one issuing thread sustains one small MMA per ~45 cycles, the pipe takes one per
-// 16: measured with tools/tc_rate.cu), each into its own accumulator. Two CTAs per SM alternate between
-// operand generation and MMA.
+// A is written from registers straight into tensor memory (tcgen05.st), B goes through shared memory
+// (K-major core matrices, no swizzle), the accumulators live in tensor memory. One CTA per SM, warp
+// specialised: 16 warps generate operands (A and B double-buffered: 2 x 128 tensor-memory columns,
+// 2 x 16 KB), 4 warps issue the MMAs -- one issuing thread sustains one small MMA per ~45 cycles while the
+// pipe takes one per 16 (tools/tc_rate.cu), so four issue concurrently, each into its own accumulator
+// (double-buffered too: the previous group's accumulators are read back, windowed and parked while the next
+// group's MMAs run). Hand-over through mbarriers: full[buf] (generators -> issuers), empty[buf] and
+// dfull[dbuf] (tcgen05.commit -> generators). Finished output tiles are written group by group.
 #pragma once
 #ifndef LLSM_EMU
 #include "tcgen05.cuh"
+#ifndef BTC_STAMP
+#define BTC_STAMP(who, tag) do { } while(0)
+#define BTC_STAMP_DECL
+#endif
 
-#define BTC_THREADS 256
+#define BTC_GEN_WARPS 16
+#define BTC_GEN_THREADS (BTC_GEN_WARPS * 32)
+#define BTC_OUT_WARPS 4      // read-back / overlap-add warps (one per tensor-memory lane quadrant)
+#define BTC_THREADS (BTC_GEN_THREADS + 32 * BTC_OUT_WARPS + 32)   // + the MMA-issuing warp
 #define BTC_KC 32           // harmonics per MMA chunk (columns of each A tile)
 #define BTC_SLOT 512        // floats per parked frame: sample n lives at index n + 256
-#define BTC_NSLOT 32        // frame slots per CTA (8 groups of 4), 30 owned output tiles
-#define BTC_CST 128         // harmonics whose coefficients are staged together
+#define BTC_NBUF 3          // operand ring depth: 3 x 128 tensor-memory columns of A, 3 x 16 KB of B
+#define BTC_NSLOT 64        // frame slots per CTA (16 groups of 4), 62 owned output tiles
+#define BTC_CST 512         // harmonics per frame in the coefficient buffers (more: CUDA-core bank)
 #define BTC_MAXH 248        // largest half window: n = 8 p + q, p < 32
 
 struct BtcFrame { unsigned long long nufix; float corr; int nh; };   // nufix = nu 2^64 (turns per sample and harmonic)
@@ -47,22 +58,51 @@ __device__ __forceinline__ void btc_split2(float2 x, uint32_t& h0, uint32_t& h1,
   float2 lo = ffma2(make_float2(__uint_as_float(h0), __uint_as_float(h1)), make_float2(-1.f, -1.f), x);
   l0 = __float_as_uint(lo.x); l1 = __float_as_uint(lo.y);
 }
+// (wr + i wi) (zr + i zi) on two packed elements
+__device__ __forceinline__ void btc_rot2(float2& wr, float2& wi, float2 zr, float2 zi, float2 nzi) {
+  const float2 t1 = fmul2(wr, zr), t2 = fmul2(wi, zr);
+  const float2 nr = ffma2(wi, nzi, t1), ni = ffma2(wr, zi, t2);
+  wr = nr; wi = ni;
+}
 
-__global__ void __launch_bounds__(BTC_THREADS, 2) hm_bank_tc_kernel(BankParams P) {
-  extern __shared__ __align__(1024) char smem[];
-  float* fb = (float*)smem;                                  // [32][512]
+// 24 MMAs of one chunk: D_U += Arh Brh + Arl Brh + Arh Brl, D_V += Aih Bih + Ail Bih + Aih Bil, four K = 8 slabs.
+// BF (operand buffer) is a compile-time constant so that every descriptor is base + constant.
+template <int BF>
+__device__ __forceinline__ void btc_issue_chunk(uint32_t tbase, uint64_t bbase, uint32_t idesc, uint32_t d_u, uint32_t d_v, int c) {
+  const uint32_t a0 = tbase + 128 * BF;
+#pragma unroll
+  for(int ks = 0; ks < 4; ks ++) {
+    const uint64_t brh = bbase + (uint64_t)((16384 * BF + 256 * ks) >> 4), brl = brh + (4096 >> 4);
+    const uint64_t bih = brh + (8192 >> 4), bil = brh + (12288 >> 4);
+    tc::mma_tf32_ts(d_u, a0 + 8 * ks, brh, idesc, (c | ks) ? 1u : 0u);
+    tc::mma_tf32_ts(d_v, a0 + 64 + 8 * ks, bih, idesc, (c | ks) ? 1u : 0u);
+    tc::mma_tf32_ts(d_u, a0 + 32 + 8 * ks, brh, idesc, 1u);
+    tc::mma_tf32_ts(d_v, a0 + 96 + 8 * ks, bih, idesc, 1u);
+    tc::mma_tf32_ts(d_u, a0 + 8 * ks, brl, idesc, 1u);
+    tc::mma_tf32_ts(d_v, a0 + 64 + 8 * ks, bil, idesc, 1u);
+  }
+}
+
+__global__ void __launch_bounds__(BTC_THREADS, 1) hm_bank_tc_kernel(BankParams P) {
+  extern __shared__ __align__(1024) char smem_tc[];
+  float* fb = (float*)smem_tc;                               // [64][512]
   float* swin = fb + BTC_NSLOT * BTC_SLOT;                   // [512]  window at index n + 256
-  float* bt = swin + BTC_SLOT;                               // 4 tiles x 1024 floats: Brh, Brl, Bih, Bil
-  float* Cr = bt + 4 * 1024;                                 // [4][128]
-  float* Ci = Cr + 4 * BTC_CST;                              // [4][128]
-  BtcFrame* finfo = (BtcFrame*)(Ci + 4 * BTC_CST);           // [32]
-  int* sb = (int*)(finfo + BTC_NSLOT);                       // [32] frame position
-  int* sv = sb + BTC_NSLOT;                                  // [32] slot holds a voiced frame
-  uint64_t* bar = (uint64_t*)(sv + BTC_NSLOT);
-  uint32_t* tbase_s = (uint32_t*)(bar + 1);
+  float* bt = swin + BTC_SLOT;                               // [3 buffers][4 tiles Brh, Brl, Bih, Bil][1024]
+  float* Cr = bt + BTC_NBUF * 4096;                          // [2 groups][4 frames][512]
+  float* Ci = Cr + 2 * 4 * BTC_CST;                          // [2][4][512]
+  BtcFrame* finfo = (BtcFrame*)(Ci + 2 * 4 * BTC_CST);       // [64]
+  int* sb = (int*)(finfo + BTC_NSLOT);                       // [64] frame position
+  int* sv = sb + BTC_NSLOT;                                  // [64] slot holds a voiced frame
+  uint64_t* full = (uint64_t*)(sv + BTC_NSLOT);              // [3] operands of a chunk are in place
+  uint64_t* empty = full + BTC_NBUF;                         // [3] the MMAs that read them have completed
+  uint64_t* dfull = empty + BTC_NBUF;                               // [2] a group's accumulators are complete
+  uint64_t* dempty = dfull + 2;                              // [2] ... and have been read back
+  uint64_t* cfull = dempty + 2;                              // [2] a group's coefficients are staged
+  uint32_t* tbase_s = (uint32_t*)(cfull + 2);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, qd = warp & 3, hh = warp >> 2;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.y, seg = blockIdx.x;
+  BTC_STAMP_DECL
   const int F = BTC_NSLOT - 2;
   const int N = P.n_hm, H = N >> 1;
   const int nf = P.nfrm_utt ? P.nfrm_utt[b] : P.nfrm;
@@ -73,15 +113,20 @@ __global__ void __launch_bounds__(BTC_THREADS, 2) hm_bank_tc_kernel(BankParams P
   if(start >= end) return;                                   // uniform per CTA
   const size_t row = (size_t)b * P.nfrm;
 
-  // ---- set-up: tensor memory, barrier, window, per-frame scalars ----
-  if(warp == 0) tc::tmem_alloc(tbase_s, 256);
-  if(tid == 0) { tc::mbar_init(bar, 4); tc::fence_mbar_init(); }
+  // ---- set-up: tensor memory, barriers, window, per-frame scalars ----
+  if(warp == 20) BTC_STAMP(2, 40);
+  if(warp == 0) tc::tmem_alloc(tbase_s, 512);
+  if(tid == 32) {
+    for(int i = 0; i < BTC_NBUF; i ++) { tc::mbar_init(full + i, 12); tc::mbar_init(empty + i, 1); }
+    for(int i = 0; i < 2; i ++) { tc::mbar_init(dfull + i, 1); tc::mbar_init(dempty + i, BTC_OUT_WARPS); tc::mbar_init(cfull + i, 8); }
+    tc::fence_mbar_init();
+  }
   for(int i = tid; i < BTC_SLOT; i += BTC_THREADS) {
     int j = i - 256 + H;
     swin[i] = (j >= 0 && j < N) ? P.win[j] : 0.f;
   }
-  if(tid < BTC_NSLOT) {
-    const int s = tid, f = t0 - 1 + s;
+  if(tid >= 64 && tid < 64 + BTC_NSLOT) {
+    const int s = tid - 64, f = t0 - 1 + s;
     const bool inrange = f >= 0 && f < nf;
     float f0 = 0; int nh = 0;
     if(inrange) { f0 = P.f0[row + f]; nh = P.nhar[row + f]; }
@@ -111,214 +156,293 @@ __global__ void __launch_bounds__(BTC_THREADS, 2) hm_bank_tc_kernel(BankParams P
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tbase = *tbase_s;
-  const uint32_t tlane = tbase + ((uint32_t)(32 * qd) << 16);
+  if(warp == 20) BTC_STAMP(2, 41);
+  const int uwarp = __shfl_sync(0xffffffffu, warp, 0);       // warp-uniform for the compiler
 
-  // roles
-  const int pp = lane;                                        // A: row (coarse time index) of frame qd
-  const int gB = tid >> 6, jB = (tid >> 3) & 7, qB = tid & 7; // B: frame, k-quad, fine time index
-  uint32_t parity = 0;
-  bool pending = false;
-  float pf_a[2], pf_p[2];                                     // prefetched amplitudes / phases of group pf_grp
-  int pf_grp = 0;
+  if(uwarp == BTC_GEN_WARPS + BTC_OUT_WARPS) {
+    // =========================== MMA issue: one warp, one elected lane ===========================
+    // (the warp stays converged and the MMA operands are warp-uniform, so the elected lane's tcgen05.mma take
+    //  them from uniform registers: one small MMA issues every 16 cycles, the tensor pipe's own rate)
+    const uint32_t idesc = tc::idesc_tf32(128, 32, false);
+    const uint64_t bbase = tc::smem_desc(tc::smem_u32(bt), 128, 1024);
+    int bf = 0, gi = 0; uint32_t ph = 0;                      // ring position and its phase parity
+    for(int grp = 0; grp < BTC_NSLOT / 4; grp ++) {
+      int nhmax = 0;
 #pragma unroll
-  for(int it = 0; it < 2; it ++) {
-    const int i = tid + it * BTC_THREADS, g = i >> 7, kl = i & 127;
-    pf_a[it] = 0.f; pf_p[it] = 0.f;
-    if(kl < finfo[g].nh) { const size_t o = (row + t0 - 1 + g) * (size_t)P.maxnhar + kl; pf_a[it] = P.ampl[o]; pf_p[it] = P.phse[o]; }
-  }
-  // MMA issue state of warps 0..3 (lane 0): accumulator t = 2 (V ? 1 : 0) + (slab parity)
-  const uint32_t mm_idesc = tc::idesc_tf32(128, 32, false);
-  const uint32_t mm_d = tbase + 128 + 32 * (warp & 3);
-  const uint32_t mm_ah = tbase + 64 * ((warp >> 1) & 1) + 8 * (warp & 1), mm_al = mm_ah + 32;
-  uint64_t mm_bh[2], mm_bl[2];
-#pragma unroll
-  for(int m = 0; m < 2; m ++) {
-    const uint32_t bh = tc::smem_u32(bt) + 8192 * ((warp >> 1) & 1) + 256 * ((warp & 1) + 2 * m);
-    mm_bh[m] = tc::smem_desc(bh, 128, 1024); mm_bl[m] = tc::smem_desc(bh + 4096, 128, 1024);
-  }
-
-  for(int grp = 0; grp < BTC_NSLOT / 4; grp ++) {
-    const int s0 = 4 * grp;
-    int nhmax = 0;
-#pragma unroll
-    for(int g = 0; g < 4; g ++) nhmax = max(nhmax, finfo[s0 + g].nh);
-    if(nhmax == 0) continue;                                  // uniform: nothing voiced in the group
-    const int nck = (nhmax + BTC_KC - 1) / BTC_KC;
-
-    // ---- phasor seeds ----
-    float2 Wr, Wi, z2, z16;
-    {
-      const unsigned long long nfA = finfo[s0 + qd].nufix;
-      const unsigned tA = 8u * (unsigned)pp, kka = 16u * (unsigned)hh + 1u;
-      const float2 z1 = btc_phasor(nfA, tA);
-      z2 = cmul(z1, z1); z16 = btc_phasor(nfA, 16u * tA);
-      const float2 wa = btc_phasor(nfA, kka * tA), wb = cmul(wa, z1);
-      Wr = make_float2(wa.x, wb.x); Wi = make_float2(wa.y, wb.y);
-    }
-    const float2 z2r = make_float2(z2.x, z2.x), z2i = make_float2(z2.y, z2.y), nz2i = make_float2(-z2.y, -z2.y);
-    const unsigned long long nfB = finfo[s0 + gB].nufix;
-    const float2 rho = btc_phasor(nfB, (unsigned)qB), rho2 = cmul(rho, rho), rho32 = btc_phasor(nfB, 32u * (unsigned)qB);
-    float2 w = btc_phasor(nfB, (unsigned)((4 * jB + 1) * qB));
-
-    for(int c = 0; c < nck; c ++) {
-      if((c & 3) == 0) {
-        // stage a_k cos(phi'_k), a_k sin(phi'_k), phi'_k = phse[k] - corr (k + 1)  (layer0.c:132)
-#pragma unroll
-        for(int it = 0; it < 2; it ++) {
-          const int i = tid + it * BTC_THREADS, g = i >> 7, kl = i & 127, k = c * BTC_KC + kl;
-          const BtcFrame fi = finfo[s0 + g];
-          float a = pf_a[it], phv = pf_p[it];
-          if(c > 0 || pf_grp != grp) {
-            a = 0.f; phv = 0.f;
-            if(k < fi.nh) { const size_t o = (row + t0 - 1 + s0 + g) * (size_t)P.maxnhar + k; a = P.ampl[o]; phv = P.phse[o]; }
-          }
-          const float ph = (float)((double)phv - (double)fi.corr * ((double)k + 1.0));
-          float sn, cs; __sincosf(ph, &sn, &cs);
-          Cr[i] = a * cs; Ci[i] = a * sn;
-        }
-        if(c == 0 && grp + 1 < BTC_NSLOT / 4) {
-          pf_grp = grp + 1;
-          // the next group's first coefficients: in flight while this group computes
-#pragma unroll
-          for(int it = 0; it < 2; it ++) {
-            const int i = tid + it * BTC_THREADS, g = i >> 7, kl = i & 127;
-            pf_a[it] = 0.f; pf_p[it] = 0.f;
-            if(kl < finfo[s0 + 4 + g].nh) {
-              const size_t o = (row + t0 - 1 + s0 + 4 + g) * (size_t)P.maxnhar + kl; pf_a[it] = P.ampl[o]; pf_p[it] = P.phse[o];
-            }
-          }
-        }
-        __syncthreads();
-      }
-      if(pending) { tc::mbar_wait(bar, parity); parity ^= 1; pending = false; tc::fence_after_sync(); }
-
-      // ---- A: rows of e^{i k theta}, 16 harmonics per thread, into tensor memory ----
-      {
-        uint32_t arh[16], arl[16], aih[16], ail[16];
-#pragma unroll
-        for(int i = 0; i < 8; i ++) {
-          btc_split2(Wr, arh[2 * i], arh[2 * i + 1], arl[2 * i], arl[2 * i + 1]);
-          btc_split2(Wi, aih[2 * i], aih[2 * i + 1], ail[2 * i], ail[2 * i + 1]);
-          float2 t1 = fmul2(Wr, z2r), t2 = fmul2(Wi, z2r);
-          float2 nWr = ffma2(Wi, nz2i, t1), nWi = ffma2(Wr, z2i, t2);
-          Wr = nWr; Wi = nWi;
-        }
-        {   // skip the other half-chunk's 16 harmonics
-          const float2 z16r = make_float2(z16.x, z16.x), z16i = make_float2(z16.y, z16.y), nz16i = make_float2(-z16.y, -z16.y);
-          float2 t1 = fmul2(Wr, z16r), t2 = fmul2(Wi, z16r);
-          float2 nWr = ffma2(Wi, nz16i, t1), nWi = ffma2(Wr, z16i, t2);
-          Wr = nWr; Wi = nWi;
-        }
-        const uint32_t ta = tlane + 16 * hh;
-        tc::tmem_st16(ta, arh); tc::tmem_st16(ta + 32, arl); tc::tmem_st16(ta + 64, aih); tc::tmem_st16(ta + 96, ail);
-      }
-      // ---- B: four harmonics of one (frame, q) column, K-major core matrices ----
-      {
-        const float2 e1 = cmul(w, rho);
-        const float2 Er = make_float2(w.x, e1.x), Ei = make_float2(w.y, e1.y);
-        const float2 r2r = make_float2(rho2.x, rho2.x), r2i = make_float2(rho2.y, rho2.y), nr2i = make_float2(-rho2.y, -rho2.y);
-        const float2 Er2 = ffma2(Ei, nr2i, fmul2(Er, r2r)), Ei2 = ffma2(Er, r2i, fmul2(Ei, r2r));
-        const float4 cr = *(const float4*)(Cr + gB * BTC_CST + (c & 3) * BTC_KC + 4 * jB);
-        const float4 ci = *(const float4*)(Ci + gB * BTC_CST + (c & 3) * BTC_KC + 4 * jB);
-        const float2 cr01 = make_float2(cr.x, cr.y), cr23 = make_float2(cr.z, cr.w);
-        const float2 ci01 = make_float2(ci.x, ci.y), ci23 = make_float2(ci.z, ci.w);
-        const float2 nci01 = make_float2(-ci.x, -ci.y), nci23 = make_float2(-ci.z, -ci.w);
-        const float2 br01 = ffma2(Ei, nci01, fmul2(Er, cr01)), bi01 = ffma2(Ei, cr01, fmul2(Er, ci01));
-        const float2 br23 = ffma2(Ei2, nci23, fmul2(Er2, cr23)), bi23 = ffma2(Ei2, cr23, fmul2(Er2, ci23));
-        uint4 rh, rl, ih, il;
-        btc_split2(br01, rh.x, rh.y, rl.x, rl.y); btc_split2(br23, rh.z, rh.w, rl.z, rl.w);
-        btc_split2(bi01, ih.x, ih.y, il.x, il.y); btc_split2(bi23, ih.z, ih.w, il.z, il.w);
-        float* d = bt + jB * 32 + gB * 256 + qB * 4;            // floats: k-quad 128 B, frame 1024 B, q 16 B
-        *(uint4*)(d) = rh; *(uint4*)(d + 1024) = rl; *(uint4*)(d + 2048) = ih; *(uint4*)(d + 3072) = il;
-        w = cmul(w, rho32);
-      }
-      tc::tmem_st_wait();
-      tc::fence_smem_to_async();
-      tc::fence_before_sync();
-      __syncthreads();
-      // ---- MMA: four issuing warps, one accumulator each ----
-      if(warp < 4 && lane == 0) {
+      for(int g = 0; g < 4; g ++) nhmax = max(nhmax, finfo[4 * grp + g].nh);
+      if(nhmax == 0) continue;
+      const int nck = (nhmax + BTC_KC - 1) / BTC_KC;
+      const uint32_t d_u = tbase + 128 * BTC_NBUF + 64 * (gi & 1), d_v = d_u + 32;
+      tc::mbar_wait(dempty + (gi & 1), ((gi >> 1) & 1) ^ 1);     // the accumulators' previous contents have been read
+      for(int c = 0; c < nck; c ++) {
+        tc::mbar_wait(full + bf, ph);
         tc::fence_after_sync();
-#pragma unroll
-        for(int m = 0; m < 2; m ++) {
-          tc::mma_tf32_ts(mm_d, mm_ah + 16 * m, mm_bh[m], mm_idesc, (c | m) ? 1u : 0u);
-          tc::mma_tf32_ts(mm_d, mm_al + 16 * m, mm_bh[m], mm_idesc, 1u);
-          tc::mma_tf32_ts(mm_d, mm_ah + 16 * m, mm_bl[m], mm_idesc, 1u);
+        BTC_STAMP(2, 30);
+        if(tc::elect_one()) {
+          if(bf == 0)      btc_issue_chunk<0>(tbase, bbase, idesc, d_u, d_v, c);
+          else if(bf == 1) btc_issue_chunk<1>(tbase, bbase, idesc, d_u, d_v, c);
+          else             btc_issue_chunk<2>(tbase, bbase, idesc, d_u, d_v, c);
+          tc::mma_commit(empty + bf);
+          if(c == nck - 1) tc::mma_commit(dfull + (gi & 1));
         }
-        tc::mma_commit(bar);
+        __syncwarp();
+        BTC_STAMP(2, 31);
+        if(++ bf == BTC_NBUF) { bf = 0; ph ^= 1; }
+      }
+      gi ++;
+    }
+  } else if(uwarp < 8) {
+    // ========== A warps: rows of e^{i k theta} into tensor memory; coefficients of the next group ==========
+    const int qd = warp & 3, hh = warp >> 2, pp = lane;          // frame (lane quadrant), half chunk, row
+    const uint32_t tlane = tbase + ((uint32_t)(32 * qd) << 16) + 16 * hh;
+    int bf = 0, gi = 0; uint32_t ph = 0;
+    const int gC = tid >> 6, kC = tid & 63;                      // staging: frame, harmonic (mod 64)
+    // a_k cos(phi'_k), a_k sin(phi'_k), phi'_k = phse[k] - corr (k + 1)  (layer0.c:132): group grp -> buffer cb.
+    // The first 128 harmonics come from the registers loaded a group earlier.
+    float pf_a[2], pf_p[2];
+    auto prefetch = [&](int grp) {
+#pragma unroll
+      for(int it = 0; it < 2; it ++) {
+        const int k = kC + 64 * it;
+        pf_a[it] = 0.f; pf_p[it] = 0.f;
+        if(k < finfo[4 * grp + gC].nh) { const size_t o = (row + t0 - 1 + 4 * grp + gC) * (size_t)P.maxnhar + k; pf_a[it] = P.ampl[o]; pf_p[it] = P.phse[o]; }
+      }
+    };
+    auto stage = [&](int grp, int cb, int nhm) {
+      const BtcFrame fi = finfo[4 * grp + gC];
+      float* cr = Cr + (cb * 4 + gC) * BTC_CST; float* cim = Ci + (cb * 4 + gC) * BTC_CST;
+      for(int k = kC, it = 0; k < nhm; k += 64, it ++) {
+        float a = 0.f, phv = 0.f;
+        if(it < 2) { a = it ? pf_a[1] : pf_a[0]; phv = it ? pf_p[1] : pf_p[0]; }
+        else if(k < fi.nh) { const size_t o = (row + t0 - 1 + 4 * grp + gC) * (size_t)P.maxnhar + k; a = P.ampl[o]; phv = P.phse[o]; }
+        const float ph2 = (float)((double)phv - (double)fi.corr * ((double)k + 1.0));
+        float sn, cs; __sincosf(ph2, &sn, &cs);
+        cr[k] = a * cs; cim[k] = a * sn;
       }
       __syncwarp();
-      pending = true;
-    }
-
-    // ---- epilogue: diagonal block of the four accumulators, window, park the frame ----
-    tc::mbar_wait(bar, parity); parity ^= 1; pending = false;
-    tc::fence_after_sync();
-    {
-      uint32_t u0[8], u1[8], v0[8], v1[8];
-      const uint32_t td = tlane + 128 + 8 * qd;
-      tc::tmem_ld8(td, u0); tc::tmem_ld8(td + 32, u1); tc::tmem_ld8(td + 64, v0); tc::tmem_ld8(td + 96, v1);
-      tc::tmem_ld_wait();
-      const int s = s0 + qd;
-      if(sv[s] && !(hh == 1 && pp == 0)) {
-        const int nb = hh == 0 ? 8 * pp : -8 * pp;
-        float* dst = fb + (size_t)s * BTC_SLOT + 256 + nb;
-        const float* wv = swin + 256 + nb;
-        float o[8];
+      if(lane == 0) tc::mbar_arrive(cfull + cb);
+    };
+    auto next_group = [&](int from, int& nhm) {
+      for(int g2 = from; g2 < BTC_NSLOT / 4; g2 ++) {
+        int m = 0;
 #pragma unroll
-        for(int q = 0; q < 8; q ++) {
-          const float U = __uint_as_float(u0[q]) + __uint_as_float(u1[q]);
-          const float V = __uint_as_float(v0[q]) + __uint_as_float(v1[q]);
-          o[q] = (hh == 0 ? U - V : U + V) * wv[q];
-        }
-        *(float4*)(dst) = make_float4(o[0], o[1], o[2], o[3]);
-        *(float4*)(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        for(int g = 0; g < 4; g ++) m = max(m, finfo[4 * g2 + g].nh);
+        if(m > 0) { nhm = m; return g2; }
       }
-    }
-    tc::fence_before_sync();
-  }
-  __syncthreads();
-
-  // ---- overlap-add, one warp per owned tile [base_f, base_f+1): the frames f - 1 .. f + 2 can reach it
-  //      (H = round(hop), positions round(f hop)); ascending frame order as in layer0.c:135-140
-  float* yrow = P.y_sin + (size_t)b * P.stride;
-  for(int ti = warp; ti < F; ti += BTC_THREADS / 32) {
-    const int f = t0 + ti, s = ti + 1;
-    if(f >= nf) break;
-    const int lo = f == 0 ? 0 : sb[s];
-    const int hi = f + 1 < nf ? sb[s + 1] : P.nsamp;
-    int off[4]; const float* src[4];
+      nhm = 0; return -1;
+    };
+    int nhmax = 0;
+    int grp = next_group(0, nhmax);
+    if(grp >= 0) { prefetch(grp); stage(grp, 0, ((nhmax + BTC_KC - 1) / BTC_KC) * BTC_KC); }
+    while(grp >= 0) {
+      const int s0 = 4 * grp;
+      const int nck = (nhmax + BTC_KC - 1) / BTC_KC;
+      int nh_next = 0;
+      const int grp_next = next_group(grp + 1, nh_next);
+      if(grp_next >= 0) prefetch(grp_next);                      // in flight while this group's chunks are generated
+      float2 Wr, Wi, z2, z18;
+      {
+        const unsigned long long nfA = finfo[s0 + qd].nufix;
+        const unsigned tA = 8u * (unsigned)pp, kka = 16u * (unsigned)hh + 1u;
+        const float2 z1 = btc_phasor(nfA, tA);
+        z2 = cmul(z1, z1); z18 = btc_phasor(nfA, 18u * tA);
+        const float2 wa = btc_phasor(nfA, kka * tA), wb = cmul(wa, z1);
+        Wr = make_float2(wa.x, wb.x); Wi = make_float2(wa.y, wb.y);
+      }
+      const float2 z2r = make_float2(z2.x, z2.x), z2i = make_float2(z2.y, z2.y), nz2i = make_float2(-z2.y, -z2.y);
+      const float2 z18r = make_float2(z18.x, z18.x), z18i = make_float2(z18.y, z18.y), nz18i = make_float2(-z18.y, -z18.y);
+      for(int c = 0; c < nck; c ++) {
+        tc::mbar_wait(empty + bf, ph ^ 1);
+        tc::fence_after_sync();
+        const uint32_t ta = tlane + 128 * bf;
 #pragma unroll
-    for(int c = 0; c < 4; c ++) {
-      const int sc = min(s - 1 + c, BTC_NSLOT - 1);
-      const bool ok = (s - 1 + c < BTC_NSLOT) && sv[sc];
-      off[c] = ok ? sb[sc] - H : (1 << 29);                   // j = idx - off; invalid slots fail j < N
-      src[c] = fb + (size_t)sc * BTC_SLOT + 256 - H;
+        for(int hf = 0; hf < 2; hf ++) {
+          uint32_t arh[8], arl[8], aih[8], ail[8];
+#pragma unroll
+          for(int i = 0; i < 4; i ++) {
+            btc_split2(Wr, arh[2 * i], arh[2 * i + 1], arl[2 * i], arl[2 * i + 1]);
+            btc_split2(Wi, aih[2 * i], aih[2 * i + 1], ail[2 * i], ail[2 * i + 1]);
+            if(hf == 1 && i == 3) btc_rot2(Wr, Wi, z18r, z18i, nz18i);     // to the next chunk's (k + 32, k + 33)
+            else btc_rot2(Wr, Wi, z2r, z2i, nz2i);
+          }
+          tc::tmem_st8(ta + 8 * hf, arh); tc::tmem_st8(ta + 32 + 8 * hf, arl);
+          tc::tmem_st8(ta + 64 + 8 * hf, aih); tc::tmem_st8(ta + 96 + 8 * hf, ail);
+        }
+        tc::tmem_st_wait();
+        tc::fence_before_sync();
+        __syncwarp();
+        if(lane == 0) tc::mbar_arrive(full + bf);
+        __syncwarp();
+        if(++ bf == BTC_NBUF) { bf = 0; ph ^= 1; }
+      }
+      // the next group's coefficients go where the previous group's were: all MMAs of that group must be complete
+      // (then the B warps have read its coefficients for the last time)
+      gi ++;
+      if(grp_next >= 0) {
+        if(gi >= 2) tc::mbar_wait(dfull + (gi & 1), ((gi - 2) >> 1) & 1);
+        stage(grp_next, gi & 1, ((nh_next + BTC_KC - 1) / BTC_KC) * BTC_KC);
+      }
+      grp = grp_next; nhmax = nh_next;
     }
-    for(int idx = lo + lane; idx < hi; idx += 32) {
-      float acc = 0.f;
-      if(idx < ny_b) {
+  } else if(uwarp < BTC_GEN_WARPS) {
+    // ====== B warps: columns a_k e^{i (k w q + phi_k)}; two teams of four warps take alternate chunks ======
+    const int team = (warp - 8) >> 2, tT = tid - 256 - 128 * team, wB = warp - 8;
+    const int qB = tT & 7, jB = (tT >> 3) & 7, g0 = tT >> 6;     // fine time index, harmonic quad, frames g0 and g0 + 2
+    int bf = 0, gi = 0, ci = 0; uint32_t ph = 0;
+    for(int grp = 0; grp < BTC_NSLOT / 4; grp ++) {
+      const int s0 = 4 * grp;
+      int nhmax = 0;
+#pragma unroll
+      for(int g = 0; g < 4; g ++) nhmax = max(nhmax, finfo[s0 + g].nh);
+      if(nhmax == 0) continue;                                  // uniform: nothing voiced in the group
+      const int nck = (nhmax + BTC_KC - 1) / BTC_KC;
+      const int cb = gi & 1;
+      const int c_first = (team ^ ci) & 1;                      // this team's first chunk of the group
+      if(wB == 0) BTC_STAMP(1, 1);
+      float2 w[2], rho[2], rho64[2], r2r[2], r2i[2];
+#pragma unroll
+      for(int m = 0; m < 2; m ++) {
+        const unsigned long long nfB = finfo[s0 + g0 + 2 * m].nufix;
+        rho[m] = btc_phasor(nfB, (unsigned)qB); rho64[m] = btc_phasor(nfB, 64u * (unsigned)qB);
+        const float2 rho2 = cmul(rho[m], rho[m]);
+        r2r[m] = make_float2(rho2.x, rho2.x); r2i[m] = make_float2(rho2.y, rho2.y);
+        w[m] = btc_phasor(nfB, (unsigned)((32 * c_first + 4 * jB + 1) * qB));
+      }
+      tc::mbar_wait(cfull + cb, (gi >> 1) & 1);                  // the group's coefficients are staged
+      if(wB == 0) BTC_STAMP(1, 3);
+      for(int c = 0; c < nck; c ++, ci ++) {
+        if(((ci ^ team) & 1) == 0) {
+          if(wB == 0) BTC_STAMP(1, 4);
+          tc::mbar_wait(empty + bf, ph ^ 1);
+          if(wB == 0) BTC_STAMP(1, 10);
+#pragma unroll
+          for(int m = 0; m < 2; m ++) {
+            const int gB = g0 + 2 * m;
+            const float2 e1 = cmul(w[m], rho[m]);
+            float2 Er = make_float2(w[m].x, e1.x), Ei = make_float2(w[m].y, e1.y);
+            const float4 cr = *(const float4*)(Cr + (cb * 4 + gB) * BTC_CST + c * BTC_KC + 4 * jB);
+            const float4 ci4 = *(const float4*)(Ci + (cb * 4 + gB) * BTC_CST + c * BTC_KC + 4 * jB);
+            const float2 cr01 = make_float2(cr.x, cr.y), cr23 = make_float2(cr.z, cr.w);
+            const float2 ci01 = make_float2(ci4.x, ci4.y), ci23 = make_float2(ci4.z, ci4.w);
+            const float2 br01 = ffma2(Ei, make_float2(-ci4.x, -ci4.y), fmul2(Er, cr01)), bi01 = ffma2(Ei, cr01, fmul2(Er, ci01));
+            btc_rot2(Er, Ei, r2r[m], r2i[m], make_float2(-r2i[m].x, -r2i[m].y));
+            const float2 br23 = ffma2(Ei, make_float2(-ci4.z, -ci4.w), fmul2(Er, cr23)), bi23 = ffma2(Ei, cr23, fmul2(Er, ci23));
+            uint4 rh, rl, ih, il;
+            btc_split2(br01, rh.x, rh.y, rl.x, rl.y); btc_split2(br23, rh.z, rh.w, rl.z, rl.w);
+            btc_split2(bi01, ih.x, ih.y, il.x, il.y); btc_split2(bi23, ih.z, ih.w, il.z, il.w);
+            float* d = bt + bf * 4096 + jB * 32 + gB * 256 + qB * 4;   // floats: k-quad 128 B, frame 1 KB, q 16 B
+            *(uint4*)(d) = rh; *(uint4*)(d + 1024) = rl; *(uint4*)(d + 2048) = ih; *(uint4*)(d + 3072) = il;
+            w[m] = cmul(w[m], rho64[m]);
+          }
+          tc::fence_smem_to_async();
+          __syncwarp();
+          if(lane == 0) tc::mbar_arrive(full + bf);
+          __syncwarp();
+          if(wB == 0) BTC_STAMP(1, 13);
+        }
+        if(++ bf == BTC_NBUF) { bf = 0; ph ^= 1; }
+      }
+      gi ++;
+    }
+  } else {
+    // ============ read-back warps: accumulators -> window -> parked frames -> overlap-add -> y_sin ============
+    const int qd = warp & 3, pp = lane, wO = warp - BTC_GEN_WARPS;
+    const uint32_t tlane = tbase + ((uint32_t)(32 * qd) << 16);
+    float* yrow = P.y_sin + (size_t)b * P.stride;
+    int gi = 0, next_tile = 1;
+    // overlap-add of the owned tiles [first, last], one warp per tile [base_f, base_f+1): the frames f - 1 .. f + 2
+    // can reach it (H = round(hop), positions round(f hop)); ascending frame order as in layer0.c:135-140
+    auto emit_tiles = [&](int first, int last) {
+      for(int s = first + ((wO - first) & 3); s <= last; s += BTC_OUT_WARPS) {
+        const int f = t0 - 1 + s;
+        if(f >= nf) break;
+        const int lo = f == 0 ? 0 : sb[s];
+        const int hi = f + 1 < nf ? sb[s + 1] : P.nsamp;
+        int off[4]; const float* src[4];
 #pragma unroll
         for(int c = 0; c < 4; c ++) {
-          const int j = idx - off[c];
-          if((unsigned)j < (unsigned)N) acc += src[c][j];
+          const int sc = min(s - 1 + c, BTC_NSLOT - 1);
+          const bool ok = (s - 1 + c < BTC_NSLOT) && sv[sc];
+          off[c] = ok ? sb[sc] - H : (1 << 29);                 // j = idx - off; invalid slots fail j < N
+          src[c] = fb + (size_t)sc * BTC_SLOT + 256 - H;
+        }
+#pragma unroll 2
+        for(int idx = lo + lane; idx < hi; idx += 32) {
+          float acc = 0.f;
+          if(idx < ny_b) {
+#pragma unroll
+            for(int c = 0; c < 4; c ++) {
+              const int j = idx - off[c];
+              if((unsigned)j < (unsigned)N) acc += src[c][j];
+            }
+          }
+          yrow[idx] = acc;
         }
       }
-      yrow[idx] = acc;
+    };
+    for(int grp = 0; grp < BTC_NSLOT / 4; grp ++) {
+      int nhmax = 0;
+#pragma unroll
+      for(int g = 0; g < 4; g ++) nhmax = max(nhmax, finfo[4 * grp + g].nh);
+      if(nhmax == 0) continue;
+      const int db = gi & 1;
+      if(wO == 0) BTC_STAMP(0, 20);
+      tc::mbar_wait(dfull + db, (gi >> 1) & 1);
+      tc::fence_after_sync();
+      if(wO == 0) BTC_STAMP(0, 21);
+      uint32_t u[8], v[8];
+      const uint32_t td = tlane + 128 * BTC_NBUF + 64 * db + 8 * qd;
+      tc::tmem_ld8(td, u); tc::tmem_ld8(td + 32, v);
+      tc::tmem_ld_wait();
+      tc::fence_before_sync();
+      __syncwarp();
+      if(lane == 0) tc::mbar_arrive(dempty + db);
+      const int s = 4 * grp + qd;
+      if(sv[s]) {
+        // y[8 pp + q] = U - V, y[-8 pp + q] = U + V
+        float* dp = fb + (size_t)s * BTC_SLOT + 256 + 8 * pp;
+        const float* wp = swin + 256 + 8 * pp;
+        const float4 w0 = *(const float4*)(wp), w1 = *(const float4*)(wp + 4);
+        float o[8];
+#pragma unroll
+        for(int q = 0; q < 8; q ++) o[q] = __uint_as_float(u[q]) - __uint_as_float(v[q]);
+        *(float4*)(dp) = make_float4(o[0] * w0.x, o[1] * w0.y, o[2] * w0.z, o[3] * w0.w);
+        *(float4*)(dp + 4) = make_float4(o[4] * w1.x, o[5] * w1.y, o[6] * w1.z, o[7] * w1.w);
+        if(pp > 0) {
+          float* dn = fb + (size_t)s * BTC_SLOT + 256 - 8 * pp;
+          const float* wn = swin + 256 - 8 * pp;
+          const float4 x0 = *(const float4*)(wn), x1 = *(const float4*)(wn + 4);
+#pragma unroll
+          for(int q = 0; q < 8; q ++) o[q] = __uint_as_float(u[q]) + __uint_as_float(v[q]);
+          *(float4*)(dn) = make_float4(o[0] * x0.x, o[1] * x0.y, o[2] * x0.z, o[3] * x0.w);
+          *(float4*)(dn + 4) = make_float4(o[4] * x1.x, o[5] * x1.y, o[6] * x1.z, o[7] * x1.w);
+        }
+      }
+      tc::named_bar_sync(2, 32 * BTC_OUT_WARPS);
+      if(wO == 0) BTC_STAMP(0, 22);
+      {   // the frames of this and of all earlier groups are parked and visible
+        const int last = min(F, 4 * grp + 1);
+        if(last >= next_tile) { emit_tiles(next_tile, last); next_tile = last + 1; }
+      }
+      if(wO == 0) BTC_STAMP(0, 23);
+      gi ++;
     }
+    if(next_tile <= F) emit_tiles(next_tile, F);
   }
+  if(warp == 20) BTC_STAMP(2, 42);
   tc::fence_before_sync();
   __syncthreads();
-  if(warp == 0) tc::tmem_dealloc(tbase, 256);
+  if(warp == 20) BTC_STAMP(2, 43);
+  if(warp == 0) tc::tmem_dealloc(tbase, 512);
 }
 
 static inline size_t bank_tc_smem_bytes() {
-  return (size_t)(BTC_NSLOT * BTC_SLOT + BTC_SLOT + 4 * 1024 + 8 * BTC_CST) * 4 + BTC_NSLOT * (sizeof(BtcFrame) + 8) + 16;
+  return (size_t)(BTC_NSLOT * BTC_SLOT + BTC_SLOT + BTC_NBUF * 4096 + 2 * 8 * BTC_CST) * 4 + BTC_NSLOT * (sizeof(BtcFrame) + 8) + 128;
 }
 
 // tensor-core path when the window fits the 32 x 8 sample grid; returns -1 otherwise
 static inline int launch_hm_bank_tc(const BankParams& P, int nutt, int nfrm_max, cudaStream_t st) {
-  if((P.n_hm >> 1) > BTC_MAXH || (P.n_hm & 1)) return -1;
+  if((P.n_hm >> 1) > BTC_MAXH || (P.n_hm & 1) || P.maxnhar > BTC_CST) return -1;
   const int F = BTC_NSLOT - 2;
   const int nseg = (std::max(nfrm_max, 1) + F - 1) / F;
   const size_t smem = bank_tc_smem_bytes();

@@ -239,8 +239,10 @@ static inline int bank_variant() {
 // returns 0 on success, -1 when the window is too long for the specialisations below
 static inline int launch_hm_bank(BankParams P, int nutt, int nfrm_max, cudaStream_t st) {
 #ifndef LLSM_EMU
-  // many harmonics: operand generation + tcgen05 GEMM (kernels_bank_tc.cuh); few: direct summation below
-  if(bank_tc_enabled() && P.maxnhar >= 24 && launch_hm_bank_tc(P, nutt, nfrm_max, st) == 0) return 0;
+  // synthesis with many harmonics: operand generation + tcgen05 GEMM (kernels_bank_tc.cuh, ~1e-7 of the
+  // frame amplitude); few harmonics, or the analysis residual (options == NULL: x - x_sin is a small difference
+  // of large numbers and wants the last digits): direct FP32 summation below
+  if(bank_tc_enabled() && P.has_options && P.maxnhar >= 24 && launch_hm_bank_tc(P, nutt, nfrm_max, st) == 0) return 0;
 #endif
   const int NTHR = 256, NW = NTHR / 32;
   P.npass = 4;                              // 32 frame slots, 30 tiles per CTA

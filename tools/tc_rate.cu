@@ -28,7 +28,8 @@ __global__ void __launch_bounds__(128) rate(long long* out, int iters) {
   }
   tc::fence_before_sync();
   __syncthreads();
-  if((threadIdx.x & 31) == 0 && warp < NISSUE) {
+  const int uwarp = __shfl_sync(0xffffffffu, warp, 0);
+  if(uwarp < NISSUE) {
     tc::fence_after_sync();
     const uint32_t idesc = tc::idesc_tf32(128, N, false);
     const uint64_t bd = tc::smem_desc(tc::smem_u32(sB), 128, 256);
@@ -36,16 +37,17 @@ __global__ void __launch_bounds__(128) rate(long long* out, int iters) {
     long long t0 = clock64();
     for(int it = 0; it < iters; it ++) {
 #pragma unroll
-      for(int a = 0; a < NACC; a ++) {
-        if(SS) tc::mma_tf32_ss(tbase + 16 + (a + warp * NACC) * N, ad, bd, idesc, 1u);
-        else   tc::mma_tf32_ts(tbase + 16 + (a + warp * NACC) * N, tbase, bd, idesc, 1u);
+      for(int a = 0; a < NACC; a ++) if(tc::elect_one()) {
+        if(SS) tc::mma_tf32_ss(tbase + 16 + (a + uwarp * NACC) * N, ad, bd, idesc, 1u);
+        else   tc::mma_tf32_ts(tbase + 16 + (a + uwarp * NACC) * N, tbase, bd, idesc, 1u);
       }
     }
     long long t1 = clock64();
-    tc::mma_commit(&bar);
+    if(tc::elect_one()) tc::mma_commit(&bar);
+    __syncwarp();
     tc::mbar_wait(&bar, 0);
     long long t2 = clock64();
-    if(blockIdx.x == 0 && warp == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+    if(blockIdx.x == 0 && threadIdx.x == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
   }
   __syncthreads();
   if(warp == 0) tc::tmem_dealloc(tbase, 512);
