@@ -65,6 +65,36 @@ __device__ __forceinline__ void btc_rot2(float2& wr, float2& wi, float2 zr, floa
   wr = nr; wi = ni;
 }
 
+// Overlap-add of one owned tile [base_f, base_f+1) by one warp: the frames f - 1 .. f + 2 can reach it
+// (H = round(hop), positions round(f hop)); ascending frame order as in layer0.c:135-140.
+__device__ __forceinline__ void btc_emit_tile(int s, int lane, int t0, int nf, int ny_b, int N, int H, int nsamp,
+                                              const int* sb, const int* sv, const float* fb, float* yrow) {
+  const int f = t0 - 1 + s;
+  if(f >= nf) return;
+  const int lo = f == 0 ? 0 : sb[s];
+  const int hi = f + 1 < nf ? sb[s + 1] : nsamp;
+  int off[4]; const float* src[4];
+#pragma unroll
+  for(int c = 0; c < 4; c ++) {
+    const int sc = min(s - 1 + c, BTC_NSLOT - 1);
+    const bool ok = (s - 1 + c < BTC_NSLOT) && sv[sc];
+    off[c] = ok ? sb[sc] - H : (1 << 29);                     // j = idx - off; invalid slots fail j < N
+    src[c] = fb + (size_t)sc * BTC_SLOT + 256 - H;
+  }
+#pragma unroll 2
+  for(int idx = lo + lane; idx < hi; idx += 32) {
+    float acc = 0.f;
+    if(idx < ny_b) {
+#pragma unroll
+      for(int c = 0; c < 4; c ++) {
+        const int j = idx - off[c];
+        if((unsigned)j < (unsigned)N) acc += src[c][j];
+      }
+    }
+    yrow[idx] = acc;
+  }
+}
+
 // 24 MMAs of one chunk: D_U += Arh Brh + Arl Brh + Arh Brl, D_V += Aih Bih + Ail Bih + Aih Bil, four K = 8 slabs.
 // BF (operand buffer) is a compile-time constant so that every descriptor is base + constant.
 template <int BF>
@@ -99,6 +129,7 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) hm_bank_tc_kernel(BankParams P
   uint64_t* dempty = dfull + 2;                              // [2] ... and have been read back
   uint64_t* cfull = dempty + 2;                              // [2] a group's coefficients are staged
   uint32_t* tbase_s = (uint32_t*)(cfull + 2);
+  int* tail_s = (int*)(tbase_s + 1);                         // first tile not yet written when the pipeline drains
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.y, seg = blockIdx.x;
@@ -350,35 +381,9 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) hm_bank_tc_kernel(BankParams P
     const uint32_t tlane = tbase + ((uint32_t)(32 * qd) << 16);
     float* yrow = P.y_sin + (size_t)b * P.stride;
     int gi = 0, next_tile = 1;
-    // overlap-add of the owned tiles [first, last], one warp per tile [base_f, base_f+1): the frames f - 1 .. f + 2
-    // can reach it (H = round(hop), positions round(f hop)); ascending frame order as in layer0.c:135-140
     auto emit_tiles = [&](int first, int last) {
-      for(int s = first + ((wO - first) & 3); s <= last; s += BTC_OUT_WARPS) {
-        const int f = t0 - 1 + s;
-        if(f >= nf) break;
-        const int lo = f == 0 ? 0 : sb[s];
-        const int hi = f + 1 < nf ? sb[s + 1] : P.nsamp;
-        int off[4]; const float* src[4];
-#pragma unroll
-        for(int c = 0; c < 4; c ++) {
-          const int sc = min(s - 1 + c, BTC_NSLOT - 1);
-          const bool ok = (s - 1 + c < BTC_NSLOT) && sv[sc];
-          off[c] = ok ? sb[sc] - H : (1 << 29);                 // j = idx - off; invalid slots fail j < N
-          src[c] = fb + (size_t)sc * BTC_SLOT + 256 - H;
-        }
-#pragma unroll 2
-        for(int idx = lo + lane; idx < hi; idx += 32) {
-          float acc = 0.f;
-          if(idx < ny_b) {
-#pragma unroll
-            for(int c = 0; c < 4; c ++) {
-              const int j = idx - off[c];
-              if((unsigned)j < (unsigned)N) acc += src[c][j];
-            }
-          }
-          yrow[idx] = acc;
-        }
-      }
+      for(int s = first + ((wO - first) & 3); s <= last; s += BTC_OUT_WARPS)
+        btc_emit_tile(s, lane, t0, nf, ny_b, N, H, P.nsamp, sb, sv, fb, yrow);
     };
     for(int grp = 0; grp < BTC_NSLOT / 4; grp ++) {
       int nhmax = 0;
@@ -427,13 +432,15 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) hm_bank_tc_kernel(BankParams P
       if(wO == 0) BTC_STAMP(0, 23);
       gi ++;
     }
-    if(next_tile <= F) emit_tiles(next_tile, F);
+    if(tid == BTC_GEN_THREADS) *tail_s = next_tile;             // the tiles left over are shared by all warps below
   }
   if(warp == 20) BTC_STAMP(2, 42);
   tc::fence_before_sync();
   __syncthreads();
   if(warp == 20) BTC_STAMP(2, 43);
   if(warp == 0) tc::tmem_dealloc(tbase, 512);
+  for(int s = *tail_s + warp; s <= F; s += BTC_THREADS / 32)
+    btc_emit_tile(s, lane, t0, nf, ny_b, N, H, P.nsamp, sb, sv, fb, P.y_sin + (size_t)b * P.stride);
 }
 
 static inline size_t bank_tc_smem_bytes() {
