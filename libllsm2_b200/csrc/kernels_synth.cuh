@@ -225,9 +225,8 @@ static inline void launch_hm_bank_t(const BankParams& P, dim3 grid, size_t smem,
 
 // LLSM_BANK_TC=0 forces the CUDA-core bank (hm_bank_ola_kernel); default: tensor-core bank where it applies
 static inline int bank_tc_enabled() {
-  static int v = -1;
-  if(v < 0) { const char* e = getenv("LLSM_BANK_TC"); v = e ? atoi(e) : 1; }
-  return v;
+  const char* e = getenv("LLSM_BANK_TC");     // read per launch: the tests switch between the two banks
+  return e ? atoi(e) : 1;
 }
 
 static inline int bank_variant() {

@@ -41,3 +41,18 @@ def test_product_never_imports_oracle():
                 assert "oracle/" not in txt and "libllsm2_ref" not in txt, f
                 if f.endswith(".py"):
                     assert "emu" not in txt.replace("enumerate", ""), f
+
+
+def test_library_contains_tcgen05_code():
+    """The harmonic bank's tensor-core path is real sm_100a tcgen05 code (UTCHMMA = tcgen05.mma, STTM / LDTM =
+    tcgen05.st / ld), not a fallback: checked in the SASS of the built library."""
+    import shutil
+    import subprocess
+    from libllsm2_b200 import _lib
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", _lib._SO], capture_output=True, text=True).stdout
+    assert "hm_bank_tc_kernel" in sass
+    for op in ("UTCHMMA", "STTM", "LDTM", "UTCBAR"):
+        assert op in sass, op

@@ -196,3 +196,33 @@ def test_harmonics_only_entry(ctx):
     ys = L.synthesize_harmonics(ctx, conf, _to_dev(fr), ny, with_options=False)
     torch.cuda.synchronize()
     assert S.rms(ys.cpu().numpy() - ref[1]) < TOL
+
+
+@pytest.mark.parametrize("shape", [
+    dict(B=3, F=130, kw=dict(seed=21)),                                              # 5 ms hop, 128 harmonics
+    dict(B=2, F=150, kw=dict(seed=22, thop=128 / 44100.0, nhar=200, maxnhar=400, nhar_e=5, npsd=128,
+                             f0_lo=70, f0_hi=200)),                                  # 128-sample hop, > 128 harmonics
+    dict(B=2, F=67, kw=dict(seed=23, nhar=40, maxnhar=40)),                          # two chunks, one short segment
+    dict(B=4, F=200, kw=dict(seed=24), nfrm_utt=[200, 1, 63, 131]),                  # ragged batch
+])
+def test_tensor_core_bank_matches_cuda_core_bank(ctx, shape, monkeypatch):
+    """hm_bank_tc_kernel (tcgen05 GEMM of generated phasors) against hm_bank_ola_kernel (direct FP32
+    summation) and against the oracle, harmonic component only (layer0.c:117-146)."""
+    import torch
+    import libllsm2_b200 as L
+    fr, conf = S.synth_frames(shape["B"], shape["F"], **shape["kw"])
+    if "nfrm_utt" in shape:
+        fr["nfrm_utt"] = np.asarray(shape["nfrm_utt"], np.int32)
+    fr["f0"][:, 40:52] = 0                                     # a run of unvoiced frames: whole groups are skipped
+    ref = S.ref_synthesize(fr, conf, seed=5)[1]
+    d = _to_dev(fr)
+    ny = ref.shape[1]
+    got = {}
+    for tc in ("1", "0"):
+        monkeypatch.setenv("LLSM_BANK_TC", tc)
+        got[tc] = L.synthesize_harmonics(ctx, conf, d, ny).cpu().numpy()
+        torch.cuda.synchronize()
+    e_tc, e_cc, e_x = S.rms(got["1"] - ref), S.rms(got["0"] - ref), S.rms(got["1"] - got["0"])
+    print("y_sin RMS error: tensor-core %.2e, CUDA-core %.2e, between %.2e, signal %.3f" % (e_tc, e_cc, e_x, S.rms(ref)))
+    assert e_cc < 1e-6 and e_tc < 2e-6 and e_x < 2e-6          # the bar is 1e-4 (TOL); both sit far below
+    assert np.abs(got["1"] - got["0"]).max() < 2e-5
