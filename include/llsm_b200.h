@@ -171,6 +171,18 @@ typedef struct {
   int    nspec;          /* LLSM_CONF_NSPEC = nfft / 2 + 1 */
 } llsm_b200_layer1;
 
+/* ---- chunk phase utilities, in place on device arrays ----
+   What real use runs between analysis and synthesis (test/test-layer0-anasynth.c:62-63, test-llsmrt.c:88,112):
+     llsm_chunk_phasepropagate(chunk, sign)      layer0.c:694-706  theta_i = cumsum(f0)_i thop sign 2 pi
+     llsm_chunk_phasesync_rps(chunk, l1_based)   layer0.c:687-692  theta_i = -phse_i[0]  (-VSPHSE_i[0] when l1_based)
+   followed by llsm_frame_phaseshift (frame.c:152-166): phse[k], the envelope phases ephse[c][k] and VSPHSE[k]
+   become wrap(. + theta_i (k + 1)). Reads frames->{f0, nhar, enhar}; rewrites frames->{phse, ephse} and, when
+   layer1 != NULL, layer1->vsphse (lengths layer1->nvs). */
+int llsm_b200_chunk_phasepropagate(llsm_b200_ctx* ctx, const llsm_b200_conf* conf, const int* nfrm_utt,
+  const llsm_b200_frames_out* frames, const llsm_b200_layer1* layer1, int sign);
+int llsm_b200_chunk_phasesync_rps(llsm_b200_ctx* ctx, const llsm_b200_conf* conf, const int* nfrm_utt,
+  const llsm_b200_frames_out* frames, const llsm_b200_layer1* layer1, int layer1_based);
+
 /* llsm_chunk_tolayer1 (layer1.c:129-149) for a batch: Rd track (glottal fitting + smoothing),
    vocal-tract envelope and source phases of every voiced frame. Device pointers. Reads
    frames->{nfrm_utt, f0, nhar, ampl, phse}. nfft as in the reference call (power of two). */

@@ -64,6 +64,9 @@ def lib():
                                        C.POINTER(C.c_int)]
     L.llsm_b200_rt_feed_l1_host.argtypes = [P, C.POINTER(abi.Frames), C.POINTER(abi.Layer1), P, C.c_int, P, P, P, P,
                                             C.c_int, C.POINTER(C.c_int)]
+    L.llsm_b200_chunk_phasepropagate.argtypes = [P, C.POINTER(abi.Conf), P, C.POINTER(abi.FramesOut),
+                                                 C.POINTER(abi.Layer1), C.c_int]
+    L.llsm_b200_chunk_phasesync_rps.argtypes = L.llsm_b200_chunk_phasepropagate.argtypes
     _lib = L
     return L
 

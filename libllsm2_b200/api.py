@@ -335,3 +335,27 @@ class RtSynth:
             self.close()
         except Exception:
             pass
+
+
+def _phase_op(fn, ctx, conf, frames, layer1, arg):
+    fo = abi.FramesOut()
+    for k in ("f0", "nhar", "phse", "enhar", "ephse"):
+        setattr(fo, k, _ptr(frames[k]))
+    l1 = None
+    if layer1 is not None:
+        l1 = abi.Layer1()
+        l1.vsphse, l1.nvs = _ptr(layer1["vsphse"]), _ptr(layer1["nvs"])
+    check(fn(ctx._h, C.byref(conf), _ptr(frames.get("nfrm_utt")), C.byref(fo),
+             C.byref(l1) if l1 is not None else None, int(arg)))
+
+
+def chunk_phasepropagate(ctx, conf, frames, layer1=None, sign=1):
+    """llsm_chunk_phasepropagate (layer0.c:694-706) on CUDA tensors, in place: frames["phse"], frames["ephse"]
+    and layer1["vsphse"] are shifted by the running phase 2 pi thop sign cumsum(f0)."""
+    _phase_op(lib().llsm_b200_chunk_phasepropagate, ctx, conf, frames, layer1, sign)
+
+
+def chunk_phasesync_rps(ctx, conf, frames, layer1=None, layer1_based=0):
+    """llsm_chunk_phasesync_rps (layer0.c:687-692) on CUDA tensors, in place: every frame is shifted so that its
+    first harmonic (or first source harmonic when layer1_based) has zero phase."""
+    _phase_op(lib().llsm_b200_chunk_phasesync_rps, ctx, conf, frames, layer1, layer1_based)

@@ -6,6 +6,7 @@
 #include "driver_layer1.h"
 #include "driver_pbp.h"
 #include "driver_rt.h"
+#include "kernels_phase.cuh"
 #include <cstdio>
 #include <cstdarg>
 #include <mutex>
@@ -34,7 +35,7 @@ struct llsm_b200_ctx {
   AnaScratch ascratch;
   std::unique_ptr<L1PlanDev> l1plan;
   PbpScratch pbp;
-  DevBuf ny_utt;
+  DevBuf ny_utt, phase_theta;
   DevBuf stage[24];          // device staging for the *_host entry points
   // copy / compute pipeline of synthesize_l0_host: two slots of input and output staging
   cudaStream_t s_in = nullptr, s_out = nullptr;

@@ -378,3 +378,32 @@ double ref_time_analyze(int nrep, const float* x, int nx, float fs, const float*
   llsm_delete_aoptions(opt);
   return tot;
 }
+
+/* chunk phase utilities (layer0.c:687-706): op 0 = llsm_chunk_phasepropagate(chunk, arg), op 1 =
+   llsm_chunk_phasesync_rps(chunk, arg). phse / ephse (and vsphse when given) are rewritten in place. */
+int ref_phase_op_soa(int nfrm, float fs, float thop, int maxnhar, int maxnhar_e, int nchannel,
+  const float* f0, const int* nhar, const float* ampl, float* phse, const int* enhar, const float* eampl,
+  float* ephse, float* vsphse, const int* nvs, int op, int arg) {
+  float cf[7] = {2000, 4000, 8000, 12000, 14000, 16000, 18000};
+  llsm_chunk* chunk = chunk_from_soa(nfrm, fs, thop, maxnhar, maxnhar_e, 8, nchannel, cf, 0.015f,
+    f0, nhar, ampl, phse, NULL, NULL, NULL, enhar, eampl, ephse);
+  if(vsphse != NULL)
+    for(int i = 0; i < nfrm; i ++) if(nvs[i] > 0) {
+      FP_TYPE* vs = llsm_create_fparray(nvs[i]);
+      memcpy(vs, vsphse + (size_t)i * maxnhar, nvs[i] * sizeof(float));
+      llsm_container_attach(chunk -> frames[i], LLSM_FRAME_VSPHSE, vs, llsm_delete_fparray, llsm_copy_fparray);
+    }
+  if(op == 0) llsm_chunk_phasepropagate(chunk, arg);
+  else llsm_chunk_phasesync_rps(chunk, arg);
+  for(int i = 0; i < nfrm; i ++) {
+    llsm_hmframe* hm = llsm_container_get(chunk -> frames[i], LLSM_FRAME_HM);
+    if(hm != NULL) memcpy(phse + (size_t)i * maxnhar, hm -> phse, hm -> nhar * sizeof(float));
+    llsm_nmframe* nm = llsm_container_get(chunk -> frames[i], LLSM_FRAME_NM);
+    for(int c = 0; c < nchannel; c ++)
+      memcpy(ephse + ((size_t)i * nchannel + c) * maxnhar_e, nm -> eenv[c] -> phse, nm -> eenv[c] -> nhar * sizeof(float));
+    FP_TYPE* vs = llsm_container_get(chunk -> frames[i], LLSM_FRAME_VSPHSE);
+    if(vs != NULL && vsphse != NULL) memcpy(vsphse + (size_t)i * maxnhar, vs, llsm_fparray_length(vs) * sizeof(float));
+  }
+  llsm_delete_chunk(chunk);
+  return 0;
+}

@@ -168,3 +168,15 @@ extern "C" int emu_rtsynth_l1(const llsm_b200_conf* conf, const llsm_b200_frames
   R.release(); lp.release();
   return 0;
 }
+
+#include "../../libllsm2_b200/csrc/kernels_phase.cuh"
+extern "C" int emu_phase_op(const llsm_b200_conf* conf, const int* nfrm_utt, const llsm_b200_frames_out* fr,
+  const llsm_b200_layer1* l1, int mode, int arg) {
+  std::vector<float> theta((size_t)conf->nutt * conf->nfrm);
+  PhaseParams P; memset(&P, 0, sizeof(P));
+  P.nutt = conf->nutt; P.nfrm = conf->nfrm; P.maxnhar = conf->maxnhar; P.maxnhar_e = conf->maxnhar_e; P.nchannel = conf->nchannel;
+  P.nfrm_utt = nfrm_utt; P.f0 = fr->f0; P.nhar = fr->nhar; P.phse = fr->phse; P.enhar = fr->enhar; P.ephse = fr->ephse;
+  if(l1) { P.vsphse = l1->vsphse; P.nvs = l1->nvs; }
+  P.thop = conf->thop; P.mode = mode; P.arg = arg; P.theta = theta.data();
+  return run_phase_op(P, nullptr, nullptr);
+}

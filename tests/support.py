@@ -258,3 +258,22 @@ def ref_rt_white(conf, seed=1):
     for b in range(conf.nutt):
         lib.ref_draw_white_noise(int(conf.fs), conf.nchannel, C.c_uint(seed + b), _p(out[b]))
     return out
+
+
+def ref_phase_op(fr, conf, op, arg, vsphse=None, nvs=None):
+    """llsm_chunk_phasepropagate (op 0, arg = sign) / llsm_chunk_phasesync_rps (op 1, arg = layer1_based) of the
+    reference build on copies of the phase arrays; returns dict(phse, ephse[, vsphse])."""
+    lib = load_ref()
+    B, F = conf.nutt, conf.nfrm
+    o = dict(phse=fr["phse"].copy(), ephse=fr["ephse"].copy())
+    if vsphse is not None:
+        o["vsphse"] = vsphse.copy()
+    for b in range(B):
+        nf = int(fr["nfrm_utt"][b]) if fr.get("nfrm_utt") is not None else F
+        lib.ref_phase_op_soa(nf, C.c_float(conf.fs), C.c_float(conf.thop), conf.maxnhar, conf.maxnhar_e, conf.nchannel,
+                             _p(np.ascontiguousarray(fr["f0"][b])), _p(np.ascontiguousarray(fr["nhar"][b])),
+                             _p(np.ascontiguousarray(fr["ampl"][b])), _p(o["phse"][b]),
+                             _p(np.ascontiguousarray(fr["enhar"][b])), _p(np.ascontiguousarray(fr["eampl"][b])),
+                             _p(o["ephse"][b]), _p(o["vsphse"][b]) if vsphse is not None else None,
+                             _p(np.ascontiguousarray(nvs[b])) if nvs is not None else None, int(op), int(arg))
+    return o
