@@ -17,13 +17,21 @@
 // FP32 -- 2^-21 relative per term, as good as the FP32 recurrences of the CUDA-core kernel.
 //
 // A is written from registers straight into tensor memory (tcgen05.st), B goes through shared memory
-// (K-major core matrices, no swizzle), the accumulators live in tensor memory. One CTA per SM, warp
-// specialised: 16 warps generate operands (A and B double-buffered: 2 x 128 tensor-memory columns,
-// 2 x 16 KB), 4 warps issue the MMAs -- one issuing thread sustains one small MMA per ~45 cycles while the
-// pipe takes one per 16 (tools/tc_rate.cu), so four issue concurrently, each into its own accumulator
-// (double-buffered too: the previous group's accumulators are read back, windowed and parked while the next
-// group's MMAs run). Hand-over through mbarriers: full[buf] (generators -> issuers), empty[buf] and
-// dfull[dbuf] (tcgen05.commit -> generators). Finished output tiles are written group by group.
+// (K-major core matrices, no swizzle), the accumulators live in tensor memory. One CTA per SM (all 512
+// tensor-memory columns: a three-deep ring of A operands, 3 x 128 columns, and two sets of U / V accumulators,
+// 2 x 64), 21 warps, warp specialised:
+//   warps  0..7   A rows: two interleaved harmonic recurrences per thread, 16 harmonics of a 32-harmonic chunk,
+//                 hi / lo split, tcgen05.st; afterwards the next group's coefficients a_k e^{i phi_k} (cfull[])
+//   warps  8..15  B columns, two teams of four on alternate chunks, into a three-deep 16 KB ring
+//   warps 16..19  read-back: tcgen05.ld of the finished accumulators (dfull[] / dempty[]), window, park the
+//                 frame, overlap-add and write every output tile whose frames are complete
+//   warp  20      issues the 24 MMAs of a chunk from one elected lane of the converged warp -- the operands are
+//                 then warp-uniform and the MMAs leave at the tensor pipe's own rate, 16 cycles each; issued
+//                 behind a plain `lane == 0` branch they cost 45 (tools/tc_rate.cu) -- and frees the ring with
+//                 tcgen05.commit (empty[])
+// full[] counts the eight A warps and the four B warps of a chunk. Phasor seeds: the turn count is reduced
+// exactly in 64-bit fixed point, sine and cosine come from the special-function unit.
+// BTC_STAMP is a tracing hook (tools/btc_trace.cu); it compiles to nothing in the library.
 #pragma once
 #ifndef LLSM_EMU
 #include "tcgen05.cuh"
@@ -173,8 +181,13 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) hm_bank_tc_kernel(BankParams P
       const float f0n = f0 / P.fs;
       const float omega0 = (float)(2.0 * LLSM_PI * (double)f0n);
       bool iczt = false;
-      if(P.has_options && P.use_iczt)
-        iczt = log((double)N) * (double)P.iczt_a < log((double)nh) - (double)P.iczt_b;
+      if(P.has_options && P.use_iczt) {
+        // log(N) a < log(nh) - b (llsmutils.c:51-53) <=> nh > exp(log(N) a + b), precomputed on the host; the two
+        // logarithms are only evaluated when nh sits on the threshold
+        iczt = (double)nh > P.iczt_nh;
+        if(fabs((double)nh - P.iczt_nh) < 1e-6 * P.iczt_nh)
+          iczt = log((double)N) * (double)P.iczt_a < log((double)nh) - (double)P.iczt_b;
+      }
       if(iczt && nh > N - 1) nh = N - 1;
       fi.nufix = __double2ull_rn((iczt ? (double)omega0 / (2.0 * LLSM_PI) : (double)f0n) * 18446744073709551616.0);
       const float frac = P.hm_frac[f];
@@ -448,7 +461,8 @@ static inline size_t bank_tc_smem_bytes() {
 }
 
 // tensor-core path when the window fits the 32 x 8 sample grid; returns -1 otherwise
-static inline int launch_hm_bank_tc(const BankParams& P, int nutt, int nfrm_max, cudaStream_t st) {
+static inline int launch_hm_bank_tc(BankParams P, int nutt, int nfrm_max, cudaStream_t st) {
+  P.iczt_nh = exp(log((double)P.n_hm) * (double)P.iczt_a + (double)P.iczt_b);
   if((P.n_hm >> 1) > BTC_MAXH || (P.n_hm & 1) || P.maxnhar > BTC_CST) return -1;
   const int F = BTC_NSLOT - 2;
   const int nseg = (std::max(nfrm_max, 1) + F - 1) / F;

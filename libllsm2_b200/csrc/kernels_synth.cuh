@@ -40,6 +40,7 @@ struct BankParams {
   int npass;                // frame slots per CTA = warps * npass
   float hop;                // thop * fs (float product): hm_base[f] = round(f * hop)
   float* y_sin;             // [B][stride]
+  double iczt_nh;           // tensor-core bank: exp(log(n_hm) a + b), the harmonic count above which the ICZT branch is taken
 };
 
 #define BANK_KC 64          // harmonics staged per chunk
