@@ -171,6 +171,21 @@ typedef struct {
   int    nspec;          /* LLSM_CONF_NSPEC = nfft / 2 + 1 */
 } llsm_b200_layer1;
 
+/* ---- frame coder: coder.c:46-292 for a batch, device pointers ----
+   A frame <-> a vector of order_spec + order_bap + 3 numbers: [voicing, f0, Rd, order_spec mel-cepstral
+   coefficients of the total power spectrum, order_bap band aperiodicities] (llsm_create_coder(conf, order_spec,
+   order_bap), llsm_coder_encode, llsm_coder_decode_layer0 / _layer1). nspec = LLSM_CONF_NSPEC (nfft / 2 + 1 of the
+   layer-1 conversion). Encoding reads f0, psd and, for voiced frames, rd and vtmagn; enc is [B][F][dim].
+   Decoding writes f0, rd, psd, nhar and either ampl / phse (use_layer1 = 0: llsm_coder_decode_layer0) or
+   layer1->vtmagn / vsphse (use_layer1 = 1; layer1->nvs receives nhar). Rows of ampl / phse / vsphse are
+   conf->maxnhar long: a decoded frame with more harmonics than that (f0 < fnyq / maxnhar) is cut there. */
+int llsm_b200_coder_dimension(int order_spec, int order_bap);
+int llsm_b200_coder_encode(llsm_b200_ctx* ctx, const llsm_b200_conf* conf, const int* nfrm_utt,
+  const float* f0, const float* psd, const llsm_b200_layer1* layer1, int order_spec, int order_bap, float* enc);
+int llsm_b200_coder_decode(llsm_b200_ctx* ctx, const llsm_b200_conf* conf, const int* nfrm_utt,
+  const float* enc, int order_spec, int order_bap, int use_layer1,
+  const llsm_b200_frames_out* out, const llsm_b200_layer1* layer1);
+
 /* ---- chunk phase utilities, in place on device arrays ----
    What real use runs between analysis and synthesis (test/test-layer0-anasynth.c:62-63, test-llsmrt.c:88,112):
      llsm_chunk_phasepropagate(chunk, sign)      layer0.c:694-706  theta_i = cumsum(f0)_i thop sign 2 pi

@@ -67,6 +67,10 @@ def lib():
     L.llsm_b200_chunk_phasepropagate.argtypes = [P, C.POINTER(abi.Conf), P, C.POINTER(abi.FramesOut),
                                                  C.POINTER(abi.Layer1), C.c_int]
     L.llsm_b200_chunk_phasesync_rps.argtypes = L.llsm_b200_chunk_phasepropagate.argtypes
+    L.llsm_b200_coder_dimension.argtypes = [C.c_int, C.c_int]
+    L.llsm_b200_coder_encode.argtypes = [P, C.POINTER(abi.Conf), P, P, P, C.POINTER(abi.Layer1), C.c_int, C.c_int, P]
+    L.llsm_b200_coder_decode.argtypes = [P, C.POINTER(abi.Conf), P, P, C.c_int, C.c_int, C.c_int,
+                                         C.POINTER(abi.FramesOut), C.POINTER(abi.Layer1)]
     _lib = L
     return L
 

@@ -359,3 +359,41 @@ def chunk_phasesync_rps(ctx, conf, frames, layer1=None, layer1_based=0):
     """llsm_chunk_phasesync_rps (layer0.c:687-692) on CUDA tensors, in place: every frame is shifted so that its
     first harmonic (or first source harmonic when layer1_based) has zero phase."""
     _phase_op(lib().llsm_b200_chunk_phasesync_rps, ctx, conf, frames, layer1, layer1_based)
+
+
+def coder_encode(ctx, conf, f0, psd, layer1, order_spec=64, order_bap=5, nfrm_utt=None):
+    """llsm_coder_encode (coder.c:85-163) for every frame, CUDA tensors: f0 [B][F], psd [B][F][npsd], layer1 =
+    dict(rd, vtmagn) -> [B][F][order_spec + order_bap + 3]."""
+    import torch
+    dim = order_spec + order_bap + 3
+    enc = torch.zeros((conf.nutt, conf.nfrm, dim), dtype=torch.float32, device=f0.device)
+    l1 = abi.Layer1()
+    l1.rd, l1.vtmagn, l1.nspec = _ptr(layer1["rd"]), _ptr(layer1["vtmagn"]), layer1["vtmagn"].shape[-1]
+    check(lib().llsm_b200_coder_encode(ctx._h, C.byref(conf), _ptr(nfrm_utt), _ptr(f0), _ptr(psd), C.byref(l1),
+                                       int(order_spec), int(order_bap), _ptr(enc)))
+    return enc
+
+
+def coder_decode(ctx, conf, enc, nspec, order_spec=64, order_bap=5, use_layer1=True, nfrm_utt=None):
+    """llsm_coder_decode_layer1 / _layer0 (coder.c:165-292) for every frame, CUDA tensors. Returns dict(f0, rd, psd,
+    nhar) plus vtmagn, vsphse (layer 1) or ampl, phse (layer 0)."""
+    import torch
+    dev = enc.device
+    B, F = conf.nutt, conf.nfrm
+    o = {"f0": torch.zeros((B, F), dtype=torch.float32, device=dev), "rd": torch.zeros((B, F), dtype=torch.float32, device=dev),
+         "psd": torch.zeros((B, F, conf.npsd), dtype=torch.float32, device=dev),
+         "nhar": torch.zeros((B, F), dtype=torch.int32, device=dev)}
+    fo, l1 = abi.FramesOut(), abi.Layer1()
+    fo.f0, fo.psd, fo.nhar = _ptr(o["f0"]), _ptr(o["psd"]), _ptr(o["nhar"])
+    l1.rd, l1.nspec = _ptr(o["rd"]), int(nspec)
+    if use_layer1:
+        o["vtmagn"] = torch.zeros((B, F, nspec), dtype=torch.float32, device=dev)
+        o["vsphse"] = torch.zeros((B, F, conf.maxnhar), dtype=torch.float32, device=dev)
+        l1.vtmagn, l1.vsphse = _ptr(o["vtmagn"]), _ptr(o["vsphse"])
+    else:
+        o["ampl"] = torch.zeros((B, F, conf.maxnhar), dtype=torch.float32, device=dev)
+        o["phse"] = torch.zeros((B, F, conf.maxnhar), dtype=torch.float32, device=dev)
+        fo.ampl, fo.phse = _ptr(o["ampl"]), _ptr(o["phse"])
+    check(lib().llsm_b200_coder_decode(ctx._h, C.byref(conf), _ptr(nfrm_utt), _ptr(enc), int(order_spec), int(order_bap),
+                                       1 if use_layer1 else 0, C.byref(fo), C.byref(l1)))
+    return o

@@ -7,6 +7,7 @@
 #include "driver_pbp.h"
 #include "driver_rt.h"
 #include "kernels_phase.cuh"
+#include "driver_coder.h"
 #include <cstdio>
 #include <cstdarg>
 #include <mutex>
@@ -34,6 +35,7 @@ struct llsm_b200_ctx {
   SynthScratch scratch;
   AnaScratch ascratch;
   std::unique_ptr<L1PlanDev> l1plan;
+  std::unique_ptr<CoderPlanDev> coderplan;
   PbpScratch pbp;
   DevBuf ny_utt, phase_theta;
   DevBuf stage[24];          // device staging for the *_host entry points

@@ -316,7 +316,11 @@ __device__ __forceinline__ StretchIdx stretch_index(int nx, int ny, int p) {
     s.base = p;
     if(ny > nx && p >= nx - overlap) s.ii = p - (nx - overlap);
   } else {
-    int q = (p - nx) / period;          // copy segment after the first template
+    // copy segment after the first template: (p - nx) / period by a float reciprocal and one correction
+    // (exact: p - nx < 2^24 and the estimate is within one of the quotient)
+    int q = (int)((float)(p - nx) * (1.0f / (float)period));
+    if(q * period > p - nx) q --;
+    else if((q + 1) * period <= p - nx) q ++;
     int head = nx + q * period;
     int i = p - head;
     s.base = i + overlap;
@@ -357,19 +361,23 @@ __global__ void __launch_bounds__(EXC_THREADS) noise_excitation_kernel(ExcParams
 
   // frames that can reach [p0, p0 + EXC_TILE): env_off + n_env + 1 > p0 and env_off - 1 <= pend, with
   // env_off[i] = round((i - 1) * hop): bounds from the hop arithmetic (one frame of slack), then made exact
-  // with a couple of table reads (every extra frame costs a test per output sample)
-  int ia, ib;
-  {
+  // with a couple of table reads (every extra frame costs a test per output sample). One thread does the
+  // search for the CTA.
+  int* srange = (int*)(fr + EXC_FCHUNK * fstride);
+  if(threadIdx.x == 0) {
     const int pend = p0 + EXC_TILE - 1;
     const float inv_hop = 1.0f / P.hop;
-    ia = (int)floorf((float)(p0 - P.n_env - 1) * inv_hop);
-    ib = (int)floorf((float)(pend + 1) * inv_hop) + 3;
-    if(ia < 0) ia = 0;
-    if(ib > nf) ib = nf;
-    if(ia > ib) ia = ib;
-    while(ia < ib && P.env_off[ia] + P.n_env + 1 <= p0) ia ++;
-    while(ib > ia && P.env_off[ib - 1] - 1 > pend) ib --;
+    int a = (int)floorf((float)(p0 - P.n_env - 1) * inv_hop);
+    int bb = (int)floorf((float)(pend + 1) * inv_hop) + 3;
+    if(a < 0) a = 0;
+    if(bb > nf) bb = nf;
+    if(a > bb) a = bb;
+    while(a < bb && P.env_off[a] + P.n_env + 1 <= p0) a ++;
+    while(bb > a && P.env_off[bb - 1] - 1 > pend) bb --;
+    srange[0] = a; srange[1] = bb;
   }
+  __syncthreads();
+  const int ia = srange[0], ib = srange[1];
 
   float env[EXC_SPT][MAXCH];
 #pragma unroll
@@ -381,9 +389,12 @@ __global__ void __launch_bounds__(EXC_THREADS) noise_excitation_kernel(ExcParams
   for(int i0 = ia; i0 < ib; i0 += EXC_FCHUNK) {
     const int nfc = min(EXC_FCHUNK, ib - i0);
     __syncthreads();
-    // ---- stage frame parameters
-    for(int e = threadIdx.x; e < nfc * fstride; e += blockDim.x) {
-      int fi = e / fstride, q = e - fi * fstride;
+    // ---- stage frame parameters (slot e -> frame e / 64, field e % 64 when a frame fits 64 fields: no divisions)
+    const bool pow2 = fstride <= 64;
+    for(int e = threadIdx.x; e < nfc * (pow2 ? 64 : fstride); e += blockDim.x) {
+      int fi, q;
+      if(pow2) { fi = e >> 6; q = e & 63; if(q >= fstride) continue; }
+      else { fi = e / fstride; q = e - fi * fstride; }
       int i = i0 + fi;
       float f0 = P.f0[row + i];
       float v;
@@ -392,7 +403,10 @@ __global__ void __launch_bounds__(EXC_THREADS) noise_excitation_kernel(ExcParams
       else if(q == 2) v = __int_as_float(P.env_off[i]);
       else if(q == 3) v = __int_as_float(P.env_contig[i]);
       else {
-        int qq = q - 4, c = qq / (2 + 2 * mne), w = qq - c * (2 + 2 * mne);
+        int qq = q - 4, c = 0;
+        const int per = 2 + 2 * mne;
+        while(qq >= per) { qq -= per; c ++; }                  // at most nchannel - 1 steps
+        const int w = qq;
         size_t ec = (row + i) * nch + c;
         int nh = f0 > 0 ? P.enhar[ec] : 0;                   // layer0.c:298 unvoiced -> 0 harmonics
         if(nh > mne) nh = mne;
@@ -407,7 +421,7 @@ __global__ void __launch_bounds__(EXC_THREADS) noise_excitation_kernel(ExcParams
           } else v = 0.f;
         }
       }
-      fr[e] = v;
+      fr[fi * fstride + q] = v;
     }
     __syncthreads();
 #pragma unroll
@@ -476,7 +490,7 @@ __global__ void __launch_bounds__(EXC_THREADS) noise_excitation_kernel(ExcParams
 }
 
 static inline size_t exc_smem_bytes(int nchannel, int maxnhar_e) {
-  return (size_t)EXC_FCHUNK * (4 + nchannel * (2 + 2 * maxnhar_e)) * 4 + 16;
+  return (size_t)EXC_FCHUNK * (4 + nchannel * (2 + 2 * maxnhar_e)) * 4 + 32;
 }
 
 static inline int launch_noise_excitation(const ExcParams& P, int nutt, cudaStream_t st) {

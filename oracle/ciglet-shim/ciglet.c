@@ -685,3 +685,20 @@ void delete_ifdetector(ifdetector* dst) {
   free(dst -> hr); free(dst -> hi); free(dst -> hdr); free(dst -> hdi);
   free(dst);
 }
+
+/* ---- ddct (coder.c:27,149-152,189-192): Ooura's in-place cosine transform, by its published definition
+   (fft4g.c header): isgn = -1  C[k] = sum_{j<n} a[j] cos(pi (j + 1/2) k / n)   (DCT)
+                     isgn = +1  C[k] = sum_{j<n} a[j] cos(pi j (k + 1/2) / n)   (inverse DCT without scale;
+   "a[0] *= 0.5; ddct(n, 1, a); a[j] *= 2 / n" inverts isgn = -1, which is how coder.c uses the pair).
+   Direct O(n^2) summation in double: test infrastructure, sizes <= 1024. ---- */
+void ddct(int n, int isgn, FP_TYPE* a) {
+  double* c = calloc(n > 0 ? n : 1, sizeof(double));
+  for(int k = 0; k < n; k ++) {
+    double acc = 0;
+    if(isgn < 0) for(int j = 0; j < n; j ++) acc += (double)a[j] * cos(M_PI * (j + 0.5) * k / n);
+    else         for(int j = 0; j < n; j ++) acc += (double)a[j] * cos(M_PI * j * (k + 0.5) / n);
+    c[k] = acc;
+  }
+  for(int k = 0; k < n; k ++) a[k] = c[k];
+  free(c);
+}

@@ -83,6 +83,10 @@ static inline FP_TYPE wrap(FP_TYPE p) {
 }
 static inline FP_TYPE phase_diff(FP_TYPE a, FP_TYPE b) { return wrap(b - a); }
 
+/* ---- mel scale (coder.c:65-70). Decision: the HTK / O'Shaughnessy curve mel = 1125 ln(1 + f / 700). ---- */
+static inline FP_TYPE freq2mel(FP_TYPE f) { return 1125.0 * log(1.0 + f / 700.0); }
+static inline FP_TYPE mel2freq(FP_TYPE m) { return 700.0 * (exp(m / 1125.0) - 1.0); }
+
 /* ---- memory / vector helpers ---- */
 void** malloc2d(size_t n, size_t m, size_t size);
 #define free2d(ptr, n) cig_free2d((void**)(ptr), (n))

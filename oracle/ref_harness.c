@@ -407,3 +407,87 @@ int ref_phase_op_soa(int nfrm, float fs, float thop, int maxnhar, int maxnhar_e,
   llsm_delete_chunk(chunk);
   return 0;
 }
+
+/* ---- coder (coder.c:46-292): frame <-> fixed-dimension vector of order_spec + order_bap + 3 numbers ----
+   Encoding reads F0, the noise PSD and (voiced frames) the layer-1 members RD, VTMAGN. */
+int ref_coder_encode_soa(int nfrm, float fs, float thop, int maxnhar, int npsd, int nchannel, int maxnhar_e,
+  float lip_radius, int nspec, int order_spec, int order_bap,
+  const float* f0, const float* psd, const float* rd, const float* vtmagn, float* enc) {
+  float cf[7] = {2000, 4000, 8000, 12000, 14000, 16000, 18000};
+  llsm_chunk* chunk = chunk_from_soa(nfrm, fs, thop, maxnhar, maxnhar_e, npsd, nchannel, cf, lip_radius,
+    f0, NULL, NULL, NULL, psd, NULL, NULL, NULL, NULL, NULL);
+  llsm_container_attach(chunk -> conf, LLSM_CONF_NSPEC, llsm_create_int(nspec), llsm_delete_int, llsm_copy_int);
+  llsm_coder* coder = llsm_create_coder(chunk -> conf, order_spec, order_bap);
+  int dim = order_spec + order_bap + 3;
+  for(int i = 0; i < nfrm; i ++) {
+    llsm_container* fr = chunk -> frames[i];
+    llsm_container_attach(fr, LLSM_FRAME_RD, llsm_create_fp(rd[i]), llsm_delete_fp, llsm_copy_fp);
+    if(f0[i] > 0) {
+      FP_TYPE* vt = llsm_create_fparray(nspec);
+      memcpy(vt, vtmagn + (size_t)i * nspec, nspec * sizeof(float));
+      llsm_container_attach(fr, LLSM_FRAME_VTMAGN, vt, llsm_delete_fparray, llsm_copy_fparray);
+    }
+    FP_TYPE* e = llsm_coder_encode(coder, fr);
+    memcpy(enc + (size_t)i * dim, e, dim * sizeof(float));
+    free(e);
+  }
+  llsm_delete_coder(coder);
+  llsm_delete_chunk(chunk);
+  return 0;
+}
+
+/* Decoding: llsm_coder_decode_layer1 (use_layer1 = 1: RD, VTMAGN, VSPHSE) or _layer0 (HM). Rows of ampl / phse /
+   vsphse are maxnhar long; harmonics beyond that are dropped (nhar_out reports the reference's count). */
+int ref_coder_decode_soa(int nfrm, float fs, float thop, int maxnhar, int npsd, int nchannel, int maxnhar_e,
+  float lip_radius, int nspec, int order_spec, int order_bap, int use_layer1, const float* enc,
+  float* f0, float* rd, float* psd, int* nhar_out, float* ampl, float* phse, float* vtmagn, float* vsphse) {
+  float cf[7] = {2000, 4000, 8000, 12000, 14000, 16000, 18000};
+  llsm_aoptions* opt = llsm_create_aoptions();
+  opt -> thop = thop; opt -> maxnhar = maxnhar; opt -> maxnhar_e = maxnhar_e; opt -> npsd = npsd; opt -> nchannel = nchannel;
+  free(opt -> chanfreq);
+  opt -> chanfreq = calloc(nchannel > 1 ? nchannel - 1 : 1, sizeof(FP_TYPE));
+  for(int c = 0; c < nchannel - 1; c ++) opt -> chanfreq[c] = cf[c];
+  opt -> lip_radius = lip_radius;
+  llsm_container* conf = llsm_aoptions_toconf(opt, fs / 2.0);
+  llsm_container_attach(conf, LLSM_CONF_NSPEC, llsm_create_int(nspec), llsm_delete_int, llsm_copy_int);
+  llsm_coder* coder = llsm_create_coder(conf, order_spec, order_bap);
+  int dim = order_spec + order_bap + 3;
+  for(int i = 0; i < nfrm; i ++) {
+    FP_TYPE* e = calloc(dim, sizeof(FP_TYPE));
+    memcpy(e, enc + (size_t)i * dim, dim * sizeof(float));
+    llsm_container* fr = use_layer1 ? llsm_coder_decode_layer1(coder, e) : llsm_coder_decode_layer0(coder, e);
+    free(e);
+    f0[i] = ((FP_TYPE*)llsm_container_get(fr, LLSM_FRAME_F0))[0];
+    rd[i] = ((FP_TYPE*)llsm_container_get(fr, LLSM_FRAME_RD))[0];
+    llsm_nmframe* nm = llsm_container_get(fr, LLSM_FRAME_NM);
+    memcpy(psd + (size_t)i * npsd, nm -> psd, npsd * sizeof(float));
+    nhar_out[i] = 0;
+    if(use_layer1) {
+      FP_TYPE* vt = llsm_container_get(fr, LLSM_FRAME_VTMAGN);
+      FP_TYPE* vs = llsm_container_get(fr, LLSM_FRAME_VSPHSE);
+      memset(vtmagn + (size_t)i * nspec, 0, nspec * sizeof(float));
+      memset(vsphse + (size_t)i * maxnhar, 0, maxnhar * sizeof(float));
+      if(vt != NULL) memcpy(vtmagn + (size_t)i * nspec, vt, nspec * sizeof(float));
+      if(vs != NULL) {
+        int n = llsm_fparray_length(vs);
+        nhar_out[i] = n;
+        memcpy(vsphse + (size_t)i * maxnhar, vs, (n < maxnhar ? n : maxnhar) * sizeof(float));
+      }
+    } else {
+      llsm_hmframe* hm = llsm_container_get(fr, LLSM_FRAME_HM);
+      memset(ampl + (size_t)i * maxnhar, 0, maxnhar * sizeof(float));
+      memset(phse + (size_t)i * maxnhar, 0, maxnhar * sizeof(float));
+      if(hm != NULL) {
+        int n = hm -> nhar;
+        nhar_out[i] = n;
+        memcpy(ampl + (size_t)i * maxnhar, hm -> ampl, (n < maxnhar ? n : maxnhar) * sizeof(float));
+        memcpy(phse + (size_t)i * maxnhar, hm -> phse, (n < maxnhar ? n : maxnhar) * sizeof(float));
+      }
+    }
+    llsm_delete_container(fr);
+  }
+  llsm_delete_coder(coder);
+  llsm_delete_container(conf);
+  llsm_delete_aoptions(opt);
+  return 0;
+}

@@ -180,3 +180,19 @@ extern "C" int emu_phase_op(const llsm_b200_conf* conf, const int* nfrm_utt, con
   P.thop = conf->thop; P.mode = mode; P.arg = arg; P.theta = theta.data();
   return run_phase_op(P, nullptr, nullptr);
 }
+
+#include "../../libllsm2_b200/csrc/driver_coder.h"
+extern "C" int emu_coder_encode(const llsm_b200_conf* conf, const float* f0, const float* psd, const llsm_b200_layer1* l1,
+  int order_spec, int order_bap, float* enc) {
+  CoderPlanDev cp; if(cp.build(conf->fs, conf->npsd, l1->nspec, order_bap, nullptr) != 0) return -100;
+  int rc = run_coder_encode(cp, *conf, nullptr, f0, psd, l1->rd, l1->vtmagn, order_spec, enc, nullptr, nullptr);
+  cp.release(); return rc;
+}
+extern "C" int emu_coder_decode(const llsm_b200_conf* conf, const float* enc, int order_spec, int order_bap, int use_layer1,
+  const llsm_b200_frames_out* out, const llsm_b200_layer1* l1) {
+  CoderPlanDev cp; if(cp.build(conf->fs, conf->npsd, l1->nspec, order_bap, nullptr) != 0) return -100;
+  L1PlanDev lp; if(lp.build(nullptr) != 0) return -101;
+  int rc = run_coder_decode(cp, lp, *conf, nullptr, enc, order_spec, use_layer1, out->f0, l1->rd, out->psd, out->nhar,
+    out->ampl, out->phse, l1->vtmagn, l1->vsphse, nullptr, nullptr);
+  cp.release(); lp.release(); return rc;
+}

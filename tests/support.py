@@ -277,3 +277,57 @@ def ref_phase_op(fr, conf, op, arg, vsphse=None, nvs=None):
                              _p(o["ephse"][b]), _p(o["vsphse"][b]) if vsphse is not None else None,
                              _p(np.ascontiguousarray(nvs[b])) if nvs is not None else None, int(op), int(arg))
     return o
+
+
+def ref_coder_encode(f0, psd, l1, conf, order_spec, order_bap):
+    """llsm_coder_encode of the reference build (coder.c:85-163) per frame: [B][F][order_spec + order_bap + 3]."""
+    lib = load_ref()
+    B, F = conf.nutt, conf.nfrm
+    nspec = l1["vtmagn"].shape[-1]
+    dim = order_spec + order_bap + 3
+    enc = np.zeros((B, F, dim), np.float32)
+    for b in range(B):
+        lib.ref_coder_encode_soa(F, C.c_float(conf.fs), C.c_float(conf.thop), conf.maxnhar, conf.npsd, conf.nchannel,
+                                 conf.maxnhar_e, C.c_float(conf.lip_radius), nspec, order_spec, order_bap,
+                                 _p(np.ascontiguousarray(f0[b])), _p(np.ascontiguousarray(psd[b])),
+                                 _p(np.ascontiguousarray(l1["rd"][b])), _p(np.ascontiguousarray(l1["vtmagn"][b])), _p(enc[b]))
+    return enc
+
+
+def ref_coder_decode(enc, conf, nspec, order_spec, order_bap, use_layer1):
+    """llsm_coder_decode_layer1 / _layer0 of the reference build (coder.c:165-292) per frame."""
+    lib = load_ref()
+    B, F = conf.nutt, conf.nfrm
+    o = dict(f0=np.zeros((B, F), np.float32), rd=np.zeros((B, F), np.float32), psd=np.zeros((B, F, conf.npsd), np.float32),
+             nhar=np.zeros((B, F), np.int32), ampl=np.zeros((B, F, conf.maxnhar), np.float32),
+             phse=np.zeros((B, F, conf.maxnhar), np.float32), vtmagn=np.zeros((B, F, nspec), np.float32),
+             vsphse=np.zeros((B, F, conf.maxnhar), np.float32))
+    for b in range(B):
+        lib.ref_coder_decode_soa(F, C.c_float(conf.fs), C.c_float(conf.thop), conf.maxnhar, conf.npsd, conf.nchannel,
+                                 conf.maxnhar_e, C.c_float(conf.lip_radius), nspec, order_spec, order_bap, int(use_layer1),
+                                 _p(np.ascontiguousarray(enc[b])), _p(o["f0"][b]), _p(o["rd"][b]), _p(o["psd"][b]),
+                                 _p(o["nhar"][b]), _p(o["ampl"][b]), _p(o["phse"][b]), _p(o["vtmagn"][b]), _p(o["vsphse"][b]))
+    return o
+
+
+def check_coder_encode(enc, ref, order_spec):
+    """Parity bars of the encoded vector: voicing / f0 / Rd identical, mel-cepstral numbers 2e-5 (log-intensity
+    units; they are sums of 1024 float terms), band aperiodicities 1e-5."""
+    assert np.array_equal(enc[..., :3], ref[..., :3])
+    assert np.abs(enc[..., 3:3 + order_spec] - ref[..., 3:3 + order_spec]).max() < 2e-5
+    assert np.abs(enc[..., 3 + order_spec:] - ref[..., 3 + order_spec:]).max() < 1e-5
+
+
+def check_coder_decode(o, ref, use_layer1):
+    assert np.array_equal(o["nhar"], ref["nhar"])
+    assert np.array_equal(o["f0"], ref["f0"]) and np.array_equal(o["rd"], ref["rd"])
+    assert np.abs(o["psd"] - ref["psd"]).max() < 2e-3                       # dB
+    if use_layer1:
+        fin = np.isfinite(ref["vtmagn"])                                    # -inf where the harmonic power underflows
+        assert np.array_equal(fin, np.isfinite(o["vtmagn"]))
+        assert np.abs(o["vtmagn"][fin] - ref["vtmagn"][fin]).max() < 2e-3   # dB
+        assert np.abs(phase_err(o["vsphse"], ref["vsphse"])).max() < 1e-5
+    else:
+        scale = max(float(np.abs(ref["ampl"]).max()), 1e-12)
+        assert np.abs(o["ampl"] - ref["ampl"]).max() < 2e-5 * scale
+        assert np.abs(phase_err(o["phse"], ref["phse"]) * ref["ampl"]).max() < 1e-4 * scale
