@@ -55,6 +55,30 @@ d = {k: (torch.from_numpy(v).cuda() if v is not None else None) for k, v in frb.
 ms = ev_time(lambda: L.tolayer1(ctx, conf, d, 2048), iters=3)
 print(json.dumps({"config": "layer0->layer1, 256 x 400 frames", "ms": ms, "frames_per_s": 256 * 400 / ms * 1e3}), flush=True)
 
+# ---------------------------------------------------------------- coder
+# 64 mel-cepstral numbers + 5 band aperiodicities (test/test-coder.c:31) on the 256 x 400 layer-1 frames above
+l1c = L.tolayer1(ctx, conf, d, 2048)
+enc = L.coder_encode(ctx, conf, d["f0"], d["psd"], l1c, 64, 5)
+nfr = 256 * 400
+ms_e = ev_time(lambda: L.coder_encode(ctx, conf, d["f0"], d["psd"], l1c, 64, 5), iters=3)
+ms_1 = ev_time(lambda: L.coder_decode(ctx, conf, enc, 1025, 64, 5, True), iters=3)
+ms_0 = ev_time(lambda: L.coder_decode(ctx, conf, enc, 1025, 64, 5, False), iters=3)
+out = {"config": "coder, 256 x 400 frames, order_spec 64, order_bap 5, nspec 1025",
+       "encode_frames_per_s": nfr / ms_e * 1e3, "decode_layer1_frames_per_s": nfr / ms_1 * 1e3,
+       "decode_layer0_frames_per_s": nfr / ms_0 * 1e3, "ms": [ms_e, ms_1, ms_0]}
+if not a.no_cpu:
+    import support as S
+    c2 = L.abi.make_conf(1, 64, conf.maxnhar, conf.maxnhar_e, conf.npsd, conf.nchannel, conf.fs, conf.thop)
+    l1h = {k: v[:1, :64].cpu().numpy().copy() for k, v in l1c.items()}
+    t0 = time.perf_counter()
+    e = S.ref_coder_encode(frb["f0"][:1, :64].copy(), frb["psd"][:1, :64].copy(), l1h, c2, 64, 5)
+    t1 = time.perf_counter()
+    S.ref_coder_decode(e, c2, 1025, 64, 5, 1)
+    t2 = time.perf_counter()
+    out["cpu_1thread_parity_build_frames_per_s"] = {"encode": 64 / (t1 - t0), "decode_layer1": 64 / (t2 - t1),
+        "note": "the oracle's ddct is a direct O(n^2) sum, the reference's is Ooura's O(n log n): not a fair CPU baseline"}
+print(json.dumps(out), flush=True)
+
 # ---------------------------------------------------------------- C3
 F = a.nfrm3
 fr, conf = synth_frames(16, F, seed=5, nhar=256, maxnhar=256, f0_lo=60, f0_hi=86)
