@@ -13,7 +13,8 @@
       void functions, as the reference does on bad input) when no CUDA device is usable
       (llsm_last_error() tells why). llsm_pbpeffect callbacks run on the host, once per pulse, in order.
     * containers, frames, chunks, option structs, phase utilities: plain host C (bookkeeping).
-    * llsm_frame_compute_snr and the coder are outside the path: see DESIGN.md "Out of scope".
+    * llsm_coder_encode / llsm_coder_decode_layer0 / _layer1: one frame per call through the batched device coder
+      (include/llsm_b200.h has the batch form). llsm_frame_compute_snr is outside the path (returns NULL).
 
   FP_TYPE must be float (the device kernels compute in FP32 like the reference's default build).
 */
@@ -152,6 +153,17 @@ FP_TYPE* llsm_chunk_getf0(llsm_chunk* src, int* dst_nfrm);
 llsm_chunk*  llsm_analyze(llsm_aoptions* options, FP_TYPE* x, int nx, FP_TYPE fs, FP_TYPE* f0,
                int nfrm, FP_TYPE** x_ap);
 llsm_output* llsm_synthesize(llsm_soptions* options, llsm_chunk* src);
+
+/* ---- coder (reference llsm.h:342-362, coder.c) ---------------------------------------------------
+   A frame <-> a vector of order_spec + order_bap + 3 numbers: [voicing, f0, Rd, order_spec mel-cepstral numbers of
+   the total power spectrum, order_bap band aperiodicities]. The conf needs FNYQ, NCHANNEL, MAXNHAR_E, NPSD, NSPEC
+   and LIPRADIUS (i.e. a layer-1 chunk's conf). Encoding reads F0, NM.psd and, for voiced frames, RD and VTMAGN. */
+typedef void llsm_coder;
+llsm_coder*     llsm_create_coder(llsm_container* conf, int order_spec, int order_bap);
+void            llsm_delete_coder(llsm_coder* dst);
+FP_TYPE*        llsm_coder_encode(llsm_coder* c, llsm_container* src);          /* caller frees */
+llsm_container* llsm_coder_decode_layer1(llsm_coder* c, FP_TYPE* src);          /* RD, VTMAGN, VSPHSE, no HM */
+llsm_container* llsm_coder_decode_layer0(llsm_coder* c, FP_TYPE* src);          /* RD, HM */
 
 /* ---- extensions of this library ---------------------------------------------------------------- */
 /* Batched forms of the two pipelines: n utterances that share one configuration go through the

@@ -185,6 +185,12 @@ int llsm_b200_coder_encode(llsm_b200_ctx* ctx, const llsm_b200_conf* conf, const
 int llsm_b200_coder_decode(llsm_b200_ctx* ctx, const llsm_b200_conf* conf, const int* nfrm_utt,
   const float* enc, int order_spec, int order_bap, int use_layer1,
   const llsm_b200_frames_out* out, const llsm_b200_layer1* layer1);
+/* the same through host buffers (copies in and out, synchronises) */
+int llsm_b200_coder_encode_host(llsm_b200_ctx* ctx, const llsm_b200_conf* conf, const int* nfrm_utt,
+  const float* f0, const float* psd, const llsm_b200_layer1* layer1, int order_spec, int order_bap, float* enc);
+int llsm_b200_coder_decode_host(llsm_b200_ctx* ctx, const llsm_b200_conf* conf, const int* nfrm_utt,
+  const float* enc, int order_spec, int order_bap, int use_layer1,
+  const llsm_b200_frames_out* out, const llsm_b200_layer1* layer1);
 
 /* ---- chunk phase utilities, in place on device arrays ----
    What real use runs between analysis and synthesis (test/test-layer0-anasynth.c:62-63, test-llsmrt.c:88,112):

@@ -436,6 +436,94 @@ void llsm_chunk_tolayer0(llsm_chunk* dst) {
   frames_tolayer0(dst -> frames, *nfrm, dst -> conf);
 }
 
+/* ------------------------------------------------------------------ coder ----------------------- */
+/* llsm_create_coder .. llsm_coder_decode_layer{0,1} (coder.c:46-292): one frame per call through the batched device
+   coder (llsm_b200_coder_*_host). NULL when no CUDA device is usable. */
+typedef struct { llsm_b200_conf c; int order_spec, order_bap, nspec; } compat_coder;
+
+llsm_coder* llsm_create_coder(llsm_container* conf, int order_spec, int order_bap) {
+  g_compat_err[0] = 0;
+  if(conf == NULL) return NULL;
+  FP_TYPE* fnyq = llsm_container_get(conf, LLSM_CONF_FNYQ);
+  int* nch = llsm_container_get(conf, LLSM_CONF_NCHANNEL);
+  int* mne = llsm_container_get(conf, LLSM_CONF_MAXNHAR_E);
+  int* npsd = llsm_container_get(conf, LLSM_CONF_NPSD);
+  int* nspec = llsm_container_get(conf, LLSM_CONF_NSPEC);
+  FP_TYPE* lip = llsm_container_get(conf, LLSM_CONF_LIPRADIUS);
+  if(fnyq == NULL || nch == NULL || mne == NULL || npsd == NULL || nspec == NULL || lip == NULL) return NULL;
+  compat_coder* r = calloc(1, sizeof(compat_coder));
+  r -> c.nutt = 1; r -> c.nfrm = 1; r -> c.maxnhar = 1; r -> c.maxnhar_e = *mne; r -> c.npsd = *npsd;
+  r -> c.nchannel = *nch; r -> c.fs = (float)(*fnyq * 2.0); r -> c.thop = 0.005f; r -> c.lip_radius = *lip;
+  r -> order_spec = order_spec; r -> order_bap = order_bap; r -> nspec = *nspec;
+  return r;
+}
+void llsm_delete_coder(llsm_coder* dst) { free(dst); }
+
+FP_TYPE* llsm_coder_encode(llsm_coder* c_, llsm_container* src) {
+  g_compat_err[0] = 0;
+  compat_coder* c = (compat_coder*)c_;
+  if(c == NULL || src == NULL) return NULL;
+  FP_TYPE* f0 = llsm_container_get(src, LLSM_FRAME_F0);
+  llsm_nmframe* nm = llsm_container_get(src, LLSM_FRAME_NM);
+  FP_TYPE* rd = llsm_container_get(src, LLSM_FRAME_RD);
+  FP_TYPE* vt = llsm_container_get(src, LLSM_FRAME_VTMAGN);
+  if(f0 == NULL || nm == NULL || nm -> npsd != c -> c.npsd) return NULL;
+  if(f0[0] > 0 && (rd == NULL || vt == NULL)) return NULL;
+  llsm_b200_ctx* ctx = shared_ctx();
+  if(ctx == NULL) return NULL;
+  float rdv = rd != NULL ? rd[0] : 0;
+  float* vtz = NULL;
+  if(vt == NULL) { vtz = calloc(c -> nspec, 4); vt = vtz; }
+  llsm_b200_layer1 l1 = {& rdv, vt, NULL, NULL, c -> nspec};
+  FP_TYPE* enc = calloc(c -> order_spec + c -> order_bap + 3, sizeof(FP_TYPE));
+  int rc = llsm_b200_coder_encode_host(ctx, & c -> c, NULL, f0, nm -> psd, & l1, c -> order_spec, c -> order_bap, enc);
+  free(vtz);
+  if(rc != 0) { snprintf(g_compat_err, sizeof(g_compat_err), "%s", llsm_b200_last_error()); free(enc); return NULL; }
+  return enc;
+}
+
+static llsm_container* coder_decode(compat_coder* c, FP_TYPE* src, int use_layer1) {
+  g_compat_err[0] = 0;
+  if(c == NULL || src == NULL) return NULL;
+  llsm_b200_ctx* ctx = shared_ctx();
+  if(ctx == NULL) return NULL;
+  const float fnyq = (float)((double)c -> c.fs / 2.0);
+  const int voicing = src[0] > 0.5;
+  const float f0c = (float)(src[1] > 20.0 ? (double)src[1] : 20.0);           /* coder.c:170 */
+  const int nhar = voicing ? (int)(fnyq / f0c) : 0;                           /* coder.c:172 */
+  llsm_b200_conf cc = c -> c; cc.maxnhar = nhar > 0 ? nhar : 1;
+  float f0 = 0, rd = 0; int nh = 0;
+  float* psd = calloc(cc.npsd, 4); float* a = calloc(cc.maxnhar, 4); float* p = calloc(cc.maxnhar, 4);
+  float* vt = calloc(c -> nspec, 4);
+  llsm_b200_frames_out o; memset(& o, 0, sizeof(o));
+  o.f0 = & f0; o.psd = psd; o.nhar = & nh; o.ampl = a; o.phse = p;
+  llsm_b200_layer1 l1 = {& rd, vt, p, NULL, c -> nspec};
+  llsm_container* ret = NULL;
+  if(llsm_b200_coder_decode_host(ctx, & cc, NULL, src, c -> order_spec, c -> order_bap, use_layer1, & o, & l1) == 0) {
+    ret = llsm_create_frame(nhar, cc.nchannel, cc.maxnhar_e, cc.npsd);
+    llsm_nmframe* nm = llsm_container_get(ret, LLSM_FRAME_NM);
+    memcpy(nm -> psd, psd, 4 * (size_t)cc.npsd);
+    llsm_container_attach(ret, LLSM_FRAME_RD, llsm_create_fp(rd), llsm_delete_fp, llsm_copy_fp);
+    llsm_container_attach(ret, LLSM_FRAME_F0, llsm_create_fp(f0), llsm_delete_fp, llsm_copy_fp);
+    if(nhar > 0 && use_layer1) {
+      llsm_container_remove(ret, LLSM_FRAME_HM);
+      FP_TYPE* v = llsm_create_fparray(c -> nspec); memcpy(v, vt, 4 * (size_t)c -> nspec);
+      FP_TYPE* s = llsm_create_fparray(nhar); memcpy(s, p, 4 * (size_t)nhar);
+      llsm_container_attach(ret, LLSM_FRAME_VTMAGN, v, llsm_delete_fparray, llsm_copy_fparray);
+      llsm_container_attach(ret, LLSM_FRAME_VSPHSE, s, llsm_delete_fparray, llsm_copy_fparray);
+    }
+    if(nhar > 0 && ! use_layer1) {
+      llsm_hmframe* hm = llsm_create_hmframe(nhar);
+      memcpy(hm -> ampl, a, 4 * (size_t)nhar); memcpy(hm -> phse, p, 4 * (size_t)nhar);
+      llsm_container_attach(ret, LLSM_FRAME_HM, hm, llsm_delete_hmframe, llsm_copy_hmframe);
+    }
+  } else snprintf(g_compat_err, sizeof(g_compat_err), "%s", llsm_b200_last_error());
+  free(psd); free(a); free(p); free(vt);
+  return ret;
+}
+llsm_container* llsm_coder_decode_layer1(llsm_coder* c, FP_TYPE* src) { return coder_decode((compat_coder*)c, src, 1); }
+llsm_container* llsm_coder_decode_layer0(llsm_coder* c, FP_TYPE* src) { return coder_decode((compat_coder*)c, src, 0); }
+
 /* ------------------------------------------------------------------ options --------------------- */
 llsm_aoptions* llsm_create_aoptions(void) {            /* defaults of layer0.c:27-43 */
   llsm_aoptions* o = malloc(sizeof(llsm_aoptions));

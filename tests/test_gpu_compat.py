@@ -214,3 +214,59 @@ def test_llsmrt_layer1_dropin(libs, effect):
     assert outs[0][1] == outs[1][1], "the effect callback must run once per pulse on both sides"
     assert a.shape == b.shape and S.rms(b[:, 0]) > 1e-3
     assert S.rms(a - b) < 1e-4, S.rms(a - b)
+
+
+def test_coder_dropin(libs):
+    """test/test-coder.c:24-38 on both libraries: llsm_chunk_tolayer1, llsm_create_coder(conf, 64, 5), then per frame
+    llsm_coder_encode -> llsm_coder_decode_layer0 / _layer1; vectors and decoded members must agree."""
+    fr, conf = S.synth_frames(1, 14, seed=23, nhar=100, maxnhar=256, f0_lo=100, f0_hi=210)
+    res = []
+    for L in libs:
+        L.llsm_create_coder.restype = C.c_void_p
+        L.llsm_create_coder.argtypes = [C.POINTER(U.Container), C.c_int, C.c_int]
+        L.llsm_coder_encode.restype = U.fp
+        L.llsm_coder_encode.argtypes = [C.c_void_p, C.POINTER(U.Container)]
+        for fn in (L.llsm_coder_decode_layer0, L.llsm_coder_decode_layer1):
+            fn.restype = C.POINTER(U.Container); fn.argtypes = [C.c_void_p, U.fp]
+        L.llsm_delete_coder.argtypes = [C.c_void_p]
+        ck = U.build_chunk(L, fr, conf)
+        L.llsm_chunk_tolayer1(ck, 2048)
+        coder = L.llsm_create_coder(ck.contents.conf, 64, 5)
+        assert coder
+        encs, psd0, amp0, phs0, vt1, vs1 = [], [], [], [], [], []
+        for i in range(conf.nfrm):
+            e = L.llsm_coder_encode(coder, ck.contents.frames[i])
+            assert e, "llsm_coder_encode returned NULL"
+            encs.append(np.ctypeslib.as_array(e, (72,)).copy())
+            f0d = L.llsm_coder_decode_layer0(coder, e)
+            f1d = L.llsm_coder_decode_layer1(coder, e)
+            assert f0d and f1d
+            nm = C.cast(L.llsm_container_get(f0d, U.NMI), C.POINTER(U.NM)).contents
+            psd0.append(np.ctypeslib.as_array(nm.psd, (conf.npsd,)).copy())
+            hm = L.llsm_container_get(f0d, U.HMI)
+            if fr["f0"][0, i] > 0:
+                h = C.cast(hm, C.POINTER(U.HM)).contents
+                amp0.append(np.ctypeslib.as_array(h.ampl, (h.nhar,)).copy()); phs0.append(np.ctypeslib.as_array(h.phse, (h.nhar,)).copy())
+                v = L.llsm_container_get(f1d, 11); s = L.llsm_container_get(f1d, 12)
+                assert v and s and not L.llsm_container_get(f1d, U.HMI)
+                n = L.llsm_fparray_length(C.cast(s, U.fp))
+                assert n == h.nhar
+                vt1.append(np.ctypeslib.as_array(C.cast(v, U.fp), (1025,)).copy()); vs1.append(np.ctypeslib.as_array(C.cast(s, U.fp), (n,)).copy())
+            else:
+                assert not L.llsm_container_get(f1d, 11)
+            L.llsm_delete_container(f0d); L.llsm_delete_container(f1d)
+            libc.free(e)
+        L.llsm_delete_coder(coder); L.llsm_delete_chunk(ck)
+        res.append((np.stack(encs), np.stack(psd0), amp0, phs0, vt1, vs1))
+    (e_a, p_a, a_a, h_a, vt_a, vs_a), (e_b, p_b, a_b, h_b, vt_b, vs_b) = res
+    # the two chunks went through two implementations of llsm_chunk_tolayer1 first: layer-1 parity bars apply
+    assert np.array_equal(e_a[:, :2], e_b[:, :2]) and np.abs(e_a[:, 2] - e_b[:, 2]).max() < 1e-5
+    assert np.abs(e_a[:, 3:67] - e_b[:, 3:67]).max() < 1e-3 and np.abs(e_a[:, 67:] - e_b[:, 67:]).max() < 1e-4
+    assert np.abs(p_a - p_b).max() < 2e-2
+    for x, y in zip(a_a, a_b):
+        assert x.shape == y.shape and np.abs(x - y).max() < 1e-3 * np.abs(y).max()
+    for x, y in zip(vt_a, vt_b):
+        fin = np.isfinite(y)
+        assert np.array_equal(fin, np.isfinite(x)) and np.abs(x[fin] - y[fin]).max() < 5e-2
+    for x, y in zip(vs_a, vs_b):
+        assert np.abs(S.phase_err(x, y)).max() < 1e-4
