@@ -958,29 +958,18 @@ __global__ void __launch_bounds__(SHW_THREADS, 2) noise_shape_warp_kernel(ShapeP
       fval[2 * warp] = doA; fval[2 * warp + 1] = doB;
     }
     __syncthreads();
-    // ---- add the round's frames to the output run, ascending frame order (layer0.c:620-624). Centres are
-    //      about one hop apart, so a sample is reached by at most NF / hop + 1 consecutive slots: start from
-    //      an arithmetic guess of the first one instead of testing all sixteen.
+    // ---- add the round's frames to the output run, ascending frame order (layer0.c:620-624): slot by slot,
+    //      every thread owning the run positions i = tid (mod blockDim) -- the same thread adds all frames to a
+    //      given sample, so the order is the reference's and no barrier is needed between slots
     {
       const int nslot = min(2 * SHW_WARPS, ib - r0);
-      const int first = fcen[0], last = fcen[nslot - 1];
-      const float inv_hop = nslot > 1 ? (float)(nslot - 1) / (float)(last - first) : 0.f;
-      int s0 = max(oa, first - HALF), s1 = min(min(ob, ny_b), last + HALF);
-      for(int n = s0 + tid; n < s1; n += blockDim.x) {
-        float a = acc[n - oa];
-        // first slot whose frame can still reach n (centre > n - HALF), from the hop arithmetic, one slot
-        // early; NF / hop + 1 <= 6 frames cover a sample, so a fixed window of 8 slots holds them all
-        int f0 = (int)((float)(n - HALF - first) * inv_hop) - 1;
-        if(f0 < 0) f0 = 0;
-#pragma unroll
-        for(int df = 0; df < 8; df ++) {
-          const int f = f0 + df;
-          if(f < nslot) {
-            const int j = n - fcen[f] + HALF;
-            if(j >= 0 && j < NF && fval[f]) a += ((const float*)(wbase + (f >> 1) * WFFT_SCRATCH_BYTES))[(f & 1) * 1024 + j];
-          }
-        }
-        acc[n - oa] = a;
+      const int run = min(ob, ny_b) - oa;                       // valid positions of the run
+      for(int f = 0; f < nslot; f ++) {
+        if(! fval[f]) continue;
+        const float* src = (const float*)(wbase + (f >> 1) * WFFT_SCRATCH_BYTES) + (f & 1) * 1024;
+        const int off = fcen[f] - HALF - oa;                    // run position of the frame's sample 0
+        const int lo = max(off, 0), hi = min(off + NF, run);
+        for(int i = lo + ((tid - lo) & (SHW_THREADS - 1)); i < hi; i += SHW_THREADS) acc[i] += src[i - off];
       }
     }
     __syncthreads();
