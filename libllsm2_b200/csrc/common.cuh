@@ -59,6 +59,20 @@ __device__ __forceinline__ float2 unit_phasor_turns(double u) {
   return make_float2(c, s);
 }
 
+// e^{i 2 pi u} for a small turn count (|u| of a few turns at most, e.g. an envelope harmonic over one window):
+// the product is formed in float, reduced with one rounding and evaluated by the special-function unit
+// (absolute error ~5e-7: the envelopes it feeds are compared at 1e-4).
+__device__ __forceinline__ float2 unit_phasor_small(float u) {
+#ifdef LLSM_EMU
+  u -= rintf(u);
+  return make_float2(cosf(6.2831853071795865f * u), sinf(6.2831853071795865f * u));
+#else
+  u -= rintf(u);
+  const float a = 6.2831853071795865f * u;
+  return make_float2(__cosf(a), __sinf(a));
+#endif
+}
+
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }

@@ -444,7 +444,7 @@ __global__ void __launch_bounds__(EXC_THREADS) noise_excitation_kernel(ExcParams
             if(idx != p) continue;
           }
           const float wj = P.win_env[j];
-          float2 z = unit_phasor_turns((double)f0n * (double)(j - half));
+          float2 z = unit_phasor_small(f0n * (float)(j - half));   // at most ~one turn across the window
           float2 w = make_float2(1.f, 0.f);
           float hs[MAXCH];
 #pragma unroll
