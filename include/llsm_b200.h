@@ -171,6 +171,16 @@ typedef struct {
   int    nspec;          /* LLSM_CONF_NSPEC = nfft / 2 + 1 */
 } llsm_b200_layer1;
 
+/* ---- flat serialisation of a batch, host memory ----
+   The reference has no on-disk / wire format (llsm_chunk only lives in memory, llsm.h:310-313). A blob is the
+   structure-of-arrays batch in one relocatable buffer: 256-byte header (magic "LLSMB200", version, the conf, which
+   arrays are present, their offsets) followed by the arrays of llsm_b200_frames, 64-byte aligned. unpack returns
+   pointers INTO the blob (no copy). Absent optional arrays (nfrm_utt, psdres; or nhar / ampl / phse of a layer-1
+   batch) are NULL on both sides. */
+size_t llsm_b200_frames_blob_size(const llsm_b200_conf* conf, const llsm_b200_frames* frames);
+int llsm_b200_frames_pack(const llsm_b200_conf* conf, const llsm_b200_frames* frames, void* blob, size_t size);
+int llsm_b200_frames_unpack(const void* blob, size_t size, llsm_b200_conf* conf, llsm_b200_frames* frames);
+
 /* ---- frame coder: coder.c:46-292 for a batch, device pointers ----
    A frame <-> a vector of order_spec + order_bap + 3 numbers: [voicing, f0, Rd, order_spec mel-cepstral
    coefficients of the total power spectrum, order_bap band aperiodicities] (llsm_create_coder(conf, order_spec,

@@ -71,6 +71,10 @@ def lib():
     L.llsm_b200_coder_encode.argtypes = [P, C.POINTER(abi.Conf), P, P, P, C.POINTER(abi.Layer1), C.c_int, C.c_int, P]
     L.llsm_b200_coder_decode.argtypes = [P, C.POINTER(abi.Conf), P, P, C.c_int, C.c_int, C.c_int,
                                          C.POINTER(abi.FramesOut), C.POINTER(abi.Layer1)]
+    L.llsm_b200_frames_blob_size.restype = C.c_size_t
+    L.llsm_b200_frames_blob_size.argtypes = [C.POINTER(abi.Conf), C.POINTER(abi.Frames)]
+    L.llsm_b200_frames_pack.argtypes = [C.POINTER(abi.Conf), C.POINTER(abi.Frames), P, C.c_size_t]
+    L.llsm_b200_frames_unpack.argtypes = [P, C.c_size_t, C.POINTER(abi.Conf), C.POINTER(abi.Frames)]
     _lib = L
     return L
 

@@ -397,3 +397,37 @@ def coder_decode(ctx, conf, enc, nspec, order_spec=64, order_bap=5, use_layer1=T
     check(lib().llsm_b200_coder_decode(ctx._h, C.byref(conf), _ptr(nfrm_utt), _ptr(enc), int(order_spec), int(order_bap),
                                        1 if use_layer1 else 0, C.byref(fo), C.byref(l1)))
     return o
+
+
+def frames_to_blob(conf, frames):
+    """Serialise a batch (dict of numpy arrays keyed as FRAME_KEYS) into one relocatable buffer (numpy uint8):
+    llsm_b200_frames_pack. What parallel.py scatters and what a file would hold."""
+    f = _frames({k: (np.ascontiguousarray(v) if v is not None else None) for k, v in frames.items()})
+    n = lib().llsm_b200_frames_blob_size(C.byref(conf), C.byref(f))
+    blob = np.zeros(n, np.uint8)
+    check(lib().llsm_b200_frames_pack(C.byref(conf), C.byref(f), blob.ctypes.data, n))
+    return blob
+
+
+def blob_to_frames(blob):
+    """llsm_b200_frames_unpack: (conf, dict of numpy views into the blob)."""
+    blob = np.ascontiguousarray(blob, np.uint8)
+    conf, f = abi.Conf(), abi.Frames()
+    check(lib().llsm_b200_frames_unpack(blob.ctypes.data, blob.size, C.byref(conf), C.byref(f)))
+    B, F, n = conf.nutt, conf.nfrm, conf.nchannel
+    shapes = {"nfrm_utt": ((B,), np.int32), "f0": ((B, F), np.float32), "nhar": ((B, F), np.int32),
+              "ampl": ((B, F, conf.maxnhar), np.float32), "phse": ((B, F, conf.maxnhar), np.float32),
+              "psd": ((B, F, conf.npsd), np.float32), "psdres": ((B, F, conf.npsd), np.float32),
+              "edc": ((B, F, n), np.float32), "enhar": ((B, F, n), np.int32),
+              "eampl": ((B, F, n, conf.maxnhar_e), np.float32), "ephse": ((B, F, n, conf.maxnhar_e), np.float32)}
+    out = {}
+    base = blob.ctypes.data
+    for k in FRAME_KEYS:
+        p = getattr(f, k)
+        if not p:
+            out[k] = None
+            continue
+        shape, dt = shapes[k]
+        cnt = int(np.prod(shape))
+        out[k] = np.frombuffer(blob, dtype=dt, count=cnt, offset=p - base).reshape(shape)
+    return conf, out

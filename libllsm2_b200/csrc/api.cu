@@ -346,5 +346,6 @@ int llsm_b200_synthesize_l0_host(llsm_b200_ctx* ctx, const llsm_b200_conf* conf,
 #include "api_analysis.inc"
 #include "api_layer1.inc"
 #include "api_rt.inc"
+#include "api_blob.inc"
 
 } // extern "C"

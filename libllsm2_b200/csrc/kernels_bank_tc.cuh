@@ -467,8 +467,11 @@ static inline int launch_hm_bank_tc(BankParams P, int nutt, int nfrm_max, cudaSt
   const int F = BTC_NSLOT - 2;
   const int nseg = (std::max(nfrm_max, 1) + F - 1) / F;
   const size_t smem = bank_tc_smem_bytes();
-  static bool attr = false;
-  if(! attr) { cudaFuncSetAttribute(hm_bank_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+  // (per launch: the attribute is per device, and a process may drive several)
+  if(cudaFuncSetAttribute(hm_bank_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;                     // not enough shared memory on this device: CUDA-core bank
+  }
   hm_bank_tc_kernel<<<dim3(nseg, nutt), dim3(BTC_THREADS), smem, st>>>(P);
   return 0;
 }

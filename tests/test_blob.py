@@ -1,0 +1,35 @@
+"""Flat serialisation of a batch (llsm_b200_frames_pack / _unpack): host-only, no GPU needed."""
+import ctypes as C
+import numpy as np
+import pytest
+import support as S
+
+
+def test_round_trip_and_views():
+    import libllsm2_b200 as L
+    fr, conf = S.synth_frames(3, 17, seed=51)
+    fr["nfrm_utt"] = np.asarray([17, 4, 9], np.int32)
+    blob = L.frames_to_blob(conf, fr)
+    assert blob[:8].tobytes() == b"LLSMB200" and blob.size % 64 == 0
+    conf2, fr2 = L.blob_to_frames(blob.copy())                 # relocatable: a copy elsewhere in memory works
+    for k in ("nutt", "nfrm", "maxnhar", "maxnhar_e", "npsd", "nchannel", "fs", "thop", "lip_radius"):
+        assert getattr(conf, k) == getattr(conf2, k)
+    for k, v in fr.items():
+        if v is None:
+            assert fr2[k] is None
+        else:
+            assert np.array_equal(fr2[k], v), k
+
+
+def test_optional_arrays_and_errors():
+    import libllsm2_b200 as L
+    fr, conf = S.synth_frames(2, 5, seed=52)
+    fr["psdres"] = None; fr["nfrm_utt"] = None
+    blob = L.frames_to_blob(conf, fr)
+    _, fr2 = L.blob_to_frames(blob)
+    assert fr2["psdres"] is None and fr2["nfrm_utt"] is None and np.array_equal(fr2["phse"], fr["phse"])
+    with pytest.raises(L.LlsmB200Error):
+        L.blob_to_frames(blob[:300])                           # truncated
+    bad = blob.copy(); bad[0] = 0
+    with pytest.raises(L.LlsmB200Error):
+        L.blob_to_frames(bad)                                  # wrong magic

@@ -83,3 +83,41 @@ def test_frame_sharding_world2_gloo():
 def test_shard_ranges():
     assert parallel.frame_shards(400, 8)[0] == (0, 50) and parallel.frame_shards(400, 8)[-1] == (350, 400)
     assert parallel.frame_shards(7, 2) == [(0, 4), (4, 7)]
+
+
+def _scatter_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    fr, conf = (S.synth_frames(5, 12, seed=61) if rank == 0 else (None, None))
+    c, f = parallel.scatter_utterances(conf, fr, rank, world)
+    q.put((rank, c.nutt, {k: (None if v is None else np.array(v)) for k, v in f.items()}))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_utterance_scatter_world2():
+    """Utterance sharding through the flat blob (llsm_b200_frames_pack / _unpack): rank 0 owns the batch, every
+    rank ends up with its contiguous range of utterances, bit for bit."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    ps = [ctx.Process(target=_scatter_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    got = dict()
+    for _ in range(2):
+        r, n, f = q.get(timeout=240)
+        got[r] = (n, f)
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    fr, conf = S.synth_frames(5, 12, seed=61)
+    shards = parallel.utterance_shards(5, 2)
+    for r, (lo, hi) in enumerate(shards):
+        n, f = got[r]
+        assert n == hi - lo
+        for k, v in fr.items():
+            if v is None:
+                assert f[k] is None
+            else:
+                assert np.array_equal(f[k], v[lo:hi]), (r, k)
