@@ -46,6 +46,9 @@ __device__ __forceinline__ void fence_after_sync()  { asm volatile("tcgen05.fenc
 __device__ __forceinline__ void fence_smem_to_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- mbarrier ----
+#ifndef LLSM_MBAR_SUSPEND_NS
+#define LLSM_MBAR_SUSPEND_NS 20000u   // try_wait time hint: a waiting warp sleeps instead of spinning through issue slots
+#endif
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
 }
@@ -54,11 +57,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
     "{\n\t.reg .pred p;\n\t"
     "LLSM_MBAR_WAIT:\n\t"
-    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"   // suspends up to the hint, wakes on completion
     "@p bra LLSM_MBAR_DONE;\n\t"
     "bra LLSM_MBAR_WAIT;\n\t"
     "LLSM_MBAR_DONE:\n\t}"
-    :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+    :: "r"(smem_u32(bar)), "r"(parity), "r"(LLSM_MBAR_SUSPEND_NS) : "memory");
 }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
