@@ -286,6 +286,17 @@ def run_b200(args):
     torch.cuda.synchronize()
     bank_ms = b0.elapsed_time(b1) / args.steps
 
+    # every kernel of the step, live: CUDA events recorded by the library between its launches (a separate pass, so
+    # that the timed region above stays free of them)
+    ctx.set_kernel_timing(True)
+    kms = {}
+    for i in range(max(3, min(args.steps, 10))):
+        step(10_000 + i)
+        for k, v in ctx.kernel_times().items():
+            kms.setdefault(k, []).append(v)
+    ctx.set_kernel_timing(False)
+    kms = {k: float(np.median(v)) for k, v in kms.items()}
+
     # end to end through the host-buffer C ABI (pinned host memory, H2D + kernels + D2H per step)
     e2e = None
     if not args.no_e2e:
@@ -349,6 +360,15 @@ def run_b200(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = BANK_BYTES_PER_FRAME * frames_per_step / (bank_ms * 1e-3) / 1e9
+    # algorithmic bytes per frame of the other kernels: shaper 2 048 B model PSDs + 882 B excitation in
+    # + 882 B out; excitation 168 B envelope parameters + 882 B out; the template kernels only touch scratch
+    # (B x nchannel templates of ~20 128 samples: written once by the fill, read + written by the IIR)
+    tmpl_bytes = float(conf.nutt) * conf.nchannel * 20128 * 4
+    kbytes = {"hm_bank": BANK_BYTES_PER_FRAME * frames_per_step, "noise_shape": 3812.0 * frames_per_step,
+              "noise_excitation": 1050.0 * frames_per_step, "iir_filtfilt": 2 * tmpl_bytes, "white_fill": tmpl_bytes}
+    kernels = {k: {"ms": v, "algorithmic_bytes_per_launch": kbytes[k], "achieved_gbs": kbytes[k] / (v * 1e-3) / 1e9,
+                   "frac": kbytes[k] / (v * 1e-3) / 1e9 / peak} for k, v in kms.items()}
+    dom = max(kernels, key=lambda k: kernels[k]["ms"])
     traffic = None
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "bank_traffic.json"))).get("dram_bytes_per_launch")
@@ -367,6 +387,9 @@ def run_b200(args):
                      "ms_per_launch": bank_ms,
                      "algorithmic_bytes_per_launch": BANK_BYTES_PER_FRAME * frames_per_step,
                      "whole_step_gbs": FULL_BYTES_PER_FRAME * frames_per_step / (ms / args.steps * 1e-3) / 1e9},
+        # the same accounting for every kernel of the step (CUDA events inside the library, llsm_b200_kernel_times);
+        # "dominant" is the longest one -- the harmonic bank above is the kernel BASELINE.json's target names
+        "kernels": kernels, "dominant_kernel": dom,
     }
     if ana is not None:
         syn = value

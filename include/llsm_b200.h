@@ -125,6 +125,12 @@ int            llsm_b200_synchronize(llsm_b200_ctx* ctx);
 /* number of kernels this library has launched on ctx since creation (bench.py gpu_launches) */
 long long      llsm_b200_launch_count(const llsm_b200_ctx* ctx);
 
+/* Per-kernel timing of the layer-0 synthesis step: when enabled, llsm_b200_synthesize_l0 records a CUDA event after
+   each of its five kernels; llsm_b200_kernel_times waits for the last step and returns their durations in ms
+   (harmonic bank, white-noise fill, template IIR, excitation, noise shaper + mix). */
+int llsm_b200_set_kernel_timing(llsm_b200_ctx* ctx, int enable);
+int llsm_b200_kernel_times(llsm_b200_ctx* ctx, float* ms5);
+
 /* ---- size helpers (host only, exact replicas of the reference's float expressions) ---- */
 int llsm_b200_output_length(int nfrm, float thop, float fs);    /* layer0.c:643 */
 int llsm_b200_template_length(int ny);                          /* dsputils.c:386-388 */

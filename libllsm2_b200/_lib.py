@@ -75,6 +75,8 @@ def lib():
     L.llsm_b200_frames_blob_size.argtypes = [C.POINTER(abi.Conf), C.POINTER(abi.Frames)]
     L.llsm_b200_frames_pack.argtypes = [C.POINTER(abi.Conf), C.POINTER(abi.Frames), P, C.c_size_t]
     L.llsm_b200_frames_unpack.argtypes = [P, C.c_size_t, C.POINTER(abi.Conf), C.POINTER(abi.Frames)]
+    L.llsm_b200_set_kernel_timing.argtypes = [P, C.c_int]
+    L.llsm_b200_kernel_times.argtypes = [P, C.POINTER(C.c_float)]
     _lib = L
     return L
 

@@ -42,6 +42,15 @@ class Context:
     def launches(self):
         return int(lib().llsm_b200_launch_count(self._h))
 
+    def set_kernel_timing(self, enable=True):
+        check(lib().llsm_b200_set_kernel_timing(self._h, 1 if enable else 0))
+
+    def kernel_times(self):
+        """ms of the five kernels of the last synthesize_l0 step: bank, white fill, IIR, excitation, shaper."""
+        ms = (C.c_float * 5)()
+        check(lib().llsm_b200_kernel_times(self._h, ms))
+        return dict(zip(("hm_bank", "white_fill", "iir_filtfilt", "noise_excitation", "noise_shape"), [float(v) for v in ms]))
+
     def close(self):
         if getattr(self, "_h", None):
             lib().llsm_b200_destroy(self._h)

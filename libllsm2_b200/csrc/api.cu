@@ -44,6 +44,7 @@ struct llsm_b200_ctx {
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
   DevBuf pin[2][12], pout[2][12];
   LaunchCounter lc;
+  cudaEvent_t kt_ev[LLSM_KT_MARKS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   std::mutex mtx;
 };
 
@@ -341,6 +342,31 @@ int llsm_b200_synthesize_l0_host(llsm_b200_ctx* ctx, const llsm_b200_conf* conf,
   if(cudaStreamSynchronize(ctx->s_out) != cudaSuccess || cudaStreamSynchronize(ctx->stream) != cudaSuccess ||
      cudaStreamSynchronize(ctx->s_in) != cudaSuccess) return cuda_ok("synchronize");
   return cuda_ok("synthesize_l0_host");
+}
+
+// Per-kernel timing of the layer-0 synthesis step (bench.py): when enabled, llsm_b200_synthesize_l0 records an
+// event after each of its five kernels; llsm_b200_kernel_times synchronises and returns the five durations (ms) of
+// the LAST step: harmonic bank, white-noise fill, template IIR, excitation, noise shaper + mix.
+int llsm_b200_set_kernel_timing(llsm_b200_ctx* ctx, int enable) {
+  if(ctx == nullptr) return fail(LLSM_B200_ENODEVICE, "no context (no CUDA device?)");
+  std::lock_guard<std::mutex> lk(ctx->mtx);
+  cudaSetDevice(ctx->device);
+  if(enable && ! ctx->kt_ev[0])
+    for(int i = 0; i < LLSM_KT_MARKS; i ++)
+      if(cudaEventCreate(&ctx->kt_ev[i]) != cudaSuccess) return cuda_ok("kernel timing events");
+  ctx->lc.ev = enable ? ctx->kt_ev : nullptr;
+  ctx->lc.mark = 0;
+  return 0;
+}
+int llsm_b200_kernel_times(llsm_b200_ctx* ctx, float* ms5) {
+  if(ctx == nullptr || ms5 == nullptr) return fail(LLSM_B200_EINVAL, "NULL argument");
+  std::lock_guard<std::mutex> lk(ctx->mtx);
+  cudaSetDevice(ctx->device);
+  if(! ctx->lc.ev || ctx->lc.mark != LLSM_KT_MARKS) return fail(LLSM_B200_EINVAL, "no timed synthesis step recorded");
+  if(cudaEventSynchronize(ctx->kt_ev[LLSM_KT_MARKS - 1]) != cudaSuccess) return cuda_ok("kernel timing");
+  for(int i = 0; i + 1 < LLSM_KT_MARKS; i ++)
+    if(cudaEventElapsedTime(&ms5[i], ctx->kt_ev[i], ctx->kt_ev[i + 1]) != cudaSuccess) return cuda_ok("kernel timing");
+  return 0;
 }
 
 #include "api_analysis.inc"
