@@ -220,6 +220,27 @@ int llsm_b200_chunk_phasepropagate(llsm_b200_ctx* ctx, const llsm_b200_conf* con
 int llsm_b200_chunk_phasesync_rps(llsm_b200_ctx* ctx, const llsm_b200_conf* conf, const int* nfrm_utt,
   const llsm_b200_frames_out* frames, const llsm_b200_layer1* layer1, int layer1_based);
 
+/* ---- frame interpolation / time-stretch of a layer-1 batch, device arrays ----
+   The reference keeps this step in a demo (test/demo-stretch.c), between llsm_chunk_tolayer1 +
+   llsm_chunk_phasepropagate(-1) and llsm_chunk_tolayer0 + llsm_chunk_phasepropagate(+1):
+     interp_llsm_frame  test/demo-stretch.c:50-129  f0, Rd, VSPHSE (circular), VTMAGN (dB, faded in / out at voicing
+                                                    boundaries, floored at -80), voiced / unvoiced cases
+     interp_nmframe     test/demo-stretch.c:16-44   psd, edc, envelope harmonics
+     the frame loop     test/demo-stretch.c:169-185 out[i] = copy(frames[base[i]]) blended towards frames[base[i] + 1]
+                                                    with weight ratio[i]; PSDRES copied from frames[residx[i]]
+   conf describes the SOURCE batch (nfrm frames); the destination arrays hold nfrm_new frames per utterance with the
+   same row strides. base / ratio / residx are device arrays of nfrm_new entries (map_per_utt = 0: one map for the
+   batch) or [B][nfrm_new] (map_per_utt = 1); residx == NULL takes PSDRES from frame base[i]. base is clamped to
+   [0, nfrm - 2], residx to [0, nfrm - 1]. psdres and the layer-0 harmonics (nhar, ampl, phse: carried over unchanged
+   from frame base[i]) are optional on both sides. Unvoiced output frames get nvs = 0 and zeroed vtmagn / vsphse rows. */
+int llsm_b200_frames_stretch(llsm_b200_ctx* ctx, const llsm_b200_conf* conf, const llsm_b200_frames* src,
+  const llsm_b200_layer1* src_layer1, int nfrm_new, const int* base, const float* ratio, const int* residx,
+  int map_per_utt, const llsm_b200_frames_out* dst, const llsm_b200_layer1* dst_layer1);
+/* host helper: the uniform map of test/demo-stretch.c:170-175 in the reference's float arithmetic
+   (mapped = (float)i * nfrm / nfrm_new; base = (int)mapped; ratio = mapped - base; base = min(base, nfrm - 2)).
+   residx (optional) receives the unclamped base, to which the caller adds its jitter (:173-174). HOST pointers. */
+int llsm_b200_stretch_map(int nfrm, int nfrm_new, int* base, float* ratio, int* residx);
+
 /* llsm_chunk_tolayer1 (layer1.c:129-149) for a batch: Rd track (glottal fitting + smoothing),
    vocal-tract envelope and source phases of every voiced frame. Device pointers. Reads
    frames->{nfrm_utt, f0, nhar, ampl, phse}. nfft as in the reference call (power of two). */

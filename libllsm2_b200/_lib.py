@@ -71,6 +71,9 @@ def lib():
     L.llsm_b200_coder_encode.argtypes = [P, C.POINTER(abi.Conf), P, P, P, C.POINTER(abi.Layer1), C.c_int, C.c_int, P]
     L.llsm_b200_coder_decode.argtypes = [P, C.POINTER(abi.Conf), P, P, C.c_int, C.c_int, C.c_int,
                                          C.POINTER(abi.FramesOut), C.POINTER(abi.Layer1)]
+    L.llsm_b200_frames_stretch.argtypes = [P, C.POINTER(abi.Conf), C.POINTER(abi.Frames), C.POINTER(abi.Layer1), C.c_int,
+                                           P, P, P, C.c_int, C.POINTER(abi.FramesOut), C.POINTER(abi.Layer1)]
+    L.llsm_b200_stretch_map.argtypes = [C.c_int, C.c_int, P, P, P]
     L.llsm_b200_frames_blob_size.restype = C.c_size_t
     L.llsm_b200_frames_blob_size.argtypes = [C.POINTER(abi.Conf), C.POINTER(abi.Frames)]
     L.llsm_b200_frames_pack.argtypes = [C.POINTER(abi.Conf), C.POINTER(abi.Frames), P, C.c_size_t]

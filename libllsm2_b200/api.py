@@ -408,6 +408,46 @@ def coder_decode(ctx, conf, enc, nspec, order_spec=64, order_bap=5, use_layer1=T
     return o
 
 
+def stretch_map(nfrm, nfrm_new):
+    """The uniform time map of test/demo-stretch.c:170-175: numpy (base int32, ratio float32, residx int32)."""
+    base, ratio, res = np.zeros(nfrm_new, np.int32), np.zeros(nfrm_new, np.float32), np.zeros(nfrm_new, np.int32)
+    check(lib().llsm_b200_stretch_map(int(nfrm), int(nfrm_new), base.ctypes.data, ratio.ctypes.data, res.ctypes.data))
+    return base, ratio, res
+
+
+def frames_stretch(ctx, conf, frames, layer1, base, ratio, residx=None):
+    """Frame interpolation / time-stretch of a layer-1 batch (test/demo-stretch.c:16-129,169-185), CUDA tensors.
+    frames: dict keyed as FRAME_KEYS, layer1: dict(rd, vtmagn, vsphse, nvs); base / ratio / residx: [nfrm_new] (one map
+    for the batch) or [B][nfrm_new]. Returns (conf_new, frames_new, layer1_new)."""
+    import torch
+    dev = frames["f0"].device
+    per_utt = base.dim() == 2
+    Fn = base.shape[-1]
+    B, n = conf.nutt, conf.nchannel
+    nspec = layer1["vtmagn"].shape[-1]
+    z = lambda shape, dt=torch.float32: torch.empty(shape, dtype=dt, device=dev)  # noqa: E731  (every row is written)
+    fo = {"f0": z((B, Fn)), "psd": z((B, Fn, conf.npsd)), "edc": z((B, Fn, n)), "enhar": z((B, Fn, n), torch.int32),
+          "eampl": z((B, Fn, n, conf.maxnhar_e)), "ephse": z((B, Fn, n, conf.maxnhar_e))}
+    if frames.get("psdres") is not None:
+        fo["psdres"] = z((B, Fn, conf.npsd))
+    if all(frames.get(k) is not None for k in ("nhar", "ampl", "phse")):
+        fo["nhar"], fo["ampl"], fo["phse"] = z((B, Fn), torch.int32), z((B, Fn, conf.maxnhar)), z((B, Fn, conf.maxnhar))
+    lo = {"rd": z((B, Fn)), "vtmagn": z((B, Fn, nspec)), "vsphse": z((B, Fn, conf.maxnhar)), "nvs": z((B, Fn), torch.int32)}
+    s, d = _frames(frames), abi.FramesOut()
+    for k, v in fo.items():
+        setattr(d, k, _ptr(v))
+    sl, dl = abi.Layer1(), abi.Layer1()
+    for k in ("rd", "vtmagn", "vsphse", "nvs"):
+        setattr(sl, k, _ptr(layer1[k]))
+        setattr(dl, k, _ptr(lo[k]))
+    sl.nspec = dl.nspec = int(nspec)
+    check(lib().llsm_b200_frames_stretch(ctx._h, C.byref(conf), C.byref(s), C.byref(sl), int(Fn), _ptr(base), _ptr(ratio),
+                                         _ptr(residx), 1 if per_utt else 0, C.byref(d), C.byref(dl)))
+    conf_new = abi.make_conf(B, Fn, conf.maxnhar, conf.maxnhar_e, conf.npsd, n, conf.fs, conf.thop,
+                             list(conf.chanfreq)[:max(n - 1, 0)], conf.lip_radius)
+    return conf_new, fo, lo
+
+
 def frames_to_blob(conf, frames):
     """Serialise a batch (dict of numpy arrays keyed as FRAME_KEYS) into one relocatable buffer (numpy uint8):
     llsm_b200_frames_pack. What parallel.py scatters and what a file would hold."""

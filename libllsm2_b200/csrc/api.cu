@@ -7,6 +7,7 @@
 #include "driver_pbp.h"
 #include "driver_rt.h"
 #include "kernels_phase.cuh"
+#include "kernels_stretch.cuh"
 #include "driver_coder.h"
 #include <cstdio>
 #include <cstdarg>

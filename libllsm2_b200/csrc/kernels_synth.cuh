@@ -806,8 +806,15 @@ __global__ void __launch_bounds__(SHW_THREADS, 2) noise_shape_warp_kernel(ShapeP
           // ---- load the two windowed frames (layer0.c:588-592) through shared memory (rolled loop:
           //      small code), then pick element j = lane + 32 r into register r
           //      (eight iterations in flight: the loop is bound by the latency of the excitation reads)
+          //      (rows that lie wholly outside the analysis window are zero-filled without any read)
+          const int row_lo = (HALF - hw) >> 5, row_hi = (HALF - hw + P.n_ns - 1) >> 5;
 #pragma unroll 1
           for(int r0 = 0; r0 < 32; r0 += 8) {
+            if(r0 + 7 < row_lo || r0 > row_hi) {             // warp-uniform
+#pragma unroll
+              for(int u = 0; u < 8; u ++) scratch[lane + 32 * (r0 + u)] = make_float2(0.f, 0.f);
+              continue;
+            }
             float va[8], vb[8], wv[8];
 #pragma unroll
             for(int u = 0; u < 8; u ++) {

@@ -491,3 +491,69 @@ int ref_coder_decode_soa(int nfrm, float fs, float thop, int maxnhar, int npsd, 
   llsm_delete_aoptions(opt);
   return 0;
 }
+
+/* ---- frame interpolation / time-stretch: the reference keeps it in a demo (test/demo-stretch.c:6-129), as file-static
+   functions. The demo is compiled here from where it lies -- its main() renamed and never called, its pitch-tracker /
+   wav-file includes satisfied by oracle/ciglet-shim/nebula.h -- so that interp_llsm_frame itself is the oracle. ---- */
+#define main ref_demo_stretch_main_unused
+#include "test/demo-stretch.c"
+#undef main
+
+/* out[i] = interp_llsm_frame(copy(frames[base[i]]), frames[base[i] + 1], ratio[i]) with PSDRES from frames[residx[i]]
+   (the loop of test/demo-stretch.c:169-185 for a given map). Rows of the layer-1 arrays of unvoiced frames are zero. */
+int ref_stretch_soa(int nfrm, float fs, float thop, int maxnhar, int maxnhar_e, int npsd, int nchannel, float lip_radius,
+  int nspec, const float* f0, const float* rd, const float* vtmagn, const float* vsphse, const int* nvs,
+  const float* psd, const float* psdres, const float* edc, const int* enhar, const float* eampl, const float* ephse,
+  int nfrm_new, const int* base, const float* ratio, const int* residx,
+  float* o_f0, float* o_rd, float* o_vtmagn, float* o_vsphse, int* o_nvs,
+  float* o_psd, float* o_psdres, float* o_edc, int* o_enhar, float* o_eampl, float* o_ephse) {
+  float cf[7] = {2000, 4000, 8000, 12000, 14000, 16000, 18000};
+  llsm_chunk* chunk = chunk_from_soa(nfrm, fs, thop, maxnhar, maxnhar_e, npsd, nchannel, cf, lip_radius,
+    f0, NULL, NULL, NULL, psd, psdres, edc, enhar, eampl, ephse);
+  for(int i = 0; i < nfrm; i ++) {
+    llsm_container* fr = chunk -> frames[i];
+    llsm_container_attach(fr, LLSM_FRAME_RD, llsm_create_fp(rd[i]), llsm_delete_fp, llsm_copy_fp);
+    if(f0[i] > 0) {
+      FP_TYPE* vt = llsm_create_fparray(nspec);
+      memcpy(vt, vtmagn + (size_t)i * nspec, nspec * sizeof(float));
+      llsm_container_attach(fr, LLSM_FRAME_VTMAGN, vt, llsm_delete_fparray, llsm_copy_fparray);
+      FP_TYPE* vs = llsm_create_fparray(nvs[i]);
+      memcpy(vs, vsphse + (size_t)i * maxnhar, nvs[i] * sizeof(float));
+      llsm_container_attach(fr, LLSM_FRAME_VSPHSE, vs, llsm_delete_fparray, llsm_copy_fparray);
+    }
+  }
+  for(int i = 0; i < nfrm_new; i ++) {
+    llsm_container* fr = llsm_copy_container(chunk -> frames[base[i]]);
+    interp_llsm_frame(fr, chunk -> frames[base[i] + 1], ratio[i]);
+    o_f0[i] = ((FP_TYPE*)llsm_container_get(fr, LLSM_FRAME_F0))[0];
+    o_rd[i] = ((FP_TYPE*)llsm_container_get(fr, LLSM_FRAME_RD))[0];
+    FP_TYPE* vt = llsm_container_get(fr, LLSM_FRAME_VTMAGN);
+    FP_TYPE* vs = llsm_container_get(fr, LLSM_FRAME_VSPHSE);
+    memset(o_vtmagn + (size_t)i * nspec, 0, nspec * sizeof(float));
+    memset(o_vsphse + (size_t)i * maxnhar, 0, maxnhar * sizeof(float));
+    o_nvs[i] = 0;
+    if(vt != NULL) memcpy(o_vtmagn + (size_t)i * nspec, vt, nspec * sizeof(float));
+    if(vs != NULL) {
+      o_nvs[i] = llsm_fparray_length(vs);
+      memcpy(o_vsphse + (size_t)i * maxnhar, vs, o_nvs[i] * sizeof(float));
+    }
+    llsm_nmframe* nm = llsm_container_get(fr, LLSM_FRAME_NM);
+    memcpy(o_psd + (size_t)i * npsd, nm -> psd, npsd * sizeof(float));
+    if(psdres != NULL && o_psdres != NULL) {
+      FP_TYPE* res = llsm_container_get(chunk -> frames[residx[i]], LLSM_FRAME_PSDRES);
+      memcpy(o_psdres + (size_t)i * npsd, res, npsd * sizeof(float));
+    }
+    for(int c = 0; c < nchannel; c ++) {
+      size_t oc = (size_t)i * nchannel + c;
+      o_edc[oc] = nm -> edc[c];
+      o_enhar[oc] = nm -> eenv[c] -> nhar;
+      memset(o_eampl + oc * maxnhar_e, 0, maxnhar_e * sizeof(float));
+      memset(o_ephse + oc * maxnhar_e, 0, maxnhar_e * sizeof(float));
+      memcpy(o_eampl + oc * maxnhar_e, nm -> eenv[c] -> ampl, nm -> eenv[c] -> nhar * sizeof(float));
+      memcpy(o_ephse + oc * maxnhar_e, nm -> eenv[c] -> phse, nm -> eenv[c] -> nhar * sizeof(float));
+    }
+    llsm_delete_container(fr);
+  }
+  llsm_delete_chunk(chunk);
+  return 0;
+}

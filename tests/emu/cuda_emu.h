@@ -100,6 +100,7 @@ static inline double cospi(double x) { return cos(3.14159265358979323846 * x); }
 static inline double sinpi(double x) { return sin(3.14159265358979323846 * x); }
 static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
+static inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 static inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
 static inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
 static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }

@@ -196,3 +196,20 @@ extern "C" int emu_coder_decode(const llsm_b200_conf* conf, const float* enc, in
     out->ampl, out->phse, l1->vtmagn, l1->vsphse, nullptr, nullptr);
   cp.release(); lp.release(); return rc;
 }
+
+#include "../../libllsm2_b200/csrc/kernels_stretch.cuh"
+extern "C" int emu_frames_stretch(const llsm_b200_conf* conf, const llsm_b200_frames* src, const llsm_b200_layer1* sl,
+  int nfrm_new, const int* base, const float* ratio, const int* residx, int map_per_utt,
+  const llsm_b200_frames_out* dst, const llsm_b200_layer1* dl) {
+  StretchParams P; memset(&P, 0, sizeof(P));
+  P.nutt = conf->nutt; P.nfrm = conf->nfrm; P.nfrm_new = nfrm_new; P.maxnhar = conf->maxnhar; P.maxnhar_e = conf->maxnhar_e;
+  P.npsd = conf->npsd; P.nchannel = conf->nchannel; P.nspec = sl->nspec; P.map_per_utt = map_per_utt;
+  P.base = base; P.ratio = ratio; P.residx = residx;
+  P.f0 = src->f0; P.rd = sl->rd; P.vtmagn = sl->vtmagn; P.vsphse = sl->vsphse; P.nvs = sl->nvs;
+  P.psd = src->psd; P.psdres = src->psdres; P.edc = src->edc; P.enhar = src->enhar; P.eampl = src->eampl; P.ephse = src->ephse;
+  P.nhar = src->nhar; P.ampl = src->ampl; P.phse = src->phse;
+  P.o_f0 = dst->f0; P.o_rd = dl->rd; P.o_vtmagn = dl->vtmagn; P.o_vsphse = dl->vsphse; P.o_nvs = dl->nvs;
+  P.o_psd = dst->psd; P.o_psdres = dst->psdres; P.o_edc = dst->edc; P.o_enhar = dst->enhar; P.o_eampl = dst->eampl;
+  P.o_ephse = dst->ephse; P.o_nhar = dst->nhar; P.o_ampl = dst->ampl; P.o_phse = dst->phse;
+  return run_frames_stretch(P, nullptr, nullptr);
+}

@@ -331,3 +331,69 @@ def check_coder_decode(o, ref, use_layer1):
         scale = max(float(np.abs(ref["ampl"]).max()), 1e-12)
         assert np.abs(o["ampl"] - ref["ampl"]).max() < 2e-5 * scale
         assert np.abs(phase_err(o["phse"], ref["phse"]) * ref["ampl"]).max() < 1e-4 * scale
+
+
+STRETCH_KEYS = ("f0", "rd", "vtmagn", "vsphse", "nvs", "psd", "psdres", "edc", "enhar", "eampl", "ephse")
+
+
+def stretch_case(B=1, F=24, seed=11, nfft=2048):
+    """Layer-1 frames for the interpolation tests: every voicing transition (voiced-voiced, voiced-unvoiced,
+    unvoiced-voiced, unvoiced-unvoiced) and envelope-harmonic counts that differ between neighbours."""
+    fr, conf = synth_frames(B, F, seed=seed, nhar=100, maxnhar=128, f0_lo=100, f0_hi=330, unvoiced=0.0)
+    rng = np.random.default_rng(seed + 1)
+    uv = np.zeros((B, F), bool)
+    uv[:, 5:9] = True
+    uv[:, 12] = True
+    uv[:, F - 3:] = True
+    for k in ("f0", "nhar"):
+        fr[k][uv] = 0
+    fr["ampl"][uv] = 0
+    fr["phse"][uv] = 0
+    fr["enhar"][...] = rng.integers(0, conf.maxnhar_e + 1, fr["enhar"].shape)
+    keep = np.arange(conf.maxnhar_e)[None, None, None, :] < fr["enhar"][..., None]
+    fr["eampl"] = np.where(keep, rng.uniform(1e-4, 1e-2, keep.shape), 0).astype(np.float32)
+    fr["ephse"] = np.where(keep, rng.uniform(-np.pi, np.pi, keep.shape), 0).astype(np.float32)
+    l1 = ref_tolayer1(fr, conf, nfft)
+    return fr, conf, l1
+
+
+def ref_stretch(fr, conf, l1, base, ratio, residx):
+    """interp_llsm_frame of the reference's demo (test/demo-stretch.c:50-129, compiled into the reference build from
+    where it lies) over a frame map: dict keyed as STRETCH_KEYS, [B][nfrm_new][...]. base / ratio / residx: [nfrm_new]."""
+    lib = load_ref()
+    B, F, Fn, n = conf.nutt, conf.nfrm, len(base), conf.nchannel
+    nspec = l1["vtmagn"].shape[-1]
+    o = dict(f0=np.zeros((B, Fn), np.float32), rd=np.zeros((B, Fn), np.float32), vtmagn=np.zeros((B, Fn, nspec), np.float32),
+             vsphse=np.zeros((B, Fn, conf.maxnhar), np.float32), nvs=np.zeros((B, Fn), np.int32),
+             psd=np.zeros((B, Fn, conf.npsd), np.float32), psdres=np.zeros((B, Fn, conf.npsd), np.float32),
+             edc=np.zeros((B, Fn, n), np.float32), enhar=np.zeros((B, Fn, n), np.int32),
+             eampl=np.zeros((B, Fn, n, conf.maxnhar_e), np.float32), ephse=np.zeros((B, Fn, n, conf.maxnhar_e), np.float32))
+    base = np.ascontiguousarray(base, np.int32)
+    ratio = np.ascontiguousarray(ratio, np.float32)
+    residx = np.ascontiguousarray(residx, np.int32)
+    c = np.ascontiguousarray
+    for b in range(B):
+        rc = lib.ref_stretch_soa(
+            F, C.c_float(conf.fs), C.c_float(conf.thop), conf.maxnhar, conf.maxnhar_e, conf.npsd, n,
+            C.c_float(conf.lip_radius), nspec, _p(c(fr["f0"][b])), _p(c(l1["rd"][b])), _p(c(l1["vtmagn"][b])),
+            _p(c(l1["vsphse"][b])), _p(c(l1["nvs"][b])), _p(c(fr["psd"][b])), _p(c(fr["psdres"][b])), _p(c(fr["edc"][b])),
+            _p(c(fr["enhar"][b])), _p(c(fr["eampl"][b])), _p(c(fr["ephse"][b])), Fn, _p(base), _p(ratio), _p(residx),
+            _p(o["f0"][b]), _p(o["rd"][b]), _p(o["vtmagn"][b]), _p(o["vsphse"][b]), _p(o["nvs"][b]), _p(o["psd"][b]),
+            _p(o["psdres"][b]), _p(o["edc"][b]), _p(o["enhar"][b]), _p(o["eampl"][b]), _p(o["ephse"][b]))
+        assert rc == 0
+    return o
+
+
+def check_stretch(o, ref, exact):
+    """Parity bar of the interpolation: counts and every linearly interpolated number identical (float operations
+    replayed one by one); the circularly interpolated phases and the dB fades go through cos / sin / atan2 / log in
+    double, rounded to float -- identical on the CPU emulation (same libm), within 1e-6 rad / dB on the GPU."""
+    for k in ("nvs", "enhar", "f0", "rd", "psd", "psdres", "edc", "eampl"):
+        assert np.array_equal(o[k], ref[k]), k
+    for k in ("vsphse", "ephse", "vtmagn"):
+        if exact:
+            assert np.array_equal(o[k], ref[k]), k
+        else:
+            d = np.abs(o[k].astype(np.float64) - ref[k]) if k == "vtmagn" else np.abs(phase_err(o[k], ref[k]))
+            assert d.max() <= (2e-5 if k == "vtmagn" else 1e-6), (k, d.max())
+            assert (o[k] == ref[k]).mean() > 0.999, (k, (o[k] == ref[k]).mean())
