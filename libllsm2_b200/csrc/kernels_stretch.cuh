@@ -33,8 +33,9 @@ __device__ __forceinline__ float st_linterp(float a, float b, float r) {
 }
 // test/demo-stretch.c:6-14
 __device__ __forceinline__ float st_linterpc(float a, float b, float r) {
-  const float ax = (float)cos((double)a), ay = (float)sin((double)a);
-  const float bx = (float)cos((double)b), by = (float)sin((double)b);
+  double sa, ca, sb, cb;
+  sincos((double)a, &sa, &ca); sincos((double)b, &sb, &cb);
+  const float ax = (float)ca, ay = (float)sa, bx = (float)cb, by = (float)sb;
   const float cx = st_linterp(ax, bx, r), cy = st_linterp(ay, by, r);
   return (float)atan2((double)cy, (double)cx);
 }
@@ -109,25 +110,25 @@ __global__ void __launch_bounds__(STRETCH_THREADS) frames_stretch_kernel(Stretch
   if(P.o_psdres && P.psdres)                                    // test/demo-stretch.c:180-183
     for(int k = tid; k < P.npsd; k += STRETCH_THREADS)
       P.o_psdres[o * P.npsd + k] = P.psdres[((size_t)b * P.nfrm + res) * P.npsd + k];
-  for(int c = 0; c < P.nchannel; c ++) {
+  for(int c = tid; c < P.nchannel; c += STRETCH_THREADS) {
+    const size_t dc = d * P.nchannel + c, sc = s * P.nchannel + c, oc = o * P.nchannel + c;
+    P.o_edc[oc] = st_linterp(P.edc[dc], P.edc[sc], ratio);
+    P.o_enhar[oc] = P.enhar[dc] > P.enhar[sc] ? P.enhar[dc] : P.enhar[sc];
+  }
+  for(int q = tid; q < P.nchannel * P.maxnhar_e; q += STRETCH_THREADS) {     // all channels in one pass
+    const int c = q / P.maxnhar_e, k = q - c * P.maxnhar_e;
     const size_t dc = d * P.nchannel + c, sc = s * P.nchannel + c, oc = o * P.nchannel + c;
     const int de = P.enhar[dc], se = P.enhar[sc];
     const int emin = de < se ? de : se, emax = de > se ? de : se;
-    if(tid == 0) {
-      P.o_edc[oc] = st_linterp(P.edc[dc], P.edc[sc], ratio);
-      P.o_enhar[oc] = emax;
+    float a = 0.f, p = 0.f;
+    if(k < emin) {
+      a = st_linterp(P.eampl[dc * P.maxnhar_e + k], P.eampl[sc * P.maxnhar_e + k], ratio);
+      p = st_linterpc(P.ephse[dc * P.maxnhar_e + k], P.ephse[sc * P.maxnhar_e + k], ratio);
+    } else if(k < emax) {                                       // the longer frame's own harmonics, unscaled
+      const size_t e = (se > de ? sc : dc) * P.maxnhar_e + k;
+      a = P.eampl[e]; p = P.ephse[e];
     }
-    for(int k = tid; k < P.maxnhar_e; k += STRETCH_THREADS) {
-      float a = 0.f, p = 0.f;
-      if(k < emin) {
-        a = st_linterp(P.eampl[dc * P.maxnhar_e + k], P.eampl[sc * P.maxnhar_e + k], ratio);
-        p = st_linterpc(P.ephse[dc * P.maxnhar_e + k], P.ephse[sc * P.maxnhar_e + k], ratio);
-      } else if(k < emax) {                                     // the longer frame's own harmonics, unscaled
-        const size_t q = (se > de ? sc : dc) * P.maxnhar_e + k;
-        a = P.eampl[q]; p = P.ephse[q];
-      }
-      P.o_eampl[oc * P.maxnhar_e + k] = a; P.o_ephse[oc * P.maxnhar_e + k] = p;
-    }
+    P.o_eampl[oc * P.maxnhar_e + k] = a; P.o_ephse[oc * P.maxnhar_e + k] = p;
   }
 
   // ---- the layer-0 harmonics ride along unchanged from frame `base` (llsm_copy_container, :176); they are

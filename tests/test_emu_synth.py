@@ -62,3 +62,10 @@ def test_silent_noise_frames_are_skipped():
         fr["psd"][:, 5:12, :] = -120.0
     ref, got = _run(1, 24, mutate=mut)
     _check(ref, got, 1e-6)
+
+
+@pytest.mark.parametrize("nch,nhar_e", [(2, 3), (3, 3), (1, 2)])
+def test_other_channel_counts(nch, nhar_e):
+    """Fewer than four noise channels: the excitation kernel's generic coefficient layout (padded frame slots)."""
+    ref, got = _run(1, 20, seed=5, nch=nch, nhar_e=nhar_e)
+    _check(ref, got, 1e-6)

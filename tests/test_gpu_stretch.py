@@ -92,13 +92,16 @@ def test_full_size_identity_and_midpoint(ctx):
 def test_demo_pipeline_stays_on_the_device(ctx):
     """test/demo-stretch.c:160-187 with device-resident arrays: tolayer1 -> phasepropagate(-1) -> stretch x2 ->
     tolayer0 -> phasepropagate(+1) -> synthesize. The stretched utterance is twice as long, finite, and carries about the
-    same power as the original."""
+    same power as the unstretched layer 0 -> 1 -> 0 round trip (which on these synthetic frames is not the power of the
+    input: the reference's envelope passes over the scattered harmonic amplitudes)."""
     import torch
     import libllsm2_b200 as L
     fr, conf = S.synth_frames(2, 120, seed=71, nhar=100, maxnhar=128, f0_lo=100, f0_hi=250)
     d = _cuda(fr)
-    y0 = L.synthesize_l0(ctx, conf, d, seed=3)["y"]
     l1 = L.tolayer1(ctx, conf, d, 2048)
+    back = dict(d)
+    back.update(L.tolayer0(ctx, conf, d["f0"], l1))                   # the unstretched layer-1 round trip
+    y0 = L.synthesize_l0(ctx, conf, back, seed=3)["y"]
     L.chunk_phasepropagate(ctx, conf, d, l1, sign=-1)
     base, ratio, res = L.stretch_map(conf.nfrm, 2 * conf.nfrm)
     t = lambda a: torch.from_numpy(a).cuda()  # noqa: E731
