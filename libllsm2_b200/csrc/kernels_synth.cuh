@@ -750,7 +750,7 @@ __global__ void __launch_bounds__(SHW_THREADS, 2) noise_shape_warp_kernel(ShapeP
   const float inv = 1.0f / 1024.0f;
   __syncthreads();
 
-  const float psc = 44100.f / P.fs;
+  const float psc = 44100.f / P.fs, psc7 = psc / 7.f;
   const float inv_wsqr = 1.0f / P.wsqr;
   for(int r0 = ia_; r0 < ib; r0 += 2 * SHW_WARPS) {
     const int i = r0 + 2 * warp;                 // this warp's pair (i, i + 1)
@@ -902,12 +902,13 @@ __global__ void __launch_bounds__(SHW_THREADS, 2) noise_shape_warp_kernel(ShapeP
                 } else {
                   for(int q = l; q <= u; q ++) { smA += pbuf[q]; smB += pbuf[NSPEC + q]; }
                 }
-                const float rc = psc / (float)(u - l + 1);
+                const float rc = (u - l == 6) ? psc7 : psc / (float)(u - l + 1);
                 int pl = P.psd_lo[kk]; float pr = P.psd_r[kk];
                 float hA = spsd[pl], hB = hasB ? spsd[npsd + pl] : 0.f;
                 if(pr != 0.f) { hA = hA + (spsd[pl + 1] - hA) * pr; if(hasB) hB = hB + (spsd[npsd + pl + 1] - hB) * pr; }
-                if(doA) HA = expf(hA * (2.3025851f / 20.0f)) * rsqrtf(smA * rc + 1e-8f);
-                if(doB) HB = expf(hB * (2.3025851f / 20.0f)) * rsqrtf(smB * rc + 1e-8f);
+                // 10^(h / 20) as 2^(h log2(10) / 20): one ex2 instead of expf's range reduction
+                if(doA) HA = exp2f(hA * 0.16609640474f) * rsqrtf(smA * rc + 1e-8f);
+                if(doB) HB = exp2f(hB * 0.16609640474f) * rsqrtf(smB * rc + 1e-8f);
               }
               __syncwarp();
               if(t >= 1) { pbuf[kk - 32] = hAp; pbuf[NSPEC + kk - 32] = hBp; }
