@@ -70,6 +70,12 @@ def test_c3_harmonics(ctx):
     _case(ctx, 2, 120, nhar=256, f0_lo=60, f0_hi=86)
 
 
+@pytest.mark.parametrize("nch,nhar_e", [(2, 3), (3, 3), (1, 2)])
+def test_other_channel_counts(ctx, nch, nhar_e):
+    """Fewer than four noise channels (the reference's default is four, `llsm_create_aoptions`)."""
+    _case(ctx, 2, 80, seed=6, nch=nch, nhar_e=nhar_e)
+
+
 def test_48k_10ms(ctx):
     _case(ctx, 2, 60, fs=48000.0, thop=0.01, nhar=100)
 
