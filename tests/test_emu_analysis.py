@@ -43,3 +43,19 @@ def test_analysis_c2_shape_small(method):
                             C.byref(fo), o["x_res"].ctypes.data_as(C.c_void_p))
     assert rc == 0
     check_analysis(o, ref, conf)
+
+
+def test_analysis_two_channels():
+    """nchannel = 2 (one band edge): the sub-band envelope analysis with fewer channels than the default four."""
+    fr, conf = S.synth_frames(1, 20, seed=4, nhar=80, maxnhar=80, nch=2, nhar_e=3)
+    y, ys, yn = S.ref_synthesize(fr, conf, seed=5)
+    nx = y.shape[1]
+    ref = S.ref_analyze(y, fr["f0"], conf, hm_method=1)
+    emu = S.load_emu()
+    o = S.alloc_analysis_out(conf, nx, fr["f0"])
+    ao = abi.AOptions(); ao.f0_refine = 1; ao.hm_method = 1; ao.rel_winsize = 4.0
+    fo = S.frames_out_struct(o)
+    rc = emu.emu_analyze_l0(C.byref(conf), C.byref(ao), y.ctypes.data_as(C.c_void_p), nx, nx,
+                            C.byref(fo), o["x_res"].ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    check_analysis(o, ref, conf)

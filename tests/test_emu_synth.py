@@ -8,8 +8,10 @@ import support as S
 from libllsm2_b200 import abi
 
 
-def _run(B, F, seed=7, nfrm_utt=None, mutate=None, **kw):
+def _run(B, F, seed=7, nfrm_utt=None, mutate=None, chanfreq=None, **kw):
     fr, conf = S.synth_frames(B, F, **kw)
+    for i, f in enumerate(chanfreq or ()):
+        conf.chanfreq[i] = f
     if mutate:
         mutate(fr)
     if nfrm_utt is not None:
@@ -68,4 +70,10 @@ def test_silent_noise_frames_are_skipped():
 def test_other_channel_counts(nch, nhar_e):
     """Fewer than four noise channels: the excitation kernel's generic coefficient layout (padded frame slots)."""
     ref, got = _run(1, 20, seed=5, nch=nch, nhar_e=nhar_e)
+    _check(ref, got, 1e-6)
+
+
+def test_six_channels():
+    """More than four noise channels: the eight-channel instance of the excitation kernel."""
+    ref, got = _run(1, 20, seed=8, nch=6, nhar_e=3, chanfreq=(1000.0, 2000.0, 4000.0, 8000.0, 12000.0))
     _check(ref, got, 1e-6)

@@ -41,8 +41,10 @@ def _compare(ref, got, tol=TOL):
     return errs
 
 
-def _case(ctx, B, F, seed=5, nfrm_utt=None, mutate=None, tol=TOL, **kw):
+def _case(ctx, B, F, seed=5, nfrm_utt=None, mutate=None, tol=TOL, chanfreq=None, **kw):
     fr, conf = S.synth_frames(B, F, **kw)
+    for i, f in enumerate(chanfreq or ()):
+        conf.chanfreq[i] = f
     if mutate:
         mutate(fr)
     if nfrm_utt is not None:
@@ -74,6 +76,10 @@ def test_c3_harmonics(ctx):
 def test_other_channel_counts(ctx, nch, nhar_e):
     """Fewer than four noise channels (the reference's default is four, `llsm_create_aoptions`)."""
     _case(ctx, 2, 80, seed=6, nch=nch, nhar_e=nhar_e)
+
+
+def test_six_channels(ctx):
+    _case(ctx, 2, 80, seed=8, nch=6, nhar_e=3, chanfreq=(1000.0, 2000.0, 4000.0, 8000.0, 12000.0))
 
 
 def test_48k_10ms(ctx):
