@@ -103,15 +103,18 @@ __device__ float2* block_fft(float2* a, float2* b, int lg, const float2* __restr
   const int tid = threadIdx.x, nth = blockDim.x;
   int p = 1; // butterflies already combined
   int rem = lg;
+  int sh = 0; while((4 << sh) < ntw) sh ++;    // twiddle index step of a radix-4 pass: ntw / (4 p) = 1 << sh
   while(rem >= 2) {
     const int t = n >> 2;
-    const int tws = ntw / (4 * p); // index step: angle -2 pi k / (4p)
     for(int i = tid; i < t; i += nth) {
       int k = i & (p - 1);
-      float2 u0 = a[FIX(i)];
-      float2 u1 = cmul(a[FIX(i + t)], fft_tw<INV>(tw, k * tws));
-      float2 u2 = cmul(a[FIX(i + 2 * t)], fft_tw<INV>(tw, 2 * k * tws));
-      float2 u3 = cmul(a[FIX(i + 3 * t)], fft_tw<INV>(tw, 3 * k * tws));
+      float2 u0 = a[FIX(i)], u1 = a[FIX(i + t)], u2 = a[FIX(i + 2 * t)], u3 = a[FIX(i + 3 * t)];
+      if(p > 1) {                               // the first pass has unit twiddles (uniform branch)
+        const int m = k << sh;                  // angle -2 pi k / (4p)
+        u1 = cmul(u1, fft_tw<INV>(tw, m));
+        u2 = cmul(u2, fft_tw<INV>(tw, 2 * m));
+        u3 = cmul(u3, fft_tw<INV>(tw, 3 * m));
+      }
       float2 v0 = make_float2(u0.x + u2.x, u0.y + u2.y);
       float2 v1 = make_float2(u0.x - u2.x, u0.y - u2.y);
       float2 v2 = make_float2(u1.x + u3.x, u1.y + u3.y);
@@ -126,15 +129,15 @@ __device__ float2* block_fft(float2* a, float2* b, int lg, const float2* __restr
     }
     __syncthreads();
     float2* sw = a; a = b; b = sw;
-    p <<= 2; rem -= 2;
+    p <<= 2; rem -= 2; sh -= 2;
   }
   if(rem == 1) {
     const int t = n >> 1;
-    const int tws = ntw / (2 * p);
     for(int i = tid; i < t; i += nth) {
       int k = i & (p - 1);
       float2 u0 = a[FIX(i)];
-      float2 u1 = cmul(a[FIX(i + t)], fft_tw<INV>(tw, k * tws));
+      float2 u1 = a[FIX(i + t)];
+      if(p > 1) u1 = cmul(u1, fft_tw<INV>(tw, k << (sh + 1)));   // ntw / (2 p)
       int j = ((i - k) << 1) + k;
       b[FIX(j)]     = make_float2(u0.x + u1.x, u0.y + u1.y);
       b[FIX(j + p)] = make_float2(u0.x - u1.x, u0.y - u1.y);

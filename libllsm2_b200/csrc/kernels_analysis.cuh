@@ -631,7 +631,7 @@ __global__ void __launch_bounds__(NS_THREADS) noise_spec_kernel(NoiseSpecParams 
       if(h == 1 && ! two) break;
       const int ws = wsv[h];
       const float rws = 2.0f / (float)ws;
-      int j0 = (kb + ws / 2) % nfs;
+      int j0 = (kb + ws / 2) & (nfs - 1);           // nfs is a power of two
       for(int j = j0; j < ws; j += nfs) {           // time aliasing when the window exceeds nfft
         int idx = cen[h] + j - ws / 2;
         if(idx >= 0 && idx < P.nx) {
@@ -690,7 +690,7 @@ __global__ void __launch_bounds__(NS_THREADS) noise_spec_kernel(NoiseSpecParams 
   __syncthreads();
   float2* Ev = block_fft<false, true>(D, Cq, P.lg_nfft_s, P.tw_s, nfs);
   for(int j = tid; j < P.nspec; j += nth) {
-    int idx = j * nfs / P.nfft;                                       // layer0.c:341-342
+    int idx = (j * nfs) >> P.lg_nfft;                                 // j * nfs / nfft, layer0.c:341-342
     const float2 e = Ev[fsw(idx)];
     P.env[orow + j] = e.x * 2.0f;
     if(two) P.env[orow + P.nspec + j] = e.y * 2.0f;
