@@ -143,7 +143,9 @@ struct HarmDftParams {
 // signal, HD_THREADS / 32 signals of the same frame per CTA: the sub-band envelope pass, where the window,
 // its sum and the frame geometry are shared by the channels). With P.edc != NULL the group also writes
 // the short-time mean of its signal (llsm_compute_dc, dsputils.c:117-124; window rule layer0.c:430,446).
-template <int G>
+// KW = harmonics the warp-per-signal variant carries in registers (its loops are unrolled to KW: with the usual four
+// envelope harmonics the eight-wide instance spent half its instructions on predicated-off harmonics).
+template <int G, int KW = HD_KW>
 __global__ void __launch_bounds__(HD_THREADS) harmonic_dft_kernel(HarmDftParams P) {
   LLSM_DYN_SMEM(smem);
   constexpr int NG = HD_THREADS / G;                  // signals per CTA
@@ -172,9 +174,15 @@ __global__ void __launch_bounds__(HD_THREADS) harmonic_dft_kernel(HarmDftParams 
     double wlen = f0 == 0 ? (double)(P.thop * 2.0f) : 2.0 / (double)f0;
     const int nw = (int)round(wlen * (double)P.fs);
     double acc = 0;
-    for(int j = gt; j < nw; j += G) {
-      int idx = center + j - nw / 2;
-      if(idx >= 0 && idx < P.nx) acc += (double)x[idx];
+    for(int j = gt; j < nw; j += 4 * G) {               // four reads in flight, summed in the same order
+      float v[4];
+#pragma unroll
+      for(int u = 0; u < 4; u ++) {
+        const int idx = center + j + u * G - nw / 2;
+        v[u] = (j + u * G < nw && idx >= 0 && idx < P.nx) ? x[idx] : 0.f;
+      }
+#pragma unroll
+      for(int u = 0; u < 4; u ++) acc += (double)v[u];
     }
     if(G == 32) {
       for(int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -266,21 +274,23 @@ __global__ void __launch_bounds__(HD_THREADS) harmonic_dft_kernel(HarmDftParams 
   if(G == 32) {
     // ---- a warp per signal, at most HD_KW harmonics: every lane walks its own samples (coalesced reads)
     //      carrying one phasor per harmonic, advanced 32 samples at a time and re-seeded every 8 steps
-    float2 w[HD_KW], z32[HD_KW]; float re[HD_KW], im[HD_KW];
+    float2 w[KW], z32[KW]; float re[KW], im[KW];
 #pragma unroll
-    for(int k = 0; k < HD_KW; k ++) {
+    for(int k = 0; k < KW; k ++) {
       re[k] = 0.f; im[k] = 0.f;
       z32[k] = k < nh ? unit_phasor_turns((double)(k + 1) * nu * 32.0) : make_float2(1.f, 0.f);
     }
     int step = 0;
+    float2 sv_next = gt < npair ? pair_at(gt) : make_float2(0.f, 0.f);
     for(int n = gt; n < npair; n += 32, step ++) {
+      const float2 sv = sv_next;                          // read one step ahead of its use
+      if(n + 32 < npair) sv_next = pair_at(n + 32);
       if((step & 7) == 0) {
 #pragma unroll
-        for(int k = 0; k < HD_KW; k ++) if(k < nh) w[k] = unit_phasor_turns((double)(k + 1) * nu * (double)n);
+        for(int k = 0; k < KW; k ++) if(k < nh) w[k] = unit_phasor_turns((double)(k + 1) * nu * (double)n);
       }
-      const float2 sv = pair_at(n);
 #pragma unroll
-      for(int k = 0; k < HD_KW; k ++) if(k < nh) {
+      for(int k = 0; k < KW; k ++) if(k < nh) {
         re[k] = fmaf(sv.x, w[k].x, re[k]);
         im[k] = fmaf(-sv.y, w[k].y, im[k]);
         w[k] = cmul(w[k], z32[k]);
@@ -288,7 +298,7 @@ __global__ void __launch_bounds__(HD_THREADS) harmonic_dft_kernel(HarmDftParams 
     }
     float myre = 0.f, myim = 0.f;
 #pragma unroll
-    for(int k = 0; k < HD_KW; k ++) {
+    for(int k = 0; k < KW; k ++) {
       float r = re[k], q = im[k];
       for(int o = 16; o > 0; o >>= 1) { r += __shfl_xor_sync(0xffffffffu, r, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
       if(gt == k) { myre = r; myim = q; }
@@ -513,8 +523,14 @@ static inline int launch_harmonic_dft(const HarmDftParams& Pin, int nutt, cudaSt
   dim3 grid(P.nfrm, nutt * ((P.nsig + ng - 1) / ng)), block(HD_THREADS);
   size_t smem = harm_dft_smem(P.max_half, ng);
   if(smem > 200 * 1024) return -1;
-  if(warp_groups) {
-    auto kfn = harmonic_dft_kernel<32>;
+  if(warp_groups && P.maxnhar <= 4) {
+    auto kfn = harmonic_dft_kernel<32, 4>;
+#ifndef LLSM_EMU
+    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#endif
+    LLSM_LAUNCH(kfn, grid, block, smem, st, P);
+  } else if(warp_groups) {
+    auto kfn = harmonic_dft_kernel<32, HD_KW>;
 #ifndef LLSM_EMU
     cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 #endif
