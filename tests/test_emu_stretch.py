@@ -105,3 +105,15 @@ def test_per_utterance_maps():
         c1 = abi.make_conf(1, conf.nfrm, conf.maxnhar, conf.maxnhar_e, conf.npsd, conf.nchannel, conf.fs, conf.thop)
         ref = S.ref_stretch(one, c1, l1b, base[b], ratio[b], res[b])
         S.check_stretch({k: o[k][b:b + 1] for k in S.STRETCH_KEYS}, ref, exact=True)
+
+
+def test_out_of_range_maps_are_clamped():
+    """base is clamped to [0, nfrm - 2] (frame base + 1 must exist), residx to [0, nfrm - 1]."""
+    fr, conf, l1 = S.stretch_case(B=1, F=24, seed=41)
+    F = conf.nfrm
+    base = np.array([-5, 0, F - 2, F - 1, 1000], np.int32)
+    ratio = np.array([0.25, 0.25, 0.5, 0.5, 0.75], np.float32)
+    res = np.array([-1, 3, F - 1, F, 1000], np.int32)
+    o = emu_stretch(fr, conf, l1, base, ratio, res)
+    ref = S.ref_stretch(fr, conf, l1, np.clip(base, 0, F - 2), ratio, np.clip(res, 0, F - 1))
+    S.check_stretch(o, ref, exact=True)
