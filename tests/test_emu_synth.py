@@ -77,3 +77,9 @@ def test_six_channels():
     """More than four noise channels: the eight-channel instance of the excitation kernel."""
     ref, got = _run(1, 20, seed=8, nch=6, nhar_e=3, chanfreq=(1000.0, 2000.0, 4000.0, 8000.0, 12000.0))
     _check(ref, got, 1e-6)
+
+
+def test_empty_utterance_in_a_ragged_batch():
+    ref, got = _run(3, 20, nfrm_utt=[20, 0, 13])
+    _check(ref, got, 1e-6)
+    assert all(np.all(g[1] == 0) for g in got)

@@ -78,6 +78,11 @@ def test_other_channel_counts(ctx, nch, nhar_e):
     _case(ctx, 2, 80, seed=6, nch=nch, nhar_e=nhar_e)
 
 
+def test_empty_utterance_in_a_ragged_batch(ctx):
+    fr, conf, white, ref, got = _case(ctx, 3, 60, nfrm_utt=[60, 0, 13])
+    assert all(np.all(g[1] == 0) for g in got)
+
+
 def test_six_channels(ctx):
     _case(ctx, 2, 80, seed=8, nch=6, nhar_e=3, chanfreq=(1000.0, 2000.0, 4000.0, 8000.0, 12000.0))
 
