@@ -143,12 +143,6 @@ __global__ void __launch_bounds__(STRETCH_THREADS) frames_stretch_kernel(Stretch
   }
 }
 
-// algorithmic bytes of one output frame: two source rows read, one written, plus the PSDRES row both ways
-static inline double stretch_bytes_per_frame(int maxnhar, int maxnhar_e, int npsd, int nchannel, int nspec) {
-  const double row = 4.0 * (2 + 1 + maxnhar + nspec + npsd + nchannel * (2 + 2 * maxnhar_e));
-  return 3.0 * row + 2.0 * 4.0 * npsd;
-}
-
 static inline int run_frames_stretch(const StretchParams& P, cudaStream_t st, LaunchCounter* lc) {
   LLSM_LAUNCH(frames_stretch_kernel, dim3(P.nfrm_new, P.nutt), dim3(STRETCH_THREADS), 0, st, P);
   if(lc) lc->n += 1;
