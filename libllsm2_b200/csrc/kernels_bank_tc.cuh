@@ -150,6 +150,11 @@ __global__ void __launch_bounds__(BTC_THREADS, 1) hm_bank_tc_kernel(BankParams P
   const int start = t0 == 0 ? 0 : (t0 < nf ? P.hm_base[t0] : P.nsamp);
   const int end = (t0 + F < nf) ? P.hm_base[t0 + F] : P.nsamp;
   if(start >= end) return;                                   // uniform per CTA
+  if(nf <= 0) {                                              // an empty utterance owns no tile: its row is silence
+    float* yrow = P.y_sin + (size_t)b * P.stride;
+    for(int i = tid; i < P.nsamp; i += BTC_THREADS) yrow[i] = 0.f;
+    return;
+  }
   const size_t row = (size_t)b * P.nfrm;
 
   // ---- set-up: tensor memory, barriers, window, per-frame scalars ----
