@@ -80,8 +80,16 @@ extern "C" int emu_synthesize_l1(const llsm_b200_conf* conf, const llsm_b200_fra
   SynthPlanDev pd; L1PlanDev lp; SynthScratch sc; PbpScratch ps;
   if(pd.build(conf->nfrm, conf->fs, conf->thop, conf->npsd, conf->nchannel, conf->chanfreq, nullptr) != 0) return -100;
   if(lp.build(nullptr) != 0) return -101;
-  int rc = run_synth_l1(pd, lp, sc, ps, *conf, *fr, *l1, pbpsyn, *opt, *out, nullptr, nullptr, nullptr);
-  sc.colored.release(); sc.y_exc.release(); ps.release(); lp.release(); pd.release();
+  DevBuf nyb;
+  const int* ny_utt = nullptr;
+  if(fr->nfrm_utt) {                                   // ragged batch: per-utterance output lengths, as the library does
+    nyb.reserve(conf->nutt * sizeof(int));
+    LLSM_LAUNCH(ny_utt_kernel, dim3((conf->nutt + 63) / 64), dim3(64), 0, nullptr,
+      fr->nfrm_utt, conf->nutt, conf->thop, conf->fs, nyb.as<int>());
+    ny_utt = nyb.as<int>();
+  }
+  int rc = run_synth_l1(pd, lp, sc, ps, *conf, *fr, *l1, pbpsyn, *opt, *out, ny_utt, nullptr, nullptr);
+  sc.colored.release(); sc.y_exc.release(); ps.release(); lp.release(); pd.release(); nyb.release();
   return rc;
 }
 

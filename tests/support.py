@@ -397,3 +397,43 @@ def check_stretch(o, ref, exact):
             d = np.abs(o[k].astype(np.float64) - ref[k]) if k == "vtmagn" else np.abs(phase_err(o[k], ref[k]))
             assert d.max() <= (2e-5 if k == "vtmagn" else 1e-6), (k, d.max())
             assert (o[k] == ref[k]).mean() > 0.999, (k, (o[k] == ref[k]).mean())
+
+
+def pbp_ragged_case(nfu=(30, 0, 11), F=30, seed=13):
+    """A ragged batch for layer-1 synthesis: per-utterance reference runs (None for an empty utterance), the layer-1
+    members they produced, the white-noise templates of the ragged batch. frames come back without the layer-0
+    harmonics (derived from layer 1) and with nfrm_utt set."""
+    B = len(nfu)
+    nfu = np.asarray(nfu, np.int32)
+    fr, conf = synth_frames(B, F, seed=seed, nhar=100, maxnhar=100)
+    pbp = np.zeros((B, F), np.int32); pbp[:, 4:20] = 1
+    refs, l1 = [], dict(rd=np.zeros((B, F), np.float32), vtmagn=np.zeros((B, F, 1025), np.float32),
+                        vsphse=np.zeros((B, F, conf.maxnhar), np.float32), nvs=np.zeros((B, F), np.int32))
+    for b in range(B):
+        n = int(nfu[b])
+        if n == 0:
+            refs.append(None)
+            continue
+        one = {k: (np.ascontiguousarray(v[b:b + 1, :n]) if v is not None else None) for k, v in fr.items()}
+        c1 = abi.make_conf(1, n, conf.maxnhar, conf.maxnhar_e, conf.npsd, conf.nchannel, conf.fs, conf.thop)
+        r, l = ref_synthesize_l1(one, c1, pbp[b:b + 1, :n], seed=9 + b)
+        refs.append(r)
+        for k in l1:
+            l1[k][b, :n] = l[k][0]
+    fr["nfrm_utt"] = nfu
+    fr["nhar"] = fr["ampl"] = fr["phse"] = None
+    ny = load_ref().ref_output_length(F, C.c_float(conf.thop), C.c_float(conf.fs))
+    white = ref_white_noise(conf, seed=9, nfrm_utt=nfu)
+    return fr, conf, pbp, l1, refs, white, ny
+
+
+def check_pbp_ragged(got, refs, tol):
+    for b, ref in enumerate(refs):
+        for k, g in enumerate(got):
+            assert np.isfinite(g[b]).all()
+            if ref is None:
+                assert np.all(g[b] == 0)
+            else:
+                nyb = ref[k].shape[1]
+                assert rms(g[b, :nyb] - ref[k][0]) < tol, (b, k, rms(g[b, :nyb] - ref[k][0]))
+                assert np.all(g[b, nyb:] == 0)

@@ -30,3 +30,19 @@ def test_pbp_synthesis(mode):
                                  C.byref(so), C.byref(out)) == 0
     for r, g, name in zip(ref, (oy, oys, oyn), ("y", "y_sin", "y_noise")):
         assert S.rms(g - r) < 1e-5, (name, S.rms(g - r))
+
+
+def test_pbp_ragged_batch_with_an_empty_utterance():
+    """Utterances of 30, 0 and 11 frames in one batch: each row equals the reference run on that utterance alone
+    (an empty utterance is silence)."""
+    fr, conf, pbp, l1, refs, white, ny = S.pbp_ragged_case()
+    B = conf.nutt
+    so = abi.default_soptions(white.ctypes.data, 0)
+    oy = np.full((B, ny), np.nan, np.float32); oys = oy.copy(); oyn = oy.copy()
+    out = abi.Output(); out.y = oy.ctypes.data; out.y_sin = oys.ctypes.data; out.y_noise = oyn.ctypes.data; out.stride = ny
+    f = S.frames_struct(fr)
+    s = abi.Layer1(); s.rd = l1["rd"].ctypes.data; s.vtmagn = l1["vtmagn"].ctypes.data
+    s.vsphse = l1["vsphse"].ctypes.data; s.nvs = l1["nvs"].ctypes.data; s.nspec = 1025
+    assert S.load_emu().emu_synthesize_l1(C.byref(conf), C.byref(f), C.byref(s), pbp.ctypes.data_as(C.c_void_p),
+                                          C.byref(so), C.byref(out)) == 0
+    S.check_pbp_ragged((oy, oys, oyn), refs, 1e-5)

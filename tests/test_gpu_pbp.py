@@ -41,3 +41,14 @@ def test_pbp_synthesis(ctx, kw, pattern):
     for r, k in zip(ref, ("y", "y_sin", "y_noise")):
         e = S.rms(out[k].cpu().numpy() - r)
         assert e < 1e-4, (k, e)
+
+
+def test_pbp_ragged_batch_with_an_empty_utterance(ctx):
+    """Utterances of 30, 0 and 11 frames in one batch against per-utterance reference runs; silence past each end."""
+    import torch
+    import libllsm2_b200 as L
+    fr, conf, pbp, l1, refs, white, ny = S.pbp_ragged_case()
+    out = L.synthesize_l1(ctx, conf, _dev(fr), _dev(l1), pbpsyn=torch.from_numpy(pbp).cuda(),
+                          white=torch.from_numpy(white).cuda())
+    torch.cuda.synchronize()
+    S.check_pbp_ragged(tuple(out[k].cpu().numpy()[:, :ny] for k in ("y", "y_sin", "y_noise")), refs, 1e-4)
