@@ -233,3 +233,29 @@ def test_if_detector_refines_f0_of_a_harmonic_signal():
     lib.llsm_refine_f0(_p(x), nx, C.c_float(fs), _p(f0), nfrm, C.c_float(thop))
     assert np.abs(f0[8:-8] - true).max() < 0.4, np.abs(f0[8:-8] - true).max()
     assert np.abs(f0[8:-8] - true).max() < 0.12 * 3.4
+
+
+@pytest.mark.parametrize("window,nwin", [("hanning", 1024), ("blackman", 882), ("hanning", 3000)])
+def test_stft_reads_amplitude_and_phase_of_a_sinusoid_at_the_frame_centre(window, nwin):
+    """Known answer: A cos(2 pi f t + phi) with f on a bin gives |X| 2 / sum(w) = A and arg X = the phase at the frame
+    centre (zero-phase window placement), also for a window longer than the transform (time aliasing)."""
+    lib = S.load_ref()
+    nfft, fs, k0, A, phi = 2048, 16000.0, 37, 0.7, 0.9
+    f = k0 * fs / nfft
+    nx = 8000
+    t = np.arange(nx)
+    x = (A * np.cos(2 * np.pi * f / fs * t + phi)).astype(F32)
+    centers = np.array([2500, 4001, 5555], np.int32)
+    nw = np.full(3, nwin, np.int32)
+    ns = nfft // 2 + 1
+    mag, ph = np.zeros((3, ns), F32), np.zeros((3, ns), F32)
+    rows = lambda a: (C.c_void_p * 3)(*[a[i].ctypes.data for i in range(3)])  # noqa: E731
+    norm = np.zeros(3, F32)
+    lib.cig_stft_forward.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_char_p, C.c_int,
+                                     C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.cig_stft_forward(_p(x), nx, _p(centers), _p(nw), 3, nfft, window.encode(), 0, 0, _p(norm), None, rows(mag), rows(ph))
+    for i, c in enumerate(centers):
+        assert abs(mag[i, k0] * 2.0 / norm[i] - A) < 2e-4
+        want = 2 * np.pi * f / fs * float(c) + phi
+        assert abs(S.phase_err(ph[i, k0], want)) < 2e-4
+        assert int(np.argmax(mag[i])) == k0
