@@ -259,3 +259,38 @@ def test_stft_reads_amplitude_and_phase_of_a_sinusoid_at_the_frame_centre(window
         want = 2 * np.pi * f / fs * float(c) + phi
         assert abs(S.phase_err(ph[i, k0], want)) < 2e-4
         assert int(np.argmax(mag[i])) == k0
+
+
+def test_spec2env_removes_ripple_at_the_pitch_period_and_keeps_the_envelope():
+    """The cepstral lifter is a sinc with its first zero at quefrency 1 / f0: harmonic ripple of period f0 in the log
+    spectrum vanishes, a slow envelope passes (times the lifter's gain at that quefrency)."""
+    lib = S.load_ref()
+    lib.cig_spec2env.restype = C.POINTER(C.c_float)
+    lib.cig_spec2env.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_void_p]
+    nfft, ns = 2048, 1025
+    f0 = 1.0 / 64.0                                   # cycles per sample: ripple period 32 bins, quefrency 64
+    k = np.arange(ns)
+    slow_q = 4                                        # envelope component at quefrency 4
+    logS = -3.0 + 0.8 * np.cos(2 * np.pi * slow_q * k / nfft) + 0.5 * np.cos(2 * np.pi * k / 32.0)
+    Sp = np.exp(logS).astype(F32)
+    env = _take(lib.cig_spec2env(_p(Sp), nfft, C.c_float(f0), 0, None), ns)
+    x = f0 * slow_q
+    gain = np.sin(np.pi * x) / (np.pi * x) * (1.18 - 0.18 * np.cos(2 * np.pi * x))
+    want = -3.0 + 0.8 * gain * np.cos(2 * np.pi * slow_q * k / nfft)
+    assert np.abs(env - want).max() < 2e-5
+
+
+def test_interp1u_has_an_exclusive_end_point_and_blank_filling_holds_the_ends():
+    lib = S.load_ref()
+    fp = C.POINTER(C.c_float)
+    lib.interp1u.restype = fp
+    lib.interp1u.argtypes = [C.c_float, C.c_float, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    yi = np.array([0.0, 1.0, 4.0, 9.0], F32)                         # knots at 0, 1, 2, 3 when x1 = 4 (last knot + one step)
+    xq = np.array([-1.0, 0.5, 2.5, 3.0, 3.9], F32)
+    got = _take(lib.interp1u(0.0, 4.0, _p(yi), 4, _p(xq), 5), 5)
+    assert np.allclose(got, [0.0, 0.5, 6.5, 9.0, 9.0], atol=1e-6)
+    lib.interp_in_blank.restype = fp
+    lib.interp_in_blank.argtypes = [C.c_void_p, C.c_int, C.c_float]
+    x = np.array([0, 0, 2, 0, 0, 5, 0], F32)
+    got = _take(lib.interp_in_blank(_p(x), 7, 0.0), 7)
+    assert np.allclose(got, [2, 2, 2, 3, 4, 5, 5], atol=1e-6)
