@@ -89,7 +89,7 @@ def _run_l1(B, F, pbp, seed=6, remove_hm=1, host_tracker=0, block=5, **kw):
 def test_rt_layer1_pulse_by_pulse(mode, host_tracker):
     """use_l1 streaming: onset two periods early, windowed hand-over from the pulse buffer, trapezoid
     catch-up at termination (llsmrt.c:305-419); HM derived from layer 1 when absent."""
-    B, F = 2, 48
+    B, F = (2 if mode == "switching" else 1), 48            # one utterance is enough for the uniform modes
     pbp = np.zeros((B, F), np.int32)
     if mode == "switching":
         pbp[0, 10:22] = 1; pbp[0, 30:41] = 1; pbp[1, 5:40] = 1
