@@ -104,3 +104,9 @@ def test_rt_layer1_with_harmonic_model_present():
     pbp = np.zeros((B, F), np.int32); pbp[0, 12:20] = 1
     ref, got = _run_l1(B, F, pbp, remove_hm=0, block=30)
     _check(ref, got, tol=1e-5)
+
+
+@pytest.mark.parametrize("nch,nhar_e", [(2, 3), (1, 2)])
+def test_rt_other_channel_counts(nch, nhar_e):
+    ref, got = _run(1, 20, nch=nch, nhar_e=nhar_e)
+    _check(ref, got)
