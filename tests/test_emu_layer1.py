@@ -30,3 +30,24 @@ def test_tolayer1_and_back():
                             o0["nhar"].ctypes.data_as(C.c_void_p), o0["ampl"].ctypes.data_as(C.c_void_p),
                             o0["phse"].ctypes.data_as(C.c_void_p)) == 0
     S.check_layer0_from_l1(o0, ref0)
+
+
+def test_tolayer1_ragged_batch_with_an_empty_utterance():
+    """Utterances of 24, 0 and 9 frames: every utterance is converted as if it were alone (the Rd track is smoothed
+    along its own frames only)."""
+    nfu = np.asarray([24, 0, 9], np.int32)
+    fr, conf = S.synth_frames(3, 24, seed=23, nhar=100, maxnhar=100)
+    nfft = 2048
+    o = dict(rd=np.zeros((3, 24), np.float32), vtmagn=np.zeros((3, 24, nfft // 2 + 1), np.float32),
+             vsphse=np.zeros((3, 24, conf.maxnhar), np.float32), nvs=np.zeros((3, 24), np.int32))
+    fr2 = dict(fr); fr2["nfrm_utt"] = nfu
+    f = S.frames_struct(fr2)
+    s = _l1struct(o)
+    assert S.load_emu().emu_tolayer1(C.byref(conf), C.byref(f), nfft, C.byref(s)) == 0
+    for b, n in enumerate(nfu):
+        if n == 0:
+            continue
+        one = {k: (np.ascontiguousarray(v[b:b + 1, :n]) if v is not None else None) for k, v in fr.items()}
+        c1 = abi.make_conf(1, int(n), conf.maxnhar, conf.maxnhar_e, conf.npsd, conf.nchannel, conf.fs, conf.thop)
+        ref = S.ref_tolayer1(one, c1, nfft)
+        S.check_layer1({k: v[b:b + 1, :n] for k, v in o.items()}, ref, one["f0"] > 0)
