@@ -164,6 +164,19 @@ int llsm_b200_analyze_l0_host(llsm_b200_ctx* ctx, const llsm_b200_conf* conf,
   const llsm_b200_frames_out* frames, float* x_res);
 
 
+/* Analysis -> [chunk phase operations] -> synthesis in one call, HOST waveforms in and out; the chunk (every frame
+   array) stays in HBM. The chain the reference's end-to-end test runs and times (test/test-layer0-anasynth.c:40-46:
+   llsm_analyze then llsm_synthesize on the chunk; :62-66 with llsm_chunk_phasesync_rps + llsm_chunk_phasepropagate in
+   between) -- the "layer0 analysis+synthesis" metric of BASELINE.json end to end.
+     x [B][xstride], f0 [B][F] (read only; the refined track is returned in f0_refined when it is not NULL)
+     phase_ops   bit 0: llsm_chunk_phasesync_rps(chunk, 0), bit 1: llsm_chunk_phasepropagate(chunk, +1), in that order
+     sopt->white HOST pointer [B][nchannel][llsm_b200_template_length(ny)] or NULL (device generator)
+     out         HOST pointers, stride >= llsm_b200_output_length(); any of y / y_sin / y_noise may be NULL */
+int llsm_b200_anasynth_host(llsm_b200_ctx* ctx, const llsm_b200_conf* conf, const llsm_b200_aoptions* aopt,
+  const llsm_b200_soptions* sopt, const float* x, int nx, int xstride, const float* f0, float* f0_refined,
+  int phase_ops, const llsm_b200_output* out);
+
+
 /* ---- layer-1 members (llsm.h:105-108): RD, VTMAGN, VSPHSE per frame, flat ----
      rd      [B][F]            Rd glottal parameter (every frame, smoothed track)
      vtmagn  [B][F][nspec]     vocal-tract magnitude response, dB (voiced frames)

@@ -45,6 +45,8 @@ def lib():
     L.llsm_b200_analyze_l0.argtypes = [P, C.POINTER(abi.Conf), C.POINTER(abi.AOptions), P, C.c_int,
                                        C.c_int, C.POINTER(abi.FramesOut), P]
     L.llsm_b200_analyze_l0_host.argtypes = L.llsm_b200_analyze_l0.argtypes
+    L.llsm_b200_anasynth_host.argtypes = [P, C.POINTER(abi.Conf), C.POINTER(abi.AOptions), C.POINTER(abi.SOptions), P,
+                                          C.c_int, C.c_int, P, P, C.c_int, C.POINTER(abi.Output)]
     L.llsm_b200_tolayer1.argtypes = [P, C.POINTER(abi.Conf), C.POINTER(abi.Frames), C.c_int, C.POINTER(abi.Layer1)]
     L.llsm_b200_synthesize_l1.argtypes = [P, C.POINTER(abi.Conf), C.POINTER(abi.Frames), C.POINTER(abi.Layer1), P,
                                           C.POINTER(abi.SOptions), C.POINTER(abi.Output)]

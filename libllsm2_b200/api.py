@@ -198,6 +198,24 @@ def analyze_l0_host(ctx, conf, x, f0, options=None, want_residual=False):
     return out
 
 
+def anasynth_host(ctx, conf, x, f0, options=None, soptions=None, white=None, seed=0, phase_ops=0, out=None,
+                  f0_refined=None):
+    """llsm_analyze -> [phasesync_rps / phasepropagate] -> llsm_synthesize in one call (test/test-layer0-anasynth.c:40-66):
+    host (numpy / pinned torch CPU) waveforms in, host waveforms out, the chunk stays on the device.
+    out: dict with any of y / y_sin / y_noise ([B][>= ny] float32); default: y only."""
+    ny = output_length(conf.nfrm, conf.thop, conf.fs)
+    if out is None:
+        out = {"y": np.empty((conf.nutt, ny), np.float32)}
+    o = abi.Output()
+    o.y, o.y_sin, o.y_noise = _ptr(out.get("y")), _ptr(out.get("y_sin")), _ptr(out.get("y_noise"))
+    o.stride = next(v for v in out.values() if v is not None).shape[1]
+    a = _aoptions(options)
+    so = _soptions(soptions, white, seed)
+    check(lib().llsm_b200_anasynth_host(ctx._h, C.byref(conf), C.byref(a), C.byref(so), _ptr(x), int(x.shape[1]),
+                                        int(x.shape[1]), _ptr(f0), _ptr(f0_refined), int(phase_ops), C.byref(o)))
+    return out
+
+
 def tolayer1(ctx, conf, frames, nfft):
     """llsm_chunk_tolayer1 (layer1.c:129-149) on CUDA tensors: returns dict(rd, vtmagn, vsphse, nvs)."""
     import torch

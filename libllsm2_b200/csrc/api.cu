@@ -46,8 +46,11 @@ struct llsm_b200_ctx {
   DevBuf pin[2][12], pout[2][12];
   LaunchCounter lc;
   cudaEvent_t kt_ev[LLSM_KT_MARKS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  std::mutex mtx;
+  // recursive: the *_host entry points hold it across their staging + the device entry they call, and a user
+  // llsm_pbpeffect callback running under it may call back into llsm_* functions of the same context
+  std::recursive_mutex mtx;
 };
+typedef std::lock_guard<std::recursive_mutex> CtxLock;
 
 static PlanKey make_key(const llsm_b200_conf* c) {
   PlanKey k; memset(&k, 0, sizeof(k));
@@ -183,7 +186,7 @@ int llsm_b200_synthesize_l0(llsm_b200_ctx* ctx, const llsm_b200_conf* conf,
   if(! fr->f0 || ! fr->nhar || ! fr->ampl || ! fr->phse || ! fr->psd || ! fr->edc || ! fr->enhar ||
      ! fr->eampl || ! fr->ephse) return fail(LLSM_B200_EINVAL, "a required frame array is NULL");
   if(! out->y_sin || ! out->y_noise) return fail(LLSM_B200_EINVAL, "y_sin and y_noise are required");
-  std::lock_guard<std::mutex> lk(ctx->mtx);
+  CtxLock lk(ctx->mtx);
   cudaSetDevice(ctx->device);
   return synth_l0_impl(ctx, conf, fr, opt, out, 0);
 }
@@ -197,7 +200,7 @@ int llsm_b200_synthesize_l0_shard(llsm_b200_ctx* ctx, const llsm_b200_conf* conf
   if(! fr->f0 || ! fr->nhar || ! fr->ampl || ! fr->phse || ! fr->psd || ! fr->edc || ! fr->enhar ||
      ! fr->eampl || ! fr->ephse) return fail(LLSM_B200_EINVAL, "a required frame array is NULL");
   if(! out->y_sin || ! out->y_noise) return fail(LLSM_B200_EINVAL, "y_sin and y_noise are required");
-  std::lock_guard<std::mutex> lk(ctx->mtx);
+  CtxLock lk(ctx->mtx);
   cudaSetDevice(ctx->device);
   SynthPlanDev* pd = get_plan(ctx, conf);
   if(pd == nullptr) return fail(LLSM_B200_ENOMEM, "could not build the synthesis plan");
@@ -230,7 +233,7 @@ int llsm_b200_synthesize_harmonics(llsm_b200_ctx* ctx, const llsm_b200_conf* con
   if(! fr || ! fr->f0 || ! fr->nhar || ! fr->ampl || ! fr->phse || ! y_sin)
     return fail(LLSM_B200_EINVAL, "NULL argument");
   if(stride < nsamp) return fail(LLSM_B200_EINVAL, "stride < nsamp");
-  std::lock_guard<std::mutex> lk(ctx->mtx);
+  CtxLock lk(ctx->mtx);
   cudaSetDevice(ctx->device);
   SynthPlanDev* pd = get_plan(ctx, conf);
   if(pd == nullptr) return fail(LLSM_B200_ENOMEM, "could not build the synthesis plan");
@@ -276,7 +279,7 @@ int llsm_b200_synthesize_l0_host(llsm_b200_ctx* ctx, const llsm_b200_conf* conf,
   if(! fr || ! opt || ! out) return fail(LLSM_B200_EINVAL, "NULL argument");
   if(! fr->f0 || ! fr->nhar || ! fr->ampl || ! fr->phse || ! fr->psd || ! fr->edc || ! fr->enhar ||
      ! fr->eampl || ! fr->ephse) return fail(LLSM_B200_EINVAL, "a required frame array is NULL");
-  std::lock_guard<std::mutex> lk(ctx->mtx);
+  CtxLock lk(ctx->mtx);
   cudaSetDevice(ctx->device);
   rc = pipeline_ready(ctx); if(rc) return rc;
   const int B = conf->nutt, F = conf->nfrm;
@@ -350,7 +353,7 @@ int llsm_b200_synthesize_l0_host(llsm_b200_ctx* ctx, const llsm_b200_conf* conf,
 // the LAST step: harmonic bank, white-noise fill, template IIR, excitation, noise shaper + mix.
 int llsm_b200_set_kernel_timing(llsm_b200_ctx* ctx, int enable) {
   if(ctx == nullptr) return fail(LLSM_B200_ENODEVICE, "no context (no CUDA device?)");
-  std::lock_guard<std::mutex> lk(ctx->mtx);
+  CtxLock lk(ctx->mtx);
   cudaSetDevice(ctx->device);
   if(enable && ! ctx->kt_ev[0])
     for(int i = 0; i < LLSM_KT_MARKS; i ++)
@@ -361,7 +364,7 @@ int llsm_b200_set_kernel_timing(llsm_b200_ctx* ctx, int enable) {
 }
 int llsm_b200_kernel_times(llsm_b200_ctx* ctx, float* ms5) {
   if(ctx == nullptr || ms5 == nullptr) return fail(LLSM_B200_EINVAL, "NULL argument");
-  std::lock_guard<std::mutex> lk(ctx->mtx);
+  CtxLock lk(ctx->mtx);
   cudaSetDevice(ctx->device);
   if(! ctx->lc.ev || ctx->lc.mark != LLSM_KT_MARKS) return fail(LLSM_B200_EINVAL, "no timed synthesis step recorded");
   if(cudaEventSynchronize(ctx->kt_ev[LLSM_KT_MARKS - 1]) != cudaSuccess) return cuda_ok("kernel timing");

@@ -8,6 +8,7 @@
 #include "../../include/llsm.h"
 #include "../../include/llsm_b200.h"
 #include <stdlib.h>
+#include <pthread.h>
 #include <string.h>
 #include <stdio.h>
 #include <math.h>
@@ -639,11 +640,15 @@ void llsm_chunk_phasepropagate(llsm_chunk* dst, int sign) {
 
 /* ------------------------------------------------------------------ device context -------------- */
 static llsm_b200_ctx* g_ctx = NULL;
+static pthread_once_t g_ctx_once = PTHREAD_ONCE_INIT;
+static void shared_ctx_init(void) {
+  const char* e = getenv("LLSM_B200_DEVICE");
+  g_ctx = llsm_b200_create(e != NULL ? atoi(e) : 0);
+}
+/* one process-wide device context, created once however many threads make the first call; the context itself
+   serialises the calls that go through it (the reference's functions are reentrant: INTEGRATION.md section 4) */
 static llsm_b200_ctx* shared_ctx(void) {
-  if(g_ctx == NULL) {
-    const char* e = getenv("LLSM_B200_DEVICE");
-    g_ctx = llsm_b200_create(e != NULL ? atoi(e) : 0);
-  }
+  pthread_once(&g_ctx_once, shared_ctx_init);
   return g_ctx;
 }
 

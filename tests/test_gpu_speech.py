@@ -1,0 +1,153 @@
+"""The reference's own audio fixtures through the DROP-IN symbols (llsm.h / llsmrt.h) of libllsm2_b200.so and of the
+reference build, side by side:
+
+* BASELINE configs[0]: test/arctic_a0001.wav -> llsm_analyze -> llsm_synthesize -> phasesync_rps + phasepropagate ->
+  llsm_synthesize with the options of test/test-layer0-anasynth.c:29-37, peak picking (HMPP) and CZT;
+* test/are-you-ready.wav -> llsm_analyze -> llsm_chunk_tolayer1 -> growl llsm_pbpeffect -> llsm_rtsynth_buffer_*
+  (test/test-pbpeffects.c:62-133; BASELINE configs[2]'s effect).
+
+Primary bar: waveform RMS error < 1e-4 against the reference build on identical inputs and rand() state (the bar
+BASELINE.json states; parity is against reference + ciglet shim, "unpinned vs real ciglet": DESIGN.md section 2).
+Secondary: the reference's statistical acceptance (test/verify-utils.h) on the CUDA output.
+The fixtures are committed copies (tests/golden/speech_fixtures.npz): /root/reference is absent on the GPU box."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import compat_util as U
+import speech_util as SU
+import support as S
+
+pytestmark = pytest.mark.gpu
+libc = C.CDLL(None)
+
+
+@pytest.fixture(scope="module")
+def libs():
+    from libllsm2_b200._lib import lib
+    return U.bind(lib()), U.bind(S.load_ref())
+
+
+def _check_chunk(a, b, tag):
+    """a: CUDA library, b: reference build."""
+    assert np.array_equal(a["nhar"], b["nhar"]), tag
+    assert np.array_equal(a["enhar"], b["enhar"]), tag
+    assert np.abs(a["f0"] - b["f0"]).max() < 1e-3, (tag, np.abs(a["f0"] - b["f0"]).max())
+    scale = float(np.abs(b["ampl"]).max())
+    assert np.abs(a["ampl"] - b["ampl"]).max() < 2e-5 * scale, (tag, np.abs(a["ampl"] - b["ampl"]).max(), scale)
+    pe = np.abs(S.phase_err(a["phse"], b["phse"]) * b["ampl"]).max()
+    assert pe < 1e-4 * scale, (tag, pe, scale)
+    assert np.abs(a["psd"] - b["psd"]).max() < 0.05, (tag, np.abs(a["psd"] - b["psd"]).max())
+    assert np.abs(a["psdres"] - b["psdres"]).max() < 0.1, (tag, np.abs(a["psdres"] - b["psdres"]).max())
+    es = float(np.abs(b["edc"]).max())
+    assert np.abs(a["edc"] - b["edc"]).max() < 1e-4 * es, tag
+    assert np.abs(a["eampl"] - b["eampl"]).max() < 1e-4 * es, tag
+
+
+@pytest.mark.parametrize("method", ["pp", "czt"])
+def test_arctic_anasynth_dropin(libs, method):
+    fx = SU.fixtures()["arctic"]
+    res = [SU.anasynth(L, fx["x"], fx["fs"], fx["f0"], fx["nhop"], method) for L in libs]
+    a, b = res
+    assert np.abs(a["f0"] - b["f0"]).max() < 1e-3                   # the caller's f0 is refined in place
+    _check_chunk(a["chunk"], b["chunk"], "analysis")
+    _check_chunk(a["chunk2"], b["chunk2"], "after phasesync_rps + phasepropagate")
+    for key in ("out1", "out2"):
+        for ya, yb, name in zip(a[key], b[key], ("y", "y_sin", "y_noise")):
+            assert ya.shape == yb.shape == (147840,)
+            assert S.rms(yb) > 1e-3
+            assert S.rms(ya - yb) < 1e-4, (key, name, S.rms(ya - yb))
+        # the reference's own acceptance bars on the CUDA output (test/test-layer0-anasynth.c:58-59,73-74)
+        y = a[key][0]
+        for k in SU.verify_data_distribution(fx["x"], y):
+            assert k < 0.05, (key, k)
+        cc, k0, k1 = SU.verify_spectral_distribution(fx["x"], y)
+        assert cc > 0.95 and k0 < 0.05 and k1 < 0.05, (key, cc, k0, k1)
+
+
+GFM = C.CFUNCTYPE(None, C.POINTER(C.c_float * 5), C.POINTER(C.c_float), C.c_void_p, C.POINTER(U.Container))
+GROWLSTRENGTH = 15                                                  # test/test-pbpeffects.c:63
+
+
+def _growl_run(L, fx, capacity=4096):
+    """test/test-pbpeffects.c:87-166 on library L; randn() of the callback replaced by a seeded generator (same
+    draws on both sides). Returns (latency, samples, number of callback invocations)."""
+    x, fs, nhop = np.ascontiguousarray(fx["x"]), fx["fs"], fx["nhop"]
+    f0 = fx["f0"].copy()
+    nfrm = len(f0)
+    rng = np.random.default_rng(1234)
+    state = {"period_count": 0, "osc": 0.0, "calls": 0}
+
+    def fgrowl(g, delta_t, info, frame):
+        p = L.llsm_container_get(frame, GROWLSTRENGTH)
+        strength = C.cast(p, U.fp)[0] if p else 1.0
+        state["calls"] += 1
+        state["period_count"] += 1
+        lfo = np.sin(state["period_count"] * 2 * np.pi / 50)
+        state["osc"] += 2 * np.pi / (6 + lfo)
+        osc = np.sin(state["osc"])
+        gm = g.contents
+        delta_t[0] = gm[3] * 0.01 * rng.normal() * strength          # T0
+        gm[0] = gm[0] * (1.0 - osc * 0.5 * strength)                 # Fa
+        gm[1] = gm[1] * (1.0 + osc * 0.3 * strength)                 # Rk
+        gm[4] = gm[4] * (1.0 - osc * 0.5 * strength)                 # Ee
+    cb = GFM(fgrowl)
+
+    ao = L.llsm_create_aoptions()
+    thop = np.float32(nhop) / np.float32(fs)
+    ao.contents.thop = thop; ao.contents.npsd = 128; ao.contents.rel_winsize = 4.0
+    ao.contents.maxnhar = 400; ao.contents.maxnhar_e = 5
+    so = L.llsm_create_soptions(C.c_float(fs))
+    ck = L.llsm_analyze(ao, x.ctypes.data_as(U.fp), len(x), C.c_float(fs), f0.ctypes.data_as(U.fp), nfrm, None)
+    assert ck, "llsm_analyze returned NULL"
+    L.llsm_chunk_tolayer1(ck, 2048)
+    L.llsm_chunk_phasepropagate(ck, -1)
+    so.contents.use_l1 = 1
+    n_begin, n_end, n_fade = int(2.0 / thop), int(4.4 / thop), 20
+    L.llsm_create_pbpeffect.restype = C.c_void_p
+    for i in range(nfrm):
+        f = ck.contents.frames[i]
+        L.llsm_container_attach_(f, U.HMI, None, None, None)
+        if n_begin < i < n_end:
+            strength = 1.0
+            if i < n_begin + n_fade:
+                strength = float(np.float32(i - n_begin) / np.float32(n_fade))
+            if i > n_end - n_fade:
+                strength = float(np.float32(n_end - i) / np.float32(n_fade))
+            L.llsm_container_attach_(f, 9, C.cast(L.llsm_create_int(1), C.c_void_p), U.fn_ptr(L, "llsm_delete_int"),
+                                     U.fn_ptr(L, "llsm_copy_int"))
+            e = L.llsm_create_pbpeffect(cb, None)
+            L.llsm_container_attach_(f, 8, C.c_void_p(e), U.fn_ptr(L, "llsm_delete_pbpeffect"),
+                                     U.fn_ptr(L, "llsm_copy_pbpeffect"))
+            L.llsm_container_attach_(f, GROWLSTRENGTH, C.cast(L.llsm_create_fp(C.c_float(strength)), C.c_void_p),
+                                     U.fn_ptr(L, "llsm_delete_fp"), U.fn_ptr(L, "llsm_copy_fp"))
+    L.llsm_chunk_phasepropagate(ck, 1)
+    L.llsm_create_rtsynth_buffer.restype = C.c_void_p
+    L.llsm_create_rtsynth_buffer.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.llsm_rtsynth_buffer_feed.argtypes = [C.c_void_p, C.c_void_p]
+    L.llsm_rtsynth_buffer_fetch.argtypes = [C.c_void_p, C.c_void_p]
+    L.llsm_rtsynth_buffer_getlatency.argtypes = [C.c_void_p]
+    L.llsm_delete_rtsynth_buffer.argtypes = [C.c_void_p]
+    libc.srand(41)
+    rt = L.llsm_create_rtsynth_buffer(so, ck.contents.conf, capacity)
+    assert rt, "llsm_create_rtsynth_buffer returned NULL"
+    lat = L.llsm_rtsynth_buffer_getlatency(rt)
+    ys = []
+    tmp = C.c_float()
+    for i in range(nfrm):
+        L.llsm_rtsynth_buffer_feed(rt, ck.contents.frames[i])
+        while L.llsm_rtsynth_buffer_fetch(rt, C.byref(tmp)):
+            ys.append(tmp.value)
+    L.llsm_delete_rtsynth_buffer(rt)
+    L.llsm_delete_chunk(ck); L.llsm_delete_aoptions(ao); L.llsm_delete_soptions(so)
+    return lat, np.array(ys, np.float32), state["calls"]
+
+
+def test_are_you_ready_growl_rtsynth_dropin(libs):
+    fx = SU.fixtures()["ready"]
+    (la, ya, ca), (lb, yb, cb) = [_growl_run(L, fx) for L in libs]
+    assert la == lb and ca == cb and cb > 100, (la, lb, ca, cb)     # one callback per glottal pulse, in order
+    assert ya.shape == yb.shape and S.rms(yb) > 1e-3
+    assert np.isfinite(ya).all()
+    assert S.rms(ya - yb) < 1e-4, S.rms(ya - yb)
