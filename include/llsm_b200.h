@@ -125,11 +125,12 @@ int            llsm_b200_synchronize(llsm_b200_ctx* ctx);
 /* number of kernels this library has launched on ctx since creation (bench.py gpu_launches) */
 long long      llsm_b200_launch_count(const llsm_b200_ctx* ctx);
 
-/* Per-kernel timing of the layer-0 synthesis step: when enabled, llsm_b200_synthesize_l0 records a CUDA event after
-   each of its five kernels; llsm_b200_kernel_times waits for the last step and returns their durations in ms
-   (harmonic bank, white-noise fill, template IIR, excitation, noise shaper + mix). */
+/* Per-kernel timing: while enabled, the analysis and synthesis pipelines record a named CUDA event after each of their
+   kernels (every call with enable != 0 restarts the list); llsm_b200_kernel_timing_read waits for the last one and
+   returns how many kernel intervals were recorded (<= max; -1 on error), their names (static strings) and durations
+   in ms, in launch order. */
 int llsm_b200_set_kernel_timing(llsm_b200_ctx* ctx, int enable);
-int llsm_b200_kernel_times(llsm_b200_ctx* ctx, float* ms5);
+int llsm_b200_kernel_timing_read(llsm_b200_ctx* ctx, int max, const char** names, float* ms);
 
 /* ---- size helpers (host only, exact replicas of the reference's float expressions) ---- */
 int llsm_b200_output_length(int nfrm, float thop, float fs);    /* layer0.c:643 */

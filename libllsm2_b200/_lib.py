@@ -81,7 +81,7 @@ def lib():
     L.llsm_b200_frames_pack.argtypes = [C.POINTER(abi.Conf), C.POINTER(abi.Frames), P, C.c_size_t]
     L.llsm_b200_frames_unpack.argtypes = [P, C.c_size_t, C.POINTER(abi.Conf), C.POINTER(abi.Frames)]
     L.llsm_b200_set_kernel_timing.argtypes = [P, C.c_int]
-    L.llsm_b200_kernel_times.argtypes = [P, C.POINTER(C.c_float)]
+    L.llsm_b200_kernel_timing_read.argtypes = [P, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float)]
     _lib = L
     return L
 

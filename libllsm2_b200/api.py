@@ -46,10 +46,13 @@ class Context:
         check(lib().llsm_b200_set_kernel_timing(self._h, 1 if enable else 0))
 
     def kernel_times(self):
-        """ms of the five kernels of the last synthesize_l0 step: bank, white fill, IIR, excitation, shaper."""
-        ms = (C.c_float * 5)()
-        check(lib().llsm_b200_kernel_times(self._h, ms))
-        return dict(zip(("hm_bank", "white_fill", "iir_filtfilt", "noise_excitation", "noise_shape"), [float(v) for v in ms]))
+        """[(name, ms), ...] of the kernels launched since set_kernel_timing(True), in launch order."""
+        names = (C.c_char_p * 48)()
+        ms = (C.c_float * 48)()
+        n = lib().llsm_b200_kernel_timing_read(self._h, 48, names, ms)
+        if n < 0:
+            raise LlsmB200Error(lib().llsm_b200_last_error().decode())
+        return [(names[i].decode(), float(ms[i])) for i in range(n)]
 
     def close(self):
         if getattr(self, "_h", None):
@@ -157,15 +160,17 @@ def analysis_shapes(conf):
             "eampl": ((B, F, n, conf.maxnhar_e), "f"), "ephse": ((B, F, n, conf.maxnhar_e), "f")}
 
 
-def analyze_l0(ctx, conf, x, f0, options=None, want_residual=False):
+def analyze_l0(ctx, conf, x, f0, options=None, want_residual=False, out=None):
     """llsm_analyze (layer0.c:478-511) for a batch of waveforms held in CUDA tensors.
     x: [B][nx] float32 CUDA tensor, f0: [B][F] (copied; the refined track is returned, as the
-    reference overwrites the caller's f0). Returns dict of frame tensors (+ x_res)."""
+    reference overwrites the caller's f0). Returns dict of frame tensors (+ x_res). out: reuse the arrays of an
+    earlier call (every row of every array is rewritten)."""
     import torch
     dev = x.device
-    out = {}
-    for k, (shape, kind) in analysis_shapes(conf).items():
-        out[k] = torch.zeros(shape, dtype=torch.float32 if kind == "f" else torch.int32, device=dev)
+    if out is None:
+        out = {}
+        for k, (shape, kind) in analysis_shapes(conf).items():
+            out[k] = torch.zeros(shape, dtype=torch.float32 if kind == "f" else torch.int32, device=dev)
     out["f0"].copy_(f0)
     fo = abi.FramesOut()
     for k in OUT_KEYS:

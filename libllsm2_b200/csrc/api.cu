@@ -45,7 +45,7 @@ struct llsm_b200_ctx {
   cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
   DevBuf pin[2][12], pout[2][12];
   LaunchCounter lc;
-  cudaEvent_t kt_ev[LLSM_KT_MARKS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t kt_ev[LLSM_KT_MAX] = {};
   // recursive: the *_host entry points hold it across their staging + the device entry they call, and a user
   // llsm_pbpeffect callback running under it may call back into llsm_* functions of the same context
   std::recursive_mutex mtx;
@@ -131,6 +131,9 @@ void llsm_b200_destroy(llsm_b200_ctx* ctx) {
     if(ctx->ev_comp[k]) cudaEventDestroy(ctx->ev_comp[k]);
     if(ctx->ev_out[k]) cudaEventDestroy(ctx->ev_out[k]);
   }
+  for(auto& e : ctx->kt_ev) if(e) cudaEventDestroy(e);
+  ctx->phase_theta.release();
+  if(ctx->coderplan) ctx->coderplan->release();
   if(ctx->s_in) cudaStreamDestroy(ctx->s_in);
   if(ctx->s_out) cudaStreamDestroy(ctx->s_out);
   if(ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -348,29 +351,33 @@ int llsm_b200_synthesize_l0_host(llsm_b200_ctx* ctx, const llsm_b200_conf* conf,
   return cuda_ok("synthesize_l0_host");
 }
 
-// Per-kernel timing of the layer-0 synthesis step (bench.py): when enabled, llsm_b200_synthesize_l0 records an
-// event after each of its five kernels; llsm_b200_kernel_times synchronises and returns the five durations (ms) of
-// the LAST step: harmonic bank, white-noise fill, template IIR, excitation, noise shaper + mix.
+// Per-kernel timing (bench.py): while enabled, the analysis and synthesis pipelines record a named CUDA event after
+// each of their kernels; every call with enable != 0 restarts the list. llsm_b200_kernel_timing_read waits for the last
+// event and returns the duration (ms) and name of every kernel interval recorded since.
 int llsm_b200_set_kernel_timing(llsm_b200_ctx* ctx, int enable) {
   if(ctx == nullptr) return fail(LLSM_B200_ENODEVICE, "no context (no CUDA device?)");
   CtxLock lk(ctx->mtx);
   cudaSetDevice(ctx->device);
   if(enable && ! ctx->kt_ev[0])
-    for(int i = 0; i < LLSM_KT_MARKS; i ++)
+    for(int i = 0; i < LLSM_KT_MAX; i ++)
       if(cudaEventCreate(&ctx->kt_ev[i]) != cudaSuccess) return cuda_ok("kernel timing events");
   ctx->lc.ev = enable ? ctx->kt_ev : nullptr;
   ctx->lc.mark = 0;
   return 0;
 }
-int llsm_b200_kernel_times(llsm_b200_ctx* ctx, float* ms5) {
-  if(ctx == nullptr || ms5 == nullptr) return fail(LLSM_B200_EINVAL, "NULL argument");
+int llsm_b200_kernel_timing_read(llsm_b200_ctx* ctx, int max, const char** names, float* ms) {
+  if(ctx == nullptr || names == nullptr || ms == nullptr) { fail(LLSM_B200_EINVAL, "NULL argument"); return -1; }
   CtxLock lk(ctx->mtx);
   cudaSetDevice(ctx->device);
-  if(! ctx->lc.ev || ctx->lc.mark != LLSM_KT_MARKS) return fail(LLSM_B200_EINVAL, "no timed synthesis step recorded");
-  if(cudaEventSynchronize(ctx->kt_ev[LLSM_KT_MARKS - 1]) != cudaSuccess) return cuda_ok("kernel timing");
-  for(int i = 0; i + 1 < LLSM_KT_MARKS; i ++)
-    if(cudaEventElapsedTime(&ms5[i], ctx->kt_ev[i], ctx->kt_ev[i + 1]) != cudaSuccess) return cuda_ok("kernel timing");
-  return 0;
+  if(! ctx->lc.ev || ctx->lc.mark < 2) { fail(LLSM_B200_EINVAL, "no timed step recorded"); return -1; }
+  if(cudaEventSynchronize(ctx->kt_ev[ctx->lc.mark - 1]) != cudaSuccess) { cuda_ok("kernel timing"); return -1; }
+  int n = 0;
+  for(int i = 1; i < ctx->lc.mark && n < max; i ++) {
+    if(strcmp(ctx->lc.names[i], "start") == 0) continue;
+    if(cudaEventElapsedTime(&ms[n], ctx->kt_ev[i - 1], ctx->kt_ev[i]) != cudaSuccess) { cuda_ok("kernel timing"); return -1; }
+    names[n ++] = ctx->lc.names[i];
+  }
+  return n;
 }
 
 #include "api_analysis.inc"

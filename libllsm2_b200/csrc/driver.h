@@ -98,21 +98,23 @@ struct SynthScratch {
   DevBuf colored, y_exc, ny_utt;
 };
 
-// launch counter of a context; when `ev` is set (llsm_b200_set_kernel_timing) the synthesis step also records an
+// launch counter of a context; when `ev` is set (llsm_b200_set_kernel_timing) every pipeline also records a named
 // event after each of its kernels so that their times can be read back live (bench.py's per-kernel rooflines)
+#define LLSM_KT_MAX 48
 struct LaunchCounter {
   long long n = 0;
 #ifndef LLSM_EMU
-  cudaEvent_t* ev = nullptr;      // [LLSM_KT_MARKS] or NULL
+  cudaEvent_t* ev = nullptr;      // [LLSM_KT_MAX] or NULL
+  const char* names[LLSM_KT_MAX];
   int mark = 0;
 #endif
 };
-#define LLSM_KT_MARKS 6           // start, bank, white fill, template IIR, excitation, shaper + mix
-static inline void lc_mark(LaunchCounter* lc, cudaStream_t st) {
+// name == "start": the interval that ends at this mark is not a kernel of ours (it is skipped when the times are read)
+static inline void lc_mark(LaunchCounter* lc, cudaStream_t st, const char* name) {
 #ifndef LLSM_EMU
-  if(lc && lc->ev && lc->mark < LLSM_KT_MARKS) cudaEventRecord(lc->ev[lc->mark ++], st);
+  if(lc && lc->ev && lc->mark < LLSM_KT_MAX) { lc->names[lc->mark] = name; cudaEventRecord(lc->ev[lc->mark ++], st); }
 #else
-  (void)lc; (void)st;
+  (void)lc; (void)st; (void)name;
 #endif
 }
 
@@ -154,14 +156,11 @@ static inline int run_synth_l0(const SynthPlanDev& pd, SynthScratch& sc, const l
   if(out.stride < h.ny) return LLSM_B200_EINVAL;
 
   // 1. harmonic component
-#ifndef LLSM_EMU
-  if(lc) lc->mark = 0;
-#endif
-  lc_mark(lc, st);
+  lc_mark(lc, st, "start");
   int rc = run_harmonics(pd, conf, fr, &opt, ny_utt_dev, out.y_sin, h.ny, out.stride, out.stride,
     st, lc, frame_lo, frame_hi);
   if(rc != 0) return rc;
-  lc_mark(lc, st);
+  lc_mark(lc, st, "hm_bank");
   return run_noise_part(pd, sc, conf, fr, opt, out, ny_utt_dev, st, lc, frame_lo, frame_hi, utt_base);
 }
 
@@ -182,7 +181,7 @@ static inline int run_noise_part(const SynthPlanDev& pd, SynthScratch& sc, const
     W.seq_base = utt_base * nch;
     LLSM_LAUNCH(white_fill_kernel, dim3((h.nt / 4 + 256) / 256, B * nch), dim3(256), 0, st, W);
     if(lc) lc->n += 1;
-    lc_mark(lc, st);
+    lc_mark(lc, st, "white_fill");
     IirParams I; memset(&I, 0, sizeof(I));
     I.nchannel = nch; I.n = h.nt; I.L = pd.iir_L; I.y = sc.colored.as<float>(); I.ystride = tstride; I.vec_ok = 1;
     I.coef = pd.iir_coef; I.mpow = pd.iir_mpow;
@@ -192,7 +191,7 @@ static inline int run_noise_part(const SynthPlanDev& pd, SynthScratch& sc, const
     }
     LLSM_LAUNCH(iir_filtfilt_kernel, dim3(B * nch), dim3(IIR_NT), 0, st, I);
     if(lc) lc->n += 1;
-    lc_mark(lc, st);
+    lc_mark(lc, st, "iir_filtfilt");
   }
 
   // 3. excitation
@@ -214,7 +213,7 @@ static inline int run_noise_part(const SynthPlanDev& pd, SynthScratch& sc, const
   E.y_exc = sc.y_exc.as<float>();
   if(launch_noise_excitation(E, B, st) != 0) return LLSM_B200_ERANGE;
   if(lc) lc->n += 1;
-  lc_mark(lc, st);
+  lc_mark(lc, st, "noise_excitation");
 
   // 4. shaping + mix
   ShapeParams S;
@@ -233,6 +232,6 @@ static inline int run_noise_part(const SynthPlanDev& pd, SynthScratch& sc, const
   if(h.nfft_ns > 8192) return LLSM_B200_ERANGE;
   if(launch_noise_shape(S, B, st) != 0) return LLSM_B200_ERANGE;
   if(lc) lc->n += 1;
-  lc_mark(lc, st);
+  lc_mark(lc, st, "noise_shape");
   return 0;
 }

@@ -142,6 +142,7 @@ static inline int run_analyze_l0(const SynthPlanDev& sp, AnaPlanDev& ap, AnaScra
   float* x_res = x_res_out ? x_res_out : sc.x_res.as<float>();
   const int rstride = x_res_out ? xstride : nx;
 
+  lc_mark(lc, st, "start");
   // 1. F0 refinement (dsputils.c:72-94)
   if(opt.f0_refine) {
     RefineParams R; memset(&R, 0, sizeof(R));
@@ -149,6 +150,7 @@ static inline int run_analyze_l0(const SynthPlanDev& sp, AnaPlanDev& ap, AnaScra
     R.center = sp.hm_base; R.fs = conf.fs; R.f0 = fr.f0;
     LLSM_LAUNCH(refine_f0_kernel, dim3(F, B), dim3(96), 0, st, R);
     if(lc) lc->n ++;
+    lc_mark(lc, st, "refine_f0");
   }
 
   // 2. harmonic analysis of x (dsputils.c:175-228)
@@ -186,6 +188,7 @@ static inline int run_analyze_l0(const SynthPlanDev& sp, AnaPlanDev& ap, AnaScra
     if(lc) lc->n ++;
   }
   { int rc = harmonic_pass(x, 1, xstride, conf.maxnhar, fr.nhar, fr.ampl, fr.phse, nullptr); if(rc) return rc; }
+  lc_mark(lc, st, opt.hm_method == 1 ? "harmonic_czt" : "harmonic_pp");
 
   // 3. residual: x - resynthesised sinusoids (layer0.c:498-501; options == NULL, ny = nx)
   {
@@ -196,6 +199,7 @@ static inline int run_analyze_l0(const SynthPlanDev& sp, AnaPlanDev& ap, AnaScra
     LLSM_LAUNCH(residual_kernel, dim3((nx + 255) / 256, B), dim3(256), 0, st,
       x, (const float*)sc.x_sin.as<float>(), x_res, nx, xstride, nx, rstride);
     if(lc) lc->n ++;
+    lc_mark(lc, st, "residual_bank");
   }
 
   // 4. noise PSD (layer0.c:318-415)
@@ -214,6 +218,7 @@ static inline int run_analyze_l0(const SynthPlanDev& sp, AnaPlanDev& ap, AnaScra
 #endif
     LLSM_LAUNCH(noise_spec_kernel, dim3((F + 1) / 2, B), dim3(NS_THREADS), smem, st, N);
     if(lc) lc->n ++;
+    lc_mark(lc, st, "noise_spec");
 
     KalmanParams K; memset(&K, 0, sizeof(K));
     K.nfrm = F; K.nspec = h.nspec; K.nfrm_utt = nfrm_utt;
@@ -221,6 +226,7 @@ static inline int run_analyze_l0(const SynthPlanDev& sp, AnaPlanDev& ap, AnaScra
     K.filt = sc.filt.as<float>(); K.pvar = sc.pvar.as<float>();
     LLSM_LAUNCH(noise_kalman_kernel, dim3((h.nspec + 127) / 128, B), dim3(128), 0, st, K);
     if(lc) lc->n ++;
+    lc_mark(lc, st, "noise_kalman");
 
     PsdOutParams O; memset(&O, 0, sizeof(O));
     O.nfrm = F; O.nspec = h.nspec; O.npsd = conf.npsd; O.nfrm_utt = nfrm_utt;
@@ -228,6 +234,7 @@ static inline int run_analyze_l0(const SynthPlanDev& sp, AnaPlanDev& ap, AnaScra
     O.fs = conf.fs; O.psd = fr.psd; O.psdres = fr.psdres;
     LLSM_LAUNCH(noise_psd_out_kernel, dim3(F, B), dim3(128), 0, st, O);
     if(lc) lc->n ++;
+    lc_mark(lc, st, "noise_psd_out");
   }
 
   // 5. noise envelope per channel (layer0.c:417-469)
@@ -241,6 +248,7 @@ static inline int run_analyze_l0(const SynthPlanDev& sp, AnaPlanDev& ap, AnaScra
     I.square = 1;
     LLSM_LAUNCH(iir_filtfilt_kernel, dim3(B * nch), dim3(IIR_NT), 0, st, I);
     if(lc) lc->n ++;
+    lc_mark(lc, st, "subband_iir");
 
     // CZT pass: the short-time means ride along in the same kernel; peak picking keeps the separate kernel
     const bool dc_fused = conf.maxnhar_e > 0 && opt.hm_method == 1;
@@ -248,6 +256,7 @@ static inline int run_analyze_l0(const SynthPlanDev& sp, AnaPlanDev& ap, AnaScra
       int rc = harmonic_pass(sc.ce.as<float>(), nch, cst, conf.maxnhar_e, fr.enhar, fr.eampl, fr.ephse,
         dc_fused ? fr.edc : nullptr);
       if(rc) return rc;
+      lc_mark(lc, st, "envelope_harmonics");
     }
     if(dc_fused) return 0;
 
@@ -256,6 +265,7 @@ static inline int run_analyze_l0(const SynthPlanDev& sp, AnaPlanDev& ap, AnaScra
     D.f0 = fr.f0; D.center = sp.hm_base; D.fs = conf.fs; D.thop = conf.thop; D.edc = fr.edc;
     LLSM_LAUNCH(frame_dc_kernel, dim3(F, B * nch), dim3(128), 0, st, D);
     if(lc) lc->n ++;
+    lc_mark(lc, st, "frame_dc");
   }
   return 0;
 }

@@ -379,6 +379,49 @@ double ref_time_analyze(int nrep, const float* x, int nx, float fs, const float*
   return tot;
 }
 
+/* timing helper for bench.py: the chain of test/test-layer0-anasynth.c:40-46 -- llsm_analyze, then llsm_synthesize on the
+   chunk it returned -- nrep times on one utterance. t[0] += seconds inside llsm_analyze, t[1] += seconds inside
+   llsm_synthesize. Optionally returns the last output (y, ny_cap samples). Returns ny. */
+int ref_time_anasynth(int nrep, const float* x, int nx, float fs, const float* f0, int nfrm, float thop,
+  int maxnhar, int maxnhar_e, int npsd, int nchannel, const float* chanfreq, int hm_method, double* t,
+  float* y, int ny_cap) {
+  struct timespec t0, t1;
+  int ny = 0;
+  llsm_aoptions* opt = llsm_create_aoptions();
+  opt -> thop = thop; opt -> maxnhar = maxnhar; opt -> maxnhar_e = maxnhar_e; opt -> npsd = npsd;
+  opt -> nchannel = nchannel;
+  free(opt -> chanfreq);
+  opt -> chanfreq = calloc(nchannel > 1 ? nchannel - 1 : 1, sizeof(FP_TYPE));
+  for(int c = 0; c < nchannel - 1; c ++) opt -> chanfreq[c] = chanfreq[c];
+  opt -> hm_method = hm_method;
+  llsm_soptions* sopt = llsm_create_soptions(fs);
+  FP_TYPE* xc = malloc(nx * sizeof(FP_TYPE));
+  FP_TYPE* fc = malloc(nfrm * sizeof(FP_TYPE));
+  for(int r = 0; r < nrep; r ++) {
+    memcpy(xc, x, nx * sizeof(FP_TYPE));
+    memcpy(fc, f0, nfrm * sizeof(FP_TYPE));
+    clock_gettime(CLOCK_MONOTONIC, & t0);
+    llsm_chunk* chunk = llsm_analyze(opt, xc, nx, fs, fc, nfrm, NULL);
+    clock_gettime(CLOCK_MONOTONIC, & t1);
+    t[0] += (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+    if(chunk == NULL) continue;
+    clock_gettime(CLOCK_MONOTONIC, & t0);
+    llsm_output* out = llsm_synthesize(sopt, chunk);
+    clock_gettime(CLOCK_MONOTONIC, & t1);
+    t[1] += (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+    if(out != NULL) {
+      ny = out -> ny;
+      if(y != NULL) for(int i = 0; i < ny && i < ny_cap; i ++) y[i] = out -> y[i];
+      llsm_delete_output(out);
+    }
+    llsm_delete_chunk(chunk);
+  }
+  free(xc); free(fc);
+  llsm_delete_aoptions(opt);
+  llsm_delete_soptions(sopt);
+  return ny;
+}
+
 /* chunk phase utilities (layer0.c:687-706): op 0 = llsm_chunk_phasepropagate(chunk, arg), op 1 =
    llsm_chunk_phasesync_rps(chunk, arg). phse / ephse (and vsphse when given) are rewritten in place. */
 int ref_phase_op_soa(int nfrm, float fs, float thop, int maxnhar, int maxnhar_e, int nchannel,

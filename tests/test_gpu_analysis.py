@@ -93,3 +93,55 @@ def test_analysis_synthesis_roundtrip(ctx):
     d["nfrm_utt"] = None
     xs = L.synthesize_harmonics(ctx, conf, d, nx, with_options=False).cpu().numpy()
     assert S.rms((y - xs) - o["x_res"]) < 1e-6
+
+
+def test_analysis_c2_128_harmonics(ctx):
+    """BASELINE configs[1] harmonic count: 128 harmonics stay below Nyquist for f0 <= 170 Hz."""
+    fr, conf, y, ref, o = _case(ctx, 2, 120, seed=31, nhar=128, maxnhar=128, f0_lo=90, f0_hi=170)
+    assert ref["nhar"].max() == 128
+
+
+@pytest.mark.parametrize("phase_ops", [0, 3])
+def test_anasynth_host_chain(ctx, phase_ops):
+    """llsm_b200_anasynth_host (wave in -> analyse -> [phasesync_rps, phasepropagate] -> synthesise -> wave out, the
+    chunk never leaves the device) against the same chain on the reference build (test/test-layer0-anasynth.c:40-66),
+    identical white-noise templates; and against the separate host entries (bit-identical)."""
+    import ctypes as C
+    import libllsm2_b200 as L
+    fr, conf = S.synth_frames(3, 70, seed=33, nhar=100, maxnhar=100)
+    x, _, _ = S.ref_synthesize(fr, conf, seed=7)
+    x = np.ascontiguousarray(x)
+    white = S.ref_white_noise(conf, seed=21)
+    ny = L.output_length(conf.nfrm, conf.thop, conf.fs)
+    out = {k: np.zeros((conf.nutt, ny), np.float32) for k in ("y", "y_sin", "y_noise")}
+    f0r = np.zeros_like(fr["f0"])
+    L.anasynth_host(ctx, conf, x, fr["f0"], white=white, phase_ops=phase_ops, out=out, f0_refined=f0r)
+    # reference: analyse, phase operations, synthesise
+    ref = S.ref_analyze(x, fr["f0"], conf)
+    assert np.abs(f0r - ref["f0"]).max() < 1e-3
+    if phase_ops:
+        r1 = S.ref_phase_op(ref, conf, 1, 0)
+        ref["phse"], ref["ephse"] = r1["phse"], r1["ephse"]
+        r2 = S.ref_phase_op(ref, conf, 0, 1)
+        ref["phse"], ref["ephse"] = r2["phse"], r2["ephse"]
+    ref["nfrm_utt"] = None
+    y, ys, yn = S.ref_synthesize(ref, conf, seed=21)
+    for got, want, name in ((out["y"], y, "y"), (out["y_sin"], ys, "y_sin"), (out["y_noise"], yn, "y_noise")):
+        assert S.rms(want) > 1e-4
+        assert S.rms(got - want) < 1e-4, (name, S.rms(got - want))
+    # the same chain through the two separate host entries
+    a = L.analyze_l0_host(ctx, conf, x, fr["f0"])
+    if phase_ops:
+        import torch
+        d = {k: torch.from_numpy(v).cuda() for k, v in a.items()}
+        L.chunk_phasesync_rps(ctx, conf, d, layer1_based=0)
+        L.chunk_phasepropagate(ctx, conf, d, sign=1)
+        torch.cuda.synchronize()
+        a = {k: v.cpu().numpy() for k, v in d.items()}
+    a["nfrm_utt"] = None
+    b = L.synthesize_l0_host(ctx, conf, a, white=white)
+    for k in ("y", "y_sin", "y_noise"):
+        assert np.array_equal(b[k], out[k]), k
+    # y only, slicing invariance
+    y_only = L.anasynth_host(ctx, conf, x, fr["f0"], white=white, phase_ops=phase_ops)
+    assert np.array_equal(y_only["y"], out["y"])
