@@ -149,6 +149,105 @@ __device__ float2* block_fft(float2* a, float2* b, int lg, const float2* __restr
 #undef FIX
 }
 
+// ---- block-wide Stockham FFT, radix 8 (register butterflies) ---------------------------------------
+// Same contract as block_fft (n = 2^lg points in `a`, ping-pong buffer `b`, full-circle table tw[m] =
+// exp(-2 pi i m / ntw), returns the buffer holding the result, every pass ends with __syncthreads()), but a thread
+// carries a whole radix-8 butterfly in registers: lg / 3 passes (+ one radix-4 or radix-2 pass) instead of lg / 2,
+// i.e. 4 shared-memory round trips for 2048 points instead of 6, and a third fewer twiddle products.
+// Buffers are indexed through fpad(): one float2 of padding after every 16 makes the stride-8 scatter of the
+// first pass conflict-free (16 lanes -> 16 distinct bank pairs); a buffer holds fpad(n) = n + n / 16 float2.
+__device__ __forceinline__ int fpad(int j) { return j + (j >> 4); }
+
+template <bool INV>
+__device__ __forceinline__ float2 mul_w8(float2 v, int m) {      // v * W8^m, W8 = exp(-+ 2 pi i / 8), m = 1, 2, 3
+  const float h = 0.70710678118654752f;
+  if(m == 2) return INV ? make_float2(-v.y, v.x) : make_float2(v.y, -v.x);
+  if(m == 1) return INV ? make_float2((v.x - v.y) * h, (v.x + v.y) * h) : make_float2((v.x + v.y) * h, (v.y - v.x) * h);
+  return INV ? make_float2(-(v.x + v.y) * h, (v.x - v.y) * h) : make_float2((v.y - v.x) * h, -(v.x + v.y) * h);
+}
+
+// 8-point DFT in registers: u[j] <- sum_q u[q] W8^{jq} (decimation in frequency, outputs written to natural order)
+template <bool INV>
+__device__ __forceinline__ void dft8_regs(float2 (&u)[8]) {
+  float2 a[8];
+#pragma unroll
+  for(int q = 0; q < 4; q ++) {
+    a[q] = make_float2(u[q].x + u[q + 4].x, u[q].y + u[q + 4].y);
+    a[q + 4] = make_float2(u[q].x - u[q + 4].x, u[q].y - u[q + 4].y);
+  }
+  a[5] = mul_w8<INV>(a[5], 1); a[6] = mul_w8<INV>(a[6], 2); a[7] = mul_w8<INV>(a[7], 3);
+#pragma unroll
+  for(int h = 0; h < 2; h ++) {                          // 4-point DFT of a[4h .. 4h + 3] -> X[h + 2m]
+    const float2 c0 = a[4 * h], c1 = a[4 * h + 1], c2 = a[4 * h + 2], c3 = a[4 * h + 3];
+    const float2 e0 = make_float2(c0.x + c2.x, c0.y + c2.y), e1 = make_float2(c0.x - c2.x, c0.y - c2.y);
+    const float2 o0 = make_float2(c1.x + c3.x, c1.y + c3.y);
+    const float2 o1 = mul_w8<INV>(make_float2(c1.x - c3.x, c1.y - c3.y), 2);
+    u[h]     = make_float2(e0.x + o0.x, e0.y + o0.y);
+    u[h + 4] = make_float2(e0.x - o0.x, e0.y - o0.y);
+    u[h + 2] = make_float2(e1.x + o1.x, e1.y + o1.y);
+    u[h + 6] = make_float2(e1.x - o1.x, e1.y - o1.y);
+  }
+}
+
+// One Stockham pass of radix R (8, 4 or 2) from buffer a to buffer b; p = product of the radices already applied.
+template <int R, bool INV>
+__device__ __forceinline__ void fft_pass(const float2* a, float2* b, int n, int p, int lg_p,
+  const float2* __restrict__ tw, int lg_ntw) {
+  const int t = n / R;
+  constexpr int LR = R == 8 ? 3 : (R == 4 ? 2 : 1);
+  const int sh = lg_ntw - lg_p - LR;                     // twiddle index step: ntw / (p R)
+  for(int i = threadIdx.x; i < t; i += blockDim.x) {
+    const int k = i & (p - 1);
+    float2 u[R];
+#pragma unroll
+    for(int q = 0; q < R; q ++) u[q] = a[fpad(i + q * t)];
+    if(p > 1) {                                          // the first pass has unit twiddles (uniform branch)
+      const int m = k << sh;
+#pragma unroll
+      for(int q = 1; q < R; q ++) u[q] = cmul(u[q], fft_tw<INV>(tw, q * m));
+    }
+    const int j = ((i - k) << LR) + k;
+    if(R == 8) {
+      float2 v[8];
+#pragma unroll
+      for(int q = 0; q < 8; q ++) v[q] = u[q < R ? q : 0];
+      dft8_regs<INV>(v);
+#pragma unroll
+      for(int q = 0; q < 8; q ++) b[fpad(j + q * p)] = v[q];
+    } else if(R == 4) {
+      const float2 v0 = make_float2(u[0].x + u[2 % R].x, u[0].y + u[2 % R].y), v1 = make_float2(u[0].x - u[2 % R].x, u[0].y - u[2 % R].y);
+      const float2 v2 = make_float2(u[1].x + u[3 % R].x, u[1].y + u[3 % R].y);
+      const float2 v3 = mul_w8<INV>(make_float2(u[1].x - u[3 % R].x, u[1].y - u[3 % R].y), 2);
+      b[fpad(j)]         = make_float2(v0.x + v2.x, v0.y + v2.y);
+      b[fpad(j + p)]     = make_float2(v1.x + v3.x, v1.y + v3.y);
+      b[fpad(j + 2 * p)] = make_float2(v0.x - v2.x, v0.y - v2.y);
+      b[fpad(j + 3 * p)] = make_float2(v1.x - v3.x, v1.y - v3.y);
+    } else {
+      b[fpad(j)]     = make_float2(u[0].x + u[1].x, u[0].y + u[1].y);
+      b[fpad(j + p)] = make_float2(u[0].x - u[1].x, u[0].y - u[1].y);
+    }
+  }
+  __syncthreads();
+}
+
+template <bool INV>
+__device__ float2* block_fft8(float2* a, float2* b, int lg, const float2* __restrict__ tw, int lg_ntw) {
+  const int n = 1 << lg;
+  int lg_p = 0;
+  while(lg - lg_p >= 3) {
+    fft_pass<8, INV>(a, b, n, 1 << lg_p, lg_p, tw, lg_ntw);
+    float2* s = a; a = b; b = s; lg_p += 3;
+  }
+  if(lg - lg_p == 2) {
+    fft_pass<4, INV>(a, b, n, 1 << lg_p, lg_p, tw, lg_ntw);
+    float2* s = a; a = b; b = s;
+  } else if(lg - lg_p == 1) {
+    fft_pass<2, INV>(a, b, n, 1 << lg_p, lg_p, tw, lg_ntw);
+    float2* s = a; a = b; b = s;
+  }
+  return a;
+}
+
 // request a line into L2 ahead of its use (no register, no stall)
 __device__ __forceinline__ void prefetch_l2(const void* p) {
 #ifndef LLSM_EMU

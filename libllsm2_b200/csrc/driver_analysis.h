@@ -20,6 +20,7 @@ struct AnaPlan {
   unsigned use_x_mask = 0;
 };
 
+static inline int fpad_host(int j) { return j + (j >> 4); }
 static inline int ilog2_ceil(int n) { int l = 0; while((1 << l) < n) l ++; return l; }
 
 static inline void build_ana_plan(AnaPlan& p, float fs, float thop, int npsd, int nchannel,
@@ -212,7 +213,7 @@ static inline int run_analyze_l0(const SynthPlanDev& sp, AnaPlanDev& ap, AnaScra
     N.win_psd = ap.win_psd; N.win_power = h.win_power; N.std_norm = h.std_norm;
     N.tw_s = ap.tw_s; N.tw_p = ap.tw_p;
     N.env = sc.env.as<float>(); N.lpsd = sc.lpsd.as<float>();
-    size_t smem = (size_t)std::max(h.nfft, h.nfft_s) * 16 + 16;
+    size_t smem = (size_t)(fpad_host(std::max(h.nfft, h.nfft_s)) + 1) * 16 + 16;
 #ifndef LLSM_EMU
     cudaFuncSetAttribute(noise_spec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 #endif

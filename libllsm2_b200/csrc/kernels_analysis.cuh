@@ -135,6 +135,23 @@ struct HarmDftParams {
   int mma_cap_half;         // capacity (half window) of the tensor-core kernel's staging
 };
 
+
+// Amplitude and phase of one harmonic from its DFT sum (re, im), as llsm_harmonic_czt finishes it (dsputils.c:158-166):
+// the sum was rotated to the window centre with the exact shift (k + 1) omega0 half; the reference rotates by the
+// FLOAT-rounded ishift = (float)(shift 2 pi f0 / fs (k + 1)) instead, so the tiny difference eps (|eps| ~ 1e-4 rad: one
+// float rounding of a ~1e3 rad angle) is applied here -- by its Taylor series, exact to 1e-17 for such arguments,
+// instead of double-precision sin / cos calls. Amplitude = |.| 2 / sum(w).
+__device__ __forceinline__ void harmonic_finish(float re, float im, int k, int half, float f0, float fs, float omega0,
+  float winsum, float* ampl, float* phse) {
+  const float ishift = (float)((double)half * 2.0 * LLSM_PI * (double)f0 / (double)fs * ((double)k + 1.0));
+  const double eps = (double)ishift - (double)(k + 1) * (double)omega0 * (double)half;
+  const double e2 = eps * eps;
+  const float se = (float)(eps * (1.0 - e2 * (1.0 / 6.0))), ce = (float)(1.0 - 0.5 * e2);
+  const float dre = re * ce - im * se, dim = re * se + im * ce;
+  *ampl = sqrtf(dre * dre + dim * dim) * (2.0f / winsum);
+  *phse = atan2f(dim, dre);
+}
+
 #define HD_THREADS 128
 #define HD_RESEED 64
 #define HD_KW 8           // harmonics per signal in the warp-per-signal variant
@@ -260,15 +277,7 @@ __global__ void __launch_bounds__(HD_THREADS) harmonic_dft_kernel(HarmDftParams 
 
   const int npair = half + 1;
   auto finish = [&](int k, float re, float im) {
-    // residual of the reference's float-rounded centre shift (dsputils.c:158-162):
-    // ishift = (float)(shift * 2 pi f0 / fs * (k + 1)) versus (k + 1) * omega0 * shift
-    float ishift = (float)((double)half * 2.0 * LLSM_PI * (double)f0 / (double)P.fs * ((double)k + 1.0));
-    double eps = (double)ishift - (double)(k + 1) * (double)omega0 * (double)half;
-    float se = (float)sin(eps), ce = (float)cos(eps);
-    float dre = re * ce - im * se, dim = re * se + im * ce;
-    float a = (float)(sqrt((double)(dre * dre + dim * dim)) * 2.0 / (double)winsum);
-    P.ampl[fidx * P.maxnhar + k] = a;
-    P.phse[fidx * P.maxnhar + k] = atan2f(dim, dre);
+    harmonic_finish(re, im, k, half, f0, P.fs, omega0, winsum, &P.ampl[fidx * P.maxnhar + k], &P.phse[fidx * P.maxnhar + k]);
   };
 
   if(G == 32) {
@@ -369,6 +378,7 @@ __global__ void __launch_bounds__(HM_THREADS) harmonic_mma_kernel(HarmDftParams 
   double* red = (double*)(wv + ((cap + 2 + 1) & ~1)); // [HM_THREADS]
   float2* sph = (float2*)(red + HM_THREADS);          // [prow][HM_ROW] (e_hi, o_hi)
   float2* spl = sph + (size_t)prow * HM_ROW;          // [prow][HM_ROW] (e_lo, o_lo)
+  float2* sums = spl + (size_t)prow * HM_ROW;         // [maxnhar] DFT sums of the harmonics
 
   const int i = blockIdx.x, b = blockIdx.y;
   const int nf = P.nfrm_utt ? P.nfrm_utt[b] : P.nfrm;
@@ -472,29 +482,187 @@ __global__ void __launch_bounds__(HM_THREADS) harmonic_mma_kernel(HarmDftParams 
       }
     re += __shfl_xor_sync(0xffffffffu, re, 1); im += __shfl_xor_sync(0xffffffffu, im, 1);
     re += __shfl_xor_sync(0xffffffffu, re, 2); im += __shfl_xor_sync(0xffffffffu, im, 2);
-    if(t == 0 && kg < nh) {
-      float ishift = (float)((double)half * 2.0 * LLSM_PI * (double)f0 / (double)P.fs * ((double)kg + 1.0));
-      double eps = (double)ishift - (double)(kg + 1) * (double)omega0 * (double)half;
-      float se = (float)sin(eps), ce = (float)cos(eps);
-      float dre = re * ce - im * se, dim = re * se + im * ce;
-      float am = (float)(sqrt((double)(dre * dre + dim * dim)) * 2.0 / (double)winsum);
-      P.ampl[fidx * P.maxnhar + kg] = am;
-      P.phse[fidx * P.maxnhar + kg] = atan2f(dim, dre);
-    }
+    if(t == 0 && kg < nh) sums[kg] = make_float2(re, im);   // parked: the finish runs with every lane busy below
+  }
+  __syncthreads();
+  for(int k = tid; k < nh; k += HM_THREADS) {
+    const float2 v = sums[k];
+    harmonic_finish(v.x, v.y, k, half, f0, P.fs, omega0, winsum, &P.ampl[fidx * P.maxnhar + k], &P.phse[fidx * P.maxnhar + k]);
   }
   for(int k = nh + tid; k < P.maxnhar; k += HM_THREADS) { P.ampl[fidx * P.maxnhar + k] = 0; P.phse[fidx * P.maxnhar + k] = 0; }
   if(tid == 0) P.nhar_out[fidx] = nh;
 }
 
-static inline size_t harm_mma_smem(int cap) {
+static inline size_t harm_mma_smem(int cap, int maxnhar) {
   const int prow = (((cap + 1 + 15) / 16) + 7) & ~7;
-  return (size_t)((cap + 3) & ~1) * 4 + HM_THREADS * 8 + (size_t)prow * HM_ROW * 8 * 2 + 16;
+  return (size_t)((cap + 3) & ~1) * 4 + HM_THREADS * 8 + (size_t)prow * HM_ROW * 8 * 2 + (size_t)maxnhar * 8 + 16;
 }
 
 static inline int dft_variant() {
   static int v = -1;
   if(v < 0) { const char* e = getenv("LLSM_DFT_VARIANT"); v = e ? atoi(e) : 1; }
   return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// Envelope pass (layer0.c:443-446): the harmonic analysis of the nchannel squared sub-band signals of one frame, at
+// most 8 harmonics each, plus their short-time means. The channels share f0, the window and every phasor, so ONE CTA
+// serves the frame: thread t walks the sample pairs n = t, t + 128, ... carrying one phasor per harmonic (advanced 128
+// samples per step, re-seeded every 8 steps) and accumulates all channels x harmonics in registers -- a phasor update is
+// paid once per sample instead of once per sample and channel; the per-thread sums are reduced through shared memory in
+// a fixed order. NC = channel capacity, KW = harmonic capacity of the instance.
+// ------------------------------------------------------------------------------------------
+#define ED_THREADS 128
+
+template <int NC, int KW>
+__global__ void __launch_bounds__(ED_THREADS) envelope_dft_kernel(HarmDftParams P) {
+  LLSM_DYN_SMEM(smem);
+  float* wv = (float*)smem;                                          // [max_half + 2] window, w(half +- n)
+  double* red = (double*)(wv + ((P.max_half + 2 + 1) & ~1));         // [ED_THREADS]
+  float* part = (float*)(red + ED_THREADS);                          // [2 * NC * KW][ED_THREADS + 1]
+  float2* zst = (float2*)(part + 2 * NC * KW * (ED_THREADS + 1) + 1);// [KW] 128-sample rotation per harmonic
+  const int i = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nf = P.nfrm_utt ? P.nfrm_utt[b] : P.nfrm;
+  if(i >= nf) return;
+  const int nsig = P.nsig;
+  const size_t f0idx = (size_t)b * P.nfrm + i;
+  const float f0 = P.f0[f0idx];
+  const int center = P.center[i];
+  const float* x0 = P.sig + (size_t)b * nsig * P.xstride;
+
+  // ---- short-time means (llsm_compute_dc, dsputils.c:117-124): one warp per channel
+  if(P.edc != nullptr) {
+    double wlen = f0 == 0 ? (double)(P.thop * 2.0f) : 2.0 / (double)f0;
+    const int nw = (int)round(wlen * (double)P.fs);
+    for(int c = warp; c < nsig; c += ED_THREADS / 32) {
+      const float* x = x0 + (size_t)c * P.xstride;
+      double acc = 0;
+      for(int j = lane; j < nw; j += 4 * 32) {                       // four reads in flight, summed in the same order
+        float v[4];
+#pragma unroll
+        for(int u = 0; u < 4; u ++) {
+          const int idx = center + j + u * 32 - nw / 2;
+          v[u] = (j + u * 32 < nw && idx >= 0 && idx < P.nx) ? x[idx] : 0.f;
+        }
+#pragma unroll
+        for(int u = 0; u < 4; u ++) acc += (double)v[u];
+      }
+      for(int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if(lane == 0) P.edc[f0idx * nsig + c] = nw > 0 ? (float)(acc / nw) : 0.f;
+    }
+  }
+  if(! (f0 > 0)) {                                                   // unvoiced: no harmonic model (layer0.c:106)
+    for(int e = tid; e < nsig * P.maxnhar; e += ED_THREADS) { P.ampl[f0idx * nsig * P.maxnhar + e] = 0; P.phse[f0idx * nsig * P.maxnhar + e] = 0; }
+    if(tid < nsig) P.nhar_out[f0idx * nsig + tid] = 0;
+    return;
+  }
+  const int ws = ana_winsize(P.fs, f0, P.rel_winsize);
+  const int nh = ana_nhar(P.fs, f0, P.maxnhar);
+  const int half = ws >> 1;
+  if(half > P.max_half) { if(tid < nsig) P.nhar_out[f0idx * nsig + tid] = -1; return; }
+
+  // ---- Blackman window and its sum (see harmonic_dft_kernel)
+  double wsum = 0;
+  {
+    double cs, sn, cstep, sstep;
+    sincospi(2.0 * (double)tid / (double)ws, &sn, &cs);
+    sincospi(2.0 * (double)ED_THREADS / (double)ws, &sstep, &cstep);
+    for(int n = tid; n <= half; n += ED_THREADS) {
+      const float w = (float)(0.42 + 0.5 * cs + 0.08 * (2.0 * cs * cs - 1.0));
+      wv[n] = w;
+      if(n < half) wsum += w;
+      if(n >= 1) wsum += w;
+      const double c2 = cs * cstep - sn * sstep;
+      sn = sn * cstep + cs * sstep; cs = c2;
+    }
+  }
+  red[tid] = wsum;
+  const float omega0 = (float)(2.0 * LLSM_PI * (double)f0 / (double)P.fs);   // czt step (FP_TYPE arg)
+  const double nu = (double)omega0 / (2.0 * LLSM_PI);                        // turns per sample
+  if(tid < KW) zst[tid] = unit_phasor_turns((double)(tid + 1) * nu * (double)ED_THREADS);
+  __syncthreads();
+  for(int o = ED_THREADS >> 1; o > 0; o >>= 1) { if(tid < o) red[tid] += red[tid + o]; __syncthreads(); }
+  const float winsum = (float)red[0];
+
+  // ---- the sums over the window: symmetric / antisymmetric sample pairs (x+ + x-, x+ - x-) against cos / sin
+  const int npair = half + 1;
+  float re[NC][KW], im[NC][KW];
+  float2 w[KW], z[KW];
+#pragma unroll
+  for(int k = 0; k < KW; k ++) {
+    z[k] = zst[k];
+#pragma unroll
+    for(int c = 0; c < NC; c ++) { re[c][k] = 0.f; im[c][k] = 0.f; }
+  }
+  int step = 0;
+  for(int n = tid; n < npair; n += ED_THREADS, step ++) {
+    if((step & 7) == 0) {
+#pragma unroll
+      for(int k = 0; k < KW; k ++) if(k < nh) w[k] = unit_phasor_turns((double)(k + 1) * nu * (double)n);
+    }
+    const float wn = wv[n];
+    const int ip = center + n, im_ = center - n;
+    const bool okp = n < half && ip >= 0 && ip < P.nx, okm = n >= 1 && im_ >= 0 && im_ < P.nx;
+    float e[NC], o[NC];
+#pragma unroll
+    for(int c = 0; c < NC; c ++) {
+      float xp = 0.f, xm = 0.f;
+      if(c < nsig) {
+        const float* x = x0 + (size_t)c * P.xstride;
+        if(okp) xp = wn * x[ip];
+        if(okm) xm = wn * x[im_];
+      }
+      e[c] = xp + xm; o[c] = xp - xm;
+    }
+#pragma unroll
+    for(int k = 0; k < KW; k ++) if(k < nh) {
+#pragma unroll
+      for(int c = 0; c < NC; c ++) {
+        re[c][k] = fmaf(e[c], w[k].x, re[c][k]);
+        im[c][k] = fmaf(-o[c], w[k].y, im[c][k]);
+      }
+      w[k] = cmul(w[k], z[k]);
+    }
+  }
+  // ---- fixed-order reduction over the 128 threads: value v = (c, k, re | im) lives in row v of `part`
+#pragma unroll
+  for(int c = 0; c < NC; c ++)
+#pragma unroll
+    for(int k = 0; k < KW; k ++) {
+      part[(2 * (c * KW + k)) * (ED_THREADS + 1) + tid] = re[c][k];
+      part[(2 * (c * KW + k) + 1) * (ED_THREADS + 1) + tid] = im[c][k];
+    }
+  __syncthreads();
+  // thread t sums a quarter of row t / 4 (rows beyond 32 in a second round), then two shuffles finish the row
+  for(int r0 = 0; r0 < 2 * NC * KW; r0 += ED_THREADS / 4) {
+    const int r = r0 + (tid >> 2), q = tid & 3;
+    float acc = 0.f;
+    if(r < 2 * NC * KW) {
+      const float* row = part + r * (ED_THREADS + 1) + q * (ED_THREADS / 4);
+#pragma unroll 8
+      for(int u = 0; u < ED_THREADS / 4; u ++) acc += row[u];
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    __syncthreads();
+    if(r < 2 * NC * KW && q == 0) part[r * (ED_THREADS + 1)] = acc;          // row total in column 0
+  }
+  __syncthreads();
+  for(int e2 = tid; e2 < nsig * P.maxnhar; e2 += ED_THREADS) {
+    const int c = e2 / P.maxnhar, k = e2 - c * P.maxnhar;
+    const size_t at = (f0idx * nsig + c) * P.maxnhar + k;
+    if(k < nh && k < KW && c < NC) {
+      const float sre = part[(2 * (c * KW + k)) * (ED_THREADS + 1)], sim = part[(2 * (c * KW + k) + 1) * (ED_THREADS + 1)];
+      harmonic_finish(sre, sim, k, half, f0, P.fs, omega0, winsum, &P.ampl[at], &P.phse[at]);
+    } else { P.ampl[at] = 0; P.phse[at] = 0; }
+  }
+  if(tid < nsig) P.nhar_out[f0idx * nsig + tid] = nh;
+}
+
+template <int NC, int KW>
+static inline size_t env_dft_smem(int max_half) {
+  return (size_t)((max_half + 3) & ~1) * 4 + ED_THREADS * 8 + (size_t)(2 * NC * KW * (ED_THREADS + 1) + 1) * 4 + KW * 8 + 32;
 }
 
 static inline size_t harm_dft_smem(int max_half, int ng) {
@@ -508,7 +676,7 @@ static inline int launch_harmonic_dft(const HarmDftParams& Pin, int nutt, cudaSt
     int cap = (int)ceil((double)P.fs / 50.0 * (double)P.rel_winsize / 4.0 * 2.0) + 4;
     if(cap > P.max_half) cap = P.max_half;
     P.mma_cap_half = cap;
-    size_t smem = harm_mma_smem(cap);
+    size_t smem = harm_mma_smem(cap, P.maxnhar);
     if(smem <= 200 * 1024) {
 #ifndef LLSM_EMU
       cudaFuncSetAttribute(harmonic_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -518,30 +686,32 @@ static inline int launch_harmonic_dft(const HarmDftParams& Pin, int nutt, cudaSt
       P.only_above_half = cap;
     }
   }
-  const bool warp_groups = P.nsig > 1 && P.maxnhar <= HD_KW;
-  const int ng = warp_groups ? HD_THREADS / 32 : 1;
-  dim3 grid(P.nfrm, nutt * ((P.nsig + ng - 1) / ng)), block(HD_THREADS);
-  size_t smem = harm_dft_smem(P.max_half, ng);
-  if(smem > 200 * 1024) return -1;
-  if(warp_groups && P.maxnhar <= 4) {
-    auto kfn = harmonic_dft_kernel<32, 4>;
+  if(P.nsig > 1 && P.maxnhar <= 8 && P.nsig <= 8) {               // envelope pass: one CTA per frame, all channels
+    dim3 grid(P.nfrm, nutt), block(ED_THREADS);
 #ifndef LLSM_EMU
-    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#define LLSM_ENV_LAUNCH(NC, KW) { auto kfn = envelope_dft_kernel<NC, KW>; size_t smem = env_dft_smem<NC, KW>(P.max_half); \
+    if(smem > 200 * 1024) return -1; \
+    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    LLSM_LAUNCH(kfn, grid, block, smem, st, P); }
+#else
+#define LLSM_ENV_LAUNCH(NC, KW) { auto kfn = envelope_dft_kernel<NC, KW>; size_t smem = env_dft_smem<NC, KW>(P.max_half); \
+    LLSM_LAUNCH(kfn, grid, block, smem, st, P); }
 #endif
-    LLSM_LAUNCH(kfn, grid, block, smem, st, P);
-  } else if(warp_groups) {
-    auto kfn = harmonic_dft_kernel<32, HD_KW>;
-#ifndef LLSM_EMU
-    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-#endif
-    LLSM_LAUNCH(kfn, grid, block, smem, st, P);
-  } else {
-    auto kfn = harmonic_dft_kernel<HD_THREADS>;
-#ifndef LLSM_EMU
-    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-#endif
-    LLSM_LAUNCH(kfn, grid, block, smem, st, P);
+    if(P.nsig <= 4 && P.maxnhar <= 4) LLSM_ENV_LAUNCH(4, 4)
+    else if(P.nsig <= 4) LLSM_ENV_LAUNCH(4, 8)
+    else if(P.maxnhar <= 4) LLSM_ENV_LAUNCH(8, 4)
+    else LLSM_ENV_LAUNCH(8, 8)
+#undef LLSM_ENV_LAUNCH
+    return 0;
   }
+  dim3 grid(P.nfrm, nutt * P.nsig), block(HD_THREADS);
+  size_t smem = harm_dft_smem(P.max_half, 1);
+  if(smem > 200 * 1024) return -1;
+  auto kfn = harmonic_dft_kernel<HD_THREADS>;
+#ifndef LLSM_EMU
+  cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#endif
+  LLSM_LAUNCH(kfn, grid, block, smem, st, P);
   return 0;
 }
 
@@ -615,12 +785,15 @@ struct NoiseSpecParams {
 // part and frame i + 1 in the imaginary part. The windowed frames are separated by Hermitian symmetry;
 // the log spectra and the liftered cepstra are real and even, so their transforms are real and the two
 // frames stay separated in re / im without any post-processing.
+// Transforms: block_fft8 (radix-8 register butterflies, padded buffers). The last transform of the envelope is only
+// read at every (nfs / nfft)-th bin (layer0.c:341-342): when that step is even, bin 2 j of the nfs-point transform
+// of the liftered cepstrum D equals bin j of the (nfs / 2)-point transform of D[n] + D[n + nfs / 2] -- half the size.
 __global__ void __launch_bounds__(NS_THREADS) noise_spec_kernel(NoiseSpecParams P) {
   LLSM_DYN_SMEM(smem);
   const int nfs = P.nfft_s;
   const int nmax = nfs > P.nfft ? nfs : P.nfft;
   float2* bufa = (float2*)smem;
-  float2* bufb = bufa + nmax;
+  float2* bufb = bufa + fpad(nmax) + 1;
   const int i0 = 2 * blockIdx.x, b = blockIdx.y;
   const int nf = P.nfrm_utt ? P.nfrm_utt[b] : P.nfrm;
   if(i0 >= nf) return;
@@ -656,36 +829,38 @@ __global__ void __launch_bounds__(NS_THREADS) noise_spec_kernel(NoiseSpecParams 
         }
       }
     }
-    bufa[fsw(kb)] = make_float2(acc[0], acc[1]);
+    bufa[fpad(kb)] = make_float2(acc[0], acc[1]);
   }
   __syncthreads();
-  float2* X = block_fft<false, true>(bufa, bufb, P.lg_nfft_s, P.tw_s, nfs);
+  float2* X = block_fft8<false>(bufa, bufb, P.lg_nfft_s, P.tw_s, P.lg_nfft_s);
   float2* Y = (X == bufa) ? bufb : bufa;
   {
     float nrm[2];
 #pragma unroll
     for(int h = 0; h < 2; h ++) { float t = 1024.0f / P.std_norm; nrm[h] = t / (float)wsv[h]; }   // dsputils.c:111
     for(int k = tid; k <= nfs / 2; k += nth) {
-      const float2 zk = X[fsw(k)], zn = X[fsw((nfs - k) & (nfs - 1))];
+      const float2 zk = X[fpad(k)], zn = X[fpad((nfs - k) & (nfs - 1))];
       // A = (Zk + conj Zn) / 2, B = (Zk - conj Zn) / (2 i)
       const float ar = 0.5f * (zk.x + zn.x), ai = 0.5f * (zk.y - zn.y);
       const float br = 0.5f * (zk.y + zn.y), bi = -0.5f * (zk.x - zn.x);
       float ma = sqrtf(ar * ar + ai * ai) * nrm[0], mb = sqrtf(br * br + bi * bi) * nrm[1];
       const float2 lg = make_float2(logf(ma > 1e-10f ? ma : 1e-10f), logf(mb > 1e-10f ? mb : 1e-10f));
-      Y[fsw(k)] = lg;
-      if(k > 0 && k < nfs / 2) Y[fsw(nfs - k)] = lg;
+      Y[fpad(k)] = lg;
+      if(k > 0 && k < nfs / 2) Y[fpad(nfs - k)] = lg;
     }
   }
   __syncthreads();
-  float2* Cq = block_fft<true, true>(Y, X, P.lg_nfft_s, P.tw_s, nfs);      // cepstra * nfft (real, even)
+  float2* Cq = block_fft8<true>(Y, X, P.lg_nfft_s, P.tw_s, P.lg_nfft_s);     // cepstra * nfft (real, even)
   float2* D = (Cq == bufa) ? bufb : bufa;
+  const int estep_lg = P.lg_nfft_s - P.lg_nfft;                              // envelope bin step nfs / nfft = 1 << estep_lg
+  const bool fold = estep_lg >= 1;
   {
     float f0s[2];
 #pragma unroll
     for(int h = 0; h < 2; h ++) f0s[h] = (f0v[h] == 0 ? 200.0f : f0v[h]) / P.fs;   // layer0.c:338
     const float inv = 1.0f / (float)nfs;
     for(int q = tid; q <= nfs / 2; q += nth) {
-      const float2 c = Cq[fsw(q)];
+      const float2 c = Cq[fpad(q)];
       float cv[2] = {c.x, c.y};
 #pragma unroll
       for(int h = 0; h < 2; h ++) {
@@ -694,22 +869,37 @@ __global__ void __launch_bounds__(NS_THREADS) noise_spec_kernel(NoiseSpecParams 
         double xr_ = xq - 2.0 * rint(xq * 0.5);                       // reduce to [-1, 1]
         float s1 = sinpif((float)xr_);
         if(q > 0) sinc = s1 / (float)(LLSM_PI * xq);
-        double x2 = 2.0 * xq; x2 -= 2.0 * rint(x2 * 0.5);
-        float c2 = cospif((float)x2);
+        const float c2 = fmaf(-2.0f * s1, s1, 1.0f);                  // cos(2 pi xq) = 1 - 2 sin^2(pi xq)
         cv[h] = cv[h] * inv * sinc * (1.18f - 0.18f * c2);
       }
       const float2 d = make_float2(cv[0], cv[1]);
-      D[fsw(q)] = d;
-      if(q > 0 && q < nfs / 2) D[fsw(nfs - q)] = d;
+      D[fpad(q)] = d;
+      if(! fold && q > 0 && q < nfs / 2) D[fpad(nfs - q)] = d;
     }
   }
   __syncthreads();
-  float2* Ev = block_fft<false, true>(D, Cq, P.lg_nfft_s, P.tw_s, nfs);
-  for(int j = tid; j < P.nspec; j += nth) {
-    int idx = (j * nfs) >> P.lg_nfft;                                 // j * nfs / nfft, layer0.c:341-342
-    const float2 e = Ev[fsw(idx)];
-    P.env[orow + j] = e.x * 2.0f;
-    if(two) P.env[orow + P.nspec + j] = e.y * 2.0f;
+  float2* Ev;
+  if(fold) {
+    // D is even: D[n + nfs / 2] = D[nfs / 2 - n]; fold into the first half (written to the other buffer)
+    const int nh2 = nfs >> 1;
+    for(int n = tid; n < nh2; n += nth) {
+      const float2 u = D[fpad(n)], v = D[fpad(nh2 - n)];
+      Cq[fpad(n)] = make_float2(u.x + v.x, u.y + v.y);
+    }
+    __syncthreads();
+    Ev = block_fft8<false>(Cq, D, P.lg_nfft_s - 1, P.tw_s, P.lg_nfft_s);
+  } else {
+    Ev = block_fft8<false>(D, Cq, P.lg_nfft_s, P.tw_s, P.lg_nfft_s);
+  }
+  {
+    const int emask = (fold ? (nfs >> 1) : nfs) - 1;
+    for(int j = tid; j < P.nspec; j += nth) {
+      int idx = (j * nfs) >> P.lg_nfft;                                // j * nfs / nfft, layer0.c:341-342
+      if(fold) idx = (idx >> 1) & emask;                               // (even by construction)
+      const float2 e = Ev[fpad(idx)];
+      P.env[orow + j] = e.x * 2.0f;
+      if(two) P.env[orow + P.nspec + j] = e.y * 2.0f;
+    }
   }
   __syncthreads();
 
@@ -724,12 +914,12 @@ __global__ void __launch_bounds__(NS_THREADS) noise_spec_kernel(NoiseSpecParams 
       idx = cen[1] + j - P.nwin / 2;
       if(two && idx >= 0 && idx < P.nx) v1 = w * xr[idx];
     }
-    bufa[fsw(j)] = make_float2(v0, v1);
+    bufa[fpad(j)] = make_float2(v0, v1);
   }
   __syncthreads();
-  float2* Z = block_fft<false, true>(bufa, bufb, P.lg_nfft, P.tw_p, P.nfft);
+  float2* Z = block_fft8<false>(bufa, bufb, P.lg_nfft, P.tw_p, P.lg_nfft);
   for(int j = tid; j < P.nspec; j += nth) {
-    const float2 zk = Z[fsw(j)], zn = Z[fsw((P.nfft - j) & (P.nfft - 1))];
+    const float2 zk = Z[fpad(j)], zn = Z[fpad((P.nfft - j) & (P.nfft - 1))];
     const float ar = 0.5f * (zk.x + zn.x), ai = 0.5f * (zk.y - zn.y);
     const float br = 0.5f * (zk.y + zn.y), bi = -0.5f * (zk.x - zn.x);
     float pa = __fadd_rn(__fmul_rn(ar, ar), __fmul_rn(ai, ai)) / P.win_power;

@@ -236,13 +236,21 @@ static inline int bank_variant() {
   return v;
 }
 
+static inline int residual_tc_enabled() {
+  static int v = -1;
+  if(v < 0) { const char* e = getenv("LLSM_RESIDUAL_TC"); v = e ? atoi(e) : 1; }
+  return v;
+}
+
 // returns 0 on success, -1 when the window is too long for the specialisations below
 static inline int launch_hm_bank(BankParams P, int nutt, int nfrm_max, cudaStream_t st) {
 #ifndef LLSM_EMU
-  // synthesis with many harmonics: operand generation + tcgen05 GEMM (kernels_bank_tc.cuh, ~1e-7 of the
-  // frame amplitude); few harmonics, or the analysis residual (options == NULL: x - x_sin is a small difference
-  // of large numbers and wants the last digits): direct FP32 summation below
-  if(bank_tc_enabled() && P.has_options && P.maxnhar >= 24 && launch_hm_bank_tc(P, nutt, nfrm_max, st) == 0) return 0;
+  // many harmonics: operand generation + tcgen05 GEMM (kernels_bank_tc.cuh, ~1e-7 of the frame amplitude, i.e. ~5e-9
+  // absolute on speech-level frames: also enough for the analysis residual x - x_sin, whose parity bar is 1e-6 RMS;
+  // LLSM_RESIDUAL_TC=0 sends the residual (options == NULL) back to the direct summation); few harmonics or long
+  // windows: direct FP32 summation below
+  if(bank_tc_enabled() && (P.has_options || residual_tc_enabled()) && P.maxnhar >= 24 &&
+     launch_hm_bank_tc(P, nutt, nfrm_max, st) == 0) return 0;
 #endif
   const int NTHR = 256, NW = NTHR / 32;
   P.npass = 4;                              // 32 frame slots, 30 tiles per CTA
