@@ -310,6 +310,27 @@ int llsm_b200_synthesize_l0_shard(llsm_b200_ctx* ctx, const llsm_b200_conf* conf
 int llsm_b200_halo_length(const llsm_b200_conf* conf);              /* samples a frame reaches past its centre */
 int llsm_b200_frame_position(int i, float thop, float fs);          /* round(i * thop * fs), layer0.c:127-128 */
 
+/* The exchange that completes frame-range shards (north_star: "a single NCCL all-gather of the overlap-add boundary
+   samples"). world ranks, rank r owning the frames [frame_edges[r], frame_edges[r + 1]) (frame_edges: HOST array of
+   world + 1 ascending entries, 0 ... nfrm) and the output samples [llsm_b200_shard_position(edge r), ..(edge r + 1)).
+   After llsm_b200_synthesize_l0_shard, llsm_b200_halo_exchange packs what this rank's frames add outside its own
+   sample range into two strips of llsm_b200_halo_length() samples per component (kernel), all-gathers the strips
+   (ncclAllGather on ctx's stream), adds the other ranks' strips into the owned range and rewrites y = y_sin + y_noise
+   there (kernel). On return the owned sample range of out->{y_sin, y_noise, y} is complete and equal to the unsharded
+   result; samples outside it still hold this rank's partial sums. Device pointers.
+   The communicator belongs to the context: either created by the library from an ncclUniqueId that the caller moves
+   from rank 0 to the other ranks by its own means (llsm_b200_comm_unique_id on rank 0, llsm_b200_comm_init on every
+   rank: collective), or the caller's own ncclComm_t (llsm_b200_comm_attach; it must come from the libnccl.so.2 this
+   process has loaded). NCCL is bound at run time; without it these calls fail with LLSM_B200_ENODEVICE. */
+#define LLSM_B200_COMM_ID_BYTES 128
+int llsm_b200_comm_unique_id(void* id /* LLSM_B200_COMM_ID_BYTES */);
+int llsm_b200_comm_init(llsm_b200_ctx* ctx, const void* id, int rank, int world);
+int llsm_b200_comm_attach(llsm_b200_ctx* ctx, void* nccl_comm, int rank, int world);
+int llsm_b200_comm_destroy(llsm_b200_ctx* ctx);
+int llsm_b200_shard_position(const llsm_b200_conf* conf, int frame_edge);   /* 0, frame positions, ny at nfrm */
+int llsm_b200_halo_exchange(llsm_b200_ctx* ctx, const llsm_b200_conf* conf, const llsm_b200_output* out,
+  const int* frame_edges);
+
 /* ---- streaming synthesis: llsm_rtsynth_buffer_* (llsmrt.h:33-56, llsmrt.c:157-602) --------------------
    One llsm_b200_rt advances conf->nutt independent streams that share fs and thop (hence one hop
    schedule: llsm_update_cycle, llsmrt.c:110-129). Every stream owns its ring buffers, circular noise

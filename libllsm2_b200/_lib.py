@@ -80,6 +80,12 @@ def lib():
     L.llsm_b200_frames_blob_size.argtypes = [C.POINTER(abi.Conf), C.POINTER(abi.Frames)]
     L.llsm_b200_frames_pack.argtypes = [C.POINTER(abi.Conf), C.POINTER(abi.Frames), P, C.c_size_t]
     L.llsm_b200_frames_unpack.argtypes = [P, C.c_size_t, C.POINTER(abi.Conf), C.POINTER(abi.Frames)]
+    L.llsm_b200_comm_unique_id.argtypes = [P]
+    L.llsm_b200_comm_init.argtypes = [P, C.c_char_p, C.c_int, C.c_int]
+    L.llsm_b200_comm_attach.argtypes = [P, P, C.c_int, C.c_int]
+    L.llsm_b200_comm_destroy.argtypes = [P]
+    L.llsm_b200_shard_position.argtypes = [C.POINTER(abi.Conf), C.c_int]
+    L.llsm_b200_halo_exchange.argtypes = [P, C.POINTER(abi.Conf), C.POINTER(abi.Output), P]
     L.llsm_b200_set_kernel_timing.argtypes = [P, C.c_int]
     L.llsm_b200_kernel_timing_read.argtypes = [P, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_float)]
     _lib = L

@@ -9,6 +9,8 @@
 #include "kernels_phase.cuh"
 #include "kernels_stretch.cuh"
 #include "driver_coder.h"
+#include "kernels_halo.cuh"
+#include <dlfcn.h>
 #include <cstdio>
 #include <cstdarg>
 #include <mutex>
@@ -21,6 +23,8 @@ static int fail(int code, const char* fmt, ...) {
   va_end(ap);
   return code;
 }
+
+struct NcclUniqueId { char internal[128]; };   // ncclUniqueId (nccl.h): passed by value to ncclCommInitRank
 
 struct PlanKey {
   int nfrm, npsd, nchannel; float fs, thop; float cf[LLSM_B200_MAXCHANNEL];
@@ -39,6 +43,9 @@ struct llsm_b200_ctx {
   std::unique_ptr<CoderPlanDev> coderplan;
   PbpScratch pbp;
   DevBuf ny_utt, phase_theta;
+  // frame-range sharding: NCCL communicator (ours or the caller's) and the strip buffers of the halo exchange
+  void* comm = nullptr; bool own_comm = false; int comm_rank = 0, comm_world = 1;
+  DevBuf halo_send, halo_recv, halo_pos;
   DevBuf stage[24];          // device staging for the *_host entry points
   // copy / compute pipeline of synthesize_l0_host: two slots of input and output staging
   cudaStream_t s_in = nullptr, s_out = nullptr;
@@ -112,10 +119,14 @@ llsm_b200_ctx* llsm_b200_create(int device) {
   return ctx;
 }
 
+int llsm_b200_comm_destroy(llsm_b200_ctx* ctx);
+
 void llsm_b200_destroy(llsm_b200_ctx* ctx) {
   if(ctx == nullptr) return;
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
+  llsm_b200_comm_destroy(ctx);
+  ctx->halo_send.release(); ctx->halo_recv.release(); ctx->halo_pos.release();
   for(auto& kv : ctx->plans) kv.second->release();
   for(auto& kv : ctx->aplans) kv.second->release();
   ctx->scratch.colored.release(); ctx->scratch.y_exc.release(); ctx->scratch.ny_utt.release();
@@ -384,5 +395,6 @@ int llsm_b200_kernel_timing_read(llsm_b200_ctx* ctx, int max, const char** names
 #include "api_layer1.inc"
 #include "api_rt.inc"
 #include "api_blob.inc"
+#include "api_halo.inc"
 
 } // extern "C"

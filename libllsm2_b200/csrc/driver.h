@@ -81,7 +81,7 @@ struct SynthPlanDev {
     rc |= up(&win_ns, h.win_ns, st);   rc |= up(&psd_lo, h.psd_lo, st);
     rc |= up(&psd_r, h.psd_r, st);
     float* twd = nullptr; rc |= up(&twd, tw, st); tw_ns = (float2*)twd;
-    iir_L = ((h.nt + IIR_NT - 1) / IIR_NT + 3) & ~3;
+    iir_L = ((h.nt + IIR_NT - 1) / IIR_NT + IIR_T - 1) & ~(IIR_T - 1);
     std::vector<double> coef((size_t)LLSM_B200_MAXCHANNEL * 2 * 9, 0.0), mpow((size_t)LLSM_B200_MAXCHANNEL * 2 * IIR_NLOG * 16, 0.0);
     for(int c = 0; c < nchannel; c ++)
       for(int s2 = 0; s2 < h.chan[c].nstage; s2 ++)

@@ -102,7 +102,7 @@ struct AnaPlanDev {
   int ensure_iir(int nx, cudaStream_t st) {
     if(nx == iir_nx) return 0;
     if(dev_sync(st) != 0) return -1;           // previous tables may still be in use / in flight
-    iir_L = ((nx + IIR_NT - 1) / IIR_NT + 3) & ~3;
+    iir_L = ((nx + IIR_NT - 1) / IIR_NT + IIR_T - 1) & ~(IIR_T - 1);
     h_coef.assign((size_t)LLSM_B200_MAXCHANNEL * 2 * 9, 0.0);
     h_mpow.assign((size_t)LLSM_B200_MAXCHANNEL * 2 * IIR_NLOG * 16, 0.0);
     for(int c = 0; c < nchannel; c ++)

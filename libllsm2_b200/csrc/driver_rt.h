@@ -125,7 +125,7 @@ static inline int rt_create(RtBatch& R, const llsm_b200_conf& conf, const llsm_b
   const int tstride = (nsrc + 3) & ~3;
   if(R.colored.reserve((size_t)S * nch * tstride * 4)) return LLSM_B200_ENOMEM;
   std::vector<double> coef((size_t)LLSM_B200_MAXCHANNEL * 2 * 9, 0.0), mpow((size_t)LLSM_B200_MAXCHANNEL * 2 * IIR_NLOG * 16, 0.0);
-  const int L = ((nsrc + IIR_NT - 1) / IIR_NT + 3) & ~3;
+  const int L = ((nsrc + IIR_NT - 1) / IIR_NT + IIR_T - 1) & ~(IIR_T - 1);
   IirParams I; memset(&I, 0, sizeof(I));
   R.chan_mask = 0;
   for(int c = 0; c < nch; c ++) {

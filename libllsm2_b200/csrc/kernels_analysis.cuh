@@ -520,7 +520,7 @@ __global__ void __launch_bounds__(ED_THREADS) envelope_dft_kernel(HarmDftParams 
   float* wv = (float*)smem;                                          // [max_half + 2] window, w(half +- n)
   double* red = (double*)(wv + ((P.max_half + 2 + 1) & ~1));         // [ED_THREADS]
   float* part = (float*)(red + ED_THREADS);                          // [2 * NC * KW][ED_THREADS + 1]
-  float2* zst = (float2*)(part + 2 * NC * KW * (ED_THREADS + 1) + 1);// [KW] 128-sample rotation per harmonic
+  float2* zst = (float2*)(part + 2 * NC * KW * (ED_THREADS + 1));   // [KW] 128-sample rotation per harmonic (8-byte aligned)
   const int i = blockIdx.x, b = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nf = P.nfrm_utt ? P.nfrm_utt[b] : P.nfrm;
@@ -662,7 +662,7 @@ __global__ void __launch_bounds__(ED_THREADS) envelope_dft_kernel(HarmDftParams 
 
 template <int NC, int KW>
 static inline size_t env_dft_smem(int max_half) {
-  return (size_t)((max_half + 3) & ~1) * 4 + ED_THREADS * 8 + (size_t)(2 * NC * KW * (ED_THREADS + 1) + 1) * 4 + KW * 8 + 32;
+  return (size_t)((max_half + 3) & ~1) * 4 + ED_THREADS * 8 + (size_t)(2 * NC * KW * (ED_THREADS + 1)) * 4 + KW * 8 + 32;
 }
 
 static inline size_t harm_dft_smem(int max_half, int ng) {

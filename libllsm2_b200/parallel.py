@@ -7,12 +7,13 @@ Two partitions of the hot path:
 * frame-range sharding -- one batch of long utterances, rank r synthesises frames
   [lo_r, hi_r) of every utterance; a frame reaches at most `halo` samples beyond its centre, so the
   partial sums only have to be completed in strips of `halo` samples around the shard boundaries:
-  ONE all-gather of the boundary strips of (y_sin, y_noise), then a local add.
+  ONE all-gather of the boundary strips of (y_sin, y_noise), then a local add -- llsm_b200_halo_exchange of the C
+  library (HaloExchange below); tests/dist_model.py keeps a plain torch restatement of it for the CPU (gloo) tests.
 """
 import torch
 import torch.distributed as dist
 
-from ._lib import lib
+from ._lib import lib, check
 
 
 def frame_shards(nfrm, world):
@@ -31,46 +32,76 @@ def shard_sample_range(conf, lo, hi, nfrm, ny):
     return sa, sb
 
 
-def exchange_halos(partial, conf, rank, world, halo=None, group=None):
-    """Complete the partial sums of a frame-range shard.
+class HaloExchange:
+    """The exchange that completes frame-range shards, done by the C library (llsm_b200_halo_exchange: pack kernel ->
+    ncclAllGather -> edge-add kernel on the context's stream). torch.distributed is only the courier of the
+    ncclUniqueId: rank 0 draws it (llsm_b200_comm_unique_id), a broadcast hands it to the others, every rank then
+    joins the library's own communicator (llsm_b200_comm_init)."""
 
-    partial: dict(y_sin, y_noise) of [B][ny] tensors holding this rank's partial sums (any device).
-    Returns dict(y_sin, y_noise, y) restricted to the samples this rank owns ([B][sb - sa]) and (sa, sb).
-    One all_gather of a [B][2 sides][2 components][halo] tensor per call.
-    """
-    import ctypes as C
-    nfrm = conf.nfrm
-    ny = partial["y_sin"].shape[1]
-    if halo is None:
-        halo = lib().llsm_b200_halo_length(C.byref(conf))
-    shards = frame_shards(nfrm, world)
-    lo, hi = shards[rank]
-    sa, sb = shard_sample_range(conf, lo, hi, nfrm, ny)
-    assert sb - sa >= halo, "shard shorter than the halo: use fewer ranks or longer utterances"
-    B = partial["y_sin"].shape[0]
-    dev = partial["y_sin"].device
-    strips = torch.zeros((B, 2, 2, halo), dtype=torch.float32, device=dev)
-    for c, k in enumerate(("y_sin", "y_noise")):
-        p = partial[k]
-        l0 = max(sa - halo, 0)
-        strips[:, 0, c, halo - (sa - l0):] = p[:, l0:sa]                 # spill into the left neighbour
-        r1 = min(sb + halo, ny)
-        strips[:, 1, c, :r1 - sb] = p[:, sb:r1]                          # spill into the right neighbour
-    gathered = [torch.empty_like(strips) for _ in range(world)]
-    if world > 1:
-        dist.all_gather(gathered, strips, group=group)
-    else:
-        gathered = [strips]
-    out = {}
-    for c, k in enumerate(("y_sin", "y_noise")):
-        own = partial[k][:, sa:sb].clone()
-        if rank > 0:                                                     # left neighbour's right strip
-            own[:, :halo] += gathered[rank - 1][:, 1, c, :]
-        if rank < world - 1:                                             # right neighbour's left strip
-            own[:, -halo:] += gathered[rank + 1][:, 0, c, :]
-        out[k] = own
-    out["y"] = out["y_sin"] + out["y_noise"]
-    return out, (sa, sb)
+    def __init__(self, ctx, conf, world, rank, stride, group=None, edges=None):
+        import ctypes as C
+        import numpy as np
+        self.ctx, self.conf, self.world, self.rank, self.stride = ctx, conf, world, rank, stride
+        L = lib()
+        self.halo = L.llsm_b200_halo_length(C.byref(conf))
+        self.bytes_per_rank = conf.nutt * 4 * self.halo * 4
+        self.edges = np.asarray(edges if edges is not None else
+                                [e for e, _ in frame_shards(conf.nfrm, world)] + [conf.nfrm], np.int32)
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (C.c_char * 128)()
+            check(L.llsm_b200_comm_unique_id(buf))
+            ident = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+        if world > 1:
+            dev = torch.device("cuda", ctx.device) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+            t = ident.to(dev)
+            dist.broadcast(t, src=0, group=group)
+            ident = t.cpu()
+        raw = bytes(ident.numpy().tobytes())
+        check(L.llsm_b200_comm_init(ctx._h, raw, int(rank), int(world)))
+
+    def sample_range(self):
+        import ctypes as C
+        L = lib()
+        return (L.llsm_b200_shard_position(C.byref(self.conf), int(self.edges[self.rank])),
+                L.llsm_b200_shard_position(C.byref(self.conf), int(self.edges[self.rank + 1])))
+
+    def exchange(self, out, lo=None, hi=None):
+        """out: dict(y, y_sin, y_noise) of [B][stride] CUDA tensors holding this rank's partial sums; on return the
+        samples this rank owns (sample_range()) are complete in all three."""
+        import ctypes as C
+        from . import abi
+        o = abi.Output()
+        o.y = out["y"].data_ptr() if out.get("y") is not None else None
+        o.y_sin, o.y_noise, o.stride = out["y_sin"].data_ptr(), out["y_noise"].data_ptr(), out["y_sin"].shape[1]
+        check(lib().llsm_b200_halo_exchange(self.ctx._h, C.byref(self.conf), C.byref(o),
+                                            self.edges.ctypes.data_as(C.c_void_p)))
+        return self.sample_range()
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this process (and, by first touch, the pinned host buffers it allocates next) to the CPUs of the NUMA node
+    the GPU hangs off, so that the ranks of one box do not all stage their host traffic through node 0. Best effort:
+    returns the cpu list it bound to, or None when the topology cannot be read."""
+    import os
+    try:
+        props = torch.cuda.get_device_properties(local_rank)
+        bus = "%04x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = set(os.sched_getaffinity(0))
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
 
 
 def utterance_shards(nutt, world):
