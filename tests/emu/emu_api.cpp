@@ -221,3 +221,24 @@ extern "C" int emu_frames_stretch(const llsm_b200_conf* conf, const llsm_b200_fr
   P.o_ephse = dst->ephse; P.o_nhar = dst->nhar; P.o_ampl = dst->ampl; P.o_phse = dst->phse;
   return run_frames_stretch(P, nullptr, nullptr);
 }
+
+// ---- halo exchange of frame-range shards: the two kernels around the all-gather (kernels_halo.cuh) ----
+#include "../../libllsm2_b200/csrc/kernels_halo.cuh"
+// spos: [world + 1] owned-range boundaries; strips: this rank's [B][2][2][halo]
+extern "C" int emu_halo_pack(int nutt, int ny, int stride, int halo, int rank, int world, const int* spos,
+  float* y_sin, float* y_noise, float* strips) {
+  HaloParams P; memset(&P, 0, sizeof(P));
+  P.nutt = nutt; P.ny = ny; P.stride = stride; P.halo = halo; P.rank = rank; P.world = world; P.spos = spos;
+  P.y_sin = y_sin; P.y_noise = y_noise; P.strips = strips;
+  run_halo_pack(P, nullptr);
+  return 0;
+}
+// gathered: [world][B][2][2][halo]
+extern "C" int emu_halo_add(int nutt, int ny, int stride, int halo, int rank, int world, const int* spos,
+  float* y_sin, float* y_noise, float* y, float* gathered) {
+  HaloParams P; memset(&P, 0, sizeof(P));
+  P.nutt = nutt; P.ny = ny; P.stride = stride; P.halo = halo; P.rank = rank; P.world = world; P.spos = spos;
+  P.y_sin = y_sin; P.y_noise = y_noise; P.y = y; P.strips = gathered;
+  run_halo_add(P, spos[rank + 1] - spos[rank], nullptr);
+  return 0;
+}

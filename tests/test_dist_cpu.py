@@ -44,9 +44,32 @@ def _worker(rank, world, port, q):
     white = rng.standard_normal((2, conf.nchannel, 20128 if False else min(20000, parallel_ny(conf)) + 128)).astype(np.float32)
     lo, hi = parallel.frame_shards(conf.nfrm, world)[rank]
     y, ys, yn = _emu_synth(conf, fr, white, lo, hi)
+    # (1) the library's exchange: pack kernel -> all-gather -> edge-add kernel (kernels_halo.cuh on the CPU emulator,
+    #     gloo standing in for ncclAllGather; same strip layout and call order as llsm_b200_halo_exchange)
+    from libllsm2_b200._lib import lib
+    L = lib()
+    emu = S.load_emu()
+    B, ny = ys.shape
+    halo = L.llsm_b200_halo_length(C.byref(conf))
+    edges = [e for e, _ in parallel.frame_shards(conf.nfrm, world)] + [conf.nfrm]
+    spos = np.array([L.llsm_b200_shard_position(C.byref(conf), e) for e in edges], np.int32)
+    ks, kn, ky = ys.copy(), yn.copy(), np.zeros_like(ys)
+    strips = np.zeros((B, 2, 2, halo), np.float32)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    emu.emu_halo_pack(B, ny, ny, halo, rank, world, vp(spos), vp(ks), vp(kn), vp(strips))
+    gathered = [torch.empty(strips.shape, dtype=torch.float32) for _ in range(world)]
+    dist.all_gather(gathered, torch.from_numpy(strips))
+    g = np.ascontiguousarray(torch.stack(gathered).numpy())
+    emu.emu_halo_add(B, ny, ny, halo, rank, world, vp(spos), vp(ks), vp(kn), vp(ky), vp(g))
+    ksa, ksb = int(spos[rank]), int(spos[rank + 1])
+    # (2) the plain torch restatement of the same exchange
+    import dist_model
     part = {"y_sin": torch.from_numpy(ys), "y_noise": torch.from_numpy(yn)}
-    out, (sa, sb) = parallel.exchange_halos(part, conf, rank, world)
-    q.put((rank, sa, sb, out["y_sin"].numpy(), out["y_noise"].numpy(), out["y"].numpy()))
+    out, (sa, sb) = dist_model.exchange_halos(part, conf, rank, world)
+    assert (sa, sb) == (ksa, ksb)
+    for a, b2 in ((ks, out["y_sin"]), (kn, out["y_noise"]), (ky, out["y"])):
+        assert np.array_equal(a[:, sa:sb], b2.numpy())
+    q.put((rank, sa, sb, ks[:, sa:sb].copy(), kn[:, sa:sb].copy(), ky[:, sa:sb].copy()))
     dist.barrier()
     dist.destroy_process_group()
 

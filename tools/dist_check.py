@@ -18,11 +18,13 @@ d = {k: (torch.from_numpy(v).to(dev) if v is not None else None) for k, v in fr.
 ctx = L.Context(local)
 lo, hi = parallel.frame_shards(F, world)[rank]
 part = L.synthesize_l0_shard(ctx, conf, d, lo, hi, white=None, seed=99)
+ex = parallel.HaloExchange(ctx, conf, world, rank, part["y"].shape[1])
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
-out, (sa, sb) = parallel.exchange_halos(part, conf, rank, world)
+sa, sb = ex.exchange(part)                  # llsm_b200_halo_exchange: pack kernel -> ncclAllGather -> edge-add kernel
 e1.record(); torch.cuda.synchronize()
+out = {k: v[:, sa:sb] for k, v in part.items()}
 full = L.synthesize_l0(ctx, conf, d, white=None, seed=99)      # every rank also computes the whole thing
 torch.cuda.synchronize()
 err = {k: float((out[k] - full[k][:, sa:sb]).abs().max()) for k in ("y", "y_sin", "y_noise")}
