@@ -149,7 +149,7 @@ static inline int run_analyze_l0(const SynthPlanDev& sp, AnaPlanDev& ap, AnaScra
     RefineParams R; memset(&R, 0, sizeof(R));
     R.nfrm = F; R.nfrm_utt = nfrm_utt; R.x = x; R.nx = nx; R.xstride = xstride;
     R.center = sp.hm_base; R.fs = conf.fs; R.f0 = fr.f0;
-    LLSM_LAUNCH(refine_f0_kernel, dim3(F, B), dim3(96), 0, st, R);
+    LLSM_LAUNCH(refine_f0_kernel, dim3((F + RF_WARPS - 1) / RF_WARPS, B), dim3(32 * RF_WARPS), 0, st, R);
     if(lc) lc->n ++;
     lc_mark(lc, st, "refine_f0");
   }

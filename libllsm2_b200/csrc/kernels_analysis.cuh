@@ -43,75 +43,94 @@ struct RefineParams {
   float* f0;                // [B][nfrm] in/out
 };
 
-// One CTA (96 threads = 3 warps) per frame; warp j estimates the instantaneous frequency around
-// harmonic j+1 with the windowed complex-demodulation detector of the oracle's ciglet shim:
-// Hann window of nh = 2 round(2 / fres) + 1 taps (fres = f0 / fs), f = fc - Im(yd / y) / (2 pi).
-__global__ void __launch_bounds__(96) refine_f0_kernel(RefineParams P) {
-  __shared__ float s_f[3];
-  __shared__ int s_ok[3];
-  const int i = blockIdx.x, b = blockIdx.y;
+// One WARP per frame (RF_WARPS frames per CTA) estimates the instantaneous frequency around harmonics 1..3 with the
+// windowed complex-demodulation detector of the oracle's ciglet shim: Hann window of nh = 2 round(2 / fres) + 1 taps
+// (fres = f0 / fs), f = fc - Im(yd / y) / (2 pi). The three detectors share their window (same fres), so a tap costs one
+// window rotation and three demodulation rotations, all in double from one seed per lane (m = lane - half, + 32, ...);
+// the taps are formed and accumulated in float (the detector stores them as FP_TYPE), ~40 terms per lane, and the
+// lane sums are combined in double. (First version: a warp per harmonic with double taps and accumulators -- the
+// kernel was bound by the double <-> float conversions, XU pipe 80 % busy.)
+#define RF_WARPS 4
+
+__global__ void __launch_bounds__(32 * RF_WARPS) refine_f0_kernel(RefineParams P) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * RF_WARPS + warp, b = blockIdx.y;
   const int nf = P.nfrm_utt ? P.nfrm_utt[b] : P.nfrm;
   if(i >= nf) return;
   const float f0 = P.f0[(size_t)b * P.nfrm + i];
   if(f0 == 0) return;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int j = warp + 1;
   const float fres = f0 / P.fs;
-  const float fc = fres * (float)j;                    // f0[i] / fs * j
   int half = (int)round(2.0 / (double)fres);
   if(half < 2) half = 2;
   const int nh = 2 * half + 1;
   const double L = 2.0 * half + 2.0;
   const float* x = P.x + (size_t)b * P.xstride;
   const int center = P.center[i];
-  double yr = 0, yi = 0, dr = 0, di = 0;
+  float fc[3];
+#pragma unroll
+  for(int j = 0; j < 3; j ++) fc[j] = fres * (float)(j + 1);          // f0[i] / fs * j (dsputils.c:79)
+  float yr[3] = {0.f, 0.f, 0.f}, yi[3] = {0.f, 0.f, 0.f}, dr[3] = {0.f, 0.f, 0.f}, di[3] = {0.f, 0.f, 0.f};
   {
-    // window angle 2 pi m / L and demodulation angle 2 pi fc m advance by fixed rotations (double) from one
-    // seed per lane: m = lane - half, lane - half + 32, ...
     const int m0 = lane - nh / 2;
-    double sw, cw, sws, cws, sp, cp, sps, cps;
+    double sw, cw, sws, cws, sp[3], cp[3], sps[3], cps[3];
     sincospi(2.0 * (double)m0 / L, &sw, &cw);
     sincospi(2.0 * 32.0 / L, &sws, &cws);
-    double u = (double)fc * (double)m0; u -= rint(u);
-    sincospi(2.0 * u, &sp, &cp);
-    double us = (double)fc * 32.0; us -= rint(us);
-    sincospi(2.0 * us, &sps, &cps);
-    const double wdk = -0.5 * (2.0 * LLSM_PI / L);
+#pragma unroll
+    for(int j = 0; j < 3; j ++) {
+      double u = (double)fc[j] * (double)m0; u -= rint(u);
+      sincospi(2.0 * u, &sp[j], &cp[j]);
+      double us = (double)fc[j] * 32.0; us -= rint(us);
+      sincospi(2.0 * us, &sps[j], &cps[j]);
+    }
+    const float wdk = (float)(-0.5 * (2.0 * LLSM_PI / L));
+    int idx = center + lane - nh / 2;
+    float xn = (lane < nh && idx >= 0 && idx < P.nx) ? x[idx] : 0.f;
     for(int t = lane; t < nh; t += 32) {
-      const int idx = center + t - nh / 2;
-      if(idx >= 0 && idx < P.nx) {
-        const double xv = (double)x[idx];
-        const double w = 0.5 + 0.5 * cw;
-        const double wd = wdk * sw;
-        // taps are stored as FP_TYPE (float) in the detector
-        float hr = (float)(w * cp), hi = (float)(-w * sp), hdr = (float)(wd * cp), hdi = (float)(-wd * sp);
-        yr += xv * hr; yi += xv * hi; dr += xv * hdr; di += xv * hdi;
+      const float xv = xn;
+      idx += 32;
+      xn = (t + 32 < nh && idx >= 0 && idx < P.nx) ? x[idx] : 0.f;    // next tap's sample, one step ahead of its use
+      const float w = 0.5f + 0.5f * (float)cw, wd = wdk * (float)sw;
+      const float xw = xv * w, xd = xv * wd;
+#pragma unroll
+      for(int j = 0; j < 3; j ++) {
+        const float c = (float)cp[j], s = (float)sp[j];
+        yr[j] = fmaf(xw, c, yr[j]); yi[j] = fmaf(-xw, s, yi[j]);
+        dr[j] = fmaf(xd, c, dr[j]); di[j] = fmaf(-xd, s, di[j]);
+        const double t2 = cp[j] * cps[j] - sp[j] * sps[j]; sp[j] = sp[j] * cps[j] + cp[j] * sps[j]; cp[j] = t2;
       }
-      double t1 = cw * cws - sw * sws; sw = sw * cws + cw * sws; cw = t1;
-      double t2 = cp * cps - sp * sps; sp = sp * cps + cp * sps; cp = t2;
+      const double t1 = cw * cws - sw * sws; sw = sw * cws + cw * sws; cw = t1;
     }
   }
-  for(int o = 16; o > 0; o >>= 1) {
-    yr += __shfl_xor_sync(0xffffffffu, yr, o); yi += __shfl_xor_sync(0xffffffffu, yi, o);
-    dr += __shfl_xor_sync(0xffffffffu, dr, o); di += __shfl_xor_sync(0xffffffffu, di, o);
-  }
-  if(lane == 0) {
-    double den = yr * yr + yi * yi;
-    float est = fc;
-    if(! (den < 1e-30)) est = (float)((double)fc - ((di * yr - dr * yi) / den) / (2.0 * LLSM_PI));
-    float fj = est / (float)j;                          // dsputils.c:81
-    float diff = fj - fres;
-    s_f[warp] = fj;
-    s_ok[warp] = fabs((double)diff) < (double)f0 * 0.1 / (double)P.fs;   // dsputils.c:82
-  }
-  __syncthreads();
-  if(threadIdx.x == 0) {
-    float favg = 0; int n = 0;
-    for(int q = 0; q < 3; q ++) if(s_ok[q]) { favg += s_f[q]; n ++; }
-    if(n > 0) {
-      favg = favg / (float)n;
-      P.f0[(size_t)b * P.nfrm + i] = favg * P.fs;       // dsputils.c:89-92
+  // lane sums -> warp sums in double; lane j then finishes harmonic j + 1
+  double myr = 0, myi = 0, mdr = 0, mdi = 0;
+#pragma unroll
+  for(int j = 0; j < 3; j ++) {
+    double a = (double)yr[j], bq = (double)yi[j], c = (double)dr[j], d = (double)di[j];
+    for(int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o); bq += __shfl_xor_sync(0xffffffffu, bq, o);
+      c += __shfl_xor_sync(0xffffffffu, c, o); d += __shfl_xor_sync(0xffffffffu, d, o);
     }
+    if(lane == j) { myr = a; myi = bq; mdr = c; mdi = d; }
+  }
+  float fj = 0.f; int ok = 0;
+  if(lane < 3) {
+    const float fcl = fres * (float)(lane + 1);
+    const double den = myr * myr + myi * myi;
+    float est = fcl;
+    if(! (den < 1e-30)) est = (float)((double)fcl - ((mdi * myr - mdr * myi) / den) / (2.0 * LLSM_PI));
+    fj = est / (float)(lane + 1);                         // dsputils.c:81
+    const float diff = fj - fres;
+    ok = fabs((double)diff) < (double)f0 * 0.1 / (double)P.fs;       // dsputils.c:82
+  }
+  float favg = 0; int n = 0;
+#pragma unroll
+  for(int q = 0; q < 3; q ++) {                           // same order as the reference's loop over harmonics
+    const float fq = __shfl_sync(0xffffffffu, fj, q); const int oq = __shfl_sync(0xffffffffu, ok, q);
+    if(oq) { favg += fq; n ++; }
+  }
+  if(lane == 0 && n > 0) {
+    favg = favg / (float)n;
+    P.f0[(size_t)b * P.nfrm + i] = favg * P.fs;           // dsputils.c:89-92
   }
 }
 
@@ -498,6 +517,12 @@ static inline size_t harm_mma_smem(int cap, int maxnhar) {
   return (size_t)((cap + 3) & ~1) * 4 + HM_THREADS * 8 + (size_t)prow * HM_ROW * 8 * 2 + (size_t)maxnhar * 8 + 16;
 }
 
+static inline double mma_min_f0() {
+  static double v = -1;
+  if(v < 0) { const char* e = getenv("LLSM_MMA_MIN_F0"); v = e ? atof(e) : 80.0; if(! (v >= 20.0)) v = 20.0; }
+  return v;
+}
+
 static inline int dft_variant() {
   static int v = -1;
   if(v < 0) { const char* e = getenv("LLSM_DFT_VARIANT"); v = e ? atoi(e) : 1; }
@@ -513,14 +538,14 @@ static inline int dft_variant() {
 // a fixed order. NC = channel capacity, KW = harmonic capacity of the instance.
 // ------------------------------------------------------------------------------------------
 #define ED_THREADS 128
+#define ED_STRIDE (ED_THREADS + 4)          // row stride of the reduction scratch: conflict-free for both access patterns
 
 template <int NC, int KW>
 __global__ void __launch_bounds__(ED_THREADS) envelope_dft_kernel(HarmDftParams P) {
   LLSM_DYN_SMEM(smem);
-  float* wv = (float*)smem;                                          // [max_half + 2] window, w(half +- n)
-  double* red = (double*)(wv + ((P.max_half + 2 + 1) & ~1));         // [ED_THREADS]
-  float* part = (float*)(red + ED_THREADS);                          // [2 * NC * KW][ED_THREADS + 1]
-  float2* zst = (float2*)(part + 2 * NC * KW * (ED_THREADS + 1));   // [KW] 128-sample rotation per harmonic (8-byte aligned)
+  double* red = (double*)smem;                                       // [ED_THREADS]
+  float* part = (float*)(red + ED_THREADS);                          // [2 * NC * KW][ED_STRIDE]
+  float2* zst = (float2*)(part + 2 * NC * KW * ED_STRIDE);           // [KW] 128-sample rotation per harmonic
   const int i = blockIdx.x, b = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nf = P.nfrm_utt ? P.nfrm_utt[b] : P.nfrm;
@@ -560,32 +585,17 @@ __global__ void __launch_bounds__(ED_THREADS) envelope_dft_kernel(HarmDftParams 
   const int ws = ana_winsize(P.fs, f0, P.rel_winsize);
   const int nh = ana_nhar(P.fs, f0, P.maxnhar);
   const int half = ws >> 1;
-  if(half > P.max_half) { if(tid < nsig) P.nhar_out[f0idx * nsig + tid] = -1; return; }
+  if(half > P.max_half) { if(tid < nsig) P.nhar_out[f0idx * nsig + tid] = -1; return; }   // same limit as the main pass
 
-  // ---- Blackman window and its sum (see harmonic_dft_kernel)
-  double wsum = 0;
-  {
-    double cs, sn, cstep, sstep;
-    sincospi(2.0 * (double)tid / (double)ws, &sn, &cs);
-    sincospi(2.0 * (double)ED_THREADS / (double)ws, &sstep, &cstep);
-    for(int n = tid; n <= half; n += ED_THREADS) {
-      const float w = (float)(0.42 + 0.5 * cs + 0.08 * (2.0 * cs * cs - 1.0));
-      wv[n] = w;
-      if(n < half) wsum += w;
-      if(n >= 1) wsum += w;
-      const double c2 = cs * cstep - sn * sstep;
-      sn = sn * cstep + cs * sstep; cs = c2;
-    }
-  }
-  red[tid] = wsum;
   const float omega0 = (float)(2.0 * LLSM_PI * (double)f0 / (double)P.fs);   // czt step (FP_TYPE arg)
   const double nu = (double)omega0 / (2.0 * LLSM_PI);                        // turns per sample
   if(tid < KW) zst[tid] = unit_phasor_turns((double)(tid + 1) * nu * (double)ED_THREADS);
   __syncthreads();
-  for(int o = ED_THREADS >> 1; o > 0; o >>= 1) { if(tid < o) red[tid] += red[tid + o]; __syncthreads(); }
-  const float winsum = (float)red[0];
 
-  // ---- the sums over the window: symmetric / antisymmetric sample pairs (x+ + x-, x+ - x-) against cos / sin
+  // ---- one pass over the sample pairs n = tid, tid + 128, ... of the window (ws is even, so the periodic Blackman
+  //      window is symmetric about m = half: w(half +- n) = 0.42 + 0.5 cos(2 pi n / ws) + 0.08 cos(4 pi n / ws), advanced
+  //      by a fixed rotation in double and used in the same iteration): symmetric / antisymmetric pairs
+  //      (x+ + x-, x+ - x-) against cos / sin of every harmonic; the window sum rides along
   const int npair = half + 1;
   float re[NC][KW], im[NC][KW];
   float2 w[KW], z[KW];
@@ -595,26 +605,38 @@ __global__ void __launch_bounds__(ED_THREADS) envelope_dft_kernel(HarmDftParams 
 #pragma unroll
     for(int c = 0; c < NC; c ++) { re[c][k] = 0.f; im[c][k] = 0.f; }
   }
+  double wsum = 0, cs, sn, cstep, sstep;
+  sincospi(2.0 * (double)tid / (double)ws, &sn, &cs);
+  sincospi(2.0 * (double)ED_THREADS / (double)ws, &sstep, &cstep);
+  auto load_pairs = [&](int n, float (&xp)[NC], float (&xm)[NC]) {
+    const int ip = center + n, im_ = center - n;
+    const bool okp = n < half && ip >= 0 && ip < P.nx, okm = n >= 1 && n < npair && im_ >= 0 && im_ < P.nx;
+#pragma unroll
+    for(int c = 0; c < NC; c ++) {
+      const float* x = x0 + (size_t)c * P.xstride;
+      xp[c] = (c < nsig && okp) ? x[ip] : 0.f;
+      xm[c] = (c < nsig && okm) ? x[im_] : 0.f;
+    }
+  };
+  float xpn[NC], xmn[NC];
+  load_pairs(tid, xpn, xmn);
   int step = 0;
   for(int n = tid; n < npair; n += ED_THREADS, step ++) {
+    float xp[NC], xm[NC];
+#pragma unroll
+    for(int c = 0; c < NC; c ++) { xp[c] = xpn[c]; xm[c] = xmn[c]; }
+    if(n + ED_THREADS < npair) load_pairs(n + ED_THREADS, xpn, xmn);       // one step ahead of its use
     if((step & 7) == 0) {
 #pragma unroll
       for(int k = 0; k < KW; k ++) if(k < nh) w[k] = unit_phasor_turns((double)(k + 1) * nu * (double)n);
     }
-    const float wn = wv[n];
-    const int ip = center + n, im_ = center - n;
-    const bool okp = n < half && ip >= 0 && ip < P.nx, okm = n >= 1 && im_ >= 0 && im_ < P.nx;
+    const float wn = (float)(0.42 + 0.5 * cs + 0.08 * (2.0 * cs * cs - 1.0));
+    if(n < half) wsum += wn;                                          // m = half + n
+    if(n >= 1) wsum += wn;                                            // m = half - n
+    { const double c2 = cs * cstep - sn * sstep; sn = sn * cstep + cs * sstep; cs = c2; }
     float e[NC], o[NC];
 #pragma unroll
-    for(int c = 0; c < NC; c ++) {
-      float xp = 0.f, xm = 0.f;
-      if(c < nsig) {
-        const float* x = x0 + (size_t)c * P.xstride;
-        if(okp) xp = wn * x[ip];
-        if(okm) xm = wn * x[im_];
-      }
-      e[c] = xp + xm; o[c] = xp - xm;
-    }
+    for(int c = 0; c < NC; c ++) { const float a = wn * xp[c], d = wn * xm[c]; e[c] = a + d; o[c] = a - d; }
 #pragma unroll
     for(int k = 0; k < KW; k ++) if(k < nh) {
 #pragma unroll
@@ -625,35 +647,38 @@ __global__ void __launch_bounds__(ED_THREADS) envelope_dft_kernel(HarmDftParams 
       w[k] = cmul(w[k], z[k]);
     }
   }
-  // ---- fixed-order reduction over the 128 threads: value v = (c, k, re | im) lives in row v of `part`
+  // ---- fixed-order reductions over the 128 threads: the window sum (double), then value v = (c, k, re | im) in row v
+  red[tid] = wsum;
 #pragma unroll
   for(int c = 0; c < NC; c ++)
 #pragma unroll
     for(int k = 0; k < KW; k ++) {
-      part[(2 * (c * KW + k)) * (ED_THREADS + 1) + tid] = re[c][k];
-      part[(2 * (c * KW + k) + 1) * (ED_THREADS + 1) + tid] = im[c][k];
+      part[(2 * (c * KW + k)) * ED_STRIDE + tid] = re[c][k];
+      part[(2 * (c * KW + k) + 1) * ED_STRIDE + tid] = im[c][k];
     }
   __syncthreads();
-  // thread t sums a quarter of row t / 4 (rows beyond 32 in a second round), then two shuffles finish the row
+  for(int o = ED_THREADS >> 1; o > 0; o >>= 1) { if(tid < o) red[tid] += red[tid + o]; __syncthreads(); }
+  const float winsum = (float)red[0];                                 // FP_TYPE winsum = sumfp(w, nx)
+  // thread t sums every fourth element of row t / 4 (rows beyond 32 in further rounds), two shuffles finish the row
   for(int r0 = 0; r0 < 2 * NC * KW; r0 += ED_THREADS / 4) {
     const int r = r0 + (tid >> 2), q = tid & 3;
     float acc = 0.f;
     if(r < 2 * NC * KW) {
-      const float* row = part + r * (ED_THREADS + 1) + q * (ED_THREADS / 4);
+      const float* row = part + r * ED_STRIDE + q;
 #pragma unroll 8
-      for(int u = 0; u < ED_THREADS / 4; u ++) acc += row[u];
+      for(int u = 0; u < ED_THREADS / 4; u ++) acc += row[4 * u];
     }
     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
     acc += __shfl_xor_sync(0xffffffffu, acc, 2);
     __syncthreads();
-    if(r < 2 * NC * KW && q == 0) part[r * (ED_THREADS + 1)] = acc;          // row total in column 0
+    if(r < 2 * NC * KW && q == 0) part[r * ED_STRIDE] = acc;          // row total in column 0
   }
   __syncthreads();
   for(int e2 = tid; e2 < nsig * P.maxnhar; e2 += ED_THREADS) {
     const int c = e2 / P.maxnhar, k = e2 - c * P.maxnhar;
     const size_t at = (f0idx * nsig + c) * P.maxnhar + k;
     if(k < nh && k < KW && c < NC) {
-      const float sre = part[(2 * (c * KW + k)) * (ED_THREADS + 1)], sim = part[(2 * (c * KW + k) + 1) * (ED_THREADS + 1)];
+      const float sre = part[(2 * (c * KW + k)) * ED_STRIDE], sim = part[(2 * (c * KW + k) + 1) * ED_STRIDE];
       harmonic_finish(sre, sim, k, half, f0, P.fs, omega0, winsum, &P.ampl[at], &P.phse[at]);
     } else { P.ampl[at] = 0; P.phse[at] = 0; }
   }
@@ -662,7 +687,8 @@ __global__ void __launch_bounds__(ED_THREADS) envelope_dft_kernel(HarmDftParams 
 
 template <int NC, int KW>
 static inline size_t env_dft_smem(int max_half) {
-  return (size_t)((max_half + 3) & ~1) * 4 + ED_THREADS * 8 + (size_t)(2 * NC * KW * (ED_THREADS + 1)) * 4 + KW * 8 + 32;
+  (void)max_half;
+  return (size_t)ED_THREADS * 8 + (size_t)(2 * NC * KW * ED_STRIDE) * 4 + KW * 8 + 32;
 }
 
 static inline size_t harm_dft_smem(int max_half, int ng) {
@@ -672,8 +698,9 @@ static inline size_t harm_dft_smem(int max_half, int ng) {
 static inline int launch_harmonic_dft(const HarmDftParams& Pin, int nutt, cudaStream_t st) {
   HarmDftParams P = Pin;
   if(P.nsig == 1 && P.edc == nullptr && dft_variant() == 1 && P.maxnhar > HD_KW) {
-    // tensor-core kernel for windows up to 4 periods of 50 Hz; the direct kernel picks up longer ones
-    int cap = (int)ceil((double)P.fs / 50.0 * (double)P.rel_winsize / 4.0 * 2.0) + 4;
+    // tensor-core kernel for windows up to 4 periods of 80 Hz (its staging buffers are sized by that capacity and decide
+    // how many CTAs share an SM: 8 instead of 5 at 50 Hz); the direct kernel picks up the rare longer windows
+    int cap = (int)ceil((double)P.fs / mma_min_f0() * (double)P.rel_winsize / 4.0 * 2.0) + 4;
     if(cap > P.max_half) cap = P.max_half;
     P.mma_cap_half = cap;
     size_t smem = harm_mma_smem(cap, P.maxnhar);

@@ -238,7 +238,7 @@ static inline int bank_variant() {
 
 static inline int residual_tc_enabled() {
   static int v = -1;
-  if(v < 0) { const char* e = getenv("LLSM_RESIDUAL_TC"); v = e ? atoi(e) : 1; }
+  if(v < 0) { const char* e = getenv("LLSM_RESIDUAL_TC"); v = e ? atoi(e) : 0; }
   return v;
 }
 
@@ -246,9 +246,11 @@ static inline int residual_tc_enabled() {
 static inline int launch_hm_bank(BankParams P, int nutt, int nfrm_max, cudaStream_t st) {
 #ifndef LLSM_EMU
   // many harmonics: operand generation + tcgen05 GEMM (kernels_bank_tc.cuh, ~1e-7 of the frame amplitude, i.e. ~5e-9
-  // absolute on speech-level frames: also enough for the analysis residual x - x_sin, whose parity bar is 1e-6 RMS;
-  // LLSM_RESIDUAL_TC=0 sends the residual (options == NULL) back to the direct summation); few harmonics or long
-  // windows: direct FP32 summation below
+  // absolute on speech-level frames). The analysis residual (options == NULL) stays on the direct summation by
+  // default: x - x_sin is a small difference of large numbers, and although 5e-9 passes the residual's own 1e-6 RMS bar
+  // it is 1e-5 of the residual, which the sub-band envelope phases of the peak-picking method feel (measured on B200:
+  // 1.8e-4 rad on envelope harmonics of 5e-5 amplitude). LLSM_RESIDUAL_TC=1 trades that for 1.3 ms per 409 600 frames.
+  // Few harmonics or long windows: direct FP32 summation below
   if(bank_tc_enabled() && (P.has_options || residual_tc_enabled()) && P.maxnhar >= 24 &&
      launch_hm_bank_tc(P, nutt, nfrm_max, st) == 0) return 0;
 #endif
