@@ -178,6 +178,23 @@ int llsm_b200_anasynth_host(llsm_b200_ctx* ctx, const llsm_b200_conf* conf, cons
   int phase_ops, const llsm_b200_output* out);
 
 
+/* ---- per-frame routines of the reference's dsputils.h that its tests call directly (test/test-dsputils.c:80,
+        test/test-harmonic.c:40-43), as batch entries ----
+   llsm_b200_harmonic_analysis    llsm_harmonic_analysis (dsputils.c:175-228): nhar / ampl / phse of x at the frame
+                                  centres round(i thop fs) for a KNOWN f0 [B][F] (no refinement, no noise model);
+                                  opt->hm_method 0 = peak picking, 1 = CZT. Device pointers; _host: host pointers.
+   llsm_b200_refine_f0_host       llsm_refine_f0 (dsputils.c:72-94): f0 [B][F] refined in place (host pointers)
+   llsm_b200_harmonic_frames_host llsm_synthesize_harmonic_frame (iczt = 0) / _iczt (iczt = 1) (dsputils.c:328-351) for
+                                  nfrm frames: unwindowed y [nfrm][nx], f0n in cycles per sample (host pointers) */
+int llsm_b200_harmonic_analysis(llsm_b200_ctx* ctx, const llsm_b200_conf* conf, const llsm_b200_aoptions* opt,
+  const float* x, int nx, int xstride, const float* f0, int* nhar, float* ampl, float* phse);
+int llsm_b200_harmonic_analysis_host(llsm_b200_ctx* ctx, const llsm_b200_conf* conf, const llsm_b200_aoptions* opt,
+  const float* x, int nx, int xstride, const float* f0, int* nhar, float* ampl, float* phse);
+int llsm_b200_refine_f0_host(llsm_b200_ctx* ctx, const llsm_b200_conf* conf, const float* x, int nx, int xstride, float* f0);
+int llsm_b200_harmonic_frames_host(llsm_b200_ctx* ctx, int nfrm, int maxnhar, const int* nhar, const float* f0n,
+  const float* ampl, const float* phse, int nx, int iczt, float* y);
+
+
 /* ---- layer-1 members (llsm.h:105-108): RD, VTMAGN, VSPHSE per frame, flat ----
      rd      [B][F]            Rd glottal parameter (every frame, smoothed track)
      vtmagn  [B][F][nspec]     vocal-tract magnitude response, dB (voiced frames)

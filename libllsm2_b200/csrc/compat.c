@@ -1008,4 +1008,75 @@ llsm_chunk* llsm_analyze(llsm_aoptions* options, FP_TYPE* x, int nx, FP_TYPE fs,
   return ret;
 }
 
+/* ------------------------------------------------------------------ dsputils.h ------------------- */
+#include "../../include/dsputils.h"
+
+static void dsp_conf(llsm_b200_conf* c, int nfrm, int maxnhar, float fs, float thop) {
+  memset(c, 0, sizeof(*c));
+  c -> nutt = 1; c -> nfrm = nfrm; c -> maxnhar = maxnhar > 0 ? maxnhar : 1; c -> maxnhar_e = 0; c -> npsd = 2;
+  c -> nchannel = 1; c -> fs = fs; c -> thop = thop; c -> lip_radius = 1.5f;
+}
+
+void llsm_refine_f0(FP_TYPE* x, int nx, FP_TYPE fs, FP_TYPE* f0, int nfrm, FP_TYPE thop) {
+  g_compat_err[0] = 0;
+  if(x == NULL || f0 == NULL || nx < 1 || nfrm < 1) return;
+  llsm_b200_ctx* ctx = shared_ctx();
+  if(ctx == NULL) return;
+  llsm_b200_conf c; dsp_conf(& c, nfrm, 1, fs, thop);
+  if(llsm_b200_refine_f0_host(ctx, & c, x, nx, nx, f0) != 0) set_err(llsm_b200_last_error());
+}
+
+int llsm_get_fftsize(FP_TYPE* f0, int nfrm, FP_TYPE fs, FP_TYPE rel_winsize) {   /* dsputils.c:318-326 */
+  FP_TYPE minf0 = 1000;
+  for(int i = 0; i < nfrm; i ++) if(f0[i] > 0 && f0[i] < minf0) minf0 = f0[i];
+  FP_TYPE t = fs / minf0; t = t * rel_winsize; t = t / 2;
+  int max_winsize = (int)round((double)t) * 2;
+  int n = 1;
+  while(n < max_winsize) n *= 2;
+  return n;
+}
+
+void llsm_harmonic_analysis(FP_TYPE* x, int nx, FP_TYPE fs, FP_TYPE* f0, int nfrm, FP_TYPE thop, FP_TYPE rel_winsize,
+  int maxnhar, int method, int* dst_nhar, FP_TYPE** dst_ampl, FP_TYPE** dst_phse) {
+  g_compat_err[0] = 0;
+  if(x == NULL || f0 == NULL || nx < 1 || nfrm < 1 || maxnhar < 1 || dst_nhar == NULL || dst_ampl == NULL || dst_phse == NULL) return;
+  llsm_b200_ctx* ctx = shared_ctx();
+  if(ctx == NULL) return;
+  llsm_b200_conf c; dsp_conf(& c, nfrm, maxnhar, fs, thop);
+  llsm_b200_aoptions ao = {0, method == LLSM_AOPTION_HMPP ? 0 : 1, rel_winsize};
+  int* nhar = calloc((size_t)nfrm, sizeof(int));
+  float* ampl = calloc((size_t)nfrm * maxnhar, sizeof(float));
+  float* phse = calloc((size_t)nfrm * maxnhar, sizeof(float));
+  if(llsm_b200_harmonic_analysis_host(ctx, & c, & ao, x, nx, nx, f0, nhar, ampl, phse) == 0) {
+    for(int i = 0; i < nfrm; i ++) {
+      if(! (f0[i] > 0) || nhar[i] < 0) continue;           /* unvoiced frames are left untouched (dsputils.c:186-192) */
+      dst_nhar[i] = nhar[i];
+      dst_ampl[i] = calloc(nhar[i] > 0 ? nhar[i] : 1, sizeof(FP_TYPE));
+      dst_phse[i] = calloc(nhar[i] > 0 ? nhar[i] : 1, sizeof(FP_TYPE));
+      memcpy(dst_ampl[i], ampl + (size_t)i * maxnhar, sizeof(FP_TYPE) * (size_t)nhar[i]);
+      memcpy(dst_phse[i], phse + (size_t)i * maxnhar, sizeof(FP_TYPE) * (size_t)nhar[i]);
+    }
+  } else set_err(llsm_b200_last_error());
+  free(nhar); free(ampl); free(phse);
+}
+
+static FP_TYPE* harmonic_frame(FP_TYPE* ampl, FP_TYPE* phse, int nhar, FP_TYPE f0, int nx, int iczt) {
+  g_compat_err[0] = 0;
+  if(nx < 1 || nhar < 0 || (nhar > 0 && (ampl == NULL || phse == NULL))) return NULL;
+  FP_TYPE* y = calloc((size_t)nx, sizeof(FP_TYPE));
+  if(nhar == 0) return y;
+  llsm_b200_ctx* ctx = shared_ctx();
+  if(ctx == NULL) { free(y); return NULL; }
+  if(llsm_b200_harmonic_frames_host(ctx, 1, nhar, & nhar, & f0, ampl, phse, nx, iczt, y) != 0) {
+    set_err(llsm_b200_last_error()); free(y); return NULL;
+  }
+  return y;
+}
+FP_TYPE* llsm_synthesize_harmonic_frame(FP_TYPE* ampl, FP_TYPE* phse, int nhar, FP_TYPE f0, int nx) {
+  return harmonic_frame(ampl, phse, nhar, f0, nx, 0);
+}
+FP_TYPE* llsm_synthesize_harmonic_frame_iczt(FP_TYPE* ampl, FP_TYPE* phse, int nhar, FP_TYPE f0, int nx) {
+  return harmonic_frame(ampl, phse, nhar, f0, nx, 1);
+}
+
 #include "compat_rt.inc"

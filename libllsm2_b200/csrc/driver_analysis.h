@@ -124,6 +124,50 @@ struct AnaScratch {
   void release() { nfft_utt.release(); x_sin.release(); x_res.release(); ce.release(); env.release(); lpsd.release(); res.release(); filt.release(); pvar.release(); }
 };
 
+// one FFT size per utterance for the peak-picking method (llsm_get_fftsize, dsputils.c:318-326)
+static inline int run_utt_fftsize(AnaScratch& sc, const llsm_b200_conf& conf, const llsm_b200_aoptions& opt,
+  const float* f0, const int* nfrm_utt, cudaStream_t st, LaunchCounter* lc) {
+  if(sc.nfft_utt.reserve((size_t)conf.nutt * 4) != 0) return LLSM_B200_ENOMEM;
+  MinF0Params M; memset(&M, 0, sizeof(M));
+  M.nfrm = conf.nfrm; M.nfrm_utt = nfrm_utt; M.f0 = f0; M.fs = conf.fs; M.rel_winsize = opt.rel_winsize;
+  M.nfft_utt = sc.nfft_utt.as<int>();
+  LLSM_LAUNCH(utt_fftsize_kernel, dim3(conf.nutt), dim3(128), 0, st, M);
+  if(lc) lc->n ++;
+  return 0;
+}
+
+// llsm_harmonic_analysis (dsputils.c:175-228) of nsig signals per utterance ([B][nsig][sstride]) at the frame centres
+// of the plan: CZT (direct DFT at the harmonics) or peak picking; optionally the short-time means (edc_o).
+static inline int run_harmonic_pass(const SynthPlanDev& sp, AnaPlanDev& ap, AnaScratch& sc, const llsm_b200_conf& conf,
+  const llsm_b200_aoptions& opt, const float* f0, const int* nfrm_utt, const float* sig, int nsig, int nx, int sstride,
+  int maxnhar, int* nhar_o, float* ampl_o, float* phse_o, float* edc_o, bool prep_fftsize, cudaStream_t st,
+  LaunchCounter* lc) {
+  const int B = conf.nutt, F = conf.nfrm;
+  const int max_half = (int)ceil((double)conf.fs / 20.0 * (double)opt.rel_winsize / 4.0 * 2.0) + 4;
+  if(opt.hm_method == 1) {
+    HarmDftParams H; memset(&H, 0, sizeof(H));
+    H.nfrm = F; H.nfrm_utt = nfrm_utt; H.sig = sig; H.nsig = nsig; H.nx = nx; H.xstride = sstride;
+    H.f0 = f0; H.center = sp.hm_base; H.fs = conf.fs; H.rel_winsize = opt.rel_winsize;
+    H.maxnhar = maxnhar; H.nhar_out = nhar_o; H.ampl = ampl_o; H.phse = phse_o; H.max_half = max_half;
+    H.edc = edc_o; H.thop = conf.thop;
+    if(launch_harmonic_dft(H, B, st) != 0) return LLSM_B200_ERANGE;
+  } else {
+    if(prep_fftsize) { int rc = run_utt_fftsize(sc, conf, opt, f0, nfrm_utt, st, lc); if(rc) return rc; }
+    HarmPpParams H; memset(&H, 0, sizeof(H));
+    H.nfrm = F; H.nfrm_utt = nfrm_utt; H.sig = sig; H.nsig = nsig; H.nx = nx; H.xstride = sstride;
+    H.f0 = f0; H.center = sp.hm_base; H.nfft_utt = sc.nfft_utt.as<int>(); H.fs = conf.fs;
+    H.rel_winsize = opt.rel_winsize; H.std_norm = ap.h.std_norm_blackman; H.maxnhar = maxnhar;
+    H.nhar_out = nhar_o; H.ampl = ampl_o; H.phse = phse_o; H.tw = ap.tw_pp; H.ntw = 8192; H.max_nfft = 8192;
+    size_t smem = (size_t)H.max_nfft * 16 + 16;
+#ifndef LLSM_EMU
+    cudaFuncSetAttribute(harmonic_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#endif
+    LLSM_LAUNCH(harmonic_pp_kernel, dim3(F, B * nsig), dim3(HP_THREADS), smem, st, H);
+  }
+  if(lc) lc->n ++;
+  return 0;
+}
+
 // x: [B][xstride] device; fr: device output arrays; x_res_out optional [B][xstride]
 static inline int run_analyze_l0(const SynthPlanDev& sp, AnaPlanDev& ap, AnaScratch& sc,
   const llsm_b200_conf& conf, const llsm_b200_aoptions& opt, const float* x, int nx, int xstride,
@@ -155,39 +199,12 @@ static inline int run_analyze_l0(const SynthPlanDev& sp, AnaPlanDev& ap, AnaScra
   }
 
   // 2. harmonic analysis of x (dsputils.c:175-228)
-  const int max_half = (int)ceil((double)conf.fs / 20.0 * (double)opt.rel_winsize / 4.0 * 2.0) + 4;
   auto harmonic_pass = [&](const float* sig, int nsig, int sstride, int maxnhar, int* nhar_o, float* ampl_o, float* phse_o,
                            float* edc_o) -> int {
-    if(opt.hm_method == 1) {
-      HarmDftParams H; memset(&H, 0, sizeof(H));
-      H.nfrm = F; H.nfrm_utt = nfrm_utt; H.sig = sig; H.nsig = nsig; H.nx = nx; H.xstride = sstride;
-      H.f0 = fr.f0; H.center = sp.hm_base; H.fs = conf.fs; H.rel_winsize = opt.rel_winsize;
-      H.maxnhar = maxnhar; H.nhar_out = nhar_o; H.ampl = ampl_o; H.phse = phse_o; H.max_half = max_half;
-      H.edc = edc_o; H.thop = conf.thop;
-      if(launch_harmonic_dft(H, B, st) != 0) return LLSM_B200_ERANGE;
-    } else {
-      HarmPpParams H; memset(&H, 0, sizeof(H));
-      H.nfrm = F; H.nfrm_utt = nfrm_utt; H.sig = sig; H.nsig = nsig; H.nx = nx; H.xstride = sstride;
-      H.f0 = fr.f0; H.center = sp.hm_base; H.nfft_utt = sc.nfft_utt.as<int>(); H.fs = conf.fs;
-      H.rel_winsize = opt.rel_winsize; H.std_norm = h.std_norm_blackman; H.maxnhar = maxnhar;
-      H.nhar_out = nhar_o; H.ampl = ampl_o; H.phse = phse_o; H.tw = ap.tw_pp; H.ntw = 8192; H.max_nfft = 8192;
-      size_t smem = (size_t)H.max_nfft * 16 + 16;
-#ifndef LLSM_EMU
-      cudaFuncSetAttribute(harmonic_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-#endif
-      LLSM_LAUNCH(harmonic_pp_kernel, dim3(F, B * nsig), dim3(HP_THREADS), smem, st, H);
-    }
-    if(lc) lc->n ++;
-    return 0;
+    return run_harmonic_pass(sp, ap, sc, conf, opt, fr.f0, nfrm_utt, sig, nsig, nx, sstride, maxnhar, nhar_o, ampl_o,
+      phse_o, edc_o, false, st, lc);
   };
-  if(opt.hm_method == 0) {                       // one FFT size per utterance (dsputils.c:318-326)
-    if(sc.nfft_utt.reserve((size_t)B * 4) != 0) return LLSM_B200_ENOMEM;
-    MinF0Params M; memset(&M, 0, sizeof(M));
-    M.nfrm = F; M.nfrm_utt = nfrm_utt; M.f0 = fr.f0; M.fs = conf.fs; M.rel_winsize = opt.rel_winsize;
-    M.nfft_utt = sc.nfft_utt.as<int>();
-    LLSM_LAUNCH(utt_fftsize_kernel, dim3(B), dim3(128), 0, st, M);
-    if(lc) lc->n ++;
-  }
+  if(opt.hm_method == 0) { int rc = run_utt_fftsize(sc, conf, opt, fr.f0, nfrm_utt, st, lc); if(rc) return rc; }
   { int rc = harmonic_pass(x, 1, xstride, conf.maxnhar, fr.nhar, fr.ampl, fr.phse, nullptr); if(rc) return rc; }
   lc_mark(lc, st, opt.hm_method == 1 ? "harmonic_czt" : "harmonic_pp");
 

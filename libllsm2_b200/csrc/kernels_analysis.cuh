@@ -1183,3 +1183,43 @@ __global__ void __launch_bounds__(HP_THREADS) harmonic_pp_kernel(HarmPpParams P)
   for(int k = nh + tid; k < P.maxnhar; k += nth) { P.ampl[fidx * P.maxnhar + k] = 0; P.phse[fidx * P.maxnhar + k] = 0; }
   if(tid == 0) P.nhar_out[fidx] = nh;
 }
+
+// ------------------------------------------------------------------------------------------
+// Unwindowed harmonic frames: llsm_synthesize_harmonic_frame (dsputils.c:328-336, gensins) and
+// llsm_synthesize_harmonic_frame_iczt (:338-351), the per-frame routines dsputils.h exports and the reference's
+// tests call directly (test/test-harmonic.c:40-43). y[f][j] = sum_k a_k cos(2 pi nu (k + 1)(j - nx / 2) + phi_k),
+// j < nx. iczt != 0 reproduces that branch's two quirks: the fundamental is the FLOAT-rounded omega0 = 2 pi f0 and
+// harmonics with index >= nx - 1 are dropped (the transform only has nx bins). One CTA per frame, a thread per
+// sample; phases are reduced in double (they reach 1e3 rad). A convenience entry, not a hot path (the synthesis
+// loops use the harmonic-bank kernels).
+// ------------------------------------------------------------------------------------------
+struct HarmFrameParams {
+  int nfrm, maxnhar, nx, iczt;
+  const int* nhar; const float* f0n;          // [nfrm] harmonics in use, fundamental in cycles per sample
+  const float* ampl; const float* phse;       // [nfrm][maxnhar]
+  float* y;                                   // [nfrm][nx]
+};
+
+__global__ void __launch_bounds__(256) harmonic_frame_kernel(HarmFrameParams P) {
+  const int f = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if(j >= P.nx) return;
+  int nh = P.nhar[f];
+  if(nh > P.maxnhar) nh = P.maxnhar;
+  const float f0 = P.f0n[f];
+  double nu = (double)f0;
+  if(P.iczt) {
+    const float omega0 = (float)(2.0 * LLSM_PI * (double)f0);
+    nu = (double)omega0 / (2.0 * LLSM_PI);
+    if(nh > P.nx - 1) nh = P.nx - 1;
+  }
+  const double t = (double)(j - P.nx / 2);
+  const float* a = P.ampl + (size_t)f * P.maxnhar; const float* ph = P.phse + (size_t)f * P.maxnhar;
+  double acc = 0;
+  for(int k = 0; k < nh; k ++) {
+    double u = nu * (double)(k + 1) * t;
+    u -= rint(u);
+    acc += (double)a[k] * cos(2.0 * LLSM_PI * u + (double)ph[k]);
+  }
+  P.y[(size_t)f * P.nx + j] = (float)acc;
+}

@@ -270,3 +270,262 @@ def test_coder_dropin(libs):
         assert np.array_equal(fin, np.isfinite(x)) and np.abs(x[fin] - y[fin]).max() < 5e-2
     for x, y in zip(vs_a, vs_b):
         assert np.abs(S.phase_err(x, y)).max() < 1e-4
+
+
+def _bind_rt(L):
+    L.llsm_create_rtsynth_buffer.restype = C.c_void_p
+    L.llsm_create_rtsynth_buffer.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.llsm_rtsynth_buffer_feed.argtypes = [C.c_void_p, C.c_void_p]
+    L.llsm_rtsynth_buffer_fetch_decomposed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.llsm_rtsynth_buffer_numoutput.argtypes = [C.c_void_p]
+    L.llsm_delete_rtsynth_buffer.argtypes = [C.c_void_p]
+
+
+def test_llsmrt_two_threads_feed_blocks_on_full_ring(libs):
+    """The reference's threading contract (test/test-llsmrt.c:29-63,123-124; llsmrt.c:489-499,523-543): a synthesis
+    thread feeds frames and BLOCKS while the output ring is full, a reading thread polls fetch_decomposed (non-blocking,
+    usleep(10) between misses). The ring holds 600 samples, less than three hops, so the feeder has to wait for the
+    reader over and over. The samples must equal those of a single-threaded run of the same library, and the
+    reference build run the same way must agree with it to the usual bar."""
+    import threading
+    import time
+    fr, conf = S.synth_frames(1, 60, seed=27, nhar=60, maxnhar=60)
+    results = []
+    for L in libs:
+        _bind_rt(L)
+        runs = []
+        for threaded in (False, True):
+            ck = U.build_chunk(L, fr, conf)
+            so = L.llsm_create_soptions(C.c_float(conf.fs))
+            libc.srand(31)
+            cap = 600 if threaded else 8192
+            rt = L.llsm_create_rtsynth_buffer(so, ck.contents.conf, cap)
+            assert rt
+            ys = []
+            if not threaded:
+                p, ap = C.c_float(), C.c_float()
+                for i in range(conf.nfrm):
+                    L.llsm_rtsynth_buffer_feed(rt, ck.contents.frames[i])
+                    while L.llsm_rtsynth_buffer_fetch_decomposed(rt, C.byref(p), C.byref(ap)):
+                        ys.append((p.value, ap.value))
+            else:
+                done = threading.Event()
+                blocked = {"full": 0}
+
+                def feeder():
+                    for i in range(conf.nfrm):
+                        if L.llsm_rtsynth_buffer_numoutput(rt) > cap - 230:
+                            blocked["full"] += 1                         # this feed will have to wait for the reader
+                        L.llsm_rtsynth_buffer_feed(rt, ck.contents.frames[i])
+                    done.set()
+
+                def reader():
+                    p, ap = C.c_float(), C.c_float()
+                    idle = 0
+                    while True:
+                        if L.llsm_rtsynth_buffer_fetch_decomposed(rt, C.byref(p), C.byref(ap)):
+                            ys.append((p.value, ap.value)); idle = 0
+                        elif done.is_set():
+                            idle += 1
+                            if idle > 3:
+                                break
+                        else:
+                            time.sleep(1e-5)
+                t1, t2 = threading.Thread(target=feeder), threading.Thread(target=reader)
+                t1.start(); t2.start()
+                t1.join(timeout=120); t2.join(timeout=120)
+                assert not t1.is_alive() and not t2.is_alive(), "feeder / reader deadlocked"
+                assert blocked["full"] > 5, blocked
+            L.llsm_delete_rtsynth_buffer(rt); L.llsm_delete_soptions(so); L.llsm_delete_chunk(ck)
+            runs.append(np.array(ys, np.float32))
+        assert runs[0].shape == runs[1].shape and np.array_equal(runs[0], runs[1]), "threaded run differs"
+        results.append(runs[1])
+    a, b = results
+    assert a.shape == b.shape and S.rms(b) > 1e-3
+    assert S.rms(a - b) < 1e-4, S.rms(a - b)
+
+
+def test_compat_entries_are_thread_safe(libs):
+    """Every drop-in call goes through one process-wide device context; concurrent callers must not corrupt each
+    other's staging buffers (the reference's functions are reentrant). Two threads run llsm_chunk_tolayer1 +
+    llsm_synthesize(use_l1) on different chunks at the same time, many times; each must reproduce its own
+    single-threaded result bit for bit."""
+    import threading
+    L = libs[0]
+    cases = []
+    for seed, F in ((51, 50), (52, 64)):
+        fr, conf = S.synth_frames(1, F, seed=seed, nhar=70, maxnhar=70)
+        cases.append((fr, conf))
+
+    def run(fr, conf):
+        ck = U.build_chunk(L, fr, conf)
+        L.llsm_chunk_tolayer1(ck, 2048)
+        l1 = _l1_members(L, ck, conf, 1025)
+        so = L.llsm_create_soptions(C.c_float(conf.fs))
+        so.contents.use_l1 = 1
+        o = L.llsm_synthesize(so, ck)
+        assert o
+        ys = U.output_arrays(o)[1]                       # y_sin: deterministic (the noise draws from the shared rand())
+        L.llsm_delete_output(o); L.llsm_delete_soptions(so); L.llsm_delete_chunk(ck)
+        return l1, ys
+
+    base = [run(fr, conf) for fr, conf in cases]
+    errs = []
+
+    def worker(k):
+        try:
+            for _ in range(6):
+                l1, ys = run(*cases[k])
+                for key in ("rd", "vtmagn", "vsphse", "nvs"):
+                    assert np.array_equal(l1[key], base[k][0][key]), key
+                assert np.array_equal(ys, base[k][1])
+        except BaseException as e:                       # noqa: BLE001
+            errs.append((k, repr(e)))
+    ts = [threading.Thread(target=worker, args=(k,)) for k in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=300)
+    assert not errs, errs
+
+
+def _bind_dsp(L):
+    L.llsm_harmonic_analysis.argtypes = [U.fp, C.c_int, C.c_float, U.fp, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int,
+                                         C.POINTER(C.c_int), C.POINTER(U.fp), C.POINTER(U.fp)]
+    L.llsm_harmonic_analysis.restype = None
+    for f in (L.llsm_synthesize_harmonic_frame, L.llsm_synthesize_harmonic_frame_iczt):
+        f.argtypes = [U.fp, U.fp, C.c_int, C.c_float, C.c_int]
+        f.restype = U.fp
+    L.llsm_get_fftsize.argtypes = [U.fp, C.c_int, C.c_float, C.c_float]
+    L.llsm_refine_f0.argtypes = [U.fp, C.c_int, C.c_float, U.fp, C.c_int, C.c_float]
+    L.llsm_refine_f0.restype = None
+
+
+@pytest.mark.parametrize("method", [0, 1])    # LLSM_AOPTION_HMPP, LLSM_AOPTION_HMCZT
+def test_dsputils_harmonic_analysis_dropin(libs, method):
+    """test/test-dsputils.c:44-133 through the exported llsm_harmonic_analysis of both libraries: the three-harmonic
+    chirp, the reference's tolerances (amplitude mean / std error < 0.01, phase-advance error < 0.1 rad) on each, and
+    the two libraries against each other."""
+    import math
+    nx, fs, thop = 100000, 20000.0, 0.005
+    nfrm = int(math.floor(np.float32(nx) / np.float32(fs) / np.float32(thop)))
+    center = np.round(np.arange(nfrm) * np.float32(thop) * np.float32(fs)).astype(int)
+    rate = center.astype(np.float32) / nx
+    f0 = (100 + 100 * rate).astype(np.float32)
+    i = np.arange(nx)
+    ph = np.cumsum((100 + 100 * i / nx) / fs * 2 * 3.1415927)
+    x = np.ascontiguousarray(((i / nx) * np.sin(ph) + 0.5 * np.sin(2 * ph) + 0.25 * np.sin(3 * ph)).astype(np.float32))
+    got = []
+    for L in libs:
+        _bind_dsp(L)
+        nhar = (C.c_int * nfrm)()
+        ampl = (U.fp * nfrm)(); phse = (U.fp * nfrm)()
+        f0c = f0.copy()
+        assert L.llsm_get_fftsize(f0c.ctypes.data_as(U.fp), nfrm, C.c_float(fs), C.c_float(4.0)) == 1024
+        L.llsm_harmonic_analysis(x.ctypes.data_as(U.fp), nx, C.c_float(fs), f0c.ctypes.data_as(U.fp), nfrm, C.c_float(thop),
+                                 C.c_float(4.0), 3, method, nhar, ampl, phse)
+        A = np.zeros((nfrm, 3), np.float32); P = np.zeros((nfrm, 3), np.float32)
+        for t in range(nfrm):
+            assert nhar[t] == 3 and ampl[t] and phse[t]
+            A[t] = np.ctypeslib.as_array(ampl[t], (3,)); P[t] = np.ctypeslib.as_array(phse[t], (3,))
+            libc.free(ampl[t]); libc.free(phse[t])
+        s = slice(5, nfrm - 5)
+        for k, truth in enumerate([rate, 0.5, 0.25]):
+            e = np.zeros(nfrm); e[s] = (A[:, k] - truth)[s]
+            assert abs(e.mean()) < 0.01 and e.std() < 0.01, (k, e.mean(), e.std())
+        pe = np.zeros(nfrm - 1)
+        for t in range(5, nfrm - 5):
+            d = P[t, 0] - (P[t - 1, 0] + f0[t] * 2 * 3.1415927 * thop)
+            pe[t - 1] = (d + math.pi) % (2 * math.pi) - math.pi
+        assert abs(pe.mean()) < 0.1 and pe.std() < 0.1, (pe.mean(), pe.std())
+        got.append((A, P))
+    (Aa, Pa), (Ab, Pb) = got
+    assert np.abs(Aa - Ab).max() < (1e-6 if method == 1 else 1e-4)
+    assert np.abs(S.phase_err(Pa, Pb) * Ab).max() < (1e-6 if method == 1 else 1e-3)
+
+
+def test_dsputils_harmonic_frame_dropin(libs):
+    """test/test-harmonic.c:29-48 through both libraries: 100 harmonics, f0 = 0.01 cycles / sample, 1024 samples; the
+    ICZT and the sinusoid-bank frame must agree (SNR printed by the reference, > 80 dB asserted here) and each must
+    match the reference build's frame."""
+    rng = np.random.default_rng(3)
+    nhar, nx, f0 = 100, 1024, 0.01
+    ampl = np.ascontiguousarray(rng.uniform(0, 1, nhar).astype(np.float32))
+    phse = np.ascontiguousarray(rng.uniform(-np.pi, np.pi, nhar).astype(np.float32))
+    frames = []
+    for L in libs:
+        _bind_dsp(L)
+        out = []
+        for fn in (L.llsm_synthesize_harmonic_frame_iczt, L.llsm_synthesize_harmonic_frame):
+            y = fn(ampl.ctypes.data_as(U.fp), phse.ctypes.data_as(U.fp), nhar, C.c_float(f0), nx)
+            assert y
+            out.append(np.ctypeslib.as_array(y, (nx,)).copy())
+            libc.free(y)
+        snr = 10 * np.log10(np.sum(out[1].astype(np.float64) ** 2) / np.sum((out[0].astype(np.float64) - out[1]) ** 2))
+        assert snr > 80, snr
+        frames.append(out)
+    for a, b in zip(frames[0], frames[1]):
+        assert S.rms(a - b) < 1e-4 * S.rms(b), S.rms(a - b) / S.rms(b)
+    # more harmonics than samples: the ICZT branch drops those beyond the transform length (dsputils.c:341-348)
+    nh2, nx2 = 300, 256
+    a2 = np.ascontiguousarray(rng.uniform(0, 1, nh2).astype(np.float32)); p2 = np.ascontiguousarray(rng.uniform(-3, 3, nh2).astype(np.float32))
+    ys = []
+    for L in libs:
+        y = L.llsm_synthesize_harmonic_frame_iczt(a2.ctypes.data_as(U.fp), p2.ctypes.data_as(U.fp), nh2, C.c_float(0.0015), nx2)
+        ys.append(np.ctypeslib.as_array(y, (nx2,)).copy()); libc.free(y)
+    assert S.rms(ys[0] - ys[1]) < 1e-4 * S.rms(ys[1])
+
+
+def test_dsputils_refine_f0_dropin(libs):
+    fr, conf = S.synth_frames(1, 60, seed=61, nhar=60, maxnhar=60)
+    y, _, _ = S.ref_synthesize(fr, conf, seed=3)
+    x = np.ascontiguousarray(y[0])
+    outs = []
+    for L in libs:
+        _bind_dsp(L)
+        f0 = (fr["f0"][0] * np.float32(1.01)).astype(np.float32)         # start one per cent off
+        L.llsm_refine_f0(x.ctypes.data_as(U.fp), len(x), C.c_float(conf.fs), f0.ctypes.data_as(U.fp), conf.nfrm, C.c_float(conf.thop))
+        outs.append(f0)
+    assert np.abs(outs[0] - outs[1]).max() < 1e-3
+    v = fr["f0"][0] > 0
+    assert np.abs(outs[1][v] - fr["f0"][0][v]).mean() < 0.5            # and it did move towards the true f0
+
+
+def test_llsmrt_attaches_hm_like_the_reference(libs):
+    """Side effect of llsm_rtsynth_buffer_feed (llsmrt.c:341-347,387-390): a layer-1 frame without a harmonic model gets
+    one attached (llsm_frame_tolayer0) whenever the stream plays its sinusoids -- PbP onset or not in PbP mode --, and
+    keeps none while the stream stays in PbP mode. Same frames on both libraries, same model."""
+    fr, conf = S.synth_frames(1, 70, seed=71, nhar=60, maxnhar=60)
+    res = []
+    for L in libs:
+        _bind_rt(L)
+        ck = U.build_chunk(L, fr, conf)
+        L.llsm_chunk_tolayer1(ck, 2048)
+        for i in range(conf.nfrm):
+            f = ck.contents.frames[i]
+            L.llsm_container_attach_(f, U.HMI, None, None, None)
+            if 20 <= i < 45:
+                L.llsm_container_attach_(f, 9, C.cast(L.llsm_create_int(1), C.c_void_p), U.fn_ptr(L, "llsm_delete_int"),
+                                         U.fn_ptr(L, "llsm_copy_int"))
+        so = L.llsm_create_soptions(C.c_float(conf.fs))
+        so.contents.use_l1 = 1
+        libc.srand(3)
+        rt = L.llsm_create_rtsynth_buffer(so, ck.contents.conf, 8192)
+        p, ap = C.c_float(), C.c_float()
+        for i in range(conf.nfrm):
+            L.llsm_rtsynth_buffer_feed(rt, ck.contents.frames[i])
+            while L.llsm_rtsynth_buffer_fetch_decomposed(rt, C.byref(p), C.byref(ap)):
+                pass
+        has, amp = [], []
+        for i in range(conf.nfrm):
+            hm = L.llsm_container_get(ck.contents.frames[i], U.HMI)
+            has.append(bool(hm))
+            if hm:
+                h = C.cast(hm, C.POINTER(U.HM)).contents
+                amp.append(np.ctypeslib.as_array(h.ampl, (h.nhar,)).copy())
+        L.llsm_delete_rtsynth_buffer(rt); L.llsm_delete_soptions(so); L.llsm_delete_chunk(ck)
+        res.append((has, amp))
+    assert res[0][0] == res[1][0], "HM members attached to different frames"
+    assert any(res[1][0]) and not all(h for h, v in zip(res[1][0], fr["f0"][0] > 0) if v)
+    for a, b in zip(res[0][1], res[1][1]):
+        assert a.shape == b.shape and np.abs(a - b).max() < 1e-4 * max(float(np.abs(b).max()), 1e-9)
