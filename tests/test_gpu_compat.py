@@ -440,8 +440,9 @@ def test_dsputils_harmonic_analysis_dropin(libs, method):
         assert abs(pe.mean()) < 0.1 and pe.std() < 0.1, (pe.mean(), pe.std())
         got.append((A, P))
     (Aa, Pa), (Ab, Pb) = got
-    assert np.abs(Aa - Ab).max() < (1e-6 if method == 1 else 1e-4)
-    assert np.abs(S.phase_err(Pa, Pb) * Ab).max() < (1e-6 if method == 1 else 1e-3)
+    # amplitudes reach 1.0 here: bars relative to that (the analysis tests' 1e-6 is on amplitudes <= 0.1)
+    assert np.abs(Aa - Ab).max() < (5e-6 if method == 1 else 1e-4)
+    assert np.abs(S.phase_err(Pa, Pb) * Ab).max() < (5e-6 if method == 1 else 1e-3)
 
 
 def test_dsputils_harmonic_frame_dropin(libs):
