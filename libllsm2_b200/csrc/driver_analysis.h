@@ -18,6 +18,12 @@ struct AnaPlan {
   struct ChanFilt { int nstage; double b[2][5]; double a[2][5]; };
   ChanFilt chan[LLSM_B200_MAXCHANNEL];
   unsigned use_x_mask = 0;
+  // Blackman windows of the harmonic estimator (dsputils.c:190-199) for every even length 2 h, h = 1 .. bw_cap, stored
+  // from the centre outwards: bwin[bw_off[h] + n] = w(h +- n) = 0.42 + 0.5 cos(2 pi n / 2h) + 0.08 cos(4 pi n / 2h),
+  // n = 0 .. h (the periodic window is symmetric about its centre sample); bw_sum[h] = (FP_TYPE) sum of the 2 h
+  // taps. Offsets are multiples of four floats so that a window is a 16-byte aligned bulk-copy source.
+  int bw_cap = 0;
+  std::vector<float> bwin, bw_sum; std::vector<int> bw_off;
 };
 
 static inline int fpad_host(int j) { return j + (j >> 4); }
@@ -59,6 +65,23 @@ static inline void build_ana_plan(AnaPlan& p, float fs, float thop, int npsd, in
     int k = (int)pos;
     p.ip_k[j] = k; p.ip_r[j] = (float)(pos - k);
   }
+  // window table of the harmonic estimator
+  p.bw_cap = (int)ceil((double)fs / mma_min_f0() * 2.0) + 4;
+  p.bw_off.assign(p.bw_cap + 1, 0); p.bw_sum.assign(p.bw_cap + 1, 0.f);
+  {
+    size_t total = 0;
+    for(int hh = 1; hh <= p.bw_cap; hh ++) { p.bw_off[hh] = (int)total; total += (size_t)((hh + 1 + 3) & ~3); }
+    p.bwin.assign(total + 4, 0.f);
+    for(int hh = 1; hh <= p.bw_cap; hh ++) {
+      const int n2 = 2 * hh;
+      float* w = &p.bwin[p.bw_off[hh]];
+      for(int n = 0; n <= hh; n ++)
+        w[n] = (float)(0.42 + 0.5 * cos(2.0 * M_PI * n / n2) + 0.08 * cos(4.0 * M_PI * n / n2));
+      double acc = 0;                                     // sumfp over m = 0 .. 2h - 1, m = h + n | h - n
+      for(int m = 0; m < n2; m ++) acc += (double)w[m < hh ? hh - m : m - hh];
+      p.bw_sum[hh] = (float)acc;
+    }
+  }
   // channel filters (layer0.c:434-440)
   p.use_x_mask = 0;
   for(int c = 0; c < LLSM_B200_MAXCHANNEL; c ++) p.chan[c].nstage = 0;
@@ -73,6 +96,7 @@ static inline void build_ana_plan(AnaPlan& p, float fs, float thop, int npsd, in
 struct AnaPlanDev {
   AnaPlan h;
   float *win_psd = nullptr, *ip_r = nullptr; int* ip_k = nullptr;
+  float *bwin = nullptr, *bw_sum = nullptr; int* bw_off = nullptr;
   float2 *tw_s = nullptr, *tw_p = nullptr, *tw_pp = nullptr;   // tw_pp: 8192-point table for HMPP
   // chunk-parallel IIR tables of the sub-band filters, valid for sequences of iir_nx samples
   DevBuf iir_coef, iir_mpow; int iir_nx = -1, iir_L = 0; int nchannel = 0;
@@ -92,6 +116,7 @@ struct AnaPlanDev {
     build_twiddle(tws, h.nfft_s); build_twiddle(twp, h.nfft);
     int rc = 0;
     rc |= up(&win_psd, h.win_psd, st); rc |= up(&ip_k, h.ip_k, st); rc |= up(&ip_r, h.ip_r, st);
+    rc |= up(&bwin, h.bwin, st); rc |= up(&bw_sum, h.bw_sum, st); rc |= up(&bw_off, h.bw_off, st);
     float* a = nullptr; rc |= up(&a, tws, st); tw_s = (float2*)a;
     float* b = nullptr; rc |= up(&b, twp, st); tw_p = (float2*)b;
     std::vector<float> twpp; build_twiddle(twpp, 8192);
@@ -121,7 +146,8 @@ struct AnaPlanDev {
 
 struct AnaScratch {
   DevBuf x_sin, x_res, ce, env, lpsd, res, filt, pvar, nfft_utt;
-  void release() { nfft_utt.release(); x_sin.release(); x_res.release(); ce.release(); env.release(); lpsd.release(); res.release(); filt.release(); pvar.release(); }
+  DevBuf long_list;      // frames the staged kernels leave to the general ones: [0] = count, [1 ..] = b * nfrm + i
+  void release() { nfft_utt.release(); long_list.release(); x_sin.release(); x_res.release(); ce.release(); env.release(); lpsd.release(); res.release(); filt.release(); pvar.release(); }
 };
 
 // one FFT size per utterance for the peak-picking method (llsm_get_fftsize, dsputils.c:318-326)
@@ -150,6 +176,11 @@ static inline int run_harmonic_pass(const SynthPlanDev& sp, AnaPlanDev& ap, AnaS
     H.f0 = f0; H.center = sp.hm_base; H.fs = conf.fs; H.rel_winsize = opt.rel_winsize;
     H.maxnhar = maxnhar; H.nhar_out = nhar_o; H.ampl = ampl_o; H.phse = phse_o; H.max_half = max_half;
     H.edc = edc_o; H.thop = conf.thop;
+    if(sc.long_list.reserve(((size_t)B * F + 1) * 4) != 0) return LLSM_B200_ENOMEM;
+    H.bwin = ap.bwin; H.bw_off = ap.bw_off; H.bw_sum = ap.bw_sum; H.bw_cap = ap.h.bw_cap;
+    H.long_list = sc.long_list.as<int>();
+    H.hop_max = 1;
+    for(int i = 1; i < F; i ++) H.hop_max = std::max(H.hop_max, sp.h.hm_base[i] - sp.h.hm_base[i - 1]);
     if(launch_harmonic_dft(H, B, st) != 0) return LLSM_B200_ERANGE;
   } else {
     if(prep_fftsize) { int rc = run_utt_fftsize(sc, conf, opt, f0, nfrm_utt, st, lc); if(rc) return rc; }

@@ -17,6 +17,7 @@
 #pragma once
 #include "common.cuh"
 #include "kernels_synth.cuh"   // ChanFiltDev
+#include "bulk_copy.cuh"
 
 // reference index helpers, float/double steps as written in the C source ---------------------
 __device__ __forceinline__ int ana_winsize(float fs, float f0, float rel) {
@@ -150,8 +151,16 @@ struct HarmDftParams {
   float* ampl; float* phse; // [B][nfrm][nsig][maxnhar]
   int max_half;             // capacity of the staged half-frame (pairs)
   float* edc; float thop;   // optional: short-time mean of every signal, [B][nfrm][nsig]
+  int hop_max;              // largest distance between consecutive frame centres (staged kernels)
   int only_above_half;      // > 0: the direct kernel only serves frames whose half window exceeds this
   int mma_cap_half;         // capacity (half window) of the tensor-core kernel's staging
+  // window table (AnaPlan::bwin): w(h +- n) at bwin[bw_off[h] + n], sums bw_sum[h], for half windows h <= bw_cap
+  const float* bwin; const int* bw_off; const float* bw_sum; int bw_cap;
+  int stage_cap;            // half-window capacity of the staged kernels' shared-memory slices
+  int seg_frames, seg_len;  // staged kernels: frames per CTA, samples per staged row (multiple of 4)
+  int nutt;                 // utterances of the batch
+  int* long_list;           // staged kernels: frames left to the general kernels ([0] = count, [1 ..] = b * nfrm + i);
+                            // general kernels: when non-NULL, serve exactly these frames
 };
 
 
@@ -182,20 +191,18 @@ __device__ __forceinline__ void harmonic_finish(float re, float im, int k, int h
 // KW = harmonics the warp-per-signal variant carries in registers (its loops are unrolled to KW: with the usual four
 // envelope harmonics the eight-wide instance spent half its instructions on predicated-off harmonics).
 template <int G, int KW = HD_KW>
-__global__ void __launch_bounds__(HD_THREADS) harmonic_dft_kernel(HarmDftParams P) {
-  LLSM_DYN_SMEM(smem);
+__device__ __forceinline__ void harmonic_dft_frame(const HarmDftParams& P, const int i, const int by, char* smem) {
   constexpr int NG = HD_THREADS / G;                  // signals per CTA
   float* wv = (float*)smem;                           // [max_half + 2] window, w(half +- n)
   double* red = (double*)(wv + ((P.max_half + 2 + 1) & ~1));   // [HD_THREADS] reduction scratch
   float* part = (float*)(red + HD_THREADS);           // [2 * HD_THREADS] slice partials
   float2* spall = (float2*)(part + 2 * HD_THREADS);   // [NG][max_half + 2] (x+ + x-, x+ - x-)
 
-  const int i = blockIdx.x;
   const int ngrp = (P.nsig + NG - 1) / NG;            // CTAs per (utterance, frame)
-  const int b = blockIdx.y / ngrp;
+  const int b = by / ngrp;
   const int tid = threadIdx.x;
   const int g = tid / G, gt = tid % G;                // group, thread in group
-  const int c = (blockIdx.y % ngrp) * NG + g;         // signal of this group
+  const int c = (by % ngrp) * NG + g;                 // signal of this group
   const bool live = c < P.nsig;
   const int nf = P.nfrm_utt ? P.nfrm_utt[b] : P.nfrm;
   const size_t fidx = ((size_t)b * P.nfrm + i) * P.nsig + (live ? c : 0);
@@ -374,6 +381,20 @@ __global__ void __launch_bounds__(HD_THREADS) harmonic_dft_kernel(HarmDftParams 
   if(gt == 0) P.nhar_out[fidx] = nh;
 }
 
+// grid (nfrm, nutt * groups): one CTA per frame and signal group; or, with P.long_list (one signal per utterance), a
+// fixed grid walking the listed frames
+template <int G, int KW = HD_KW>
+__global__ void __launch_bounds__(HD_THREADS) harmonic_dft_kernel(HarmDftParams P) {
+  LLSM_DYN_SMEM(smem);
+  if(P.long_list == nullptr) { harmonic_dft_frame<G, KW>(P, blockIdx.x, blockIdx.y, smem); return; }
+  const int n = P.long_list[0];
+  for(int e = blockIdx.x; e < n; e += gridDim.x) {
+    const int f = P.long_list[1 + e];
+    harmonic_dft_frame<G, KW>(P, f % P.nfrm, f / P.nfrm, smem);
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Tensor-core variant of the main pass (one signal, up to maxnhar harmonics per frame).
 // With the pair index n = 16 p + q the sums over the window factor into a small GEMM per frame:
@@ -393,9 +414,7 @@ __global__ void __launch_bounds__(HM_THREADS) harmonic_mma_kernel(HarmDftParams 
   LLSM_DYN_SMEM(smem);
   const int cap = P.mma_cap_half;
   const int prow = (((cap + 1 + 15) / 16) + 7) & ~7;   // staged p-rows (multiple of 8)
-  float* wv = (float*)smem;                           // [cap + 2]
-  double* red = (double*)(wv + ((cap + 2 + 1) & ~1)); // [HM_THREADS]
-  float2* sph = (float2*)(red + HM_THREADS);          // [prow][HM_ROW] (e_hi, o_hi)
+  float2* sph = (float2*)smem;                        // [prow][HM_ROW] (e_hi, o_hi)
   float2* spl = sph + (size_t)prow * HM_ROW;          // [prow][HM_ROW] (e_lo, o_lo)
   float2* sums = spl + (size_t)prow * HM_ROW;         // [maxnhar] DFT sums of the harmonics
 
@@ -413,47 +432,43 @@ __global__ void __launch_bounds__(HM_THREADS) harmonic_mma_kernel(HarmDftParams 
   const int ws = ana_winsize(P.fs, f0, P.rel_winsize);
   const int nh = ana_nhar(P.fs, f0, P.maxnhar);
   const int half = ws >> 1;
-  if(half > P.max_half) { if(tid == 0) P.nhar_out[fidx] = -1; return; }
-  if(half > cap) return;                              // left to the direct kernel
+  if(half > cap || half < 1) {                        // left to the general kernel (harmonic_dft_kernel in list mode)
+    if(tid == 0) { const int at = atomicAdd(P.long_list, 1); P.long_list[1 + at] = (int)fidx; }
+    return;
+  }
   const float* x = P.sig + (size_t)b * P.xstride;
   const int center = P.center[i];
-
-  // ---- window (see harmonic_dft_kernel) and its sum
-  double wsum = 0;
-  {
-    double cs, sn, cstep, sstep;
-    sincospi(2.0 * (double)tid / (double)ws, &sn, &cs);
-    sincospi(2.0 * (double)HM_THREADS / (double)ws, &sstep, &cstep);
-    for(int n = tid; n <= half; n += HM_THREADS) {
-      const float w = (float)(0.42 + 0.5 * cs + 0.08 * (2.0 * cs * cs - 1.0));
-      wv[n] = w;
-      if(n < half) wsum += w;
-      if(n >= 1) wsum += w;
-      const double c2 = cs * cstep - sn * sstep;
-      sn = sn * cstep + cs * sstep; cs = c2;
-    }
-  }
-  red[tid] = wsum;
-  __syncthreads();
-  for(int o = HM_THREADS >> 1; o > 0; o >>= 1) { if(tid < o) red[tid] += red[tid + o]; __syncthreads(); }
-  const float winsum = (float)red[0];
+  // ---- Blackman window and its sum from the plan's table (w(half +- n) at wv[n])
+  const float* wv = P.bwin + P.bw_off[half];
+  const float winsum = P.bw_sum[half];
 
   // ---- stage e | o (symmetric / antisymmetric halves), split for 3xTF32, rows of 16 pairs
   const int npair = half + 1;
   const int np8 = (((npair + 15) / 16) + 7) & ~7;     // p-rows in use (multiple of 8, <= prow)
-  for(int n = tid; n < np8 * 16; n += HM_THREADS) {
-    float e = 0.f, o = 0.f;
-    if(n < npair) {
-      const float w = wv[n];
-      float xp = 0, xm = 0;
-      if(n < half) { int idx = center + n; if(idx >= 0 && idx < P.nx) xp = w * x[idx]; }
-      if(n >= 1) { int idx = center - n; if(idx >= 0 && idx < P.nx) xm = w * x[idx]; }
-      e = xp + xm; o = xp - xm;
+  for(int n0 = tid; n0 < np8 * 16; n0 += 2 * HM_THREADS) {
+    float e[2], o[2];
+#pragma unroll
+    for(int u = 0; u < 2; u ++) {                     // two elements in flight per thread
+      const int n = n0 + u * HM_THREADS;
+      float w = 0.f, xp = 0.f, xm = 0.f;
+      if(n < npair) {
+        w = wv[n];
+        if(n < half) { const int idx = center + n; if(idx >= 0 && idx < P.nx) xp = x[idx]; }
+        if(n >= 1) { const int idx = center - n; if(idx >= 0 && idx < P.nx) xm = x[idx]; }
+      }
+      const float a = w * xp, d = w * xm;
+      e[u] = a + d; o[u] = a - d;
     }
-    float eh, el, oh, ol;
-    tf32_split(e, eh, el); tf32_split(o, oh, ol);
-    const int at = (n >> 4) * HM_ROW + (n & 15);
-    sph[at] = make_float2(eh, oh); spl[at] = make_float2(el, ol);
+#pragma unroll
+    for(int u = 0; u < 2; u ++) {
+      const int n = n0 + u * HM_THREADS;
+      if(n < np8 * 16) {
+        float eh, el, oh, ol;
+        tf32_split(e[u], eh, el); tf32_split(o[u], oh, ol);
+        const int at = (n >> 4) * HM_ROW + (n & 15);
+        sph[at] = make_float2(eh, oh); spl[at] = make_float2(el, ol);
+      }
+    }
   }
   __syncthreads();
 
@@ -465,8 +480,18 @@ __global__ void __launch_bounds__(HM_THREADS) harmonic_mma_kernel(HarmDftParams 
   for(int mt = warp; mt * 8 < nh; mt += HM_THREADS / 32) {
     const int kg = mt * 8 + g;                        // this lane's harmonic (rows g: cosine, g + 8: sine)
     const double th = (double)(kg + 1) * nu;
-    const float2 z8 = unit_phasor_turns(th * 128.0);  // 8 p-rows ahead
-    float2 uA = unit_phasor_turns(th * 16.0 * (double)t), uB = unit_phasor_turns(th * 16.0 * (double)(t + 4));
+    // ---- phasors of this harmonic, b = e^{i 2 pi th}: two seeds with the angle reduced in double (b, b^16), the rest
+    //      by short float product chains (at most four roundings, ~3e-7): b^{2t}, b^{2t+1}, b^{2t+8}, b^{2t+9} for the
+    //      epilogue, b^{16t}, b^{16(t+4)} for the first fragment rows, b^128 to advance them. (Seven independently
+    //      reduced sincospif per tile were 23 % of the kernel's instructions: profiles/r2c.)
+    const float2 b1 = unit_phasor_turns(th), b16 = unit_phasor_turns(th * 16.0);
+    const float2 b2 = cmul(b1, b1), b4 = cmul(b2, b2), b6 = cmul(b4, b2), b8 = cmul(b4, b4);
+    const float2 one = make_float2(1.f, 0.f);
+    const float2 q00 = t == 0 ? one : (t == 1 ? b2 : (t == 2 ? b4 : b6));
+    const float2 q01 = cmul(q00, b1), q10 = cmul(q00, b8), q11 = cmul(q01, b8);
+    const float2 b32 = cmul(b16, b16), b48 = cmul(b32, b16), b64 = cmul(b32, b32), z8 = cmul(b64, b64);
+    float2 uA = t == 0 ? one : (t == 1 ? b16 : (t == 2 ? b32 : b48));
+    float2 uB = cmul(uA, b64);
     float d[4][4];
 #pragma unroll
     for(int j = 0; j < 4; j ++) { d[j][0] = 0.f; d[j][1] = 0.f; d[j][2] = 0.f; d[j][3] = 0.f; }
@@ -491,11 +516,12 @@ __global__ void __launch_bounds__(HM_THREADS) harmonic_mma_kernel(HarmDftParams 
     }
     // ---- epilogue: q-phasors and the sum over the 16 columns (4 per lane, then across the 4 lanes of a row)
     float re = 0.f, im = 0.f;
+    const float2 wqv[2][2] = {{q00, q01}, {q10, q11}};
 #pragma unroll
     for(int j = 0; j < 2; j ++)
 #pragma unroll
       for(int e = 0; e < 2; e ++) {
-        const float2 wq = unit_phasor_turns(th * (double)(8 * j + 2 * t + e));
+        const float2 wq = wqv[j][e];                  // e^{i th (8 j + 2 t + e)}
         re = fmaf(wq.x, d[j][e], fmaf(-wq.y, d[j][2 + e], re));
         im = fmaf(-wq.x, d[j + 2][2 + e], fmaf(-wq.y, d[j + 2][e], im));
       }
@@ -514,12 +540,35 @@ __global__ void __launch_bounds__(HM_THREADS) harmonic_mma_kernel(HarmDftParams 
 
 static inline size_t harm_mma_smem(int cap, int maxnhar) {
   const int prow = (((cap + 1 + 15) / 16) + 7) & ~7;
-  return (size_t)((cap + 3) & ~1) * 4 + HM_THREADS * 8 + (size_t)prow * HM_ROW * 8 * 2 + (size_t)maxnhar * 8 + 16;
+  return (size_t)prow * HM_ROW * 8 * 2 + (size_t)maxnhar * 8 + 16;
 }
 
 static inline double mma_min_f0() {
   static double v = -1;
   if(v < 0) { const char* e = getenv("LLSM_MMA_MIN_F0"); v = e ? atof(e) : 80.0; if(! (v >= 20.0)) v = 20.0; }
+  return v;
+}
+
+static inline int env_variant() {
+  static int v = -1;
+  if(v < 0) { const char* e = getenv("LLSM_ENV_VARIANT"); v = e ? atoi(e) : 1; }
+  return v;
+}
+
+// CTAs of a persistent grid: per_sm resident CTAs on every SM of the current device
+static inline int ana_resident_ctas(int per_sm) {
+#ifdef LLSM_EMU
+  return 3 * per_sm;
+#else
+  int dev = 0, sms = 148;
+  if(cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms * per_sm;
+#endif
+}
+
+static inline int env_seg_frames() {
+  static int v = -1;
+  if(v < 0) { const char* e = getenv("LLSM_ENV_SEG"); v = e ? atoi(e) : 16; if(v < 1) v = 1; }
   return v;
 }
 
@@ -541,12 +590,10 @@ static inline int dft_variant() {
 #define ED_STRIDE (ED_THREADS + 4)          // row stride of the reduction scratch: conflict-free for both access patterns
 
 template <int NC, int KW>
-__global__ void __launch_bounds__(ED_THREADS) envelope_dft_kernel(HarmDftParams P) {
-  LLSM_DYN_SMEM(smem);
+__device__ __forceinline__ void envelope_dft_frame(const HarmDftParams& P, const int i, const int b, char* smem) {
   double* red = (double*)smem;                                       // [ED_THREADS]
   float* part = (float*)(red + ED_THREADS);                          // [2 * NC * KW][ED_STRIDE]
   float2* zst = (float2*)(part + 2 * NC * KW * ED_STRIDE);           // [KW] 128-sample rotation per harmonic
-  const int i = blockIdx.x, b = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nf = P.nfrm_utt ? P.nfrm_utt[b] : P.nfrm;
   if(i >= nf) return;
@@ -685,10 +732,188 @@ __global__ void __launch_bounds__(ED_THREADS) envelope_dft_kernel(HarmDftParams 
   if(tid < nsig) P.nhar_out[f0idx * nsig + tid] = nh;
 }
 
+// grid (nfrm, nutt): one CTA per frame; or, with P.long_list, a fixed grid walking the listed frames
+template <int NC, int KW>
+__global__ void __launch_bounds__(ED_THREADS) envelope_dft_kernel(HarmDftParams P) {
+  LLSM_DYN_SMEM(smem);
+  if(P.long_list == nullptr) { envelope_dft_frame<NC, KW>(P, blockIdx.x, blockIdx.y, smem); return; }
+  const int n = P.long_list[0];
+  for(int e = blockIdx.x; e < n; e += gridDim.x) {
+    const int f = P.long_list[1 + e];
+    envelope_dft_frame<NC, KW>(P, f % P.nfrm, f / P.nfrm, smem);
+    __syncthreads();
+  }
+}
+
 template <int NC, int KW>
 static inline size_t env_dft_smem(int max_half) {
   (void)max_half;
   return (size_t)ED_THREADS * 8 + (size_t)(2 * NC * KW * ED_STRIDE) * 4 + KW * 8 + 32;
+}
+
+// ------------------------------------------------------------------------------------------
+// Envelope pass from a STAGED SEGMENT: a CTA owns seg_frames consecutive frames of one utterance; thread 0 brings the
+// slice of every sub-band signal those frames touch -- [centre(first) - cap, centre(last) + cap], clipped, 16-byte
+// aligned -- into shared memory with one bulk asynchronous copy per channel (cp.async.bulk, the TMA engine's 1-D form,
+// completed on an mbarrier), and each WARP then analyses whole frames out of it: the short-time means, then the pairs
+// n = lane, lane + 32, ... of the window against one phasor per harmonic (advanced 32 samples per step, re-seeded every
+// 16 steps), all channels x harmonics accumulated in registers, reduced by a transposing butterfly inside the warp (31
+// shuffles per 32 values; lane q ends up with value q) and finished by the lanes that hold them. Neighbouring frames
+// overlap by three quarters of their windows, so a sample crosses L2 -> SM about 1.3 times instead of 4 times, no thread
+// ever waits on a global load of sample data (the one-CTA-per-frame kernel above spent 44 % of its stall samples there
+// and lived ~10 us per frame: profiles/r2c, r2f), and there is no block barrier after the copy has landed.
+// The Blackman window comes from the plan's table (AnaPlan::bwin, L2-resident). Frames whose windows exceed the
+// capacity (f0 below ~80 Hz) are appended to P.long_list and served by envelope_dft_kernel in list mode.
+// ------------------------------------------------------------------------------------------
+#define EVS_WARPS 8
+#define EVS_THREADS (EVS_WARPS * 32)
+
+// sum over the 32 lanes of each of 32 per-lane values; lane q returns the total of value q
+__device__ __forceinline__ float warp_transpose_sum32(float (&a)[32], int lane) {
+#pragma unroll
+  for(int o = 16; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for(int j = 0; j < o; j ++) {
+      const float send = up ? a[j] : a[j + o];
+      const float keep = up ? a[j + o] : a[j];
+      a[j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return a[0];
+}
+
+static inline size_t env_seg_smem(int nsig, int seg_len) { return 16 + (size_t)nsig * seg_len * 4 + 16; }
+
+template <int NC, int KW>
+__global__ void __launch_bounds__(EVS_THREADS, 2) envelope_seg_kernel(HarmDftParams P) {
+  LLSM_DYN_SMEM(smem);
+  constexpr int NV = 2 * NC * KW;                                    // values reduced per frame
+  static_assert(NV % 32 == 0, "whole groups of 32 values");
+  bulk_bar_t* bar = (bulk_bar_t*)smem;
+  float* sl = (float*)(smem + 16);                                   // [nsig][SL]
+  const int SL = P.seg_len, cap = P.stage_cap, nsig = P.nsig;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.y, i_lo = blockIdx.x * P.seg_frames;
+  const int nf = P.nfrm_utt ? P.nfrm_utt[b] : P.nfrm;
+  if(i_lo >= nf) return;
+  const int i_hi = min(i_lo + P.seg_frames, nf);
+  int lo = P.center[i_lo] - cap, hi = P.center[i_hi - 1] + cap + 1;
+  lo = max(lo, 0) & ~3; hi = (min(hi, P.nx) + 3) & ~3;               // (rows are padded to a multiple of four samples)
+  const int len = min(max(hi - lo, 0), SL);
+  if(tid == 0) bulk_bar_init(bar);
+  __syncthreads();
+  if(tid == 0) {
+    bulk_expect(bar, (uint32_t)(nsig * len * 4));
+    if(len > 0)
+      for(int c = 0; c < nsig; c ++)
+        bulk_g2s(sl + (size_t)c * SL, P.sig + ((size_t)b * nsig + c) * P.xstride + lo, (uint32_t)(len * 4), bar);
+  }
+  // this warp's first frame is fetched while the copy is in flight
+  int i = i_lo + warp;
+  float f0_next = i < i_hi ? P.f0[(size_t)b * P.nfrm + i] : 0.f;
+  int cen_next = i < i_hi ? P.center[i] : 0;
+  bulk_wait(bar, 0);
+
+  for(; i < i_hi; i += EVS_WARPS) {
+    const float f0 = f0_next; const int center = cen_next;
+    if(i + EVS_WARPS < i_hi) { f0_next = P.f0[(size_t)b * P.nfrm + i + EVS_WARPS]; cen_next = P.center[i + EVS_WARPS]; }
+    const size_t fidx = (size_t)b * P.nfrm + i;
+    const double wlen = f0 == 0 ? (double)(P.thop * 2.0f) : 2.0 / (double)f0;
+    const int nw = P.edc != nullptr ? (int)round(wlen * (double)P.fs) : 0;
+    int half = 0, nh = 0;
+    bool listed = nw / 2 + 1 > cap;
+    if(f0 > 0) {
+      const int ws = ana_winsize(P.fs, f0, P.rel_winsize);
+      half = ws >> 1; nh = ana_nhar(P.fs, f0, P.maxnhar);
+      listed = listed || half > cap || half > P.bw_cap || half > P.max_half || half < 1;
+    }
+    if(listed) {                                                     // left to the general kernel
+      if(lane == 0) { const int at = atomicAdd(P.long_list, 1); P.long_list[1 + at] = (int)fidx; }
+      continue;
+    }
+    // ---- short-time means (llsm_compute_dc, dsputils.c:117-124)
+    if(P.edc != nullptr) {
+      for(int c = 0; c < nsig; c ++) {
+        const float* x = sl + (size_t)c * SL - lo;
+        double acc = 0;
+        for(int j = lane; j < nw; j += 4 * 32) {
+          float v[4];
+#pragma unroll
+          for(int u = 0; u < 4; u ++) {
+            const int idx = center + j + u * 32 - nw / 2;
+            v[u] = (j + u * 32 < nw && idx >= 0 && idx < P.nx) ? x[idx] : 0.f;
+          }
+#pragma unroll
+          for(int u = 0; u < 4; u ++) acc += (double)v[u];
+        }
+        for(int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if(lane == 0) P.edc[fidx * nsig + c] = nw > 0 ? (float)(acc / nw) : 0.f;
+      }
+    }
+    if(! (f0 > 0)) {                                                 // unvoiced: no harmonic model (layer0.c:106)
+      for(int q = lane; q < nsig * P.maxnhar; q += 32) { P.ampl[fidx * nsig * P.maxnhar + q] = 0; P.phse[fidx * nsig * P.maxnhar + q] = 0; }
+      if(lane < nsig) P.nhar_out[fidx * nsig + lane] = 0;
+      continue;
+    }
+    const float omega0 = (float)(2.0 * LLSM_PI * (double)f0 / (double)P.fs);   // czt step (FP_TYPE arg)
+    const double nu = (double)omega0 / (2.0 * LLSM_PI);
+    const float* wv = P.bwin + P.bw_off[half];
+    const float winsum = P.bw_sum[half];
+    const int npair = half + 1;
+    float v[NV];
+#pragma unroll
+    for(int q = 0; q < NV; q ++) v[q] = 0.f;                         // v[2 (c KW + k)] = re, [.. + 1] = im
+    float2 w[KW], z[KW];
+#pragma unroll
+    for(int k = 0; k < KW; k ++) z[k] = k < nh ? unit_phasor_turns((double)(k + 1) * nu * 32.0) : make_float2(1.f, 0.f);
+    const float* xb = sl - lo + center;
+    int step = 0;
+    float wn_next = lane < npair ? __ldg(wv + lane) : 0.f;
+    for(int n = lane; n < npair; n += 32, step ++) {
+      if((step & 15) == 0) {
+#pragma unroll
+        for(int k = 0; k < KW; k ++) if(k < nh) w[k] = unit_phasor_turns((double)(k + 1) * nu * (double)n);
+      }
+      const float wn = wn_next;
+      if(n + 32 < npair) wn_next = __ldg(wv + n + 32);
+      const int ip = center + n, im_ = center - n;
+      const bool okp = n < half && ip >= 0 && ip < P.nx, okm = n >= 1 && im_ >= 0 && im_ < P.nx;
+      float e_[NC], o_[NC];
+#pragma unroll
+      for(int c = 0; c < NC; c ++) {
+        const float xp = (c < nsig && okp) ? xb[(size_t)c * SL + n] : 0.f;
+        const float xm = (c < nsig && okm) ? xb[(size_t)c * SL - n] : 0.f;
+        const float a = wn * xp, d = wn * xm;
+        e_[c] = a + d; o_[c] = a - d;
+      }
+#pragma unroll
+      for(int k = 0; k < KW; k ++) if(k < nh) {
+#pragma unroll
+        for(int c = 0; c < NC; c ++) {
+          v[2 * (c * KW + k)] = fmaf(e_[c], w[k].x, v[2 * (c * KW + k)]);
+          v[2 * (c * KW + k) + 1] = fmaf(-o_[c], w[k].y, v[2 * (c * KW + k) + 1]);
+        }
+        w[k] = cmul(w[k], z[k]);
+      }
+    }
+    // ---- lane 2 j (+ 32 g) receives re, its neighbour im, of the pair j = c KW + k
+#pragma unroll
+    for(int g = 0; g < NV / 32; g ++) {
+      float a[32];
+#pragma unroll
+      for(int q = 0; q < 32; q ++) a[q] = v[32 * g + q];
+      const float tot = warp_transpose_sum32(a, lane);
+      const float sim = __shfl_down_sync(0xffffffffu, tot, 1);
+      const int j = 16 * g + (lane >> 1), c = j / KW, k = j - c * KW;
+      if((lane & 1) == 0 && c < nsig && k < P.maxnhar) {
+        const size_t at = (fidx * nsig + c) * P.maxnhar + k;
+        if(k < nh) harmonic_finish(tot, sim, k, half, f0, P.fs, omega0, winsum, &P.ampl[at], &P.phse[at]);
+        else { P.ampl[at] = 0; P.phse[at] = 0; }
+      }
+    }
+    if(lane < nsig) P.nhar_out[fidx * nsig + lane] = nh;
+  }
 }
 
 static inline size_t harm_dft_smem(int max_half, int ng) {
@@ -697,40 +922,77 @@ static inline size_t harm_dft_smem(int max_half, int ng) {
 
 static inline int launch_harmonic_dft(const HarmDftParams& Pin, int nutt, cudaStream_t st) {
   HarmDftParams P = Pin;
-  if(P.nsig == 1 && P.edc == nullptr && dft_variant() == 1 && P.maxnhar > HD_KW) {
+  int* const long_list = P.long_list;
+  if(P.nsig == 1 && P.edc == nullptr && dft_variant() == 1 && P.maxnhar > HD_KW && P.bwin != nullptr && long_list != nullptr) {
     // tensor-core kernel for windows up to 4 periods of 80 Hz (its staging buffers are sized by that capacity and decide
-    // how many CTAs share an SM: 8 instead of 5 at 50 Hz); the direct kernel picks up the rare longer windows
+    // how many CTAs share an SM); the rare longer windows are listed and served by the direct kernel in list mode
     int cap = (int)ceil((double)P.fs / mma_min_f0() * (double)P.rel_winsize / 4.0 * 2.0) + 4;
     if(cap > P.max_half) cap = P.max_half;
+    if(cap > P.bw_cap) cap = P.bw_cap;
     P.mma_cap_half = cap;
     size_t smem = harm_mma_smem(cap, P.maxnhar);
-    if(smem <= 200 * 1024) {
+    size_t smem_d = harm_dft_smem(P.max_half, 1);
+    if(smem <= 200 * 1024 && smem_d <= 200 * 1024) {
+      if(dev_memset(long_list, 0, 4, st) != 0) return -1;
 #ifndef LLSM_EMU
       cudaFuncSetAttribute(harmonic_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 #endif
       LLSM_LAUNCH(harmonic_mma_kernel, dim3(P.nfrm, nutt), dim3(HM_THREADS), smem, st, P);
-      if(cap >= P.max_half) return 0;
-      P.only_above_half = cap;
+      auto kfn = harmonic_dft_kernel<HD_THREADS>;
+#ifndef LLSM_EMU
+      cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d);
+#endif
+      const long long total = (long long)nutt * P.nfrm;
+      dim3 lgrid((unsigned)std::max(1LL, std::min(total, (long long)ana_resident_ctas(2))));
+      LLSM_LAUNCH(kfn, lgrid, dim3(HD_THREADS), smem_d, st, P);
+      return 0;
     }
   }
-  if(P.nsig > 1 && P.maxnhar <= 8 && P.nsig <= 8) {               // envelope pass: one CTA per frame, all channels
-    dim3 grid(P.nfrm, nutt), block(ED_THREADS);
+  if(P.nsig > 1 && P.maxnhar <= 8 && P.nsig <= 8) {               // envelope pass: all channels of a frame in one CTA
 #ifndef LLSM_EMU
-#define LLSM_ENV_LAUNCH(NC, KW) { auto kfn = envelope_dft_kernel<NC, KW>; size_t smem = env_dft_smem<NC, KW>(P.max_half); \
-    if(smem > 200 * 1024) return -1; \
-    cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    LLSM_LAUNCH(kfn, grid, block, smem, st, P); }
+#define LLSM_ENV_ATTR(kfn, smem) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem))
 #else
-#define LLSM_ENV_LAUNCH(NC, KW) { auto kfn = envelope_dft_kernel<NC, KW>; size_t smem = env_dft_smem<NC, KW>(P.max_half); \
-    LLSM_LAUNCH(kfn, grid, block, smem, st, P); }
+#define LLSM_ENV_ATTR(kfn, smem) (void)0
 #endif
-    if(P.nsig <= 4 && P.maxnhar <= 4) LLSM_ENV_LAUNCH(4, 4)
-    else if(P.nsig <= 4) LLSM_ENV_LAUNCH(4, 8)
-    else if(P.maxnhar <= 4) LLSM_ENV_LAUNCH(8, 4)
-    else LLSM_ENV_LAUNCH(8, 8)
+#define LLSM_ENV_LAUNCH(NC, KW, grid) { auto kfn = envelope_dft_kernel<NC, KW>; size_t smem = env_dft_smem<NC, KW>(P.max_half); \
+    if(smem > 200 * 1024) return -1; \
+    LLSM_ENV_ATTR(kfn, smem); \
+    LLSM_LAUNCH(kfn, grid, dim3(ED_THREADS), smem, st, P); }
+#define LLSM_ENVS_LAUNCH(NC, KW, grid, smem) { auto kfn = envelope_seg_kernel<NC, KW>; \
+    LLSM_ENV_ATTR(kfn, smem); \
+    LLSM_LAUNCH(kfn, grid, dim3(EVS_THREADS), smem, st, P); }
+    // segment kernel (bulk asynchronous copy of the sub-band slices, a warp per frame) + the general kernel on the frames
+    // it lists; the copies need 16-byte aligned rows
+    const bool staged = P.bwin != nullptr && long_list != nullptr && env_variant() == 1 && P.nsig <= 4 &&
+      (P.xstride & 3) == 0 && ((uintptr_t)P.sig & 15) == 0 && P.hop_max > 0;
+    if(staged) {
+      int cap = P.bw_cap;
+      if(cap > P.max_half) cap = P.max_half;
+      P.stage_cap = cap; P.nutt = nutt;
+      P.seg_frames = env_seg_frames();
+      P.seg_len = ((P.seg_frames - 1) * P.hop_max + 2 * cap + 1 + 8 + 3) & ~3;
+      const size_t smem = env_seg_smem(P.nsig, P.seg_len);
+      if(smem <= 110 * 1024) {
+        if(dev_memset(long_list, 0, 4, st) != 0) return -1;
+        dim3 grid((P.nfrm + P.seg_frames - 1) / P.seg_frames, nutt);
+        if(P.maxnhar <= 4) LLSM_ENVS_LAUNCH(4, 4, grid, smem) else LLSM_ENVS_LAUNCH(4, 8, grid, smem)
+        const long long total = (long long)nutt * P.nfrm;
+        dim3 lgrid((unsigned)std::max(1LL, std::min(total, (long long)ana_resident_ctas(2))));
+        if(P.maxnhar <= 4) LLSM_ENV_LAUNCH(4, 4, lgrid) else LLSM_ENV_LAUNCH(4, 8, lgrid)
+        return 0;
+      }
+    }
+    P.long_list = nullptr;
+    dim3 grid(P.nfrm, nutt);
+    if(P.nsig <= 4 && P.maxnhar <= 4) LLSM_ENV_LAUNCH(4, 4, grid)
+    else if(P.nsig <= 4) LLSM_ENV_LAUNCH(4, 8, grid)
+    else if(P.maxnhar <= 4) LLSM_ENV_LAUNCH(8, 4, grid)
+    else LLSM_ENV_LAUNCH(8, 8, grid)
 #undef LLSM_ENV_LAUNCH
+#undef LLSM_ENVS_LAUNCH
     return 0;
   }
+  P.long_list = nullptr;
   dim3 grid(P.nfrm, nutt * P.nsig), block(HD_THREADS);
   size_t smem = harm_dft_smem(P.max_half, 1);
   if(smem > 200 * 1024) return -1;

@@ -85,6 +85,7 @@ template <class T> static inline T __shfl_up_sync(unsigned, T v, int d) {
   int l = (int)(emu::t_threadIdx.x & 31) - d; return emu_shfl_from(v, l < 0 ? (int)(emu::t_threadIdx.x & 31) : l);
 }
 float atomicAdd(float* p, float v); // mutex-serialised (cuda_emu.cpp)
+static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 
 // device math used by the kernels
 static inline void sincospif(float x, float* s, float* c) {

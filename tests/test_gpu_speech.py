@@ -29,8 +29,13 @@ def libs():
     return U.bind(lib()), U.bind(S.load_ref())
 
 
-def _check_chunk(a, b, tag, method):
-    """a: CUDA library, b: reference build.
+def _check_chunk(a, b, tag, method, shifted=False):
+    """a: CUDA library, b: reference build. shifted: the chunk went through phasesync_rps + phasepropagate, which add
+    (k + 1) times a per-frame angle to harmonic k (frame.c:152-178): a 1e-7 rad difference of the first harmonic's phase
+    or of the running f0 sum arrives at harmonic k multiplied by k + 1 (up to 400 here), on both libraries alike -- the
+    phase bar of that chunk is therefore taken per harmonic number, with a loose absolute bar beside it (measured on
+    B200: 6.3e-6 of the largest amplitude per harmonic number -- the refined f0 of the two libraries differs in the last
+    float digits and the running sum of 1154 frames carries that; the waveform bar below is unaffected, 1e-7 RMS).
     CZT (the reference's default method): a direct sum per harmonic -- amplitudes 2e-5 of the largest, noise PSD 0.05 dB.
     Peak picking: the estimator itself sits on knife edges on real speech -- cig_find_peak takes the first of two bins
     whose float log-magnitudes tie when a harmonic falls half-way between them, and a last-bit difference of the
@@ -45,8 +50,12 @@ def _check_chunk(a, b, tag, method):
     atol = 2e-5 if method == "czt" else 1e-4
     assert np.abs(a["ampl"] - b["ampl"]).max() < atol * scale, (tag, np.abs(a["ampl"] - b["ampl"]).max(), scale)
     if method == "czt":
-        pe = np.abs(S.phase_err(a["phse"], b["phse"]) * b["ampl"]).max()
-        assert pe < 1e-4 * scale, (tag, pe, scale)
+        pw = np.abs(S.phase_err(a["phse"], b["phse"]) * b["ampl"])
+        if shifted:
+            pk = pw / (1.0 + np.arange(pw.shape[-1]))
+            assert pk.max() < 1e-4 * scale and pw.max() < 1e-2 * scale, (tag, pk.max(), pw.max(), scale)
+        else:
+            assert pw.max() < 1e-4 * scale, (tag, pw.max(), scale)
     dp = np.abs(a["psd"] - b["psd"])
     if method == "czt":
         assert dp.max() < 0.05, (tag, dp.max())
@@ -67,7 +76,7 @@ def test_arctic_anasynth_dropin(libs, method):
     a, b = res
     assert np.abs(a["f0"] - b["f0"]).max() < 1e-3                   # the caller's f0 is refined in place
     _check_chunk(a["chunk"], b["chunk"], "analysis", method)
-    _check_chunk(a["chunk2"], b["chunk2"], "after phasesync_rps + phasepropagate", method)
+    _check_chunk(a["chunk2"], b["chunk2"], "after phasesync_rps + phasepropagate", method, shifted=True)
     for key in ("out1", "out2"):
         for ya, yb, name in zip(a[key], b[key], ("y", "y_sin", "y_noise")):
             assert ya.shape == yb.shape == (147840,)
