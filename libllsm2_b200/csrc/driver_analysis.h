@@ -27,6 +27,11 @@ struct AnaPlan {
 };
 
 static inline int fpad_host(int j) { return j + (j >> 4); }
+static inline int noise_spec_variant() {
+  static int v = -1;
+  if(v < 0) { const char* e = getenv("LLSM_NS_VARIANT"); v = e ? atoi(e) : 1; }
+  return v;
+}
 static inline int ilog2_ceil(int n) { int l = 0; while((1 << l) < n) l ++; return l; }
 
 static inline void build_ana_plan(AnaPlan& p, float fs, float thop, int npsd, int nchannel,
@@ -261,11 +266,21 @@ static inline int run_analyze_l0(const SynthPlanDev& sp, AnaPlanDev& ap, AnaScra
     N.win_psd = ap.win_psd; N.win_power = h.win_power; N.std_norm = h.std_norm;
     N.tw_s = ap.tw_s; N.tw_p = ap.tw_p;
     N.env = sc.env.as<float>(); N.lpsd = sc.lpsd.as<float>();
-    size_t smem = (size_t)(fpad_host(std::max(h.nfft, h.nfft_s)) + 1) * 16 + 16;
+    if(h.nfft_s == 2048 && h.nfft == 1024 && noise_spec_variant() == 1) {
+      // register-resident transforms, one warp per frame pair
+      const size_t smem = noise_spec_warp_smem();
 #ifndef LLSM_EMU
-    cudaFuncSetAttribute(noise_spec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(noise_spec_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 #endif
-    LLSM_LAUNCH(noise_spec_kernel, dim3((F + 1) / 2, B), dim3(NS_THREADS), smem, st, N);
+      const int npair = (F + 1) / 2;
+      LLSM_LAUNCH(noise_spec_warp_kernel, dim3((npair + NSW_WARPS - 1) / NSW_WARPS, B), dim3(NSW_THREADS), smem, st, N);
+    } else {
+      size_t smem = (size_t)(fpad_host(std::max(h.nfft, h.nfft_s)) + 1) * 16 + 16;
+#ifndef LLSM_EMU
+      cudaFuncSetAttribute(noise_spec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+#endif
+      LLSM_LAUNCH(noise_spec_kernel, dim3((F + 1) / 2, B), dim3(NS_THREADS), smem, st, N);
+    }
     if(lc) lc->n ++;
     lc_mark(lc, st, "noise_spec");
 

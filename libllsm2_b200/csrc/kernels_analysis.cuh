@@ -1218,6 +1218,244 @@ __global__ void __launch_bounds__(NS_THREADS) noise_spec_kernel(NoiseSpecParams 
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// The same spectra with every transform held in REGISTERS: one warp per pair of consecutive frames, six 1024-point
+// complex FFTs (warp_fft.cuh: 32 lanes x 32 points, no block barrier) instead of two 2048-point and two 1024-point
+// block FFTs through shared memory. Sizes fixed at nfft_s = 2048, nfft = 1024 (44.1 / 48 kHz at a 5 ms hop); other
+// configurations use noise_spec_kernel above.
+//   step 0 / 2  frame A / B: the Hann-windowed (zero-phase, time-aliased) frame as z[n] = x[2n] + i x[2n + 1];
+//               Z = FFT1024(z); the 2048-point real spectrum X[k] = (Z[k] + Z*[N-k]) / 2 - i W^k (Z[k] - Z*[N-k]) / 2
+//               (W = e^{-2 pi i / 2048}; the partner bin N - k sits in lane 32 - l, register 31 - r), L[k] = log |X[k]|, and
+//               at once the packed spectrum of the inverse real transform, Z'[k] = (L[k] + L[N-k]) + i W^{-k} (L[k] - L[N-k]).
+//   step 1 / 3  IFFT1024(Z') = 2048 (c[2n] + i c[2n + 1]): the cepstrum; lifter (sinc and raised cosine by a rotation
+//               along each lane's arithmetic progression of quefrencies); fold D[n] + D[n + 1024] (layer0.c:341-342 reads
+//               only the even bins of the last transform) -- registers r and r + 16 of the same lane.
+//   step 4      both folded, real and even sequences in one complex FFT (A real, B imaginary): their transforms are
+//               real, so re / im are the two envelopes. Frame A's sequence waits in its own (not yet written) output
+//               rows while the warp's shared memory serves frame B's transforms.
+//   step 5      Blackman PSD of the residual pair (dsputils.c:246-265), separated by Hermitian symmetry.
+// The six transforms share ONE inlined copy of the FFT (rolled loop over the steps): unrolled, the kernel would not fit
+// the instruction cache.
+// ------------------------------------------------------------------------------------------
+#define NSW_WARPS 8
+#define NSW_THREADS (NSW_WARPS * 32)
+#define NSW_WBYTES (WFFT_SCRATCH_BYTES)
+static inline size_t noise_spec_warp_smem() { return (size_t)2 * 1024 * 8 + (size_t)NSW_WARPS * NSW_WBYTES + 16; }
+
+// log |X[k]| of the 2048-point real spectrum from the packed transform: Z = Z[k], Zp = Z[N - k], W = W2048^k
+__device__ __forceinline__ float nsw_logmag(float2 Z, float2 Zp, float2 W, float nrm2) {
+  const float ar = 0.5f * (Z.x + Zp.x), ai = 0.5f * (Z.y - Zp.y);
+  const float br = 0.5f * (Z.x - Zp.x), bi = 0.5f * (Z.y + Zp.y);
+  const float tr = W.x * br - W.y * bi, ti = W.x * bi + W.y * br;     // W^k (Z - Z*p) / 2
+  const float xr = ar + ti, xi = ai - tr;
+  const float m = (xr * xr + xi * xi) * nrm2;                           // log(|X| nrm) = log(|X|^2 nrm^2) / 2: no square root
+  return 0.5f * logf(m > 1e-20f ? m : 1e-20f);
+}
+// packed spectrum of the inverse real transform from L = L[k], Lp = L[N - k] (both real), W = W2048^k
+__device__ __forceinline__ float2 nsw_pack(float L, float Lp, float2 W) {
+  const float e = L + Lp, h = L - Lp;
+  return make_float2(e + h * W.y, h * W.x);                           // e + i h conj(W)
+}
+
+__device__ __forceinline__ float nsw_rcp(float v) {
+#ifdef LLSM_EMU
+  return 1.0f / v;
+#else
+  float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r;
+#endif
+}
+
+__global__ void __launch_bounds__(NSW_THREADS, 2) noise_spec_warp_kernel(NoiseSpecParams P) {
+  LLSM_DYN_SMEM(smem);
+  constexpr int NF = 1024, NSPEC = 513;
+  float2* tw2 = (float2*)smem;                                   // [1024] W1024^{lane k2} (warp_fft1024)
+  float2* w2k = tw2 + 1024;                                      // [1024] W2048^k
+  char* wbase = (char*)(w2k + 1024);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float2* scratch = (float2*)(wbase + (size_t)warp * NSW_WBYTES);   // [1024] (+ padding: the FFT's transposes)
+  float* buf = (float*)scratch;                                  // [2048] float view
+  wfft_build_tw2(tw2, P.tw_p);
+  for(int e = tid; e < 1024; e += blockDim.x) w2k[e] = P.tw_s[e];
+
+  const int b = blockIdx.y;
+  const int i0 = 2 * (blockIdx.x * NSW_WARPS + warp);
+  const int nf = P.nfrm_utt ? P.nfrm_utt[b] : P.nfrm;
+  const bool live = i0 < nf;                                     // (idle warps keep the block barriers company)
+  const bool two = i0 + 1 < nf;
+  const float* xs = P.x + (size_t)b * P.xstride;
+  const float* xr = P.x_res + (size_t)b * P.rstride;
+  const size_t orow = ((size_t)b * P.nfrm + (live ? i0 : 0)) * NSPEC;
+  float2 x[32];
+#pragma unroll
+  for(int r = 0; r < 32; r ++) x[r] = make_float2(0.f, 0.f);
+
+#pragma unroll 1
+  for(int step = 0; step < 6; step ++) {
+    // the warps of a CTA walk the steps together: the instruction cache then holds one step's code, not all six
+    __syncthreads();
+    const int h = (step >> 1) & 1;
+    if(! live || (step < 4 && h == 1 && ! two)) continue;
+    float f0 = 0.f; int cen = 0, ws = P.nwin;
+    if(step < 4) {
+      f0 = P.f0[(size_t)b * P.nfrm + i0 + h];
+      cen = P.center[i0 + h];
+      if(f0 != 0) { float t = P.fs / f0; t = __fmul_rn(t, 3.0f); ws = (int)t; }      // layer0.c:331
+    }
+    // ---------------- before the transform
+    if(step == 0 || step == 2) {
+      // Hann-windowed frame, zero phase (window centre at index 0), time-aliased beyond 2048 samples
+      const float rws = 2.0f / (float)ws;
+      if(ws <= 2 * NF) {
+        for(int q = lane; q < 512; q += 32) ((float4*)buf)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncwarp();
+        const int first = cen - ws / 2;
+        if(first >= 0 && first + ws <= P.nx) {                   // interior frame: no bounds tests
+          for(int j = lane; j < ws; j += 32)
+            buf[(j - ws / 2) & (2 * NF - 1)] = xs[first + j] * (0.5f - 0.5f * cospif((float)j * rws));
+        } else {
+          for(int j = lane; j < ws; j += 32) {
+            const int idx = first + j;
+            float v = 0.f;
+            if(idx >= 0 && idx < P.nx) v = xs[idx] * (0.5f - 0.5f * cospif((float)j * rws));
+            buf[(j - ws / 2) & (2 * NF - 1)] = v;
+          }
+        }
+      } else {
+        for(int kb = lane; kb < 2 * NF; kb += 32) {
+          float acc = 0.f;
+          for(int j = (kb + ws / 2) & (2 * NF - 1); j < ws; j += 2 * NF) {
+            const int idx = cen + j - ws / 2;
+            if(idx >= 0 && idx < P.nx) acc += xs[idx] * (0.5f - 0.5f * cospif((float)j * rws));
+          }
+          buf[kb] = acc;
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for(int r = 0; r < 32; r ++) x[r] = scratch[lane + 32 * r];
+      __syncwarp();
+    } else if(step == 4) {
+      // folded, liftered cepstra: A from its output rows (the scratch when the pair is a single frame), B from the scratch
+      const float* dA = two ? P.env + orow + (orow & 1) : buf;              // (8-byte aligned start inside the two rows)
+#pragma unroll
+      for(int r = 0; r < 32; r ++) x[r] = make_float2(dA[lane + 32 * r], two ? buf[lane + 32 * r] : 0.f);
+      __syncwarp();
+    } else if(step == 5) {
+      // Blackman-windowed residual frames, zero-padded at the end
+      const int c0 = P.center[i0], c1 = P.center[i0 + (two ? 1 : 0)];
+      for(int j = lane; j < NF; j += 32) {
+        float v0 = 0.f, v1 = 0.f;
+        if(j < P.nwin) {
+          const float w = P.win_psd[j];
+          int idx = c0 + j - P.nwin / 2;
+          if(idx >= 0 && idx < P.nx) v0 = w * xr[idx];
+          idx = c1 + j - P.nwin / 2;
+          if(two && idx >= 0 && idx < P.nx) v1 = w * xr[idx];
+        }
+        scratch[j] = make_float2(v0, v1);
+      }
+      __syncwarp();
+#pragma unroll
+      for(int r = 0; r < 32; r ++) x[r] = scratch[lane + 32 * r];
+      __syncwarp();
+    }
+    // ---------------- the transform (steps 1 and 3: inverse)
+    warp_fft1024(x, scratch, tw2, lane, (step == 1 || step == 3) ? 1 : 0);
+    // ---------------- after the transform: the result goes back to shared memory in natural order and is worked on by
+    //                  ROLLED loops (an unrolled register version of these passes was 10 k instructions in all: the
+    //                  kernel stalled on instruction fetch, profiles/r2k)
+    if(step != 4) {
+#pragma unroll
+      for(int r = 0; r < 32; r ++) scratch[lane + 32 * r] = x[r];
+      __syncwarp();
+    }
+    if(step == 0 || step == 2) {
+      float nrm = 1024.0f / P.std_norm; nrm = nrm / (float)ws;                    // dsputils.c:111
+      const float nrm2 = nrm * nrm;
+      // bins k and N - k are worked on together, in place: L[k], L[N-k] from Z[k], Z[N-k], then Z'[k], Z'[N-k]
+      for(int k = lane; k <= 512; k += 32) {
+        const float2 za = scratch[k], zb = scratch[(NF - k) & (NF - 1)];
+        const float2 wa = w2k[k], wb = make_float2(-wa.x, wa.y);                   // W^{N-k} = -conj(W^k)
+        if(k == 0) {
+          const float m0 = (za.x + za.y) * (za.x + za.y) * nrm2, m1 = (za.x - za.y) * (za.x - za.y) * nrm2;   // X[0], X[1024]
+          const float L0 = 0.5f * logf(m0 > 1e-20f ? m0 : 1e-20f), L1 = 0.5f * logf(m1 > 1e-20f ? m1 : 1e-20f);
+          scratch[0] = make_float2(L0 + L1, L0 - L1);
+        } else {
+          const float La = nsw_logmag(za, zb, wa, nrm2), Lb = nsw_logmag(zb, za, wb, nrm2);
+          scratch[k] = nsw_pack(La, Lb, wa);
+          if(k < 512) scratch[NF - k] = nsw_pack(Lb, La, wb);
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for(int r = 0; r < 32; r ++) x[r] = scratch[lane + 32 * r];
+      __syncwarp();
+    } else if(step == 1 || step == 3) {
+      // scratch[n] = 2048 (c[2n], c[2n + 1]). Lifter (layer0.c:338-340 via spec2env): quefrency q and its mirror 2048 - q
+      // carry the same weight; fold D[q] + D[q + 1024] (only the even bins of the next transform are read): elements
+      // m and m + 512. Four progressions per lane: q = 2 lane + e + 64 r and q' = 1024 - 2 lane - e - 64 r, e = 0, 1;
+      // sin / cos (pi f0s q) advance by a fixed rotation from seeds reduced in double.
+      const float f0s = (f0 == 0 ? 200.0f : f0) / P.fs;                           // layer0.c:338
+      const float inv = 1.0f / 2048.0f;
+      float2 rot, ph[2][2];
+      {
+        double u = (double)f0s * 64.0 * 0.5; u -= rint(u);
+        float sn, cs; sincospif(2.0f * (float)u, &sn, &cs); rot = make_float2(cs, sn);
+      }
+#pragma unroll
+      for(int m = 0; m < 2; m ++)
+#pragma unroll
+        for(int e = 0; e < 2; e ++) {
+          const int q = m == 0 ? 2 * lane + e : 1024 - 2 * lane - e;
+          ph[m][e] = unit_phasor_turns((double)f0s * (double)q * 0.5);
+        }
+      const float rpf = inv / (float)(LLSM_PI * (double)f0s);
+      float2* dst = (step == 1 && two) ? (float2*)(P.env + orow + (orow & 1)) : scratch;
+#pragma unroll 2
+      for(int r = 0; r < 16; r ++) {
+        const int mm = lane + 32 * r;
+        const float2 ca = scratch[mm], cb = scratch[mm + 512];
+        float wgt[2][2];
+#pragma unroll
+        for(int m = 0; m < 2; m ++)
+#pragma unroll
+          for(int e = 0; e < 2; e ++) {
+            const int q = m == 0 ? 2 * mm + e : 1024 - 2 * mm - e;
+            const float s1 = ph[m][e].y;                                           // sin(pi f0s q)
+            const float sinc = q > 0 ? s1 * rpf * nsw_rcp((float)q) : inv;
+            const float c2 = fmaf(-2.0f * s1, s1, 1.0f);                           // cos(2 pi f0s q)
+            wgt[m][e] = sinc * (1.18f - 0.18f * c2);
+            ph[m][e] = m == 0 ? cmul(ph[m][e], rot) : cmul(ph[m][e], make_float2(rot.x, -rot.y));
+          }
+        dst[mm] = make_float2(ca.x * wgt[0][0] + cb.x * wgt[1][0], ca.y * wgt[0][1] + cb.y * wgt[1][1]);
+      }
+#ifndef LLSM_EMU
+      __threadfence_block();
+#endif
+      __syncwarp();
+    } else if(step == 4) {
+#pragma unroll
+      for(int r = 0; r <= 16; r ++) {
+        const int j = lane + 32 * r;
+        if(j < NSPEC) {
+          P.env[orow + j] = x[r].x * 2.0f;
+          if(two) P.env[orow + NSPEC + j] = x[r].y * 2.0f;
+        }
+      }
+    } else {
+      for(int j = lane; j < NSPEC; j += 32) {
+        const float2 zk = scratch[j], zn = scratch[(NF - j) & (NF - 1)];
+        const float ar = 0.5f * (zk.x + zn.x), ai = 0.5f * (zk.y - zn.y);
+        const float br = 0.5f * (zk.y + zn.y), bi = -0.5f * (zk.x - zn.x);
+        const float pa = __fadd_rn(__fmul_rn(ar, ar), __fmul_rn(ai, ai)) / P.win_power;
+        const float pb = __fadd_rn(__fmul_rn(br, br), __fmul_rn(bi, bi)) / P.win_power;
+        P.lpsd[orow + j] = logf(pa > 1e-10f ? pa : 1e-10f);                        // layer0.c:358
+        if(two) P.lpsd[orow + NSPEC + j] = logf(pb > 1e-10f ? pb : 1e-10f);
+      }
+    }
+  }
+}
+
 #define KCH 8
 struct KalmanParams {
   int nfrm, nspec; const int* nfrm_utt;

@@ -97,6 +97,7 @@ static inline void sincospi(double x, double* s, double* c) {
 static inline float cospif(float x) { double r = std::fmod((double)x, 2.0); return (float)std::cos(M_PI * r); }
 static inline float sinpif(float x) { double r = std::fmod((double)x, 2.0); return (float)std::sin(M_PI * r); }
 static inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
+static inline float __frcp_rn(float x) { return 1.0f / x; }
 static inline double cospi(double x) { return cos(3.14159265358979323846 * x); }
 static inline double sinpi(double x) { return sin(3.14159265358979323846 * x); }
 static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
