@@ -5,6 +5,7 @@
 #include "../../include/llsm_b200.h"
 #include "plan.h"
 #include "kernels_synth.cuh"
+#include "kernels_iir_smem.cuh"
 #include <vector>
 #include <string>
 #include <map>
@@ -58,6 +59,8 @@ struct SynthPlanDev {
   float2* tw_ns = nullptr;
   double *iir_coef = nullptr, *iir_mpow = nullptr;   // template filters, chunk length iir_L
   int iir_L = 0;
+  // shared-memory resident variant (kernels_iir_smem.cuh): cluster size (0: not applicable) and its tables
+  int iis_cs = 0, iis_L = 0; double *iis_mpow = nullptr, *iis_wts = nullptr;
   std::vector<void*> owned;
   template <class T> int up(T** dst, const std::vector<T>& src, cudaStream_t st) {
     void* d = nullptr;
@@ -88,11 +91,28 @@ struct SynthPlanDev {
         build_iir_section(h.chan[c].b[s2], h.chan[c].a[s2], iir_L, IIR_NLOG,
           &coef[((size_t)c * 2 + s2) * 9], &mpow[((size_t)c * 2 + s2) * IIR_NLOG * 16]);
     rc |= up(&iir_coef, coef, st); rc |= up(&iir_mpow, mpow, st);
+    iir_smem_geometry(h.nt, iis_cs, iis_L);
+    std::vector<double> mpow9, wts;
+    if(iis_cs > 0) {
+      std::vector<double> coef2(9);
+      mpow9.assign((size_t)LLSM_B200_MAXCHANNEL * 2 * IIS_NLOG * 16, 0.0); wts.assign((size_t)LLSM_B200_MAXCHANNEL * 2 * iis_L * 4, 0.0);
+      for(int c = 0; c < nchannel; c ++)
+        for(int s2 = 0; s2 < h.chan[c].nstage; s2 ++)
+          build_iir_smem_section(h.chan[c].b[s2], h.chan[c].a[s2], iis_L, coef2.data(),
+            &mpow9[((size_t)c * 2 + s2) * IIS_NLOG * 16], &wts[((size_t)c * 2 + s2) * iis_L * 4]);
+      rc |= up(&iis_mpow, mpow9, st); rc |= up(&iis_wts, wts, st);
+    }
     if(dev_sync(st) != 0) rc = -1;   // the host vectors must outlive the async copies
     return rc;
   }
   void release() { for(void* p : owned) dev_free(p); owned.clear(); }
 };
+
+static inline int iir_variant() {
+  static int v = -1;
+  if(v < 0) { const char* e = getenv("LLSM_IIR_VARIANT"); v = e ? atoi(e) : 1; }
+  return v;
+}
 
 struct SynthScratch {
   DevBuf colored, y_exc, ny_utt;
@@ -189,7 +209,12 @@ static inline int run_noise_part(const SynthPlanDev& pd, SynthScratch& sc, const
       I.nstage[c] = h.chan[c].nstage;
       if(h.chan[c].nstage > 0) mask |= 1u << c;
     }
-    LLSM_LAUNCH(iir_filtfilt_kernel, dim3(B * nch), dim3(IIR_NT), 0, st, I);
+    bool done = false;
+    if(pd.iis_cs > 0 && iir_variant() == 1) {      // sequences resident in (distributed) shared memory
+      IirSmemParams Q; Q.base = I; Q.mpow = pd.iis_mpow; Q.wts = pd.iis_wts; Q.L = pd.iis_L;
+      done = launch_iir_smem(Q, B * nch, pd.iis_cs, st) == 0;
+    }
+    if(! done) LLSM_LAUNCH(iir_filtfilt_kernel, dim3(B * nch), dim3(IIR_NT), 0, st, I);
     if(lc) lc->n += 1;
     lc_mark(lc, st, "iir_filtfilt");
   }

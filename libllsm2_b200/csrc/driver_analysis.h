@@ -106,6 +106,9 @@ struct AnaPlanDev {
   // chunk-parallel IIR tables of the sub-band filters, valid for sequences of iir_nx samples
   DevBuf iir_coef, iir_mpow; int iir_nx = -1, iir_L = 0; int nchannel = 0;
   std::vector<double> h_coef, h_mpow;
+  // shared-memory resident variant (kernels_iir_smem.cuh): cluster size (0: not applicable), chunk length, tables
+  DevBuf iis_mpow, iis_wts; int iis_cs = 0, iis_L = 0;
+  std::vector<double> h_mpow9, h_wts;
   std::vector<void*> owned;
   template <class T> int up(T** dst, const std::vector<T>& src, cudaStream_t st) {
     void* d = nullptr;
@@ -142,11 +145,22 @@ struct AnaPlanDev {
     if(iir_coef.reserve(h_coef.size() * 8) || iir_mpow.reserve(h_mpow.size() * 8)) return -1;
     if(dev_upload(iir_coef.p, h_coef.data(), h_coef.size() * 8, st) ||
        dev_upload(iir_mpow.p, h_mpow.data(), h_mpow.size() * 8, st)) return -1;
+    iir_smem_geometry(nx, iis_cs, iis_L);
+    if(iis_cs > 0) {
+      std::vector<double> coef2(9);
+      h_mpow9.assign((size_t)LLSM_B200_MAXCHANNEL * 2 * IIS_NLOG * 16, 0.0); h_wts.assign((size_t)LLSM_B200_MAXCHANNEL * 2 * iis_L * 4, 0.0);
+      for(int c = 0; c < nchannel; c ++)
+        for(int s2 = 0; s2 < h.chan[c].nstage; s2 ++)
+          build_iir_smem_section(h.chan[c].b[s2], h.chan[c].a[s2], iis_L, coef2.data(),
+            &h_mpow9[((size_t)c * 2 + s2) * IIS_NLOG * 16], &h_wts[((size_t)c * 2 + s2) * iis_L * 4]);
+      if(iis_mpow.reserve(h_mpow9.size() * 8) || iis_wts.reserve(h_wts.size() * 8)) return -1;
+      if(dev_upload(iis_mpow.p, h_mpow9.data(), h_mpow9.size() * 8, st) || dev_upload(iis_wts.p, h_wts.data(), h_wts.size() * 8, st)) return -1;
+    }
     if(dev_sync(st) != 0) return -1;
     iir_nx = nx;
     return 0;
   }
-  void release() { for(void* p : owned) dev_free(p); owned.clear(); iir_coef.release(); iir_mpow.release(); iir_nx = -1; }
+  void release() { for(void* p : owned) dev_free(p); owned.clear(); iir_coef.release(); iir_mpow.release(); iis_mpow.release(); iis_wts.release(); iir_nx = -1; }
 };
 
 struct AnaScratch {
@@ -310,7 +324,12 @@ static inline int run_analyze_l0(const SynthPlanDev& sp, AnaPlanDev& ap, AnaScra
     I.coef = ap.iir_coef.as<double>(); I.mpow = ap.iir_mpow.as<double>();
     for(int c = 0; c < nch; c ++) I.nstage[c] = h.chan[c].nstage;
     I.square = 1;
-    LLSM_LAUNCH(iir_filtfilt_kernel, dim3(B * nch), dim3(IIR_NT), 0, st, I);
+    bool done = false;
+    if(ap.iis_cs > 0 && iir_variant() == 1) {      // sequences resident in (distributed) shared memory
+      IirSmemParams Q; Q.base = I; Q.mpow = ap.iis_mpow.as<double>(); Q.wts = ap.iis_wts.as<double>(); Q.L = ap.iis_L;
+      done = launch_iir_smem(Q, B * nch, ap.iis_cs, st) == 0;
+    }
+    if(! done) LLSM_LAUNCH(iir_filtfilt_kernel, dim3(B * nch), dim3(IIR_NT), 0, st, I);
     if(lc) lc->n ++;
     lc_mark(lc, st, "subband_iir");
 
