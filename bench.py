@@ -465,6 +465,60 @@ def extra_legs(args, ctx, conf, d, x, f0_in, chunk, out, dev):
         res["c1"] = c1_leg(args, ctx, dev)
     except Exception as e:
         res["c1"] = {"unavailable": str(e)}
+    try:
+        res["c3"] = c3_leg(args, ctx, dev)
+    except Exception as e:
+        res["c3"] = {"unavailable": str(e)}
+    return res
+
+
+def c3_leg(args, ctx, dev):
+    """BASELINE configs[2]: batch of 1024 pulse-by-pulse streams through the streaming synthesizer (llsmrt, use_l1), 256
+    harmonics, with the growl llsm_pbpeffect (tools/growl_hook.c, the modifier of test/test-pbpeffects.c:70-85, a host C
+    function called once per glottal pulse in time order) and without it. Host buffers in and out on both arms
+    (llsm_b200_rt_feed_l1_host); with the hook the sequential pulse tracker runs on the host, every sample is still
+    produced on the device."""
+    import subprocess
+    import torch
+    import libllsm2_b200 as L
+    from libllsm2_b200.synthetic import synth_frames
+    so = os.path.join(ROOT, "build", "growl_hook.so")
+    os.makedirs(os.path.dirname(so), exist_ok=True)
+    subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-o", so, os.path.join(ROOT, "tools", "growl_hook.c"), "-lm"])
+    hooklib = C.CDLL(so)
+    S_, K, NFEED = 1024, 8, 6
+    fr, conf = synth_frames(16, K * NFEED, seed=5, nhar=256, maxnhar=256, f0_lo=60, f0_hi=86)
+    rep = (S_ + 15) // 16
+    frb = {k: (np.ascontiguousarray(np.concatenate([v] * rep, 0)[:S_]) if v is not None else None) for k, v in fr.items()}
+    conf.nutt = S_
+    d = {k: (torch.from_numpy(v).to(dev) if v is not None and k != "nfrm_utt" else None) for k, v in frb.items()}
+    l1d = L.tolayer1(ctx, conf, d, 2048)
+    l1 = {k: v.cpu().numpy() for k, v in l1d.items()}
+    pbp = np.ones((S_, K * NFEED), np.int32)
+    res = {"config": "%d streams x %d frames per feed, 256 harmonics, f0 60-86 Hz, every voiced frame pulse-by-pulse, "
+                     "host buffers in / out" % (S_, K)}
+    for name, hooked in (("no_effect_device_tracker", False), ("growl_effect_host_tracker", True)):
+        conf_k = L.abi.make_conf(S_, K, conf.maxnhar, conf.maxnhar_e, conf.npsd, conf.nchannel, conf.fs, conf.thop)
+        rt = L.RtSynth(ctx, conf_k, seed=5, nspec=1025, host_tracker=hooked)
+        state = np.zeros((S_, 3), np.uint32)
+        state[:, 2] = np.arange(S_, dtype=np.uint32) * np.uint32(2654435761) + np.uint32(12345)
+        hook = C.cast(hooklib.growl_hook, C.c_void_p) if hooked else None
+        user = state.ctypes.data_as(C.c_void_p) if hooked else None
+        ts = []
+        for q in range(NFEED):
+            sl = slice(q * K, (q + 1) * K)
+            fq = {k: (np.ascontiguousarray(v[:, sl]) if v is not None and k != "nfrm_utt" else None) for k, v in frb.items()}
+            fq["nhar"] = fq["ampl"] = fq["phse"] = None                 # harmonic model derived from layer 1
+            lq = {k: np.ascontiguousarray(v[:, sl]) for k, v in l1.items()}
+            t0 = time.perf_counter()
+            rt.feed(fq, K, layer1=lq, pbpsyn=np.ascontiguousarray(pbp[:, sl]), hook=hook, user=user)
+            ts.append(time.perf_counter() - t0)
+        dt = float(np.median(ts[1:]))
+        res[name] = {"ms_per_feed": dt * 1e3, "frames_per_s": S_ * K / dt,
+                     "x_realtime_per_stream": K * float(conf.thop) / dt}
+        if hooked:
+            res[name]["pulses_seen_by_hook"] = int(state[:, 0].sum())
+        rt.close()
     return res
 
 

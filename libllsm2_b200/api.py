@@ -327,7 +327,7 @@ class RtSynth:
     def clear(self):
         check(lib().llsm_b200_rt_clear(self._h))
 
-    def feed(self, frames, nfeed=1, layer1=None, pbpsyn=None, hook=None):
+    def feed(self, frames, nfeed=1, layer1=None, pbpsyn=None, hook=None, user=None):
         n = self.output_length(nfeed)
         f = _frames({k: v for k, v in frames.items() if k != "nfrm_utt"})
         got = C.c_int(0)
@@ -353,7 +353,7 @@ class RtSynth:
                 check(lib().llsm_b200_rt_feed_host(self._h, C.byref(f), int(nfeed), _ptr(p), _ptr(ap), n, C.byref(got)))
             else:
                 check(lib().llsm_b200_rt_feed_l1_host(self._h, C.byref(f), C.byref(l1), _ptr(pbpsyn), int(nfeed),
-                                                      hook, None, _ptr(p), _ptr(ap), n, C.byref(got)))
+                                                      hook, user, _ptr(p), _ptr(ap), n, C.byref(got)))
         assert got.value == n
         return p, ap
 

@@ -289,6 +289,50 @@ __device__ __forceinline__ void tf32_split(float x, float& hi, float& lo) {
   lo = x - hi;
 }
 
+// ---- warp-level tensor-core MMA, FP16 operands, FP32 accumulate ---------------------------------------
+// D (16 x 8) += A (16 x 16, row) * B (16 x 8, col). Fragment ownership (g = lane / 4, t = lane % 4), two halves per
+// register, the lower column / row index in the low 16 bits:
+//   a0 = A[g][2t, 2t+1], a1 = A[g+8][2t, 2t+1], a2 = A[g][2t+8, 2t+9], a3 = A[g+8][2t+8, 2t+9]
+//   b0 = B[2t, 2t+1][g], b1 = B[2t+8, 2t+9][g];   d as for the TF32 form.
+// Twice the multiply-adds of the TF32 instruction per issue slot of the tensor pipe.
+__device__ __forceinline__ uint32_t pack_f16x2(float lo_elem, float hi_elem) {
+#ifdef LLSM_EMU
+  _Float16 a = (_Float16)lo_elem, b = (_Float16)hi_elem;
+  uint16_t ua, ub; memcpy(&ua, &a, 2); memcpy(&ub, &b, 2);
+  return (uint32_t)ua | ((uint32_t)ub << 16);
+#else
+  uint32_t d; asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi_elem), "f"(lo_elem)); return d;
+#endif
+}
+__device__ __forceinline__ void mma_f16_16x8x16(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+#ifdef LLSM_EMU
+  static float sa[64][16][16], sb[64][16][8];           // per warp of the (single) running CTA
+  const int lane = threadIdx.x & 31, w = (threadIdx.x >> 5) & 63, g = lane >> 2, t = lane & 3;
+  auto lo = [](uint32_t v) { uint16_t u = (uint16_t)(v & 0xffffu); _Float16 h; memcpy(&h, &u, 2); return (float)h; };
+  auto hi = [](uint32_t v) { uint16_t u = (uint16_t)(v >> 16); _Float16 h; memcpy(&h, &u, 2); return (float)h; };
+  __syncwarp();
+  sa[w][g][2 * t] = lo(a[0]); sa[w][g][2 * t + 1] = hi(a[0]); sa[w][g + 8][2 * t] = lo(a[1]); sa[w][g + 8][2 * t + 1] = hi(a[1]);
+  sa[w][g][2 * t + 8] = lo(a[2]); sa[w][g][2 * t + 9] = hi(a[2]); sa[w][g + 8][2 * t + 8] = lo(a[3]); sa[w][g + 8][2 * t + 9] = hi(a[3]);
+  sb[w][2 * t][g] = lo(b[0]); sb[w][2 * t + 1][g] = hi(b[0]); sb[w][2 * t + 8][g] = lo(b[1]); sb[w][2 * t + 9][g] = hi(b[1]);
+  __syncwarp();
+  for(int k = 0; k < 16; k ++) {
+    d[0] += sa[w][g][k] * sb[w][k][2 * t];     d[1] += sa[w][g][k] * sb[w][k][2 * t + 1];
+    d[2] += sa[w][g + 8][k] * sb[w][k][2 * t]; d[3] += sa[w][g + 8][k] * sb[w][k][2 * t + 1];
+  }
+#else
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+    : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+    : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+#endif
+}
+// x = hi + lo / 2048: hi on FP16's 11-bit mantissa grid (exactly convertible while |x| >= 2^-14), lo the exact
+// remainder scaled into FP16's normal range; products hi hi + (hi lo + lo hi) / 2048 carry 22 bits, as 3xTF32 does
+#define F16_LO_SCALE 2048.0f
+__device__ __forceinline__ void f16_split(float x, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+  lo = (x - hi) * F16_LO_SCALE;
+}
+
 // 2^ceil(e) as an exact integer (device pow() is only accurate to an ulp, and the reference
 // truncates pow(2, ceil(log2(x))) to int: layer0.c:201, dsputils.c:485)
 __host__ __device__ __forceinline__ int pow2_ceil(double e) {

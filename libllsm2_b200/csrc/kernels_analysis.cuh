@@ -401,22 +401,24 @@ __global__ void __launch_bounds__(HD_THREADS) harmonic_dft_kernel(HarmDftParams 
 //   Re X_k =  sum_q [ cos(k w q) Ecc(k, q) - sin(k w q) Ecs(k, q) ],
 //   Im X_k = -sum_q [ cos(k w q) Ocs(k, q) + sin(k w q) Occ(k, q) ],
 //   E{c,s}(k, q) = sum_p e[16 p + q] {cos, sin}(16 k w p)   (same with o),
-// i.e. D[2K x 32] = A[2K x P] * B[P x 32]: A holds the stride-16 phasors (generated in the fragment
-// registers by rotation), B the windowed signal halves e | o (staged once in shared memory). TF32 tensor
-// cores with FP32 accumulation, each product as hi*hi + lo*hi + hi*lo (3xTF32) -- the dropped lo*lo
-// terms are 2^-20 relative. One warp owns tiles of 8 harmonics (16 rows: 8 cosine + 8 sine); the
-// q-phasors and the 16-term q-sum are the FP32 epilogue.
+// i.e. D[2K x 32] = A[2K x P] * B[P x 32]: A holds the stride-16 phasors (generated in the fragment registers by
+// rotation -- no operand staging, which is what a tcgen05 form of this contraction would have to pay: both operands
+// depend on the frame), B the windowed signal halves e | o (staged once in shared memory). Warp-level FP16 tensor-core
+// instructions (m16n8k16) with FP32 accumulation; every operand is split x = hi + lo / 2048 (f16_split) and the product
+// taken as hi hi + (hi lo + lo hi) / 2048 in two accumulator sets: 22 bits, the accuracy of the 3xTF32 form this kernel
+// used before at half its tensor-pipe cycles (that form ran into the pipe: math-pipe throttle was its first stall reason,
+// profiles/r2k). One warp owns tiles of 8 harmonics (16 rows: 8 cosine + 8 sine); the q-phasors and the 16-term q-sum
+// are the FP32 epilogue.
 // ------------------------------------------------------------------------------------------
 #define HM_THREADS 128
-#define HM_ROW 20                                     // float2 row stride of a staged p-row (16 used): conflict-free LDS.64
+#define HM_QS 18                                      // uint4 row stride of a staged p-pair row (16 used): conflict-free LDS.128
 
 __global__ void __launch_bounds__(HM_THREADS) harmonic_mma_kernel(HarmDftParams P) {
   LLSM_DYN_SMEM(smem);
   const int cap = P.mma_cap_half;
-  const int prow = (((cap + 1 + 15) / 16) + 7) & ~7;   // staged p-rows (multiple of 8)
-  float2* sph = (float2*)smem;                        // [prow][HM_ROW] (e_hi, o_hi)
-  float2* spl = sph + (size_t)prow * HM_ROW;          // [prow][HM_ROW] (e_lo, o_lo)
-  float2* sums = spl + (size_t)prow * HM_ROW;         // [maxnhar] DFT sums of the harmonics
+  const int prow = (((cap + 1 + 15) / 16) + 15) & ~15;  // staged p-rows (multiple of 16)
+  uint4* sB = (uint4*)smem;                           // [prow / 2][HM_QS]: {e_hi, e_lo, o_hi, o_lo} of rows (2 p2, 2 p2 + 1), column q
+  float2* sums = (float2*)(sB + (size_t)(prow / 2) * HM_QS);   // [maxnhar] DFT sums of the harmonics
 
   const int i = blockIdx.x, b = blockIdx.y;
   const int nf = P.nfrm_utt ? P.nfrm_utt[b] : P.nfrm;
@@ -442,88 +444,85 @@ __global__ void __launch_bounds__(HM_THREADS) harmonic_mma_kernel(HarmDftParams 
   const float* wv = P.bwin + P.bw_off[half];
   const float winsum = P.bw_sum[half];
 
-  // ---- stage e | o (symmetric / antisymmetric halves), split for 3xTF32, rows of 16 pairs
+  // ---- stage e | o (symmetric / antisymmetric halves of the windowed frame), split, as FP16 pairs over p
   const int npair = half + 1;
-  const int np8 = (((npair + 15) / 16) + 7) & ~7;     // p-rows in use (multiple of 8, <= prow)
-  for(int n0 = tid; n0 < np8 * 16; n0 += 2 * HM_THREADS) {
+  const int np16 = (((npair + 15) / 16) + 15) & ~15;  // p-rows in use (multiple of 16, <= prow)
+  for(int idx = tid; idx < (np16 / 2) * 16; idx += HM_THREADS) {
+    const int p2 = idx >> 4, q = idx & 15;
     float e[2], o[2];
 #pragma unroll
-    for(int u = 0; u < 2; u ++) {                     // two elements in flight per thread
-      const int n = n0 + u * HM_THREADS;
+    for(int u = 0; u < 2; u ++) {
+      const int n = 32 * p2 + 16 * u + q;
       float w = 0.f, xp = 0.f, xm = 0.f;
       if(n < npair) {
         w = wv[n];
-        if(n < half) { const int idx = center + n; if(idx >= 0 && idx < P.nx) xp = x[idx]; }
-        if(n >= 1) { const int idx = center - n; if(idx >= 0 && idx < P.nx) xm = x[idx]; }
+        if(n < half) { const int ix = center + n; if(ix >= 0 && ix < P.nx) xp = x[ix]; }
+        if(n >= 1) { const int ix = center - n; if(ix >= 0 && ix < P.nx) xm = x[ix]; }
       }
       const float a = w * xp, d = w * xm;
       e[u] = a + d; o[u] = a - d;
     }
+    float eh[2], el[2], oh[2], ol[2];
 #pragma unroll
-    for(int u = 0; u < 2; u ++) {
-      const int n = n0 + u * HM_THREADS;
-      if(n < np8 * 16) {
-        float eh, el, oh, ol;
-        tf32_split(e[u], eh, el); tf32_split(o[u], oh, ol);
-        const int at = (n >> 4) * HM_ROW + (n & 15);
-        sph[at] = make_float2(eh, oh); spl[at] = make_float2(el, ol);
-      }
-    }
+    for(int u = 0; u < 2; u ++) { f16_split(e[u], eh[u], el[u]); f16_split(o[u], oh[u], ol[u]); }
+    sB[p2 * HM_QS + q] = make_uint4(pack_f16x2(eh[0], eh[1]), pack_f16x2(el[0], el[1]), pack_f16x2(oh[0], oh[1]), pack_f16x2(ol[0], ol[1]));
   }
   __syncthreads();
 
   const float omega0 = (float)(2.0 * LLSM_PI * (double)f0 / (double)P.fs);   // czt step (FP_TYPE arg)
   const double nu = (double)omega0 / (2.0 * LLSM_PI);                        // turns per sample
   const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int nsteps = np8 >> 3;
+  const int nsteps = np16 >> 4;
 
   for(int mt = warp; mt * 8 < nh; mt += HM_THREADS / 32) {
     const int kg = mt * 8 + g;                        // this lane's harmonic (rows g: cosine, g + 8: sine)
     const double th = (double)(kg + 1) * nu;
     // ---- phasors of this harmonic, b = e^{i 2 pi th}: two seeds with the angle reduced in double (b, b^16), the rest
-    //      by short float product chains (at most four roundings, ~3e-7): b^{2t}, b^{2t+1}, b^{2t+8}, b^{2t+9} for the
-    //      epilogue, b^{16t}, b^{16(t+4)} for the first fragment rows, b^128 to advance them. (Seven independently
-    //      reduced sincospif per tile were 23 % of the kernel's instructions: profiles/r2c.)
+    //      by short float product chains (at most five roundings, ~3e-7): b^{2t}, b^{2t+1}, b^{2t+8}, b^{2t+9} for the
+    //      epilogue; b^{32t} for the first fragment rows, b^16 and b^128 to reach their neighbours, b^256 to advance.
     const float2 b1 = unit_phasor_turns(th), b16 = unit_phasor_turns(th * 16.0);
     const float2 b2 = cmul(b1, b1), b4 = cmul(b2, b2), b6 = cmul(b4, b2), b8 = cmul(b4, b4);
     const float2 one = make_float2(1.f, 0.f);
     const float2 q00 = t == 0 ? one : (t == 1 ? b2 : (t == 2 ? b4 : b6));
     const float2 q01 = cmul(q00, b1), q10 = cmul(q00, b8), q11 = cmul(q01, b8);
-    const float2 b32 = cmul(b16, b16), b48 = cmul(b32, b16), b64 = cmul(b32, b32), z8 = cmul(b64, b64);
-    float2 uA = t == 0 ? one : (t == 1 ? b16 : (t == 2 ? b32 : b48));
-    float2 uB = cmul(uA, b64);
-    float d[4][4];
+    const float2 b32 = cmul(b16, b16), b64 = cmul(b32, b32), b96 = cmul(b64, b32), b128 = cmul(b64, b64), b256 = cmul(b128, b128);
+    float2 u0 = t == 0 ? one : (t == 1 ? b32 : (t == 2 ? b64 : b96));        // p-row 16 s + 2 t
+    float d1[4][4], d2[4][4];
 #pragma unroll
-    for(int j = 0; j < 4; j ++) { d[j][0] = 0.f; d[j][1] = 0.f; d[j][2] = 0.f; d[j][3] = 0.f; }
+    for(int j = 0; j < 4; j ++)
+#pragma unroll
+      for(int c = 0; c < 4; c ++) { d1[j][c] = 0.f; d2[j][c] = 0.f; }
     for(int s = 0; s < nsteps; s ++) {
-      if(s > 0 && (s & 7) == 0) {                     // re-seed every 64 p-rows
-        uA = unit_phasor_turns(th * 16.0 * (double)(8 * s + t));
-        uB = unit_phasor_turns(th * 16.0 * (double)(8 * s + t + 4));
-      }
-      const float a[4] = {uA.x, uA.y, uB.x, uB.y};
-      float ah[4], al[4];
-#pragma unroll
-      for(int e = 0; e < 4; e ++) tf32_split(a[e], ah[e], al[e]);
-      const int r0 = (8 * s + t) * HM_ROW + g, r1 = (8 * s + t + 4) * HM_ROW + g;
+      if(s > 0 && (s & 3) == 0) u0 = unit_phasor_turns(th * 16.0 * (double)(16 * s + 2 * t));   // re-seed every 64 p-rows
+      const float2 u1 = cmul(u0, b16), u2 = cmul(u0, b128), u3 = cmul(u2, b16);   // rows + 1, + 8, + 9
+      float ch[4], cl[4], sh[4], sl[4];
+      f16_split(u0.x, ch[0], cl[0]); f16_split(u1.x, ch[1], cl[1]); f16_split(u2.x, ch[2], cl[2]); f16_split(u3.x, ch[3], cl[3]);
+      f16_split(u0.y, sh[0], sl[0]); f16_split(u1.y, sh[1], sl[1]); f16_split(u2.y, sh[2], sl[2]); f16_split(u3.y, sh[3], sl[3]);
+      const uint32_t ah[4] = {pack_f16x2(ch[0], ch[1]), pack_f16x2(sh[0], sh[1]), pack_f16x2(ch[2], ch[3]), pack_f16x2(sh[2], sh[3])};
+      const uint32_t al[4] = {pack_f16x2(cl[0], cl[1]), pack_f16x2(sl[0], sl[1]), pack_f16x2(cl[2], cl[3]), pack_f16x2(sl[2], sl[3])};
+      const int r0 = (8 * s + t) * HM_QS + g, r1 = (8 * s + t + 4) * HM_QS + g;
 #pragma unroll
       for(int j = 0; j < 2; j ++) {
-        const float2 h0 = sph[r0 + 8 * j], h1 = sph[r1 + 8 * j], l0 = spl[r0 + 8 * j], l1 = spl[r1 + 8 * j];
-        const float beh[2] = {h0.x, h1.x}, boh[2] = {h0.y, h1.y}, bel[2] = {l0.x, l1.x}, bol[2] = {l0.y, l1.y};
-        mma_tf32_16x8x8(d[j], ah, beh); mma_tf32_16x8x8(d[j], al, beh); mma_tf32_16x8x8(d[j], ah, bel);
-        mma_tf32_16x8x8(d[j + 2], ah, boh); mma_tf32_16x8x8(d[j + 2], al, boh); mma_tf32_16x8x8(d[j + 2], ah, bol);
+        const uint4 v0 = sB[r0 + 8 * j], v1 = sB[r1 + 8 * j];
+        const uint32_t beh[2] = {v0.x, v1.x}, bel[2] = {v0.y, v1.y}, boh[2] = {v0.z, v1.z}, bol[2] = {v0.w, v1.w};
+        mma_f16_16x8x16(d1[j], ah, beh); mma_f16_16x8x16(d2[j], ah, bel); mma_f16_16x8x16(d2[j], al, beh);
+        mma_f16_16x8x16(d1[j + 2], ah, boh); mma_f16_16x8x16(d2[j + 2], ah, bol); mma_f16_16x8x16(d2[j + 2], al, boh);
       }
-      uA = cmul(uA, z8); uB = cmul(uB, z8);
+      u0 = cmul(u0, b256);
     }
     // ---- epilogue: q-phasors and the sum over the 16 columns (4 per lane, then across the 4 lanes of a row)
     float re = 0.f, im = 0.f;
     const float2 wqv[2][2] = {{q00, q01}, {q10, q11}};
+    const float rs = 1.0f / F16_LO_SCALE;
 #pragma unroll
     for(int j = 0; j < 2; j ++)
 #pragma unroll
       for(int e = 0; e < 2; e ++) {
         const float2 wq = wqv[j][e];                  // e^{i th (8 j + 2 t + e)}
-        re = fmaf(wq.x, d[j][e], fmaf(-wq.y, d[j][2 + e], re));
-        im = fmaf(-wq.x, d[j + 2][2 + e], fmaf(-wq.y, d[j + 2][e], im));
+        const float ecc = fmaf(d2[j][e], rs, d1[j][e]), ecs = fmaf(d2[j][2 + e], rs, d1[j][2 + e]);
+        const float occ = fmaf(d2[j + 2][e], rs, d1[j + 2][e]), ocs = fmaf(d2[j + 2][2 + e], rs, d1[j + 2][2 + e]);
+        re = fmaf(wq.x, ecc, fmaf(-wq.y, ecs, re));
+        im = fmaf(-wq.x, ocs, fmaf(-wq.y, occ, im));
       }
     re += __shfl_xor_sync(0xffffffffu, re, 1); im += __shfl_xor_sync(0xffffffffu, im, 1);
     re += __shfl_xor_sync(0xffffffffu, re, 2); im += __shfl_xor_sync(0xffffffffu, im, 2);
@@ -539,8 +538,8 @@ __global__ void __launch_bounds__(HM_THREADS) harmonic_mma_kernel(HarmDftParams 
 }
 
 static inline size_t harm_mma_smem(int cap, int maxnhar) {
-  const int prow = (((cap + 1 + 15) / 16) + 7) & ~7;
-  return (size_t)prow * HM_ROW * 8 * 2 + (size_t)maxnhar * 8 + 16;
+  const int prow = (((cap + 1 + 15) / 16) + 15) & ~15;
+  return (size_t)(prow / 2) * HM_QS * 16 + (size_t)maxnhar * 8 + 16;
 }
 
 static inline double mma_min_f0() {
@@ -1469,6 +1468,10 @@ struct KalmanParams {
 // One thread per (utterance, bin): process variance from a 3-frame moving variance of the
 // envelope, observation variance pi^2/6, random-walk Kalman filter + RTS smoother along time
 // (layer0.c:361-385; filter conventions of the oracle's ciglet shim: x0 = z0, P0 = R0).
+// (Tried and dropped: the output stage fused into the backward pass -- 127 bins + a halo bin per CTA, the smoother's
+//  results of eight frames parked in shared memory, the process variance recomputed instead of stored: 7 array passes
+//  instead of 13, but 3.01 ms against 2.06 + 0.79 ms for the two kernels at C2: the double-precision exp / log10 of the
+//  output stage do not overlap with the latency-bound time recursion inside one CTA.)
 __global__ void __launch_bounds__(128) noise_kalman_kernel(KalmanParams P) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
   if(j >= P.nspec) return;

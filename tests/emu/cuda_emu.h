@@ -36,6 +36,7 @@ static inline float2 make_float2(float a, float b) { float2 r = {a, b}; return r
 static inline float4 make_float4(float a, float b, float c, float d) { float4 r = {a, b, c, d}; return r; }
 static inline double2 make_double2(double a, double b) { double2 r = {a, b}; return r; }
 static inline int2 make_int2(int a, int b) { int2 r = {a, b}; return r; }
+static inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) { uint4 r = {a, b, c, d}; return r; }
 
 namespace emu {
 struct BlockCtx {
