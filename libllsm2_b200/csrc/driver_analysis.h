@@ -262,11 +262,17 @@ static inline int run_analyze_l0(const SynthPlanDev& sp, AnaPlanDev& ap, AnaScra
   {
     llsm_b200_frames fin; memset(&fin, 0, sizeof(fin));
     fin.nfrm_utt = nfrm_utt; fin.f0 = fr.f0; fin.nhar = fr.nhar; fin.ampl = fr.ampl; fin.phse = fr.phse;
-    int rc = run_harmonics(sp, conf, fin, nullptr, nullptr, sc.x_sin.as<float>(), nx, nx, nx, st, lc);
+    // the subtraction rides in the bank's write when the direct-summation kernel runs (options == NULL keeps it there
+    // unless LLSM_RESIDUAL_TC is set): one pass over the waveform and one launch less
+    const bool fused = ! (bank_tc_enabled() && residual_tc_enabled() && conf.maxnhar >= 24);
+    int rc = fused ? run_harmonics(sp, conf, fin, nullptr, nullptr, x_res, nx, nx, rstride, st, lc, 0, 0, x, xstride)
+                   : run_harmonics(sp, conf, fin, nullptr, nullptr, sc.x_sin.as<float>(), nx, nx, nx, st, lc);
     if(rc != 0) return rc;
-    LLSM_LAUNCH(residual_kernel, dim3((nx + 255) / 256, B), dim3(256), 0, st,
-      x, (const float*)sc.x_sin.as<float>(), x_res, nx, xstride, nx, rstride);
-    if(lc) lc->n ++;
+    if(! fused) {
+      LLSM_LAUNCH(residual_kernel, dim3((nx + 255) / 256, B), dim3(256), 0, st,
+        x, (const float*)sc.x_sin.as<float>(), x_res, nx, xstride, nx, rstride);
+      if(lc) lc->n ++;
+    }
     lc_mark(lc, st, "residual_bank");
   }
 

@@ -39,6 +39,7 @@ struct BankParams {
   int frame_lo, frame_hi;   // frames [lo, hi) contribute (frame-range sharding); hi <= 0 means all
   int npass;                // frame slots per CTA = warps * npass
   float hop;                // thop * fs (float product): hm_base[f] = round(f * hop)
+  const float* sub_from; int sub_stride;   // optional [B][sub_stride]: write sub_from - y instead of y (analysis residual, layer0.c:500-501)
   float* y_sin;             // [B][stride]
   double iczt_nh;           // tensor-core bank: exp(log(n_hm) a + b), the harmonic count above which the ICZT branch is taken
 };
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(NTHR, MINB) hm_bank_ola_kernel(BankParams P) {
         if(sv[s] && j < N) acc += fb[(size_t)s * npad + j];
       }
     }
-    yrow[idx] = acc;
+    yrow[idx] = P.sub_from ? P.sub_from[(size_t)b * P.sub_stride + idx] - acc : acc;
   }
 }
 
