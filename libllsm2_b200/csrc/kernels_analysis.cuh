@@ -1241,6 +1241,16 @@ __global__ void __launch_bounds__(NS_THREADS) noise_spec_kernel(NoiseSpecParams 
 #define NSW_WBYTES (WFFT_SCRATCH_BYTES)
 static inline size_t noise_spec_warp_smem() { return (size_t)2 * 1024 * 8 + (size_t)NSW_WARPS * NSW_WBYTES + 16; }
 
+// natural logarithm through the special-function unit (lg2.approx: ~2 ulp at the magnitudes met here, i.e. ~2e-6
+// nepers on log spectra around -10; logf's range reduction and polynomial were 12 % of the kernel's instructions)
+__device__ __forceinline__ float nsw_log(float v) {
+#ifdef LLSM_EMU
+  return logf(v);
+#else
+  return __logf(v);
+#endif
+}
+
 // log |X[k]| of the 2048-point real spectrum from the packed transform: Z = Z[k], Zp = Z[N - k], W = W2048^k
 __device__ __forceinline__ float nsw_logmag(float2 Z, float2 Zp, float2 W, float nrm2) {
   const float ar = 0.5f * (Z.x + Zp.x), ai = 0.5f * (Z.y - Zp.y);
@@ -1248,7 +1258,7 @@ __device__ __forceinline__ float nsw_logmag(float2 Z, float2 Zp, float2 W, float
   const float tr = W.x * br - W.y * bi, ti = W.x * bi + W.y * br;     // W^k (Z - Z*p) / 2
   const float xr = ar + ti, xi = ai - tr;
   const float m = (xr * xr + xi * xi) * nrm2;                           // log(|X| nrm) = log(|X|^2 nrm^2) / 2: no square root
-  return 0.5f * logf(m > 1e-20f ? m : 1e-20f);
+  return 0.5f * nsw_log(m > 1e-20f ? m : 1e-20f);
 }
 // packed spectrum of the inverse real transform from L = L[k], Lp = L[N - k] (both real), W = W2048^k
 __device__ __forceinline__ float2 nsw_pack(float L, float Lp, float2 W) {
@@ -1309,8 +1319,15 @@ __global__ void __launch_bounds__(NSW_THREADS, 2) noise_spec_warp_kernel(NoiseSp
         __syncwarp();
         const int first = cen - ws / 2;
         if(first >= 0 && first + ws <= P.nx) {                   // interior frame: no bounds tests
-          for(int j = lane; j < ws; j += 32)
-            buf[(j - ws / 2) & (2 * NF - 1)] = xs[first + j] * (0.5f - 0.5f * cospif((float)j * rws));
+          // cos(2 pi j / ws) along the lane's taps j = lane, lane + 32, ... by rotation from two seeds (<= 69 steps,
+          // ~4e-6 at the far end of the longest window; the envelope only feeds the Kalman filter's process variance)
+          float cj, sj, cd, sd;
+          sincospif((float)lane * rws, &sj, &cj);
+          sincospif(32.0f * rws, &sd, &cd);
+          for(int j = lane; j < ws; j += 32) {
+            buf[(j - ws / 2) & (2 * NF - 1)] = xs[first + j] * fmaf(-0.5f, cj, 0.5f);
+            const float cn = cj * cd - sj * sd; sj = fmaf(sj, cd, cj * sd); cj = cn;
+          }
         } else {
           for(int j = lane; j < ws; j += 32) {
             const int idx = first + j;
@@ -1377,7 +1394,7 @@ __global__ void __launch_bounds__(NSW_THREADS, 2) noise_spec_warp_kernel(NoiseSp
         const float2 wa = w2k[k], wb = make_float2(-wa.x, wa.y);                   // W^{N-k} = -conj(W^k)
         if(k == 0) {
           const float m0 = (za.x + za.y) * (za.x + za.y) * nrm2, m1 = (za.x - za.y) * (za.x - za.y) * nrm2;   // X[0], X[1024]
-          const float L0 = 0.5f * logf(m0 > 1e-20f ? m0 : 1e-20f), L1 = 0.5f * logf(m1 > 1e-20f ? m1 : 1e-20f);
+          const float L0 = 0.5f * nsw_log(m0 > 1e-20f ? m0 : 1e-20f), L1 = 0.5f * nsw_log(m1 > 1e-20f ? m1 : 1e-20f);
           scratch[0] = make_float2(L0 + L1, L0 - L1);
         } else {
           const float La = nsw_logmag(za, zb, wa, nrm2), Lb = nsw_logmag(zb, za, wb, nrm2);
@@ -1448,8 +1465,8 @@ __global__ void __launch_bounds__(NSW_THREADS, 2) noise_spec_warp_kernel(NoiseSp
         const float br = 0.5f * (zk.y + zn.y), bi = -0.5f * (zk.x - zn.x);
         const float pa = __fadd_rn(__fmul_rn(ar, ar), __fmul_rn(ai, ai)) / P.win_power;
         const float pb = __fadd_rn(__fmul_rn(br, br), __fmul_rn(bi, bi)) / P.win_power;
-        P.lpsd[orow + j] = logf(pa > 1e-10f ? pa : 1e-10f);                        // layer0.c:358
-        if(two) P.lpsd[orow + NSPEC + j] = logf(pb > 1e-10f ? pb : 1e-10f);
+        P.lpsd[orow + j] = nsw_log(pa > 1e-10f ? pa : 1e-10f);                     // layer0.c:358
+        if(two) P.lpsd[orow + NSPEC + j] = nsw_log(pb > 1e-10f ? pb : 1e-10f);
       }
     }
   }
