@@ -39,6 +39,7 @@ struct llsm_b200_ctx {
   std::map<AnaKey, std::unique_ptr<AnaPlanDev>> aplans;
   SynthScratch scratch;
   AnaScratch ascratch;
+  AnaFork afork;
   std::unique_ptr<L1PlanDev> l1plan;
   std::unique_ptr<CoderPlanDev> coderplan;
   PbpScratch pbp;
@@ -145,6 +146,9 @@ void llsm_b200_destroy(llsm_b200_ctx* ctx) {
   for(auto& e : ctx->kt_ev) if(e) cudaEventDestroy(e);
   ctx->phase_theta.release();
   if(ctx->coderplan) ctx->coderplan->release();
+  if(ctx->afork.st2) cudaStreamDestroy(ctx->afork.st2);
+  if(ctx->afork.fork) cudaEventDestroy(ctx->afork.fork);
+  if(ctx->afork.join) cudaEventDestroy(ctx->afork.join);
   if(ctx->s_in) cudaStreamDestroy(ctx->s_in);
   if(ctx->s_out) cudaStreamDestroy(ctx->s_out);
   if(ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);

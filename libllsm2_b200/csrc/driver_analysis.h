@@ -218,11 +218,27 @@ static inline int run_harmonic_pass(const SynthPlanDev& sp, AnaPlanDev& ap, AnaS
   return 0;
 }
 
+// Second stream of the analysis: after the residual the noise-PSD chain (spectra -> Kalman / RTS -> output) and the
+// sub-band envelope chain (IIR -> envelope harmonics) are independent; on two streams the HBM-bound smoother runs beside
+// the FP64-bound filter and the output stage beside the envelope kernel. Not used while per-kernel timing is recorded.
+struct AnaFork {
+#ifndef LLSM_EMU
+  cudaStream_t st2 = nullptr; cudaEvent_t fork = nullptr, join = nullptr;
+#else
+  int unused = 0;
+#endif
+};
+static inline int ana_overlap_enabled() {
+  static int v = -1;
+  if(v < 0) { const char* e = getenv("LLSM_ANA_OVERLAP"); v = e ? atoi(e) : 1; }
+  return v;
+}
+
 // x: [B][xstride] device; fr: device output arrays; x_res_out optional [B][xstride]
 static inline int run_analyze_l0(const SynthPlanDev& sp, AnaPlanDev& ap, AnaScratch& sc,
   const llsm_b200_conf& conf, const llsm_b200_aoptions& opt, const float* x, int nx, int xstride,
   const llsm_b200_frames_out& fr, const int* nfrm_utt, float* x_res_out, cudaStream_t st,
-  LaunchCounter* lc) {
+  LaunchCounter* lc, const AnaFork* fork = nullptr) {
   const int B = conf.nutt, F = conf.nfrm, nch = conf.nchannel;
   const AnaPlan& h = ap.h;
   if(opt.hm_method != 0 && opt.hm_method != 1) return LLSM_B200_EINVAL;
@@ -250,12 +266,12 @@ static inline int run_analyze_l0(const SynthPlanDev& sp, AnaPlanDev& ap, AnaScra
 
   // 2. harmonic analysis of x (dsputils.c:175-228)
   auto harmonic_pass = [&](const float* sig, int nsig, int sstride, int maxnhar, int* nhar_o, float* ampl_o, float* phse_o,
-                           float* edc_o) -> int {
+                           float* edc_o, cudaStream_t hs) -> int {
     return run_harmonic_pass(sp, ap, sc, conf, opt, fr.f0, nfrm_utt, sig, nsig, nx, sstride, maxnhar, nhar_o, ampl_o,
-      phse_o, edc_o, false, st, lc);
+      phse_o, edc_o, false, hs, lc);
   };
   if(opt.hm_method == 0) { int rc = run_utt_fftsize(sc, conf, opt, fr.f0, nfrm_utt, st, lc); if(rc) return rc; }
-  { int rc = harmonic_pass(x, 1, xstride, conf.maxnhar, fr.nhar, fr.ampl, fr.phse, nullptr); if(rc) return rc; }
+  { int rc = harmonic_pass(x, 1, xstride, conf.maxnhar, fr.nhar, fr.ampl, fr.phse, nullptr, st); if(rc) return rc; }
   lc_mark(lc, st, opt.hm_method == 1 ? "harmonic_czt" : "harmonic_pp");
 
   // 3. residual: x - resynthesised sinusoids (layer0.c:498-501; options == NULL, ny = nx)
@@ -276,8 +292,8 @@ static inline int run_analyze_l0(const SynthPlanDev& sp, AnaPlanDev& ap, AnaScra
     lc_mark(lc, st, "residual_bank");
   }
 
-  // 4. noise PSD (layer0.c:318-415)
-  {
+  // 4. noise PSD (layer0.c:318-415): spectra, Kalman / RTS smoother, output stage
+  auto noise_spec_stage = [&](cudaStream_t s) {
     NoiseSpecParams N; memset(&N, 0, sizeof(N));
     N.nfrm = F; N.nfrm_utt = nfrm_utt; N.x = x; N.xstride = xstride; N.x_res = x_res; N.rstride = rstride;
     N.nx = nx; N.f0 = fr.f0; N.center = sp.hm_base; N.fs = conf.fs;
@@ -293,36 +309,38 @@ static inline int run_analyze_l0(const SynthPlanDev& sp, AnaPlanDev& ap, AnaScra
       cudaFuncSetAttribute(noise_spec_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 #endif
       const int npair = (F + 1) / 2;
-      LLSM_LAUNCH(noise_spec_warp_kernel, dim3((npair + NSW_WARPS - 1) / NSW_WARPS, B), dim3(NSW_THREADS), smem, st, N);
+      LLSM_LAUNCH(noise_spec_warp_kernel, dim3((npair + NSW_WARPS - 1) / NSW_WARPS, B), dim3(NSW_THREADS), smem, s, N);
     } else {
       size_t smem = (size_t)(fpad_host(std::max(h.nfft, h.nfft_s)) + 1) * 16 + 16;
 #ifndef LLSM_EMU
       cudaFuncSetAttribute(noise_spec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 #endif
-      LLSM_LAUNCH(noise_spec_kernel, dim3((F + 1) / 2, B), dim3(NS_THREADS), smem, st, N);
+      LLSM_LAUNCH(noise_spec_kernel, dim3((F + 1) / 2, B), dim3(NS_THREADS), smem, s, N);
     }
     if(lc) lc->n ++;
-    lc_mark(lc, st, "noise_spec");
-
+    lc_mark(lc, s, "noise_spec");
+  };
+  auto kalman_stage = [&](cudaStream_t s) {
     KalmanParams K; memset(&K, 0, sizeof(K));
     K.nfrm = F; K.nspec = h.nspec; K.nfrm_utt = nfrm_utt;
     K.env = sc.env.as<float>(); K.lpsd = sc.lpsd.as<float>(); K.res = sc.res.as<float>();
     K.filt = sc.filt.as<float>(); K.pvar = sc.pvar.as<float>();
-    LLSM_LAUNCH(noise_kalman_kernel, dim3((h.nspec + 127) / 128, B), dim3(128), 0, st, K);
+    LLSM_LAUNCH(noise_kalman_kernel, dim3((h.nspec + 127) / 128, B), dim3(128), 0, s, K);
     if(lc) lc->n ++;
-    lc_mark(lc, st, "noise_kalman");
-
+    lc_mark(lc, s, "noise_kalman");
+  };
+  auto psd_out_stage = [&](cudaStream_t s) {
     PsdOutParams O; memset(&O, 0, sizeof(O));
     O.nfrm = F; O.nspec = h.nspec; O.npsd = conf.npsd; O.nfrm_utt = nfrm_utt;
     O.lpsd = sc.lpsd.as<float>(); O.res = sc.res.as<float>(); O.ip_k = ap.ip_k; O.ip_r = ap.ip_r;
     O.fs = conf.fs; O.psd = fr.psd; O.psdres = fr.psdres;
-    LLSM_LAUNCH(noise_psd_out_kernel, dim3(F, B), dim3(128), 0, st, O);
+    LLSM_LAUNCH(noise_psd_out_kernel, dim3(F, B), dim3(128), 0, s, O);
     if(lc) lc->n ++;
-    lc_mark(lc, st, "noise_psd_out");
-  }
+    lc_mark(lc, s, "noise_psd_out");
+  };
 
-  // 5. noise envelope per channel (layer0.c:417-469)
-  {
+  // 5. noise envelope per channel (layer0.c:417-469): sub-band IIR, then harmonics + short-time means of the envelopes
+  auto iir_stage = [&](cudaStream_t s) {
     IirParams I; memset(&I, 0, sizeof(I));
     I.nchannel = nch; I.n = nx; I.L = ap.iir_L; I.y = sc.ce.as<float>(); I.ystride = cst; I.vec_ok = 1;
     I.src_a = x_res; I.sa_stride = rstride; I.src_b = x; I.sb_stride = xstride;
@@ -333,28 +351,52 @@ static inline int run_analyze_l0(const SynthPlanDev& sp, AnaPlanDev& ap, AnaScra
     bool done = false;
     if(ap.iis_cs > 0 && iir_variant() == 1) {      // sequences resident in (distributed) shared memory
       IirSmemParams Q; Q.base = I; Q.mpow = ap.iis_mpow.as<double>(); Q.wts = ap.iis_wts.as<double>(); Q.L = ap.iis_L;
-      done = launch_iir_smem(Q, B * nch, ap.iis_cs, st) == 0;
+      done = launch_iir_smem(Q, B * nch, ap.iis_cs, s, s != st) == 0;
     }
-    if(! done) LLSM_LAUNCH(iir_filtfilt_kernel, dim3(B * nch), dim3(IIR_NT), 0, st, I);
+    if(! done) LLSM_LAUNCH(iir_filtfilt_kernel, dim3(B * nch), dim3(IIR_NT), 0, s, I);
     if(lc) lc->n ++;
-    lc_mark(lc, st, "subband_iir");
-
-    // CZT pass: the short-time means ride along in the same kernel; peak picking keeps the separate kernel
-    const bool dc_fused = conf.maxnhar_e > 0 && opt.hm_method == 1;
+    lc_mark(lc, s, "subband_iir");
+  };
+  // CZT pass: the short-time means ride along in the same kernel; peak picking keeps the separate kernel
+  const bool dc_fused = conf.maxnhar_e > 0 && opt.hm_method == 1;
+  auto envelope_stage = [&](cudaStream_t s) -> int {
     if(conf.maxnhar_e > 0) {
       int rc = harmonic_pass(sc.ce.as<float>(), nch, cst, conf.maxnhar_e, fr.enhar, fr.eampl, fr.ephse,
-        dc_fused ? fr.edc : nullptr);
+        dc_fused ? fr.edc : nullptr, s);
       if(rc) return rc;
-      lc_mark(lc, st, "envelope_harmonics");
+      lc_mark(lc, s, "envelope_harmonics");
     }
     if(dc_fused) return 0;
-
     DcParams D; memset(&D, 0, sizeof(D));
     D.nfrm = F; D.nchannel = nch; D.nfrm_utt = nfrm_utt; D.ce = sc.ce.as<float>(); D.cstride = cst; D.nx = nx;
     D.f0 = fr.f0; D.center = sp.hm_base; D.fs = conf.fs; D.thop = conf.thop; D.edc = fr.edc;
-    LLSM_LAUNCH(frame_dc_kernel, dim3(F, B * nch), dim3(128), 0, st, D);
+    LLSM_LAUNCH(frame_dc_kernel, dim3(F, B * nch), dim3(128), 0, s, D);
     if(lc) lc->n ++;
-    lc_mark(lc, st, "frame_dc");
+    lc_mark(lc, s, "frame_dc");
+    return 0;
+  };
+
+#ifndef LLSM_EMU
+  if(fork && fork->st2 && dc_fused && ana_overlap_enabled() && ! (lc && lc->ev)) {
+    // The second stream joins in after the spectra: the sub-band filter's grid is persistent (one cluster slot per SM),
+    // so all of it is dispatched at once and the smoother's CTAs, launched right behind it, share the SMs with it -- a
+    // grid larger than the machine would keep the block scheduler to itself until its last wave (measured: two full-size
+    // kernels on two streams take exactly the sum of their times).
+    noise_spec_stage(st);
+    cudaEventRecord(fork->fork, st);
+    cudaStreamWaitEvent(fork->st2, fork->fork, 0);
+    iir_stage(fork->st2);
+    kalman_stage(st);
+    const int rc = envelope_stage(fork->st2);
+    psd_out_stage(st);
+    cudaEventRecord(fork->join, fork->st2);
+    cudaStreamWaitEvent(st, fork->join, 0);
+    return rc;
   }
-  return 0;
+#else
+  (void)fork;
+#endif
+  noise_spec_stage(st); kalman_stage(st); psd_out_stage(st);
+  iir_stage(st);
+  return envelope_stage(st);
 }

@@ -1576,22 +1576,24 @@ struct PsdOutParams {
   float* psd; float* psdres;           // [B][nfrm][npsd]
 };
 
+// (Arithmetic in float: the reference evaluates these in FP_TYPE; the double-precision exp / log10 this kernel used first
+//  made it FP64- and conversion-bound -- 44 % / 49 % of those pipes, profiles/r2t -- for differences of 1e-6 dB.)
 __global__ void __launch_bounds__(128) noise_psd_out_kernel(PsdOutParams P) {
   const int i = blockIdx.x, b = blockIdx.y;
   const int nf = P.nfrm_utt ? P.nfrm_utt[b] : P.nfrm;
   if(i >= nf) return;
   const size_t irow = ((size_t)b * P.nfrm + i) * P.nspec, orow = ((size_t)b * P.nfrm + i) * P.npsd;
+  const float sc = 44100.0f / P.fs;
   for(int j = threadIdx.x; j < P.npsd; j += blockDim.x) {
-    int k = P.ip_k[j]; float r = P.ip_r[j];
+    const int k = P.ip_k[j]; const float r = P.ip_r[j];
     float a = P.lpsd[irow + k], rr = P.res[irow + k];
     if(r != 0.f) {
-      a = (float)((double)a + ((double)P.lpsd[irow + k + 1] - (double)a) * (double)r);
-      rr = (float)((double)rr + ((double)P.res[irow + k + 1] - (double)rr) * (double)r);
+      a = fmaf(P.lpsd[irow + k + 1] - a, r, a);
+      rr = fmaf(P.res[irow + k + 1] - rr, r, rr);
     }
-    float ex = (float)exp((double)a);                                           // layer0.c:402
-    float lin = ex * 44100.0f / P.fs;
-    P.psd[orow + j] = (float)(10.0 * log10((double)lin + 1e-12));               // layer0.c:403
-    P.psdres[orow + j] = (float)((double)rr / 2.3025851 * 10.0);                // LOG2IN
+    const float lin = expf(a) * sc;                                               // layer0.c:402
+    P.psd[orow + j] = 10.0f * log10f(lin + 1e-12f);                               // layer0.c:403
+    P.psdres[orow + j] = rr * (float)(10.0 / 2.3025851);                          // LOG2IN
   }
 }
 

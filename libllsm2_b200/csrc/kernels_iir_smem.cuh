@@ -34,6 +34,7 @@ struct IirSmemParams {
   const double* mpow;       // [nchannel][2][IIS_NLOG][16]
   const double* wts;        // [nchannel][2][L][4]: A^j B, j = 0 .. L - 1
   int L;                    // chunk length (odd)
+  int nseq;                 // sequences; the grid is persistent: cluster c serves sequences c, c + gridDim / CS, ...
 };
 
 static inline size_t iir_smem_bytes(int L) {
@@ -53,17 +54,26 @@ __global__ void __launch_bounds__(IIS_NT, 2) iir_smem_kernel(IirSmemParams Q) {
   double* wt = mp + IIS_NLOG * 16;                         // [L][4]
   float* s = (float*)(wt + (size_t)L * 4);                 // [IIS_NT * L] this CTA's samples
   const int tid = threadIdx.x;
-  const int seq = blockIdx.x / CS, rank = blockIdx.x % CS;
-  const int c = seq % P.nchannel;
-  float* y = P.y + (size_t)seq * P.ystride;
+  const int rank = blockIdx.x % CS;
   const int n = P.n;
-  const int nst = P.nstage[c];
   const int part = IIS_NT * L;                             // samples per CTA
   const int g0 = rank * part;                              // first sample of this CTA
   const int mine = max(0, min(n - g0, part));              // real samples held here
+#ifndef LLSM_EMU
+  cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
+#endif
+  if(tid == 0) bulk_bar_init(bar);
+  __syncthreads();
+  int phase = 0, round = 0;
+  // persistent: the grid is sized to the machine, so every CTA is dispatched at once and a kernel launched behind this
+  // one on another stream (the analysis runs the HBM-bound Kalman smoother there) shares the SMs with it
+  for(int seq = blockIdx.x / CS; seq < Q.nseq; seq += gridDim.x / CS) {
+  const int c = seq % P.nchannel;
+  float* y = P.y + (size_t)seq * P.ystride;
+  const int nst = P.nstage[c];
   if(nst == 0) {                                           // channel absent: silence (uniform over the cluster)
     for(int i = tid; i < mine; i += IIS_NT) y[g0 + i] = 0.f;
-    return;
+    continue;
   }
   const float* src = y;
   if(P.src_a || P.src_b) {
@@ -74,21 +84,20 @@ __global__ void __launch_bounds__(IIS_NT, 2) iir_smem_kernel(IirSmemParams Q) {
   // ---- the sequence part: bulk copies when the row is 16-byte aligned, plain loads otherwise; zero padding behind it
   const bool aligned = (((uintptr_t)(src + g0)) & 15) == 0;
   const int nbulk = aligned ? (mine & ~3) : 0;
-  if(tid == 0) bulk_bar_init(bar);
-  __syncthreads();
+#ifndef LLSM_EMU
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy accesses above, async-proxy writes below
+#endif
+  __syncthreads();                                          // the previous sequence has left shared memory
   if(tid == 0) {
     bulk_expect(bar, (uint32_t)(nbulk * 4));
     for(int o = 0; o < nbulk; o += 8192)
       bulk_g2s(s + o, src + g0 + o, (uint32_t)(min(8192, nbulk - o) * 4), bar);
   }
   for(int i = nbulk + tid; i < part; i += IIS_NT) s[i] = i < mine ? src[g0 + i] : 0.f;
-  bulk_wait(bar, 0);
+  bulk_wait(bar, (uint32_t)(round & 1));
+  round ++;
   __syncthreads();
 
-#ifndef LLSM_EMU
-  cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
-#endif
-  int phase = 0;
   for(int st = 0; st < nst; st ++) {
     __syncthreads();
     if(tid < 9) cfs[tid] = P.coef[((size_t)c * 2 + st) * 9 + tid];
@@ -194,6 +203,7 @@ __global__ void __launch_bounds__(IIS_NT, 2) iir_smem_kernel(IirSmemParams Q) {
   } else {
     for(int i = tid; i < mine; i += IIS_NT) y[g0 + i] = s[i];
   }
+  }
 #ifndef LLSM_EMU
   if(CS > 1) cluster.sync();                                 // no CTA leaves while its totals may still be read
 #endif
@@ -230,24 +240,35 @@ static inline void build_iir_smem_section(const double b[5], const double a[5], 
 }
 
 // launch on nseq sequences; returns -1 when the configuration does not fit (caller falls back to the streaming kernel)
-static inline int launch_iir_smem(const IirSmemParams& Q, int nseq, int cs, cudaStream_t st) {
+static inline int launch_iir_smem(const IirSmemParams& Q, int nseq, int cs, cudaStream_t st, bool persistent = false) {
   const size_t smem = iir_smem_bytes(Q.L);
   if(getenv("LLSM_IIR_TRACE")) fprintf(stderr, "iir_smem: nseq %d n %d cluster %d L %d smem %zu\n", nseq, Q.base.n, cs, Q.L, smem);
 #ifdef LLSM_EMU
   if(cs != 1) return -1;
-  LLSM_LAUNCH(iir_smem_kernel<1>, dim3(nseq), dim3(IIS_NT), smem, st, Q);
+  IirSmemParams Q2 = Q; Q2.nseq = nseq;
+  LLSM_LAUNCH(iir_smem_kernel<1>, dim3(std::min(nseq, 3)), dim3(IIS_NT), smem, st, Q2);
   return 0;
 #else
   if(smem > 227 * 1024) return -1;
+  IirSmemParams Q2 = Q; Q2.nseq = nseq;
+  int dev = 0, sms = 148;
+  if(cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int per_sm = smem <= 110 * 1024 ? 2 : 1;
+  // persistent (a machine-sized grid walking the sequences) only where another stream is to share the SMs: with a
+  // CTA per sequence the hardware overlaps one CTA's load and store with its neighbour's arithmetic (templates: 0.58 ms
+  // against 0.77 ms persistent)
+  int nclu = persistent ? sms * per_sm / cs : nseq;
+  if(nclu > nseq) nclu = nseq;
+  if(nclu < 1) nclu = 1;
   cudaLaunchConfig_t cfg; memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((unsigned)(nseq * cs)); cfg.blockDim = dim3(IIS_NT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cfg.gridDim = dim3((unsigned)(nclu * cs)); cfg.blockDim = dim3(IIS_NT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = (unsigned)cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
   cudaError_t e = cudaErrorInvalidValue;
 #define LLSM_IIS_GO(CSV) { auto kfn = iir_smem_kernel<CSV>; \
     if(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { cudaGetLastError(); return -1; } \
-    e = cudaLaunchKernelEx(&cfg, kfn, Q); }
+    e = cudaLaunchKernelEx(&cfg, kfn, Q2); }
   if(cs == 1) LLSM_IIS_GO(1) else if(cs == 2) LLSM_IIS_GO(2) else if(cs == 4) LLSM_IIS_GO(4) else if(cs == 8) LLSM_IIS_GO(8)
 #undef LLSM_IIS_GO
   if(e != cudaSuccess) { cudaGetLastError(); return -1; }
