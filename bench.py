@@ -258,7 +258,7 @@ def kernel_bytes(conf, nx):
     hm = 2.0 * conf.maxnhar * 4 + 8                          # ampl, phse, f0, nhar
     return {
         "refine_f0": hop + 8, "harmonic_czt": hop + 4 + hm, "harmonic_pp": hop + 4 + hm,
-        "residual_bank": hm + 3 * hop,                       # parameters in, x in, x_sin + x_res
+        "residual_bank": hm + 2 * hop,                       # parameters in, x in, x_res out (the subtraction is fused)
         "noise_spec": 2 * hop + 2 * nspec * 4, "noise_kalman": 4 * nspec * 4,
         "noise_psd_out": 2 * nspec * 4 + 2 * conf.npsd * 4, "subband_iir": 2 * hop + nch * hop,
         "envelope_harmonics": nch * hop + nch * (8 + 8 * ne), "frame_dc": nch * hop + nch * 4,
