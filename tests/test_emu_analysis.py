@@ -59,3 +59,30 @@ def test_analysis_two_channels():
                             C.byref(fo), o["x_res"].ctypes.data_as(C.c_void_p))
     assert rc == 0
     check_analysis(o, ref, conf)
+
+
+def _emu_case(B, F, **kw):
+    fr, conf = S.synth_frames(B, F, **kw)
+    y, ys, yn = S.ref_synthesize(fr, conf, seed=7)
+    nx = y.shape[1]
+    ref = S.ref_analyze(y, fr["f0"], conf, hm_method=1)
+    emu = S.load_emu()
+    o = S.alloc_analysis_out(conf, nx, fr["f0"])
+    ao = abi.AOptions(); ao.f0_refine = 1; ao.hm_method = 1; ao.rel_winsize = 4.0
+    fo = S.frames_out_struct(o)
+    rc = emu.emu_analyze_l0(C.byref(conf), C.byref(ao), y.ctypes.data_as(C.c_void_p), nx, nx,
+                            C.byref(fo), o["x_res"].ctypes.data_as(C.c_void_p))
+    assert rc == 0
+    check_analysis(o, ref, conf)
+
+
+def test_analysis_low_f0_frame_list():
+    """f0 50-78 Hz: windows beyond the staged kernels' capacity (four periods of 80 Hz) -- both harmonic passes hand
+    every voiced frame to the general kernels through the device frame list; the noise spectra's three-period Hann
+    window exceeds 2048 samples (time-aliased path of the warp kernel)."""
+    _emu_case(1, 21, seed=22, nhar=100, maxnhar=128, f0_lo=50, f0_hi=78)
+
+
+def test_analysis_16k_three_channels():
+    """16 kHz, three noise channels: transform sizes 512 / 512 (block-FFT noise spectra), odd frame count."""
+    _emu_case(1, 25, seed=24, nhar=40, maxnhar=40, fs=16000.0, f0_lo=100, f0_hi=200, nch=3)

@@ -145,3 +145,28 @@ def test_anasynth_host_chain(ctx, phase_ops):
     # y only, slicing invariance
     y_only = L.anasynth_host(ctx, conf, x, fr["f0"], white=white, phase_ops=phase_ops)
     assert np.array_equal(y_only["y"], out["y"])
+
+
+def test_analysis_long_utterance_cluster_of_eight(ctx):
+    """7.5 s utterance: the sub-band filter's sequence (330 k samples) is spread over a cluster of eight CTAs
+    (kernels_iir_smem.cuh: carry between the CTAs through distributed shared memory); odd frame count, so the noise
+    spectra's last warp works on a lone frame."""
+    _case(ctx, 1, 1501, seed=21, nhar=60, maxnhar=64)
+
+
+def test_analysis_low_f0_long_windows(ctx):
+    """f0 50-78 Hz: every voiced frame's window exceeds the staged kernels' capacity (four periods of 80 Hz), so the
+    main and the envelope pass go through the device frame list to the general kernels, and the noise spectra's Hann
+    window (three periods) exceeds 2048 samples: the time-aliased path of the warp kernel."""
+    _case(ctx, 2, 60, seed=22, nhar=100, maxnhar=128, f0_lo=50, f0_hi=78)
+
+
+def test_analysis_48k(ctx):
+    """48 kHz: other window lengths, same transform sizes (2048 / 1024: the warp kernel)."""
+    _case(ctx, 1, 80, seed=23, nhar=100, maxnhar=128, fs=48000.0)
+
+
+def test_analysis_16k_block_fft_path(ctx):
+    """16 kHz: transform sizes 512 / 512, served by the block-FFT noise-spectra kernel; sequences short enough for a
+    single-CTA filter."""
+    _case(ctx, 2, 80, seed=24, nhar=40, maxnhar=40, fs=16000.0, f0_lo=100, f0_hi=200, nch=3)
