@@ -82,6 +82,13 @@ static SynthPlanDev* get_plan(llsm_b200_ctx* ctx, const llsm_b200_conf* conf) {
   PlanKey k = make_key(conf);
   auto it = ctx->plans.find(k);
   if(it != ctx->plans.end()) return it->second.get();
+  // one plan per distinct (nfrm, configuration): a service that synthesises variable-length utterances would grow the
+  // cache without bound, so it is emptied (after the stream has drained: plans may be in use) when it reaches the cap
+  if(ctx->plans.size() >= 64) {
+    cudaStreamSynchronize(ctx->stream);
+    for(auto& kv : ctx->plans) kv.second->release();
+    ctx->plans.clear();
+  }
   std::unique_ptr<SynthPlanDev> p(new SynthPlanDev());
   if(p->build(conf->nfrm, conf->fs, conf->thop, conf->npsd, conf->nchannel, conf->chanfreq,
        ctx->stream) != 0) { p->release(); return nullptr; }

@@ -33,3 +33,26 @@ def test_optional_arrays_and_errors():
     bad = blob.copy(); bad[0] = 0
     with pytest.raises(L.LlsmB200Error):
         L.blob_to_frames(bad)                                  # wrong magic
+
+
+def test_hostile_headers_are_rejected():
+    """A blob may come from another process or a file: sizes that would wrap size_t, offsets outside the blob and
+    unaligned offsets must all be refused (none of them may yield views outside the buffer)."""
+    import libllsm2_b200 as L
+    fr, conf = S.synth_frames(2, 5, seed=53)
+    blob = L.frames_to_blob(conf, fr)
+    i32 = lambda b: b[:256].view(np.int32)
+    u64 = lambda b: b[88:88 + 96].view(np.uint64)              # offset[11], total (after the 68-byte conf, 8-aligned)
+    assert int(u64(blob.copy())[11]) == blob.size              # layout check: `total` sits where this test expects it
+    bad = blob.copy(); i32(bad)[4] = 0x7fffffff; i32(bad)[5] = 0x7fffffff       # nutt, nfrm: B * F * maxnhar * 4 wraps
+    with pytest.raises(L.LlsmB200Error):
+        L.blob_to_frames(bad)
+    bad = blob.copy(); u64(bad)[3] = np.uint64(2 ** 64 - 64)                     # offset + size wraps around
+    with pytest.raises(L.LlsmB200Error):
+        L.blob_to_frames(bad)
+    bad = blob.copy(); u64(bad)[3] = u64(bad)[3] + np.uint64(4)                  # unaligned offset
+    with pytest.raises(L.LlsmB200Error):
+        L.blob_to_frames(bad)
+    bad = blob.copy(); u64(bad)[3] = np.uint64(blob.size)                        # offset at the end: size does not fit
+    with pytest.raises(L.LlsmB200Error):
+        L.blob_to_frames(bad)
