@@ -413,32 +413,56 @@ __global__ void __launch_bounds__(HD_THREADS) harmonic_dft_kernel(HarmDftParams 
 #define HM_THREADS 128
 #define HM_QS 18                                      // uint4 row stride of a staged p-pair row (16 used): conflict-free LDS.128
 
+// A CTA owns P.seg_frames consecutive frames of one utterance (P.seg_frames == 1: one frame, samples read from global
+// memory); for longer segments thread 0 stages the waveform slice those frames touch with one bulk asynchronous copy
+// (cp.async.bulk, as envelope_seg_kernel does): neighbouring windows overlap by three quarters, and the frames' split /
+// pack passes then read shared memory instead of waiting on L2.
 __global__ void __launch_bounds__(HM_THREADS) harmonic_mma_kernel(HarmDftParams P) {
   LLSM_DYN_SMEM(smem);
   const int cap = P.mma_cap_half;
   const int prow = (((cap + 1 + 15) / 16) + 15) & ~15;  // staged p-rows (multiple of 16)
-  uint4* sB = (uint4*)smem;                           // [prow / 2][HM_QS]: {e_hi, e_lo, o_hi, o_lo} of rows (2 p2, 2 p2 + 1), column q
+  bulk_bar_t* bar = (bulk_bar_t*)smem;
+  uint4* sB = (uint4*)(smem + 16);                    // [prow / 2][HM_QS]: {e_hi, e_lo, o_hi, o_lo} of rows (2 p2, 2 p2 + 1), column q
   float2* sums = (float2*)(sB + (size_t)(prow / 2) * HM_QS);   // [maxnhar] DFT sums of the harmonics
+  float* slice = (float*)(sums + P.maxnhar);          // [P.seg_len] staged waveform (segments only)
 
-  const int i = blockIdx.x, b = blockIdx.y;
+  const int b = blockIdx.y, i_lo = blockIdx.x * P.seg_frames;
   const int nf = P.nfrm_utt ? P.nfrm_utt[b] : P.nfrm;
   const int tid = threadIdx.x;
+  if(i_lo >= nf) return;
+  const int i_hi = min(i_lo + P.seg_frames, nf);
+  const float* xg = P.sig + (size_t)b * P.xstride;
+  const bool staged = P.seg_frames > 1;
+  int lo = 0;
+  if(staged) {
+    int hi = P.center[i_hi - 1] + cap + 1;
+    lo = max(P.center[i_lo] - cap, 0) & ~3; hi = (min(hi, P.nx) + 3) & ~3;   // (rows are padded to a multiple of four samples)
+    const int len = min(max(hi - lo, 0), P.seg_len);
+    if(tid == 0) bulk_bar_init(bar);
+    __syncthreads();
+    if(tid == 0) {
+      bulk_expect(bar, (uint32_t)(len * 4));
+      if(len > 0) bulk_g2s(slice, xg + lo, (uint32_t)(len * 4), bar);
+    }
+    bulk_wait(bar, 0);
+  }
+  const float* x = staged ? slice - lo : xg;          // x[ix], ix = sample index in the utterance
+
+  for(int i = i_lo; i < i_hi; i ++) {
   const size_t fidx = (size_t)b * P.nfrm + i;
-  if(i >= nf) return;
   const float f0 = P.f0[fidx];
   if(! (f0 > 0)) {                                    // unvoiced: no harmonic model (layer0.c:106)
     if(tid == 0) P.nhar_out[fidx] = 0;
     for(int k = tid; k < P.maxnhar; k += HM_THREADS) { P.ampl[fidx * P.maxnhar + k] = 0; P.phse[fidx * P.maxnhar + k] = 0; }
-    return;
+    continue;
   }
   const int ws = ana_winsize(P.fs, f0, P.rel_winsize);
   const int nh = ana_nhar(P.fs, f0, P.maxnhar);
   const int half = ws >> 1;
   if(half > cap || half < 1) {                        // left to the general kernel (harmonic_dft_kernel in list mode)
     if(tid == 0) { const int at = atomicAdd(P.long_list, 1); P.long_list[1 + at] = (int)fidx; }
-    return;
+    continue;
   }
-  const float* x = P.sig + (size_t)b * P.xstride;
   const int center = P.center[i];
   // ---- Blackman window and its sum from the plan's table (w(half +- n) at wv[n])
   const float* wv = P.bwin + P.bw_off[half];
@@ -447,6 +471,7 @@ __global__ void __launch_bounds__(HM_THREADS) harmonic_mma_kernel(HarmDftParams 
   // ---- stage e | o (symmetric / antisymmetric halves of the windowed frame), split, as FP16 pairs over p
   const int npair = half + 1;
   const int np16 = (((npair + 15) / 16) + 15) & ~15;  // p-rows in use (multiple of 16, <= prow)
+  __syncthreads();                                    // the previous frame's operand and sums are no longer read
   for(int idx = tid; idx < (np16 / 2) * 16; idx += HM_THREADS) {
     const int p2 = idx >> 4, q = idx & 15;
     float e[2], o[2];
@@ -535,11 +560,12 @@ __global__ void __launch_bounds__(HM_THREADS) harmonic_mma_kernel(HarmDftParams 
   }
   for(int k = nh + tid; k < P.maxnhar; k += HM_THREADS) { P.ampl[fidx * P.maxnhar + k] = 0; P.phse[fidx * P.maxnhar + k] = 0; }
   if(tid == 0) P.nhar_out[fidx] = nh;
+  }
 }
 
-static inline size_t harm_mma_smem(int cap, int maxnhar) {
+static inline size_t harm_mma_smem(int cap, int maxnhar, int seg_len) {
   const int prow = (((cap + 1 + 15) / 16) + 15) & ~15;
-  return (size_t)(prow / 2) * HM_QS * 16 + (size_t)maxnhar * 8 + 16;
+  return 16 + (size_t)(prow / 2) * HM_QS * 16 + (size_t)maxnhar * 8 + (size_t)seg_len * 4 + 16;
 }
 
 static inline double mma_min_f0() {
@@ -565,6 +591,11 @@ static inline int ana_resident_ctas(int per_sm) {
 #endif
 }
 
+static inline int mma_seg_frames() {
+  static int v = -1;
+  if(v < 0) { const char* e = getenv("LLSM_MMA_SEG"); v = e ? atoi(e) : 8; if(v < 1) v = 1; }
+  return v;
+}
 static inline int env_seg_frames() {
   static int v = -1;
   if(v < 0) { const char* e = getenv("LLSM_ENV_SEG"); v = e ? atoi(e) : 16; if(v < 1) v = 1; }
@@ -929,14 +960,20 @@ static inline int launch_harmonic_dft(const HarmDftParams& Pin, int nutt, cudaSt
     if(cap > P.max_half) cap = P.max_half;
     if(cap > P.bw_cap) cap = P.bw_cap;
     P.mma_cap_half = cap;
-    size_t smem = harm_mma_smem(cap, P.maxnhar);
+    // segments of frames with the waveform slice staged by bulk copy when the rows are 16-byte aligned
+    P.seg_frames = 1; P.seg_len = 0;
+    if(mma_seg_frames() > 1 && (P.xstride & 3) == 0 && ((uintptr_t)P.sig & 15) == 0 && P.hop_max > 0) {
+      P.seg_frames = mma_seg_frames();
+      P.seg_len = ((P.seg_frames - 1) * P.hop_max + 2 * cap + 1 + 8 + 3) & ~3;
+    }
+    size_t smem = harm_mma_smem(cap, P.maxnhar, P.seg_len);
     size_t smem_d = harm_dft_smem(P.max_half, 1);
     if(smem <= 200 * 1024 && smem_d <= 200 * 1024) {
       if(dev_memset(long_list, 0, 4, st) != 0) return -1;
 #ifndef LLSM_EMU
       cudaFuncSetAttribute(harmonic_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 #endif
-      LLSM_LAUNCH(harmonic_mma_kernel, dim3(P.nfrm, nutt), dim3(HM_THREADS), smem, st, P);
+      LLSM_LAUNCH(harmonic_mma_kernel, dim3((P.nfrm + P.seg_frames - 1) / P.seg_frames, nutt), dim3(HM_THREADS), smem, st, P);
       auto kfn = harmonic_dft_kernel<HD_THREADS>;
 #ifndef LLSM_EMU
       cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d);
