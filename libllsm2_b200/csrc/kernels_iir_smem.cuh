@@ -14,6 +14,9 @@
 //     the CTAs of a cluster from their totals read through distributed shared memory (one cluster barrier per pass,
 //     totals double-buffered), spread to a chunk by the binary decomposition of its index.
 //   * true pass: the recurrence in place, in double, rounded to float where the streaming kernel rounds.
+// (Tried and dropped: accumulating the next pass's chunk end states inside the true pass, whose samples it is producing
+//  -- one loop less per pass, but 3.29 ms against 2.80 ms at C2: the extra FMAs and the conversion back to double sit in
+//  the recurrence's issue stream, and the FP64 / conversion pipes, not the latency, are what the kernel runs into.)
 // The g++ -DLLSM_EMU build (tests/emu) compiles the CS = 1 instance only (no clusters on the CPU emulation).
 #pragma once
 #include "kernels_iir.cuh"
