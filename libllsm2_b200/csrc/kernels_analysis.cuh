@@ -152,7 +152,6 @@ struct HarmDftParams {
   int max_half;             // capacity of the staged half-frame (pairs)
   float* edc; float thop;   // optional: short-time mean of every signal, [B][nfrm][nsig]
   int hop_max;              // largest distance between consecutive frame centres (staged kernels)
-  int only_above_half;      // > 0: the direct kernel only serves frames whose half window exceeds this
   int mma_cap_half;         // capacity (half window) of the tensor-core kernel's staging
   // window table (AnaPlan::bwin): w(h +- n) at bwin[bw_off[h] + n], sums bw_sum[h], for half windows h <= bw_cap
   const float* bwin; const int* bw_off; const float* bw_sum; int bw_cap;
@@ -253,7 +252,6 @@ __device__ __forceinline__ void harmonic_dft_frame(const HarmDftParams& P, const
     if(live && gt == 0) P.nhar_out[fidx] = -1;
     return;
   }
-  if(P.only_above_half > 0 && half <= P.only_above_half) return;   // served by harmonic_mma_kernel
 
   // ---- Blackman window once per CTA. ws is even, so the periodic window is symmetric about m = half:
   //   w(half +- n) = 0.42 + 0.5 cos(2 pi n / ws) + 0.08 cos(4 pi n / ws).

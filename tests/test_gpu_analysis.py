@@ -170,3 +170,9 @@ def test_analysis_16k_block_fft_path(ctx):
     """16 kHz: transform sizes 512 / 512, served by the block-FFT noise-spectra kernel; sequences short enough for a
     single-CTA filter."""
     _case(ctx, 2, 80, seed=24, nhar=40, maxnhar=40, fs=16000.0, f0_lo=100, f0_hi=200, nch=3)
+
+
+def test_analysis_bench_length_cluster_of_two(ctx):
+    """400 frames (2 s, BASELINE configs[1]'s utterance length): 88 200 samples per sub-band sequence = a cluster of two
+    CTAs in the shared-memory filter, the configuration bench.py times."""
+    _case(ctx, 1, 400, seed=25, nhar=128, maxnhar=128)
