@@ -308,13 +308,13 @@ struct ExcParams {
   unsigned chan_mask;       // bit c set when channel c exists (fmin < fs / 2)
   float hop;                // thop * fs (float product), spacing of env_off
   int samp_lo, samp_hi;     // only samples [lo, hi) are needed (frame-range sharding); hi <= 0 means all
+  int tile_nq;              // tiles of EXC_THREADS samples per CTA (set by the launcher)
   float* y_exc;             // [B][stride]
 };
 
 #define EXC_THREADS 256                 // (512 measured slower: 3.68 ms vs 2.68 ms at C2)
-#define EXC_SPT 1                       // output samples per thread (2 measured slower: 4.9 ms vs 3.1 ms at C2)
-#define EXC_TILE (EXC_THREADS * EXC_SPT)
-#define EXC_FCHUNK 8
+#define EXC_FCHUNK 16                   // frame slots staged at a time
+#define EXC_NQ_MAX 8                    // a CTA owns up to EXC_NQ_MAX tiles of EXC_THREADS consecutive samples
 
 // stretch_stationary_noise (dsputils.c:363-383) as a closed-form index map: output position p reads
 // template index `base`, cross-faded with template index `ii` (>= 0) at the 128-sample seams.
@@ -351,13 +351,20 @@ __device__ __forceinline__ float stretched_value(const float* __restrict__ x, St
   return base;
 }
 
+// A CTA owns P.tile_nq consecutive tiles of EXC_THREADS samples (a thread: one sample of each tile, one after the other --
+// the two-samples-at-once variant ran out of registers: 4.9 ms against 3.1 ms). The parameters of every frame that reaches
+// the CTA's samples are staged ONCE for all tiles: with one 256-sample tile per CTA (the first version) the staging -- a
+// dependent chain of global reads and a sincosf per envelope harmonic, then a block barrier -- was repeated for every 1.2
+// frames of output and its stalls (barrier 2.6, long scoreboard 2.6 per issued instruction, profiles/r2t) were the kernel.
 template <int MAXCH>
 __global__ void __launch_bounds__(EXC_THREADS) noise_excitation_kernel(ExcParams P) {
   LLSM_DYN_SMEM(smem);
   const int b = blockIdx.y;
-  const int p0 = blockIdx.x * EXC_TILE;
-  if(P.samp_hi > 0 && (p0 + EXC_TILE <= P.samp_lo || p0 >= P.samp_hi)) {   // CTA outside the shard (uniform)
-    for(int q = 0; q < EXC_SPT; q ++) {
+  const int nq_all = P.tile_nq > 0 ? P.tile_nq : 1;
+  const int span = nq_all * EXC_THREADS;
+  const int p0 = blockIdx.x * span;
+  if(P.samp_hi > 0 && (p0 + span <= P.samp_lo || p0 >= P.samp_hi)) {   // CTA outside the shard (uniform)
+    for(int q = 0; q < nq_all; q ++) {
       const int p = p0 + q * EXC_THREADS + (int)threadIdx.x;
       if(p < P.nsamp) P.y_exc[(size_t)blockIdx.y * P.stride + p] = 0.f;
     }
@@ -372,14 +379,13 @@ __global__ void __launch_bounds__(EXC_THREADS) noise_excitation_kernel(ExcParams
   float* fr = (float*)smem;                        // [EXC_FCHUNK][fstride]
   const size_t row = (size_t)b * P.nfrm;
 
-  // frames that can reach [p0, p0 + EXC_TILE): env_off + n_env + 1 > p0 and env_off - 1 <= pend, with
+  // frames that can reach [p0, p0 + span): env_off + n_env + 1 > p0 and env_off - 1 <= pend, with
   // env_off[i] = round((i - 1) * hop): bounds from the hop arithmetic (one frame of slack), then made exact
-  // with a couple of table reads (every extra frame costs a test per output sample). One thread does the
-  // search for the CTA.
+  // with a couple of table reads. One thread does the search for the CTA.
   int* srange = (int*)(fr + EXC_FCHUNK * fstride);
+  const float inv_hop = 1.0f / P.hop;
   if(threadIdx.x == 0) {
-    const int pend = p0 + EXC_TILE - 1;
-    const float inv_hop = 1.0f / P.hop;
+    const int pend = p0 + span - 1;
     int a = (int)floorf((float)(p0 - P.n_env - 1) * inv_hop);
     int bb = (int)floorf((float)(pend + 1) * inv_hop) + 3;
     if(a < 0) a = 0;
@@ -391,18 +397,11 @@ __global__ void __launch_bounds__(EXC_THREADS) noise_excitation_kernel(ExcParams
   }
   __syncthreads();
   const int ia = srange[0], ib = srange[1];
-
-  float env[EXC_SPT][MAXCH];
-#pragma unroll
-  for(int q = 0; q < EXC_SPT; q ++)
-#pragma unroll
-    for(int c = 0; c < MAXCH; c ++) env[q][c] = 0.f;
   const int half = P.n_env / 2;
+  const bool single = ib - ia <= EXC_FCHUNK;       // every frame of the CTA fits the staging slots (the launcher sees to it)
 
-  for(int i0 = ia; i0 < ib; i0 += EXC_FCHUNK) {
-    const int nfc = min(EXC_FCHUNK, ib - i0);
-    __syncthreads();
-    // ---- stage frame parameters (slot e -> frame e / 64, field e % 64 when a frame fits 64 fields: no divisions)
+  // ---- stage the parameters of frames [i0, i0 + nfc) (slot e -> frame e / 64, field e % 64 when a frame fits 64 fields)
+  auto stage = [&](int i0, int nfc) {
     const bool pow2 = fstride <= 64;
     for(int e = threadIdx.x; e < nfc * (pow2 ? 64 : fstride); e += blockDim.x) {
       int fi, q;
@@ -436,78 +435,104 @@ __global__ void __launch_bounds__(EXC_THREADS) noise_excitation_kernel(ExcParams
       }
       fr[fi * fstride + q] = v;
     }
-    __syncthreads();
+  };
+  // ---- envelope contributions of the staged frames [i0, i0 + nfc) to sample p (frames ascend in position)
+  auto accumulate = [&](int p, int i0, int nfc, float (&env)[MAXCH]) {
+    int fi0 = (int)floorf((float)(p - P.n_env - 2) * inv_hop) - i0;   // a frame before the first that can reach p
+    if(fi0 < 0) fi0 = 0;
+    for(int fi = fi0; fi < nfc; fi ++) {
+      const float* F = fr + fi * fstride;
+      const float f0n = F[0], r = F[1];
+      const int off = __float_as_int(F[2]);
+      if(off - 1 > p) break;                                 // this frame and every later one start beyond p
+      const unsigned rel = (unsigned)(p - off + 1);
+      if(rel > (unsigned)(P.n_env + 1)) continue;            // frame cannot reach this sample
+      const int contig = __float_as_int(F[3]);
+      for(int dj = contig ? 0 : -1; dj <= (contig ? 0 : 1); dj ++) {
+        int j = p - off + dj;
+        if(j < 0 || j >= P.n_env) continue;
+        if(! contig) {
+          float tpos = __fadd_rn(r, (float)j);               // (i - 1) * thop * fs + j in float
+          int idx = (int)roundf(tpos);                       // layer0.c:307
+          if(idx != p) continue;
+        }
+        const float wj = P.win_env[j];
+        float2 z = unit_phasor_small(f0n * (float)(j - half));   // at most ~one turn across the window
+        float2 w = make_float2(1.f, 0.f);
+        float hs[MAXCH];
 #pragma unroll
-    for(int q = 0; q < EXC_SPT; q ++) {
-    const int p = p0 + q * EXC_THREADS + (int)threadIdx.x;
-    if(p < P.nsamp && p < ny_b) {
-      for(int fi = 0; fi < nfc; fi ++) {
-        const float* F = fr + fi * fstride;
-        const float f0n = F[0], r = F[1];
-        const int off = __float_as_int(F[2]);
-        const unsigned rel = (unsigned)(p - off + 1);
-        if(rel > (unsigned)(P.n_env + 1)) continue;            // frame cannot reach this sample
-        const int contig = __float_as_int(F[3]);
-        for(int dj = contig ? 0 : -1; dj <= (contig ? 0 : 1); dj ++) {
-          int j = p - off + dj;
-          if(j < 0 || j >= P.n_env) continue;
-          if(! contig) {
-            float tpos = __fadd_rn(r, (float)j);               // (i - 1) * thop * fs + j in float
-            int idx = (int)roundf(tpos);                       // layer0.c:307
-            if(idx != p) continue;
-          }
-          const float wj = P.win_env[j];
-          float2 z = unit_phasor_small(f0n * (float)(j - half));   // at most ~one turn across the window
-          float2 w = make_float2(1.f, 0.f);
-          float hs[MAXCH];
-#pragma unroll
-          for(int c = 0; c < MAXCH; c ++) hs[c] = 0.f;
-          for(int k = 0; k < mne; k ++) {
-            w = cmul(w, z);
-#pragma unroll
-            for(int c = 0; c < MAXCH; c ++) if(c < nch) {
-              const float2 ab = ((const float2*)(F + 4 + c * (2 + 2 * mne) + 2))[k];
-              hs[c] = fmaf(ab.x, w.x, fmaf(-ab.y, w.y, hs[c]));
-            }
-          }
+        for(int c = 0; c < MAXCH; c ++) hs[c] = 0.f;
+        for(int k = 0; k < mne; k ++) {
+          w = cmul(w, z);
 #pragma unroll
           for(int c = 0; c < MAXCH; c ++) if(c < nch) {
-            float v = hs[c] + F[4 + c * (2 + 2 * mne)];
-            if(! (v > 1e-8f)) v = 1e-8f;                     // layer0.c:304
-            env[q][c] += v * wj;                             // layer0.c:306,309
+            const float2 ab = ((const float2*)(F + 4 + c * (2 + 2 * mne) + 2))[k];
+            hs[c] = fmaf(ab.x, w.x, fmaf(-ab.y, w.y, hs[c]));
           }
+        }
+#pragma unroll
+        for(int c = 0; c < MAXCH; c ++) if(c < nch) {
+          float v = hs[c] + F[4 + c * (2 + 2 * mne)];
+          if(! (v > 1e-8f)) v = 1e-8f;                       // layer0.c:304
+          env[c] += v * wj;                                  // layer0.c:306,309
         }
       }
     }
-    }
-  }
+  };
 
+  if(single) { stage(ia, ib - ia); __syncthreads(); }
+#pragma unroll 1
+  for(int q = 0; q < nq_all; q ++) {
+    const int p = p0 + q * EXC_THREADS + (int)threadIdx.x;
+    float env[MAXCH];
 #pragma unroll
-  for(int q = 0; q < EXC_SPT; q ++) {
-  const int p = p0 + q * EXC_THREADS + (int)threadIdx.x;
-  if(p < P.nsamp) {
-    float y = 0.f;
-    if(p < ny_b) {
-      const StretchIdx si = stretch_index(P.ntemplate, ny_b, p);
-#pragma unroll
-      for(int c = 0; c < MAXCH; c ++) if(c < nch && ((P.chan_mask >> c) & 1u)) {
-        const float* tp = P.colored + ((size_t)b * nch + c) * P.tstride;
-        float x = stretched_value(tp, si);
-        x = x * sqrtf(env[q][c]);                            // layer0.c:548
-        y += x;                                              // layer0.c:549
+    for(int c = 0; c < MAXCH; c ++) env[c] = 0.f;
+    const bool livep = p < P.nsamp && p < ny_b;
+    if(single) {
+      if(livep) accumulate(p, ia, ib - ia, env);
+    } else {
+      for(int i0 = ia; i0 < ib; i0 += EXC_FCHUNK) {           // (more frames than slots: tiny hops)
+        const int nfc = min(EXC_FCHUNK, ib - i0);
+        __syncthreads();
+        stage(i0, nfc);
+        __syncthreads();
+        if(livep) accumulate(p, i0, nfc, env);
       }
     }
-    P.y_exc[(size_t)b * P.stride + p] = y;
+    if(p < P.nsamp) {
+      float y = 0.f;
+      if(p < ny_b) {
+        const StretchIdx si = stretch_index(P.ntemplate, ny_b, p);
+#pragma unroll
+        for(int c = 0; c < MAXCH; c ++) if(c < nch && ((P.chan_mask >> c) & 1u)) {
+          const float* tp = P.colored + ((size_t)b * nch + c) * P.tstride;
+          float x = stretched_value(tp, si);
+          x = x * sqrtf(env[c]);                             // layer0.c:548
+          y += x;                                            // layer0.c:549
+        }
+      }
+      P.y_exc[(size_t)b * P.stride + p] = y;
+    }
   }
-  }
+}
+
+static inline int exc_tile_nq() {
+  static int v = -1;
+  if(v < 0) { const char* e = getenv("LLSM_EXC_NQ"); v = e ? atoi(e) : EXC_NQ_MAX; if(v < 1) v = 1; if(v > EXC_NQ_MAX) v = EXC_NQ_MAX; }
+  return v;
 }
 
 static inline size_t exc_smem_bytes(int nchannel, int maxnhar_e) {
   return (size_t)EXC_FCHUNK * (4 + nchannel * (2 + 2 * maxnhar_e)) * 4 + 32;
 }
 
-static inline int launch_noise_excitation(const ExcParams& P, int nutt, cudaStream_t st) {
-  dim3 grid((P.nsamp + EXC_TILE - 1) / EXC_TILE, nutt), block(EXC_THREADS);
+static inline int launch_noise_excitation(const ExcParams& Pin, int nutt, cudaStream_t st) {
+  ExcParams P = Pin;
+  // tiles per CTA: as many as keep the frames reaching a CTA's samples within the staging slots
+  int nq = exc_tile_nq();
+  while(nq > 1 && (float)(nq * EXC_THREADS + P.n_env) / P.hop + 3.0f > (float)EXC_FCHUNK) nq --;
+  P.tile_nq = nq;
+  dim3 grid((P.nsamp + nq * EXC_THREADS - 1) / (nq * EXC_THREADS), nutt), block(EXC_THREADS);
   size_t smem = exc_smem_bytes(P.nchannel, P.maxnhar_e);
   if(smem > 200 * 1024) return -1;
 #ifndef LLSM_EMU
