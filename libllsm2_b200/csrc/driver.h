@@ -108,6 +108,13 @@ struct SynthPlanDev {
   void release() { for(void* p : owned) dev_free(p); owned.clear(); }
 };
 
+// output samples a noise-shaper CTA owns (its eight warps take 16 frames a round: the default keeps the frames that touch
+// a segment within a whole number of rounds at a 5 ms hop)
+static inline int shape_seg() {
+  static int v = -1;
+  if(v < 0) { const char* e = getenv("LLSM_SHAPE_SEG"); v = e ? atoi(e) : 6016; if(v < 1024) v = 1024; if(v > 16384) v = 16384; }
+  return v;
+}
 static inline int iir_variant() {
   static int v = -1;
   if(v < 0) { const char* e = getenv("LLSM_IIR_VARIANT"); v = e ? atoi(e) : 1; }
@@ -254,7 +261,7 @@ static inline int run_noise_part(const SynthPlanDev& pd, SynthScratch& sc, const
   S.y_exc = sc.y_exc.as<float>(); S.stride_exc = out.stride;
   S.y_sin = out.y_sin; S.y_noise = out.y_noise; S.y = out.y;
   S.ny = h.ny; S.nsamp = out.stride; S.stride = out.stride;
-  S.seg = 8192; S.frame_lo = frame_lo; S.frame_hi = frame_hi;
+  S.seg = shape_seg(); S.frame_lo = frame_lo; S.frame_hi = frame_hi;
   if(h.nfft_ns > 8192) return LLSM_B200_ERANGE;
   if(launch_noise_shape(S, B, st) != 0) return LLSM_B200_ERANGE;
   if(lc) lc->n += 1;
