@@ -208,6 +208,7 @@ static inline int run_harmonic_pass(const SynthPlanDev& sp, AnaPlanDev& ap, AnaS
     H.f0 = f0; H.center = sp.hm_base; H.nfft_utt = sc.nfft_utt.as<int>(); H.fs = conf.fs;
     H.rel_winsize = opt.rel_winsize; H.std_norm = ap.h.std_norm_blackman; H.maxnhar = maxnhar;
     H.nhar_out = nhar_o; H.ampl = ampl_o; H.phse = phse_o; H.tw = ap.tw_pp; H.ntw = 8192; H.max_nfft = 8192;
+    H.bwin = ap.bwin; H.bw_off = ap.bw_off; H.bw_cap = ap.h.bw_cap;
     size_t smem = (size_t)H.max_nfft * 16 + 16;
 #ifndef LLSM_EMU
     cudaFuncSetAttribute(harmonic_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -1664,6 +1664,7 @@ struct HarmPpParams {
   int maxnhar;
   int* nhar_out; float* ampl; float* phse;
   const float2* tw; int ntw; int max_nfft;
+  const float* bwin; const int* bw_off; int bw_cap;   // window table (AnaPlan::bwin), optional
 };
 
 #define HP_THREADS 256
@@ -1694,13 +1695,19 @@ __global__ void __launch_bounds__(HP_THREADS) harmonic_pp_kernel(HarmPpParams P)
   // zero-phase Blackman frame (window centre at buffer index 0)
   for(int k = tid; k < nfft; k += nth) bufa[k] = make_float2(0.f, 0.f);
   __syncthreads();
+  const int hw = ws >> 1;
+  const float* wtab = (P.bwin != nullptr && hw >= 1 && hw <= P.bw_cap) ? P.bwin + P.bw_off[hw] : nullptr;   // w(hw +- n) at [n]
   for(int j = tid; j < ws; j += nth) {
     int idx = center + j - ws / 2;
     float v = 0.f;
     if(idx >= 0 && idx < P.nx) {
-      double s1, c1, s2, c2;
-      sincospi(2.0 * (double)j / (double)ws, &s1, &c1); sincospi(4.0 * (double)j / (double)ws, &s2, &c2);
-      float w = (float)(0.42 - 0.5 * c1 + 0.08 * c2);
+      float w;
+      if(wtab) w = wtab[j >= hw ? j - hw : hw - j];
+      else {
+        double s1, c1, s2, c2;
+        sincospi(2.0 * (double)j / (double)ws, &s1, &c1); sincospi(4.0 * (double)j / (double)ws, &s2, &c2);
+        w = (float)(0.42 - 0.5 * c1 + 0.08 * c2);
+      }
       v = x[idx] * w;
     }
     int k = ((j - ws / 2) % nfft + nfft) % nfft;      // ws <= nfft here: no aliasing, plain placement
@@ -1711,7 +1718,16 @@ __global__ void __launch_bounds__(HP_THREADS) harmonic_pp_kernel(HarmPpParams P)
   float2* Y = (X == bufa) ? bufb : bufa;
   // log magnitude (x: log(|X| normaliser + 1e-8)) and phase (y) per bin
   float normalizer = 1024.0f / P.std_norm; normalizer = normalizer / (float)ws;
-  for(int k = tid; k <= nfft / 2; k += nth) {
+  // only the bins the peak picker can read: up to the upper search bound of the last harmonic, plus the parabola's and
+  // the phase interpolation's neighbours (the envelope pass asks for 5 harmonics: 1 / 8 of the spectrum)
+  int kneed = nfft / 2;
+  {
+    float up_f = __fmul_rn(f0, (float)nh + 0.3f); up_f = up_f / P.fs; up_f = __fmul_rn(up_f, (float)nfft);
+    const int u = (int)round((double)up_f) + 3;
+    if(u < kneed) kneed = u;
+    if(kneed < 3) kneed = 3;
+  }
+  for(int k = tid; k <= kneed; k += nth) {
     float2 v = X[k];
     float mag = (float)sqrt((double)v.x * v.x + (double)v.y * v.y) * normalizer;
     Y[k] = make_float2((float)log((double)mag + 1e-8), (float)atan2((double)v.y, (double)v.x));
