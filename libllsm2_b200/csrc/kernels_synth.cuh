@@ -313,8 +313,8 @@ struct ExcParams {
 };
 
 #define EXC_THREADS 256                 // (512 measured slower: 3.68 ms vs 2.68 ms at C2)
-#define EXC_FCHUNK 16                   // frame slots staged at a time
-#define EXC_NQ_MAX 8                    // a CTA owns up to EXC_NQ_MAX tiles of EXC_THREADS consecutive samples
+#define EXC_FCHUNK 32                   // frame slots staged at a time
+#define EXC_NQ_MAX 16                   // a CTA owns up to EXC_NQ_MAX tiles of EXC_THREADS consecutive samples
 
 // stretch_stationary_noise (dsputils.c:363-383) as a closed-form index map: output position p reads
 // template index `base`, cross-faded with template index `ii` (>= 0) at the 128-sample seams.
