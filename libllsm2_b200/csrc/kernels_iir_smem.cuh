@@ -186,14 +186,17 @@ __global__ void __launch_bounds__(IIS_NT, 2) iir_smem_kernel(IirSmemParams Q) {
         z0 += c0; z1 += c1; z2 += c2; z3 += c3;
       }
       // ---- C: true pass, in place
+      // (samples behind the end of the sequence stay zero: a pass must not see the previous pass ring on into the padding
+      //  -- filtfilt filters exactly n samples each way)
       const bool last = P.square && st == nst - 1 && dir == 1;
+      const int kend = mine - tid * L;                        // chunk positions k >= kend lie behind the end
       double yn;
 #pragma unroll 4
       for(int e = 0; e < L; e ++) {
         const int k = dir == 0 ? e : L - 1 - e;
         iir_step(cf, (double)mych[k], z0, z1, z2, z3, yn);
         const float yf = (float)yn;
-        mych[k] = last ? yf * yf : yf;
+        mych[k] = k < kend ? (last ? yf * yf : yf) : 0.f;
       }
       __syncthreads();                                       // (fs is rewritten by the next pass)
     }

@@ -242,3 +242,33 @@ extern "C" int emu_halo_add(int nutt, int ny, int stride, int halo, int rank, in
   run_halo_add(P, spos[rank + 1] - spos[rank], nullptr);
   return 0;
 }
+
+// Zero-phase sub-band filter, two implementations side by side (test_emu_iir.py): the streaming kernel
+// (kernels_iir.cuh) and the shared-memory resident one (kernels_iir_smem.cuh, single-CTA instance) on the same input.
+// src: [nutt][sstride] (one row per utterance, read by every channel's first section), y_*: [nutt * nch][ystride].
+extern "C" int emu_iir_both(int nutt, int nch, int n, float fs, const float* chanfreq, const float* src, int sstride,
+  int square, float* y_stream, float* y_smem, int ystride) {
+  AnaPlan h;
+  build_ana_plan(h, fs, 0.005f, 64, nch, chanfreq);
+  const int L = ((n + IIR_NT - 1) / IIR_NT + IIR_T - 1) & ~(IIR_T - 1);
+  std::vector<double> coef((size_t)LLSM_B200_MAXCHANNEL * 2 * 9, 0.0), mpow((size_t)LLSM_B200_MAXCHANNEL * 2 * IIR_NLOG * 16, 0.0);
+  int cs = 0, Ls = 0;
+  iir_smem_geometry(n, cs, Ls);
+  if(cs != 1) return -2;
+  std::vector<double> coef2(9), mpow9((size_t)LLSM_B200_MAXCHANNEL * 2 * IIS_NLOG * 16, 0.0), wts((size_t)LLSM_B200_MAXCHANNEL * 2 * Ls * 4, 0.0);
+  for(int c = 0; c < nch; c ++)
+    for(int s2 = 0; s2 < h.chan[c].nstage; s2 ++) {
+      build_iir_section(h.chan[c].b[s2], h.chan[c].a[s2], L, IIR_NLOG, &coef[((size_t)c * 2 + s2) * 9], &mpow[((size_t)c * 2 + s2) * IIR_NLOG * 16]);
+      build_iir_smem_section(h.chan[c].b[s2], h.chan[c].a[s2], Ls, coef2.data(), &mpow9[((size_t)c * 2 + s2) * IIS_NLOG * 16],
+        &wts[((size_t)c * 2 + s2) * Ls * 4]);
+    }
+  IirParams I; memset(&I, 0, sizeof(I));
+  I.nchannel = nch; I.n = n; I.L = L; I.ystride = ystride; I.vec_ok = (ystride & 3) == 0;
+  I.src_a = src; I.sa_stride = sstride; I.src_per_utt = 1; I.coef = coef.data(); I.mpow = mpow.data();
+  for(int c = 0; c < nch; c ++) I.nstage[c] = h.chan[c].nstage;
+  I.square = square;
+  I.y = y_stream;
+  LLSM_LAUNCH(iir_filtfilt_kernel, dim3(nutt * nch), dim3(IIR_NT), 0, nullptr, I);
+  IirSmemParams Q; Q.base = I; Q.base.y = y_smem; Q.mpow = mpow9.data(); Q.wts = wts.data(); Q.L = Ls;
+  return launch_iir_smem(Q, nutt * nch, cs, nullptr);
+}
