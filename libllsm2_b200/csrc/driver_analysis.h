@@ -209,11 +209,20 @@ static inline int run_harmonic_pass(const SynthPlanDev& sp, AnaPlanDev& ap, AnaS
     H.rel_winsize = opt.rel_winsize; H.std_norm = ap.h.std_norm_blackman; H.maxnhar = maxnhar;
     H.nhar_out = nhar_o; H.ampl = ampl_o; H.phse = phse_o; H.tw = ap.tw_pp; H.ntw = 8192; H.max_nfft = 8192;
     H.bwin = ap.bwin; H.bw_off = ap.bw_off; H.bw_cap = ap.h.bw_cap;
-    size_t smem = (size_t)H.max_nfft * 16 + 16;
+    // The transform size is per utterance (device data); the shared-memory footprint decides how many CTAs share an SM
+    // (8192 points: one, 2048: seven). One launch per size tier, each serving the utterances of its tier (the others'
+    // CTAs leave at once), instead of one launch sized for the largest transform.
+    int lo = 0;
+    for(int tier = 2048; tier <= 8192; tier <<= 1) {
+      H.min_nfft = lo; H.max_nfft = tier;
+      size_t smem = (size_t)tier * 16 + 16;
 #ifndef LLSM_EMU
-    cudaFuncSetAttribute(harmonic_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(harmonic_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 #endif
-    LLSM_LAUNCH(harmonic_pp_kernel, dim3(F, B * nsig), dim3(HP_THREADS), smem, st, H);
+      LLSM_LAUNCH(harmonic_pp_kernel, dim3(F, B * nsig), dim3(HP_THREADS), smem, st, H);
+      if(lc && tier > 2048) lc->n ++;
+      lo = tier;
+    }
   }
   if(lc) lc->n ++;
   return 0;

@@ -1663,6 +1663,7 @@ struct HarmPpParams {
   int maxnhar;
   int* nhar_out; float* ampl; float* phse;
   const float2* tw; int ntw; int max_nfft;
+  int min_nfft;                                       // this launch serves utterances with min_nfft < nfft <= max_nfft
   const float* bwin; const int* bw_off; int bw_cap;   // window table (AnaPlan::bwin), optional
 };
 
@@ -1685,7 +1686,8 @@ __global__ void __launch_bounds__(HP_THREADS) harmonic_pp_kernel(HarmPpParams P)
     return;
   }
   const int nfft = P.nfft_utt[b];
-  if(nfft > P.max_nfft) { if(tid == 0) P.nhar_out[fidx] = -1; return; }
+  if(nfft <= P.min_nfft) return;                      // served by the launch of a smaller tier
+  if(nfft > P.max_nfft) { if(tid == 0 && P.max_nfft >= 8192) P.nhar_out[fidx] = -1; return; }
   int lg = 0; while((1 << lg) < nfft) lg ++;
   const int ws = ana_winsize(P.fs, f0, P.rel_winsize);
   const int nh = ana_nhar(P.fs, f0, P.maxnhar);
