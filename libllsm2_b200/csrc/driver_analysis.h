@@ -24,23 +24,12 @@ struct AnaPlan {
   // taps. Offsets are multiples of four floats so that a window is a 16-byte aligned bulk-copy source.
   int bw_cap = 0;
   std::vector<float> bwin, bw_sum; std::vector<int> bw_off;
-  // Hann windows of the noise-spectra kernel (layer0.c:331-333: hanning(ws), ws = (int)(fs / f0 * 3)) for every length
-  // ws = 1 .. hn_cap (the kernel's 2048-point buffer; longer windows are time-aliased and evaluated per tap):
-  // hann[hn_off[ws] + j] = (FP_TYPE)(0.5 - 0.5 cos(2 pi j / ws)), j = 0 .. ws / 2; w[j] = w[ws - j] for the other half.
-  // The values are the oracle's (double expression, one float rounding). 4.2 MB, L2-resident.
-  int hn_cap = 0;
-  std::vector<float> hann; std::vector<int> hn_off;
 };
 
 static inline int fpad_host(int j) { return j + (j >> 4); }
 static inline int noise_spec_variant() {
   static int v = -1;
   if(v < 0) { const char* e = getenv("LLSM_NS_VARIANT"); v = e ? atoi(e) : 1; }
-  return v;
-}
-static inline int noise_hann_table() {
-  static int v = -1;
-  if(v < 0) { const char* e = getenv("LLSM_NS_HANN_TABLE"); v = e ? atoi(e) : 1; }
   return v;
 }
 static inline int ilog2_ceil(int n) { int l = 0; while((1 << l) < n) l ++; return l; }
@@ -98,18 +87,6 @@ static inline void build_ana_plan(AnaPlan& p, float fs, float thop, int npsd, in
       p.bw_sum[hh] = (float)acc;
     }
   }
-  // Hann table of the noise spectra
-  p.hn_cap = 2048;
-  p.hn_off.assign(p.hn_cap + 1, 0);
-  {
-    size_t total = 0;
-    for(int ws = 1; ws <= p.hn_cap; ws ++) { p.hn_off[ws] = (int)total; total += (size_t)(ws / 2 + 1); }
-    p.hann.assign(total + 4, 0.f);
-    for(int ws = 1; ws <= p.hn_cap; ws ++) {
-      float* w = &p.hann[p.hn_off[ws]];
-      for(int j = 0; j <= ws / 2; j ++) w[j] = (float)(0.5 - 0.5 * cos(2.0 * M_PI * j / ws));
-    }
-  }
   // channel filters (layer0.c:434-440)
   p.use_x_mask = 0;
   for(int c = 0; c < LLSM_B200_MAXCHANNEL; c ++) p.chan[c].nstage = 0;
@@ -125,7 +102,6 @@ struct AnaPlanDev {
   AnaPlan h;
   float *win_psd = nullptr, *ip_r = nullptr; int* ip_k = nullptr;
   float *bwin = nullptr, *bw_sum = nullptr; int* bw_off = nullptr;
-  float* hann = nullptr; int* hn_off = nullptr;
   float2 *tw_s = nullptr, *tw_p = nullptr, *tw_pp = nullptr;   // tw_pp: 8192-point table for HMPP
   // chunk-parallel IIR tables of the sub-band filters, valid for sequences of iir_nx samples
   DevBuf iir_coef, iir_mpow; int iir_nx = -1, iir_L = 0; int nchannel = 0;
@@ -149,7 +125,6 @@ struct AnaPlanDev {
     int rc = 0;
     rc |= up(&win_psd, h.win_psd, st); rc |= up(&ip_k, h.ip_k, st); rc |= up(&ip_r, h.ip_r, st);
     rc |= up(&bwin, h.bwin, st); rc |= up(&bw_sum, h.bw_sum, st); rc |= up(&bw_off, h.bw_off, st);
-    rc |= up(&hann, h.hann, st); rc |= up(&hn_off, h.hn_off, st);
     float* a = nullptr; rc |= up(&a, tws, st); tw_s = (float2*)a;
     float* b = nullptr; rc |= up(&b, twp, st); tw_p = (float2*)b;
     std::vector<float> twpp; build_twiddle(twpp, 8192);
@@ -336,7 +311,6 @@ static inline int run_analyze_l0(const SynthPlanDev& sp, AnaPlanDev& ap, AnaScra
     N.nfft_s = h.nfft_s; N.lg_nfft_s = h.lg_nfft_s;
     N.win_psd = ap.win_psd; N.win_power = h.win_power; N.std_norm = h.std_norm;
     N.tw_s = ap.tw_s; N.tw_p = ap.tw_p;
-    if(noise_hann_table()) { N.hann = ap.hann; N.hn_off = ap.hn_off; N.hn_cap = ap.h.hn_cap; }
     N.env = sc.env.as<float>(); N.lpsd = sc.lpsd.as<float>();
     if(h.nfft_s == 2048 && h.nfft == 1024 && noise_spec_variant() == 1) {
       // register-resident transforms, one warp per frame pair

@@ -1100,7 +1100,6 @@ struct NoiseSpecParams {
   float win_power;                    // float-accumulated sum of squares    dsputils.c:254-258
   float std_norm;                     // 0.5 * sum(hanning(1024))            dsputils.c:100-105
   const float2* tw_s; const float2* tw_p;
-  const float* hann; const int* hn_off; int hn_cap;   // Hann table (AnaPlan::hann), optional: warp kernel only
   float* env;                         // [B][nfrm][nspec] log-power envelope (x 2)
   float* lpsd;                        // [B][nfrm][nspec] log PSD of the residual
 };
@@ -1361,17 +1360,11 @@ __global__ void __launch_bounds__(NSW_THREADS, 2) noise_spec_warp_kernel(NoiseSp
           //  spectrum of the longest windows -- invisible at the peaks, 4e-3 nepers in the valleys between harmonics, and the
           //  smoother's process variance reads exactly those: 0.07 dB between the two noise-spectra kernels on a 7.5 s
           //  utterance at 60 Hz, for 0.15 ms)
-          //  Round 2, last: the taps come from the plan's table (AnaPlan::hann: the oracle's own float values, two
-          //  independent loads per tap instead of a 30-instruction cosine: the line was 13 % of the kernel's instructions).
-          if(P.hann != nullptr && ws <= P.hn_cap) {
-            const float* hw = P.hann + P.hn_off[ws];
-#pragma unroll 4
-            for(int j = lane; j < ws; j += 32)
-              buf[(j - ws / 2) & (2 * NF - 1)] = xs[first + j] * hw[min(j, ws - j)];
-          } else {
-            for(int j = lane; j < ws; j += 32)
-              buf[(j - ws / 2) & (2 * NF - 1)] = xs[first + j] * (0.5f - 0.5f * cospif((float)j * rws));
-          }
+          // (Tried and dropped: the taps from a per-plan table holding the oracle's own float values, 4.2 MB in L2 -- 5.11 ->
+          //  5.06 ms only, although this line is 13 % of the kernel's instructions: the cosine hides under the tap's global
+          //  read; and the exact window moved a -93 dB notch of the 7.5 s test utterance by 0.05 dB)
+          for(int j = lane; j < ws; j += 32)
+            buf[(j - ws / 2) & (2 * NF - 1)] = xs[first + j] * (0.5f - 0.5f * cospif((float)j * rws));
         } else {
           for(int j = lane; j < ws; j += 32) {
             const int idx = first + j;
