@@ -150,7 +150,7 @@ static inline void lc_mark(LaunchCounter* lc, cudaStream_t st, const char* name)
 static inline int run_harmonics(const SynthPlanDev& pd, const llsm_b200_conf& conf,
   const llsm_b200_frames& fr, const llsm_b200_soptions* opt, const int* ny_utt_dev,
   float* y_sin, int ny_valid, int nsamp, int stride, cudaStream_t st, LaunchCounter* lc,
-  int frame_lo = 0, int frame_hi = 0, const float* sub_from = nullptr, int sub_stride = 0) {
+  int frame_lo = 0, int frame_hi = 0, const float* sub_from = nullptr, int sub_stride = 0, bool residual_tc = false) {
   BankParams P;
   memset(&P, 0, sizeof(P));
   P.nfrm = conf.nfrm; P.maxnhar = conf.maxnhar;
@@ -162,7 +162,7 @@ static inline int run_harmonics(const SynthPlanDev& pd, const llsm_b200_conf& co
   P.has_options = opt != nullptr;
   if(opt) { P.use_iczt = opt->use_iczt; P.iczt_a = opt->iczt_param_a; P.iczt_b = opt->iczt_param_b; }
   P.y_sin = y_sin; P.frame_lo = frame_lo; P.frame_hi = frame_hi;
-  P.sub_from = sub_from; P.sub_stride = sub_stride;
+  P.sub_from = sub_from; P.sub_stride = sub_stride; P.residual_tc = residual_tc ? 1 : 0;
   if(launch_hm_bank(P, conf.nutt, conf.nfrm, st) != 0) return LLSM_B200_ERANGE;
   if(lc) lc->n += 1;
   return 0;

@@ -288,13 +288,17 @@ static inline int run_analyze_l0(const SynthPlanDev& sp, AnaPlanDev& ap, AnaScra
   {
     llsm_b200_frames fin; memset(&fin, 0, sizeof(fin));
     fin.nfrm_utt = nfrm_utt; fin.f0 = fr.f0; fin.nhar = fr.nhar; fin.ampl = fr.ampl; fin.phse = fr.phse;
-    // the subtraction rides in the bank's write when the direct-summation kernel runs (options == NULL keeps it there
-    // unless LLSM_RESIDUAL_TC is set): one pass over the waveform and one launch less
-    const bool fused = ! (bank_tc_enabled() && residual_tc_enabled() && conf.maxnhar >= 24);
-    int rc = fused ? run_harmonics(sp, conf, fin, nullptr, nullptr, x_res, nx, nx, rstride, st, lc, 0, 0, x, xstride)
-                   : run_harmonics(sp, conf, fin, nullptr, nullptr, sc.x_sin.as<float>(), nx, nx, nx, st, lc);
+    // Which bank: the tensor-core one for the CZT estimator (into x_sin, then one subtraction pass), the direct FP32
+    // summation for peak picking, with the subtraction riding in its write-once output (kernels_synth.cuh: launch_hm_bank
+    // has the measurements); LLSM_RESIDUAL_TC = 0 / 1 forces either. (The subtraction inside the tensor-core bank's tile
+    // emit measured 3.52 ms against 1.94 ms for bank + subtraction pass: the four read-back warps are that kernel's
+    // critical path and would wait on the global read of x.)
+    const int rtc = residual_tc_enabled();
+    const bool tc = (rtc >= 0 ? rtc != 0 : opt.hm_method == 1) && bank_tc_enabled() && conf.maxnhar >= 24;
+    int rc = tc ? run_harmonics(sp, conf, fin, nullptr, nullptr, sc.x_sin.as<float>(), nx, nx, nx, st, lc, 0, 0, nullptr, 0, true)
+                : run_harmonics(sp, conf, fin, nullptr, nullptr, x_res, nx, nx, rstride, st, lc, 0, 0, x, xstride);
     if(rc != 0) return rc;
-    if(! fused) {
+    if(tc) {
       LLSM_LAUNCH(residual_kernel, dim3((nx + 255) / 256, B), dim3(256), 0, st,
         x, (const float*)sc.x_sin.as<float>(), x_res, nx, xstride, nx, rstride);
       if(lc) lc->n ++;

@@ -39,6 +39,7 @@ struct BankParams {
   int frame_lo, frame_hi;   // frames [lo, hi) contribute (frame-range sharding); hi <= 0 means all
   int npass;                // frame slots per CTA = warps * npass
   float hop;                // thop * fs (float product): hm_base[f] = round(f * hop)
+  int residual_tc;          // options == NULL only: the tensor-core bank may serve this call (see launch_hm_bank)
   const float* sub_from; int sub_stride;   // optional [B][sub_stride]: write sub_from - y instead of y (analysis residual, layer0.c:500-501)
   float* y_sin;             // [B][stride]
   double iczt_nh;           // tensor-core bank: exp(log(n_hm) a + b), the harmonic count above which the ICZT branch is taken
@@ -237,9 +238,11 @@ static inline int bank_variant() {
   return v;
 }
 
+// LLSM_RESIDUAL_TC: 1 = the analysis residual always on the tensor-core bank, 0 = never, unset (-1) = the caller decides
+// (driver_analysis.h: yes for the CZT estimator, no for peak picking)
 static inline int residual_tc_enabled() {
-  static int v = -1;
-  if(v < 0) { const char* e = getenv("LLSM_RESIDUAL_TC"); v = e ? atoi(e) : 0; }
+  static int v = -2;
+  if(v == -2) { const char* e = getenv("LLSM_RESIDUAL_TC"); v = e ? atoi(e) : -1; }
   return v;
 }
 
@@ -247,12 +250,13 @@ static inline int residual_tc_enabled() {
 static inline int launch_hm_bank(BankParams P, int nutt, int nfrm_max, cudaStream_t st) {
 #ifndef LLSM_EMU
   // many harmonics: operand generation + tcgen05 GEMM (kernels_bank_tc.cuh, ~1e-7 of the frame amplitude, i.e. ~5e-9
-  // absolute on speech-level frames). The analysis residual (options == NULL) stays on the direct summation by
-  // default: x - x_sin is a small difference of large numbers, and although 5e-9 passes the residual's own 1e-6 RMS bar
-  // it is 1e-5 of the residual, which the sub-band envelope phases of the peak-picking method feel (measured on B200:
-  // 1.8e-4 rad on envelope harmonics of 5e-5 amplitude). LLSM_RESIDUAL_TC=1 trades that for 1.3 ms per 409 600 frames.
+  // absolute on speech-level frames). The analysis residual (options == NULL, x - x_sin: a small difference of large
+  // numbers) takes it only when the caller allows (P.residual_tc): 5e-9 passes the residual's 1e-6 RMS bar and every bar
+  // of the CZT estimator's outputs, but it is 1e-5 of the residual, which the sub-band envelope phases of the
+  // peak-picking method feel (measured on B200: 1.8e-4 rad on envelope harmonics of 5e-5 amplitude) -- that method keeps
+  // the direct summation, at 1.4 ms more per 409 600 frames.
   // Few harmonics or long windows: direct FP32 summation below
-  if(bank_tc_enabled() && (P.has_options || residual_tc_enabled()) && P.maxnhar >= 24 &&
+  if(bank_tc_enabled() && (P.has_options || P.residual_tc) && P.maxnhar >= 24 &&
      launch_hm_bank_tc(P, nutt, nfrm_max, st) == 0) return 0;
 #endif
   const int NTHR = 256, NW = NTHR / 32;
