@@ -74,7 +74,11 @@ __global__ void __launch_bounds__(32 * RF_WARPS) refine_f0_kernel(RefineParams P
   for(int j = 0; j < 3; j ++) fc[j] = fres * (float)(j + 1);          // f0[i] / fs * j (dsputils.c:79)
   float yr[3] = {0.f, 0.f, 0.f}, yi[3] = {0.f, 0.f, 0.f}, dr[3] = {0.f, 0.f, 0.f}, di[3] = {0.f, 0.f, 0.f};
   {
-    const int m0 = lane - nh / 2;
+    // The taps m and -m share everything but the sample: w(-m) = w(m), w'(-m) = -w'(m), e^{-i th (-m)} = conj. With
+    // e = x(m) + x(-m), o = x(m) - x(-m):  y += e w cos - i o w sin,  yd += o w' cos - i e w' sin  -- one rotation set and
+    // one set of double -> float conversions per PAIR of taps (the kernel is bound by exactly those: XU pipe 64 %,
+    // FP64 39 % with a tap per iteration). Lane l takes m = l + 1, l + 33, ...; the centre tap (w = 1, w' = 0) is lane 0's.
+    const int m0 = lane + 1;
     double sw, cw, sws, cws, sp[3], cp[3], sps[3], cps[3];
     sincospi(2.0 * (double)m0 / L, &sw, &cw);
     sincospi(2.0 * 32.0 / L, &sws, &cws);
@@ -86,19 +90,27 @@ __global__ void __launch_bounds__(32 * RF_WARPS) refine_f0_kernel(RefineParams P
       sincospi(2.0 * us, &sps[j], &cps[j]);
     }
     const float wdk = (float)(-0.5 * (2.0 * LLSM_PI / L));
-    int idx = center + lane - nh / 2;
-    float xn = (lane < nh && idx >= 0 && idx < P.nx) ? x[idx] : 0.f;
-    for(int t = lane; t < nh; t += 32) {
-      const float xv = xn;
-      idx += 32;
-      xn = (t + 32 < nh && idx >= 0 && idx < P.nx) ? x[idx] : 0.f;    // next tap's sample, one step ahead of its use
+    if(lane == 0 && center >= 0 && center < P.nx) {
+      const float x0 = x[center];
+#pragma unroll
+      for(int j = 0; j < 3; j ++) yr[j] = x0;
+    }
+    int ip = center + m0, im = center - m0;
+    float xpn = (m0 <= half && ip >= 0 && ip < P.nx) ? x[ip] : 0.f;
+    float xmn = (m0 <= half && im >= 0 && im < P.nx) ? x[im] : 0.f;
+    for(int m = m0; m <= half; m += 32) {
+      const float xp = xpn, xm = xmn;
+      ip += 32; im -= 32;
+      xpn = (m + 32 <= half && ip >= 0 && ip < P.nx) ? x[ip] : 0.f;   // the next pair's samples, one step ahead of their use
+      xmn = (m + 32 <= half && im >= 0 && im < P.nx) ? x[im] : 0.f;
       const float w = 0.5f + 0.5f * (float)cw, wd = wdk * (float)sw;
-      const float xw = xv * w, xd = xv * wd;
+      const float e = xp + xm, o = xp - xm;
+      const float ew = e * w, ow = o * w, ed = e * wd, od = o * wd;
 #pragma unroll
       for(int j = 0; j < 3; j ++) {
         const float c = (float)cp[j], s = (float)sp[j];
-        yr[j] = fmaf(xw, c, yr[j]); yi[j] = fmaf(-xw, s, yi[j]);
-        dr[j] = fmaf(xd, c, dr[j]); di[j] = fmaf(-xd, s, di[j]);
+        yr[j] = fmaf(ew, c, yr[j]); yi[j] = fmaf(-ow, s, yi[j]);
+        dr[j] = fmaf(od, c, dr[j]); di[j] = fmaf(-ed, s, di[j]);
         const double t2 = cp[j] * cps[j] - sp[j] * sps[j]; sp[j] = sp[j] * cps[j] + cp[j] * sps[j]; cp[j] = t2;
       }
       const double t1 = cw * cws - sw * sws; sw = sw * cws + cw * sws; cw = t1;
