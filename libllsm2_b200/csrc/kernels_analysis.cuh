@@ -1538,6 +1538,8 @@ struct KalmanParams {
 //  results of eight frames parked in shared memory, the process variance recomputed instead of stored: 7 array passes
 //  instead of 13, but 3.01 ms against 2.06 + 0.79 ms for the two kernels at C2: the double-precision exp / log10 of the
 //  output stage do not overlap with the latency-bound time recursion inside one CTA.)
+// (Also dropped: the process variance recomputed from the envelope in the backward pass instead of stored and read back --
+//  one array pass less, bit-identical, but 2.12 against 2.06 ms: the two float divisions per frame cost more than the pass.)
 __global__ void __launch_bounds__(128) noise_kalman_kernel(KalmanParams P) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
   if(j >= P.nspec) return;
