@@ -177,6 +177,12 @@ int llsm_b200_anasynth_host(llsm_b200_ctx* ctx, const llsm_b200_conf* conf, cons
   const llsm_b200_soptions* sopt, const float* x, int nx, int xstride, const float* f0, float* f0_refined,
   int phase_ops, const llsm_b200_output* out);
 
+/* Slice sizes the call above uses for a batch of nutt utterances x nfrm frames moving bytes_per_utt host bytes (in + out)
+   per utterance: small slices at both ends (the first upload and the last download overlap with nothing), few large
+   ones between (every kernel of a slice ends in a tail). Writes up to cap_sizes entries (each >= 1, sum = nutt) and
+   returns their number; host arithmetic only. LLSM_B200_HOST_SLICES / LLSM_B200_HOST_SLICE_LIST override. */
+int llsm_b200_host_slice_plan(int nutt, int nfrm, size_t bytes_per_utt, int* out_sizes, int cap_sizes);
+
 
 /* ---- per-frame routines of the reference's dsputils.h that its tests call directly (test/test-dsputils.c:80,
         test/test-harmonic.c:40-43), as batch entries ----

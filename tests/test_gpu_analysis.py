@@ -147,6 +147,24 @@ def test_anasynth_host_chain(ctx, phase_ops):
     assert np.array_equal(y_only["y"], out["y"])
 
 
+@pytest.mark.parametrize("slice_list", ["1,3,1", "2,1", "7"])
+def test_anasynth_host_is_slicing_invariant(ctx, slice_list, monkeypatch):
+    """The chained host entry cuts the batch into unequal slices (small at both ends: llsm_b200_host_slice_plan); the
+    waveforms must not depend on the cut (utterances are independent; the device noise generator is indexed by the
+    absolute utterance number)."""
+    import libllsm2_b200 as L
+    fr, conf = S.synth_frames(7, 40, seed=34, nhar=60, maxnhar=64)
+    x, _, _ = S.ref_synthesize(fr, conf, seed=7)
+    x = np.ascontiguousarray(x)
+    monkeypatch.setenv("LLSM_B200_HOST_SLICES", "1")
+    a = L.anasynth_host(ctx, conf, x, fr["f0"], seed=5)["y"].copy()
+    monkeypatch.delenv("LLSM_B200_HOST_SLICES")
+    monkeypatch.setenv("LLSM_B200_HOST_SLICE_LIST", slice_list)
+    b = L.anasynth_host(ctx, conf, x, fr["f0"], seed=5)["y"]
+    assert S.rms(a) > 1e-3
+    assert np.array_equal(a, b)
+
+
 def test_analysis_long_utterance_cluster_of_eight(ctx):
     """7.5 s utterance: the sub-band filter's sequence (330 k samples) is spread over a cluster of eight CTAs
     (kernels_iir_smem.cuh: carry between the CTAs through distributed shared memory); odd frame count, so the noise

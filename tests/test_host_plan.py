@@ -35,3 +35,47 @@ def test_output_length_matches_reference():
     for nfrm in (1, 7, 400, 1154):
         for thop, fs in ((0.005, 44100.0), (128 / 44100.0, 44100.0), (0.005, 48000.0), (100.5 / 44100.0, 44100.0)):
             assert output_length(nfrm, thop, fs) == ref.ref_output_length(nfrm, C.c_float(thop), C.c_float(fs))
+
+
+def _slice_plan(B, F, bytes_per_utt, cap=None, **env):
+    """llsm_b200_host_slice_plan through the product library (host arithmetic only: loads without a GPU)."""
+    import os
+    from libllsm2_b200._lib import lib
+    L = lib()
+    L.llsm_b200_host_slice_plan.restype = C.c_int
+    L.llsm_b200_host_slice_plan.argtypes = [C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_int]
+    cap = cap or B
+    out = (C.c_int * cap)()
+    old = {k: os.environ.get(k) for k in ("LLSM_B200_HOST_SLICES", "LLSM_B200_HOST_SLICE_LIST")}
+    try:
+        for k in old:
+            os.environ.pop(k, None)
+        os.environ.update(env)
+        n = L.llsm_b200_host_slice_plan(B, F, bytes_per_utt, out, cap)
+    finally:
+        for k, v in old.items():
+            os.environ.pop(k, None)
+            if v is not None:
+                os.environ[k] = v
+    return list(out[:n])
+
+
+def test_host_slice_plan_c2_is_tapered():
+    """The anasynth host pipeline's slices at BASELINE configs[1]: small ends, two large slices (the measured optimum)."""
+    per_utt = (88200 + 88420) * 4
+    assert _slice_plan(1024, 400, per_utt) == [16, 144, 352, 352, 144, 16]
+    big = _slice_plan(8192, 400, per_utt)                     # configs[4]'s per-GPU shard: large slices capped at 352
+    assert sum(big) == 8192 and big[0] == 32 and big[-1] == 32 and max(big) <= 352 and min(big) >= 1
+
+
+def test_host_slice_plan_small_batches_and_overrides():
+    per_utt = (88200 + 88420) * 4
+    for B in (1, 2, 3, 5, 17, 45, 46, 64, 100, 1000, 1025):
+        for F in (1, 40, 400, 1154, 200000):
+            s = _slice_plan(B, F, per_utt)
+            assert sum(s) == B and min(s) >= 1, (B, F, s)
+    assert _slice_plan(3, 70, per_utt) == [3]                                        # below 8 MB per slice: one slice
+    assert _slice_plan(10, 400, per_utt, LLSM_B200_HOST_SLICES="4") == [3, 3, 3, 1]    # forced even split
+    assert _slice_plan(10, 400, per_utt, LLSM_B200_HOST_SLICE_LIST="1,4") == [1, 4, 4, 1]   # the last entry repeats
+    assert _slice_plan(10, 400, per_utt, LLSM_B200_HOST_SLICE_LIST="64") == [10]
+    assert _slice_plan(1024, 400, per_utt, cap=3) == [16, 144, 864]                   # no room: the tail is merged
